@@ -1,0 +1,216 @@
+/*
+ * uavdet_b200 — C-ABI of the B200-native detector hot path (libuavdet_b200.so).
+ *
+ * This is the drop-in boundary.  The reference
+ * (alfialdo/multimodal-uav-det) is pure Python on ATen/cuDNN/torchvision; each entry
+ * point below cites the reference call site it replaces (paths relative to the
+ * reference root).  The reference-side binding is a ctypes stub — see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; all pointers are DEVICE pointers unless
+ *     the name ends in `_host`;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs
+ *     no allocation and no implicit synchronisation unless stated;
+ *   - return 0 on success, non-zero error code otherwise; `uavdet_last_error()` gives
+ *     the thread-local message;
+ *   - activations are NHWC bf16 with an explicit pixel stride (`ld`, in elements) so a
+ *     tensor may be a channel slice of a wider buffer (route concat, DyYOLO.py:139-141);
+ *   - fp32 "stat" / weight-gradient buffers are accumulated with atomics and must be
+ *     zeroed by the caller.
+ */
+#ifndef UAVDET_B200_H_
+#define UAVDET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UAVDET_OK 0
+#define UAVDET_ERR_ARG 1
+#define UAVDET_ERR_CUDA 2
+#define UAVDET_ERR_UNSUPPORTED 3
+#define UAVDET_ERR_DEVICE 4 /* kernel reported a pipeline timeout (debug watchdog) */
+
+/* activation codes (BaselineModel.py:16 LeakyReLU(0.1); _base.py:20 SiLU / ReLU) */
+#define UAVDET_ACT_NONE 0
+#define UAVDET_ACT_LEAKY 1
+#define UAVDET_ACT_SILU 2
+#define UAVDET_ACT_RELU 3
+#define UAVDET_ACT_GELU 4
+
+/* ---- library ---------------------------------------------------------------------- */
+const char* uavdet_last_error(void);
+int uavdet_version(void);
+/* number of kernels launched by this library in this process (bench.py `gpu_launches`). */
+uint64_t uavdet_launch_count(void);
+/* reads and clears the device-side watchdog word (non-zero = a pipeline wait timed out).
+ * Synchronises `stream`. */
+int uavdet_check_device(void* stream, int* flag_host);
+
+/* NHWC bf16 activation view. */
+typedef struct {
+  void* ptr;   /* bf16 */
+  int n, h, w; /* batch, height, width */
+  int c;       /* channels visible through this view */
+  int ld;      /* pixel stride in elements (>= c) */
+} uavdet_act;
+
+/* ---- K9: NMS  (replaces torchvision.ops.nms at model/_base.py:203) ----------------- */
+/* Greedy IoU suppression, bit-exact with torchvision's CPU kernel: stable descending
+ * sort (ties: lower index first, NaN scores first), suppress iff
+ * inter/(a_i+a_j-inter) > thr with all arithmetic in unfused fp32.
+ *   boxes   (batch, n, 4) fp32 xyxy      scores (batch, n) fp32
+ *   keep    (batch, n) int64 — kept ORIGINAL indices in score order, first keep_count[b]
+ *   keep_count (batch) int32
+ *   score_floor: candidates with score <= score_floor are dropped before NMS (extension,
+ *   SURVEY §8f-3; pass -INFINITY for the reference semantics: no threshold).            */
+size_t uavdet_nms_workspace_bytes(int batch, int n);
+int uavdet_nms(const float* boxes, const float* scores, int batch, int n, double iou_thr,
+               float score_floor, int64_t* keep, int32_t* keep_count, void* workspace,
+               size_t workspace_bytes, void* stream);
+
+/* ---- K8: box decode ---------------------------------------------------------------- */
+/* YOLOHead.__pred_bbox_decoding + __prepare_nms_preds (model/_base.py:214-248) for one
+ * head scale: logits (batch, A, S_h, S_w, 4) / (batch, A, S_h, S_w, 1) fp32 ->
+ * boxes xyxy written at candidate offset `cand_off` of a (batch, n_total, 4) buffer and
+ * scores (raw logits, _base.py:203) at (batch, n_total).  anchors_scaled_host: A*(w,h)
+ * already divided by the head scale (_base.py:170).  ciou != 0 adds the grid offsets and
+ * anchor scaling (_base.py:224-237); ciou == 0 reproduces the 'mse' branch.             */
+int uavdet_decode_yolo(const float* bbox_logits, const float* obj_logits, int batch, int A,
+                       int S_h, int S_w, const float* anchors_scaled_host, int ciou,
+                       float* boxes, float* scores, int n_total, int cand_off, void* stream);
+/* RTMHead.__calculate_bbox_size (model/RTMUAVDet.py:274-291): input is already
+ * sigmoid-activated (B,A,H,W,4); writes decoded cxcywh in place layout (B,A,H,W,4).     */
+int uavdet_decode_rtm(const float* bbox_sig, int batch, int A, int S_h, int S_w,
+                      const float* anchors_host, float* bbox_out, void* stream);
+/* cxcywh (.., 4) -> xyxy, torchvision box_convert arithmetic (_base.py:246). */
+int uavdet_cxcywh_to_xyxy(const float* in, float* out, int64_t count, void* stream);
+
+/* ---- K1/K2: implicit-GEMM convolution on tcgen05 ------------------------------------ */
+/* Epilogue of the implicit GEMM. */
+#define UAVDET_EPI_AFFINE 0 /* y = act(acc*scale[c]+shift[c]) (+res) -> bf16 NHWC        */
+#define UAVDET_EPI_STATS 1  /* y = acc -> bf16 NHWC; sum[c]+=acc, sumsq[c]+=acc^2 (fp32) */
+#define UAVDET_EPI_HEAD 2   /* fp32 (B,A,H,W,1)+(B,A,H,W,4) logits, _base.py:88-120      */
+
+typedef struct {
+  int epi;            /* UAVDET_EPI_*                                                    */
+  int act;            /* UAVDET_ACT_* (AFFINE only)                                      */
+  const float* scale; /* [cout] or NULL (=1)                                             */
+  const float* shift; /* [cout] or NULL (=0)  — conv bias or folded BN shift             */
+  const void* res;    /* bf16 residual added after activation, NHWC, or NULL             */
+  int res_ld;
+  float* sum;         /* STATS: [cout] fp32, caller-zeroed                               */
+  float* sumsq;
+  float* head_obj;    /* HEAD: (B,A,H,W,1) fp32                                          */
+  float* head_bbox;   /* HEAD: (B,A,H,W,4) fp32                                          */
+  int head_anchors;   /* A; cout must be 5*A packed [A obj | 4A bbox]                    */
+} uavdet_epilogue;
+
+/* Forward convolution  y = conv(x, w), square kernel k in {1,3,5}, stride 1|2, zero pad.
+ * Replaces nn.Conv2d / F.conv2d at BaselineModel.py:13, _base.py:18,72-74,85,107,
+ * DySOEM_SimFPN.py:58,103-111, RTMUAVDet.py:19.
+ *   x: NHWC bf16 (cin multiple of 32); y: NHWC bf16 view (n, ho, wo, cout)
+ *   w_packed: bf16 [w_batch][cout][k*k*cin] (tap-major, cin fastest) from uavdet_pack_weight;
+ *   w_batch = 1 (static) or n (per-sample dynamic kernels, _base.py:65-74).
+ *   s2d != 0: x is read through a fused space-to-depth(2) gather (DySOEM_SimFPN.py:71-75):
+ *   logical input is (n, h/2, w/2, 4*c) and cin = 4*x.c.                                 */
+int uavdet_conv_fwd(const uavdet_act* x, const void* w_packed, int w_batch, int cout, int k,
+                    int stride, int pad, int s2d, const uavdet_act* y,
+                    const uavdet_epilogue* epi, void* stream);
+
+/* Data gradient dx = conv_transpose(dy, w).  w_packed_t: bf16 [w_batch][cin][k*k*cout]
+ * from uavdet_pack_weight(transposed=1).  epi: AFFINE with optional `res` (skip-path
+ * gradient accumulated in the epilogue).  (autograd of the sites above)                  */
+int uavdet_conv_dgrad(const uavdet_act* dy, const void* w_packed_t, int w_batch, int cin, int k,
+                      int stride, int pad, const uavdet_act* dx, const uavdet_epilogue* epi,
+                      void* stream);
+
+/* Weight gradient dw[co][tap][ci] += sum_pixels dy[p][co] * x[p+tap][ci]  (fp32, atomics,
+ * caller-zeroed; layout = packed weight layout).  per_sample != 0 keeps one dw per image
+ * ([n][cout][k*k*cin]) for the dynamic-kernel contraction.                               */
+int uavdet_conv_wgrad(const uavdet_act* x, const uavdet_act* dy, int k, int stride, int pad,
+                      int s2d, float* dw_packed, int per_sample, void* stream);
+
+/* OIHW fp32 -> packed bf16.  transposed=0: [O][kh][kw][I]; transposed=1: [I][kh][kw][O].   */
+int uavdet_pack_weight(const float* w_oihw, int O, int I, int k, int transposed, void* out_bf16,
+                       void* stream);
+/* packed fp32 grad [O][kh][kw][I] -> OIHW fp32 (accumulate != 0: +=).                      */
+int uavdet_unpack_wgrad(const float* dw_packed, int O, int I, int k, float* grad_oihw,
+                        int accumulate, void* stream);
+
+/* Stem: direct convolution for cin in {1,3} reading the NCHW fp32 network input
+ * (BaselineModel.py:89-97 first layer, DySOEM_SimFPN.py:30, RTMUAVDet.py:31).
+ * w: OIHW fp32.  Writes NHWC bf16 raw conv output (+ optional batch stats) or, with
+ * scale/shift, the activated output.                                                     */
+int uavdet_stem_fwd(const float* x_nchw, int n, int cin, int h, int w, const float* w_oihw,
+                    int cout, int k, int stride, int pad, const uavdet_act* y,
+                    const uavdet_epilogue* epi, void* stream);
+int uavdet_stem_wgrad(const float* x_nchw, int n, int cin, int h, int w, const uavdet_act* dy,
+                      int k, int stride, int pad, float* grad_oihw, void* stream);
+
+/* ---- K5: batch-norm + activation (two-phase, train mode) ---------------------------- */
+/* From batch sums: mean/invstd, running-stat update (momentum, unbiased var —
+ * nn.BatchNorm2d at BaselineModel.py:14), and folded scale=gamma*invstd,
+ * shift=beta-mean*scale.  count = n*h*w.                                                */
+int uavdet_bn_finalize(const float* sum, const float* sumsq, int c, double count, float eps,
+                       float momentum, const float* gamma, const float* beta,
+                       float* running_mean, float* running_var, float* mean, float* invstd,
+                       float* scale, float* shift, void* stream);
+/* y = act(raw*scale+shift) (+res).  raw,y,res: NHWC bf16 views of equal n,h,w,c.          */
+int uavdet_bn_act_fwd(const uavdet_act* raw, const float* scale, const float* shift, int act,
+                      const uavdet_act* res, const uavdet_act* y, void* stream);
+/* backward phase 1: dz = dy*act'(raw*scale+shift); sum_dz[c] += dz; sum_dzx[c] += dz*xhat. */
+int uavdet_bn_act_bwd_reduce(const uavdet_act* dy, const uavdet_act* raw, const float* scale,
+                             const float* shift, const float* mean, const float* invstd,
+                             int act, float* sum_dz, float* sum_dzx, void* stream);
+/* backward phase 2: d_raw = gamma*invstd*(dz - sum_dz/M - xhat*sum_dzx/M).               */
+int uavdet_bn_act_bwd_apply(const uavdet_act* dy, const uavdet_act* raw, const float* scale,
+                            const float* shift, const float* mean, const float* invstd,
+                            const float* gamma, int act, const float* sum_dz,
+                            const float* sum_dzx, const uavdet_act* d_raw, void* stream);
+/* eval-mode / bias-only activation backward: dx = dy*act'(raw*scale+shift)*scale.         */
+int uavdet_act_bwd(const uavdet_act* dy, const uavdet_act* raw, const float* scale,
+                   const float* shift, int act, const uavdet_act* dx, void* stream);
+
+/* ---- data movement ------------------------------------------------------------------ */
+/* nearest x2 upsample of x into y (y.h = 2*x.h) — nn.Upsample(2) + cat (BaselineModel.py:86,
+ * 120-122): y is typically a channel slice of the concat buffer.                         */
+int uavdet_upsample2x_fwd(const uavdet_act* x, const uavdet_act* y, void* stream);
+/* dx = sum over the 2x2 replicas of dy (accumulate: dx += ...).                           */
+int uavdet_upsample2x_bwd(const uavdet_act* dy, const uavdet_act* dx, int accumulate, void* stream);
+/* y = a (+ b) elementwise over views (copy into / accumulate from channel slices).        */
+int uavdet_add(const uavdet_act* a, const uavdet_act* b, const uavdet_act* y, void* stream);
+/* NHWC bf16 <-> NCHW fp32 (API edge only: parity tests and user-facing feature maps).     */
+int uavdet_nhwc_to_nchw_f32(const uavdet_act* x, float* y_nchw, void* stream);
+int uavdet_nchw_f32_to_nhwc(const float* x_nchw, const uavdet_act* y, void* stream);
+
+/* ---- K4: dynamic-kernel attention + aggregation -------------------------------------- */
+/* Global average pool over h*w -> (n, c) fp32 (nn.AdaptiveAvgPool2d(1), _base.py:42).     */
+int uavdet_gap(const uavdet_act* x, int s2d, float* out, void* stream);
+int uavdet_gap_nchw(const float* x_nchw, int n, int c, int hw, float* out, void* stream);
+/* Two-layer MLP + softmax(./T): pooled (n,c) -> attn (n,K)  (_base.py:41-46,60-62;
+ * DySOEM_SimFPN.py:46-52,78-79).  w1 [hid][c], b1 [hid]|NULL, w2 [K][hid], b2 [K].
+ * Saves hidden (n,hid) post-ReLU for backward when non-NULL.                             */
+int uavdet_attn_mlp_softmax(const float* pooled, int n, int c, const float* w1, const float* b1,
+                            int hid, const float* w2, const float* b2, int K, float temperature,
+                            float* attn, float* hidden, void* stream);
+/* Per-sample kernel aggregation  W_b = sum_k attn[b,k] * bank[k]  (_base.py:65-66) fused
+ * with the bf16 pack: bank fp32 [K][O][I][k][k] -> out bf16 [n][O][k*k*I] (or transposed).
+ * bias_bank [K][O] -> bias_out [n][O] when non-NULL (DySOEM_SimFPN.py:83-91 by linearity). */
+int uavdet_dyn_aggregate(const float* attn, int n, int K, const float* bank, int O, int I, int k,
+                         int transposed, void* out_bf16, const float* bias_bank, float* bias_out,
+                         void* stream);
+
+/* ---- optimiser ----------------------------------------------------------------------- */
+/* torch.optim.SGD(momentum) step over a flat fp32 parameter arena (_base.py:292-293):
+ * buf = momentum*buf + grad*grad_scale; p -= lr*buf   (first_step: buf = grad).            */
+int uavdet_sgd_momentum(float* param, const float* grad, float* momentum_buf, int64_t count,
+                        float lr, float momentum, float grad_scale, int first_step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UAVDET_B200_H_ */

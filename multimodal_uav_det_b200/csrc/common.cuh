@@ -1,0 +1,98 @@
+// Shared host/device helpers for libuavdet_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "../../include/uavdet_b200.h"
+
+namespace uavdet {
+
+// ---- error plumbing -------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+// device-side watchdog word (igemm/wgrad pipeline waits) — defined in api.cu
+unsigned int* watchdog_word();
+
+#define UAVDET_CHECK_ARG(cond, ...)            \
+  do {                                         \
+    if (!(cond)) {                             \
+      uavdet::set_error(__VA_ARGS__);          \
+      return UAVDET_ERR_ARG;                   \
+    }                                          \
+  } while (0)
+
+#define UAVDET_CUDA(expr)                                                               \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      uavdet::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                        __LINE__);                                                      \
+      return UAVDET_ERR_CUDA;                                                           \
+    }                                                                                   \
+  } while (0)
+
+#define UAVDET_LAUNCH_CHECK()                                                            \
+  do {                                                                                   \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess) {                                                             \
+      uavdet::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),      \
+                        __FILE__, __LINE__);                                             \
+      return UAVDET_ERR_CUDA;                                                            \
+    }                                                                                    \
+    uavdet::count_launch();                                                              \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- device helpers -------------------------------------------------------------------
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_fwd(float z) {
+  if (ACT == UAVDET_ACT_LEAKY) return z > 0.f ? z : 0.1f * z;
+  if (ACT == UAVDET_ACT_SILU) return z / (1.f + __expf(-z));
+  if (ACT == UAVDET_ACT_RELU) return z > 0.f ? z : 0.f;
+  if (ACT == UAVDET_ACT_GELU) return 0.5f * z * (1.f + erff(z * 0.70710678118654752f));
+  return z;
+}
+__device__ __forceinline__ float act_fwd_rt(int act, float z) {
+  switch (act) {
+    case UAVDET_ACT_LEAKY: return act_fwd<UAVDET_ACT_LEAKY>(z);
+    case UAVDET_ACT_SILU: return act_fwd<UAVDET_ACT_SILU>(z);
+    case UAVDET_ACT_RELU: return act_fwd<UAVDET_ACT_RELU>(z);
+    case UAVDET_ACT_GELU: return act_fwd<UAVDET_ACT_GELU>(z);
+    default: return z;
+  }
+}
+// derivative of the activation w.r.t. its pre-activation z
+__device__ __forceinline__ float act_grad_rt(int act, float z) {
+  switch (act) {
+    case UAVDET_ACT_LEAKY: return z > 0.f ? 1.f : 0.1f;
+    case UAVDET_ACT_SILU: {
+      float s = 1.f / (1.f + __expf(-z));
+      return s * (1.f + z * (1.f - s));
+    }
+    case UAVDET_ACT_RELU: return z > 0.f ? 1.f : 0.f;
+    case UAVDET_ACT_GELU: {
+      float cdf = 0.5f * (1.f + erff(z * 0.70710678118654752f));
+      float pdf = 0.3989422804014327f * __expf(-0.5f * z * z);
+      return cdf + z * pdf;
+    }
+    default: return 1.f;
+  }
+}
+
+}  // namespace uavdet

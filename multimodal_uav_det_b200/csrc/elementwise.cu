@@ -1,0 +1,706 @@
+// K5 and friends — HBM-bound kernels: BN finalize / normalise+activation (fwd, bwd), nearest
+// upsample, adds, layout conversion, weight (un)packing, SGD.  All NHWC bf16, 128-bit accesses,
+// grid-stride loops sized to a multiple of the SM count.
+// Reference sites: BaselineModel.py:14-22 (BN+LeakyReLU), _base.py:19-20,50,75 (BN+SiLU/ReLU),
+// BaselineModel.py:43 (residual), BaselineModel.py:86,120-122 (Upsample+cat), _base.py:292 (SGD).
+#include "common.cuh"
+
+namespace uavdet {
+
+static inline int ew_grid(long long work_items, int threads) {
+  long long blocks = (work_items + threads - 1) / threads;
+  long long cap = (long long)kNumSMs * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+struct View {
+  __nv_bfloat16* p;
+  long long npix;  // n*h*w
+  int c, ld;
+};
+static inline View mkview(const uavdet_act* a) {
+  return View{(__nv_bfloat16*)a->ptr, (long long)a->n * a->h * a->w, a->c, a->ld};
+}
+static int check_view(const uavdet_act* a, const char* what) {
+  UAVDET_CHECK_ARG(a && a->ptr, "%s: null view", what);
+  UAVDET_CHECK_ARG(a->c % 8 == 0 && a->ld % 8 == 0 && ((uintptr_t)a->ptr & 15) == 0,
+                   "%s: view must be 8-channel / 16-byte aligned (c=%d ld=%d)", what, a->c, a->ld);
+  return UAVDET_OK;
+}
+static int same_shape(const uavdet_act* a, const uavdet_act* b, const char* what) {
+  UAVDET_CHECK_ARG(a->n == b->n && a->h == b->h && a->w == b->w && a->c == b->c,
+                   "%s: shape mismatch (%d,%d,%d,%d) vs (%d,%d,%d,%d)", what, a->n, a->h, a->w, a->c, b->n,
+                   b->h, b->w, b->c);
+  return UAVDET_OK;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+__device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// ---- BN finalize --------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const float* sum, const float* sumsq, int c, double count, float eps,
+                                   float momentum, const float* gamma, const float* beta,
+                                   float* running_mean, float* running_var, float* mean, float* invstd,
+                                   float* scale, float* shift) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  double m = (double)sum[i] / count;
+  double var = (double)sumsq[i] / count - m * m;
+  if (var < 0.0) var = 0.0;
+  float is = (float)(1.0 / sqrt(var + (double)eps));
+  float g = gamma ? gamma[i] : 1.f, b = beta ? beta[i] : 0.f;
+  if (mean) mean[i] = (float)m;
+  if (invstd) invstd[i] = is;
+  scale[i] = g * is;
+  shift[i] = b - (float)m * g * is;
+  if (running_mean) {
+    double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * (float)m;
+    running_var[i] = (1.f - momentum) * running_var[i] + momentum * (float)unbiased;
+  }
+}
+
+// ---- y = act(raw*scale+shift) (+res) -------------------------------------------------------
+__global__ void bn_act_fwd_kernel(View raw, const float* __restrict__ scale, const float* __restrict__ shift,
+                                  int act, const __nv_bfloat16* __restrict__ res, int res_ld, View y) {
+  const int c8 = raw.c >> 3;
+  const long long total = raw.npix * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long px = i / c8;
+    const int c = (int)(i - px * c8) << 3;
+    float v[8], s[8], t[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(raw.p + px * raw.ld + c)), v);
+    if (scale) load8f(scale + c, s);
+    if (shift) load8f(shift + c, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float z = v[j];
+      if (scale) z *= s[j];
+      if (shift) z += t[j];
+      v[j] = act_fwd_rt(act, z);
+    }
+    if (res) {
+      float r[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(res + px * res_ld + c)), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+    *reinterpret_cast<uint4*>(y.p + px * y.ld + c) = pack8(v);
+  }
+}
+
+// ---- BN backward, phase 1: per-channel sums of dz and dz*xhat ---------------------------------
+// grid = (pixel blocks, channel chunks of 256).  blockDim 256: Gb = min(c/8, 32) channel groups x
+// PL pixel lanes; coalesced 16 B per thread, Gb*16 B contiguous per pixel.
+__global__ void bn_bwd_reduce_kernel(View dy, View raw, const float* __restrict__ scale,
+                                     const float* __restrict__ shift, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, int act, float* __restrict__ sum_dz,
+                                     float* __restrict__ sum_dzx) {
+  __shared__ float red[256 * 16];
+  const int G = dy.c >> 3;
+  const int Gb = G < 32 ? G : 32;
+  const int PL = 256 / Gb;
+  const int g = threadIdx.x % Gb + blockIdx.y * Gb;
+  const int pl = threadIdx.x / Gb;
+  float a_dz[8], a_dzx[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a_dz[j] = 0.f; a_dzx[j] = 0.f; }
+  if (g < G && pl < PL) {
+    const int c = g << 3;
+    float s[8], t[8], m[8], is[8];
+    load8f(scale + c, s); load8f(shift + c, t); load8f(mean + c, m); load8f(invstd + c, is);
+    for (long long px = (long long)blockIdx.x * PL + pl; px < dy.npix; px += (long long)gridDim.x * PL) {
+      float d[8], r[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dy.p + px * dy.ld + c)), d);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(raw.p + px * raw.ld + c)), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float z = r[j] * s[j] + t[j];
+        float dz = d[j] * act_grad_rt(act, z);
+        a_dz[j] += dz;
+        a_dzx[j] += dz * ((r[j] - m[j]) * is[j]);
+      }
+    }
+  }
+  // block reduce over pixel lanes
+  float* mine = red + threadIdx.x * 16;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { mine[j] = a_dz[j]; mine[8 + j] = a_dzx[j]; }
+  __syncthreads();
+  // thread t < Gb*16 sums column (group t/16, slot t%16) over PL lanes
+  for (int t = threadIdx.x; t < Gb * 16; t += 256) {
+    const int gg = t >> 4, slot = t & 15;
+    float acc = 0.f;
+    for (int l = 0; l < PL; ++l) acc += red[(l * Gb + gg) * 16 + slot];
+    const int gch = (gg + blockIdx.y * Gb);
+    if (gch < G) {
+      const int c = (gch << 3) + (slot & 7);
+      atomicAdd((slot < 8 ? sum_dz : sum_dzx) + c, acc);
+    }
+  }
+}
+
+// ---- BN backward, phase 2 ----------------------------------------------------------------------
+__global__ void bn_bwd_apply_kernel(View dy, View raw, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ gamma, int act,
+                                    const float* __restrict__ sum_dz, const float* __restrict__ sum_dzx,
+                                    float inv_count, View dr) {
+  const int c8 = dy.c >> 3;
+  const long long total = dy.npix * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long px = i / c8;
+    const int c = (int)(i - px * c8) << 3;
+    float d[8], r[8], s[8], t[8], m[8], is[8], g[8], sd[8], sx[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy.p + px * dy.ld + c)), d);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(raw.p + px * raw.ld + c)), r);
+    load8f(scale + c, s); load8f(shift + c, t); load8f(mean + c, m); load8f(invstd + c, is);
+    load8f(sum_dz + c, sd); load8f(sum_dzx + c, sx);
+    if (gamma) load8f(gamma + c, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float z = r[j] * s[j] + t[j];
+      float dz = d[j] * act_grad_rt(act, z);
+      float xh = (r[j] - m[j]) * is[j];
+      float gg = gamma ? g[j] : 1.f;
+      d[j] = gg * is[j] * (dz - sd[j] * inv_count - xh * sx[j] * inv_count);
+    }
+    *reinterpret_cast<uint4*>(dr.p + px * dr.ld + c) = pack8(d);
+  }
+}
+
+__global__ void act_bwd_kernel(View dy, View raw, const float* __restrict__ scale,
+                               const float* __restrict__ shift, int act, View dx) {
+  const int c8 = dy.c >> 3;
+  const long long total = dy.npix * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long px = i / c8;
+    const int c = (int)(i - px * c8) << 3;
+    float d[8], r[8], s[8], t[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy.p + px * dy.ld + c)), d);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(raw.p + px * raw.ld + c)), r);
+    if (scale) load8f(scale + c, s);
+    if (shift) load8f(shift + c, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float sc = scale ? s[j] : 1.f;
+      float z = r[j] * sc + (shift ? t[j] : 0.f);
+      d[j] = d[j] * act_grad_rt(act, z) * sc;
+    }
+    *reinterpret_cast<uint4*>(dx.p + px * dx.ld + c) = pack8(d);
+  }
+}
+
+// ---- upsample / add ---------------------------------------------------------------------------
+__global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int n, int h, int w, int c,
+                                      __nv_bfloat16* __restrict__ y, int y_ld) {
+  const int c8 = c >> 3;
+  const int H = 2 * h, W = 2 * w;
+  const long long total = (long long)n * H * W * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long px = i / c8;
+    const int cc = (int)(i - px * c8) << 3;
+    const int ox = (int)(px % W); long long t = px / W;
+    const int oy = (int)(t % H);
+    const int b = (int)(t / H);
+    const long long src = ((long long)b * h + (oy >> 1)) * w + (ox >> 1);
+    *reinterpret_cast<uint4*>(y + px * y_ld + cc) = __ldg(reinterpret_cast<const uint4*>(x + src * x_ld + cc));
+  }
+}
+
+__global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ld, int n, int h, int w, int c,
+                                      __nv_bfloat16* __restrict__ dx, int dx_ld, int accumulate) {
+  // dx is (n,h,w,c); dy is (n,2h,2w,c)
+  const int c8 = c >> 3;
+  const int W = 2 * w;
+  const long long total = (long long)n * h * w * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long px = i / c8;
+    const int cc = (int)(i - px * c8) << 3;
+    const int x0 = (int)(px % w); long long t = px / w;
+    const int y0 = (int)(t % h);
+    const int b = (int)(t / h);
+    const long long base = ((long long)b * 2 * h + 2 * y0) * W + 2 * x0;
+    float acc[8], v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + base * dy_ld + cc)), acc);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (base + 1) * dy_ld + cc)), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (base + W) * dy_ld + cc)), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (base + W + 1) * dy_ld + cc)), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    if (accumulate) {
+      unpack8(*reinterpret_cast<const uint4*>(dx + px * dx_ld + cc), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+    *reinterpret_cast<uint4*>(dx + px * dx_ld + cc) = pack8(acc);
+  }
+}
+
+__global__ void add_kernel(View a, const __nv_bfloat16* __restrict__ b, int b_ld, View y) {
+  const int c8 = a.c >> 3;
+  const long long total = a.npix * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long px = i / c8;
+    const int c = (int)(i - px * c8) << 3;
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(a.p + px * a.ld + c));
+    if (b) {
+      float va[8], vb[8];
+      unpack8(u, va);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(b + px * b_ld + c)), vb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) va[j] += vb[j];
+      u = pack8(va);
+    }
+    *reinterpret_cast<uint4*>(y.p + px * y.ld + c) = u;
+  }
+}
+
+// ---- layout conversion (API edge) ----------------------------------------------------------------
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int ld, int n, int hw, int c,
+                                    float* __restrict__ y) {
+  // tile transpose 32 (pixels) x 32 (channels) through shared memory
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int p = p0 + r, cc = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (p < hw && cc < c) ? __bfloat162float(x[((long long)b * hw + p) * ld + cc]) : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int cc = c0 + r, p = p0 + threadIdx.x;
+    if (p < hw && cc < c) y[((long long)b * c + cc) * hw + p] = tile[threadIdx.x][r];
+  }
+}
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int n, int hw, int c,
+                                    __nv_bfloat16* __restrict__ y, int ld) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int cc = c0 + r, p = p0 + threadIdx.x;
+    tile[r][threadIdx.x] = (p < hw && cc < c) ? x[((long long)b * c + cc) * hw + p] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int p = p0 + r, cc = c0 + threadIdx.x;
+    if (p < hw && cc < c) y[((long long)b * hw + p) * ld + cc] = __float2bfloat16(tile[threadIdx.x][r]);
+  }
+}
+
+// ---- weights ---------------------------------------------------------------------------------------
+// out[o][tap][i] (transposed: out[i][tap][o]) = w[o][i][tap]
+__global__ void pack_weight_kernel(const float* __restrict__ w, int O, int I, int kk, int transposed,
+                                   __nv_bfloat16* __restrict__ out) {
+  const long long total = (long long)O * I * kk;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int o, i, t;
+    if (!transposed) { i = (int)(idx % I); long long r = idx / I; t = (int)(r % kk); o = (int)(r / kk); }
+    else { o = (int)(idx % O); long long r = idx / O; t = (int)(r % kk); i = (int)(r / kk); }
+    out[idx] = __float2bfloat16(__ldg(w + ((long long)o * I + i) * kk + t));
+  }
+}
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int O, int I, int kk, float* __restrict__ g,
+                                    int accumulate) {
+  const long long total = (long long)O * I * kk;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    // idx enumerates the OIHW destination; read the packed [o][tap][i] source
+    int t = (int)(idx % kk); long long r = idx / kk; int i = (int)(r % I); int o = (int)(r / I);
+    float v = __ldg(dwp + ((long long)o * kk + t) * I + i);
+    g[idx] = accumulate ? g[idx] + v : v;
+  }
+}
+
+// out[b][o][tap][i] = sum_k attn[b][k] * bank[k][o][i][tap]   (transposed: out[b][i][tap][o])
+__global__ void dyn_aggregate_kernel(const float* __restrict__ attn, int n, int K, const float* __restrict__ bank,
+                                     int O, int I, int kk, int transposed, __nv_bfloat16* __restrict__ out) {
+  const long long per = (long long)O * I * kk;
+  const long long total = per * n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / per);
+    const long long e = idx - (long long)b * per;
+    int o, i, t;
+    if (!transposed) { i = (int)(e % I); long long r = e / I; t = (int)(r % kk); o = (int)(r / kk); }
+    else { o = (int)(e % O); long long r = e / O; t = (int)(r % kk); i = (int)(r / kk); }
+    const long long src = ((long long)o * I + i) * kk + t;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) acc += __ldg(attn + b * K + k) * __ldg(bank + (long long)k * per + src);
+    out[idx] = __float2bfloat16(acc);
+  }
+}
+__global__ void dyn_bias_kernel(const float* __restrict__ attn, int n, int K, const float* __restrict__ bias_bank,
+                                int O, float* __restrict__ bias_out) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * O) return;
+  int b = idx / O, o = idx - b * O;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc += attn[b * K + k] * bias_bank[k * O + o];
+  bias_out[idx] = acc;
+}
+
+// ---- global average pool -------------------------------------------------------------------------
+// out[b][q*C + c] += sum over pixels of parity class q (s2d) / all pixels (q = 0), scaled by inv_count
+__global__ void gap_kernel(const __nv_bfloat16* __restrict__ x, int ld, int h, int w, int c, int s2d,
+                           float inv_count, float* __restrict__ out) {
+  __shared__ float red[256 * 8];
+  const int G = c >> 3;
+  const int Gb = G < 32 ? G : 32;
+  const int PL = 256 / Gb;
+  const int g = threadIdx.x % Gb + blockIdx.y * Gb;
+  const int pl = threadIdx.x / Gb;
+  const int b = blockIdx.z;
+  const int nq = s2d ? 4 : 1;
+  const long long hw = (long long)h * w;
+  for (int q = 0; q < nq; ++q) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (g < G && pl < PL) {
+      const int cc = g << 3;
+      for (long long p = (long long)blockIdx.x * PL + pl; p < hw; p += (long long)gridDim.x * PL) {
+        if (s2d) {
+          const int py = (int)(p / w), px = (int)(p - (long long)py * w);
+          if (((py & 1) * 2 + (px & 1)) != q) continue;
+        }
+        float v[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + ((long long)b * hw + p) * ld + cc)), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      }
+    }
+    float* mine = red + threadIdx.x * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mine[j] = acc[j];
+    __syncthreads();
+    for (int t = threadIdx.x; t < Gb * 8; t += 256) {
+      const int gg = t >> 3, slot = t & 7;
+      float s = 0.f;
+      for (int l = 0; l < PL; ++l) s += red[(l * Gb + gg) * 8 + slot];
+      const int gch = gg + blockIdx.y * Gb;
+      if (gch < G) atomicAdd(out + (long long)b * nq * c + q * c + (gch << 3) + slot, s * inv_count);
+    }
+    __syncthreads();
+  }
+}
+__global__ void gap_nchw_kernel(const float* __restrict__ x, int hw, float* __restrict__ out) {
+  // one block per (n, c) plane
+  const float* p = x + (long long)blockIdx.x * hw;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) s += p[i];
+  __shared__ float red[32];
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) out[blockIdx.x] = s / (float)hw;
+  }
+}
+
+// ---- attention MLP + softmax (one block per sample) ---------------------------------------------------
+__global__ void attn_mlp_softmax_kernel(const float* __restrict__ pooled, int c, const float* __restrict__ w1,
+                                        const float* __restrict__ b1, int hid, const float* __restrict__ w2,
+                                        const float* __restrict__ b2, int K, float inv_t, float* __restrict__ attn,
+                                        float* __restrict__ hidden) {
+  extern __shared__ float sh[];  // [c] pooled, [hid] hidden, [K] logits
+  float* sp = sh; float* shid = sh + c; float* slog = shid + hid;
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) sp[i] = pooled[(long long)b * c + i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < hid; j += nw) {
+    float s = 0.f;
+    for (int i = lane; i < c; i += 32) s += sp[i] * __ldg(w1 + (long long)j * c + i);
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      s += b1 ? b1[j] : 0.f;
+      s = s > 0.f ? s : 0.f;
+      shid[j] = s;
+      if (hidden) hidden[(long long)b * hid + j] = s;
+    }
+  }
+  __syncthreads();
+  for (int k = warp; k < K; k += nw) {
+    float s = 0.f;
+    for (int i = lane; i < hid; i += 32) s += shid[i] * __ldg(w2 + (long long)k * hid + i);
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) slog[k] = (s + (b2 ? b2[k] : 0.f)) * inv_t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mx = -INFINITY;
+    for (int k = 0; k < K; ++k) mx = fmaxf(mx, slog[k]);
+    float den = 0.f;
+    for (int k = 0; k < K; ++k) { float e = expf(slog[k] - mx); slog[k] = e; den += e; }
+    for (int k = 0; k < K; ++k) attn[(long long)b * K + k] = slog[k] / den;
+  }
+}
+
+// ---- SGD ------------------------------------------------------------------------------------------
+__global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                    long long count, float lr, float momentum, float grad_scale, int first) {
+  const long long n4 = count >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 gp = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    float4 mm = first ? make_float4(0, 0, 0, 0) : reinterpret_cast<float4*>(m)[i];
+    gp.x *= grad_scale; gp.y *= grad_scale; gp.z *= grad_scale; gp.w *= grad_scale;
+    mm.x = first ? gp.x : momentum * mm.x + gp.x; mm.y = first ? gp.y : momentum * mm.y + gp.y;
+    mm.z = first ? gp.z : momentum * mm.z + gp.z; mm.w = first ? gp.w : momentum * mm.w + gp.w;
+    pp.x -= lr * mm.x; pp.y -= lr * mm.y; pp.z -= lr * mm.z; pp.w -= lr * mm.w;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(p)[i] = pp;
+  }
+  // tail
+  for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    float gg = g[i] * grad_scale;
+    float mm = first ? gg : momentum * m[i] + gg;
+    m[i] = mm;
+    p[i] -= lr * mm;
+  }
+}
+
+}  // namespace uavdet
+
+using namespace uavdet;
+#define ST ((cudaStream_t)stream)
+
+extern "C" int uavdet_bn_finalize(const float* sum, const float* sumsq, int c, double count, float eps,
+                                  float momentum, const float* gamma, const float* beta, float* running_mean,
+                                  float* running_var, float* mean, float* invstd, float* scale, float* shift,
+                                  void* stream) {
+  UAVDET_CHECK_ARG(sum && sumsq && scale && shift && c > 0 && count > 0, "bn_finalize: bad arguments");
+  bn_finalize_kernel<<<ceil_div(c, 128), 128, 0, ST>>>(sum, sumsq, c, count, eps, momentum, gamma, beta,
+                                                       running_mean, running_var, mean, invstd, scale, shift);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_bn_act_fwd(const uavdet_act* raw, const float* scale, const float* shift, int act,
+                                 const uavdet_act* res, const uavdet_act* y, void* stream) {
+  int rc;
+  if ((rc = check_view(raw, "bn_act_fwd raw")) || (rc = check_view(y, "bn_act_fwd y")) ||
+      (rc = same_shape(raw, y, "bn_act_fwd")))
+    return rc;
+  if (res && ((rc = check_view(res, "bn_act_fwd res")) || (rc = same_shape(raw, res, "bn_act_fwd res")))) return rc;
+  View r = mkview(raw), o = mkview(y);
+  bn_act_fwd_kernel<<<ew_grid(r.npix * (r.c / 8), 256), 256, 0, ST>>>(
+      r, scale, shift, act, res ? (const __nv_bfloat16*)res->ptr : nullptr, res ? res->ld : 0, o);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+static dim3 reduce_grid(const uavdet_act* v, int* PL_out) {
+  int G = v->c / 8, Gb = G < 32 ? G : 32, PL = 256 / Gb;
+  long long npix = (long long)v->n * v->h * v->w;
+  long long bx = (npix + (long long)PL * 16 - 1) / ((long long)PL * 16);
+  if (bx > kNumSMs * 8) bx = kNumSMs * 8;
+  if (bx < 1) bx = 1;
+  if (PL_out) *PL_out = PL;
+  return dim3((unsigned)bx, (unsigned)ceil_div(G, Gb), 1);
+}
+
+extern "C" int uavdet_bn_act_bwd_reduce(const uavdet_act* dy, const uavdet_act* raw, const float* scale,
+                                        const float* shift, const float* mean, const float* invstd, int act,
+                                        float* sum_dz, float* sum_dzx, void* stream) {
+  int rc;
+  if ((rc = check_view(dy, "bn_bwd_reduce dy")) || (rc = check_view(raw, "bn_bwd_reduce raw")) ||
+      (rc = same_shape(dy, raw, "bn_bwd_reduce")))
+    return rc;
+  UAVDET_CHECK_ARG(scale && shift && mean && invstd && sum_dz && sum_dzx, "bn_bwd_reduce: null stats");
+  bn_bwd_reduce_kernel<<<reduce_grid(dy, nullptr), 256, 0, ST>>>(mkview(dy), mkview(raw), scale, shift, mean,
+                                                                   invstd, act, sum_dz, sum_dzx);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_bn_act_bwd_apply(const uavdet_act* dy, const uavdet_act* raw, const float* scale,
+                                       const float* shift, const float* mean, const float* invstd,
+                                       const float* gamma, int act, const float* sum_dz, const float* sum_dzx,
+                                       const uavdet_act* d_raw, void* stream) {
+  int rc;
+  if ((rc = check_view(dy, "bn_bwd_apply dy")) || (rc = check_view(raw, "bn_bwd_apply raw")) ||
+      (rc = check_view(d_raw, "bn_bwd_apply d_raw")) || (rc = same_shape(dy, raw, "bn_bwd_apply")) ||
+      (rc = same_shape(dy, d_raw, "bn_bwd_apply")))
+    return rc;
+  View d = mkview(dy);
+  bn_bwd_apply_kernel<<<ew_grid(d.npix * (d.c / 8), 256), 256, 0, ST>>>(
+      d, mkview(raw), scale, shift, mean, invstd, gamma, act, sum_dz, sum_dzx, 1.f / (float)d.npix,
+      mkview(d_raw));
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_act_bwd(const uavdet_act* dy, const uavdet_act* raw, const float* scale,
+                              const float* shift, int act, const uavdet_act* dx, void* stream) {
+  int rc;
+  if ((rc = check_view(dy, "act_bwd dy")) || (rc = check_view(raw, "act_bwd raw")) ||
+      (rc = check_view(dx, "act_bwd dx")) || (rc = same_shape(dy, raw, "act_bwd")) ||
+      (rc = same_shape(dy, dx, "act_bwd")))
+    return rc;
+  View d = mkview(dy);
+  act_bwd_kernel<<<ew_grid(d.npix * (d.c / 8), 256), 256, 0, ST>>>(d, mkview(raw), scale, shift, act, mkview(dx));
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_upsample2x_fwd(const uavdet_act* x, const uavdet_act* y, void* stream) {
+  int rc;
+  if ((rc = check_view(x, "upsample2x_fwd x")) || (rc = check_view(y, "upsample2x_fwd y"))) return rc;
+  UAVDET_CHECK_ARG(y->n == x->n && y->h == 2 * x->h && y->w == 2 * x->w && y->c == x->c, "upsample2x_fwd: shapes");
+  long long total = (long long)y->n * y->h * y->w * (y->c / 8);
+  upsample2x_fwd_kernel<<<ew_grid(total, 256), 256, 0, ST>>>((const __nv_bfloat16*)x->ptr, x->ld, x->n, x->h, x->w,
+                                                            x->c, (__nv_bfloat16*)y->ptr, y->ld);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_upsample2x_bwd(const uavdet_act* dy, const uavdet_act* dx, int accumulate, void* stream) {
+  int rc;
+  if ((rc = check_view(dy, "upsample2x_bwd dy")) || (rc = check_view(dx, "upsample2x_bwd dx"))) return rc;
+  UAVDET_CHECK_ARG(dy->n == dx->n && dy->h == 2 * dx->h && dy->w == 2 * dx->w && dy->c == dx->c, "upsample2x_bwd: shapes");
+  long long total = (long long)dx->n * dx->h * dx->w * (dx->c / 8);
+  upsample2x_bwd_kernel<<<ew_grid(total, 256), 256, 0, ST>>>((const __nv_bfloat16*)dy->ptr, dy->ld, dx->n, dx->h,
+                                                            dx->w, dx->c, (__nv_bfloat16*)dx->ptr, dx->ld, accumulate);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_add(const uavdet_act* a, const uavdet_act* b, const uavdet_act* y, void* stream) {
+  int rc;
+  if ((rc = check_view(a, "add a")) || (rc = check_view(y, "add y")) || (rc = same_shape(a, y, "add"))) return rc;
+  if (b && ((rc = check_view(b, "add b")) || (rc = same_shape(a, b, "add b")))) return rc;
+  View va = mkview(a);
+  add_kernel<<<ew_grid(va.npix * (va.c / 8), 256), 256, 0, ST>>>(va, b ? (const __nv_bfloat16*)b->ptr : nullptr,
+                                                                 b ? b->ld : 0, mkview(y));
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_nhwc_to_nchw_f32(const uavdet_act* x, float* y_nchw, void* stream) {
+  UAVDET_CHECK_ARG(x && x->ptr && y_nchw, "nhwc_to_nchw: null");
+  int hw = x->h * x->w;
+  dim3 grid(ceil_div(hw, 32), ceil_div(x->c, 32), x->n), block(32, 8);
+  nhwc_to_nchw_kernel<<<grid, block, 0, ST>>>((const __nv_bfloat16*)x->ptr, x->ld, x->n, hw, x->c, y_nchw);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+extern "C" int uavdet_nchw_f32_to_nhwc(const float* x_nchw, const uavdet_act* y, void* stream) {
+  UAVDET_CHECK_ARG(y && y->ptr && x_nchw, "nchw_to_nhwc: null");
+  int hw = y->h * y->w;
+  dim3 grid(ceil_div(hw, 32), ceil_div(y->c, 32), y->n), block(32, 8);
+  nchw_to_nhwc_kernel<<<grid, block, 0, ST>>>(x_nchw, y->n, hw, y->c, (__nv_bfloat16*)y->ptr, y->ld);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_pack_weight(const float* w_oihw, int O, int I, int k, int transposed, void* out_bf16,
+                                  void* stream) {
+  UAVDET_CHECK_ARG(w_oihw && out_bf16 && O > 0 && I > 0 && k > 0, "pack_weight: bad arguments");
+  long long total = (long long)O * I * k * k;
+  pack_weight_kernel<<<ew_grid(total, 256), 256, 0, ST>>>(w_oihw, O, I, k * k, transposed, (__nv_bfloat16*)out_bf16);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+extern "C" int uavdet_unpack_wgrad(const float* dw_packed, int O, int I, int k, float* grad_oihw, int accumulate,
+                                   void* stream) {
+  UAVDET_CHECK_ARG(dw_packed && grad_oihw, "unpack_wgrad: null");
+  long long total = (long long)O * I * k * k;
+  unpack_wgrad_kernel<<<ew_grid(total, 256), 256, 0, ST>>>(dw_packed, O, I, k * k, grad_oihw, accumulate);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_dyn_aggregate(const float* attn, int n, int K, const float* bank, int O, int I, int k,
+                                    int transposed, void* out_bf16, const float* bias_bank, float* bias_out,
+                                    void* stream) {
+  UAVDET_CHECK_ARG(attn && bank && out_bf16 && n > 0 && K > 0, "dyn_aggregate: bad arguments");
+  long long total = (long long)n * O * I * k * k;
+  dyn_aggregate_kernel<<<ew_grid(total, 256), 256, 0, ST>>>(attn, n, K, bank, O, I, k * k, transposed,
+                                                            (__nv_bfloat16*)out_bf16);
+  UAVDET_LAUNCH_CHECK();
+  if (bias_bank && bias_out) {
+    dyn_bias_kernel<<<ceil_div(n * O, 256), 256, 0, ST>>>(attn, n, K, bias_bank, O, bias_out);
+    UAVDET_LAUNCH_CHECK();
+  }
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_gap(const uavdet_act* x, int s2d, float* out, void* stream) {
+  int rc;
+  if ((rc = check_view(x, "gap x"))) return rc;
+  UAVDET_CHECK_ARG(out, "gap: null out");
+  const int nq = s2d ? 4 : 1;
+  UAVDET_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)x->n * nq * x->c, ST));
+  int G = x->c / 8, Gb = G < 32 ? G : 32, PL = 256 / Gb;
+  long long hw = (long long)x->h * x->w;
+  long long bx = (hw + (long long)PL * 8 - 1) / ((long long)PL * 8);
+  long long cap = (kNumSMs * 4) / (x->n > 0 ? x->n : 1) + 1;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid((unsigned)bx, (unsigned)ceil_div(G, Gb), (unsigned)x->n);
+  gap_kernel<<<grid, 256, 0, ST>>>((const __nv_bfloat16*)x->ptr, x->ld, x->h, x->w, x->c, s2d,
+                                   (float)(nq / (double)hw), out);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+extern "C" int uavdet_gap_nchw(const float* x_nchw, int n, int c, int hw, float* out, void* stream) {
+  UAVDET_CHECK_ARG(x_nchw && out && n > 0 && c > 0 && hw > 0, "gap_nchw: bad arguments");
+  gap_nchw_kernel<<<n * c, 256, 0, ST>>>(x_nchw, hw, out);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_attn_mlp_softmax(const float* pooled, int n, int c, const float* w1, const float* b1, int hid,
+                                       const float* w2, const float* b2, int K, float temperature, float* attn,
+                                       float* hidden, void* stream) {
+  UAVDET_CHECK_ARG(pooled && w1 && w2 && attn && n > 0 && c > 0 && hid > 0 && K > 0, "attn_mlp_softmax: bad arguments");
+  size_t sh = sizeof(float) * (size_t)(c + hid + K);
+  UAVDET_CHECK_ARG(sh <= 48 * 1024, "attn_mlp_softmax: c+hid+K too large");
+  attn_mlp_softmax_kernel<<<n, 256, sh, ST>>>(pooled, c, w1, b1, hid, w2, b2, K, 1.f / temperature, attn, hidden);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_sgd_momentum(float* param, const float* grad, float* momentum_buf, int64_t count, float lr,
+                                   float momentum, float grad_scale, int first_step, void* stream) {
+  UAVDET_CHECK_ARG(param && grad && momentum_buf && count >= 0, "sgd: bad arguments");
+  UAVDET_CHECK_ARG((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)momentum_buf) & 15) == 0, "sgd: 16-byte alignment");
+  if (count == 0) return UAVDET_OK;
+  sgd_momentum_kernel<<<ew_grid(count / 4 + 1, 256), 256, 0, ST>>>(param, grad, momentum_buf, count, lr, momentum,
+                                                                   grad_scale, first_step);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}

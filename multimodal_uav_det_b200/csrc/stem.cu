@@ -1,0 +1,207 @@
+// Stem convolution for cin in {1,3}: direct CUDA-core kernel reading the NCHW fp32 network
+// input and writing NHWC bf16.  K = cin*k*k <= 75 is far below the tensor-core ridge
+// (SURVEY.md §7 "thin-channel early layers"): the layer is bound by the 64 B/pixel output
+// write, so one thread owns one output pixel and all 32 output channels.
+// Reference: first layer of BaselineModel.py:89-97 / DyYOLO.py:89-100 (via per-sample weights),
+// DySOEM_SimFPN.py:30 (1x1), RTMUAVDet.py:31 (5x5 s2 p1).
+#include "common.cuh"
+
+namespace uavdet {
+
+constexpr int kStemCout = 32;
+constexpr int kStemMaxK = 75;  // 3 * 5 * 5
+
+struct StemParams {
+  const float* x; int n, cin, h, w;
+  const float* wgt;        // [w_batch][32][cin][k][k] fp32
+  int w_batch;
+  int k, stride, pad, ho, wo;
+  __nv_bfloat16* y; long long y_ld;
+  int epi, act;
+  const float* scale; const float* shift;
+  float* sum; float* sumsq;
+};
+
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int step = 16; step >= 1; step >>= 1) {
+    const bool upper = (lane & step) != 0;
+#pragma unroll
+    for (int i = 0; i < step; ++i) {
+      float send = upper ? v[i] : v[i + step];
+      float keep = upper ? v[i + step] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+    }
+  }
+  return v[0];
+}
+
+// grid.y = image; each block handles 256 consecutive output pixels of that image
+__global__ void __launch_bounds__(256) stem_fwd_kernel(StemParams P) {
+  __shared__ float sw[kStemMaxK * kStemCout];  // [tap*cin][32] (cout fastest -> broadcast-free reads)
+  __shared__ float ssum[2][kStemCout];
+  const int img = blockIdx.y;
+  const int K = P.cin * P.k * P.k;
+  const float* wsrc = P.wgt + (P.w_batch > 1 ? (long long)img * kStemCout * K : 0);
+  for (int i = threadIdx.x; i < K * kStemCout; i += blockDim.x) {
+    const int co = i % kStemCout, kk = i / kStemCout;  // kk = (ci*k + kh)*k + kw
+    sw[kk * kStemCout + co] = wsrc[co * K + kk];
+  }
+  if (threadIdx.x < 2 * kStemCout) ssum[threadIdx.x / kStemCout][threadIdx.x % kStemCout] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long hw_out = (long long)P.ho * P.wo;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = p < hw_out;
+  float acc[kStemCout];
+#pragma unroll
+  for (int c = 0; c < kStemCout; ++c) acc[c] = 0.f;
+  if (valid) {
+    const int oy = (int)(p / P.wo), ox = (int)(p - (long long)oy * P.wo);
+    const float* xin = P.x + (long long)img * P.cin * P.h * P.w;
+    for (int ci = 0; ci < P.cin; ++ci)
+      for (int kh = 0; kh < P.k; ++kh) {
+        const int iy = oy * P.stride + kh - P.pad;
+        if (iy < 0 || iy >= P.h) continue;
+        for (int kw = 0; kw < P.k; ++kw) {
+          const int ix = ox * P.stride + kw - P.pad;
+          if (ix < 0 || ix >= P.w) continue;
+          const float xv = __ldg(xin + ((long long)ci * P.h + iy) * P.w + ix);
+          const float* wr = sw + ((ci * P.k + kh) * P.k + kw) * kStemCout;
+#pragma unroll
+          for (int c = 0; c < kStemCout; ++c) acc[c] = fmaf(xv, wr[c], acc[c]);
+        }
+      }
+  }
+  __nv_bfloat16* yp = P.y + ((long long)img * hw_out + p) * P.y_ld;
+  if (P.epi == UAVDET_EPI_STATS) {
+    if (valid) {
+#pragma unroll
+      for (int c = 0; c < kStemCout; c += 8) {
+        uint4 o;
+        o.x = pack_bf16x2(acc[c], acc[c + 1]); o.y = pack_bf16x2(acc[c + 2], acc[c + 3]);
+        o.z = pack_bf16x2(acc[c + 4], acc[c + 5]); o.w = pack_bf16x2(acc[c + 6], acc[c + 7]);
+        *reinterpret_cast<uint4*>(yp + c) = o;
+      }
+    }
+    float sq[kStemCout];
+#pragma unroll
+    for (int c = 0; c < kStemCout; ++c) sq[c] = acc[c] * acc[c];  // invalid lanes hold zeros
+    const float s1 = warp_colsum32(acc, lane);
+    const float s2 = warp_colsum32(sq, lane);
+    atomicAdd(&ssum[0][lane], s1);
+    atomicAdd(&ssum[1][lane], s2);
+    __syncthreads();
+    if (threadIdx.x < kStemCout) {
+      atomicAdd(P.sum + threadIdx.x, ssum[0][threadIdx.x]);
+      atomicAdd(P.sumsq + threadIdx.x, ssum[1][threadIdx.x]);
+    }
+  } else if (valid) {
+#pragma unroll
+    for (int c = 0; c < kStemCout; ++c) {
+      float z = acc[c];
+      if (P.scale) z *= __ldg(P.scale + c);
+      if (P.shift) z += __ldg(P.shift + c);
+      acc[c] = act_fwd_rt(P.act, z);
+    }
+#pragma unroll
+    for (int c = 0; c < kStemCout; c += 8) {
+      uint4 o;
+      o.x = pack_bf16x2(acc[c], acc[c + 1]); o.y = pack_bf16x2(acc[c + 2], acc[c + 3]);
+      o.z = pack_bf16x2(acc[c + 4], acc[c + 5]); o.w = pack_bf16x2(acc[c + 6], acc[c + 7]);
+      *reinterpret_cast<uint4*>(yp + c) = o;
+    }
+  }
+}
+
+// dW[co][ci][kh][kw] += sum_p dy[p][co] * x[p + tap][ci]; lane = co, a warp walks pixels.
+// per_sample: one gradient per image ([n][32][K]) for the dynamic-kernel stem (DyYOLO layer 0).
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, int n, int cin, int h, int w,
+                                                         const __nv_bfloat16* __restrict__ dy, long long dy_ld,
+                                                         int k, int stride, int pad, int ho, int wo,
+                                                         float* __restrict__ grad, int per_sample) {
+  __shared__ float red[kStemMaxK * kStemCout];
+  const int K = cin * k * k;
+  const int img = blockIdx.y;
+  for (int i = threadIdx.x; i < K * kStemCout; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float acc[kStemMaxK];
+#pragma unroll
+  for (int i = 0; i < kStemMaxK; ++i) acc[i] = 0.f;
+  const long long hw_out = (long long)ho * wo;
+  const float* xin = x + (long long)img * cin * h * w;
+  for (long long p = (long long)blockIdx.x * nw + warp; p < hw_out; p += (long long)gridDim.x * nw) {
+    const int oy = (int)(p / wo), ox = (int)(p - (long long)oy * wo);
+    const float g = __bfloat162float(dy[((long long)img * hw_out + p) * dy_ld + lane]);
+    int kk = 0;
+    for (int ci = 0; ci < cin; ++ci)
+      for (int kh = 0; kh < k; ++kh) {
+        const int iy = oy * stride + kh - pad;
+        for (int kw = 0; kw < k; ++kw, ++kk) {
+          const int ix = ox * stride + kw - pad;
+          float xv = 0.f;
+          if (iy >= 0 && iy < h && ix >= 0 && ix < w) xv = __ldg(xin + ((long long)ci * h + iy) * w + ix);
+          // kk is a loop counter over <= 75 taps: keep the accumulators addressable
+          acc[kk] = fmaf(g, xv, acc[kk]);
+        }
+      }
+  }
+  for (int kk = 0; kk < K; ++kk) atomicAdd(&red[kk * kStemCout + lane], acc[kk]);
+  __syncthreads();
+  float* gdst = grad + (per_sample ? (long long)img * kStemCout * K : 0);
+  for (int i = threadIdx.x; i < K * kStemCout; i += blockDim.x) {
+    const int co = i % kStemCout, kk = i / kStemCout;
+    atomicAdd(gdst + co * K + kk, red[i]);
+  }
+}
+
+}  // namespace uavdet
+
+using namespace uavdet;
+
+extern "C" int uavdet_stem_fwd(const float* x_nchw, int n, int cin, int h, int w, const float* w_oihw, int cout,
+                               int k, int stride, int pad, const uavdet_act* y, const uavdet_epilogue* epi,
+                               void* stream) {
+  UAVDET_CHECK_ARG(x_nchw && w_oihw && y && y->ptr, "stem_fwd: null pointer");
+  UAVDET_CHECK_ARG(cout == kStemCout, "stem_fwd: cout must be %d (got %d)", kStemCout, cout);
+  UAVDET_CHECK_ARG(cin >= 1 && cin <= 3 && cin * k * k <= kStemMaxK, "stem_fwd: cin=%d k=%d unsupported", cin, k);
+  StemParams P{};
+  P.x = x_nchw; P.n = n; P.cin = cin; P.h = h; P.w = w; P.wgt = w_oihw;
+  P.w_batch = (epi && epi->head_anchors < 0) ? n : 1;  // head_anchors = -1 flags per-sample stem weights
+  P.k = k; P.stride = stride; P.pad = pad;
+  P.ho = (h + 2 * pad - k) / stride + 1;
+  P.wo = (w + 2 * pad - k) / stride + 1;
+  UAVDET_CHECK_ARG(y->n == n && y->h == P.ho && y->w == P.wo && y->c == cout, "stem_fwd: output view mismatch");
+  UAVDET_CHECK_ARG(y->ld % 8 == 0 && ((uintptr_t)y->ptr & 15) == 0, "stem_fwd: output alignment");
+  P.y = (__nv_bfloat16*)y->ptr; P.y_ld = y->ld;
+  P.epi = epi ? epi->epi : UAVDET_EPI_AFFINE;
+  P.act = epi ? epi->act : UAVDET_ACT_NONE;
+  P.scale = epi ? epi->scale : nullptr; P.shift = epi ? epi->shift : nullptr;
+  P.sum = epi ? epi->sum : nullptr; P.sumsq = epi ? epi->sumsq : nullptr;
+  if (P.epi == UAVDET_EPI_STATS) UAVDET_CHECK_ARG(P.sum && P.sumsq, "stem_fwd: STATS needs sum/sumsq");
+  UAVDET_CHECK_ARG(P.epi != UAVDET_EPI_HEAD, "stem_fwd: HEAD epilogue unsupported");
+  dim3 grid((unsigned)ceil_div64((long long)P.ho * P.wo, 256), (unsigned)n);
+  stem_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_stem_wgrad(const float* x_nchw, int n, int cin, int h, int w, const uavdet_act* dy, int k,
+                                 int stride, int pad, float* grad_oihw, void* stream) {
+  UAVDET_CHECK_ARG(x_nchw && dy && dy->ptr && grad_oihw, "stem_wgrad: null pointer");
+  UAVDET_CHECK_ARG(dy->c == kStemCout && cin >= 1 && cin <= 3 && cin * k * k <= kStemMaxK, "stem_wgrad: unsupported shape");
+  const int per_sample = n < 0 ? 1 : 0;  // n < 0 flags per-sample gradients ([|n|][32][K])
+  if (n < 0) n = -n;
+  const long long hw_out = (long long)dy->h * dy->w;
+  int bx = (int)((hw_out + 8 * 64 - 1) / (8 * 64));
+  int cap = (kNumSMs * 8) / (n > 0 ? n : 1) + 1;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid((unsigned)bx, (unsigned)n);
+  stem_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, n, cin, h, w, (const __nv_bfloat16*)dy->ptr,
+                                                             dy->ld, k, stride, pad, dy->h, dy->w, grad_oihw,
+                                                             per_sample);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}

@@ -1,0 +1,432 @@
+"""Tensor-level wrappers over the C-ABI (include/uavdet_b200.h).
+
+PyTorch is used only for device memory and streams: every function takes CUDA tensors, passes
+raw pointers + the current stream to libuavdet_b200.so and returns tensors it allocated with
+torch.empty.  Activations are NHWC bf16 tensors of shape (N,H,W,C) whose last-dim stride is 1
+and whose pixel stride (`stride(2)`) may exceed C (channel-slice views of a concat buffer).
+No op has a PyTorch/CPU fallback: a missing library or a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT, EPI_AFFINE, EPI_HEAD, EPI_STATS, Act, Epilogue, UavdetError, check
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _require_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise UavdetError("uavdet ops need CUDA tensors (there is no CPU fallback)")
+
+
+def _f32(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise UavdetError("expected a contiguous float32 tensor")
+    return t
+
+
+def act_view(t: torch.Tensor) -> Act:
+    """Describe an NHWC bf16 tensor (possibly a channel slice) to the C-ABI."""
+    if t.dtype != torch.bfloat16 or t.dim() != 4:
+        raise UavdetError(f"expected a 4-D NHWC bfloat16 tensor, got {t.dtype} {tuple(t.shape)}")
+    n, h, w, c = t.shape
+    sn, sh, sw, sc = t.stride()
+    if c > 1 and sc != 1:
+        raise UavdetError("channel stride must be 1")
+    ld = sw if w > 1 else (sh if h > 1 else max(c, sw))
+    if w > 1 and h > 1 and sh != w * ld or (n > 1 and sn != h * w * ld):
+        raise UavdetError(f"NHWC view must be dense in pixels: strides {t.stride()} shape {tuple(t.shape)}")
+    return Act(t.data_ptr(), n, h, w, c, ld)
+
+
+def empty_act(n: int, h: int, w: int, c: int, device) -> torch.Tensor:
+    return torch.empty((n, h, w, c), dtype=torch.bfloat16, device=device)
+
+
+def launch_count() -> int:
+    return int(_lib.load().uavdet_launch_count())
+
+
+def check_device() -> None:
+    """Synchronise and raise if a kernel's pipeline watchdog tripped."""
+    flag = C.c_int(0)
+    check(_lib.load().uavdet_check_device(_stream(), C.byref(flag)), "device watchdog")
+
+
+# --------------------------------------------------------------------------------------------
+# NMS / decode
+# --------------------------------------------------------------------------------------------
+def nms_batched(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float,
+                score_floor: float = float("-inf")) -> Tuple[torch.Tensor, torch.Tensor]:
+    """boxes (B,N,4) fp32 xyxy, scores (B,N) fp32 -> keep (B,N) int64 (first count[b] valid), count (B,) int32."""
+    _require_cuda(boxes, scores)
+    boxes = _f32(boxes)
+    scores = _f32(scores)
+    b, n = scores.shape
+    lib = _lib.load()
+    keep = torch.empty((b, n), dtype=torch.int64, device=boxes.device)
+    count = torch.zeros((b,), dtype=torch.int32, device=boxes.device)
+    ws_bytes = lib.uavdet_nms_workspace_bytes(b, n)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=boxes.device)
+    check(lib.uavdet_nms(_ptr(boxes), _ptr(scores), b, n, float(iou_threshold), float(score_floor), _ptr(keep),
+                         _ptr(count), _ptr(ws), ws_bytes, _stream()), "nms")
+    return keep, count
+
+
+def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float) -> torch.Tensor:
+    """Drop-in for torchvision.ops.nms(boxes (N,4), scores (N,), thr) -> int64 kept indices."""
+    keep, count = nms_batched(boxes.reshape(1, -1, 4).contiguous(), scores.reshape(1, -1).contiguous(),
+                              iou_threshold)
+    return keep[0, : int(count[0].item())]
+
+
+def decode_yolo(outs: Sequence, anchors, head_scales, ciou: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    """outs: list of (bbox (B,A,S,S,4), obj (B,A,S,S,1)) fp32 logits per head ->
+    boxes (B, sum A*S*S, 4) xyxy in grid units, scores (B, sum) raw logits (model/_base.py:196-203)."""
+    lib = _lib.load()
+    bboxes = [_f32(o.bbox if hasattr(o, "bbox") else o[0]) for o in outs]
+    objs = [_f32(o.obj if hasattr(o, "obj") else o[1]) for o in outs]
+    _require_cuda(*bboxes, *objs)
+    b = bboxes[0].shape[0]
+    counts = [t.shape[1] * t.shape[2] * t.shape[3] for t in bboxes]
+    n_total = sum(counts)
+    boxes = torch.empty((b, n_total, 4), dtype=torch.float32, device=bboxes[0].device)
+    scores = torch.empty((b, n_total), dtype=torch.float32, device=bboxes[0].device)
+    off = 0
+    for hi, (tb, to) in enumerate(zip(bboxes, objs)):
+        _, a, sh, sw, _ = tb.shape
+        # anchors / head_scale evaluated in fp32 exactly like torch.tensor(anchors).float() / scale
+        anc = (torch.tensor(anchors[hi]).float() / torch.tensor(head_scales)[hi]).flatten().tolist()
+        arr = (C.c_float * len(anc))(*anc)
+        check(lib.uavdet_decode_yolo(_ptr(tb), _ptr(to), b, a, sh, sw, arr, 1 if ciou else 0, _ptr(boxes),
+                                     _ptr(scores), n_total, off, _stream()), "decode_yolo")
+        off += counts[hi]
+    return boxes, scores
+
+
+def decode_rtm(bbox_sig: torch.Tensor, anchors_head) -> torch.Tensor:
+    lib = _lib.load()
+    _require_cuda(bbox_sig)
+    bbox_sig = _f32(bbox_sig)
+    b, a, sh, sw, _ = bbox_sig.shape
+    anc = torch.as_tensor(anchors_head).float().flatten().tolist()
+    arr = (C.c_float * len(anc))(*anc)
+    out = torch.empty_like(bbox_sig)
+    check(lib.uavdet_decode_rtm(_ptr(bbox_sig), b, a, sh, sw, arr, _ptr(out), _stream()), "decode_rtm")
+    return out
+
+
+def cxcywh_to_xyxy(t: torch.Tensor) -> torch.Tensor:
+    _require_cuda(t)
+    t = _f32(t)
+    out = torch.empty_like(t)
+    check(_lib.load().uavdet_cxcywh_to_xyxy(_ptr(t), _ptr(out), t.numel() // 4, _stream()), "cxcywh_to_xyxy")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# weights
+# --------------------------------------------------------------------------------------------
+def pack_weight(w: torch.Tensor, transposed: bool = False, rows: Optional[int] = None) -> torch.Tensor:
+    """OIHW fp32 -> bf16 [O][kh*kw*I] (or [I][kh*kw*O]).  rows > O zero-pads (head convs)."""
+    _require_cuda(w)
+    w = _f32(w)
+    o, i, kh, kw = w.shape
+    assert kh == kw
+    r = i if transposed else o
+    kt = kh * kw * (o if transposed else i)
+    rows = rows or r
+    out = torch.zeros((rows, kt), dtype=torch.bfloat16, device=w.device) if rows != r else \
+        torch.empty((rows, kt), dtype=torch.bfloat16, device=w.device)
+    check(_lib.load().uavdet_pack_weight(_ptr(w), o, i, kh, 1 if transposed else 0, _ptr(out), _stream()),
+          "pack_weight")
+    return out
+
+
+def unpack_wgrad(dw_packed: torch.Tensor, o: int, i: int, k: int, grad: Optional[torch.Tensor] = None,
+                 accumulate: bool = False) -> torch.Tensor:
+    if grad is None:
+        grad = torch.empty((o, i, k, k), dtype=torch.float32, device=dw_packed.device)
+        accumulate = False
+    check(_lib.load().uavdet_unpack_wgrad(_ptr(dw_packed), o, i, k, _ptr(grad), 1 if accumulate else 0, _stream()),
+          "unpack_wgrad")
+    return grad
+
+
+# --------------------------------------------------------------------------------------------
+# convolution
+# --------------------------------------------------------------------------------------------
+def _epilogue(epi: int = EPI_AFFINE, act=None, scale=None, shift=None, res: Optional[torch.Tensor] = None,
+              sum_=None, sumsq=None, head_obj=None, head_bbox=None, head_anchors: int = 0) -> Epilogue:
+    e = Epilogue()
+    e.epi = epi
+    e.act = ACT[act] if not isinstance(act, int) else act
+    e.scale = scale.data_ptr() if scale is not None else None
+    e.shift = shift.data_ptr() if shift is not None else None
+    if res is not None:
+        rv = act_view(res)
+        e.res, e.res_ld = rv.ptr, rv.ld
+    else:
+        e.res, e.res_ld = None, 0
+    e.sum = sum_.data_ptr() if sum_ is not None else None
+    e.sumsq = sumsq.data_ptr() if sumsq is not None else None
+    e.head_obj = head_obj.data_ptr() if head_obj is not None else None
+    e.head_bbox = head_bbox.data_ptr() if head_bbox is not None else None
+    e.head_anchors = head_anchors
+    return e
+
+
+def conv_out_hw(h: int, w: int, k: int, stride: int, pad: int) -> Tuple[int, int]:
+    return (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+
+
+def conv_fwd(x: torch.Tensor, w_packed: torch.Tensor, cout: int, k: int, stride: int, pad: int, *,
+             s2d: bool = False, w_batch: int = 1, out: Optional[torch.Tensor] = None, epi: int = EPI_AFFINE,
+             act=None, scale=None, shift=None, res=None, sum_=None, sumsq=None) -> torch.Tensor:
+    """Implicit-GEMM conv.  x NHWC bf16; w_packed from pack_weight / dyn_aggregate."""
+    _require_cuda(x, w_packed)
+    n, h, w, _ = x.shape
+    hin, win = (h // 2, w // 2) if s2d else (h, w)
+    ho, wo = conv_out_hw(hin, win, k, stride, pad)
+    if out is None:
+        out = empty_act(n, ho, wo, cout, x.device)
+    xv, yv = act_view(x), act_view(out)
+    e = _epilogue(epi, act, _f32(scale), _f32(shift), res, _f32(sum_), _f32(sumsq))
+    check(_lib.load().uavdet_conv_fwd(C.byref(xv), _ptr(w_packed), w_batch, cout, k, stride, pad, 1 if s2d else 0,
+                                      C.byref(yv), C.byref(e), _stream()), "conv_fwd")
+    return out
+
+
+def conv_head(x: torch.Tensor, w_packed16: torch.Tensor, bias15: torch.Tensor, anchors: int
+              ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fused objectness+bbox 1x1 head conv (model/_base.py:80-120): one N=16 GEMM writes both
+    (B,A,H,W,1) and (B,A,H,W,4) fp32 logits in their final layout."""
+    _require_cuda(x, w_packed16, bias15)
+    n, h, w, _ = x.shape
+    obj = torch.empty((n, anchors, h, w, 1), dtype=torch.float32, device=x.device)
+    bbox = torch.empty((n, anchors, h, w, 4), dtype=torch.float32, device=x.device)
+    xv = act_view(x)
+    e = _epilogue(EPI_HEAD, None, None, _f32(bias15), None, None, None, obj, bbox, anchors)
+    check(_lib.load().uavdet_conv_fwd(C.byref(xv), _ptr(w_packed16), 1, 5 * anchors, 1, 1, 0, 0, None, C.byref(e),
+                                      _stream()), "conv_head")
+    return obj, bbox
+
+
+def conv_dgrad(dy: torch.Tensor, w_packed_t: torch.Tensor, cin: int, k: int, stride: int, pad: int,
+               in_hw: Tuple[int, int], *, w_batch: int = 1, out: Optional[torch.Tensor] = None,
+               res: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _require_cuda(dy, w_packed_t)
+    n = dy.shape[0]
+    if out is None:
+        out = empty_act(n, in_hw[0], in_hw[1], cin, dy.device)
+    dv, xv = act_view(dy), act_view(out)
+    e = _epilogue(EPI_AFFINE, None, None, None, res)
+    check(_lib.load().uavdet_conv_dgrad(C.byref(dv), _ptr(w_packed_t), w_batch, cin, k, stride, pad, C.byref(xv),
+                                        C.byref(e), _stream()), "conv_dgrad")
+    return out
+
+
+def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, k: int, stride: int, pad: int, *, s2d: bool = False,
+               per_sample: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Returns the packed fp32 gradient [cout][k*k*cin] (or [n][cout][k*k*cin])."""
+    _require_cuda(x, dy)
+    cin = x.shape[3] * (4 if s2d else 1)
+    cout = dy.shape[3]
+    shape = (x.shape[0], cout, k * k * cin) if per_sample else (cout, k * k * cin)
+    if out is None:
+        out = torch.zeros(shape, dtype=torch.float32, device=x.device)
+    xv, dv = act_view(x), act_view(dy)
+    check(_lib.load().uavdet_conv_wgrad(C.byref(xv), C.byref(dv), k, stride, pad, 1 if s2d else 0, _ptr(out),
+                                        1 if per_sample else 0, _stream()), "conv_wgrad")
+    return out
+
+
+def stem_fwd(x_nchw: torch.Tensor, w: torch.Tensor, k: int, stride: int, pad: int, *, epi: int = EPI_AFFINE,
+             act=None, scale=None, shift=None, sum_=None, sumsq=None, per_sample_w: bool = False) -> torch.Tensor:
+    _require_cuda(x_nchw, w)
+    x_nchw = _f32(x_nchw)
+    w = _f32(w)
+    n, cin, h, ww = x_nchw.shape
+    cout = w.shape[-4]
+    ho, wo = conv_out_hw(h, ww, k, stride, pad)
+    out = empty_act(n, ho, wo, cout, x_nchw.device)
+    yv = act_view(out)
+    e = _epilogue(epi, act, _f32(scale), _f32(shift), None, _f32(sum_), _f32(sumsq),
+                  head_anchors=-1 if per_sample_w else 0)
+    check(_lib.load().uavdet_stem_fwd(_ptr(x_nchw), n, cin, h, ww, _ptr(w), cout, k, stride, pad, C.byref(yv),
+                                      C.byref(e), _stream()), "stem_fwd")
+    return out
+
+
+def stem_wgrad(x_nchw: torch.Tensor, dy: torch.Tensor, k: int, stride: int, pad: int,
+               per_sample: bool = False) -> torch.Tensor:
+    _require_cuda(x_nchw, dy)
+    n, cin, h, w = x_nchw.shape
+    shape = (n, dy.shape[3], cin, k, k) if per_sample else (dy.shape[3], cin, k, k)
+    grad = torch.zeros(shape, dtype=torch.float32, device=dy.device)
+    dv = act_view(dy)
+    check(_lib.load().uavdet_stem_wgrad(_ptr(_f32(x_nchw)), -n if per_sample else n, cin, h, w, C.byref(dv), k,
+                                        stride, pad, _ptr(grad), _stream()), "stem_wgrad")
+    return grad
+
+
+# --------------------------------------------------------------------------------------------
+# batch-norm / activation / data movement
+# --------------------------------------------------------------------------------------------
+def bn_finalize(sum_, sumsq, count: float, eps: float, momentum: float, gamma, beta, running_mean, running_var):
+    c = sum_.numel()
+    dev = sum_.device
+    mean = torch.empty(c, dtype=torch.float32, device=dev)
+    invstd = torch.empty_like(mean)
+    scale = torch.empty_like(mean)
+    shift = torch.empty_like(mean)
+    check(_lib.load().uavdet_bn_finalize(_ptr(sum_), _ptr(sumsq), c, float(count), float(eps), float(momentum),
+                                         _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), _ptr(mean),
+                                         _ptr(invstd), _ptr(scale), _ptr(shift), _stream()), "bn_finalize")
+    return mean, invstd, scale, shift
+
+
+def bn_act_fwd(raw, scale, shift, act, res=None, out=None):
+    if out is None:
+        out = torch.empty(raw.shape, dtype=torch.bfloat16, device=raw.device)
+    rv, yv = act_view(raw), act_view(out)
+    resv = act_view(res) if res is not None else None
+    check(_lib.load().uavdet_bn_act_fwd(C.byref(rv), _ptr(scale), _ptr(shift), ACT[act] if not isinstance(act, int) else act,
+                                        C.byref(resv) if resv is not None else None, C.byref(yv), _stream()),
+          "bn_act_fwd")
+    return out
+
+
+def bn_act_bwd(dy, raw, scale, shift, mean, invstd, gamma, act):
+    """Train-mode BN(+act) backward.  Returns (d_raw bf16, dgamma fp32, dbeta fp32)."""
+    c = raw.shape[3]
+    a = ACT[act] if not isinstance(act, int) else act
+    sums = torch.zeros((2, c), dtype=torch.float32, device=raw.device)
+    dv, rv = act_view(dy), act_view(raw)
+    lib = _lib.load()
+    check(lib.uavdet_bn_act_bwd_reduce(C.byref(dv), C.byref(rv), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd),
+                                       a, _ptr(sums[0]), _ptr(sums[1]), _stream()), "bn_act_bwd_reduce")
+    d_raw = torch.empty(raw.shape, dtype=torch.bfloat16, device=raw.device)
+    ov = act_view(d_raw)
+    check(lib.uavdet_bn_act_bwd_apply(C.byref(dv), C.byref(rv), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd),
+                                      _ptr(gamma), a, _ptr(sums[0]), _ptr(sums[1]), C.byref(ov), _stream()),
+          "bn_act_bwd_apply")
+    return d_raw, sums[1], sums[0]
+
+
+def act_bwd(dy, raw, scale, shift, act):
+    dx = torch.empty(raw.shape, dtype=torch.bfloat16, device=raw.device)
+    dv, rv, ov = act_view(dy), act_view(raw), act_view(dx)
+    check(_lib.load().uavdet_act_bwd(C.byref(dv), C.byref(rv), _ptr(scale), _ptr(shift),
+                                     ACT[act] if not isinstance(act, int) else act, C.byref(ov), _stream()), "act_bwd")
+    return dx
+
+
+def upsample2x_fwd(x, out=None):
+    n, h, w, c = x.shape
+    if out is None:
+        out = empty_act(n, 2 * h, 2 * w, c, x.device)
+    xv, yv = act_view(x), act_view(out)
+    check(_lib.load().uavdet_upsample2x_fwd(C.byref(xv), C.byref(yv), _stream()), "upsample2x_fwd")
+    return out
+
+
+def upsample2x_bwd(dy, out=None, accumulate=False):
+    n, h2, w2, c = dy.shape
+    if out is None:
+        out = empty_act(n, h2 // 2, w2 // 2, c, dy.device)
+        accumulate = False
+    dv, ov = act_view(dy), act_view(out)
+    check(_lib.load().uavdet_upsample2x_bwd(C.byref(dv), C.byref(ov), 1 if accumulate else 0, _stream()),
+          "upsample2x_bwd")
+    return out
+
+
+def add(a, b=None, out=None):
+    if out is None:
+        out = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
+    av, ov = act_view(a), act_view(out)
+    bv = act_view(b) if b is not None else None
+    check(_lib.load().uavdet_add(C.byref(av), C.byref(bv) if bv is not None else None, C.byref(ov), _stream()), "add")
+    return out
+
+
+def nhwc_to_nchw_f32(x):
+    n, h, w, c = x.shape
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    xv = act_view(x)
+    check(_lib.load().uavdet_nhwc_to_nchw_f32(C.byref(xv), _ptr(out), _stream()), "nhwc_to_nchw")
+    return out
+
+
+def nchw_f32_to_nhwc(x):
+    x = _f32(x)
+    n, c, h, w = x.shape
+    out = empty_act(n, h, w, c, x.device)
+    ov = act_view(out)
+    check(_lib.load().uavdet_nchw_f32_to_nhwc(_ptr(x), C.byref(ov), _stream()), "nchw_to_nhwc")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# dynamic-kernel attention
+# --------------------------------------------------------------------------------------------
+def gap(x, s2d=False):
+    n, h, w, c = x.shape
+    out = torch.empty((n, (4 if s2d else 1) * c), dtype=torch.float32, device=x.device)
+    xv = act_view(x)
+    check(_lib.load().uavdet_gap(C.byref(xv), 1 if s2d else 0, _ptr(out), _stream()), "gap")
+    return out
+
+
+def gap_nchw(x):
+    x = _f32(x)
+    n, c, h, w = x.shape
+    out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    check(_lib.load().uavdet_gap_nchw(_ptr(x), n, c, h * w, _ptr(out), _stream()), "gap_nchw")
+    return out
+
+
+def attn_mlp_softmax(pooled, w1, b1, w2, b2, temperature, want_hidden=False):
+    n, c = pooled.shape
+    hid, k = w1.shape[0], w2.shape[0]
+    attn = torch.empty((n, k), dtype=torch.float32, device=pooled.device)
+    hidden = torch.empty((n, hid), dtype=torch.float32, device=pooled.device) if want_hidden else None
+    check(_lib.load().uavdet_attn_mlp_softmax(_ptr(_f32(pooled)), n, c, _ptr(_f32(w1)), _ptr(b1), hid, _ptr(_f32(w2)),
+                                              _ptr(b2), k, float(temperature), _ptr(attn), _ptr(hidden), _stream()),
+          "attn_mlp_softmax")
+    return (attn, hidden) if want_hidden else attn
+
+
+def dyn_aggregate(attn, bank, transposed=False, bias_bank=None):
+    """attn (n,K) fp32, bank (K,O,I,k,k) fp32 -> bf16 (n, O, k*k*I) [or (n, I, k*k*O)], bias (n,O)|None."""
+    n, kk_ = attn.shape
+    K, o, i, k, _ = bank.shape
+    assert K == kk_
+    rows, kt = (i, k * k * o) if transposed else (o, k * k * i)
+    out = torch.empty((n, rows, kt), dtype=torch.bfloat16, device=attn.device)
+    bias_out = torch.empty((n, o), dtype=torch.float32, device=attn.device) if bias_bank is not None else None
+    check(_lib.load().uavdet_dyn_aggregate(_ptr(_f32(attn)), n, K, _ptr(_f32(bank.contiguous())), o, i, k,
+                                           1 if transposed else 0, _ptr(out), _ptr(bias_bank), _ptr(bias_out),
+                                           _stream()), "dyn_aggregate")
+    return out, bias_out
+
+
+def sgd_momentum(param, grad, buf, lr, momentum, grad_scale=1.0, first_step=False):
+    check(_lib.load().uavdet_sgd_momentum(_ptr(param), _ptr(grad), _ptr(buf), param.numel(), float(lr),
+                                          float(momentum), float(grad_scale), 1 if first_step else 0, _stream()),
+          "sgd_momentum")
