@@ -1,0 +1,472 @@
+"""GPU parity tests of the individual kernels, called through the C-ABI (via ops.py) and checked
+against the CPU oracle / fp32 torch-on-CPU restatements on identical (bf16-rounded) inputs.
+
+Tolerances: conv outputs are bf16 -> |err| <= 2^-7 * ref_scale style bound, stated
+per test; fp32 reductions 1e-3 relative; NMS kept indices bit-exact."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops(lib):
+    from multimodal_uav_det_b200 import ops
+    return ops
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def nhwc(t_nchw):
+    return t_nchw.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).to(DEV)
+
+
+def to_nchw(t_nhwc):
+    return t_nhwc.float().cpu().permute(0, 3, 1, 2).contiguous()
+
+
+def rel_l2(a, b):
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def assert_close_bf16(got, ref, what, rel=6e-3, frac=2.0 ** -6):
+    """bf16 output: relative L2 <= rel and every element within frac*max|ref| (+bf16 ulp of itself)."""
+    r = rel_l2(got, ref)
+    scale = ref.abs().max().item() + 1e-6
+    worst = (got - ref).abs().max().item()
+    assert math.isfinite(r) and r <= rel and worst <= frac * scale, \
+        f"{what}: rel_l2={r:.3e} (<= {rel}), max_abs={worst:.3e} (<= {frac * scale:.3e})"
+
+
+# ------------------------------------------------------------------------------------------------
+# NMS
+# ------------------------------------------------------------------------------------------------
+def _random_boxes(n, g, span=100.0, size=40.0, quant=None):
+    c = torch.rand(n, 2, generator=g) * span
+    wh = torch.rand(n, 2, generator=g) * size
+    boxes = torch.cat([c - wh / 2, c + wh / 2], 1)
+    scores = torch.randn(n, generator=g)
+    if quant:
+        scores = (scores * quant).round() / quant
+    return boxes, scores
+
+
+@pytest.mark.parametrize("n,quant,thr", [(1, None, 0.5), (7, None, 0.5), (64, None, 0.5), (65, 4, 0.5),
+                                         (1000, None, 0.5), (3000, 20, 0.5), (5000, None, 0.3),
+                                         (25200, 20, 0.5), (4097, None, 0.45)])
+def test_nms_matches_oracle_bit_exact(lib, n, quant, thr):
+    from oracle import oracle as O
+    ops = _ops(lib)
+    g = torch.Generator().manual_seed(n)
+    boxes, scores = _random_boxes(n, g, quant=quant)
+    want = O.nms(boxes.numpy(), scores.numpy(), thr)
+    got = ops.nms(boxes.to(DEV), scores.to(DEV), thr).cpu().numpy()
+    ops.check_device()
+    assert got.dtype == np.int64
+    assert np.array_equal(got, want), f"n={n}: kept {len(got)} vs {len(want)}"
+
+
+def test_nms_edge_cases(lib):
+    from oracle import oracle as O
+    ops = _ops(lib)
+    # empty
+    k, c = ops.nms_batched(torch.zeros(2, 0, 4, device=DEV), torch.zeros(2, 0, device=DEV), 0.5)
+    assert c.tolist() == [0, 0]
+    # degenerate (zero-area -> 0/0 NaN never suppresses), identical boxes, NaN score, +-0 ties, inf
+    boxes = torch.tensor([[0, 0, 0, 0], [0, 0, 0, 0], [1, 1, 5, 5], [1, 1, 5, 5], [1, 1, 5, 5.0001],
+                          [2, 2, 1, 1], [0, 0, 10, 10], [0, 0, 10, 10]], dtype=torch.float32)
+    scores = torch.tensor([0.5, 0.5, float("nan"), 0.0, -0.0, 3.0, float("inf"), float("-inf")])
+    want = O.nms(boxes.numpy(), scores.numpy(), 0.5)
+    import torchvision
+    assert np.array_equal(want, torchvision.ops.nms(boxes, scores, 0.5).numpy())
+    got = ops.nms(boxes.to(DEV), scores.to(DEV), 0.5).cpu().numpy()
+    assert np.array_equal(got, want)
+
+
+def test_nms_batched_and_score_floor(lib):
+    from oracle import oracle as O
+    ops = _ops(lib)
+    g = torch.Generator().manual_seed(5)
+    bs, n = 5, 2000
+    boxes = torch.empty(bs, n, 4)
+    scores = torch.empty(bs, n)
+    for b in range(bs):
+        boxes[b], scores[b] = _random_boxes(n, g, quant=8 if b % 2 else None)
+    keep, count = ops.nms_batched(boxes.to(DEV), scores.to(DEV), 0.5)
+    for b in range(bs):
+        want = O.nms(boxes[b].numpy(), scores[b].numpy(), 0.5)
+        assert np.array_equal(keep[b, : int(count[b])].cpu().numpy(), want)
+    # extension: score floor == torchvision nms on the filtered subset
+    floor = 0.25
+    keep, count = ops.nms_batched(boxes.to(DEV), scores.to(DEV), 0.5, score_floor=floor)
+    for b in range(bs):
+        idx = torch.nonzero(scores[b] > floor).flatten()
+        want = idx.numpy()[O.nms(boxes[b][idx].numpy(), scores[b][idx].numpy(), 0.5)]
+        assert np.array_equal(keep[b, : int(count[b])].cpu().numpy(), want)
+
+
+# ------------------------------------------------------------------------------------------------
+# decode
+# ------------------------------------------------------------------------------------------------
+ANCHORS = [[[199, 73], [315, 92], [268, 182]], [[91, 54], [120, 75], [157, 60]], [[29, 23], [48, 30], [67, 38]]]
+SCALES = [32, 16, 8]
+
+
+@pytest.mark.parametrize("ciou", [True, False])
+def test_decode_yolo_matches_oracle(lib, ciou):
+    from oracle import oracle as O
+    ops = _ops(lib)
+    g = torch.Generator().manual_seed(3)
+    outs = [(torch.randn(2, 3, s, s, 4, generator=g) * 2, torch.randn(2, 3, s, s, 1, generator=g)) for s in (4, 8, 16)]
+    wb, ws = O.decode_yolo(outs, ANCHORS, SCALES, ciou)
+    gb, gs = ops.decode_yolo([(b.to(DEV), o.to(DEV)) for b, o in outs], ANCHORS, SCALES, ciou)
+    assert torch.equal(gs.cpu(), ws)  # scores are a pure copy
+    torch.testing.assert_close(gb.cpu(), wb, rtol=2e-6, atol=2e-6)  # fp32; expf differs by <= 2 ulp
+
+
+def test_decode_rtm_matches_oracle(lib):
+    from oracle import oracle as O
+    ops = _ops(lib)
+    g = torch.Generator().manual_seed(4)
+    t = torch.rand(2, 3, 10, 12, 4, generator=g)
+    anc = torch.tensor(ANCHORS[2]).float()
+    want = O.decode_rtm(t, anc)
+    got = ops.decode_rtm(t.to(DEV), anc)
+    torch.testing.assert_close(got.cpu(), want, rtol=1e-6, atol=1e-6)
+    assert torch.equal(ops.cxcywh_to_xyxy(want.to(DEV)).cpu(), O.cxcywh_to_xyxy(want))
+
+
+# ------------------------------------------------------------------------------------------------
+# implicit-GEMM convolution (tcgen05)
+# ------------------------------------------------------------------------------------------------
+def _conv_case(n, cin, cout, k, stride, h, w, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = bf16_round(torch.randn(n, cin, h, w, generator=g))
+    wt = bf16_round(torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k))
+    return x, wt
+
+
+FWD_CASES = [
+    # n, cin, cout, k, stride, h, w
+    (1, 64, 64, 1, 1, 16, 8),       # single tile, BK=64
+    (2, 64, 128, 1, 1, 16, 16),
+    (2, 64, 64, 3, 1, 16, 16),      # 3x3 halo / zero padding through TMA OOB
+    (1, 32, 64, 3, 1, 16, 16),      # BK=32 (SWIZZLE_64B)
+    (2, 32, 64, 3, 2, 32, 32),      # stride 2 through the parity view
+    (1, 128, 256, 3, 2, 16, 16),
+    (2, 256, 128, 1, 1, 20, 20),    # 20x20 map: non power-of-two tile
+    (1, 512, 1024, 3, 1, 20, 20),   # 4 n-tiles, K = 4608
+    (3, 128, 256, 3, 1, 40, 40),    # many tiles per CTA: pipeline wrap-around + TMEM double buffering
+    (2, 768, 256, 1, 1, 40, 40),
+    (1, 64, 192, 1, 1, 24, 24),     # block_n = 192
+    (1, 64, 32, 1, 1, 64, 64),
+    (1, 64, 64, 5, 1, 12, 12),      # 25 taps
+]
+
+
+@pytest.mark.parametrize("case", FWD_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_fwd_plain(lib, case):
+    ops = _ops(lib)
+    n, cin, cout, k, stride, h, w = case
+    pad = k // 2
+    x, wt = _conv_case(*case)
+    ref = F.conv2d(x, wt, None, stride, pad)
+    wp = ops.pack_weight(wt.to(DEV))
+    y = ops.conv_fwd(nhwc(x), wp, cout, k, stride, pad)
+    ops.check_device()
+    assert_close_bf16(to_nchw(y), ref, f"conv_fwd{case}")
+
+
+def test_pack_weight_layouts(lib):
+    ops = _ops(lib)
+    wt = torch.randn(8, 6, 3, 3)
+    p = ops.pack_weight(wt.to(DEV)).float().cpu()
+    assert torch.equal(p, bf16_round(wt.permute(0, 2, 3, 1).reshape(8, -1)))
+    pt = ops.pack_weight(wt.to(DEV), transposed=True).float().cpu()
+    assert torch.equal(pt, bf16_round(wt.permute(1, 2, 3, 0).reshape(6, -1)))
+    g = torch.randn(8, 3 * 3 * 6)
+    back = ops.unpack_wgrad(g.to(DEV), 8, 6, 3).cpu()
+    assert torch.equal(back, g.view(8, 3, 3, 6).permute(0, 3, 1, 2))
+
+
+@pytest.mark.parametrize("act", ["leaky", "silu", "relu", "none"])
+def test_conv_fwd_affine_epilogue(lib, act):
+    ops = _ops(lib)
+    n, cin, cout, k, stride, h, w = 2, 64, 128, 3, 1, 16, 16
+    x, wt = _conv_case(n, cin, cout, k, stride, h, w, seed=1)
+    g = torch.Generator().manual_seed(9)
+    scale = torch.rand(cout, generator=g) + 0.5
+    shift = torch.randn(cout, generator=g) * 0.1
+    res = bf16_round(torch.randn(n, cout, h, w, generator=g))
+    z = F.conv2d(x, wt, None, stride, 1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    a = {"leaky": lambda t: F.leaky_relu(t, 0.1), "silu": F.silu, "relu": F.relu, "none": lambda t: t}[act](z)
+    ref = a + res
+    y = ops.conv_fwd(nhwc(x), ops.pack_weight(wt.to(DEV)), cout, k, stride, 1, act=act, scale=scale.to(DEV),
+                     shift=shift.to(DEV), res=nhwc(res))
+    ops.check_device()
+    assert_close_bf16(to_nchw(y), ref, f"affine[{act}]")
+
+
+def test_conv_fwd_stats_epilogue_and_channel_slice(lib):
+    """STATS epilogue: raw bf16 output + fp32 per-channel sum / sum of squares; output written into
+    a channel slice of a wider buffer (route concat, BaselineModel.py:120-122)."""
+    ops = _ops(lib)
+    n, cin, cout, k, stride, h, w = 2, 128, 256, 3, 1, 20, 20
+    x, wt = _conv_case(n, cin, cout, k, stride, h, w, seed=2)
+    ref = F.conv2d(x, wt, None, stride, 1)
+    buf = torch.full((n, h, w, 384), 7.0, dtype=torch.bfloat16, device=DEV)
+    s1 = torch.zeros(cout, device=DEV)
+    s2 = torch.zeros(cout, device=DEV)
+    from multimodal_uav_det_b200._lib import EPI_STATS
+    ops.conv_fwd(nhwc(x), ops.pack_weight(wt.to(DEV)), cout, k, stride, 1, out=buf[..., 128:], epi=EPI_STATS,
+                 sum_=s1, sumsq=s2)
+    ops.check_device()
+    assert_close_bf16(to_nchw(buf[..., 128:]), ref, "stats raw")
+    assert torch.all(buf[..., :128].float() == 7.0), "wrote outside the channel slice"
+    torch.testing.assert_close(s1.cpu(), ref.sum(dim=(0, 2, 3)), rtol=2e-3, atol=2e-2)
+    torch.testing.assert_close(s2.cpu(), (ref * ref).sum(dim=(0, 2, 3)), rtol=2e-3, atol=2e-2)
+
+
+def test_conv_fwd_strided_input_view(lib):
+    """Input is a channel slice (ld > c), stride-2 parity view must honour the pixel stride."""
+    ops = _ops(lib)
+    n, cin, cout, h, w = 2, 64, 128, 16, 16
+    x, wt = _conv_case(n, cin, cout, 3, 2, h, w, seed=3)
+    buf = torch.randn(n, h, w, 192, device=DEV).to(torch.bfloat16)
+    buf[..., 64:128] = nhwc(x)
+    for stride in (1, 2):
+        ref = F.conv2d(x, wt, None, stride, 1)
+        y = ops.conv_fwd(buf[..., 64:128], ops.pack_weight(wt.to(DEV)), cout, 3, stride, 1)
+        ops.check_device()
+        assert_close_bf16(to_nchw(y), ref, f"strided view s{stride}")
+
+
+def test_conv_head_epilogue(lib):
+    """Fused obj+bbox 1x1 head (model/_base.py:80-120) in the final (B,A,H,W,{1,4}) fp32 layout."""
+    from oracle import oracle as O
+    ops = _ops(lib)
+    n, cin, h, w, A = 2, 256, 20, 20, 3
+    g = torch.Generator().manual_seed(11)
+    x = bf16_round(torch.randn(n, cin, h, w, generator=g))
+    sd = {"h.0.obj.conv_obj.weight": bf16_round(torch.randn(A, cin, 1, 1, generator=g) / 16),
+          "h.0.obj.conv_obj.bias": torch.randn(A, generator=g),
+          "h.0.bbox.conv_bbox.weight": bf16_round(torch.randn(4 * A, cin, 1, 1, generator=g) / 16),
+          "h.0.bbox.conv_bbox.bias": torch.randn(4 * A, generator=g)}
+    (ref_bbox, ref_obj), = O.yolo_head([x], sd, "h")
+    w15 = torch.cat([sd["h.0.obj.conv_obj.weight"], sd["h.0.bbox.conv_bbox.weight"]]).to(DEV)
+    b15 = torch.cat([sd["h.0.obj.conv_obj.bias"], sd["h.0.bbox.conv_bbox.bias"]]).to(DEV)
+    obj, bbox = ops.conv_head(nhwc(x), ops.pack_weight(w15, rows=16), b15, A)
+    ops.check_device()
+    torch.testing.assert_close(obj.cpu(), ref_obj, rtol=1e-3, atol=1e-3)   # fp32 accumulate, fp32 out
+    torch.testing.assert_close(bbox.cpu(), ref_bbox, rtol=1e-3, atol=1e-3)
+
+
+def test_conv_fwd_per_sample_weights(lib):
+    """Dynamic kernels: one aggregated weight matrix per image (model/_base.py:65-74)."""
+    ops = _ops(lib)
+    n, cin, cout, k, h, w = 3, 64, 64, 3, 16, 16
+    g = torch.Generator().manual_seed(12)
+    x = bf16_round(torch.randn(n, cin, h, w, generator=g))
+    bank = torch.randn(4, cout, cin, k, k, generator=g)
+    attn = torch.softmax(torch.randn(n, 4, generator=g), 1)
+    wp, _ = ops.dyn_aggregate(attn.to(DEV), bank.to(DEV))
+    filt = (attn @ bank.flatten(1)).view(n, cout, cin, k, k)
+    assert rel_l2(wp.float().cpu(), filt.permute(0, 1, 3, 4, 2).reshape(n, cout, -1)) < 4e-3
+    ref = torch.cat([F.conv2d(x[i:i + 1], bf16_round(filt[i]), None, 1, 1) for i in range(n)])
+    y = ops.conv_fwd(nhwc(x), wp, cout, k, 1, 1, w_batch=n)
+    ops.check_device()
+    assert_close_bf16(to_nchw(y), ref, "per-sample weights", rel=1e-2)
+
+
+def test_conv_fwd_space_to_depth(lib):
+    """DynamicSOEM gather fused into the loader (DySOEM_SimFPN.py:71-75): conv over s2d(x)."""
+    from oracle import oracle as O
+    ops = _ops(lib)
+    n, c, h, w, cout = 2, 32, 32, 32, 64
+    g = torch.Generator().manual_seed(13)
+    x = bf16_round(torch.randn(n, c, h, w, generator=g))
+    wt = bf16_round(torch.randn(cout, 4 * c, 3, 3, generator=g) / math.sqrt(36 * c))
+    ref = F.conv2d(O.space_to_depth2(x), wt, None, 1, 1)
+    y = ops.conv_fwd(nhwc(x), ops.pack_weight(wt.to(DEV)), cout, 3, 1, 1, s2d=True)
+    ops.check_device()
+    assert_close_bf16(to_nchw(y), ref, "s2d conv")
+
+
+DGRAD_CASES = [(2, 64, 64, 1, 1, 16, 16), (2, 64, 128, 3, 1, 16, 16), (2, 32, 64, 3, 2, 32, 32),
+               (1, 128, 256, 3, 2, 20, 20), (2, 64, 128, 1, 2, 16, 16), (1, 256, 512, 3, 1, 20, 20)]
+
+
+@pytest.mark.parametrize("case", DGRAD_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_dgrad(lib, case):
+    ops = _ops(lib)
+    n, cin, cout, k, stride, h, w = case
+    pad = k // 2
+    x, wt = _conv_case(*case)
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    g = torch.Generator().manual_seed(21)
+    dy = bf16_round(torch.randn(n, cout, ho, wo, generator=g))
+    skip = bf16_round(torch.randn(n, cin, h, w, generator=g))
+    ref = torch.nn.grad.conv2d_input(x.shape, wt, dy, stride, pad) + skip
+    dx = ops.conv_dgrad(nhwc(dy), ops.pack_weight(wt.to(DEV), transposed=True), cin, k, stride, pad, (h, w),
+                        res=nhwc(skip))
+    ops.check_device()
+    assert_close_bf16(to_nchw(dx), ref, f"dgrad{case}")
+
+
+WGRAD_CASES = [(2, 64, 64, 1, 1, 16, 16), (2, 64, 128, 3, 1, 16, 16), (2, 32, 64, 3, 2, 32, 32),
+               (1, 128, 256, 3, 2, 20, 20), (2, 256, 128, 1, 1, 20, 20), (1, 64, 32, 1, 1, 32, 32),
+               (4, 512, 1024, 3, 1, 20, 20), (2, 64, 128, 1, 2, 16, 16)]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_wgrad(lib, case):
+    ops = _ops(lib)
+    n, cin, cout, k, stride, h, w = case
+    pad = k // 2
+    x, wt = _conv_case(*case)
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    g = torch.Generator().manual_seed(22)
+    dy = bf16_round(torch.randn(n, cout, ho, wo, generator=g))
+    ref = torch.nn.grad.conv2d_weight(x, wt.shape, dy, stride, pad)
+    dwp = ops.conv_wgrad(nhwc(x), nhwc(dy), k, stride, pad)
+    ops.check_device()
+    got = ops.unpack_wgrad(dwp, cout, cin, k).cpu()
+    r = rel_l2(got, ref)
+    assert r < 2e-3, f"wgrad{case}: rel_l2={r:.3e}"   # fp32 accumulate of bf16 products
+
+
+def test_conv_wgrad_s2d_and_per_sample(lib):
+    from oracle import oracle as O
+    ops = _ops(lib)
+    n, c, h, w, cout = 2, 32, 32, 32, 64
+    g = torch.Generator().manual_seed(23)
+    x = bf16_round(torch.randn(n, c, h, w, generator=g))
+    dy = bf16_round(torch.randn(n, cout, h // 2, w // 2, generator=g))
+    ref = torch.nn.grad.conv2d_weight(O.space_to_depth2(x), (cout, 4 * c, 3, 3), dy, 1, 1)
+    got = ops.unpack_wgrad(ops.conv_wgrad(nhwc(x), nhwc(dy), 3, 1, 1, s2d=True), cout, 4 * c, 3).cpu()
+    ops.check_device()
+    assert rel_l2(got, ref) < 2e-3
+    # per-sample gradients (dynamic-kernel contraction input)
+    x2 = bf16_round(torch.randn(3, 64, 16, 16, generator=g))
+    dy2 = bf16_round(torch.randn(3, 64, 16, 16, generator=g))
+    per = ops.conv_wgrad(nhwc(x2), nhwc(dy2), 3, 1, 1, per_sample=True)
+    ops.check_device()
+    for i in range(3):
+        ref_i = torch.nn.grad.conv2d_weight(x2[i:i + 1], (64, 64, 3, 3), dy2[i:i + 1], 1, 1)
+        got_i = ops.unpack_wgrad(per[i].contiguous(), 64, 64, 3).cpu()
+        assert rel_l2(got_i, ref_i) < 2e-3, f"per-sample {i}"
+
+
+# ------------------------------------------------------------------------------------------------
+# stem + memory-bound kernels
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cin,k,stride,pad", [(3, 3, 1, 1), (3, 1, 1, 0), (1, 1, 1, 0), (3, 5, 2, 1)])
+def test_stem_fwd_and_wgrad(lib, cin, k, stride, pad):
+    ops = _ops(lib)
+    from multimodal_uav_det_b200._lib import EPI_STATS
+    g = torch.Generator().manual_seed(31)
+    x = torch.rand(2, cin, 40, 36, generator=g)
+    wt = torch.randn(32, cin, k, k, generator=g)
+    ref = F.conv2d(x, wt, None, stride, pad)
+    s1 = torch.zeros(32, device=DEV)
+    s2 = torch.zeros(32, device=DEV)
+    y = ops.stem_fwd(x.to(DEV), wt.to(DEV), k, stride, pad, epi=EPI_STATS, sum_=s1, sumsq=s2)
+    assert_close_bf16(to_nchw(y), ref, "stem raw", rel=4e-3)
+    torch.testing.assert_close(s1.cpu(), ref.sum(dim=(0, 2, 3)), rtol=1e-3, atol=1e-2)
+    torch.testing.assert_close(s2.cpu(), (ref * ref).sum(dim=(0, 2, 3)), rtol=1e-3, atol=1e-2)
+    y2 = ops.stem_fwd(x.to(DEV), wt.to(DEV), k, stride, pad, act="silu", scale=torch.full((32,), 0.5, device=DEV),
+                      shift=torch.full((32,), 0.1, device=DEV))
+    assert_close_bf16(to_nchw(y2), F.silu(ref * 0.5 + 0.1), "stem affine", rel=4e-3)
+    dy = bf16_round(torch.randn(ref.shape, generator=g))
+    gw = ops.stem_wgrad(x.to(DEV), nhwc(dy), k, stride, pad).cpu()
+    ref_gw = torch.nn.grad.conv2d_weight(x, wt.shape, dy, stride, pad)
+    assert rel_l2(gw, ref_gw) < 1e-3
+
+
+@pytest.mark.parametrize("act", ["leaky", "silu", "relu"])
+@pytest.mark.parametrize("c", [32, 64, 192, 1024])
+def test_bn_act_train_fwd_bwd(lib, act, c):
+    """Two-phase train-mode BN + activation (+residual) against autograd on the CPU."""
+    ops = _ops(lib)
+    n, h, w = 2, 10, 12
+    g = torch.Generator().manual_seed(41 + c)
+    raw = bf16_round(torch.randn(n, c, h, w, generator=g) * 2 + 0.3).requires_grad_(True)
+    gamma = (torch.rand(c, generator=g) + 0.5).requires_grad_(True)
+    beta = (torch.randn(c, generator=g) * 0.2).requires_grad_(True)
+    res = bf16_round(torch.randn(n, c, h, w, generator=g))
+    rm, rv = torch.zeros(c), torch.ones(c)
+    fn = {"leaky": lambda t: F.leaky_relu(t, 0.1), "silu": F.silu, "relu": F.relu}[act]
+    out_ref = fn(F.batch_norm(raw, rm, rv, gamma, beta, True, 0.1, 1e-5)) + res
+    dy = bf16_round(torch.randn(n, c, h, w, generator=g))
+    out_ref.backward(dy)
+    # GPU
+    raw_d = nhwc(raw.detach())
+    s1 = raw.detach().sum(dim=(0, 2, 3)).to(DEV)
+    s2 = (raw.detach() ** 2).sum(dim=(0, 2, 3)).to(DEV)
+    rm_d, rv_d = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    mean, invstd, scale, shift = ops.bn_finalize(s1, s2, n * h * w, 1e-5, 0.1, gamma.detach().to(DEV),
+                                                 beta.detach().to(DEV), rm_d, rv_d)
+    torch.testing.assert_close(rm_d.cpu(), rm, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(rv_d.cpu(), rv, rtol=1e-4, atol=1e-5)
+    y = ops.bn_act_fwd(raw_d, scale, shift, act, res=nhwc(res))
+    assert_close_bf16(to_nchw(y), out_ref.detach(), "bn_act_fwd")
+    d_raw, dgamma, dbeta = ops.bn_act_bwd(nhwc(dy), raw_d, scale, shift, mean, invstd, gamma.detach().to(DEV), act)
+    assert_close_bf16(to_nchw(d_raw), raw.grad, "bn d_raw", rel=1e-2, frac=2.0 ** -5)
+    torch.testing.assert_close(dgamma.cpu(), gamma.grad, rtol=5e-3, atol=5e-2)
+    torch.testing.assert_close(dbeta.cpu(), beta.grad, rtol=5e-3, atol=5e-2)
+
+
+def test_upsample_add_layout_gap(lib):
+    ops = _ops(lib)
+    g = torch.Generator().manual_seed(51)
+    x = bf16_round(torch.randn(2, 64, 6, 5, generator=g))
+    buf = torch.zeros(2, 12, 10, 192, dtype=torch.bfloat16, device=DEV)
+    ops.upsample2x_fwd(nhwc(x), out=buf[..., :64])
+    assert torch.equal(to_nchw(buf[..., :64]), F.interpolate(x, scale_factor=2, mode="nearest"))
+    dy = bf16_round(torch.randn(2, 64, 12, 10, generator=g))
+    dx = ops.upsample2x_bwd(nhwc(dy))
+    ref = dy.view(2, 64, 6, 2, 5, 2).sum(dim=(3, 5))
+    assert_close_bf16(to_nchw(dx), ref, "upsample bwd")
+    a, b = bf16_round(torch.randn(2, 64, 6, 5, generator=g)), bf16_round(torch.randn(2, 64, 6, 5, generator=g))
+    assert_close_bf16(to_nchw(ops.add(nhwc(a), nhwc(b))), a + b, "add")
+    assert torch.equal(ops.nhwc_to_nchw_f32(nhwc(a)).cpu(), a)
+    assert torch.equal(to_nchw(ops.nchw_f32_to_nhwc(a.to(DEV))), a)
+    big = bf16_round(torch.randn(3, 64, 20, 20, generator=g))
+    torch.testing.assert_close(ops.gap(nhwc(big)).cpu(), big.mean(dim=(2, 3)), rtol=1e-4, atol=1e-5)
+    from oracle import oracle as O
+    torch.testing.assert_close(ops.gap(nhwc(big), s2d=True).cpu(), O.space_to_depth2(big).mean(dim=(2, 3)),
+                               rtol=1e-4, atol=1e-5)
+    img = torch.rand(3, 3, 20, 20, generator=g)
+    torch.testing.assert_close(ops.gap_nchw(img.to(DEV)).cpu(), img.mean(dim=(2, 3)), rtol=1e-5, atol=1e-6)
+
+
+def test_attention_mlp_softmax(lib):
+    ops = _ops(lib)
+    g = torch.Generator().manual_seed(61)
+    pooled = torch.randn(5, 128, generator=g)
+    w1, w2, b2 = torch.randn(33, 128, generator=g), torch.randn(4, 33, generator=g), torch.randn(4, generator=g)
+    ref = torch.softmax((F.relu(pooled @ w1.t()) @ w2.t() + b2) / 30.0, 1)
+    got = ops.attn_mlp_softmax(pooled.to(DEV), w1.to(DEV), None, w2.to(DEV), b2.to(DEV), 30.0)
+    torch.testing.assert_close(got.cpu(), ref, rtol=1e-4, atol=1e-6)
+
+
+def test_sgd_momentum(lib):
+    ops = _ops(lib)
+    g = torch.Generator().manual_seed(71)
+    p = torch.randn(1003, generator=g)
+    opt_p = p.clone().requires_grad_(True)
+    opt = torch.optim.SGD([opt_p], lr=0.01, momentum=0.7)
+    pd, buf = p.clone().to(DEV), torch.zeros(1003, device=DEV)
+    for step in range(3):
+        gr = torch.randn(1003, generator=g)
+        opt_p.grad = gr.clone()
+        opt.step()
+        ops.sgd_momentum(pd, gr.to(DEV), buf, 0.01, 0.7, first_step=(step == 0))
+    torch.testing.assert_close(pd.cpu(), opt_p.detach(), rtol=1e-6, atol=1e-6)
