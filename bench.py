@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the detector hot path (contract: task prompt §④ / BASELINE.json).
+
+Workload (N=1): configs[1] — "BaselineModel training step bf16 batch 32 on 1xB200, synthetic
+Anti-UAV-shaped pairs": one step = forward (train-mode BN) + YOLO loss + backward + SGD(momentum)
+update on 32 frames (16 RGB+IR pairs) of 3x640x640.  N>1: same per-GPU batch (weak scaling), data
+parallel with bucketed NCCL gradient all-reduce overlapped with backward.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's CPU implementation of the
+same step (oracle port of the reference's ATen-CPU path; the reference itself is pure Python on
+torch and is not present on the GPU box) on the host cores with a bounded batch.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ANCHORS = [[[199, 73], [315, 92], [268, 182]], [[91, 54], [120, 75], [157, 60]], [[29, 23], [48, 30], [67, 38]]]
+HEAD_SCALES = [32, 16, 8]
+LOSS_BAL = dict(obj_scales_w=[0.5, 1.0, 2.0], bbox_w=4.0, objectness_w=1.0, no_obj_w=4.0)
+DARKNET53 = [[32, 3, 1], [64, 3, 2], ["B", 1], [128, 3, 2], ["B", 2], [256, 3, 2], ["B", 8], [512, 3, 2], ["B", 8],
+             [1024, 3, 2], ["B", 4], [512, 1, 1], [1024, 3, 1], ["S"], [256, 1, 1], ["U"], [256, 1, 1], [512, 3, 1],
+             ["S"], [128, 1, 1], ["U"], [128, 1, 1], [256, 3, 1], ["S"]]
+HPARAMS = dict(anchors=ANCHORS, head_scales=HEAD_SCALES, lr=1e-4, lr_scheduler=False, loss_balancing=LOSS_BAL,
+               bbox_loss_fn="ciou", optim=dict(name="SGD", momentum=0.7), layer_config=DARKNET53)
+IMG = 640
+FWD_GFLOP_PER_FRAME = 154.52          # SURVEY.md §6 [probe], 2*MAC, BaselineModel forward
+METRIC = "train_frames_per_sec"
+UNIT = "frames/s"
+
+
+def synth_batch(b, seed=1234):
+    """even index 'RGB' = 3 independent channels, odd 'IR' = one channel replicated x3;
+    one target box per frame, cx,cy~U(120,520), w~U(20,80), h~U(15,55) px."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(b, 3, IMG, IMG, generator=g)
+    x[1::2] = x[1::2, :1].expand(-1, 3, -1, -1)
+    g2 = torch.Generator().manual_seed(1)
+    cxy = torch.rand(b, 2, generator=g2) * 400 + 120
+    w = torch.rand(b, generator=g2) * 60 + 20
+    h = torch.rand(b, generator=g2) * 40 + 15
+    boxes = torch.stack([cxy[:, 0] - w / 2, cxy[:, 1] - h / 2, cxy[:, 0] + w / 2, cxy[:, 1] + h / 2], 1)
+    return x, boxes
+
+
+def encode_targets_stacked(boxes):
+    """Per head (B,A,S,S,5) targets; the encoder is the reference's dataset-side CPU code
+    (dataset/AntiUAVDataset.py:141-185), restated in oracle/ — data preparation, outside the timed
+    region like the reference's DataLoader workers."""
+    import torch
+    from oracle import oracle as O
+    per = [O.encode_targets(boxes[i:i + 1], ANCHORS, HEAD_SCALES, IMG) for i in range(boxes.shape[0])]
+    return [torch.stack([p[h] for p in per]) for h in range(3)]
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampler running during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference / CPU arm
+# ------------------------------------------------------------------------------------------------
+def cpu_train_step_rate(batch, steps, warmup):
+    """The reference's CPU path for the same step (fp32, ATen/MKL-DNN through the oracle's functional
+    restatement of BaselineModel + YOLOHead.compute_metrics + torch.optim.SGD), all host threads."""
+    import torch
+    from oracle import oracle as O
+    from multimodal_uav_det_b200.model import BaselineModel
+    from multimodal_uav_det_b200.utils.datatype import Config
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    model = BaselineModel(hparams=Config(HPARAMS))          # parameter container only (same init)
+    sd = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone())
+          for k, v in model.state_dict().items()}
+    params = [v for v in sd.values() if v.requires_grad]
+    opt = torch.optim.SGD(params, lr=HPARAMS["lr"], momentum=0.7)
+    x, boxes = synth_batch(batch)
+    tg = [O.encode_targets(boxes[i:i + 1], ANCHORS, HEAD_SCALES, IMG) for i in range(batch)]
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        outs = O.darknet_forward(x, sd, DARKNET53, train=True)
+        loss, _, _ = O.yolo_loss(outs, tg, ANCHORS, HEAD_SCALES, LOSS_BAL, "ciou")
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return batch * len(times) / total, total / len(times), float(loss)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    batch = 4
+    fps, sec_per_step, _ = cpu_train_step_rate(batch, args.steps, max(1, min(args.warmup, 1)))
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": max(1, min(args.warmup, 1)), "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BaselineModel train step (fwd+loss+bwd+SGD), 640x640, CPU fp32",
+                   "per_step_batch": batch, "sample": f"batch {batch} per step (bounded sample of the batch-32 workload)"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps of batch {batch} (fwd+loss+bwd+SGD), fp32, {cores} threads"},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+class ConvTimer:
+    """Live per-launch timing of the implicit-GEMM kernel (CUDA events on the launching stream):
+    wraps ops.conv_fwd / ops.conv_dgrad for ONE instrumented step after the timed region."""
+
+    def __init__(self, ops, torch):
+        self.ops, self.torch = ops, torch
+        self.records = []   # (kind, flops, start_event, end_event)
+
+    def __enter__(self):
+        ops, torch = self.ops, self.torch
+        self._orig = (ops.conv_fwd, ops.conv_dgrad, ops.conv_wgrad)
+        rec = self.records
+
+        def timed(fn, kind, flops_of):
+            def wrapper(*a, **k):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                out = fn(*a, **k)
+                e.record()
+                rec.append((kind, flops_of(a, k), s, e))
+                return out
+            return wrapper
+
+        def fwd_flops(a, kw):
+            x, cout, k, stride, pad = a[0], a[2], a[3], a[4], a[5]
+            n, h, w, c = x.shape
+            if kw.get("s2d"):
+                h, w, c = h // 2, w // 2, 4 * c
+            ho, wo = ops.conv_out_hw(h, w, k, stride, pad)
+            return 2.0 * n * ho * wo * cout * c * k * k
+
+        def dgrad_flops(a, kw):
+            dy, cin, k = a[0], a[2], a[3]
+            n, ho, wo, cout = dy.shape
+            return 2.0 * n * ho * wo * cout * cin * k * k
+
+        def wgrad_flops(a, kw):
+            x, dy, k = a[0], a[1], a[2]
+            n, ho, wo, cout = dy.shape
+            cin = x.shape[3] * (4 if kw.get("s2d") else 1)
+            return 2.0 * n * ho * wo * cout * cin * k * k
+
+        ops.conv_fwd = timed(self._orig[0], "igemm", fwd_flops)
+        ops.conv_dgrad = timed(self._orig[1], "igemm", dgrad_flops)
+        ops.conv_wgrad = timed(self._orig[2], "wgrad", wgrad_flops)
+        return self
+
+    def __exit__(self, *exc):
+        self.ops.conv_fwd, self.ops.conv_dgrad, self.ops.conv_wgrad = self._orig
+
+    def summary(self):
+        self.torch.cuda.synchronize()
+        agg = {}
+        for kind, fl, s, e in self.records:
+            a = agg.setdefault(kind, [0.0, 0.0, 0])
+            a[0] += fl
+            a[1] += s.elapsed_time(e) * 1e-3
+            a[2] += 1
+        return {k: {"flops": v[0], "seconds": v[1], "launches": v[2]} for k, v in agg.items()}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from multimodal_uav_det_b200 import build, ops
+    from multimodal_uav_det_b200.model import BaselineModel
+    from multimodal_uav_det_b200.parallel import FlatSGDTrainer
+    from multimodal_uav_det_b200.utils.datatype import BatchData, Config
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if rank == 0:
+        build.build_library()
+    if world > 1:
+        dist.barrier()
+    B = args.batch
+    torch.manual_seed(0)
+    model = BaselineModel(hparams=Config(HPARAMS)).to(dev).train()
+    model.yolo_head.mutate_targets = False      # targets are re-supplied every step (fresh copies)
+    trainer = FlatSGDTrainer(model, lr=HPARAMS["lr"], momentum=0.7)
+    x_host, boxes = synth_batch(B, seed=1234 + rank)
+    tg_host = encode_targets_stacked(boxes)
+    x_pin = x_host.pin_memory()
+    tg_pin = [t.pin_memory() for t in tg_host]
+    x_dev = x_pin.to(dev, non_blocking=True)
+    tg_dev = [t.to(dev, non_blocking=True) for t in tg_pin]
+    h2d_bytes = x_pin.numel() * 4 + sum(t.numel() * 4 for t in tg_pin)
+
+    def step(x, tg):
+        trainer.zero_grad()
+        outs = model(x)
+        loss, _, _, _ = model.yolo_head.compute_metrics(outs, BatchData(image=x, bbox=tg))
+        loss.backward()
+        trainer.step()
+        return loss
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, iters):
+        sync_all()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters):
+            fn()
+        e.record()
+        sync_all()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 3)):
+        loss = step(x_dev, tg_dev)
+    ops.check_device()
+
+    # ---- device-resident timing (value) ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.launch_count()
+    ms = timed(lambda: step(x_dev, tg_dev), args.steps)
+    launches = ops.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    final_loss = float(loss.item())
+
+    # ---- end-to-end timing: pinned host -> device every step, loss read back every step ----
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        xd = x_pin.to(dev, non_blocking=True)
+        td = [t.to(dev, non_blocking=True) for t in tg_pin]
+        l = step(xd, td)
+        loss_host.copy_(l.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the user reads the loss value every step
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+
+    # ---- roofline of the dominant kernel: one instrumented step ----
+    with ConvTimer(ops, torch) as ct:
+        step(x_dev, tg_dev)
+    ksum = ct.summary()
+    ops.check_device()
+
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)     # kernel timed inside a long step
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
+    ig = ksum.get("igemm", {"flops": 0.0, "seconds": 1.0, "launches": 0})
+    wg = ksum.get("wgrad", {"flops": 0.0, "seconds": 1.0, "launches": 0})
+    dom_name, dom = ("igemm_kernel", ig) if ig["seconds"] >= wg["seconds"] else ("wgrad_kernel", wg)
+    achieved = dom["flops"] / dom["seconds"] / 1e12
+    step_s = ms / args.steps * 1e-3
+    frames = B * world
+    value = frames / step_s
+    e2e_value = frames / (ms_e2e / args.steps * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"BaselineModel (Darknet-53) training step: fwd(batch-stat BN)+YOLO ciou loss+bwd+SGD, "
+                               f"batch {B}/GPU ({B // 2} RGB+IR pairs), 3x640x640",
+                   "per_gpu_batch": B, "global_batch": frames, "pairs_per_sec": value / 2,
+                   "l2_policy": "inputs larger than L2: every layer streams >126 MB of activations per step",
+                   "parallelism": f"dp{world}", "final_loss": final_loss},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": dom_name, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                     "launches_per_step": dom["launches"], "kernel_seconds_per_step": dom["seconds"],
+                     "other_kernel": {"name": "wgrad_kernel" if dom_name == "igemm_kernel" else "igemm_kernel",
+                                      "achieved": (wg if dom_name == "igemm_kernel" else ig)["flops"] /
+                                                  (wg if dom_name == "igemm_kernel" else ig)["seconds"] / 1e12,
+                                      "seconds_per_step": (wg if dom_name == "igemm_kernel" else ig)["seconds"]},
+                     "model_flops_utilisation": 3 * FWD_GFLOP_PER_FRAME * 1e9 * B / step_s / 1e12 / peak_tf},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        fps, sec, _ = cpu_train_step_rate(2, 1, 1)
+        line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"1 warm + 1 timed step of batch 2 (fwd+loss+bwd+SGD), fp32, {cores} threads, "
+                                          f"{sec:.1f} s/step"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=None)
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,44 @@
+"""Inference entry point: forward -> fused box decode -> batched NMS, all on the GPU.
+
+The reference has no inference script; its only decode+NMS sequence is the `return_ap` branch of
+`YOLOHead.compute_metrics` (model/_base.py:196-203): per image, decode each head, flatten
+`(a h w)`, cxcywh->xyxy, concatenate the heads, `torchvision.ops.nms(boxes, logits, 0.5)`.
+`detect` reproduces exactly that (boxes stay in per-head grid units, scores are raw logits, no
+score threshold) for the whole batch with 3 decode launches + 1 NMS launch.  `score_floor` is an
+extension: NMS on the subset with score > floor."""
+from __future__ import annotations
+
+from typing import List, NamedTuple
+
+import torch
+
+from . import ops
+
+
+class Detections(NamedTuple):
+    boxes: torch.Tensor       # (B, N, 4) xyxy, all candidates
+    scores: torch.Tensor      # (B, N)
+    keep: torch.Tensor        # (B, N) int64, first keep_count[b] entries valid, score-descending
+    keep_count: torch.Tensor  # (B,) int32
+
+
+@torch.no_grad()
+def postprocess(outs, anchors, head_scales, bbox_loss_fn: str = "ciou", iou_threshold: float = 0.5,
+                score_floor: float = float("-inf")) -> Detections:
+    boxes, scores = ops.decode_yolo(outs, anchors, head_scales, bbox_loss_fn == "ciou")
+    keep, count = ops.nms_batched(boxes, scores, iou_threshold, score_floor)
+    return Detections(boxes, scores, keep, count)
+
+
+@torch.no_grad()
+def detect(model, x: torch.Tensor, iou_threshold: float = 0.5, score_floor: float = float("-inf")) -> Detections:
+    """model: BaselineModel | DyYOLO | DySOEM_SimFPN (anything with `.yolo_head`)."""
+    head = model.yolo_head
+    outs = model(x)
+    return postprocess(outs, head.anchors.tolist(), head.head_scales.tolist(), head.bbox_loss_fn, iou_threshold,
+                       score_floor)
+
+
+def kept_lists(det: Detections) -> List[torch.Tensor]:
+    counts = det.keep_count.tolist()
+    return [det.keep[b, :c] for b, c in enumerate(counts)]

@@ -1,0 +1,135 @@
+"""Data-parallel training plumbing (new work: the reference trains on one GPU).
+
+One process per GPU.  Parameters and gradients are re-homed into a few large flat fp32 arenas
+("buckets", reverse registration order ~ the order backward produces gradients):
+  * `param.data` / `param.grad` become views, so the executor's in-place gradient accumulation,
+    torch optimizers and checkpoints keep working unchanged;
+  * the optimiser step is ONE fused SGD-momentum kernel launch per bucket;
+  * with world_size > 1 each bucket is all-reduced (NCCL, sum) on a side stream as soon as the
+    last gradient of the bucket has been written, overlapping the rest of backward; the 1/world
+    mean is folded into the SGD kernel's `grad_scale`.  BatchNorm statistics stay per replica,
+    matching Lightning's default DDP for this model (no SyncBN in the reference).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .engine import bump_param_epoch
+
+
+class _Bucket:
+    def __init__(self, params: List[torch.nn.Parameter], device):
+        self.params = params
+        self.offsets = []
+        off = 0
+        for p in params:
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4          # keep every view 16-byte aligned
+        self.numel = off
+        self.param = torch.zeros(off, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=device)
+        self.momentum = torch.zeros(off, dtype=torch.float32, device=device)
+        self.pending = 0
+        self.work = None
+        for p, o in zip(params, self.offsets):
+            view = self.param[o:o + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+
+class FlatSGDTrainer:
+    """Flat-arena SGD(momentum) + bucketed gradient all-reduce for one model replica."""
+
+    def __init__(self, model: torch.nn.Module, lr: float, momentum: float, bucket_mb: float = 32.0,
+                 process_group=None):
+        self.model = model
+        self.lr, self.momentum = lr, momentum
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        params = [p for p in model.parameters() if p.requires_grad]
+        device = params[0].device
+        cap = int(bucket_mb * 1024 * 1024 / 4)
+        self.buckets: List[_Bucket] = []
+        cur, cur_n = [], 0
+        for p in reversed(params):
+            if cur and cur_n + p.numel() > cap:
+                self.buckets.append(_Bucket(cur, device))
+                cur, cur_n = [], 0
+            cur.append(p)
+            cur_n += p.numel()
+        if cur:
+            self.buckets.append(_Bucket(cur, device))
+        self._bucket_of: Dict[int, _Bucket] = {id(p): b for b in self.buckets for p in b.params}
+        self._first = True
+        self._comm_stream = torch.cuda.Stream(device=device) if (self.world > 1 and device.type == "cuda") else None
+        self._device = device
+        bump_param_epoch()
+        execs = [m._exec for m in model.modules() if hasattr(m, "_exec") and hasattr(m, "_forward_program")]
+        for ex in execs:
+            ex.grad_ready_hook = self._on_grad_ready
+        self._arm()
+
+    # ---- gradient lifecycle ------------------------------------------------------------------
+    def _arm(self):
+        for b in self.buckets:
+            b.pending = len(b.params)
+            b.work = None
+
+    def zero_grad(self):
+        for b in self.buckets:
+            b.grad.zero_()
+            for p, o in zip(b.params, b.offsets):      # re-attach if someone set grads to None
+                if p.grad is None or p.grad.data_ptr() != b.grad.data_ptr() + 4 * o:
+                    p.grad = b.grad[o:o + p.numel()].view(p.shape)
+        self._arm()
+
+    def _on_grad_ready(self, p):
+        b = self._bucket_of.get(id(p))
+        if b is None:
+            return
+        b.pending -= 1
+        if b.pending == 0 and self.world > 1:
+            self._launch_reduce(b)
+
+    def _launch_reduce(self, b: _Bucket):
+        if self._comm_stream is not None:
+            self._comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._comm_stream):
+                b.work = dist.all_reduce(b.grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        else:  # gloo / CPU tests
+            b.work = dist.all_reduce(b.grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def finish_reduce(self):
+        """Reduce any bucket whose hook did not fire (unused parameters) and join the side stream."""
+        if self.world == 1:
+            return
+        for b in self.buckets:
+            if b.work is None:
+                self._launch_reduce(b)
+        for b in self.buckets:
+            b.work.wait()
+        if self._comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+
+    # ---- optimiser ----------------------------------------------------------------------------
+    def step(self):
+        """All-reduce join + fused SGD(momentum) on every bucket (torch.optim.SGD semantics,
+        reference _base.py:292-293; gradient averaged over the data-parallel world)."""
+        self.finish_reduce()
+        scale = 1.0 / self.world
+        for b in self.buckets:
+            if b.param.is_cuda:
+                ops.sgd_momentum(b.param, b.grad, b.momentum, self.lr, self.momentum, grad_scale=scale,
+                                 first_step=self._first)
+            else:  # host-side logic tests (gloo): same arithmetic in torch
+                g = b.grad * scale
+                b.momentum.copy_(g if self._first else self.momentum * b.momentum + g)
+                b.param.add_(b.momentum, alpha=-self.lr)
+        self._first = False
+        bump_param_epoch()
+        self._arm()

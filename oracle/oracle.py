@@ -216,7 +216,7 @@ def yolo_head(feats, sd, p="yolo_head.detection_head"):
     return outs
 
 
-def darknet_forward(x, sd, layer_config, attn_temperature=None, train=False, taps=None):
+def darknet_forward(x, sd, layer_config, attn_temperature=None, train=False, taps=None, route_repeats=8):
     """BaselineModel.forward / DyYOLO.forward (BaselineModel.py:105-124, DyYOLO.py:122-144).
     Returns per-head (bbox, obj).  `taps`, if a dict, receives named intermediate tensors."""
     idx = 0
@@ -225,7 +225,7 @@ def darknet_forward(x, sd, layer_config, attn_temperature=None, train=False, tap
         kind = entry[0]
         if kind == "B":
             x = residual_block(x, sd, f"layers.{idx}", entry[1], True, train)
-            if entry[1] == 8:
+            if entry[1] == route_repeats:   # the reference hard-codes 8 (BaselineModel.py:116)
                 routes.append(x)
             idx += 1
         elif kind == "S":
