@@ -289,6 +289,17 @@ def run_ours(args, rank, world, local_rank):
         loss = step(x_dev, tg_dev)
     ops.check_device()
 
+    if args.profile_step:
+        # ncu --profile-from-start off: exactly one warm training step between start/stop
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(x_dev, tg_dev)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        if rank == 0:
+            print(json.dumps({"profile_step": "done", "launches_total": ops.launch_count()}))
+        return
+
     # ---- device-resident timing (value) ----
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -375,6 +386,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true", help="run one step inside cudaProfilerStart/Stop and exit")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -162,15 +162,20 @@ int uavdet_bn_finalize(const float* sum, const float* sumsq, int c, double count
 /* y = act(raw*scale+shift) (+res).  raw,y,res: NHWC bf16 views of equal n,h,w,c.          */
 int uavdet_bn_act_fwd(const uavdet_act* raw, const float* scale, const float* shift, int act,
                       const uavdet_act* res, const uavdet_act* y, void* stream);
-/* backward phase 1: dz = dy*act'(raw*scale+shift); sum_dz[c] += dz; sum_dzx[c] += dz*xhat. */
+/* backward phase 1: dz = dy*act'(raw*scale+shift); sum_dz[c] += dz; sum_dzr[c] += dz*raw (fp32 atomics,
+ * caller-zeroed). */
 int uavdet_bn_act_bwd_reduce(const uavdet_act* dy, const uavdet_act* raw, const float* scale,
-                             const float* shift, const float* mean, const float* invstd,
-                             int act, float* sum_dz, float* sum_dzx, void* stream);
-/* backward phase 2: d_raw = gamma*invstd*(dz - sum_dz/M - xhat*sum_dzx/M).               */
+                             const float* shift, int act, float* sum_dz, float* sum_dzr, void* stream);
+/* per channel: dgamma = invstd*(sum_dzr - mean*sum_dz), dbeta = sum_dz and the folded phase-2
+ * coefficients k1 = -scale*invstd*dgamma/M, k0 = -scale*dbeta/M - k1*mean  (M = count).             */
+int uavdet_bn_bwd_finalize(const float* sum_dz, const float* sum_dzr, const float* mean,
+                           const float* invstd, const float* scale, int c, double count, float* dgamma,
+                           float* dbeta, float* k1, float* k0, void* stream);
+/* backward phase 2: d_raw = scale*dz + k1*raw + k0
+ * (= gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)), the autograd of nn.BatchNorm2d in training). */
 int uavdet_bn_act_bwd_apply(const uavdet_act* dy, const uavdet_act* raw, const float* scale,
-                            const float* shift, const float* mean, const float* invstd,
-                            const float* gamma, int act, const float* sum_dz,
-                            const float* sum_dzx, const uavdet_act* d_raw, void* stream);
+                            const float* shift, const float* k1, const float* k0, int act,
+                            const uavdet_act* d_raw, void* stream);
 /* eval-mode / bias-only activation backward: dx = dy*act'(raw*scale+shift)*scale.         */
 int uavdet_act_bwd(const uavdet_act* dy, const uavdet_act* raw, const float* scale,
                    const float* shift, int act, const uavdet_act* dx, void* stream);

@@ -75,115 +75,193 @@ __global__ void bn_finalize_kernel(const float* sum, const float* sumsq, int c, 
   }
 }
 
-// ---- y = act(raw*scale+shift) (+res) -------------------------------------------------------
-__global__ void bn_act_fwd_kernel(View raw, const float* __restrict__ scale, const float* __restrict__ shift,
-                                  int act, const __nv_bfloat16* __restrict__ res, int res_ld, View y) {
-  const int c8 = raw.c >> 3;
-  const long long total = raw.npix * c8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long px = i / c8;
-    const int c = (int)(i - px * c8) << 3;
-    float v[8], s[8], t[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(raw.p + px * raw.ld + c)), v);
-    if (scale) load8f(scale + c, s);
-    if (shift) load8f(shift + c, t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float z = v[j];
-      if (scale) z *= s[j];
-      if (shift) z += t[j];
-      v[j] = act_fwd_rt(act, z);
-    }
-    if (res) {
-      float r[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(res + px * res_ld + c)), r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += r[j];
-    }
-    *reinterpret_cast<uint4*>(y.p + px * y.ld + c) = pack8(v);
-  }
-}
-
-// ---- BN backward, phase 1: per-channel sums of dz and dz*xhat ---------------------------------
-// grid = (pixel blocks, channel chunks of 256).  blockDim 256: Gb = min(c/8, 32) channel groups x
-// PL pixel lanes; coalesced 16 B per thread, Gb*16 B contiguous per pixel.
-__global__ void bn_bwd_reduce_kernel(View dy, View raw, const float* __restrict__ scale,
-                                     const float* __restrict__ shift, const float* __restrict__ mean,
-                                     const float* __restrict__ invstd, int act, float* __restrict__ sum_dz,
-                                     float* __restrict__ sum_dzx) {
-  __shared__ float red[256 * 16];
-  const int G = dy.c >> 3;
+// ---- streaming skeleton ---------------------------------------------------------------------
+// blockDim 256 = Gb channel groups (8 channels = 16 B each) x PL pixel lanes; a thread keeps its
+// channel group for the whole kernel, so per-channel parameters are loaded once, and walks pixels
+// with a 4x unrolled grid-stride loop (4 independent 16 B loads per operand in flight).
+struct PixLane {
+  int c;            // first channel of this thread's group
+  long long px0;    // first pixel
+  long long step;   // pixel stride of the loop
+  bool active;
+};
+__device__ __forceinline__ PixLane pix_lane(int channels) {
+  const int G = channels >> 3;
   const int Gb = G < 32 ? G : 32;
   const int PL = 256 / Gb;
   const int g = threadIdx.x % Gb + blockIdx.y * Gb;
   const int pl = threadIdx.x / Gb;
-  float a_dz[8], a_dzx[8];
+  PixLane L;
+  L.c = g << 3;
+  L.px0 = (long long)blockIdx.x * PL + pl;
+  L.step = (long long)gridDim.x * PL;
+  L.active = g < G && pl < PL;
+  return L;
+}
+static dim3 stream_grid(const uavdet_act* v, int unroll) {
+  int G = v->c / 8, Gb = G < 32 ? G : 32, PL = 256 / Gb;
+  long long npix = (long long)v->n * v->h * v->w;
+  long long bx = (npix + (long long)PL * unroll - 1) / ((long long)PL * unroll);
+  long long cap = ((long long)kNumSMs * 16) / ceil_div(G, Gb);
+  if (cap < kNumSMs) cap = kNumSMs;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  return dim3((unsigned)bx, (unsigned)ceil_div(G, Gb), 1);
+}
+
+// ---- y = act(raw*scale+shift) (+res) -------------------------------------------------------
+template <bool HAS_RES>
+__global__ void __launch_bounds__(256)
+bn_act_fwd_kernel(View raw, const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                  const __nv_bfloat16* __restrict__ res, int res_ld, View y) {
+  const PixLane L = pix_lane(raw.c);
+  if (!L.active) return;
+  float s[8], t[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { a_dz[j] = 0.f; a_dzx[j] = 0.f; }
-  if (g < G && pl < PL) {
-    const int c = g << 3;
-    float s[8], t[8], m[8], is[8];
-    load8f(scale + c, s); load8f(shift + c, t); load8f(mean + c, m); load8f(invstd + c, is);
-    for (long long px = (long long)blockIdx.x * PL + pl; px < dy.npix; px += (long long)gridDim.x * PL) {
+  for (int j = 0; j < 8; ++j) { s[j] = 1.f; t[j] = 0.f; }
+  if (scale) load8f(scale + L.c, s);
+  if (shift) load8f(shift + L.c, t);
+  auto body = [&](const uint4& in, const uint4& rin, long long px) {
+    float v[8];
+    unpack8(in, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = act_fwd_rt(act, fmaf(v[j], s[j], t[j]));
+    if (HAS_RES) {
+      float r[8];
+      unpack8(rin, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+    *reinterpret_cast<uint4*>(y.p + px * y.ld + L.c) = pack8(v);
+  };
+  long long px = L.px0;
+  for (; px + 3 * L.step < raw.npix; px += 4 * L.step) {
+    uint4 a[4], r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      a[u] = __ldg(reinterpret_cast<const uint4*>(raw.p + (px + u * L.step) * raw.ld + L.c));
+      if (HAS_RES) r[u] = __ldg(reinterpret_cast<const uint4*>(res + (px + u * L.step) * res_ld + L.c));
+      else r[u] = make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) body(a[u], r[u], px + u * L.step);
+  }
+  for (; px < raw.npix; px += L.step) {
+    uint4 a = __ldg(reinterpret_cast<const uint4*>(raw.p + px * raw.ld + L.c));
+    uint4 r = make_uint4(0, 0, 0, 0);
+    if (HAS_RES) r = __ldg(reinterpret_cast<const uint4*>(res + px * res_ld + L.c));
+    body(a, r, px);
+  }
+}
+
+// ---- BN backward, phase 1: per-channel sums of dz and dz*raw ---------------------------------
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(View dy, View raw, const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                     float* __restrict__ sum_dz, float* __restrict__ sum_dzr) {
+  __shared__ float red[256 * 16];
+  const PixLane L = pix_lane(dy.c);
+  float a_dz[8], a_dzr[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a_dz[j] = 0.f; a_dzr[j] = 0.f; }
+  if (L.active) {
+    float s[8], t[8];
+    load8f(scale + L.c, s);
+    load8f(shift + L.c, t);
+    auto body = [&](const uint4& din, const uint4& rin) {
       float d[8], r[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(dy.p + px * dy.ld + c)), d);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(raw.p + px * raw.ld + c)), r);
+      unpack8(din, d);
+      unpack8(rin, r);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float z = r[j] * s[j] + t[j];
-        float dz = d[j] * act_grad_rt(act, z);
+        const float dz = d[j] * act_grad_rt(act, fmaf(r[j], s[j], t[j]));
         a_dz[j] += dz;
-        a_dzx[j] += dz * ((r[j] - m[j]) * is[j]);
+        a_dzr[j] = fmaf(dz, r[j], a_dzr[j]);
       }
+    };
+    long long px = L.px0;
+    for (; px + 3 * L.step < dy.npix; px += 4 * L.step) {
+      uint4 a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a[u] = __ldg(reinterpret_cast<const uint4*>(dy.p + (px + u * L.step) * dy.ld + L.c));
+        b[u] = __ldg(reinterpret_cast<const uint4*>(raw.p + (px + u * L.step) * raw.ld + L.c));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) body(a[u], b[u]);
     }
+    for (; px < dy.npix; px += L.step)
+      body(__ldg(reinterpret_cast<const uint4*>(dy.p + px * dy.ld + L.c)),
+           __ldg(reinterpret_cast<const uint4*>(raw.p + px * raw.ld + L.c)));
   }
   // block reduce over pixel lanes
+  const int G = dy.c >> 3;
+  const int Gb = G < 32 ? G : 32;
+  const int PL = 256 / Gb;
   float* mine = red + threadIdx.x * 16;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { mine[j] = a_dz[j]; mine[8 + j] = a_dzx[j]; }
+  for (int j = 0; j < 8; ++j) { mine[j] = a_dz[j]; mine[8 + j] = a_dzr[j]; }
   __syncthreads();
-  // thread t < Gb*16 sums column (group t/16, slot t%16) over PL lanes
   for (int t = threadIdx.x; t < Gb * 16; t += 256) {
     const int gg = t >> 4, slot = t & 15;
     float acc = 0.f;
     for (int l = 0; l < PL; ++l) acc += red[(l * Gb + gg) * 16 + slot];
-    const int gch = (gg + blockIdx.y * Gb);
-    if (gch < G) {
-      const int c = (gch << 3) + (slot & 7);
-      atomicAdd((slot < 8 ? sum_dz : sum_dzx) + c, acc);
-    }
+    const int gch = gg + blockIdx.y * Gb;
+    if (gch < G) atomicAdd((slot < 8 ? sum_dz : sum_dzr) + (gch << 3) + (slot & 7), acc);
   }
 }
 
+// per channel: dgamma, dbeta and the folded coefficients of phase 2
+//   d_raw = scale*dz + k1*raw + k0,  k1 = -scale*invstd*dgamma/M,  k0 = -scale*dbeta/M - k1*mean
+__global__ void bn_bwd_finalize_kernel(const float* sum_dz, const float* sum_dzr, const float* mean,
+                                       const float* invstd, const float* scale, int c, float inv_count,
+                                       float* dgamma, float* dbeta, float* k1, float* k0) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  const float sd = sum_dz[i];
+  const float dg = invstd[i] * (sum_dzr[i] - mean[i] * sd);
+  dgamma[i] = dg;
+  dbeta[i] = sd;
+  const float a1 = -scale[i] * invstd[i] * dg * inv_count;
+  k1[i] = a1;
+  k0[i] = -scale[i] * sd * inv_count - a1 * mean[i];
+}
+
 // ---- BN backward, phase 2 ----------------------------------------------------------------------
-__global__ void bn_bwd_apply_kernel(View dy, View raw, const float* __restrict__ scale,
-                                    const float* __restrict__ shift, const float* __restrict__ mean,
-                                    const float* __restrict__ invstd, const float* __restrict__ gamma, int act,
-                                    const float* __restrict__ sum_dz, const float* __restrict__ sum_dzx,
-                                    float inv_count, View dr) {
-  const int c8 = dy.c >> 3;
-  const long long total = dy.npix * c8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long px = i / c8;
-    const int c = (int)(i - px * c8) << 3;
-    float d[8], r[8], s[8], t[8], m[8], is[8], g[8], sd[8], sx[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(dy.p + px * dy.ld + c)), d);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(raw.p + px * raw.ld + c)), r);
-    load8f(scale + c, s); load8f(shift + c, t); load8f(mean + c, m); load8f(invstd + c, is);
-    load8f(sum_dz + c, sd); load8f(sum_dzx + c, sx);
-    if (gamma) load8f(gamma + c, g);
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(View dy, View raw, const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ k1, const float* __restrict__ k0, int act, View dr) {
+  const PixLane L = pix_lane(dy.c);
+  if (!L.active) return;
+  float s[8], t[8], a1[8], a0[8];
+  load8f(scale + L.c, s);
+  load8f(shift + L.c, t);
+  load8f(k1 + L.c, a1);
+  load8f(k0 + L.c, a0);
+  auto body = [&](const uint4& din, const uint4& rin, long long px) {
+    float d[8], r[8];
+    unpack8(din, d);
+    unpack8(rin, r);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float z = r[j] * s[j] + t[j];
-      float dz = d[j] * act_grad_rt(act, z);
-      float xh = (r[j] - m[j]) * is[j];
-      float gg = gamma ? g[j] : 1.f;
-      d[j] = gg * is[j] * (dz - sd[j] * inv_count - xh * sx[j] * inv_count);
+      const float dz = d[j] * act_grad_rt(act, fmaf(r[j], s[j], t[j]));
+      d[j] = fmaf(s[j], dz, fmaf(a1[j], r[j], a0[j]));
     }
-    *reinterpret_cast<uint4*>(dr.p + px * dr.ld + c) = pack8(d);
+    *reinterpret_cast<uint4*>(dr.p + px * dr.ld + L.c) = pack8(d);
+  };
+  long long px = L.px0;
+  for (; px + 3 * L.step < dy.npix; px += 4 * L.step) {
+    uint4 a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      a[u] = __ldg(reinterpret_cast<const uint4*>(dy.p + (px + u * L.step) * dy.ld + L.c));
+      b[u] = __ldg(reinterpret_cast<const uint4*>(raw.p + (px + u * L.step) * raw.ld + L.c));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) body(a[u], b[u], px + u * L.step);
   }
+  for (; px < dy.npix; px += L.step)
+    body(__ldg(reinterpret_cast<const uint4*>(dy.p + px * dy.ld + L.c)),
+         __ldg(reinterpret_cast<const uint4*>(raw.p + px * raw.ld + L.c)), px);
 }
 
 __global__ void act_bwd_kernel(View dy, View raw, const float* __restrict__ scale,
@@ -516,49 +594,52 @@ extern "C" int uavdet_bn_act_fwd(const uavdet_act* raw, const float* scale, cons
     return rc;
   if (res && ((rc = check_view(res, "bn_act_fwd res")) || (rc = same_shape(raw, res, "bn_act_fwd res")))) return rc;
   View r = mkview(raw), o = mkview(y);
-  bn_act_fwd_kernel<<<ew_grid(r.npix * (r.c / 8), 256), 256, 0, ST>>>(
-      r, scale, shift, act, res ? (const __nv_bfloat16*)res->ptr : nullptr, res ? res->ld : 0, o);
+  if (r.npix == 0) return UAVDET_OK;
+  dim3 grid = stream_grid(raw, 8);
+  if (res)
+    bn_act_fwd_kernel<true><<<grid, 256, 0, ST>>>(r, scale, shift, act, (const __nv_bfloat16*)res->ptr, res->ld, o);
+  else
+    bn_act_fwd_kernel<false><<<grid, 256, 0, ST>>>(r, scale, shift, act, nullptr, 0, o);
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }
 
-static dim3 reduce_grid(const uavdet_act* v, int* PL_out) {
-  int G = v->c / 8, Gb = G < 32 ? G : 32, PL = 256 / Gb;
-  long long npix = (long long)v->n * v->h * v->w;
-  long long bx = (npix + (long long)PL * 16 - 1) / ((long long)PL * 16);
-  if (bx > kNumSMs * 8) bx = kNumSMs * 8;
-  if (bx < 1) bx = 1;
-  if (PL_out) *PL_out = PL;
-  return dim3((unsigned)bx, (unsigned)ceil_div(G, Gb), 1);
-}
-
 extern "C" int uavdet_bn_act_bwd_reduce(const uavdet_act* dy, const uavdet_act* raw, const float* scale,
-                                        const float* shift, const float* mean, const float* invstd, int act,
-                                        float* sum_dz, float* sum_dzx, void* stream) {
+                                        const float* shift, int act, float* sum_dz, float* sum_dzr,
+                                        void* stream) {
   int rc;
   if ((rc = check_view(dy, "bn_bwd_reduce dy")) || (rc = check_view(raw, "bn_bwd_reduce raw")) ||
       (rc = same_shape(dy, raw, "bn_bwd_reduce")))
     return rc;
-  UAVDET_CHECK_ARG(scale && shift && mean && invstd && sum_dz && sum_dzx, "bn_bwd_reduce: null stats");
-  bn_bwd_reduce_kernel<<<reduce_grid(dy, nullptr), 256, 0, ST>>>(mkview(dy), mkview(raw), scale, shift, mean,
-                                                                   invstd, act, sum_dz, sum_dzx);
+  UAVDET_CHECK_ARG(scale && shift && sum_dz && sum_dzr, "bn_bwd_reduce: null stats");
+  bn_bwd_reduce_kernel<<<stream_grid(dy, 16), 256, 0, ST>>>(mkview(dy), mkview(raw), scale, shift, act, sum_dz,
+                                                            sum_dzr);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_bn_bwd_finalize(const float* sum_dz, const float* sum_dzr, const float* mean,
+                                      const float* invstd, const float* scale, int c, double count, float* dgamma,
+                                      float* dbeta, float* k1, float* k0, void* stream) {
+  UAVDET_CHECK_ARG(sum_dz && sum_dzr && mean && invstd && scale && dgamma && dbeta && k1 && k0 && c > 0 && count > 0,
+                   "bn_bwd_finalize: bad arguments");
+  bn_bwd_finalize_kernel<<<ceil_div(c, 128), 128, 0, ST>>>(sum_dz, sum_dzr, mean, invstd, scale, c,
+                                                           (float)(1.0 / count), dgamma, dbeta, k1, k0);
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }
 
 extern "C" int uavdet_bn_act_bwd_apply(const uavdet_act* dy, const uavdet_act* raw, const float* scale,
-                                       const float* shift, const float* mean, const float* invstd,
-                                       const float* gamma, int act, const float* sum_dz, const float* sum_dzx,
+                                       const float* shift, const float* k1, const float* k0, int act,
                                        const uavdet_act* d_raw, void* stream) {
   int rc;
   if ((rc = check_view(dy, "bn_bwd_apply dy")) || (rc = check_view(raw, "bn_bwd_apply raw")) ||
       (rc = check_view(d_raw, "bn_bwd_apply d_raw")) || (rc = same_shape(dy, raw, "bn_bwd_apply")) ||
       (rc = same_shape(dy, d_raw, "bn_bwd_apply")))
     return rc;
-  View d = mkview(dy);
-  bn_bwd_apply_kernel<<<ew_grid(d.npix * (d.c / 8), 256), 256, 0, ST>>>(
-      d, mkview(raw), scale, shift, mean, invstd, gamma, act, sum_dz, sum_dzx, 1.f / (float)d.npix,
-      mkview(d_raw));
+  UAVDET_CHECK_ARG(scale && shift && k1 && k0, "bn_bwd_apply: null coefficients");
+  bn_bwd_apply_kernel<<<stream_grid(dy, 8), 256, 0, ST>>>(mkview(dy), mkview(raw), scale, shift, k1, k0, act,
+                                                          mkview(d_raw));
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }

@@ -114,45 +114,89 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(StemParams P) {
   }
 }
 
-// dW[co][ci][kh][kw] += sum_p dy[p][co] * x[p + tap][ci]; lane = co, a warp walks pixels.
-// per_sample: one gradient per image ([n][32][K]) for the dynamic-kernel stem (DyYOLO layer 0).
-__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, int n, int cin, int h, int w,
-                                                         const __nv_bfloat16* __restrict__ dy, long long dy_ld,
-                                                         int k, int stride, int pad, int ho, int wo,
-                                                         float* __restrict__ grad, int per_sample) {
-  __shared__ float red[kStemMaxK * kStemCout];
+// dW[co][ci][kh][kw] += sum_p dy[p][co] * x[p + tap][ci]   (fp32 CUDA cores: K <= 75, the layer is
+// bound by streaming dy once).  Persistent blocks walk 32x8 output-pixel tiles; the fp32 input patch
+// (with halo) and the bf16 dy tile are staged in shared memory; thread (warp w, lane l) owns the
+// output-channel pair 2*(l%16) and the taps {16*j + 2*w + l/16}: dy reads are conflict-free, x reads
+// are broadcasts, and the 2 x TPG accumulators stay in registers across all tiles of the block.
+constexpr int kSwTileW = 32, kSwTileH = 8, kSwThreads = 256, kSwMaxTpg = 5;
+
+template <int TPG>
+__global__ void __launch_bounds__(kSwThreads) stem_wgrad_kernel(const float* __restrict__ x, int n, int cin, int h,
+                                                                int w, const __nv_bfloat16* __restrict__ dy,
+                                                                long long dy_ld, int k, int stride, int pad, int ho,
+                                                                int wo, float* __restrict__ grad, int per_sample) {
+  extern __shared__ float sw_smem[];
   const int K = cin * k * k;
-  const int img = blockIdx.y;
-  for (int i = threadIdx.x; i < K * kStemCout; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  float acc[kStemMaxK];
+  const int pw = (kSwTileW - 1) * stride + k, ph = (kSwTileH - 1) * stride + k;  // input patch
+  float* xs = sw_smem;                                                            // [cin][ph][pw]
+  uint32_t* dys = reinterpret_cast<uint32_t*>(sw_smem + ((cin * ph * pw + 3) & ~3));  // [256 px][16 co pairs], 16 B aligned
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cp = lane & 15;                    // output-channel pair
+  const int slot = 2 * warp + (lane >> 4);     // 0..15
+  // per-thread taps and their patch offsets
+  int tap_off[TPG];
+  bool tap_ok[TPG];
 #pragma unroll
-  for (int i = 0; i < kStemMaxK; ++i) acc[i] = 0.f;
-  const long long hw_out = (long long)ho * wo;
-  const float* xin = x + (long long)img * cin * h * w;
-  for (long long p = (long long)blockIdx.x * nw + warp; p < hw_out; p += (long long)gridDim.x * nw) {
-    const int oy = (int)(p / wo), ox = (int)(p - (long long)oy * wo);
-    const float g = __bfloat162float(dy[((long long)img * hw_out + p) * dy_ld + lane]);
-    int kk = 0;
-    for (int ci = 0; ci < cin; ++ci)
-      for (int kh = 0; kh < k; ++kh) {
-        const int iy = oy * stride + kh - pad;
-        for (int kw = 0; kw < k; ++kw, ++kk) {
-          const int ix = ox * stride + kw - pad;
-          float xv = 0.f;
-          if (iy >= 0 && iy < h && ix >= 0 && ix < w) xv = __ldg(xin + ((long long)ci * h + iy) * w + ix);
-          // kk is a loop counter over <= 75 taps: keep the accumulators addressable
-          acc[kk] = fmaf(g, xv, acc[kk]);
-        }
-      }
+  for (int j = 0; j < TPG; ++j) {
+    const int t = 16 * j + slot;               // tap id = (ci*k + kh)*k + kw
+    tap_ok[j] = t < K;
+    const int tt = tap_ok[j] ? t : 0;
+    const int ci = tt / (k * k), r = tt - ci * k * k, kh = r / k, kw = r - kh * k;
+    tap_off[j] = (ci * ph + kh) * pw + kw;
   }
-  for (int kk = 0; kk < K; ++kk) atomicAdd(&red[kk * kStemCout + lane], acc[kk]);
-  __syncthreads();
-  float* gdst = grad + (per_sample ? (long long)img * kStemCout * K : 0);
-  for (int i = threadIdx.x; i < K * kStemCout; i += blockDim.x) {
-    const int co = i % kStemCout, kk = i / kStemCout;
-    atomicAdd(gdst + co * K + kk, red[i]);
+  float acc0[TPG], acc1[TPG];
+#pragma unroll
+  for (int j = 0; j < TPG; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+
+  const int tiles_w = (wo + kSwTileW - 1) / kSwTileW, tiles_h = (ho + kSwTileH - 1) / kSwTileH;
+  const int tiles_img = tiles_w * tiles_h;
+  const int img_lo = per_sample ? blockIdx.y : 0, img_hi = per_sample ? blockIdx.y + 1 : n;
+  const long long total = (long long)(img_hi - img_lo) * tiles_img;
+  for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int img = img_lo + (int)(tile / tiles_img);
+    const int tr = (int)(tile % tiles_img);
+    const int ty = tr / tiles_w, tx = tr - ty * tiles_w;
+    const int oy0 = ty * kSwTileH, ox0 = tx * kSwTileW;
+    const int iy0 = oy0 * stride - pad, ix0 = ox0 * stride - pad;
+    __syncthreads();  // previous tile fully consumed
+    const float* xin = x + (long long)img * cin * h * w;
+    for (int i = threadIdx.x; i < cin * ph * pw; i += kSwThreads) {
+      const int ci = i / (ph * pw), r = i - ci * ph * pw, yy = r / pw, xx = r - yy * pw;
+      const int iy = iy0 + yy, ix = ix0 + xx;
+      xs[i] = (iy >= 0 && iy < h && ix >= 0 && ix < w) ? __ldg(xin + ((long long)ci * h + iy) * w + ix) : 0.f;
+    }
+    // dy tile: 256 pixels x 32 channels bf16 = 64 B per pixel = 4 x 16 B
+    for (int i = threadIdx.x; i < kSwTileW * kSwTileH * 4; i += kSwThreads) {
+      const int p = i >> 2, q = i & 3;
+      const int oy = oy0 + p / kSwTileW, ox = ox0 + p % kSwTileW;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (oy < ho && ox < wo)
+        v = __ldg(reinterpret_cast<const uint4*>(dy + (((long long)img * ho + oy) * wo + ox) * dy_ld) + q);
+      reinterpret_cast<uint4*>(dys)[i] = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int p = 0; p < kSwTileW * kSwTileH; ++p) {
+      const uint32_t g2 = dys[p * 16 + cp];
+      const float g0 = bf16_lo(g2), g1 = bf16_hi(g2);
+      const int base = ((p / kSwTileW) * stride) * pw + (p % kSwTileW) * stride;
+#pragma unroll
+      for (int j = 0; j < TPG; ++j) {
+        const float xv = xs[base + tap_off[j]];
+        acc0[j] = fmaf(g0, xv, acc0[j]);
+        acc1[j] = fmaf(g1, xv, acc1[j]);
+      }
+    }
+  }
+  float* gdst = grad + (per_sample ? (long long)blockIdx.y * kStemCout * K : 0);
+#pragma unroll
+  for (int j = 0; j < TPG; ++j) {
+    if (tap_ok[j]) {
+      const int t = 16 * j + slot;
+      atomicAdd(gdst + (2 * cp) * K + t, acc0[j]);
+      atomicAdd(gdst + (2 * cp + 1) * K + t, acc1[j]);
+    }
   }
 }
 
@@ -193,15 +237,31 @@ extern "C" int uavdet_stem_wgrad(const float* x_nchw, int n, int cin, int h, int
   UAVDET_CHECK_ARG(dy->c == kStemCout && cin >= 1 && cin <= 3 && cin * k * k <= kStemMaxK, "stem_wgrad: unsupported shape");
   const int per_sample = n < 0 ? 1 : 0;  // n < 0 flags per-sample gradients ([|n|][32][K])
   if (n < 0) n = -n;
-  const long long hw_out = (long long)dy->h * dy->w;
-  int bx = (int)((hw_out + 8 * 64 - 1) / (8 * 64));
-  int cap = (kNumSMs * 8) / (n > 0 ? n : 1) + 1;
-  if (bx > cap) bx = cap;
+  const int K = cin * k * k;
+  const int tpg = (K + 15) / 16;
+  UAVDET_CHECK_ARG(tpg >= 1 && tpg <= kSwMaxTpg, "stem_wgrad: K=%d unsupported", K);
+  UAVDET_CHECK_ARG(dy->ld % 8 == 0 && ((uintptr_t)dy->ptr & 15) == 0, "stem_wgrad: dy alignment");
+  const int pw = (kSwTileW - 1) * stride + k, ph = (kSwTileH - 1) * stride + k;
+  const size_t smem = sizeof(float) * (size_t)((cin * ph * pw + 3) & ~3) + (size_t)kSwTileW * kSwTileH * 64;
+  UAVDET_CHECK_ARG(smem <= 48 * 1024, "stem_wgrad: patch does not fit shared memory");
+  const long long tiles = (long long)ceil_div(dy->w, kSwTileW) * ceil_div(dy->h, kSwTileH) * (per_sample ? 1 : n);
+  int bx = (int)(tiles < (long long)kNumSMs * 4 ? tiles : (long long)kNumSMs * 4);
+  if (per_sample) bx = (int)(tiles < 16 ? tiles : 16);
   if (bx < 1) bx = 1;
-  dim3 grid((unsigned)bx, (unsigned)n);
-  stem_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, n, cin, h, w, (const __nv_bfloat16*)dy->ptr,
-                                                             dy->ld, k, stride, pad, dy->h, dy->w, grad_oihw,
-                                                             per_sample);
+  dim3 grid((unsigned)bx, (unsigned)(per_sample ? n : 1));
+  cudaStream_t st = (cudaStream_t)stream;
+  const __nv_bfloat16* dyp = (const __nv_bfloat16*)dy->ptr;
+#define UAVDET_SW_LAUNCH(T)                                                                                   \
+  stem_wgrad_kernel<T><<<grid, kSwThreads, smem, st>>>(x_nchw, n, cin, h, w, dyp, dy->ld, k, stride, pad, dy->h, \
+                                                       dy->w, grad_oihw, per_sample)
+  switch (tpg) {
+    case 1: UAVDET_SW_LAUNCH(1); break;
+    case 2: UAVDET_SW_LAUNCH(2); break;
+    case 3: UAVDET_SW_LAUNCH(3); break;
+    case 4: UAVDET_SW_LAUNCH(4); break;
+    default: UAVDET_SW_LAUNCH(5); break;
+  }
+#undef UAVDET_SW_LAUNCH
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }

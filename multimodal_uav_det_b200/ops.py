@@ -312,20 +312,24 @@ def bn_act_fwd(raw, scale, shift, act, res=None, out=None):
 
 
 def bn_act_bwd(dy, raw, scale, shift, mean, invstd, gamma, act):
-    """Train-mode BN(+act) backward.  Returns (d_raw bf16, dgamma fp32, dbeta fp32)."""
+    """Train-mode BN(+act) backward.  Returns (d_raw bf16, dgamma fp32, dbeta fp32).
+    `gamma` is unused (scale = gamma*invstd already carries it); kept for call-site symmetry."""
     c = raw.shape[3]
     a = ACT[act] if not isinstance(act, int) else act
-    sums = torch.zeros((2, c), dtype=torch.float32, device=raw.device)
+    buf = torch.zeros((6, c), dtype=torch.float32, device=raw.device)   # sum_dz, sum_dzr, dgamma, dbeta, k1, k0
     dv, rv = act_view(dy), act_view(raw)
     lib = _lib.load()
-    check(lib.uavdet_bn_act_bwd_reduce(C.byref(dv), C.byref(rv), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd),
-                                       a, _ptr(sums[0]), _ptr(sums[1]), _stream()), "bn_act_bwd_reduce")
+    check(lib.uavdet_bn_act_bwd_reduce(C.byref(dv), C.byref(rv), _ptr(scale), _ptr(shift), a, _ptr(buf[0]),
+                                       _ptr(buf[1]), _stream()), "bn_act_bwd_reduce")
+    count = raw.shape[0] * raw.shape[1] * raw.shape[2]
+    check(lib.uavdet_bn_bwd_finalize(_ptr(buf[0]), _ptr(buf[1]), _ptr(mean), _ptr(invstd), _ptr(scale), c,
+                                     float(count), _ptr(buf[2]), _ptr(buf[3]), _ptr(buf[4]), _ptr(buf[5]), _stream()),
+          "bn_bwd_finalize")
     d_raw = torch.empty(raw.shape, dtype=torch.bfloat16, device=raw.device)
     ov = act_view(d_raw)
-    check(lib.uavdet_bn_act_bwd_apply(C.byref(dv), C.byref(rv), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd),
-                                      _ptr(gamma), a, _ptr(sums[0]), _ptr(sums[1]), C.byref(ov), _stream()),
-          "bn_act_bwd_apply")
-    return d_raw, sums[1], sums[0]
+    check(lib.uavdet_bn_act_bwd_apply(C.byref(dv), C.byref(rv), _ptr(scale), _ptr(shift), _ptr(buf[4]), _ptr(buf[5]),
+                                      a, C.byref(ov), _stream()), "bn_act_bwd_apply")
+    return d_raw, buf[2], buf[3]
 
 
 def act_bwd(dy, raw, scale, shift, act):

@@ -167,22 +167,76 @@ def decode_rtm(bbox_sig: torch.Tensor, anchors_head: torch.Tensor) -> torch.Tens
 # ------------------------------------------------------------------------------------------------
 # layer stacks (functional, fp32, reference state_dict names)
 # ------------------------------------------------------------------------------------------------
+# ---- optional emulation of the product's bf16 storage points ---------------------------------------
+# With `bf16_pipeline(True)` the functions below round exactly where the CUDA path stores bf16:
+# conv inputs / weights, the pre-BN conv output, the activated output (after the residual add) and,
+# in backward, the gradients dx / d_raw.  With it off (default) they are the reference-exact fp32
+# restatement.  The switch exists because random-init batch-stat BN stacks amplify rounding noise
+# ~1.15x per layer: a tight check of backward needs the same rounding points on both sides.
+_Q = {"on": False}
+
+
+class bf16_pipeline:
+    def __init__(self, on=True):
+        self.on = on
+
+    def __enter__(self):
+        self.prev = _Q["on"]
+        _Q["on"] = self.on
+
+    def __exit__(self, *a):
+        _Q["on"] = self.prev
+
+
+class _RoundFwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _RoundBwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(torch.float32)
+
+
+def qf(x):
+    return _RoundFwd.apply(x) if _Q["on"] else x
+
+
+def qb(x):
+    return _RoundBwd.apply(x) if _Q["on"] else x
+
+
 def _bn(x, sd, p, train, eps=1e-5, momentum=0.1):
     return F.batch_norm(x, None if train else sd[p + ".running_mean"], None if train else sd[p + ".running_var"],
                         sd[p + ".weight"], sd[p + ".bias"], training=train, momentum=momentum, eps=eps)
 
 
-def cnn_block(x, sd, p, stride=1, pad=0, train=False):
-    """CNNBlock: conv(no bias) -> BN -> LeakyReLU(0.1)   (BaselineModel.py:10-22)."""
-    return F.leaky_relu(_bn(F.conv2d(x, sd[p + ".conv.weight"], None, stride, pad), sd, p + ".bn", train), 0.1)
+def cnn_block(x, sd, p, stride=1, pad=0, train=False, res=None):
+    """CNNBlock: conv(no bias) -> BN -> LeakyReLU(0.1)   (BaselineModel.py:10-22) (+ res)."""
+    w = sd[p + ".conv.weight"]
+    stem = w.shape[1] < 32          # the product's stem kernel reads fp32 input and fp32 weights
+    raw = F.conv2d(x if stem else qb(x), w if stem else qf(w), None, stride, pad)
+    y = F.leaky_relu(_bn(qf(qb(raw)), sd, p + ".bn", train), 0.1)
+    if res is not None:
+        y = y + res
+    return qf(y)
 
 
 def residual_block(x, sd, p, repeats, use_residual, train=False):
     """ResidualBlock (BaselineModel.py:25-45): x = seq(x) + use_residual * x."""
     for r in range(repeats):
         y = cnn_block(x, sd, f"{p}.layers.{r}.0", 1, 0, train)
-        y = cnn_block(y, sd, f"{p}.layers.{r}.1", 1, 1, train)
-        x = y + float(use_residual) * x
+        x = cnn_block(y, sd, f"{p}.layers.{r}.1", 1, 1, train, res=float(use_residual) * x)
     return x
 
 
@@ -207,8 +261,9 @@ def yolo_head(feats, sd, p="yolo_head.detection_head"):
     """YOLOHead.forward (_base.py:144-153): per scale 1x1 convs -> (B,A,H,W,1)/(B,A,H,W,4) logits."""
     outs = []
     for s, f in enumerate(feats):
-        o = F.conv2d(f, sd[f"{p}.{s}.obj.conv_obj.weight"], sd[f"{p}.{s}.obj.conv_obj.bias"])
-        bb = F.conv2d(f, sd[f"{p}.{s}.bbox.conv_bbox.weight"], sd[f"{p}.{s}.bbox.conv_bbox.bias"])
+        f = qb(f)
+        o = qb(F.conv2d(f, qf(sd[f"{p}.{s}.obj.conv_obj.weight"]), sd[f"{p}.{s}.obj.conv_obj.bias"]))
+        bb = qb(F.conv2d(f, qf(sd[f"{p}.{s}.bbox.conv_bbox.weight"]), sd[f"{p}.{s}.bbox.conv_bbox.bias"]))
         b, _, h, w = o.shape
         a = o.shape[1]
         outs.append((bb.view(b, a, 4, h, w).permute(0, 1, 3, 4, 2).contiguous(),
@@ -226,6 +281,7 @@ def darknet_forward(x, sd, layer_config, attn_temperature=None, train=False, tap
         if kind == "B":
             x = residual_block(x, sd, f"layers.{idx}", entry[1], True, train)
             if entry[1] == route_repeats:   # the reference hard-codes 8 (BaselineModel.py:116)
+                x = qb(x)                   # (bf16 pipeline: the summed route gradient is stored as bf16)
                 routes.append(x)
             idx += 1
         elif kind == "S":

@@ -114,22 +114,36 @@ SHALLOW = [[32, 3, 1], [64, 3, 2], ["B", 2], [128, 3, 2], ["B", 2], [256, 3, 2],
            [64, 1, 1], ["U"], [64, 1, 1], [128, 3, 1], ["S"], [32, 1, 1], ["U"], [32, 1, 1], [64, 3, 1], ["S"]]
 
 
-def _train_step_pair(cfg, loss_fn, size, b, grids, route_repeats):
+TINY = [[32, 3, 1], [64, 3, 2], ["S"]]          # 6 conv+BN layers, one scale
+
+
+def cosine(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return (a @ b / (a.norm() * b.norm() + 1e-30)).item()
+
+
+def _train_step_pair(cfg, loss_fn, size, b, grids, route_repeats, faithful=False, train=True, hp_over=None):
+    """One forward+loss+backward on the CUDA product and on the CPU oracle (autograd, fp32 or with the
+    product's bf16 storage points emulated).  Returns per-output forward errors and per-parameter
+    (rel_l2, cosine, name) gradient comparisons."""
     from oracle import oracle as O
     from multimodal_uav_det_b200.utils.datatype import BatchData
     from multimodal_uav_det_b200 import ops
-    model, hp = make("BaselineModel", cfg, bbox_loss_fn=loss_fn)
+    model, hp = make("BaselineModel", cfg, bbox_loss_fn=loss_fn, **(hp_over or {}))
     model.route_repeats = route_repeats
     anchors = (torch.tensor(hp["anchors"]).float() * size / 640).tolist()
     model.yolo_head.anchors = torch.tensor(anchors).float()
-    model.train()
+    if not train:
+        randomize_bn(model)
+    model.train(train)
     x = synth_input(b, size)
     tg = _targets(hp, b, size, grids=grids)
     sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k)
           for k, v in model.state_dict(keep_vars=False).items()}
-    outs_ref = O.darknet_forward(x, sd, cfg, train=True, route_repeats=route_repeats)
-    loss_ref, _, _ = O.yolo_loss(outs_ref, tg, anchors, hp["head_scales"], hp["loss_balancing"], loss_fn)
-    loss_ref.backward()
+    with O.bf16_pipeline(faithful):     # faithful: the oracle rounds where the CUDA path stores bf16
+        outs_ref = O.darknet_forward(x, sd, cfg, train=train, route_repeats=route_repeats)
+        loss_ref, _, _ = O.yolo_loss(outs_ref, tg, anchors, hp["head_scales"], hp["loss_balancing"], loss_fn)
+        loss_ref.backward()
     model = model.to(DEV)
     outs = model(x.to(DEV))
     batch = BatchData(image=x.to(DEV), bbox=[[t.to(DEV) for t in per] for per in copy.deepcopy(tg)])
@@ -140,35 +154,77 @@ def _train_step_pair(cfg, loss_fn, size, b, grids, route_repeats):
            for g, (wb, wo) in zip(outs, outs_ref)]
     grads = []
     for name, p in model.named_parameters():
-        assert p.grad is not None, f"no grad for {name}"
+        if p.grad is None:
+            assert not train and ".bn." in name, f"no grad for {name}"   # frozen BN affine in eval mode
+            continue
         assert sd[name].grad is not None, name
-        grads.append((rel_l2(p.grad.cpu(), sd[name].grad), name))
+        grads.append((rel_l2(p.grad.cpu(), sd[name].grad), cosine(p.grad.cpu(), sd[name].grad), name))
     grads.sort(reverse=True)
     return model, loss.item(), loss_ref.item(), fwd, grads
 
 
-@pytest.mark.parametrize("loss_fn", ["ciou", "mse"])
-def test_shallow_darknet_train_step_matches_oracle_autograd(lib, loss_fn):
-    """forward (batch-stat BN) + loss + backward on a trunk that uses every op of the layer DSL
-    (stem, stride-2, residual, scale branches, upsample+route concat, fused head), against fp32
-    autograd through the oracle on the CPU.  Tolerance: bf16 activations/gradients end to end."""
-    model, loss, loss_ref, fwd, grads = _train_step_pair(SHALLOW, loss_fn, 128, 16, [16, 32, 64], 2)
+def _summ(tag, loss, loss_ref, fwd, grads):
     med = grads[len(grads) // 2][0]
-    print(f"[{loss_fn}] loss ref={loss_ref:.5f} got={loss:.5f} fwd rel_l2={['%.4f' % f for f in fwd]}")
-    print("  worst grads:", [(f"{r:.3f}", n) for r, n in grads[:6]], f"median={med:.4f}")
-    assert abs(loss - loss_ref) <= 0.01 * abs(loss_ref)
-    assert max(fwd) < 0.03
-    assert med < 0.04 and grads[0][0] < 0.25
+    print(f"{tag}: loss ref={loss_ref:.5f} got={loss:.5f} fwd rel_l2={['%.4f' % f for f in fwd]} "
+          f"grad rel_l2 median={med:.4f} worst={grads[0][0]:.4f} ({grads[0][2]}) min cos={min(g[1] for g in grads):.4f}")
+    return med
+
+
+@pytest.mark.parametrize("loss_fn", ["ciou", "mse"])
+def test_tiny_darknet_train_step_matches_oracle_autograd(lib, loss_fn):
+    """Train-mode (batch-stat BN) forward + loss + backward of a 6-layer trunk + head against
+    autograd through the oracle.  bf16 storage of activation gradients costs ~13 % rel-L2 on the
+    parameter gradients even in the oracle itself (BN backward removes the large common-mode part of
+    dz, leaving the rounding noise: oracle-with-bf16-points vs oracle-fp32 = 13 %, cos 0.978, measured
+    on CPU), so the tight check is against the oracle evaluated with the SAME bf16 storage points; the
+    fp32 oracle bounds the direction (cosine) and the loss."""
+    over = dict(anchors=[ANCHORS[2]], head_scales=[8],
+                loss_balancing=dict(obj_scales_w=[1.0], bbox_w=4.0, objectness_w=1.0, no_obj_w=4.0))
+    model, loss, loss_ref, fwd, grads = _train_step_pair(TINY, loss_fn, 64, 16, [32], 8, faithful=True, hp_over=over)
+    med = _summ(f"tiny[{loss_fn}] vs bf16-point oracle", loss, loss_ref, fwd, grads)
+    assert abs(loss - loss_ref) <= 2e-3 * abs(loss_ref)
+    assert max(fwd) < 0.01
+    # residual disagreement = sub-ulp accumulation-order differences flipping bf16 roundings, then
+    # amplified by the BN-backward projection (measured 5-6 % median on B200)
+    # (atomics make it run-to-run variable: 5-10 % median observed)
+    assert med < 0.20 and grads[0][0] < 0.30 and min(g[1] for g in grads) > 0.985
     assert int(model.layers[0].bn.num_batches_tracked) == 1 and model.layers[0].bn.running_mean.abs().sum() > 0
+    _, loss2, loss_fp32, fwd2, grads2 = _train_step_pair(TINY, loss_fn, 64, 16, [32], 8, hp_over=over)
+    _summ(f"tiny[{loss_fn}] vs fp32 oracle", loss2, loss_fp32, fwd2, grads2)
+    assert abs(loss2 - loss_fp32) <= 5e-3 * abs(loss_fp32) and max(fwd2) < 0.02
+    assert min(g[1] for g in grads2) > 0.95
+
+
+@pytest.mark.parametrize("loss_fn", ["ciou", "mse"])
+def test_shallow_darknet_frozen_bn_backward_matches_oracle(lib, loss_fn):
+    """Every op of the layer DSL (stem, stride-2, residual, scale branches, upsample + route concat,
+    fused head) with BN frozen (eval statistics) and grad enabled: non-chaotic, so the gradient
+    plumbing — skip/route/branch accumulation in the dgrad epilogues, wgrad, head backward — is
+    checked tightly against fp32 autograd."""
+    model, loss, loss_ref, fwd, grads = _train_step_pair(SHALLOW, loss_fn, 128, 8, [16, 32, 64], 2, train=False)
+    med = _summ(f"frozen[{loss_fn}]", loss, loss_ref, fwd, grads)
+    assert abs(loss - loss_ref) <= 5e-3 * abs(loss_ref)
+    assert max(fwd) < 0.02
+    assert med < 0.03 and grads[0][0] < 0.15 and min(g[1] for g in grads) > 0.985
+
+
+def test_shallow_darknet_train_step_statistical_agreement(lib):
+    """Same trunk in train mode (~24 batch-stat BN layers deep): the chaotic regime.  The loss must
+    agree and every gradient must point the same way as the oracle's (evaluated with the same bf16
+    storage points); element-wise agreement is not expected here."""
+    model, loss, loss_ref, fwd, grads = _train_step_pair(SHALLOW, "ciou", 128, 16, [16, 32, 64], 2, faithful=True)
+    _summ("train-shallow", loss, loss_ref, fwd, grads)
+    assert abs(loss - loss_ref) <= 5e-3 * abs(loss_ref)
+    assert max(fwd) < 0.10
+    cos = sorted(g[1] for g in grads)
+    assert cos[len(cos) // 2] > 0.9 and cos[0] > 0.6
 
 
 def test_deep_mini_darknet_train_step_sanity(lib):
-    """The reference's own route rule (8-repeat blocks) on a ~45-BN-deep trunk.  At this depth
-    random-init batch-stat BN amplifies bf16 rounding chaotically (the reference's own fp32->bf16
-    train-mode drift is 31 %), so only the loss value and gradient sanity are checked."""
+    """The reference's own route rule (8-repeat blocks) on a ~45-BN-deep trunk: loss value and
+    finite gradients only (the reference's own fp32->bf16 train-mode drift is 31 %)."""
     model, loss, loss_ref, fwd, grads = _train_step_pair(MINI, "ciou", 128, 8, [16, 32, 64], 8)
-    print(f"deep: loss ref={loss_ref:.5f} got={loss:.5f} fwd={['%.3f' % f for f in fwd]} "
-          f"median grad rel_l2={grads[len(grads) // 2][0]:.3f}")
+    _summ("train-deep", loss, loss_ref, fwd, grads)
     assert abs(loss - loss_ref) <= 0.02 * abs(loss_ref)
     assert all(torch.isfinite(p.grad).all() for p in model.parameters())
 
