@@ -480,3 +480,74 @@ def encode_targets(box_xyxy_px: torch.Tensor, anchors, head_scales, input_size: 
                 t[a, gy, gx, 1:5] = cell
         out.append(t)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# RTMUAVDet  (model/RTMUAVDet.py — deprecated in the reference but forward-runnable)
+# ------------------------------------------------------------------------------------------------
+def rtm_conv_module(x, sd, p, stride=1, pad=0, act="silu", train=False, eps=1e-3, momentum=0.03):
+    """RTMUAVDet.ConvModule (RTMUAVDet.py:15-25): defaults eps=1e-3, momentum=0.03."""
+    return conv_module(x, sd, p, stride, pad, act, train, eps, momentum)
+
+
+def mdyconv(x, sd, p, k, pad, train=False):
+    """MDyConv.forward (RTMUAVDet.py:68-100): 1x1 ConvModule(ReLU, eps 1e-5) -> GAP -> 1x1(+b)+ReLU ->
+    channel_fc (C) x kernel_fc (k*k) outer product -> per-sample depthwise conv -> + residual."""
+    y = rtm_conv_module(x, sd, p + ".base_conv", 1, 0, "relu", train, 1e-5, 0.1)
+    b, c = y.shape[:2]
+    pooled = y.mean(dim=(2, 3), keepdim=True)
+    a = F.relu(F.conv2d(pooled, sd[p + ".attention.1.weight"], sd[p + ".attention.1.bias"]))
+    ch_w = F.conv2d(a, sd[p + ".channel_fc.weight"], sd[p + ".channel_fc.bias"])          # (B,C,1,1)
+    k_w = F.conv2d(a, sd[p + ".kernel_fc.weight"], sd[p + ".kernel_fc.bias"]).view(b, 1, k, k)
+    filt = (k_w * ch_w).reshape(b * c, 1, k, k)
+    out = F.conv2d(y.reshape(1, b * c, *y.shape[2:]), filt, None, 1, pad, groups=b * c).view_as(y)
+    return out + y
+
+
+def mdycsp_module(x, sd, p, train=False):
+    """MDyCSPModule.forward (RTMUAVDet.py:122-140)."""
+    x = rtm_conv_module(x, sd, p + ".base_conv", 2, 1, "silu", train)
+    x1 = rtm_conv_module(x, sd, p + ".conv1", 1, 0, "silu", train)
+    x2 = rtm_conv_module(x, sd, p + ".conv2", 1, 0, "silu", train)
+    x1 = mdyconv(x1, sd, p + ".mdy_conv", 3, 1, train)
+    x1 = rtm_conv_module(x1, sd, p + ".transition1", 1, 0, "silu", train)
+    return rtm_conv_module(torch.cat([x1, x2], 1), sd, p + ".transition2", 1, 1, "silu", train)
+
+
+def mdy_encoder(x, sd, p, train=False):
+    """MDyEncoder.forward (RTMUAVDet.py:163-184).  Dropout(0.2) is identity in eval mode."""
+    res = x
+    c = x.shape[1]
+    y = F.group_norm(x, 1, sd[p + ".group_norm_in.weight"], sd[p + ".group_norm_in.bias"], 1e-5)
+    y = torch.cat([mdyconv(y, sd, p + ".mdy_conv_1x1", 1, 0, train), mdyconv(y, sd, p + ".mdy_conv_3x3", 3, 1, train),
+                   mdyconv(y, sd, p + ".mdy_conv_5x5", 5, 2, train)], 1)
+    y = y + res
+    y = F.group_norm(y, 1, sd[p + ".group_norm_out.weight"], sd[p + ".group_norm_out.bias"], 1e-5)
+    y = F.gelu(F.conv2d(y, sd[p + ".channel_mlp.0.weight"], sd[p + ".channel_mlp.0.bias"]))
+    if train:
+        raise NotImplementedError("train-mode Dropout(0.2) is stochastic; the oracle covers eval mode")
+    return F.conv2d(y, sd[p + ".channel_mlp.3.weight"], sd[p + ".channel_mlp.3.bias"])
+
+
+def rtm_forward(x, sd, anchors, train=False):
+    """RTMUAVDet.forward (RTMUAVDet.py:336-345) incl. RTMHead sigmoid + in-forward decode (:274-310).
+    anchors: (2,3,2) tensor.  Returns per head (decoded bbox (B,A,H,W,4), obj (B,A,H,W,1))."""
+    x = rtm_conv_module(x, sd, "backbone.MDyCSP_1.0.conv", 2, 1, "silu", train)           # 5x5 s2 p1 stem
+    x1 = mdycsp_module(x, sd, "backbone.MDyCSP_1.1", train)
+    x2 = mdycsp_module(x1, sd, "backbone.MDyCSP_2", train)
+    up = F.interpolate(x2, scale_factor=2, mode="bilinear")
+    f = F.conv2d(up, sd["neck.upsample.1.weight"], sd["neck.upsample.1.bias"], 1, 1)
+    x1 = mdy_encoder(torch.cat([x1, f], 1), sd, "neck.encoder_x1", train)
+    d = F.conv2d(x1, sd["neck.downsample.weight"], sd["neck.downsample.bias"], 2, 1)
+    x2 = mdy_encoder(torch.cat([x2, d], 1), sd, "neck.encoder_x2", train)
+    outs = []
+    for i, f_map in enumerate((x1, x2)):
+        p = f"head.detection_head.{i}"
+        # attribute names are swapped in the reference (obj head holds `conv_bbox`), RTMUAVDet.py:223,243
+        o = torch.sigmoid(F.conv2d(f_map, sd[p + ".obj.conv_bbox.weight"], sd[p + ".obj.conv_bbox.bias"]))
+        bb = torch.sigmoid(F.conv2d(f_map, sd[p + ".bbox.conv_obj.weight"], sd[p + ".bbox.conv_obj.bias"]))
+        b, a, h, w = o.shape
+        o = o.view(b, a, 1, h, w).permute(0, 1, 3, 4, 2).contiguous()
+        bb = bb.view(b, a, 4, h, w).permute(0, 1, 3, 4, 2).contiguous()
+        outs.append((decode_rtm(bb, anchors[i]), o))
+    return outs

@@ -1,0 +1,211 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol the header declares,
+the product refuses to run without CUDA (no fallback), drop-in API surface, the batched loss against
+the reference's golden numbers, and the data-parallel trainer over gloo (world_size 2)."""
+import copy
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def load(name):
+    return torch.load(os.path.join(GOLD, name), weights_only=False)
+
+
+def golden_logits(seed, batch, grids):
+    g = torch.Generator().manual_seed(seed)
+    return [(torch.randn(batch, 3, s, s, 4, generator=g), torch.randn(batch, 3, s, s, 1, generator=g)) for s in grids]
+
+
+# ---- C-ABI ------------------------------------------------------------------------------------------
+def test_library_exports_every_symbol_declared_in_the_header(lib):
+    from multimodal_uav_det_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "uavdet_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(uavdet_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 30
+    nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (uavdet_[a-z0-9_]+)", nm))
+    assert declared <= exported, f"declared but not exported: {sorted(declared - exported)}"
+    assert declared == set(_lib.SIGNATURES), f"ctypes table out of sync: {sorted(declared ^ set(_lib.SIGNATURES))}"
+    assert lib.uavdet_version() >= 100
+    assert lib.uavdet_last_error() is not None
+
+
+def test_library_is_cuda_only_sm100a(lib):
+    from multimodal_uav_det_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+def test_no_cpu_fallback():
+    from multimodal_uav_det_b200 import ops
+    from multimodal_uav_det_b200._lib import UavdetError
+    from multimodal_uav_det_b200.model import BaselineModel
+    from multimodal_uav_det_b200.utils.datatype import Config
+    gold = load("model_forwards.pt")["baseline"]
+    model = BaselineModel(hparams=Config(gold["hp"]))
+    with pytest.raises(RuntimeError):
+        model(torch.rand(1, 3, 64, 64))
+    with pytest.raises(UavdetError):
+        ops.nms(torch.zeros(4, 4), torch.zeros(4), 0.5)
+    # the product package must never import the oracle
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "multimodal_uav_det_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f"{f} imports the oracle"
+
+
+# ---- drop-in surface ------------------------------------------------------------------------------------
+def test_model_api_surface_matches_reference_contract():
+    from multimodal_uav_det_b200 import model as M
+    from multimodal_uav_det_b200.model import _base
+    from multimodal_uav_det_b200.utils.datatype import BatchData, Config, DetectionResults
+    assert DetectionResults._fields == ("bbox", "obj") and BatchData._fields == ("image", "bbox")
+    gold = load("model_forwards.pt")
+    for name, cls in (("baseline", M.BaselineModel), ("dy-yolo", M.DyYOLO)):
+        hp = gold[name]["hp"]
+        m = cls(hparams=Config(hp))
+        for attr in ("forward", "training_step", "validation_step", "configure_optimizers", "log"):
+            assert callable(getattr(m, attr))
+        opt = m.configure_optimizers()
+        assert isinstance(opt, torch.optim.SGD) and opt.defaults["momentum"] == hp["optim"]["momentum"]
+        assert isinstance(m.yolo_head, _base.YOLOHead) and not any(k.startswith("yolo_head.anchors") for k in m.state_dict())
+    bad = dict(gold["baseline"]["hp"], optim=dict(name="RMSprop", momentum=0.0))
+    with pytest.raises(ValueError):
+        M.BaselineModel(hparams=Config(bad)).configure_optimizers()
+    with pytest.raises(ValueError):
+        M.BaselineModel(hparams=Config(gold["dy-yolo"]["hp"]))     # DyConv layers need DyYOLO
+    cfg = Config({"a": 1, "b": {"c": [1, 2], "d": {"e": "x"}}})
+    assert cfg.a == 1 and cfg.b.c == [1, 2] and cfg.b.d.e == "x"
+
+
+def test_calculate_iou_matches_golden_including_first_target_quirk():
+    from multimodal_uav_det_b200.utils.postprocess import calculate_iou
+    g = load("blocks.pt")["calculate_iou"]
+    for mode in ("mse", "ciou"):
+        got = calculate_iou(g["preds"], g["targets"], g["anchors"], g["mask"], mode)
+        torch.testing.assert_close(got, g[mode], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["baseline", "dy-yolo"])
+def test_batched_loss_matches_reference_golden(name):
+    """YOLOHead.compute_metrics (batched, sync-free) == the reference's per-sample loop: value,
+    gradients w.r.t. every logit, and the in-place rewrite of batch.bbox."""
+    from multimodal_uav_det_b200.model._base import YOLOHead
+    from multimodal_uav_det_b200.utils.datatype import BatchData, Config, DetectionResults
+    gold = load("head_loss_decode.pt")[name]
+    hp = gold["hp"]
+    head = YOLOHead([8, 8, 8], hp["anchors"], hp["head_scales"], Config(hp["loss_balancing"]), hp["bbox_loss_fn"])
+    grids = [gold["size"] // s for s in hp["head_scales"]]
+    logits = golden_logits(gold["logits_seed"], 3, grids)
+    outs = [DetectionResults(bbox=b.clone().requires_grad_(True), obj=o.clone().requires_grad_(True)) for b, o in logits]
+    batch = BatchData(image=torch.zeros(3, 3, 8, 8), bbox=copy.deepcopy(gold["targets"]))
+    loss, ap, bl, ol = head.compute_metrics(outs, batch)
+    loss.backward()
+    assert ap is None
+    torch.testing.assert_close(loss.detach(), gold["loss"], rtol=2e-6, atol=1e-6)
+    torch.testing.assert_close(bl.detach(), gold["bbox_loss"], rtol=2e-6, atol=1e-6)
+    torch.testing.assert_close(ol.detach(), gold["obj_loss"], rtol=2e-6, atol=1e-6)
+    for o, (gb, go) in zip(outs, gold["grads"]):
+        torch.testing.assert_close(o.bbox.grad, gb, rtol=1e-4, atol=1e-7)
+        torch.testing.assert_close(o.obj.grad, go, rtol=1e-4, atol=1e-7)
+    for per, gper in zip(batch.bbox, gold["mutated_targets"]):
+        for t, gt in zip(per, gper):
+            torch.testing.assert_close(t, gt, rtol=1e-6, atol=1e-7)
+    # pre-stacked targets (the bench / fast path) give the same loss
+    stacked = [torch.stack([gold["targets"][i][h] for i in range(3)]) for h in range(3)]
+    head.mutate_targets = False
+    outs2 = [DetectionResults(bbox=b, obj=o) for b, o in logits]
+    loss2, _, _, _ = head.compute_metrics(outs2, BatchData(image=torch.zeros(3, 3, 8, 8), bbox=stacked))
+    torch.testing.assert_close(loss2, gold["loss"], rtol=2e-6, atol=1e-6)
+
+
+# ---- data-parallel trainer over gloo -----------------------------------------------------------------------
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from multimodal_uav_det_b200.parallel import FlatSGDTrainer
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=2)
+torch.manual_seed(0)
+model = torch.nn.Sequential(torch.nn.Linear(37, 19), torch.nn.BatchNorm1d(19), torch.nn.Linear(19, 5))
+ref = [p.detach().clone() for p in model.parameters()]
+trainer = FlatSGDTrainer(model, lr=0.1, momentum=0.7, bucket_mb=0.001)
+assert len(trainer.buckets) > 1
+bufs = [torch.zeros_like(p) for p in ref]
+for step in range(3):
+    trainer.zero_grad()
+    g = torch.Generator().manual_seed(100 * step + rank)
+    grads = []
+    for p in model.parameters():
+        gr = torch.randn(p.shape, generator=g)
+        p.grad.add_(gr)                 # accumulate into the arena view, as the executor does
+        trainer._on_grad_ready(p)      # grad_ready_hook
+        grads.append(gr)
+    trainer.step()
+    # expected: SGD(momentum) on the mean gradient of both ranks
+    for i in range(len(ref)):
+        g0 = torch.randn(ref[i].shape, generator=torch.Generator().manual_seed(100 * step + 0))
+        g1 = torch.randn(ref[i].shape, generator=torch.Generator().manual_seed(100 * step + 1))
+    gens = [torch.Generator().manual_seed(100 * step + r) for r in range(2)]
+    for i in range(len(ref)):
+        mean_g = sum(torch.randn(ref[i].shape, generator=gens[r]) for r in range(2)) / 2
+        bufs[i] = mean_g if step == 0 else 0.7 * bufs[i] + mean_g
+        ref[i] = ref[i] - 0.1 * bufs[i]
+for p, r in zip(model.parameters(), ref):
+    assert torch.allclose(p.detach(), r, rtol=1e-5, atol=1e-6), (p.detach() - r).abs().max()
+# parameters are views of the flat arenas and identical on both ranks
+flat = torch.cat([b.param for b in trainer.buckets])
+other = [torch.zeros_like(flat) for _ in range(2)]
+dist.all_gather(other, flat)
+assert torch.equal(other[0], other[1])
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_flat_sgd_trainer_gloo_world_size_2(tmp_path):
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(os.environ, RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, f"rank {r} failed:\n{o}"
+        assert f"rank {r} ok" in o
+
+
+def test_flat_sgd_trainer_single_process_matches_torch_sgd():
+    from multimodal_uav_det_b200.parallel import FlatSGDTrainer
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(11, 7), torch.nn.Linear(7, 3))
+    twin = copy.deepcopy(model)
+    opt = torch.optim.SGD(twin.parameters(), lr=0.05, momentum=0.78)
+    trainer = FlatSGDTrainer(model, lr=0.05, momentum=0.78)
+    for step in range(4):
+        trainer.zero_grad()
+        opt.zero_grad()
+        g = torch.Generator().manual_seed(step)
+        for p, q in zip(model.parameters(), twin.parameters()):
+            gr = torch.randn(p.shape, generator=g)
+            p.grad.add_(gr)
+            q.grad = gr.clone()
+        trainer.step()
+        opt.step()
+    for p, q in zip(model.parameters(), twin.parameters()):
+        torch.testing.assert_close(p.detach(), q.detach(), rtol=1e-6, atol=1e-7)
+    # state_dict still works on the re-homed parameters
+    assert set(model.state_dict()) == set(twin.state_dict())
