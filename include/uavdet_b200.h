@@ -107,6 +107,8 @@ typedef struct {
   float* head_obj;    /* HEAD: (B,A,H,W,1) fp32                                          */
   float* head_bbox;   /* HEAD: (B,A,H,W,4) fp32                                          */
   int head_anchors;   /* A; cout must be 5*A packed [A obj | 4A bbox]                    */
+  int shift_per_sample; /* != 0: shift is [n][cout] (aggregated expert bias, DySOEM_SimFPN.py:83-91);
+                           in STATS mode a given shift is added before the statistics        */
 } uavdet_epilogue;
 
 /* Forward convolution  y = conv(x, w), square kernel k in {1,3,5}, stride 1|2, zero pad.
@@ -186,6 +188,10 @@ int uavdet_act_bwd(const uavdet_act* dy, const uavdet_act* raw, const float* sca
 int uavdet_upsample2x_fwd(const uavdet_act* x, const uavdet_act* y, void* stream);
 /* dx = sum over the 2x2 replicas of dy (accumulate: dx += ...).                           */
 int uavdet_upsample2x_bwd(const uavdet_act* dy, const uavdet_act* dx, int accumulate, void* stream);
+/* y = a_mult*a + nearest_upsample2x(b)  (SimplifiedFPN top-down adds, DySOEM_SimFPN.py:116-118; the
+ * 1x1 conv commutes with nearest upsampling, so it runs at low resolution and is upsampled here). */
+int uavdet_upsample2x_add(const uavdet_act* b_low, const uavdet_act* a, float a_mult, const uavdet_act* y,
+                          void* stream);
 /* y = a (+ b) elementwise over views (copy into / accumulate from channel slices).        */
 int uavdet_add(const uavdet_act* a, const uavdet_act* b, const uavdet_act* y, void* stream);
 /* NHWC bf16 <-> NCHW fp32 (API edge only: parity tests and user-facing feature maps).     */
@@ -208,6 +214,24 @@ int uavdet_attn_mlp_softmax(const float* pooled, int n, int c, const float* w1, 
 int uavdet_dyn_aggregate(const float* attn, int n, int K, const float* bank, int O, int I, int k,
                          int transposed, void* out_bf16, const float* bias_bank, float* bias_out,
                          void* stream);
+
+/* ---- K3 / K6 / K7: RTMUAVDet memory-bound ops -------------------------------------------- */
+/* Per-sample depthwise dynamic conv + residual (MDyConv.forward, RTMUAVDet.py:80-98):
+ * y[b,p,c] = x[b,p,c] + channel_w[b,c] * sum_t kernel_w[b,t] * x[b,p+t,c]; k odd, pad = k/2.      */
+int uavdet_dwdynconv_fwd(const uavdet_act* x, const float* channel_w, const float* kernel_w, int k, int pad,
+                         const uavdet_act* y, void* stream);
+/* out[r][o] = act(in[r][:] . w[o][:] + bias[o])  — the 1x1 convs on pooled vectors (RTMUAVDet.py:54-62). */
+int uavdet_linear(const float* in, int rows, int c, const float* w, const float* bias, int out_dim, int act,
+                  float* out, void* stream);
+/* GroupNorm(num_groups=1) of (a [+ b]) with per-channel affine (RTMUAVDet.py:147,153,165,174).
+ * stats_ws: 2*n floats of scratch.                                                              */
+int uavdet_groupnorm1(const uavdet_act* a, const uavdet_act* b, const float* gamma, const float* beta,
+                      float eps, float* stats_ws, const uavdet_act* y, void* stream);
+/* nn.Upsample(scale_factor=2, mode='bilinear'), align_corners=False (RTMUAVDet.py:193).           */
+int uavdet_bilinear2x_fwd(const uavdet_act* x, const uavdet_act* y, void* stream);
+/* RTMHead post: sigmoid on obj / bbox logits (RTMUAVDet.py:234,253) + decode (:285-289).           */
+int uavdet_rtm_head_post(const float* bbox_logits, const float* obj_logits, int batch, int A, int S_h, int S_w,
+                         const float* anchors_host, float* bbox_out, float* obj_out, void* stream);
 
 /* ---- optimiser ----------------------------------------------------------------------- */
 /* torch.optim.SGD(momentum) step over a flat fp32 parameter arena (_base.py:292-293):

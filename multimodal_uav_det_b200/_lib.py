@@ -23,7 +23,8 @@ class Act(C.Structure):
 class Epilogue(C.Structure):
     _fields_ = [("epi", C.c_int), ("act", C.c_int), ("scale", C.c_void_p), ("shift", C.c_void_p),
                 ("res", C.c_void_p), ("res_ld", C.c_int), ("sum", C.c_void_p), ("sumsq", C.c_void_p),
-                ("head_obj", C.c_void_p), ("head_bbox", C.c_void_p), ("head_anchors", C.c_int)]
+                ("head_obj", C.c_void_p), ("head_bbox", C.c_void_p), ("head_anchors", C.c_int),
+                ("shift_per_sample", C.c_int)]
 
 
 class UavdetError(RuntimeError):
@@ -61,6 +62,7 @@ SIGNATURES = {
     "uavdet_act_bwd": (_i, [_AP, _AP, _P, _P, _i, _AP, _P]),
     "uavdet_upsample2x_fwd": (_i, [_AP, _AP, _P]),
     "uavdet_upsample2x_bwd": (_i, [_AP, _AP, _i, _P]),
+    "uavdet_upsample2x_add": (_i, [_AP, _AP, _f, _AP, _P]),
     "uavdet_add": (_i, [_AP, _AP, _AP, _P]),
     "uavdet_nhwc_to_nchw_f32": (_i, [_AP, _P, _P]),
     "uavdet_nchw_f32_to_nhwc": (_i, [_P, _AP, _P]),
@@ -68,6 +70,11 @@ SIGNATURES = {
     "uavdet_gap_nchw": (_i, [_P, _i, _i, _i, _P, _P]),
     "uavdet_attn_mlp_softmax": (_i, [_P, _i, _i, _P, _P, _i, _P, _P, _i, _f, _P, _P, _P]),
     "uavdet_dyn_aggregate": (_i, [_P, _i, _i, _P, _i, _i, _i, _i, _P, _P, _P, _P]),
+    "uavdet_dwdynconv_fwd": (_i, [_AP, _P, _P, _i, _i, _AP, _P]),
+    "uavdet_linear": (_i, [_P, _i, _i, _P, _P, _i, _i, _P, _P]),
+    "uavdet_groupnorm1": (_i, [_AP, _AP, _P, _P, _f, _P, _AP, _P]),
+    "uavdet_bilinear2x_fwd": (_i, [_AP, _AP, _P]),
+    "uavdet_rtm_head_post": (_i, [_P, _P, _i, _i, _i, _i, C.POINTER(_f), _P, _P, _P]),
     "uavdet_sgd_momentum": (_i, [_P, _P, _P, _i64, _f, _f, _f, _i, _P]),
 }
 

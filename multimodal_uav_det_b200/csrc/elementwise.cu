@@ -339,6 +339,30 @@ __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int 
   }
 }
 
+__global__ void upsample2x_add_kernel(const __nv_bfloat16* __restrict__ b, int b_ld, int n, int h, int w, int c,
+                                      const __nv_bfloat16* __restrict__ a, int a_ld, float a_mult,
+                                      __nv_bfloat16* __restrict__ y, int y_ld) {
+  // (n, 2h, 2w, c) output; b is (n, h, w, c)
+  const int c8 = c >> 3;
+  const int H = 2 * h, W = 2 * w;
+  const long long total = (long long)n * H * W * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long px = i / c8;
+    const int cc = (int)(i - px * c8) << 3;
+    const int ox = (int)(px % W); long long t = px / W;
+    const int oy = (int)(t % H);
+    const int img = (int)(t / H);
+    const long long src = ((long long)img * h + (oy >> 1)) * w + (ox >> 1);
+    float va[8], vb[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(a + px * a_ld + cc)), va);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(b + src * b_ld + cc)), vb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) va[j] = fmaf(a_mult, va[j], vb[j]);
+    *reinterpret_cast<uint4*>(y + px * y_ld + cc) = pack8(va);
+  }
+}
+
 __global__ void add_kernel(View a, const __nv_bfloat16* __restrict__ b, int b_ld, View y) {
   const int c8 = a.c >> 3;
   const long long total = a.npix * c8;
@@ -675,6 +699,22 @@ extern "C" int uavdet_upsample2x_bwd(const uavdet_act* dy, const uavdet_act* dx,
   long long total = (long long)dx->n * dx->h * dx->w * (dx->c / 8);
   upsample2x_bwd_kernel<<<ew_grid(total, 256), 256, 0, ST>>>((const __nv_bfloat16*)dy->ptr, dy->ld, dx->n, dx->h,
                                                             dx->w, dx->c, (__nv_bfloat16*)dx->ptr, dx->ld, accumulate);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_upsample2x_add(const uavdet_act* b_low, const uavdet_act* a, float a_mult,
+                                     const uavdet_act* y, void* stream) {
+  int rc;
+  if ((rc = check_view(b_low, "upsample2x_add b")) || (rc = check_view(a, "upsample2x_add a")) ||
+      (rc = check_view(y, "upsample2x_add y")) || (rc = same_shape(a, y, "upsample2x_add")))
+    return rc;
+  UAVDET_CHECK_ARG(a->n == b_low->n && a->h == 2 * b_low->h && a->w == 2 * b_low->w && a->c == b_low->c,
+                   "upsample2x_add: shapes");
+  long long total = (long long)a->n * a->h * a->w * (a->c / 8);
+  upsample2x_add_kernel<<<ew_grid(total, 256), 256, 0, ST>>>((const __nv_bfloat16*)b_low->ptr, b_low->ld, b_low->n,
+                                                            b_low->h, b_low->w, b_low->c, (const __nv_bfloat16*)a->ptr,
+                                                            a->ld, a_mult, (__nv_bfloat16*)y->ptr, y->ld);
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }

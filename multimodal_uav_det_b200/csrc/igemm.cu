@@ -30,7 +30,8 @@ constexpr int kAccStride = 256;  // TMEM columns per accumulator buffer
 
 template <int ACT>
 __device__ __forceinline__ void affine_act_store(const uint32_t (&r)[32], const IgemmParams& P, int cg,
-                                                 __nv_bfloat16* out_px, const __nv_bfloat16* res_px) {
+                                                 __nv_bfloat16* out_px, const __nv_bfloat16* res_px,
+                                                 const float* shift) {
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
@@ -41,10 +42,10 @@ __device__ __forceinline__ void affine_act_store(const uint32_t (&r)[32], const 
       v[i] *= s.x; v[i + 1] *= s.y; v[i + 2] *= s.z; v[i + 3] *= s.w;
     }
   }
-  if (P.shift) {
+  if (shift) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      float4 s = __ldg(reinterpret_cast<const float4*>(P.shift + cg + i));
+      float4 s = __ldg(reinterpret_cast<const float4*>(shift + cg + i));
       v[i] += s.x; v[i + 1] += s.y; v[i + 2] += s.z; v[i + 3] += s.w;
     }
   }
@@ -248,6 +249,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         const __nv_bfloat16* res_px =
             P.res ? P.res + (size_t)img * P.res_sn + (size_t)oh * P.res_sh + (size_t)ow * P.res_sw
                   : nullptr;
+        const float* shift = P.shift ? P.shift + (size_t)img * P.shift_sn : nullptr;
         for (int c0 = 0; c0 < P.block_n; c0 += 32) {
           const int cg = n0 + c0;
           if (cg >= P.cout) break;  // uniform: last n-tile of a cout that is not a block_n multiple
@@ -258,6 +260,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             float v[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = valid ? __uint_as_float(r[i]) : 0.f;
+            if (shift && valid) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                float4 s = __ldg(reinterpret_cast<const float4*>(shift + cg + i));
+                v[i] += s.x; v[i + 1] += s.y; v[i + 2] += s.z; v[i + 3] += s.w;
+              }
+            }
             if (valid) {
 #pragma unroll
               for (int i = 0; i < 32; i += 8) {
@@ -278,11 +287,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             atomicAdd(&stat[(acc * 2 + 1) * 256 + c0 + lane], s2);
           } else if (valid) {
             switch (P.act) {
-              case UAVDET_ACT_LEAKY: affine_act_store<UAVDET_ACT_LEAKY>(r, P, cg, out_px, res_px); break;
-              case UAVDET_ACT_SILU: affine_act_store<UAVDET_ACT_SILU>(r, P, cg, out_px, res_px); break;
-              case UAVDET_ACT_RELU: affine_act_store<UAVDET_ACT_RELU>(r, P, cg, out_px, res_px); break;
-              case UAVDET_ACT_GELU: affine_act_store<UAVDET_ACT_GELU>(r, P, cg, out_px, res_px); break;
-              default: affine_act_store<UAVDET_ACT_NONE>(r, P, cg, out_px, res_px); break;
+              case UAVDET_ACT_LEAKY: affine_act_store<UAVDET_ACT_LEAKY>(r, P, cg, out_px, res_px, shift); break;
+              case UAVDET_ACT_SILU: affine_act_store<UAVDET_ACT_SILU>(r, P, cg, out_px, res_px, shift); break;
+              case UAVDET_ACT_RELU: affine_act_store<UAVDET_ACT_RELU>(r, P, cg, out_px, res_px, shift); break;
+              case UAVDET_ACT_GELU: affine_act_store<UAVDET_ACT_GELU>(r, P, cg, out_px, res_px, shift); break;
+              default: affine_act_store<UAVDET_ACT_NONE>(r, P, cg, out_px, res_px, shift); break;
             }
           }
         }
@@ -484,6 +493,7 @@ static int fill_epilogue(IgemmParams& P, const uavdet_epilogue* epi, const uavde
   P.act = epi ? epi->act : UAVDET_ACT_NONE;
   P.scale = epi ? epi->scale : nullptr;
   P.shift = epi ? epi->shift : nullptr;
+  P.shift_sn = (epi && epi->shift_per_sample) ? cout : 0;
   P.res = epi ? (const __nv_bfloat16*)epi->res : nullptr;
   P.sum = epi ? epi->sum : nullptr;
   P.sumsq = epi ? epi->sumsq : nullptr;

@@ -26,6 +26,7 @@ struct IgemmParams {
   int epi, act;
   const float* scale;
   const float* shift;
+  long long shift_sn;   // per-image stride of `shift` (0 = shared)
   const __nv_bfloat16* res;
   long long res_sn, res_sh, res_sw;
   __nv_bfloat16* out;

@@ -16,6 +16,7 @@ struct StemParams {
   const float* wgt;        // [w_batch][32][cin][k][k] fp32
   int w_batch;
   int k, stride, pad, ho, wo;
+  int yh, yw;              // output buffer grid (== ho,wo, or ho+1,wo+1: zero-padded last row/col)
   __nv_bfloat16* y; long long y_ld;
   int epi, act;
   const float* scale; const float* shift;
@@ -50,14 +51,15 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(StemParams P) {
   if (threadIdx.x < 2 * kStemCout) ssum[threadIdx.x / kStemCout][threadIdx.x % kStemCout] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const long long hw_out = (long long)P.ho * P.wo;
+  const long long hw_out = (long long)P.yh * P.yw;
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = p < hw_out;
+  const bool in_buf = p < hw_out;
+  const bool valid = in_buf && (int)(p / P.yw) < P.ho && (int)(p % P.yw) < P.wo;
   float acc[kStemCout];
 #pragma unroll
   for (int c = 0; c < kStemCout; ++c) acc[c] = 0.f;
   if (valid) {
-    const int oy = (int)(p / P.wo), ox = (int)(p - (long long)oy * P.wo);
+    const int oy = (int)(p / P.yw), ox = (int)(p - (long long)oy * P.yw);
     const float* xin = P.x + (long long)img * P.cin * P.h * P.w;
     for (int ci = 0; ci < P.cin; ++ci)
       for (int kh = 0; kh < P.k; ++kh) {
@@ -96,13 +98,13 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(StemParams P) {
       atomicAdd(P.sum + threadIdx.x, ssum[0][threadIdx.x]);
       atomicAdd(P.sumsq + threadIdx.x, ssum[1][threadIdx.x]);
     }
-  } else if (valid) {
+  } else if (in_buf) {
 #pragma unroll
     for (int c = 0; c < kStemCout; ++c) {
       float z = acc[c];
       if (P.scale) z *= __ldg(P.scale + c);
       if (P.shift) z += __ldg(P.shift + c);
-      acc[c] = act_fwd_rt(P.act, z);
+      acc[c] = valid ? act_fwd_rt(P.act, z) : 0.f;   // padded last row / column stays zero
     }
 #pragma unroll
     for (int c = 0; c < kStemCout; c += 8) {
@@ -216,7 +218,10 @@ extern "C" int uavdet_stem_fwd(const float* x_nchw, int n, int cin, int h, int w
   P.k = k; P.stride = stride; P.pad = pad;
   P.ho = (h + 2 * pad - k) / stride + 1;
   P.wo = (w + 2 * pad - k) / stride + 1;
-  UAVDET_CHECK_ARG(y->n == n && y->h == P.ho && y->w == P.wo && y->c == cout, "stem_fwd: output view mismatch");
+  const bool padded = (y->h == P.ho + 1 && y->w == P.wo + 1);
+  UAVDET_CHECK_ARG(y->n == n && y->c == cout && ((y->h == P.ho && y->w == P.wo) || padded),
+                   "stem_fwd: output view (%d,%d) != conv output (%d,%d) [or +1 zero-padded]", y->h, y->w, P.ho, P.wo);
+  P.yh = y->h; P.yw = y->w;
   UAVDET_CHECK_ARG(y->ld % 8 == 0 && ((uintptr_t)y->ptr & 15) == 0, "stem_fwd: output alignment");
   P.y = (__nv_bfloat16*)y->ptr; P.y_ld = y->ld;
   P.epi = epi ? epi->epi : UAVDET_EPI_AFFINE;
@@ -225,7 +230,8 @@ extern "C" int uavdet_stem_fwd(const float* x_nchw, int n, int cin, int h, int w
   P.sum = epi ? epi->sum : nullptr; P.sumsq = epi ? epi->sumsq : nullptr;
   if (P.epi == UAVDET_EPI_STATS) UAVDET_CHECK_ARG(P.sum && P.sumsq, "stem_fwd: STATS needs sum/sumsq");
   UAVDET_CHECK_ARG(P.epi != UAVDET_EPI_HEAD, "stem_fwd: HEAD epilogue unsupported");
-  dim3 grid((unsigned)ceil_div64((long long)P.ho * P.wo, 256), (unsigned)n);
+  UAVDET_CHECK_ARG(!(padded && P.epi == UAVDET_EPI_STATS), "stem_fwd: zero-padded output needs the AFFINE epilogue");
+  dim3 grid((unsigned)ceil_div64((long long)P.yh * P.yw, 256), (unsigned)n);
   stem_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;

@@ -251,7 +251,7 @@ class BaseModel(LightningModule):
     def __init__(self, hparams):
         super().__init__()
         self.learning_rate = hparams.lr
-        self.optimizer = hparams.optim
+        self.optimizer = getattr(hparams, "optim", None)   # dy-soem_fpn.yaml keeps `optim` outside hparams (D5)
         self.head_scales = hparams.head_scales
         self.lr_scheduler = hparams.lr_scheduler
         self.backbone = None
@@ -262,6 +262,8 @@ class BaseModel(LightningModule):
         return x
 
     def configure_optimizers(self):
+        if self.optimizer is None:
+            raise ValueError("Invalid optimizer: hparams.optim is missing")
         if self.optimizer.name == "SGD":
             opt = torch.optim.SGD(self.parameters(), lr=self.learning_rate, momentum=self.optimizer.momentum)
         elif self.optimizer.name == "Adam":

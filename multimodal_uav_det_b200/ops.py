@@ -171,7 +171,8 @@ def unpack_wgrad(dw_packed: torch.Tensor, o: int, i: int, k: int, grad: Optional
 # convolution
 # --------------------------------------------------------------------------------------------
 def _epilogue(epi: int = EPI_AFFINE, act=None, scale=None, shift=None, res: Optional[torch.Tensor] = None,
-              sum_=None, sumsq=None, head_obj=None, head_bbox=None, head_anchors: int = 0) -> Epilogue:
+              sum_=None, sumsq=None, head_obj=None, head_bbox=None, head_anchors: int = 0,
+              shift_per_sample: bool = False) -> Epilogue:
     e = Epilogue()
     e.epi = epi
     e.act = ACT[act] if not isinstance(act, int) else act
@@ -187,6 +188,7 @@ def _epilogue(epi: int = EPI_AFFINE, act=None, scale=None, shift=None, res: Opti
     e.head_obj = head_obj.data_ptr() if head_obj is not None else None
     e.head_bbox = head_bbox.data_ptr() if head_bbox is not None else None
     e.head_anchors = head_anchors
+    e.shift_per_sample = 1 if shift_per_sample else 0
     return e
 
 
@@ -196,8 +198,10 @@ def conv_out_hw(h: int, w: int, k: int, stride: int, pad: int) -> Tuple[int, int
 
 def conv_fwd(x: torch.Tensor, w_packed: torch.Tensor, cout: int, k: int, stride: int, pad: int, *,
              s2d: bool = False, w_batch: int = 1, out: Optional[torch.Tensor] = None, epi: int = EPI_AFFINE,
-             act=None, scale=None, shift=None, res=None, sum_=None, sumsq=None) -> torch.Tensor:
-    """Implicit-GEMM conv.  x NHWC bf16; w_packed from pack_weight / dyn_aggregate."""
+             act=None, scale=None, shift=None, res=None, sum_=None, sumsq=None,
+             shift_per_sample: bool = False) -> torch.Tensor:
+    """Implicit-GEMM conv.  x NHWC bf16; w_packed from pack_weight / dyn_aggregate.
+    shift_per_sample: `shift` is (n, cout) — one bias row per image."""
     _require_cuda(x, w_packed)
     n, h, w, _ = x.shape
     hin, win = (h // 2, w // 2) if s2d else (h, w)
@@ -205,7 +209,7 @@ def conv_fwd(x: torch.Tensor, w_packed: torch.Tensor, cout: int, k: int, stride:
     if out is None:
         out = empty_act(n, ho, wo, cout, x.device)
     xv, yv = act_view(x), act_view(out)
-    e = _epilogue(epi, act, _f32(scale), _f32(shift), res, _f32(sum_), _f32(sumsq))
+    e = _epilogue(epi, act, _f32(scale), _f32(shift), res, _f32(sum_), _f32(sumsq), shift_per_sample=shift_per_sample)
     check(_lib.load().uavdet_conv_fwd(C.byref(xv), _ptr(w_packed), w_batch, cout, k, stride, pad, 1 if s2d else 0,
                                       C.byref(yv), C.byref(e), _stream()), "conv_fwd")
     return out
@@ -256,13 +260,16 @@ def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, k: int, stride: int, pad: int,
 
 
 def stem_fwd(x_nchw: torch.Tensor, w: torch.Tensor, k: int, stride: int, pad: int, *, epi: int = EPI_AFFINE,
-             act=None, scale=None, shift=None, sum_=None, sumsq=None, per_sample_w: bool = False) -> torch.Tensor:
+             act=None, scale=None, shift=None, sum_=None, sumsq=None, per_sample_w: bool = False,
+             pad_to_even: bool = False) -> torch.Tensor:
     _require_cuda(x_nchw, w)
     x_nchw = _f32(x_nchw)
     w = _f32(w)
     n, cin, h, ww = x_nchw.shape
     cout = w.shape[-4]
     ho, wo = conv_out_hw(h, ww, k, stride, pad)
+    if pad_to_even and ho % 2 == 1 and wo % 2 == 1:
+        ho, wo = ho + 1, wo + 1      # extra last row/column written as zeros (== the next conv's zero padding)
     out = empty_act(n, ho, wo, cout, x_nchw.device)
     yv = act_view(out)
     e = _epilogue(epi, act, _f32(scale), _f32(shift), None, _f32(sum_), _f32(sumsq),
@@ -360,6 +367,16 @@ def upsample2x_bwd(dy, out=None, accumulate=False):
     return out
 
 
+def upsample2x_add(b_low, a, a_mult=1.0, out=None):
+    """a_mult * a + nearest_upsample2x(b_low)."""
+    if out is None:
+        out = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
+    bv, av, ov = act_view(b_low), act_view(a), act_view(out)
+    check(_lib.load().uavdet_upsample2x_add(C.byref(bv), C.byref(av), float(a_mult), C.byref(ov), _stream()),
+          "upsample2x_add")
+    return out
+
+
 def add(a, b=None, out=None):
     if out is None:
         out = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
@@ -428,6 +445,58 @@ def dyn_aggregate(attn, bank, transposed=False, bias_bank=None):
                                            1 if transposed else 0, _ptr(out), _ptr(bias_bank), _ptr(bias_out),
                                            _stream()), "dyn_aggregate")
     return out, bias_out
+
+
+# --------------------------------------------------------------------------------------------
+# RTMUAVDet ops
+# --------------------------------------------------------------------------------------------
+def dwdynconv_fwd(x, channel_w, kernel_w, k, pad, out=None):
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    xv, yv = act_view(x), act_view(out)
+    check(_lib.load().uavdet_dwdynconv_fwd(C.byref(xv), _ptr(_f32(channel_w)), _ptr(_f32(kernel_w)), k, pad,
+                                           C.byref(yv), _stream()), "dwdynconv_fwd")
+    return out
+
+
+def linear(inp, w, bias=None, act=None):
+    rows, c = inp.shape
+    o = w.shape[0]
+    out = torch.empty((rows, o), dtype=torch.float32, device=inp.device)
+    check(_lib.load().uavdet_linear(_ptr(_f32(inp)), rows, c, _ptr(_f32(w)), _ptr(bias), o,
+                                    ACT[act] if not isinstance(act, int) else act, _ptr(out), _stream()), "linear")
+    return out
+
+
+def groupnorm1(a, gamma, beta, eps, b=None, out=None):
+    if out is None:
+        out = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
+    ws = torch.empty((2 * a.shape[0],), dtype=torch.float32, device=a.device)
+    av, yv = act_view(a), act_view(out)
+    bv = act_view(b) if b is not None else None
+    check(_lib.load().uavdet_groupnorm1(C.byref(av), C.byref(bv) if bv is not None else None, _ptr(_f32(gamma)),
+                                        _ptr(_f32(beta)), float(eps), _ptr(ws), C.byref(yv), _stream()), "groupnorm1")
+    return out
+
+
+def bilinear2x_fwd(x, out=None):
+    n, h, w, c = x.shape
+    if out is None:
+        out = empty_act(n, 2 * h, 2 * w, c, x.device)
+    xv, yv = act_view(x), act_view(out)
+    check(_lib.load().uavdet_bilinear2x_fwd(C.byref(xv), C.byref(yv), _stream()), "bilinear2x_fwd")
+    return out
+
+
+def rtm_head_post(bbox_logits, obj_logits, anchors_head):
+    b, a, sh, sw, _ = bbox_logits.shape
+    anc = torch.as_tensor(anchors_head).float().flatten().tolist()
+    arr = (C.c_float * len(anc))(*anc)
+    bbox = torch.empty_like(bbox_logits)
+    obj = torch.empty_like(obj_logits)
+    check(_lib.load().uavdet_rtm_head_post(_ptr(_f32(bbox_logits)), _ptr(_f32(obj_logits)), b, a, sh, sw, arr, _ptr(bbox),
+                                           _ptr(obj), _stream()), "rtm_head_post")
+    return bbox, obj
 
 
 def sgd_momentum(param, grad, buf, lr, momentum, grad_scale=1.0, first_step=False):

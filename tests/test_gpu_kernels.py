@@ -470,3 +470,90 @@ def test_sgd_momentum(lib):
         opt.step()
         ops.sgd_momentum(pd, gr.to(DEV), buf, 0.01, 0.7, first_step=(step == 0))
     torch.testing.assert_close(pd.cpu(), opt_p.detach(), rtol=1e-6, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# DySOEM / RTMUAVDet kernels
+# ------------------------------------------------------------------------------------------------
+def test_conv_fwd_per_sample_shift_and_stats(lib):
+    """Aggregated per-sample expert bias (DySOEM_SimFPN.py:83-91 by linearity) in both epilogues."""
+    ops = _ops(lib)
+    from multimodal_uav_det_b200._lib import EPI_STATS
+    n, cin, cout, h, w = 3, 64, 64, 16, 16
+    x, wt = _conv_case(n, cin, cout, 3, 1, h, w, seed=5)
+    g = torch.Generator().manual_seed(55)
+    bias = torch.randn(n, cout, generator=g)
+    ref = F.conv2d(x, wt, None, 1, 1) + bias.view(n, cout, 1, 1)
+    wp = ops.pack_weight(wt.to(DEV))
+    y = ops.conv_fwd(nhwc(x), wp, cout, 3, 1, 1, act="silu", shift=bias.to(DEV), shift_per_sample=True)
+    assert_close_bf16(to_nchw(y), F.silu(ref), "per-sample shift")
+    s1, s2 = torch.zeros(cout, device=DEV), torch.zeros(cout, device=DEV)
+    raw = ops.conv_fwd(nhwc(x), wp, cout, 3, 1, 1, epi=EPI_STATS, shift=bias.to(DEV), shift_per_sample=True, sum_=s1, sumsq=s2)
+    ops.check_device()
+    assert_close_bf16(to_nchw(raw), ref, "per-sample shift stats raw")
+    torch.testing.assert_close(s1.cpu(), ref.sum(dim=(0, 2, 3)), rtol=2e-3, atol=2e-2)
+    torch.testing.assert_close(s2.cpu(), (ref * ref).sum(dim=(0, 2, 3)), rtol=2e-3, atol=2e-2)
+
+
+def test_upsample2x_add(lib):
+    ops = _ops(lib)
+    g = torch.Generator().manual_seed(56)
+    a = bf16_round(torch.randn(2, 64, 12, 10, generator=g))
+    b = bf16_round(torch.randn(2, 64, 6, 5, generator=g))
+    got = ops.upsample2x_add(nhwc(b), nhwc(a), 2.0)
+    assert_close_bf16(to_nchw(got), 2 * a + F.interpolate(b, scale_factor=2, mode="nearest"), "upsample2x_add")
+
+
+@pytest.mark.parametrize("k", [1, 3, 5])
+def test_dwdynconv_matches_oracle_mdyconv_core(lib, k):
+    """MDyConv's per-sample depthwise conv + residual (RTMUAVDet.py:80-98)."""
+    ops = _ops(lib)
+    g = torch.Generator().manual_seed(57 + k)
+    n, c, h, w = 3, 64, 14, 12
+    x = bf16_round(torch.randn(n, c, h, w, generator=g))
+    ch_w, k_w = torch.randn(n, c, generator=g), torch.randn(n, k * k, generator=g)
+    filt = (k_w.view(n, 1, k, k) * ch_w.view(n, c, 1, 1)).reshape(n * c, 1, k, k)
+    ref = F.conv2d(x.reshape(1, n * c, h, w), filt, None, 1, k // 2, groups=n * c).view(n, c, h, w) + x
+    buf = torch.zeros(n, h, w, 192, dtype=torch.bfloat16, device=DEV)
+    ops.dwdynconv_fwd(nhwc(x), ch_w.to(DEV), k_w.to(DEV), k, k // 2, out=buf[..., 64:128])
+    assert_close_bf16(to_nchw(buf[..., 64:128]), ref, f"dwdynconv k={k}")
+    assert torch.all(buf[..., :64] == 0) and torch.all(buf[..., 128:] == 0)
+
+
+def test_linear_groupnorm_bilinear_rtm_head(lib):
+    from oracle import oracle as O
+    ops = _ops(lib)
+    g = torch.Generator().manual_seed(58)
+    inp, wgt, b = torch.randn(5, 70, generator=g), torch.randn(16, 70, generator=g), torch.randn(16, generator=g)
+    torch.testing.assert_close(ops.linear(inp.to(DEV), wgt.to(DEV), b.to(DEV), "relu").cpu(), F.relu(inp @ wgt.t() + b),
+                               rtol=1e-5, atol=1e-5)
+    x = bf16_round(torch.randn(3, 96, 10, 12, generator=g) * 2 + 0.5)
+    r = bf16_round(torch.randn(3, 96, 10, 12, generator=g))
+    gamma, beta = torch.rand(96, generator=g) + 0.5, torch.randn(96, generator=g) * 0.1
+    assert_close_bf16(to_nchw(ops.groupnorm1(nhwc(x), gamma.to(DEV), beta.to(DEV), 1e-5)),
+                      F.group_norm(x, 1, gamma, beta, 1e-5), "groupnorm")
+    assert_close_bf16(to_nchw(ops.groupnorm1(nhwc(x), gamma.to(DEV), beta.to(DEV), 1e-5, b=nhwc(r))),
+                      F.group_norm(x + r, 1, gamma, beta, 1e-5), "groupnorm(a+b)")
+    assert_close_bf16(to_nchw(ops.bilinear2x_fwd(nhwc(x))), F.interpolate(x, scale_factor=2, mode="bilinear"), "bilinear")
+    bl, ol = torch.randn(2, 3, 6, 7, 4, generator=g), torch.randn(2, 3, 6, 7, 1, generator=g)
+    anc = torch.tensor([[29.0, 23.0], [48.0, 30.0], [67.0, 38.0]])
+    bbox, obj = ops.rtm_head_post(bl.to(DEV), ol.to(DEV), anc)
+    torch.testing.assert_close(bbox.cpu(), O.decode_rtm(torch.sigmoid(bl), anc), rtol=2e-6, atol=2e-5)
+    torch.testing.assert_close(obj.cpu(), torch.sigmoid(ol), rtol=2e-6, atol=1e-6)
+
+
+def test_stem_zero_padded_odd_output(lib):
+    """RTM stem 5x5 s2 p1: 39 -> 18.. odd outputs are stored with a zero last row/column."""
+    ops = _ops(lib)
+    g = torch.Generator().manual_seed(59)
+    x = torch.rand(2, 3, 42, 42, generator=g)          # (42+2-5)//2+1 = 20 -> even, no padding
+    wt = torch.randn(32, 3, 5, 5, generator=g) * 0.2
+    y = ops.stem_fwd(x.to(DEV), wt.to(DEV), 5, 2, 1, act="silu", pad_to_even=True)
+    assert y.shape == (2, 20, 20, 32)
+    x = torch.rand(2, 3, 40, 40, generator=g)          # (40+2-5)//2+1 = 19 -> padded to 20
+    ref = F.silu(F.conv2d(x, wt, None, 2, 1))
+    y = ops.stem_fwd(x.to(DEV), wt.to(DEV), 5, 2, 1, act="silu", pad_to_even=True)
+    assert y.shape == (2, 20, 20, 32)
+    got = to_nchw(y)
+    assert_close_bf16(got[:, :, :19, :19], ref, "stem padded interior", rel=4e-3)
+    assert torch.all(got[:, :, 19, :] == 0) and torch.all(got[:, :, :, 19] == 0)

@@ -229,6 +229,76 @@ def test_deep_mini_darknet_train_step_sanity(lib):
     assert all(torch.isfinite(p.grad).all() for p in model.parameters())
 
 
+DYSOEM_HP = dict(anchors=[ANCHORS[2], ANCHORS[1], ANCHORS[0]], head_scales=[32, 16, 8], lr=1e-4, lr_scheduler=False,
+                 attention_temperature=30, num_dy_conv=[3, 3, 3], dy_kernel_size=[3, 3, 3], bbox_loss_fn="mse",
+                 loss_balancing=dict(obj_scales_w=[2.0, 1.0, 0.5], bbox_w=4.0, objectness_w=1.0, no_obj_w=4.0),
+                 optim=dict(name="SGD", momentum=0.7))
+
+
+@pytest.mark.parametrize("train", [False, True])
+def test_dysoem_simfpn_forward_matches_oracle(lib, train):
+    """DySOEM_SimFPN forward: aggregate-first dynamic kernels (1 GEMM instead of the reference's 3),
+    fused space-to-depth, SimFPN — against the oracle, which executes the reference's formulation."""
+    from oracle import oracle as O
+    from multimodal_uav_det_b200.model import DySOEM_SimFPN
+    from multimodal_uav_det_b200.utils.datatype import Config
+    torch.manual_seed(0)
+    model = DySOEM_SimFPN(hparams=Config(DYSOEM_HP))
+    randomize_bn(model)
+    model.train(train)
+    sd = copy.deepcopy(model.state_dict())
+    x = synth_input(4, 128)
+    with torch.no_grad():
+        want = O.dysoem_simfpn_forward(x, sd, 30.0, train=train)
+        got = model.to(DEV)(x.to(DEV), attn_temp=30.0)
+    from multimodal_uav_det_b200 import ops
+    ops.check_device()
+    for s, (g, (wb, wo)) in enumerate(zip(got, want)):
+        assert g.bbox.shape == wb.shape
+        rb, ro = rel_l2(g.bbox.cpu(), wb), rel_l2(g.obj.cpu(), wo)
+        print(f"dysoem train={train} scale {s}: rel_l2 bbox={rb:.4f} obj={ro:.4f}")
+        assert rb < 0.02 and ro < 0.02      # ~2 x 0.77 % reference self-drift (SURVEY §8a)
+
+
+def test_dysoem_golden_forward(lib):
+    """Against the committed reference output (tests/golden/model_forwards.pt, eval, 64x64)."""
+    import os
+    from multimodal_uav_det_b200.model import DySOEM_SimFPN
+    from multimodal_uav_det_b200.utils.datatype import Config
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "model_forwards.pt"), weights_only=False)["dy-soem_fpn"]
+    torch.manual_seed(gold["seed"])
+    model = DySOEM_SimFPN(hparams=Config(gold["hp"])).eval().to(DEV)
+    x = torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(gold["x_seed"]))
+    x[1] = x[1, :1].expand(3, -1, -1)
+    with torch.no_grad():
+        got = model(x.to(DEV), 30.0)
+    for g, (gb, go) in zip(got, gold["outs"]):
+        assert rel_l2(g.bbox.cpu(), gb) < 0.02 and rel_l2(g.obj.cpu(), go) < 0.02
+
+
+def test_rtmuavdet_forward_matches_oracle(lib):
+    """RTMUAVDet eval forward incl. sigmoid heads + in-forward decode, 640x640 (319x319 stem quirk)."""
+    from oracle import oracle as O
+    from multimodal_uav_det_b200.model import RTMUAVDet
+    anchors = torch.tensor([[[29, 23], [48, 30], [67, 38]], [[91, 54], [120, 75], [157, 60]]]).float()
+    torch.manual_seed(0)
+    model = RTMUAVDet([3, 640, 640], anchors, 1e-4)
+    randomize_bn(model)
+    model.eval()
+    sd = copy.deepcopy(model.state_dict())
+    x = synth_input(2, 640)
+    with torch.no_grad():
+        want = O.rtm_forward(x, sd, anchors)
+        got = model.to(DEV)(x.to(DEV))
+    from multimodal_uav_det_b200 import ops
+    ops.check_device()
+    for s, (g, (wb, wo)) in enumerate(zip(got, want)):
+        assert g.bbox.shape == wb.shape and g.obj.shape == wo.shape
+        rb, ro = rel_l2(g.bbox.cpu(), wb), rel_l2(g.obj.cpu(), wo)
+        print(f"rtm scale {s}: rel_l2 bbox={rb:.4f} obj={ro:.4f}")
+        assert rb < 0.01 and ro < 0.01      # ~2 x 0.40 % reference self-drift
+
+
 def test_detect_decode_nms_bit_exact_on_model_outputs(lib):
     """C1: BaselineModel forward + decode + NMS.  Kept indices must be bit-identical to the oracle's
     NMS on the SAME fp32 boxes/scores (the decode itself is checked to fp32 tolerance)."""
