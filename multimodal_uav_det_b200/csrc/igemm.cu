@@ -25,16 +25,35 @@
 namespace uavdet {
 using namespace sm100;
 
-constexpr int kIgemmThreads = 192;
-constexpr int kAccStride = 256;  // TMEM columns per accumulator buffer
+constexpr int kProdWarps = 4;      // TMA producer warps (P.prod_warps of them active)
+constexpr int kMmaWarp = 4;        // tcgen05.mma issuer (+ TMEM alloc)
+constexpr int kEpiWarp0 = 5;       // first of the 8 epilogue warps
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kIgemmThreads = (kProdWarps + 1 + kEpiWarps) * 32;   // 416
+constexpr int kAccStride = 256;    // TMEM columns per accumulator buffer
 
+// n / d for 0 <= n < 2^31 without a hardware divide (d fixed per launch, constants from the host).
+__device__ __forceinline__ int fast_div(int n, const FastDiv& f) {
+  return f.d == 1 ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr);
+}
+
+struct TileCoord { int n0, ow0, oh0, img; };
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& P, int tile) {
+  int m = fast_div(tile, P.fd_n);
+  TileCoord t;
+  t.n0 = (tile - m * P.n_tiles) * P.block_n;
+  int m2 = fast_div(m, P.fd_w);
+  t.ow0 = (m - m2 * P.tiles_w) * P.tile_w;
+  t.img = fast_div(m2, P.fd_h);
+  t.oh0 = (m2 - t.img * P.tiles_h) * P.tile_h;
+  return t;
+}
+
+// 32 accumulator columns of this lane's row -> (scale, shift, act, residual), in place.
 template <int ACT>
-__device__ __forceinline__ void affine_act_store(const uint32_t (&r)[32], const IgemmParams& P, int cg,
-                                                 __nv_bfloat16* out_px, const __nv_bfloat16* res_px,
-                                                 const float* shift) {
-  float v[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+__device__ __forceinline__ void affine_act(float (&v)[32], const IgemmParams& P, int cg, const float* shift,
+                                           const __nv_bfloat16* res_px) {
   if (P.scale) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
@@ -61,38 +80,63 @@ __device__ __forceinline__ void affine_act_store(const uint32_t (&r)[32], const 
       v[i + 6] += bf16_lo(rr.w); v[i + 7] += bf16_hi(rr.w);
     }
   }
-#pragma unroll
-  for (int i = 0; i < 32; i += 8) {
-    uint4 o;
-    o.x = pack_bf16x2(v[i], v[i + 1]);
-    o.y = pack_bf16x2(v[i + 2], v[i + 3]);
-    o.z = pack_bf16x2(v[i + 4], v[i + 5]);
-    o.w = pack_bf16x2(v[i + 6], v[i + 7]);
-    *reinterpret_cast<uint4*>(out_px + cg + i) = o;
-  }
 }
 
-// Sum v[c] over the 32 lanes of the warp for 32 columns; lane l returns column l's total.
-__device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
+// One 32-column chunk of one accumulator row: TMEM -> fp32 -> epilogue math -> bf16 -> swizzled staging row.
+// `chunk_in_slab` = which 32-column half of the (64-wide) slab; `sw_mask` = the row's swizzle XOR.
+__device__ __forceinline__ void stage_chunk(const IgemmParams& P, uint32_t taddr, int cg, bool valid, const float* shift,
+                                            const __nv_bfloat16* res_px, uint8_t* srow, int chunk_in_slab, int sw_mask,
+                                            bool release, uint32_t tempty, int lane) {
+  uint32_t r[32];
+  tmem_ld_32x32(taddr, r);
+  tmem_ld_wait();
+  if (release) {
+    // last TMEM read of this tile by this warp: hand the accumulator buffer back to the MMA warp
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty);
+  }
+  float v[32];
 #pragma unroll
-  for (int step = 16; step >= 1; step >>= 1) {
-    const bool upper = (lane & step) != 0;
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  if (P.epi == UAVDET_EPI_STATS) {
+    if (shift) {
 #pragma unroll
-    for (int i = 0; i < step; ++i) {
-      float send = upper ? v[i] : v[i + step];
-      float keep = upper ? v[i + step] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+      for (int i = 0; i < 32; i += 4) {
+        float4 s4 = __ldg(reinterpret_cast<const float4*>(shift + cg + i));
+        v[i] += s4.x; v[i + 1] += s4.y; v[i + 2] += s4.z; v[i + 3] += s4.w;
+      }
+    }
+  } else if (valid) {
+    switch (P.act) {
+      case UAVDET_ACT_LEAKY: affine_act<UAVDET_ACT_LEAKY>(v, P, cg, shift, res_px); break;
+      case UAVDET_ACT_SILU: affine_act<UAVDET_ACT_SILU>(v, P, cg, shift, res_px); break;
+      case UAVDET_ACT_RELU: affine_act<UAVDET_ACT_RELU>(v, P, cg, shift, res_px); break;
+      case UAVDET_ACT_GELU: affine_act<UAVDET_ACT_GELU>(v, P, cg, shift, res_px); break;
+      default: affine_act<UAVDET_ACT_NONE>(v, P, cg, shift, res_px); break;
     }
   }
-  return v[0];
+  // rows outside the image / tile carry garbage or bias only: stage zeros (the clipped TMA store skips them and
+  // they must not enter the statistics)
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 o;
+    o.x = valid ? pack_bf16x2(v[8 * j + 0], v[8 * j + 1]) : 0u;
+    o.y = valid ? pack_bf16x2(v[8 * j + 2], v[8 * j + 3]) : 0u;
+    o.z = valid ? pack_bf16x2(v[8 * j + 4], v[8 * j + 5]) : 0u;
+    o.w = valid ? pack_bf16x2(v[8 * j + 6], v[8 * j + 7]) : 0u;
+    const int chunk = (chunk_in_slab * 4 + j) ^ sw_mask;
+    *reinterpret_cast<uint4*>(srow + chunk * 16) = o;
+  }
 }
 
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+             const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapOutTail,
              const __grid_constant__ IgemmParams P) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~(uintptr_t)1023);
+  // 1024-byte alignment is what SWIZZLE_128B needs for TMA and UMMA; no static shared memory is used,
+  // so the dynamic window starts at the (aligned) base of the CTA's shared memory.
+  extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -100,14 +144,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   const int b_bytes = P.block_n * P.block_k * 2;
   const int stage_bytes = a_bytes + b_bytes;
   const int a_tx = P.tile_w * P.tile_h * P.block_k * 2;  // bytes the A box actually delivers
-  uint8_t* ctrl = smem + (size_t)P.stages * stage_bytes;
+  uint8_t* staging = smem + (size_t)P.stages * stage_bytes;  // output staging, 1024-aligned (stage_bytes is)
+  uint8_t* ctrl = staging + P.staging_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   volatile uint32_t* dead = tmem_ptr + 1;
-  float* stat = reinterpret_cast<float*>(tmem_ptr + 4);  // [2 acc][2 (sum,sumsq)][256]
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) {
@@ -116,15 +160,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);
-      mbar_init(smem_u32(&tempty_bar[a]), 4);
+      mbar_init(smem_u32(&tempty_bar[a]), kEpiWarps);
     }
     *dead = 0;
     fence_barrier_init();
     prefetch_tensormap(&mapA);
     prefetch_tensormap(&mapB);
+    if (P.epi != UAVDET_EPI_HEAD) prefetch_tensormap(&mapOut);
   }
-  for (int i = threadIdx.x; i < 2 * 2 * 256; i += kIgemmThreads) stat[i] = 0.f;
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tmem_alloc(smem_u32(tmem_ptr), 512);
     tmem_relinquish();
   }
@@ -135,55 +179,63 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 
   const int num_kb = P.num_taps * P.kc_per_tap;
 
-  if (warp == 0) {
-    // ============================ TMA producer ============================
-    if (elect_one()) {
+  if (warp < kProdWarps) {
+    // ============================ TMA producers ===========================
+    // k-block g (counted across this CTA's tiles) belongs to producer warp g % prod_warps; `stages` is a
+    // multiple of prod_warps, so a pipeline stage is always refilled by the same warp (program order keeps the
+    // two uses of its empty barrier apart).
+    if (warp < P.prod_warps && elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % P.n_tiles;
-        int m_tile = tile / P.n_tiles;
-        const int tw = m_tile % P.tiles_w; m_tile /= P.tiles_w;
-        const int th = m_tile % P.tiles_h;
-        const int img = m_tile / P.tiles_h;
-        const int ow0 = tw * P.tile_w, oh0 = th * P.tile_h, n0 = n_tile * P.block_n;
+      uint32_t g = 0;
+      const uint32_t pmask = (uint32_t)P.prod_warps - 1u;
+      for (int tile = blockIdx.x, tl = 0; tile < P.total_tiles; tile += gridDim.x, ++tl) {
+        const TileCoord tc = decode_tile(P, tile);
+        const bool tr = P.trace && blockIdx.x == 0 && tl < P.trace_tiles && warp == 0;
+        if (tr) P.trace[tl * 16 + 0] = clock64();
         for (int t = 0; t < P.num_taps; ++t) {
-          const ConvTap tap = P.taps[t];
-          for (int kc = 0; kc < P.kc_per_tap; ++kc) {
-            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u, dead, P.watchdog, 0x1u);
-            const uint32_t fb = smem_u32(&full_bar[stage]);
-            mbar_arrive_expect_tx(fb, (uint32_t)(a_tx + b_bytes));
-            uint8_t* sa = smem + (size_t)stage * stage_bytes;
-            tma_load_5d(smem_u32(sa), &mapA, fb, tap.c_off + kc * P.block_k, ow0 + tap.dw, tap.p,
-                        oh0 + tap.dh, img);
-            tma_load_3d(smem_u32(sa + a_bytes), &mapB, fb, tap.w_koff + kc * P.block_k, n0,
-                        P.w_batch > 1 ? img : 0);
+          for (int kc = 0; kc < P.kc_per_tap; ++kc, ++g) {
+            if ((g & pmask) == (uint32_t)warp) {
+              const ConvTap tap = P.taps[t];
+              mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u, dead, P.watchdog, 0x1u);
+              const uint32_t fb = smem_u32(&full_bar[stage]);
+              mbar_arrive_expect_tx(fb, (uint32_t)(a_tx + b_bytes));
+              uint8_t* sa = smem + (size_t)stage * stage_bytes;
+              tma_load_5d(smem_u32(sa), &mapA, fb, tap.c_off + kc * P.block_k, tc.ow0 + tap.dw, tap.p,
+                          tc.oh0 + tap.dh, tc.img);
+              tma_load_3d(smem_u32(sa + a_bytes), &mapB, fb, tap.w_koff + kc * P.block_k, tc.n0,
+                          P.w_batch > 1 ? tc.img : 0);
+            }
             if (++stage == P.stages) { stage = 0; phase ^= 1u; }
           }
         }
+        if (tr) P.trace[tl * 16 + 1] = clock64();
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ============================ MMA issuer ==============================
     if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(P.block_n, 0, 0);
       const uint32_t layout = (P.block_k == 64) ? 2u : 4u;      // SWIZZLE_128B : SWIZZLE_64B
       const uint32_t sbo = 8u * (uint32_t)P.block_k * 2u;        // 8 rows of one swizzle atom
+      const int ksteps = P.block_k / 16;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x, tl = 0; tile < P.total_tiles; tile += gridDim.x, ++tl) {
+        const bool tr = P.trace && blockIdx.x == 0 && tl < P.trace_tiles;
+        if (tr) P.trace[tl * 16 + 2] = clock64();
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u, dead, P.watchdog, 0x2u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(smem_u32(&full_bar[stage]), phase, dead, P.watchdog, 0x4u);
+          if (tr && kb == 0) P.trace[tl * 16 + 3] = clock64();
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint64_t a_desc = make_smem_desc(sa, 16, sbo, layout);
           const uint64_t b_desc = make_smem_desc(sa + a_bytes, 16, sbo, layout);
-          const int ksteps = P.block_k / 16;
           for (int k = 0; k < ksteps; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the >>4 field
             tc_mma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
@@ -193,132 +245,284 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           if (++stage == P.stages) { stage = 0; phase ^= 1u; }
         }
         tc_commit(smem_u32(&tfull_bar[acc]));
+        if (tr) P.trace[tl * 16 + 4] = clock64();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
-    // ============================ epilogue (warps 2..5) ====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    // ============================ epilogue (8 warps) =======================
+    // Two warps per TMEM lane quarter (q = warp % 4).  bf16 outputs go TMEM -> registers -> swizzled smem ->
+    // TMA store, so global writes are full 128-byte rows whatever the channel stride of the tensor is.
+    const int ew = warp - kEpiWarp0;
+    const int q = warp & 3;
+    const int half = ew >> 2;
     const int row = q * 32 + lane;
     const int hl = row / P.tile_w, wl = row - hl * P.tile_w;
-    const int e_tid = (warp - 2) * 32 + lane;
+    const int kp = P.tile_w * P.tile_h;
+    const int n_slabs = P.block_n / P.slab_w;
+    const int row_bytes = P.slab_w * 2;
+    const int sw_mask = (P.slab_w == 64) ? (row & 7) : ((row >> 1) & 3);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      const int n_tile = tile % P.n_tiles;
-      int m_tile = tile / P.n_tiles;
-      const int tw = m_tile % P.tiles_w; m_tile /= P.tiles_w;
-      const int th = m_tile % P.tiles_h;
-      const int img = m_tile / P.tiles_h;
-      const int oh = th * P.tile_h + hl, ow = tw * P.tile_w + wl;
-      const int n0 = n_tile * P.block_n;
-      const bool valid = (row < P.tile_w * P.tile_h) && (oh < P.ho) && (ow < P.wo);
 
-      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, dead, P.watchdog, 0x8u);
-      tc_fence_after();
-      const uint32_t tbase = tmem_base + (uint32_t)(acc * kAccStride) + ((uint32_t)(q * 32) << 16);
-
-      if (P.epi == UAVDET_EPI_HEAD) {
-        uint32_t r[16];
-        tmem_ld_32x16(tbase, r);
-        tmem_ld_wait();
-        if (valid) {
-          const int A = P.head_anchors;
-          const size_t hw = (size_t)P.ho * P.wo;
-          const size_t px = (size_t)oh * P.wo + ow;
-          for (int a = 0; a < A; ++a) {
-            float o = __uint_as_float(r[a]) + (P.shift ? __ldg(P.shift + a) : 0.f);
-            P.head_obj[((size_t)img * A + a) * hw + px] = o;
-          }
-          for (int a = 0; a < A; ++a) {
-            float4 b;
-            b.x = __uint_as_float(r[A + 4 * a + 0]);
-            b.y = __uint_as_float(r[A + 4 * a + 1]);
-            b.z = __uint_as_float(r[A + 4 * a + 2]);
-            b.w = __uint_as_float(r[A + 4 * a + 3]);
-            if (P.shift) {
-              b.x += __ldg(P.shift + A + 4 * a + 0); b.y += __ldg(P.shift + A + 4 * a + 1);
-              b.z += __ldg(P.shift + A + 4 * a + 2); b.w += __ldg(P.shift + A + 4 * a + 3);
-            }
-            reinterpret_cast<float4*>(P.head_bbox)[((size_t)img * A + a) * hw + px] = b;
-          }
-        }
-      } else {
-        __nv_bfloat16* out_px =
-            P.out + (size_t)img * P.out_sn + (size_t)oh * P.out_sh + (size_t)ow * P.out_sw;
-        const __nv_bfloat16* res_px =
-            P.res ? P.res + (size_t)img * P.res_sn + (size_t)oh * P.res_sh + (size_t)ow * P.res_sw
-                  : nullptr;
-        const float* shift = P.shift ? P.shift + (size_t)img * P.shift_sn : nullptr;
-        for (int c0 = 0; c0 < P.block_n; c0 += 32) {
-          const int cg = n0 + c0;
-          if (cg >= P.cout) break;  // uniform: last n-tile of a cout that is not a block_n multiple
-          uint32_t r[32];
-          tmem_ld_32x32(tbase + (uint32_t)c0, r);
+    if (P.epi == UAVDET_EPI_HEAD) {
+      for (int tile = blockIdx.x, tl = 0; tile < P.total_tiles; tile += gridDim.x, ++tl) {
+        const TileCoord tc = decode_tile(P, tile);
+        const int oh = tc.oh0 + hl, ow = tc.ow0 + wl;
+        const bool valid = (row < kp) && (oh < P.ho) && (ow < P.wo);
+        mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, dead, P.watchdog, 0x8u);
+        tc_fence_after();
+        if (half == 0) {
+          uint32_t r[16];
+          tmem_ld_32x16(tmem_base + (uint32_t)(acc * kAccStride) + ((uint32_t)(q * 32) << 16), r);
           tmem_ld_wait();
+          if (valid) {
+            const int A = P.head_anchors;
+            const size_t hw = (size_t)P.ho * P.wo;
+            const size_t px = (size_t)oh * P.wo + ow;
+            for (int a = 0; a < A; ++a) {
+              float o = __uint_as_float(r[a]) + (P.shift ? __ldg(P.shift + a) : 0.f);
+              P.head_obj[((size_t)tc.img * A + a) * hw + px] = o;
+            }
+            for (int a = 0; a < A; ++a) {
+              float4 b;
+              b.x = __uint_as_float(r[A + 4 * a + 0]);
+              b.y = __uint_as_float(r[A + 4 * a + 1]);
+              b.z = __uint_as_float(r[A + 4 * a + 2]);
+              b.w = __uint_as_float(r[A + 4 * a + 3]);
+              if (P.shift) {
+                b.x += __ldg(P.shift + A + 4 * a + 0); b.y += __ldg(P.shift + A + 4 * a + 1);
+                b.z += __ldg(P.shift + A + 4 * a + 2); b.w += __ldg(P.shift + A + 4 * a + 3);
+              }
+              reinterpret_cast<float4*>(P.head_bbox)[((size_t)tc.img * A + a) * hw + px] = b;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    } else if (P.epi_mode != 0) {
+      // ---- warp-private epilogue: every warp stages and TMA-stores its own 32 accumulator rows -----------
+      //   mode 1: the 32 rows are a {bw x bh} rectangle of the output tile (tile_w | 32 or 32 | tile_w);
+      //   mode 2: the tile spans full image rows of a pixel-dense tensor, so the rows are a run of 32
+      //           pixels of the flattened [C][H*W][N] view (a shorter tail map serves the tile's last rows).
+      // No CTA-wide synchronisation: the only waits are this warp's own TMA-store reads.
+      // Work units (tile, slab) alternate between the two warps of a quarter.  Batch statistics are summed
+      // per warp in registers (lane <-> column pair) and flushed once per CTA / change of channel block.
+      const int wbuf_bytes = 32 * row_bytes;
+      uint8_t* wbuf0 = staging + (size_t)ew * P.epi_bufs * wbuf_bytes;
+      const int rows_here = min(32, max(0, kp - q * 32));            // live tile rows of this warp
+      const bool use_tail = rows_here > 0 && rows_here < 32;
+      const int bw = P.tile_w < 32 ? P.tile_w : 32;
+      const int q_ow = (q * 32) % P.tile_w, q_oh = (q * 32) / P.tile_w;   // mode 1 box origin inside the tile
+      const bool single = n_slabs == 1;
+      float st[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f; }
+      int cur_n0 = -1;
+      uint32_t ucount = 0;
+      auto flush_stats = [&](int n0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int sl = single ? 0 : half + 2 * j;
+          if (sl < n_slabs && (!single || j == 0)) {
+            float s0 = st[j][0], s1 = st[j][1], q0 = st[j][2], q1 = st[j][3];
+            int pair = lane;
+            bool owner = true;
+            if (P.slab_w == 32) {
+              s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+              q0 += __shfl_xor_sync(0xffffffffu, q0, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+              pair = lane & 15;
+              owner = lane < 16;
+            }
+            const int col = n0 + sl * P.slab_w + 2 * pair;
+            if (owner && col < P.cout) {
+              atomicAdd(P.sum + col, s0); atomicAdd(P.sum + col + 1, s1);
+              atomicAdd(P.sumsq + col, q0); atomicAdd(P.sumsq + col + 1, q1);
+            }
+          }
+          st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f;
+        }
+      };
+      for (int tile = blockIdx.x, tl = 0; tile < P.total_tiles; tile += gridDim.x, ++tl) {
+        const TileCoord tc = decode_tile(P, tile);
+        const int oh = tc.oh0 + hl, ow = tc.ow0 + wl;
+        const bool valid = (row < kp) && (oh < P.ho) && (ow < P.wo);
+        const bool tr = P.trace && blockIdx.x == 0 && tl < P.trace_tiles && ew == 0 && lane == 0;
+        if (P.epi == UAVDET_EPI_STATS && tc.n0 != cur_n0) {
+          if (cur_n0 >= 0) flush_stats(cur_n0);
+          cur_n0 = tc.n0;
+        }
+        const __nv_bfloat16* res_px =
+            P.res ? P.res + (size_t)tc.img * P.res_sn + (size_t)oh * P.res_sh + (size_t)ow * P.res_sw : nullptr;
+        const float* shift = P.shift ? P.shift + (size_t)tc.img * P.shift_sn : nullptr;
+        if (tr) P.trace[tl * 16 + 5] = clock64();
+        mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, dead, P.watchdog, 0x8u);
+        if (tr) P.trace[tl * 16 + 6] = clock64();
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + (uint32_t)(acc * kAccStride) + ((uint32_t)(q * 32) << 16);
+        const uint32_t tempty = smem_u32(&tempty_bar[acc]);
+        const bool mine = !single || ((tl & 1) == half);
+        if (!mine) {
+          // nothing to read from this accumulator: still one arrival per warp per tile
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int sl = single ? 0 : half + 2 * j;
+            if (sl < n_slabs && (!single || j == 0)) {
+              const int cs = tc.n0 + sl * P.slab_w;                  // first global channel of the slab
+              uint8_t* wbuf = wbuf0 + (P.epi_bufs == 2 ? (ucount & 1u) * wbuf_bytes : 0);
+              ++ucount;
+              // the TMA store that last read this buffer must be done reading it
+              if (lane == 0) {
+                if (P.epi_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+              }
+              __syncwarp();
+              const bool last = single || (sl + 2 >= n_slabs);
+              uint8_t* srow = wbuf + lane * row_bytes;
+              const int c0 = sl * P.slab_w;                          // accumulator column of the slab
+              if (P.slab_w == 64) {
+                stage_chunk(P, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, srow, 0, sw_mask, false,
+                            tempty, lane);
+                stage_chunk(P, tbase + (uint32_t)(c0 + 32), tc.n0 + c0 + 32, valid, shift, res_px, srow, 1, sw_mask,
+                            last, tempty, lane);
+              } else {
+                stage_chunk(P, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, srow, 0, sw_mask, last, tempty,
+                            lane);
+              }
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                if (P.epi_mode == 1) {
+                  if (rows_here > 0) {
+                    tma_store_5d(&mapOut, smem_u32(wbuf), cs, tc.ow0 + q_ow, 0, tc.oh0 + q_oh, tc.img);
+                    tma_store_commit();
+                  }
+                } else if (rows_here > 0) {
+                  tma_store_3d(use_tail ? &mapOutTail : &mapOut, smem_u32(wbuf), cs, tc.oh0 * P.wo + q * 32, tc.img);
+                  tma_store_commit();
+                }
+              }
+              if (P.epi == UAVDET_EPI_STATS) {
+                // column sums of the staged (bf16-rounded) rows: exactly the values the BatchNorm that follows
+                // will normalise.  Conflict-free: a row is one 128-byte line (slab 64) / two rows are (slab 32).
+                float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                if (P.slab_w == 64) {
+#pragma unroll 8
+                  for (int r_ = 0; r_ < 32; ++r_) {
+                    const int word = (((lane >> 2) ^ (r_ & 7)) << 2) | (lane & 3);
+                    const uint32_t u = *reinterpret_cast<const uint32_t*>(wbuf + r_ * 128 + word * 4);
+                    const float a = bf16_lo(u), b = bf16_hi(u);
+                    s0 += a; s1 += b; q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1);
+                  }
+                } else {
+                  const int pair = lane & 15;
+#pragma unroll 8
+                  for (int i = 0; i < 16; ++i) {
+                    const int r_ = 2 * i + (lane >> 4);
+                    const int word = (((pair >> 2) ^ ((r_ >> 1) & 3)) << 2) | (pair & 3);
+                    const uint32_t u = *reinterpret_cast<const uint32_t*>(wbuf + r_ * 64 + word * 4);
+                    const float a = bf16_lo(u), b = bf16_hi(u);
+                    s0 += a; s1 += b; q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1);
+                  }
+                }
+                st[j][0] += s0; st[j][1] += s1; st[j][2] += q0; st[j][3] += q1;
+              }
+            }
+          }
+        }
+        if (tr) P.trace[tl * 16 + 7] = clock64();
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+      if (P.epi == UAVDET_EPI_STATS && cur_n0 >= 0) flush_stats(cur_n0);
+      if (lane == 0) tma_store_wait_all();   // smem must stay valid until the last store has read it
+    } else {
+      // ---- CTA-wide epilogue (tiles whose 32-row groups are not rectangles) ------------------------------
+      // The 8 warps fill one 128-row slab (two 32-column halves), one thread TMA-stores it; two slabs in
+      // flight.  Statistics: shuffle-folded column sums of the staged slab, one global reduction per column.
+      const int e_tid = ew * 32 + lane;
+      const int slab_bytes = 128 * row_bytes;
+      const int chunks_per_slab = P.slab_w / 32;              // 2 (slab 64) or 1 (slab 32)
+      uint32_t slab_counter = 0;
+      for (int tile = blockIdx.x, tl = 0; tile < P.total_tiles; tile += gridDim.x, ++tl) {
+        const TileCoord tc = decode_tile(P, tile);
+        const int oh = tc.oh0 + hl, ow = tc.ow0 + wl;
+        const bool valid = (row < kp) && (oh < P.ho) && (ow < P.wo);
+        const bool tr = P.trace && blockIdx.x == 0 && tl < P.trace_tiles && ew == 0 && lane == 0;
+        const __nv_bfloat16* res_px =
+            P.res ? P.res + (size_t)tc.img * P.res_sn + (size_t)oh * P.res_sh + (size_t)ow * P.res_sw : nullptr;
+        const float* shift = P.shift ? P.shift + (size_t)tc.img * P.shift_sn : nullptr;
+        if (tr) P.trace[tl * 16 + 5] = clock64();
+        mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, dead, P.watchdog, 0x8u);
+        if (tr) P.trace[tl * 16 + 6] = clock64();
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + (uint32_t)(acc * kAccStride) + ((uint32_t)(q * 32) << 16);
+        const uint32_t tempty = smem_u32(&tempty_bar[acc]);
+        for (int sl = 0; sl < n_slabs; ++sl, ++slab_counter) {
+          const int cs = tc.n0 + sl * P.slab_w;
+          uint8_t* sbuf = staging + (slab_counter & 1u) * slab_bytes;
+          if (e_tid == 0) tma_store_wait_read<1>();           // the store that read this buffer two slabs ago
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          const bool last = sl == n_slabs - 1;
+          if (half < chunks_per_slab) {
+            const int c0 = sl * P.slab_w + half * 32;
+            stage_chunk(P, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, sbuf + row * row_bytes, half,
+                        sw_mask, last, tempty, lane);
+            fence_proxy_async();
+          } else if (last) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty);
+          }
+          asm volatile("bar.sync 3, 256;" ::: "memory");
+          if (e_tid == 0) {
+            tma_store_5d(&mapOut, smem_u32(sbuf), cs, tc.ow0, 0, tc.oh0, tc.img);
+            tma_store_commit();
+          }
           if (P.epi == UAVDET_EPI_STATS) {
-            float v[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = valid ? __uint_as_float(r[i]) : 0.f;
-            if (shift && valid) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                float4 s = __ldg(reinterpret_cast<const float4*>(shift + cg + i));
-                v[i] += s.x; v[i + 1] += s.y; v[i + 2] += s.z; v[i + 3] += s.w;
-              }
+            // warp -> `ppw` column pairs, lane -> (pair, row group g) with rows g, g+groups, ... so the 32
+            // lanes of a load hit 32 different banks; row groups are folded with xor-shuffles.
+            const int ppw = P.slab_w >> 4;                    // 4 (slab 64) | 2 (slab 32)
+            const int groups = 32 / ppw;                      // 8 | 16
+            const int p_ = lane & (ppw - 1), g = lane / ppw;
+            const int pr = ew * ppw + p_;                     // column pair inside the slab
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 4
+            for (int r_ = g; r_ < 128; r_ += groups) {
+              const int m_ = (P.slab_w == 64) ? (r_ & 7) : ((r_ >> 1) & 3);
+              const int word = (((pr >> 2) ^ m_) << 2) | (pr & 3);
+              const uint32_t u = *reinterpret_cast<const uint32_t*>(sbuf + r_ * row_bytes + word * 4);
+              const float a = bf16_lo(u), b = bf16_hi(u);
+              s0 += a; s1 += b; q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1);
             }
-            if (valid) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                uint4 o;
-                o.x = pack_bf16x2(v[i], v[i + 1]);
-                o.y = pack_bf16x2(v[i + 2], v[i + 3]);
-                o.z = pack_bf16x2(v[i + 4], v[i + 5]);
-                o.w = pack_bf16x2(v[i + 6], v[i + 7]);
-                *reinterpret_cast<uint4*>(out_px + cg + i) = o;
-              }
+            for (int off = ppw; off < 32; off <<= 1) {
+              s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+              s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+              q0 += __shfl_xor_sync(0xffffffffu, q0, off);
+              q1 += __shfl_xor_sync(0xffffffffu, q1, off);
             }
-            float sq[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
-            const float s1 = warp_column_sums(v, lane);
-            const float s2 = warp_column_sums(sq, lane);
-            atomicAdd(&stat[(acc * 2 + 0) * 256 + c0 + lane], s1);
-            atomicAdd(&stat[(acc * 2 + 1) * 256 + c0 + lane], s2);
-          } else if (valid) {
-            switch (P.act) {
-              case UAVDET_ACT_LEAKY: affine_act_store<UAVDET_ACT_LEAKY>(r, P, cg, out_px, res_px, shift); break;
-              case UAVDET_ACT_SILU: affine_act_store<UAVDET_ACT_SILU>(r, P, cg, out_px, res_px, shift); break;
-              case UAVDET_ACT_RELU: affine_act_store<UAVDET_ACT_RELU>(r, P, cg, out_px, res_px, shift); break;
-              case UAVDET_ACT_GELU: affine_act_store<UAVDET_ACT_GELU>(r, P, cg, out_px, res_px, shift); break;
-              default: affine_act_store<UAVDET_ACT_NONE>(r, P, cg, out_px, res_px, shift); break;
+            const int col = cs + 2 * pr;
+            if (lane < ppw && col < P.cout) {
+              atomicAdd(P.sum + col, s0); atomicAdd(P.sum + col + 1, s1);
+              atomicAdd(P.sumsq + col, q0); atomicAdd(P.sumsq + col + 1, q1);
             }
           }
         }
+        if (tr) P.trace[tl * 16 + 7] = clock64();
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
-      // TMEM buffer drained: hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
-
-      if (P.epi == UAVDET_EPI_STATS) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int c = e_tid; c < P.block_n; c += 128) {
-          if (n0 + c < P.cout) {
-            atomicAdd(P.sum + n0 + c, stat[(acc * 2 + 0) * 256 + c]);
-            atomicAdd(P.sumsq + n0 + c, stat[(acc * 2 + 1) * 256 + c]);
-          }
-          stat[(acc * 2 + 0) * 256 + c] = 0.f;
-          stat[(acc * 2 + 1) * 256 + c] = 0.f;
-        }
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (e_tid == 0) tma_store_wait_all();
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -394,24 +598,61 @@ int make_act_map(CUtensorMap* m, const uavdet_act* x, int parity, int box_c, int
   return encode_tensor_map(m, x->ptr, 5, dims, str, box, box_c * 2);
 }
 
-// Pick the output tile rectangle (tile_w * tile_h <= 128) that wastes the fewest MMA rows;
-// ties go to the squarest tile (smallest halo, best L2 reuse across the filter taps).
-void choose_tile(int ho, int wo, int* tile_w, int* tile_h) {
-  double best_eff = -1.0;
-  int best_halo = 1 << 30, bw = 1, bh = 1;
+static long long* g_trace = nullptr;
+static int g_trace_tiles = 0;
+void get_trace(long long** ptr, int* tiles) { *ptr = g_trace; *tiles = g_trace_tiles; }
+
+// 5-D output map for the TMA-store epilogue: [C, Wo, 1, Ho, N] with arbitrary pixel strides (elements), so the
+// same code writes plain NHWC tensors, channel slices and the parity planes of a stride-2 data gradient.
+int make_out_map(CUtensorMap* m, void* ptr, int n, int ho, int wo, int c, long long sn, long long sh, long long sw,
+                 int box_c, int box_w, int box_h) {
+  uint64_t dims[5] = {(uint64_t)c, (uint64_t)wo, 1, (uint64_t)ho, (uint64_t)n};
+  uint64_t str[4] = {(uint64_t)sw * 2, (uint64_t)sh * 2, (uint64_t)sh * 2, (uint64_t)sn * 2};
+  uint32_t box[5] = {(uint32_t)box_c, (uint32_t)box_w, 1u, (uint32_t)box_h, 1u};
+  return encode_tensor_map(m, ptr, 5, dims, str, box, box_c * 2);
+}
+
+// Pick the output tile rectangle (tile_w * tile_h <= 128) and the epilogue flavour it allows.
+//   mode 1: every 32-row group of the tile is a rectangle (tile_w | 32 with whole box rows, or 32 | tile_w);
+//   mode 2: the tile spans full image rows of a pixel-dense tensor (32-row groups are pixel runs);
+//   mode 0: anything else (CTA-wide slab epilogue).
+// The warp-private modes are taken unless they waste > 10 % more MMA rows than the best rectangle; ties go to
+// the squarest tile (smallest halo, best L2 reuse across the filter taps).
+void choose_tile(int ho, int wo, bool dense_rows, int* tile_w, int* tile_h, int* epi_mode) {
+  double best_eff[2] = {-1.0, -1.0};          // [0] any tile, [1] warp-private tiles
+  int best_halo[2] = {1 << 30, 1 << 30}, bw[2] = {1, 1}, bh[2] = {1, 1}, bm[2] = {0, 0};
   const int max_w = wo < 128 ? wo : 128;
   for (int tw = 1; tw <= max_w; ++tw) {
     int th = 128 / tw;
     if (th > ho) th = ho;
-    const double tiles = (double)ceil_div(ho, th) * ceil_div(wo, tw);
-    const double eff = (double)ho * wo / (tiles * 128.0);
-    const int halo = (tw + 2) * (th + 2);
-    if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && halo < best_halo)) {
-      best_eff = eff; best_halo = halo; bw = tw; bh = th;
+    for (int pass = 0; pass < 2; ++pass) {
+      int t_h = th, mode = 0;
+      if (pass == 1) {
+        if (tw == wo && dense_rows && (long long)ho * wo >= 32) {
+          mode = 2;
+        } else if (32 % tw == 0) {
+          const int rows = 32 / tw;
+          t_h = (th / rows) * rows;
+          if (t_h == 0) continue;
+          mode = 1;
+        } else if (tw % 32 == 0) {
+          mode = 1;
+        } else {
+          continue;
+        }
+      }
+      const double tiles = (double)ceil_div(ho, t_h) * ceil_div(wo, tw);
+      const double eff = (double)ho * wo / (tiles * 128.0);
+      const int halo = (tw + 2) * (t_h + 2);
+      if (eff > best_eff[pass] + 1e-9 || (eff > best_eff[pass] - 1e-9 && halo < best_halo[pass])) {
+        best_eff[pass] = eff; best_halo[pass] = halo; bw[pass] = tw; bh[pass] = t_h; bm[pass] = mode;
+      }
     }
   }
-  *tile_w = bw;
-  *tile_h = bh;
+  const int pick = (best_eff[1] >= 0.9 * best_eff[0]) ? 1 : 0;
+  *tile_w = bw[pick];
+  *tile_h = bh[pick];
+  *epi_mode = bm[pick];
 }
 
 __global__ void fill_plane_kernel(IgemmParams P) {
@@ -450,9 +691,38 @@ static int pick_block_n(int cout) {
 
 int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int w_rows, int k_total,
                  int w_batch, IgemmParams& P, cudaStream_t st) {
-  CUtensorMap mapA, mapB;
+  CUtensorMap mapA, mapB, mapOut, mapOutTail;
   int rc = make_act_map(&mapA, a_src, parity, P.block_k, P.tile_w, P.tile_h);
   if (rc) return rc;
+  P.slab_w = (P.block_n % 64 == 0) ? 64 : 32;
+  const int kp = P.tile_w * P.tile_h;
+  if (P.epi == UAVDET_EPI_HEAD) {
+    P.epi_mode = 0;
+    mapOut = mapA;   // unused by the HEAD epilogue
+    mapOutTail = mapA;
+  } else if (P.epi_mode == 1) {
+    const int bw = P.tile_w < 32 ? P.tile_w : 32;
+    rc = make_out_map(&mapOut, P.out, P.n_img, P.ho, P.wo, P.cout, P.out_sn, P.out_sh, P.out_sw, P.slab_w, bw, 32 / bw);
+    if (rc) return rc;
+    mapOutTail = mapOut;
+  } else if (P.epi_mode == 2) {
+    uint64_t dims[3] = {(uint64_t)P.cout, (uint64_t)P.ho * P.wo, (uint64_t)P.n_img};
+    uint64_t str[2] = {(uint64_t)P.out_sw * 2, (uint64_t)P.out_sn * 2};
+    uint32_t box[3] = {(uint32_t)P.slab_w, 32u, 1u};
+    rc = encode_tensor_map(&mapOut, P.out, 3, dims, str, box, P.slab_w * 2);
+    if (rc) return rc;
+    mapOutTail = mapOut;
+    if (kp % 32) {
+      box[1] = (uint32_t)(kp % 32);
+      rc = encode_tensor_map(&mapOutTail, P.out, 3, dims, str, box, P.slab_w * 2);
+      if (rc) return rc;
+    }
+  } else {
+    rc = make_out_map(&mapOut, P.out, P.n_img, P.ho, P.wo, P.cout, P.out_sn, P.out_sh, P.out_sw, P.slab_w, P.tile_w,
+                      P.tile_h);
+    if (rc) return rc;
+    mapOutTail = mapOut;
+  }
   {
     uint64_t dims[3] = {(uint64_t)k_total, (uint64_t)w_rows, (uint64_t)w_batch};
     uint64_t str[2] = {(uint64_t)k_total * 2, (uint64_t)k_total * 2 * w_rows};
@@ -464,15 +734,30 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
   P.tiles_h = ceil_div(P.ho, P.tile_h);
   P.n_tiles = ceil_div(P.cout, P.block_n);
   P.total_tiles = P.n_img * P.tiles_h * P.tiles_w * P.n_tiles;
+  P.fd_n = make_fast_div(P.n_tiles);
+  P.fd_w = make_fast_div(P.tiles_w);
+  P.fd_h = make_fast_div(P.tiles_h);
   P.w_batch = w_batch;
+  // shared memory: [stages x (A + B)] [output staging] [barriers]
   const int stage_bytes = 128 * P.block_k * 2 + P.block_n * P.block_k * 2;
-  const int ctrl_bytes = 8 * (2 * kMaxStages + 4) + 16 + 2 * 2 * 256 * 4;
+  const int ctrl_bytes = 8 * (2 * kMaxStages + 4) + 64;
   const int max_smem = 227 * 1024;
-  int stages = (max_smem - 1024 - ctrl_bytes) / stage_bytes;
+  const int staging1 = 2 * 128 * P.slab_w * 2;      // CTA-wide: 2 slabs; warp-private: 8 warps x 1 buffer
+  P.epi_bufs = 1;
+  P.staging_bytes = (P.epi == UAVDET_EPI_HEAD) ? 0 : staging1;
+  if (P.epi_mode != 0 && (max_smem - ctrl_bytes - 2 * staging1) / stage_bytes >= 4) {
+    P.epi_bufs = 2;
+    P.staging_bytes = 2 * staging1;
+  }
+  int stages = (max_smem - ctrl_bytes - P.staging_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   UAVDET_CHECK_ARG(stages >= 2, "igemm: tile does not fit shared memory");
+  if (stages >= 8) { stages = 8; P.prod_warps = 4; }
+  else if (stages >= 4) { P.prod_warps = (stages % 4 == 0) ? 4 : 2; stages &= ~1; }
+  else { P.prod_warps = 1; }
   P.stages = stages;
   P.watchdog = watchdog_word();
+  get_trace(&P.trace, &P.trace_tiles);
   // Always request (almost) the whole shared memory so exactly one CTA is resident per SM:
   // each CTA allocates all 512 TMEM columns.
   const int smem_bytes = max_smem;
@@ -483,7 +768,7 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
   }
   if (P.total_tiles <= 0) return UAVDET_OK;
   int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
-  igemm_kernel<<<grid, kIgemmThreads, smem_bytes, st>>>(mapA, mapB, P);
+  igemm_kernel<<<grid, kIgemmThreads, smem_bytes, st>>>(mapA, mapB, mapOut, mapOutTail, P);
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }
@@ -518,6 +803,9 @@ static int fill_epilogue(IgemmParams& P, const uavdet_epilogue* epi, const uavde
 }  // namespace uavdet
 
 using namespace uavdet;
+
+// debug hook (not part of the public header): device buffer receiving 8 clock64 stamps per tile of CTA 0
+extern "C" void uavdet_debug_set_trace(long long* dev_buf, int tiles) { g_trace = dev_buf; g_trace_tiles = tiles; }
 
 extern "C" int uavdet_conv_fwd(const uavdet_act* x, const void* w_packed, int w_batch, int cout, int k,
                                int stride, int pad, int s2d, const uavdet_act* y,
@@ -571,7 +859,7 @@ extern "C" int uavdet_conv_fwd(const uavdet_act* x, const void* w_packed, int w_
     P.out_sw = y->ld; P.out_sh = (long long)y->w * y->ld; P.out_sn = (long long)y->h * y->w * y->ld;
     if (P.res) { P.res_sw = epi->res_ld; P.res_sh = (long long)y->w * epi->res_ld; P.res_sn = (long long)y->h * y->w * epi->res_ld; }
   }
-  choose_tile(P.ho, P.wo, &P.tile_w, &P.tile_h);
+  choose_tile(P.ho, P.wo, true, &P.tile_w, &P.tile_h, &P.epi_mode);
   const int w_rows = (P.epi == UAVDET_EPI_HEAD) ? 16 : cout;
   return launch_igemm(x, parity, w_packed, w_rows, k * k * cin, w_batch, P, (cudaStream_t)stream);
 }
@@ -627,7 +915,7 @@ extern "C" int uavdet_conv_dgrad(const uavdet_act* dy, const void* w_packed_t, i
         P.res = P.res + ((long long)ph * dx->w + pw) * rl;
         P.res_sw = stride * rl; P.res_sh = (long long)stride * dx->w * rl; P.res_sn = (long long)dx->h * dx->w * rl;
       }
-      choose_tile(P.ho, P.wo, &P.tile_w, &P.tile_h);
+      choose_tile(P.ho, P.wo, stride == 1, &P.tile_w, &P.tile_h, &P.epi_mode);
       if (nt == 0) {
         // no filter tap reaches this parity plane (1x1 stride-2): the gradient is the residual or zero
         rc = fill_plane(P, st);

@@ -17,12 +17,34 @@ struct ConvTap {
   int w_koff;  // K offset of this tap inside the packed weight matrix
 };
 
+// n / d by multiply-high: q = umulhi(n, mul) >> shr (d > 1), exact for 0 <= n < 2^31.
+struct FastDiv {
+  uint32_t d, mul, shr;
+};
+inline FastDiv make_fast_div(int d) {
+  FastDiv f{(uint32_t)d, 0u, 0u};
+  if (d > 1) {
+    int lg = 0;
+    while ((1u << lg) < (uint32_t)d) ++lg;
+    const int p = 31 + lg;
+    f.mul = (uint32_t)(((1ull << p) + (uint64_t)d - 1) / (uint64_t)d);
+    f.shr = (uint32_t)(p - 32);
+  }
+  return f;
+}
+
 struct IgemmParams {
   int n_img, ho, wo;
   int tile_w, tile_h, tiles_w, tiles_h;
   int cout, block_n, n_tiles;
   int num_taps, kc_per_tap, block_k;
   int w_batch, stages, total_tiles;
+  int slab_w;           // columns per TMA-store slab of the bf16 epilogues (64 | 32)
+  int epi_mode;         // 0 = CTA-wide slab, 1 = per-warp rectangle (5-D map), 2 = per-warp pixel run (flat 3-D map)
+  int epi_bufs;         // staging buffers per epilogue warp (modes 1/2)
+  int staging_bytes;    // shared memory reserved for output staging
+  int prod_warps;       // active TMA producer warps (1 | 2 | 4), divides `stages`
+  FastDiv fd_n, fd_w, fd_h;   // dividers for the tile decode (n_tiles, tiles_w, tiles_h)
   int epi, act;
   const float* scale;
   const float* shift;
@@ -37,13 +59,18 @@ struct IgemmParams {
   float* head_bbox;
   int head_anchors;
   unsigned int* watchdog;
+  long long* trace;     // debug: per-tile role timestamps of CTA 0 (NULL = off), 8 slots per tile
+  int trace_tiles;
   ConvTap taps[kMaxTaps];
 };
 
 int encode_tensor_map(CUtensorMap* m, void* base, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 int make_act_map(CUtensorMap* m, const uavdet_act* x, int parity, int box_c, int box_w, int box_h);
-void choose_tile(int ho, int wo, int* tile_w, int* tile_h);
+int make_out_map(CUtensorMap* m, void* ptr, int n, int ho, int wo, int c, long long sn, long long sh, long long sw,
+                 int box_c, int box_w, int box_h);
+void choose_tile(int ho, int wo, bool dense_rows, int* tile_w, int* tile_h, int* epi_mode);
 int fill_plane(const IgemmParams& P, cudaStream_t st);
+void get_trace(long long** ptr, int* tiles);
 
 }  // namespace uavdet

@@ -150,21 +150,28 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ 
     }
   } else if (num_kb > 0) {
     // ---- epilogue: TMEM -> fp32 atomics into the packed gradient ----------------------------
+    // Each warp owns 32 output-channel rows; a 32x32 chunk is transposed through a per-warp smem
+    // scratch so that every RED instruction covers 32 consecutive floats of ONE row (one 128-byte
+    // line) instead of 32 different rows.
     const int q = warp & 3;
-    const int co = co0 + q * 32 + lane;
+    float* scratch = reinterpret_cast<float*>(tmem_ptr + 4) + (warp - 2) * (32 * 33);
     mbar_wait(smem_u32(done_bar), 0, dead, P.watchdog, 0x40u);
     tc_fence_after();
-    float* base = P.dw + (P.per_sample ? (long long)img_only * P.sample_stride : 0) + (long long)co * P.k_total;
+    const int row0 = co0 + q * 32;
+    float* base = P.dw + (P.per_sample ? (long long)img_only * P.sample_stride : 0);
     for (int t = 0; t < ntap; ++t) {
       const long long koff = P.taps[tap0 + t].w_koff + (long long)cib * P.cin_blk;
       for (int c0 = 0; c0 < P.cin_blk; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (uint32_t)(t * P.cin_blk + c0) + ((uint32_t)(q * 32) << 16), r);
         tmem_ld_wait();
-        if (co < P.cout) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) atomicAdd(base + koff + c0 + i, __uint_as_float(r[i]));
-        }
+        for (int i = 0; i < 32; ++i) scratch[lane * 33 + i] = __uint_as_float(r[i]);
+        __syncwarp();
+        const int nrows = min(32, P.cout - row0);
+        for (int rr = 0; rr < nrows; ++rr)
+          atomicAdd(base + (long long)(row0 + rr) * P.k_total + koff + c0 + lane, scratch[rr * 33 + lane]);
+        __syncwarp();
       }
     }
   }
@@ -248,7 +255,7 @@ extern "C" int uavdet_conv_wgrad(const uavdet_act* x, const uavdet_act* dy, int 
   P.total_pixel_tiles = P.n_img * P.tiles_h * P.tiles_w;
   // taps per CTA: bounded by 512 TMEM columns and by shared memory (>= 3 stages)
   const int max_smem = 227 * 1024;
-  const int ctrl_bytes = 8 * (2 * kMaxStages + 1) + 16;
+  const int ctrl_bytes = 8 * (2 * kMaxStages + 1) + 16 + 4 * 32 * 33 * 4;   // barriers + per-warp transpose scratch
   const int a_bytes = 128 * P.kp * 2;
   int group = 512 / P.cin_blk;
   if (group > nt) group = nt;
@@ -267,9 +274,17 @@ extern "C" int uavdet_conv_wgrad(const uavdet_act* x, const uavdet_act* dy, int 
   P.per_sample = per_sample ? 1 : 0;
   const int tiles_avail = per_sample ? P.tiles_h * P.tiles_w : P.total_pixel_tiles;
   const int samples = per_sample ? P.n_img : 1;
-  int splits = ceil_div(2 * kNumSMs, P.items * samples);
-  if (splits < 1) splits = 1;
-  if (splits > tiles_avail) splits = tiles_avail;
+  // split-K factor: minimise (waves of CTAs) x (pixel tiles per CTA); one CTA per SM is resident
+  int splits = 1;
+  {
+    long long best = -1;
+    const int ctas_per_split = P.items * samples;
+    for (int s_ = 1; s_ <= 64 && s_ <= tiles_avail; ++s_) {
+      const long long waves = ceil_div(ctas_per_split * s_, kNumSMs);
+      const long long cost = waves * (ceil_div(tiles_avail, s_) + 6);   // +6: per-CTA prologue/epilogue in tile units
+      if (best < 0 || cost < best) { best = cost; splits = s_; }
+    }
+  }
   P.tiles_per_split = ceil_div(tiles_avail, splits);
   P.k_splits = ceil_div(tiles_avail, P.tiles_per_split);
   P.k_total = (long long)k * k * cin;

@@ -1,0 +1,36 @@
+"""GPU-box diagnostic: per-role pipeline timeline (clock64) of CTA 0 of igemm_kernel for a few layer shapes."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from multimodal_uav_det_b200 import _lib, ops
+from multimodal_uav_det_b200._lib import EPI_STATS
+lib = _lib.load()
+lib.uavdet_debug_set_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
+lib.uavdet_debug_set_trace.restype = None
+NT = 6
+trace = torch.zeros(NT * 16, dtype=torch.int64, device="cuda")
+for (n, cin, cout, k, s, hw, stats) in [(32, 256, 128, 1, 1, 80, True), (32, 128, 256, 3, 1, 80, True), (32, 128, 256, 3, 1, 80, False),
+                                        (32, 64, 32, 1, 1, 320, True)]:
+    x = torch.randn(n, hw, hw, cin, device="cuda").bfloat16()
+    w = ops.pack_weight(torch.randn(cout, cin, k, k, device="cuda") * 0.05)
+    s1 = torch.zeros(cout, device="cuda"); s2 = torch.zeros(cout, device="cuda")
+    kw = dict(epi=EPI_STATS, sum_=s1, sumsq=s2) if stats else dict(act="leaky")
+    for _ in range(2):
+        ops.conv_fwd(x, w, cout, k, s, k // 2, **kw)
+    torch.cuda.synchronize()
+    trace.zero_()
+    lib.uavdet_debug_set_trace(trace.data_ptr(), NT)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); ops.conv_fwd(x, w, cout, k, s, k // 2, **kw); e1.record()
+    torch.cuda.synchronize()
+    lib.uavdet_debug_set_trace(None, 0)
+    t = trace.cpu().view(NT, 16)
+    t0 = int(t[0, 0])
+    print(f"=== {cin}->{cout} k{k} s{s} @{hw} stats={stats}: kernel {e0.elapsed_time(e1)*1000:.0f} us; cycles rel. to first TMA issue")
+    print(" tile | prod_start prod_end | mma_wait_tempty mma_first_full mma_commit | epi_wait epi_start epi_end")
+    for i in range(NT):
+        if int(t[i, 0]) == 0: break
+        r = [int(v) - t0 for v in t[i]]
+        e = r[6]
+        fine = " ".join(f"{(r[j] - e) if int(t[i, j]) else -1:6d}" for j in range(8, 16))
+        print(f" {i:4d} | {r[0]:9d} {r[1]:9d} | {r[2]:9d} {r[3]:9d} {r[4]:9d} | {r[5]:9d} {r[6]:9d} {r[7]:9d} | rel epi_start: slab0: start waitrd bar2 tmemld sts fence bar3 storeissue: {fine}")
