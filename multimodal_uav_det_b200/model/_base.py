@@ -184,6 +184,7 @@ class YOLOHead(LightningModule):
             self.detection_head.append(nn.ModuleDict(dict(obj=ObjectnessHead(c, n_anchors),
                                                           bbox=BBoxHead(c, n_anchors))))
         self._packs = {}
+        self._sa_cache = {}
 
     # ---- fused head conv -------------------------------------------------------------------------
     def fused_weight(self, s: int):
@@ -211,6 +212,16 @@ class YOLOHead(LightningModule):
     def forward(self, f_maps: List[torch.Tensor]):
         return self.forward_nhwc([to_nhwc(f) for f in f_maps])
 
+    def _scaled_anchors(self, h: int, device) -> torch.Tensor:
+        """anchors[h] / head_scales[h] (reference _base.py:170) as a cached device tensor, so the loss does no
+        host->device copy per step (and can be captured into a CUDA graph)."""
+        key = (h, str(device))
+        hit = self._sa_cache.get(key)
+        if hit is None:
+            hit = (self.anchors[h] / self.head_scales[h]).to(device)
+            self._sa_cache[key] = hit
+        return hit
+
     # ---- loss ------------------------------------------------------------------------------------
     def compute_metrics(self, outs: List[DetectionResults], batch: BatchData, return_ap=False):
         """-> (total_loss, ap|None, bbox_loss, obj_loss), reference _base.py:155-212, evaluated as
@@ -229,7 +240,7 @@ class YOLOHead(LightningModule):
                 tgt = torch.stack([targets[i][h] for i in range(bsz)]).to(out.bbox.device)
             else:
                 tgt = targets[h].to(out.bbox.device)
-            sa = self.anchors[h] / self.head_scales[h]
+            sa = self._scaled_anchors(h, out.bbox.device)
             bl, ol, new_t = yolo_head_loss(out.bbox.float(), out.obj.float(), tgt, sa, self.obj_scales_w[h], weights,
                                            self.bbox_loss_fn)
             bbox_losses = bbox_losses + bl

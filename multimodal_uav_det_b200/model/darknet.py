@@ -160,9 +160,10 @@ class DarknetDetector(BaseModel):
             raise RuntimeError("multimodal_uav_det_b200 models run on CUDA only (no CPU fallback)")
         x = x.float().contiguous()
         if torch.is_grad_enabled() and self.training_graph and any(p.requires_grad for p in self.parameters()):
-            if self._anchor is None or self._anchor.device != x.device:
-                self._anchor = torch.zeros((), device=x.device, requires_grad=True)
-            flat = _TrunkFn.apply(self, x, self._anchor)
+            # a fresh (uninitialised, never read) leaf per call: its AccumulateGrad node then belongs to the
+            # stream of THIS forward, which CUDA-graph capture of the step needs
+            anchor = torch.empty((), device=x.device).requires_grad_()
+            flat = _TrunkFn.apply(self, x, anchor)
             return [DetectionResults(bbox=flat[2 * i], obj=flat[2 * i + 1]) for i in range(len(flat) // 2)]
         return self._forward_program(x, None)
 

@@ -133,3 +133,66 @@ class FlatSGDTrainer:
         self._first = False
         bump_param_epoch()
         self._arm()
+
+
+class GraphedTrainStep:
+    """One whole training step (zero-grad, forward, loss, backward, bucketed all-reduce, SGD) captured
+    into a CUDA graph and replayed: the step is ~2,000 kernel launches of a fixed shape, so launching it
+    from Python costs more than executing it.  Inputs live in static device buffers; `__call__` copies
+    the new batch in (device->device, or straight from pinned host memory) and replays.
+
+        step = GraphedTrainStep(model, trainer, x_example, targets_example)
+        loss = step(x, targets)          # loss: 0-dim device tensor, overwritten by the next call
+
+    The graph holds the per-step activation memory in its private pool.  Capturing needs a few eager
+    warm-up steps first (lazy initialisation, cuTensorMap entry point, allocator warm-up); they are run
+    here on a side stream and DO update the parameters (they are ordinary training steps on the example
+    batch) unless `warmup=0`."""
+
+    def __init__(self, model, trainer: FlatSGDTrainer, x: torch.Tensor, targets, warmup: int = 2):
+        from .utils.datatype import BatchData
+        self.model, self.trainer = model, trainer
+        self.x = x.detach().clone().float().contiguous()
+        self.targets = [t.detach().clone() for t in targets]
+        head = model.yolo_head
+        for h in range(len(self.targets)):
+            head._scaled_anchors(h, self.x.device)      # host->device constants must exist before capture
+        prev_mut = head.mutate_targets
+        head.mutate_targets = False            # targets are inputs of the graph, never rewritten in place
+
+        def body():
+            trainer.zero_grad()
+            outs = model(self.x)
+            loss, _, bbox_loss, obj_loss = head.compute_metrics(outs, BatchData(image=self.x, bbox=self.targets))
+            loss.backward()
+            trainer.step()
+            return loss.detach(), bbox_loss.detach(), obj_loss.detach()
+
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=self.x.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                body()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.x.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.bbox_loss, self.obj_loss = body()
+        head.mutate_targets = prev_mut
+        bump_param_epoch()
+
+    def load(self, x: torch.Tensor, targets) -> None:
+        """Stage a batch into the static buffers (asynchronous on the current stream)."""
+        if x is not self.x:
+            self.x.copy_(x, non_blocking=True)
+        for dst, src in zip(self.targets, targets):
+            if src is not dst:
+                dst.copy_(src, non_blocking=True)
+
+    def __call__(self, x: Optional[torch.Tensor] = None, targets=None) -> torch.Tensor:
+        if x is not None:
+            self.load(x, targets if targets is not None else self.targets)
+        self.graph.replay()
+        bump_param_epoch()      # parameters were rewritten on the device: packed-weight caches are stale
+        return self.loss

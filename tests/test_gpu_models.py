@@ -318,3 +318,58 @@ def test_detect_decode_nms_bit_exact_on_model_outputs(lib):
         want = O.nms(det.boxes[b].cpu().numpy(), det.scores[b].cpu().numpy(), 0.5)
         assert np.array_equal(kept.cpu().numpy(), want)
         print(f"image {b}: kept {len(want)} of 25200")
+
+
+@pytest.mark.parametrize("train_bn", [False, True])
+def test_graphed_train_step_equals_eager(lib, train_bn):
+    """parallel.GraphedTrainStep (whole step replayed from one CUDA graph) follows the eager trainer: the same
+    kernels on the same data.  With frozen BN the comparison is tight; with batch-stat BN the fp32-atomic
+    accumulation order is amplified chaotically (two eager runs differ as much), so only the loss trajectory
+    and the BN bookkeeping are compared there."""
+    from multimodal_uav_det_b200.parallel import FlatSGDTrainer, GraphedTrainStep
+    from multimodal_uav_det_b200.utils.datatype import BatchData
+    from multimodal_uav_det_b200 import ops
+    size, b = 128, 8
+    runs = {}
+    for mode in ("eager", "graph"):
+        model, hp = make("BaselineModel", SHALLOW, lr=1e-3)
+        model.route_repeats = 2
+        if not train_bn:
+            randomize_bn(model)
+        model = model.to(DEV).train(train_bn)
+        model.yolo_head.mutate_targets = False
+        init = {k: v.detach().float().cpu().clone() for k, v in model.named_parameters()}
+        trainer = FlatSGDTrainer(model, lr=1e-3, momentum=0.7)
+        xs = [synth_input(b, size, seed=100 + i).to(DEV) for i in range(3)]
+        per = _targets(hp, b, size, grids=[16, 32, 64])
+        tg = [torch.stack([per[i][h] for i in range(b)]).to(DEV) for h in range(3)]
+        losses = []
+        if mode == "eager":
+            for x in xs:
+                trainer.zero_grad()
+                outs = model(x)
+                loss, _, _, _ = model.yolo_head.compute_metrics(outs, BatchData(image=x, bbox=tg))
+                loss.backward()
+                trainer.step()
+                losses.append(loss.item())
+        else:
+            step = GraphedTrainStep(model, trainer, xs[0], tg, warmup=0)   # capture only: parameters untouched
+            for x in xs:
+                losses.append(step(x, tg).item())
+        ops.check_device()
+        delta = torch.cat([(p.detach().float().cpu() - init[k]).flatten() for k, p in model.named_parameters()])
+        runs[mode] = (losses, delta, int(model.layers[0].bn.num_batches_tracked))
+    le, lg = runs["eager"][0], runs["graph"][0]
+    cos = cosine(runs["eager"][1], runs["graph"][1])
+    print("train_bn", train_bn, "eager", le, "graph", lg, "update cosine", cos)
+    if train_bn:
+        assert np.allclose(le, lg, rtol=0.05), (le, lg)
+        assert runs["eager"][2] == runs["graph"][2] == 3       # BN counters advance inside the graph too
+    else:
+        assert np.allclose(le, lg, rtol=2e-3), (le, lg)
+        assert cos > 0.995
+    # the graph bumps the parameter epoch: an eager eval forward afterwards sees the updated weights
+    model.eval()
+    with torch.no_grad():
+        out = model(xs[0])
+    assert torch.isfinite(out[0].bbox).all()
