@@ -130,6 +130,15 @@ int uavdet_conv_dgrad(const uavdet_act* dy, const void* w_packed_t, int w_batch,
                       int stride, int pad, const uavdet_act* dx, const uavdet_epilogue* epi,
                       void* stream);
 
+/* Data gradient through the fused space-to-depth(2) gather of uavdet_conv_fwd(s2d=1)
+ * (autograd of DySOEM_SimFPN.py:71-91): dy (n, h/2, w/2, cout) -> dx (n, h, w, c) where the conv's
+ * logical input had 4*c channels, block q = 2*(row parity) + (column parity).  w_packed_t: bf16
+ * [w_batch][4*c][k*k*cout].  Runs one implicit GEMM per parity plane of dx.  epi: AFFINE; `res` is a
+ * full-resolution gradient added in the epilogue; `shift` with shift_per_sample is [n][4*c] (the
+ * pooled-attention gradient broadcast over each parity class).                             */
+int uavdet_conv_dgrad_s2d(const uavdet_act* dy, const void* w_packed_t, int w_batch, int c, int k, int pad,
+                          const uavdet_act* dx, const uavdet_epilogue* epi, void* stream);
+
 /* Weight gradient dw[co][tap][ci] += sum_pixels dy[p][co] * x[p+tap][ci]  (fp32, atomics,
  * caller-zeroed; layout = packed weight layout).  per_sample != 0 keeps one dw per image
  * ([n][cout][k*k*cin]) for the dynamic-kernel contraction.                               */
@@ -214,6 +223,14 @@ int uavdet_attn_mlp_softmax(const float* pooled, int n, int c, const float* w1, 
 int uavdet_dyn_aggregate(const float* attn, int n, int K, const float* bank, int O, int I, int k,
                          int transposed, void* out_bf16, const float* bias_bank, float* bias_out,
                          void* stream);
+
+/* Backward of the aggregation: from the per-sample kernel gradients dwb [n][O*I*k*k] fp32
+ * (packed != 0: the [O][k*k][I] layout uavdet_conv_wgrad(per_sample=1) writes, I may be 4*c for s2d;
+ * packed == 0: OIHW, what uavdet_stem_wgrad writes) accumulate
+ *   d_bank[kk][e] += sum_b attn[b,kk] * dwb[b][e]      (OIHW fp32, autograd of _base.py:65-66)
+ *   d_attn[b,kk]  += sum_e dwb[b][e] * bank[kk][e].                                          */
+int uavdet_dyn_bwd_contract(const float* dwb, int n, int K, const float* attn, const float* bank, int O, int I,
+                            int k, int packed, float* d_bank, float* d_attn, void* stream);
 
 /* ---- K3 / K6 / K7: RTMUAVDet memory-bound ops -------------------------------------------- */
 /* Per-sample depthwise dynamic conv + residual (MDyConv.forward, RTMUAVDet.py:80-98):

@@ -49,6 +49,7 @@ SIGNATURES = {
     "uavdet_cxcywh_to_xyxy": (_i, [_P, _P, _i64, _P]),
     "uavdet_conv_fwd": (_i, [_AP, _P, _i, _i, _i, _i, _i, _i, _AP, _EP, _P]),
     "uavdet_conv_dgrad": (_i, [_AP, _P, _i, _i, _i, _i, _i, _AP, _EP, _P]),
+    "uavdet_conv_dgrad_s2d": (_i, [_AP, _P, _i, _i, _i, _i, _AP, _EP, _P]),
     "uavdet_conv_wgrad": (_i, [_AP, _AP, _i, _i, _i, _i, _P, _i, _P]),
     "uavdet_pack_weight": (_i, [_P, _i, _i, _i, _i, _P, _P]),
     "uavdet_unpack_wgrad": (_i, [_P, _i, _i, _i, _P, _i, _P]),
@@ -70,6 +71,7 @@ SIGNATURES = {
     "uavdet_gap_nchw": (_i, [_P, _i, _i, _i, _P, _P]),
     "uavdet_attn_mlp_softmax": (_i, [_P, _i, _i, _P, _P, _i, _P, _P, _i, _f, _P, _P, _P]),
     "uavdet_dyn_aggregate": (_i, [_P, _i, _i, _P, _i, _i, _i, _i, _P, _P, _P, _P]),
+    "uavdet_dyn_bwd_contract": (_i, [_P, _i, _i, _P, _P, _i, _i, _i, _i, _P, _P, _P]),
     "uavdet_dwdynconv_fwd": (_i, [_AP, _P, _P, _i, _i, _AP, _P]),
     "uavdet_linear": (_i, [_P, _i, _i, _P, _P, _i, _i, _P, _P]),
     "uavdet_groupnorm1": (_i, [_AP, _AP, _P, _P, _f, _P, _AP, _P]),

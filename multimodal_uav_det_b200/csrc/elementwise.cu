@@ -469,6 +469,80 @@ __global__ void dyn_bias_kernel(const float* __restrict__ attn, int n, int K, co
   bias_out[idx] = acc;
 }
 
+// ---- backward of the per-sample kernel aggregation ---------------------------------------------------
+// thread <-> up to E kernel elements (OIHW index e); loops over the batch once: d_bank accumulates in
+// registers, the d_attn partial products are folded per warp (shuffles) and parked in shared memory
+// [warp][b][k]; one global reduction per (b, k) per block at the end.
+constexpr int kDbcThreads = 256;
+constexpr int kDbcE = 4;
+constexpr int kDbcMaxK = 8;
+__global__ void __launch_bounds__(kDbcThreads)
+dyn_bwd_contract_kernel(const float* __restrict__ dwb, int n, int K, const float* __restrict__ attn,
+                        const float* __restrict__ bank, int O, int I, int kk, int packed,
+                        float* __restrict__ d_bank, float* __restrict__ d_attn) {
+  extern __shared__ float sda[];   // [warps][n][K]
+  const long long per = (long long)O * I * kk;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long e[kDbcE], pidx[kDbcE];
+  float bk[kDbcE][kDbcMaxK], acc[kDbcE][kDbcMaxK];
+#pragma unroll
+  for (int j = 0; j < kDbcE; ++j) {
+    e[j] = ((long long)blockIdx.x * kDbcE + j) * kDbcThreads + threadIdx.x;
+    const bool live = e[j] < per;
+    pidx[j] = -1;
+    if (live) {
+      if (packed) {
+        const int t = (int)(e[j] % kk);
+        const long long r = e[j] / kk;
+        const int i = (int)(r % I);
+        const long long o = r / I;
+        pidx[j] = (o * kk + t) * I + i;
+      } else {
+        pidx[j] = e[j];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kDbcMaxK; ++k) {
+      bk[j][k] = (live && k < K) ? __ldg(bank + (long long)k * per + e[j]) : 0.f;
+      acc[j][k] = 0.f;
+    }
+  }
+  for (int b = 0; b < n; ++b) {
+    float g[kDbcE];
+#pragma unroll
+    for (int j = 0; j < kDbcE; ++j) g[j] = pidx[j] >= 0 ? __ldg(dwb + (long long)b * per + pidx[j]) : 0.f;
+#pragma unroll
+    for (int k = 0; k < kDbcMaxK; ++k) {
+      if (k < K) {
+        const float a = __ldg(attn + b * K + k);
+        float da = 0.f;
+#pragma unroll
+        for (int j = 0; j < kDbcE; ++j) {
+          acc[j][k] = fmaf(a, g[j], acc[j][k]);
+          da = fmaf(g[j], bk[j][k], da);
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) da += __shfl_xor_sync(0xffffffffu, da, off);
+        if (lane == 0) sda[(warp * n + b) * K + k] = da;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kDbcE; ++j) {
+    if (pidx[j] >= 0) {
+#pragma unroll
+      for (int k = 0; k < kDbcMaxK; ++k)
+        if (k < K) d_bank[(long long)k * per + e[j]] += acc[j][k];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n * K; i += kDbcThreads) {
+    float s = 0.f;
+    for (int w = 0; w < kDbcThreads / 32; ++w) s += sda[w * n * K + i];
+    atomicAdd(d_attn + i, s);
+  }
+}
+
 // ---- global average pool -------------------------------------------------------------------------
 // out[b][q*C + c] += sum over pixels of parity class q (s2d) / all pixels (q = 0), scaled by inv_count
 __global__ void gap_kernel(const __nv_bfloat16* __restrict__ x, int ld, int h, int w, int c, int s2d,
@@ -776,6 +850,20 @@ extern "C" int uavdet_dyn_aggregate(const float* attn, int n, int K, const float
     dyn_bias_kernel<<<ceil_div(n * O, 256), 256, 0, ST>>>(attn, n, K, bias_bank, O, bias_out);
     UAVDET_LAUNCH_CHECK();
   }
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_dyn_bwd_contract(const float* dwb, int n, int K, const float* attn, const float* bank, int O,
+                                       int I, int k, int packed, float* d_bank, float* d_attn, void* stream) {
+  UAVDET_CHECK_ARG(dwb && attn && bank && d_bank && d_attn && n > 0 && K > 0 && K <= kDbcMaxK,
+                   "dyn_bwd_contract: bad arguments (K <= %d)", kDbcMaxK);
+  const long long per = (long long)O * I * k * k;
+  const size_t sh = sizeof(float) * (size_t)(kDbcThreads / 32) * n * K;
+  UAVDET_CHECK_ARG(sh <= 48 * 1024, "dyn_bwd_contract: batch too large for the shared accumulator");
+  const long long blocks = (per + (long long)kDbcThreads * kDbcE - 1) / ((long long)kDbcThreads * kDbcE);
+  dyn_bwd_contract_kernel<<<(unsigned)blocks, kDbcThreads, sh, ST>>>(dwb, n, K, attn, bank, O, I, k * k, packed, d_bank,
+                                                                    d_attn);
+  UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }
 

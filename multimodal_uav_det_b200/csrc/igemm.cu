@@ -690,7 +690,8 @@ static int pick_block_n(int cout) {
 }
 
 int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int w_rows, int k_total,
-                 int w_batch, IgemmParams& P, cudaStream_t st) {
+                 int w_batch, IgemmParams& P, cudaStream_t st, int w_batch_rows = 0) {
+  if (w_batch_rows <= 0) w_batch_rows = w_rows;   // rows between the weight matrices of consecutive samples
   CUtensorMap mapA, mapB, mapOut, mapOutTail;
   int rc = make_act_map(&mapA, a_src, parity, P.block_k, P.tile_w, P.tile_h);
   if (rc) return rc;
@@ -725,7 +726,7 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
   }
   {
     uint64_t dims[3] = {(uint64_t)k_total, (uint64_t)w_rows, (uint64_t)w_batch};
-    uint64_t str[2] = {(uint64_t)k_total * 2, (uint64_t)k_total * 2 * w_rows};
+    uint64_t str[2] = {(uint64_t)k_total * 2, (uint64_t)k_total * 2 * w_batch_rows};
     uint32_t box[3] = {(uint32_t)P.block_k, (uint32_t)P.block_n, 1u};
     rc = encode_tensor_map(&mapB, const_cast<void*>(w_packed), 3, dims, str, box, P.block_k * 2);
     if (rc) return rc;
@@ -924,5 +925,57 @@ extern "C" int uavdet_conv_dgrad(const uavdet_act* dy, const void* w_packed_t, i
       }
       if (rc) return rc;
     }
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_conv_dgrad_s2d(const uavdet_act* dy, const void* w_packed_t, int w_batch, int c, int k, int pad,
+                                     const uavdet_act* dx, const uavdet_epilogue* epi, void* stream) {
+  UAVDET_CHECK_ARG(dy && dy->ptr && w_packed_t && dx && dx->ptr, "conv_dgrad_s2d: null input");
+  UAVDET_CHECK_ARG(k >= 1 && k <= 5, "conv_dgrad_s2d: k=%d unsupported", k);
+  UAVDET_CHECK_ARG(dy->ld % 8 == 0 && ((uintptr_t)dy->ptr & 15) == 0, "conv_dgrad_s2d: dy must be 16-byte aligned");
+  UAVDET_CHECK_ARG(w_batch == 1 || w_batch == dy->n, "conv_dgrad_s2d: w_batch must be 1 or n");
+  const int cout = dy->c;
+  UAVDET_CHECK_ARG(cout % 32 == 0 && c % 32 == 0, "conv_dgrad_s2d: channels must be multiples of 32");
+  UAVDET_CHECK_ARG(dx->n == dy->n && dx->c == c && dx->h % 2 == 0 && dx->w % 2 == 0, "conv_dgrad_s2d: dx view mismatch");
+  UAVDET_CHECK_ARG((dx->h / 2 + 2 * pad - k) + 1 == dy->h && (dx->w / 2 + 2 * pad - k) + 1 == dy->w,
+                   "conv_dgrad_s2d: spatial sizes inconsistent");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long k_total = (long long)k * k * cout;
+  for (int q = 0; q < 4; ++q) {
+    const int pi = q >> 1, pj = q & 1;   // row / column parity of this channel block (DySOEM_SimFPN.py:71-73)
+    IgemmParams P{};
+    P.n_img = dy->n;
+    P.ho = dx->h / 2;
+    P.wo = dx->w / 2;
+    P.cout = c;
+    P.block_k = (cout % 64 == 0) ? 64 : 32;
+    P.block_n = pick_block_n(c);
+    P.kc_per_tap = cout / P.block_k;
+    int nt = 0;
+    for (int kh = 0; kh < k; ++kh)
+      for (int kw = 0; kw < k; ++kw) {
+        UAVDET_CHECK_ARG(nt < kMaxTaps, "conv_dgrad_s2d: too many taps");
+        P.taps[nt++] = ConvTap{0, pad - kw, 0, pad - kh, (kh * k + kw) * cout};
+      }
+    P.num_taps = nt;
+    uavdet_act dxv = *dx;
+    dxv.h = P.ho; dxv.w = P.wo;
+    int rc = fill_epilogue(P, epi, &dxv, c);
+    if (rc) return rc;
+    UAVDET_CHECK_ARG(P.epi == UAVDET_EPI_AFFINE, "conv_dgrad_s2d: only the AFFINE epilogue is supported");
+    const long long ld = dx->ld;
+    P.out = (__nv_bfloat16*)dx->ptr + ((long long)pi * dx->w + pj) * ld;
+    P.out_sw = 2 * ld; P.out_sh = 2ll * dx->w * ld; P.out_sn = (long long)dx->h * dx->w * ld;
+    if (P.res) {
+      const long long rl = epi->res_ld;
+      P.res = P.res + ((long long)pi * dx->w + pj) * rl;
+      P.res_sw = 2 * rl; P.res_sh = 2ll * dx->w * rl; P.res_sn = (long long)dx->h * dx->w * rl;
+    }
+    if (P.shift && epi->shift_per_sample) { P.shift = P.shift + q * c; P.shift_sn = 4 * c; }
+    choose_tile(P.ho, P.wo, false, &P.tile_w, &P.tile_h, &P.epi_mode);
+    const __nv_bfloat16* wq = (const __nv_bfloat16*)w_packed_t + (long long)q * c * k_total;
+    rc = launch_igemm(dy, 0, wq, c, (int)k_total, w_batch, P, st, 4 * c);
+    if (rc) return rc;
+  }
   return UAVDET_OK;
 }

@@ -112,6 +112,47 @@ class ConvRecord:
     in_hw: Tuple[int, int] = (0, 0)
 
 
+@dataclass
+class DynSpec:
+    """One dynamic-kernel convolution site: attention MLP over the pooled input mixes an expert bank into one
+    kernel per sample (reference _base.py:26-77 DyConvModule, DySOEM_SimFPN.py:38-94 DynamicSOEM)."""
+    bank: Callable[[], torch.Tensor]                       # () -> (K,O,I,k,k) fp32, detached, contiguous
+    bias_bank: Optional[Callable[[], torch.Tensor]]        # () -> (K,O) fp32 or None
+    bank_params: Callable[[], list]                        # () -> [(param, index into d_bank | None)] see accumulate
+    w1: torch.Tensor                                       # first attention layer weight (hid, C[,1,1])
+    b1: Optional[torch.Tensor]
+    w2: torch.Tensor                                       # (K, hid[,1,1])
+    b2: torch.Tensor
+    temperature: float
+    bn: nn.BatchNorm2d
+    act: str
+    cin: int                                               # channels of the tensor the site reads (before s2d)
+    cout: int
+    k: int
+    stride: int
+    pad: int
+    s2d: bool = False
+    stem: bool = False
+
+
+@dataclass
+class DynRecord:
+    spec: DynSpec
+    x: torch.Tensor
+    pooled: torch.Tensor
+    hidden: torch.Tensor
+    attn: torch.Tensor
+    bank: torch.Tensor
+    bias_bank: Optional[torch.Tensor]
+    raw: torch.Tensor
+    scale: Optional[torch.Tensor]
+    shift: Optional[torch.Tensor]
+    mean: Optional[torch.Tensor]
+    invstd: Optional[torch.Tensor]
+    in_hw: Tuple[int, int] = (0, 0)
+    has_res: bool = False
+
+
 class Executor:
     """Forward/backward of ConvUnits with a shared pack cache and per-step scratch."""
 
@@ -230,6 +271,127 @@ class Executor:
             raise NotImplementedError("dgrad through the fused space-to-depth gather")
         wt = self.packs.get(w, transposed=True)
         return ops.conv_dgrad(d_raw, wt, w.shape[1], u.k, u.stride, u.pad, rec.in_hw, res=res, out=out)
+
+    # ---- dynamic-kernel convolution ----------------------------------------------------------------
+    def dyn_forward(self, sp: DynSpec, x: torch.Tensor, train: bool, tape: Optional[list]) -> torch.Tensor:
+        """y = act(bn(conv(x, sum_k a_k(x) W_k) + sum_k a_k(x) b_k)), one kernel per sample as a batched GEMM
+        operand.  x: NHWC bf16 (or the NCHW fp32 network input for a cin=3 site)."""
+        pooled = ops.gap_nchw(x) if sp.stem else ops.gap(x, s2d=sp.s2d)
+        w1 = sp.w1.detach().flatten(1)
+        w2 = sp.w2.detach().flatten(1)
+        b1 = sp.b1.detach() if sp.b1 is not None else None
+        attn, hidden = ops.attn_mlp_softmax(pooled, w1, b1, w2, sp.b2.detach(), float(sp.temperature), want_hidden=True)
+        n = attn.shape[0]
+        bank = sp.bank()
+        bias_bank = sp.bias_bank() if sp.bias_bank is not None else None
+        if sp.stem:
+            w_b = torch.mm(attn, bank.flatten(1)).view(n, *bank.shape[1:])        # fp32 kernels for the direct stem
+            bias_b = None
+        else:
+            w_b, bias_b = ops.dyn_aggregate(attn, bank, bias_bank=bias_bank)
+        bn, k, s, p, co = sp.bn, sp.k, sp.stride, sp.pad, sp.cout
+        in_hw = (x.shape[2], x.shape[3]) if sp.stem else (x.shape[1], x.shape[2])
+        if train:
+            sums = torch.zeros((2, co), dtype=torch.float32, device=attn.device)
+            if sp.stem:
+                raw = ops.stem_fwd(x, w_b, k, s, p, epi=EPI_STATS, sum_=sums[0], sumsq=sums[1], per_sample_w=True)
+            else:
+                raw = ops.conv_fwd(x, w_b, co, k, s, p, s2d=sp.s2d, w_batch=n, epi=EPI_STATS, shift=bias_b,
+                                   shift_per_sample=bias_b is not None, sum_=sums[0], sumsq=sums[1])
+            _, ho, wo, _ = raw.shape
+            mom = 0.1 if bn.momentum is None else bn.momentum
+            mean, invstd, scale, shift = ops.bn_finalize(sums[0], sums[1], n * ho * wo, bn.eps, mom, bn.weight.detach(),
+                                                         bn.bias.detach(), bn.running_mean, bn.running_var)
+            if bn.num_batches_tracked is not None:
+                self._bn_counters.append(bn.num_batches_tracked)
+            y = ops.bn_act_fwd(raw, scale, shift, sp.act)
+            if tape is not None:
+                tape.append(DynRecord(sp, x, pooled, hidden, attn, bank, bias_bank, raw, scale, shift, mean, invstd, in_hw))
+            return y
+        scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
+        shift = bn.bias.detach() - bn.running_mean * scale
+        per_sample_shift = bias_b is not None
+        if per_sample_shift:
+            shift = (shift.unsqueeze(0) + bias_b * scale.unsqueeze(0)).contiguous()
+        if tape is not None:
+            # frozen-BN training: keep z = scale*conv + shift for act'(z)
+            if sp.stem:
+                z = ops.stem_fwd(x, w_b, k, s, p, scale=scale, shift=shift, per_sample_w=True)
+            else:
+                z = ops.conv_fwd(x, w_b, co, k, s, p, s2d=sp.s2d, w_batch=n, scale=scale, shift=shift,
+                                 shift_per_sample=per_sample_shift)
+            y = ops.bn_act_fwd(z, None, None, sp.act)
+            tape.append(DynRecord(sp, x, pooled, hidden, attn, bank, bias_bank, z, scale, None, None, None, in_hw))
+            return y
+        if sp.stem:
+            return ops.stem_fwd(x, w_b, k, s, p, act=sp.act, scale=scale, shift=shift, per_sample_w=True)
+        return ops.conv_fwd(x, w_b, co, k, s, p, s2d=sp.s2d, w_batch=n, act=sp.act, scale=scale, shift=shift,
+                            shift_per_sample=per_sample_shift)
+
+    def _accumulate(self, p: torch.Tensor, g: torch.Tensor) -> None:
+        if not p.requires_grad:
+            return
+        if p.grad is None:
+            p.grad = g.reshape(p.shape).clone()
+        else:
+            p.grad.add_(g.reshape(p.shape))
+        if self.grad_ready_hook is not None:
+            self.grad_ready_hook(p)
+
+    def dyn_backward(self, rec: DynRecord, dy: torch.Tensor, res: Optional[torch.Tensor] = None,
+                     need_dx: bool = True) -> Optional[torch.Tensor]:
+        """Backward of dyn_forward.  The per-sample kernel gradients (n x |W| fp32, <= 67 MB at the largest
+        site) are contracted with the attention / the expert bank by one kernel; the attention-MLP chain is
+        a handful of (n x C)-sized fp32 products; the pooled-input gradient is broadcast over the pixels by
+        the data-gradient epilogue (per-sample shift)."""
+        sp = rec.spec
+        n = rec.attn.shape[0]
+        if rec.mean is not None:
+            d_raw, dgamma, dbeta = ops.bn_act_bwd(dy, rec.raw, rec.scale, rec.shift, rec.mean, rec.invstd,
+                                                  sp.bn.weight.detach(), sp.act)
+            self._bn_grads.append((sp.bn.weight, dgamma))
+            self._bn_grads.append((sp.bn.bias, dbeta))
+        else:
+            d_pre = ops.act_bwd(dy, rec.raw, None, None, sp.act)
+            d_raw = ops.bn_act_fwd(d_pre, rec.scale, None, "none")
+        # per-sample kernel gradient -> expert-bank gradient + attention gradient
+        if sp.stem:
+            dwb = ops.stem_wgrad(rec.x, d_raw, sp.k, sp.stride, sp.pad, per_sample=True)
+        else:
+            dwb = ops.conv_wgrad(rec.x, d_raw, sp.k, sp.stride, sp.pad, s2d=sp.s2d, per_sample=True)
+        d_attn = torch.zeros_like(rec.attn)
+        d_bank = torch.zeros_like(rec.bank)
+        ops.dyn_bwd_contract(dwb.view(n, -1), rec.attn, rec.bank, d_bank, d_attn, packed=not sp.stem)
+        d_bias_bank = None
+        if rec.bias_bank is not None:
+            dsum = ops.gap(d_raw) * float(d_raw.shape[1] * d_raw.shape[2])         # (n, O) per-sample channel sums
+            d_bias_bank = rec.attn.t() @ dsum
+            d_attn = d_attn + dsum @ rec.bias_bank.t()
+        for p, idx, is_bias in sp.bank_params():
+            src = d_bias_bank if is_bias else d_bank
+            self._accumulate(p, src if idx is None else src[idx])
+        # attention MLP backward (softmax(s/T), Linear/conv1x1, ReLU, Linear/conv1x1)
+        a = rec.attn
+        g = a * (d_attn - (a * d_attn).sum(dim=1, keepdim=True)) / float(sp.temperature)
+        w1 = sp.w1.detach().flatten(1)
+        w2 = sp.w2.detach().flatten(1)
+        self._accumulate(sp.w2, g.t() @ rec.hidden)
+        self._accumulate(sp.b2, g.sum(dim=0))
+        dh = (g @ w2) * (rec.hidden > 0).to(g.dtype)
+        self._accumulate(sp.w1, dh.t() @ rec.pooled)
+        if sp.b1 is not None:
+            self._accumulate(sp.b1, dh.sum(dim=0))
+        if not need_dx or sp.stem:
+            return None
+        d_pooled = dh @ w1                                                            # (n, C) or (n, 4C)
+        h, w = rec.in_hw
+        wt, _ = ops.dyn_aggregate(a, rec.bank, transposed=True)
+        if sp.s2d:
+            shift = (d_pooled * (4.0 / (h * w))).contiguous()
+            return ops.conv_dgrad_s2d(d_raw, wt, sp.cin, sp.k, sp.pad, w_batch=n, res=res, shift=shift)
+        shift = (d_pooled * (1.0 / (h * w))).contiguous()
+        return ops.conv_dgrad(d_raw, wt, sp.cin, sp.k, sp.stride, sp.pad, rec.in_hw, w_batch=n, res=res, shift=shift,
+                              shift_per_sample=True)
 
     @staticmethod
     def _channel_sum(t: torch.Tensor) -> torch.Tensor:

@@ -23,7 +23,7 @@ from torch import nn
 
 from .. import ops
 from .._lib import EPI_STATS
-from ..engine import ConvUnit, Executor
+from ..engine import ConvUnit, DynSpec, Executor
 from ..utils.datatype import BatchData, DetectionResults
 from ._base import BaseModel, ConvModule, LightningModule, YOLOHead, to_nchw, to_nhwc
 
@@ -68,31 +68,31 @@ class DynamicSOEM(LightningModule):
         self.bn = nn.BatchNorm2d(num_features=in_attn // reduction_ratio, affine=True)
         self.silu = nn.SiLU(inplace=True)
         self.out_channels = in_attn // reduction_ratio
+        self.in_channels = in_channels
         self.kernel_size = dy_kernel_size
+        self._exec = Executor()
 
-    def forward_nhwc(self, x: torch.Tensor, attn_temp: float, train: bool) -> torch.Tensor:
-        n = x.shape[0]
-        pooled = ops.gap(x, s2d=True)                                               # (B, 4C)
+    def dyn_spec(self, attn_temp) -> DynSpec:
         lin1, lin2 = self.attention[2], self.attention[4]
-        attn = ops.attn_mlp_softmax(pooled, lin1.weight.detach(), lin1.bias.detach(), lin2.weight.detach(),
-                                    lin2.bias.detach(), float(attn_temp))             # (B, K)
-        bank = torch.stack([c.weight.detach() for c in self.dy_convs])                # (K, O, 4C, k, k)
-        bias_bank = torch.stack([c.bias.detach() for c in self.dy_convs]).contiguous()
-        w_b, bias_b = ops.dyn_aggregate(attn, bank, bias_bank=bias_bank)              # (B,O,k*k*4C) bf16, (B,O)
-        k, co, bn = self.kernel_size, self.out_channels, self.bn
-        if train:
-            sums = torch.zeros((2, co), dtype=torch.float32, device=x.device)
-            raw = ops.conv_fwd(x, w_b, co, k, 1, k // 2, s2d=True, w_batch=n, epi=EPI_STATS, shift=bias_b,
-                               shift_per_sample=True, sum_=sums[0], sumsq=sums[1])
-            _, ho, wo, _ = raw.shape
-            _, _, scale, shift = ops.bn_finalize(sums[0], sums[1], n * ho * wo, bn.eps, bn.momentum, bn.weight.detach(),
-                                                 bn.bias.detach(), bn.running_mean, bn.running_var)
-            bn.num_batches_tracked += 1
-            return ops.bn_act_fwd(raw, scale, shift, "silu")
-        scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
-        shift_b = (bn.bias.detach() - bn.running_mean * scale).unsqueeze(0) + bias_b * scale.unsqueeze(0)
-        return ops.conv_fwd(x, w_b, co, k, 1, k // 2, s2d=True, w_batch=n, act="silu", scale=scale,
-                            shift=shift_b.contiguous(), shift_per_sample=True)
+        convs = list(self.dy_convs)
+        return DynSpec(bank=lambda: torch.stack([c.weight.detach() for c in convs]),
+                       bias_bank=lambda: torch.stack([c.bias.detach() for c in convs]).contiguous(),
+                       bank_params=lambda: [(c.weight, i, False) for i, c in enumerate(convs)] +
+                                           [(c.bias, i, True) for i, c in enumerate(convs)],
+                       w1=lin1.weight, b1=lin1.bias, w2=lin2.weight, b2=lin2.bias, temperature=float(attn_temp),
+                       bn=self.bn, act="silu", cin=self.in_channels, cout=self.out_channels, k=self.kernel_size,
+                       stride=1, pad=self.kernel_size // 2, s2d=True, stem=False)
+
+    def forward_nhwc(self, x: torch.Tensor, attn_temp: float, train: bool, tape=None, ex=None) -> torch.Tensor:
+        """The K expert convolutions weighted by the attention and summed (reference :83-91) are linear in the
+        kernels: one aggregated kernel (+ bias) per sample, a single implicit GEMM reading x through the
+        space-to-depth parity view."""
+        own = ex is None
+        ex = self._exec if own else ex
+        y = ex.dyn_forward(self.dyn_spec(attn_temp), x, train, tape)
+        if own:
+            ex.end_forward()
+        return y
 
     def forward(self, x, attn_temp):
         return to_nchw(self.forward_nhwc(to_nhwc(x), attn_temp, self.training))
@@ -115,22 +115,47 @@ class SimplifiedFPN(LightningModule):
         self.x1_out_up = nn.Conv2d(c1, c2, kernel_size=1, stride=2)
         self._exec = Executor()
 
-    def forward_nhwc(self, f_maps, train: bool):
-        ex = self._exec
+    def forward_nhwc(self, f_maps, train: bool, tape=None, ex=None):
+        own = ex is None
+        ex = self._exec if own else ex
         x0, x1, x2 = f_maps
+        sub = [] if tape is not None else None
         bias_unit = lambda conv: ConvUnit(conv, None, "none")
         # center = x1 + conv(up(x2)) + x1   (x1 counted twice, reference :116 — reproduced)
-        t = ex.conv_forward(bias_unit(self.x2_in_down), x2, False, None)
+        t = ex.conv_forward(bias_unit(self.x2_in_down), x2, False, sub)
         center = ops.upsample2x_add(t, x1, 2.0)
-        t = ex.conv_forward(bias_unit(self.center_down), center, False, None)
+        t = ex.conv_forward(bias_unit(self.center_down), center, False, sub)
         x0 = ops.upsample2x_add(t, x0, 1.0)
-        x1 = ex.conv_forward(bias_unit(self.x0_out_up), x0, False, None, res=center)     # center + conv_s2(x0)
-        x2 = ex.conv_forward(bias_unit(self.x1_out_up), x1, False, None, res=x2)
-        outs = (ex.conv_forward(self.x0_conv_out.unit(), x0, train, None),
-                ex.conv_forward(self.x1_conv_out.unit(), x1, train, None),
-                ex.conv_forward(self.x2_conv_out.unit(), x2, train, None))
-        ex.end_forward()
+        x1 = ex.conv_forward(bias_unit(self.x0_out_up), x0, False, sub, res=center)     # center + conv_s2(x0)
+        x2 = ex.conv_forward(bias_unit(self.x1_out_up), x1, False, sub, res=x2)
+        outs = (ex.conv_forward(self.x0_conv_out.unit(), x0, train, sub),
+                ex.conv_forward(self.x1_conv_out.unit(), x1, train, sub),
+                ex.conv_forward(self.x2_conv_out.unit(), x2, train, sub))
+        if own:
+            ex.end_forward()
+        if tape is not None:
+            tape.append(("neck", sub))
         return outs
+
+    def backward_nhwc(self, d_outs, sub, ex):
+        """Reverse of forward_nhwc: gradients w.r.t. the three input maps; skip-path gradients ride in the
+        data-gradient epilogues."""
+        r_t1, r_t2, r_up0, r_up1, r_o0, r_o1, r_o2 = sub
+        dx2 = ex.conv_backward(r_o2, d_outs[2])
+        dx1 = ex.conv_backward(r_o1, d_outs[1])
+        dx0 = ex.conv_backward(r_o0, d_outs[0])
+        dx1 = ex.conv_backward(r_up1, dx2, res=dx1)           # x2 = f2 + conv_s2(x1)
+        d_f2 = dx2
+        dx0 = ex.conv_backward(r_up0, dx1, res=dx0)           # x1 = center + conv_s2(x0)
+        d_center = dx1
+        d_f0 = dx0                                            # x0 = f0 + up(t2)
+        d_t2 = ops.upsample2x_bwd(dx0)
+        d_center = ex.conv_backward(r_t2, d_t2, res=d_center)  # t2 = conv(center)
+        two = torch.full((d_center.shape[3],), 2.0, dtype=torch.float32, device=d_center.device)
+        d_f1 = ops.bn_act_fwd(d_center, two, None, "none")     # center = 2*f1 + up(t1)
+        d_t1 = ops.upsample2x_bwd(d_center)
+        d_f2 = ex.conv_backward(r_t1, d_t1, res=d_f2)          # t1 = conv(f2)
+        return d_f0, d_f1, d_f2
 
     def forward(self, f_maps: List[torch.Tensor]):
         return tuple(to_nchw(t) for t in self.forward_nhwc([to_nhwc(f) for f in f_maps], self.training))
@@ -158,17 +183,42 @@ class DySOEM_SimFPN(BaseModel):
     def forward(self, x, attn_temp=1.0) -> List[DetectionResults]:
         if not x.is_cuda:
             raise RuntimeError("multimodal_uav_det_b200 models run on CUDA only (no CPU fallback)")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError("DySOEM_SimFPN backward is scheduled for the next round (SURVEY §7 step 6); "
-                                      "wrap the forward in torch.no_grad()")
-        train = self.training
-        h = self._exec.conv_forward(self.input_stem.conv.unit(stem=True), x.float().contiguous(), train, None)
-        self._exec.end_forward()
+        x = x.float().contiguous()
+        self._attn_temp = attn_temp
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .darknet import _TrunkFn
+            anchor = torch.empty((), device=x.device).requires_grad_()
+            flat = _TrunkFn.apply(self, x, anchor)
+            return [DetectionResults(bbox=flat[2 * i], obj=flat[2 * i + 1]) for i in range(len(flat) // 2)]
+        return self._forward_program(x, None)
+
+    def _forward_program(self, x, tape):
+        ex, train, temp = self._exec, self.training, self._attn_temp
+        h = ex.conv_forward(self.input_stem.conv.unit(stem=True), x, train, tape)
         feats = []
         for soem in self.backbone:
-            h = soem.forward_nhwc(h, attn_temp, train)
+            h = soem.forward_nhwc(h, temp, train, tape, ex)
             feats.append(h)
-        return self.yolo_head.forward_nhwc(self.neck.forward_nhwc(feats, train))
+        outs = self.neck.forward_nhwc(feats, train, tape, ex)
+        ex.end_forward()
+        if tape is not None:
+            tape.append(("head", outs))
+        return self.yolo_head.forward_nhwc(outs)
+
+    def _backward_program(self, tape, head_grads):
+        """tape = [stem, soem0, soem1, soem2, ("neck", records), ("head", feature maps)]."""
+        ex = self._exec
+        feats = tape[-1][1]
+        d_outs = [self.yolo_head.backward_nhwc(s, feats[s], head_grads[s][0], head_grads[s][1], ex.grad_ready_hook)
+                  for s in range(len(feats))]
+        d_f0, d_f1, d_f2 = self.neck.backward_nhwc(d_outs, tape[-2][1], ex)
+        nb = len(self.backbone)
+        skips = [d_f0, d_f1, d_f2]
+        d = skips[nb - 1]
+        for j in range(nb - 1, -1, -1):
+            d = ex.dyn_backward(tape[1 + j], d, res=skips[j - 1] if j > 0 else None)
+        ex.conv_backward(tape[0], d, need_dx=False)
+        ex.end_backward()
 
     def training_step(self, batch: BatchData, batch_idx):
         outs = self.forward(batch.image, attn_temp=self.attn_temperature)

@@ -17,7 +17,7 @@ import torch
 from torch import nn
 
 from .. import ops
-from ..engine import ConvUnit, Executor, param_epoch
+from ..engine import ConvUnit, DynSpec, Executor, param_epoch
 from ..utils.datatype import BatchData, DetectionResults
 from ..utils.metrics import yolo_head_loss
 
@@ -96,46 +96,27 @@ class DyConvModule(LightningModule):
                                     requires_grad=True)
         self.bn = nn.BatchNorm2d(num_features=out_channels, affine=True)
         self.silu = nn.SiLU(inplace=True)
+        self._exec = Executor()
 
     # ---- NHWC path used by DyYOLO ----------------------------------------------------------------
-    def attention_scores(self, x, attn_temp) -> torch.Tensor:
-        """(B,K) softmax(MLP(GAP(x))/T) — one pooling kernel + one fused MLP/softmax kernel."""
-        pooled = ops.gap_nchw(x) if self.in_channels < 32 else ops.gap(x)
-        w1 = self.attention[1].weight.detach().flatten(1).contiguous()
-        w2 = self.attention[3].weight.detach().flatten(1).contiguous()
-        return ops.attn_mlp_softmax(pooled, w1, None, w2, self.attention[3].bias.detach(), float(attn_temp))
+    def dyn_spec(self, attn_temp) -> DynSpec:
+        return DynSpec(bank=lambda: self.weights.detach(), bias_bank=None,
+                       bank_params=lambda: [(self.weights, None, False)],
+                       w1=self.attention[1].weight, b1=None, w2=self.attention[3].weight, b2=self.attention[3].bias,
+                       temperature=float(attn_temp), bn=self.bn, act="silu", cin=self.in_channels,
+                       cout=self.out_channels, k=self.kernel_size, stride=self.stride, pad=self.padding,
+                       s2d=False, stem=self.in_channels < 32)
 
-    def forward_nhwc(self, x, attn_temp, train: Optional[bool] = None) -> torch.Tensor:
+    def forward_nhwc(self, x, attn_temp, train: Optional[bool] = None, tape: Optional[list] = None,
+                     ex: Optional[Executor] = None) -> torch.Tensor:
         """x: NHWC bf16, or the NCHW fp32 network input when in_channels == 3."""
         train = self.training if train is None else train
-        from .._lib import EPI_STATS
-        attn = self.attention_scores(x, attn_temp)
-        n = attn.shape[0]
-        k, s, p, co = self.kernel_size, self.stride, self.padding, self.out_channels
-        bn = self.bn
-        stem = self.in_channels < 32
-        if stem:
-            # per-sample fp32 kernels for the direct stem kernel: (B,O,I,k,k)
-            w_b = torch.mm(attn, self.weights.detach().flatten(1)).view(n, co, self.in_channels, k, k)
-        else:
-            w_b, _ = ops.dyn_aggregate(attn, self.weights.detach())
-        if train:
-            sums = torch.zeros((2, co), dtype=torch.float32, device=attn.device)
-            if stem:
-                raw = ops.stem_fwd(x, w_b, k, s, p, epi=EPI_STATS, sum_=sums[0], sumsq=sums[1], per_sample_w=True)
-            else:
-                raw = ops.conv_fwd(x, w_b, co, k, s, p, w_batch=n, epi=EPI_STATS, sum_=sums[0], sumsq=sums[1])
-            _, ho, wo, _ = raw.shape
-            mean, invstd, scale, shift = ops.bn_finalize(sums[0], sums[1], n * ho * wo, bn.eps, bn.momentum,
-                                                         bn.weight.detach(), bn.bias.detach(), bn.running_mean,
-                                                         bn.running_var)
-            bn.num_batches_tracked += 1
-            return ops.bn_act_fwd(raw, scale, shift, "silu")
-        scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
-        shift = bn.bias.detach() - bn.running_mean * scale
-        if stem:
-            return ops.stem_fwd(x, w_b, k, s, p, act="silu", scale=scale, shift=shift, per_sample_w=True)
-        return ops.conv_fwd(x, w_b, co, k, s, p, w_batch=n, act="silu", scale=scale, shift=shift)
+        own = ex is None
+        ex = self._exec if own else ex
+        y = ex.dyn_forward(self.dyn_spec(attn_temp), x, train, tape)
+        if own:
+            ex.end_forward()
+        return y
 
     def forward(self, x, attn_temp):
         stem = self.in_channels < 32
@@ -211,6 +192,44 @@ class YOLOHead(LightningModule):
 
     def forward(self, f_maps: List[torch.Tensor]):
         return self.forward_nhwc([to_nhwc(f) for f in f_maps])
+
+    def backward_nhwc(self, s: int, feat: torch.Tensor, d_bbox: Optional[torch.Tensor], d_obj: Optional[torch.Tensor],
+                      hook=None) -> torch.Tensor:
+        """Backward of the fused 1x1 head conv of scale `s`: returns dL/d(feature map) (NHWC bf16) and
+        accumulates the weight/bias gradients of conv_obj / conv_bbox."""
+        a = self.n_anchors
+        n, hh, ww, cin = feat.shape
+        dev = feat.device
+        # (B,A,H,W,1|4) fp32 -> NHWC bf16 with 32 channels [A obj | 4A bbox | zero pad]
+        dyh = torch.zeros((n, hh, ww, 32), dtype=torch.bfloat16, device=dev)
+        if d_obj is not None:
+            dyh[..., :a] = d_obj.squeeze(-1).permute(0, 2, 3, 1)
+        if d_bbox is not None:
+            dyh[..., a:5 * a] = d_bbox.permute(0, 2, 3, 1, 4).reshape(n, hh, ww, 4 * a)
+        conv_o = self.detection_head[s]["obj"].conv_obj
+        conv_b = self.detection_head[s]["bbox"].conv_bbox
+        dwp = ops.conv_wgrad(feat, dyh, 1, 1, 0)              # packed [32][cin]
+        for conv, lo, hi in ((conv_o, 0, a), (conv_b, a, 5 * a)):
+            g = dwp[lo:hi].view(hi - lo, cin, 1, 1)
+            if conv.weight.grad is None:
+                conv.weight.grad = g.clone()
+            else:
+                conv.weight.grad.add_(g)
+        bias_g = dyh.float().sum(dim=(0, 1, 2))
+        for conv, lo, hi in ((conv_o, 0, a), (conv_b, a, 5 * a)):
+            if conv.bias.grad is None:
+                conv.bias.grad = bias_g[lo:hi].clone()
+            else:
+                conv.bias.grad.add_(bias_g[lo:hi])
+        if hook is not None:
+            for conv in (conv_o, conv_b):
+                hook(conv.weight)
+                hook(conv.bias)
+        w = torch.zeros((32, cin, 1, 1), dtype=torch.float32, device=dev)
+        w[:a] = conv_o.weight.detach()
+        w[a:5 * a] = conv_b.weight.detach()
+        wt = ops.pack_weight(w, transposed=True)              # W^T packed [cin][32]
+        return ops.conv_dgrad(dyh, wt, cin, 1, 1, 0, (hh, ww))
 
     def _scaled_anchors(self, h: int, device) -> torch.Tensor:
         """anchors[h] / head_scales[h] (reference _base.py:170) as a cached device tensor, so the loss does no

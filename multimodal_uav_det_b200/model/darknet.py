@@ -18,7 +18,7 @@ import torch
 from torch import nn
 
 from .. import ops
-from ..engine import ConvUnit, Executor
+from ..engine import ConvUnit, DynRecord, Executor
 from ..utils.datatype import BatchData, DetectionResults
 from ._base import BaseModel, DyConvModule, LightningModule, YOLOHead, to_nhwc, to_nchw
 
@@ -213,10 +213,7 @@ class DarknetDetector(BaseModel):
                 if tape is not None:
                     tape.append(("concat", c))
             elif isinstance(layer, DyConvModule):
-                if tape is not None:
-                    raise NotImplementedError("DyConvModule backward is scheduled for the next round "
-                                              "(SURVEY §7 step 6); run DyYOLO under torch.no_grad()")
-                h = layer.forward_nhwc(h, self.attn_temp, train)
+                h = layer.forward_nhwc(h, self.attn_temp, train, tape, ex)
             else:
                 raise TypeError(f"unsupported layer {type(layer)}")
             if self._debug_taps is not None and not isinstance(layer, ScalePrediction) and li > 0:
@@ -257,6 +254,10 @@ class DarknetDetector(BaseModel):
                     dy = ops.add(dy, rg) if dy is not None else ops.add(rg, None)
                 i -= 1
                 continue
+            if isinstance(rec, DynRecord):
+                dy = ex.dyn_backward(rec, dy, need_dx=(i > 0))
+                i -= 1
+                continue
             if pending_scale is not None:
                 # scale-prediction conv: its input is the running activation; fuse `+ dy` (gradient
                 # from the layers after the branch) into the dgrad epilogue
@@ -278,42 +279,4 @@ class DarknetDetector(BaseModel):
 
     def _head_backward(self, s: int, feat: torch.Tensor, d_bbox: Optional[torch.Tensor],
                        d_obj: Optional[torch.Tensor]) -> torch.Tensor:
-        """Backward of the fused 1x1 head conv of scale `s`: returns dL/d(feature map), accumulates
-        the weight/bias gradients of conv_obj / conv_bbox."""
-        head = self.yolo_head
-        a = head.n_anchors
-        n, hh, ww, cin = feat.shape
-        dev = feat.device
-        # (B,A,H,W,1|4) fp32 -> NHWC bf16 with 32 channels [A obj | 4A bbox | zero pad]
-        dyh = torch.zeros((n, hh, ww, 32), dtype=torch.bfloat16, device=dev)
-        if d_obj is not None:
-            dyh[..., :a] = d_obj.squeeze(-1).permute(0, 2, 3, 1)
-        if d_bbox is not None:
-            dyh[..., a:5 * a] = d_bbox.permute(0, 2, 3, 1, 4).reshape(n, hh, ww, 4 * a)
-        conv_o = head.detection_head[s]["obj"].conv_obj
-        conv_b = head.detection_head[s]["bbox"].conv_bbox
-        # weight grads: packed [32][cin]
-        dwp = ops.conv_wgrad(feat, dyh, 1, 1, 0)
-        for conv, lo, hi in ((conv_o, 0, a), (conv_b, a, 5 * a)):
-            g = dwp[lo:hi].view(hi - lo, cin, 1, 1)
-            if conv.weight.grad is None:
-                conv.weight.grad = g.clone()
-            else:
-                conv.weight.grad.add_(g)
-        bias_g = dyh.float().sum(dim=(0, 1, 2))
-        for conv, lo, hi in ((conv_o, 0, a), (conv_b, a, 5 * a)):
-            if conv.bias.grad is None:
-                conv.bias.grad = bias_g[lo:hi].clone()
-            else:
-                conv.bias.grad.add_(bias_g[lo:hi])
-        hook = self._exec.grad_ready_hook
-        if hook is not None:
-            for conv in (conv_o, conv_b):
-                hook(conv.weight)
-                hook(conv.bias)
-        # data grad: W^T packed [cin][32]
-        w = torch.zeros((32, cin, 1, 1), dtype=torch.float32, device=dev)
-        w[:a] = conv_o.weight.detach()
-        w[a:5 * a] = conv_b.weight.detach()
-        wt = ops.pack_weight(w, transposed=True)
-        return ops.conv_dgrad(dyh, wt, cin, 1, 1, 0, (hh, ww))
+        return self.yolo_head.backward_nhwc(s, feat, d_bbox, d_obj, self._exec.grad_ready_hook)

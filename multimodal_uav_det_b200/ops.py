@@ -232,15 +232,34 @@ def conv_head(x: torch.Tensor, w_packed16: torch.Tensor, bias15: torch.Tensor, a
 
 def conv_dgrad(dy: torch.Tensor, w_packed_t: torch.Tensor, cin: int, k: int, stride: int, pad: int,
                in_hw: Tuple[int, int], *, w_batch: int = 1, out: Optional[torch.Tensor] = None,
-               res: Optional[torch.Tensor] = None) -> torch.Tensor:
+               res: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
+               shift_per_sample: bool = False) -> torch.Tensor:
+    """dx = conv_transpose(dy, w) (+ res) (+ shift[c] or shift[n][c], e.g. the gradient of a global average
+    pool broadcast over the pixels)."""
     _require_cuda(dy, w_packed_t)
     n = dy.shape[0]
     if out is None:
         out = empty_act(n, in_hw[0], in_hw[1], cin, dy.device)
     dv, xv = act_view(dy), act_view(out)
-    e = _epilogue(EPI_AFFINE, None, None, None, res)
+    e = _epilogue(EPI_AFFINE, None, None, _f32(shift), res, shift_per_sample=shift_per_sample)
     check(_lib.load().uavdet_conv_dgrad(C.byref(dv), _ptr(w_packed_t), w_batch, cin, k, stride, pad, C.byref(xv),
                                         C.byref(e), _stream()), "conv_dgrad")
+    return out
+
+
+def conv_dgrad_s2d(dy: torch.Tensor, w_packed_t: torch.Tensor, c: int, k: int, pad: int, *, w_batch: int = 1,
+                   out: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
+                   shift: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Data gradient through conv_fwd(s2d=True): dy (n,h/2,w/2,cout) -> dx (n,h,w,c).  `shift` is (n, 4c)."""
+    _require_cuda(dy, w_packed_t)
+    n, h2, w2, _ = dy.shape
+    hin, win = h2 + k - 1 - 2 * pad, w2 + k - 1 - 2 * pad
+    if out is None:
+        out = empty_act(n, 2 * hin, 2 * win, c, dy.device)
+    dv, xv = act_view(dy), act_view(out)
+    e = _epilogue(EPI_AFFINE, None, None, _f32(shift), res, shift_per_sample=shift is not None)
+    check(_lib.load().uavdet_conv_dgrad_s2d(C.byref(dv), _ptr(w_packed_t), w_batch, c, k, pad, C.byref(xv), C.byref(e),
+                                            _stream()), "conv_dgrad_s2d")
     return out
 
 
@@ -445,6 +464,15 @@ def dyn_aggregate(attn, bank, transposed=False, bias_bank=None):
                                            1 if transposed else 0, _ptr(out), _ptr(bias_bank), _ptr(bias_out),
                                            _stream()), "dyn_aggregate")
     return out, bias_out
+
+
+def dyn_bwd_contract(dwb, attn, bank, d_bank, d_attn, packed: bool):
+    """dwb (n, O*I*k*k) per-sample kernel gradients -> d_bank (K,O,I,k,k) += , d_attn (n,K) += ."""
+    n, K = attn.shape
+    _, o, i, k, _ = bank.shape
+    check(_lib.load().uavdet_dyn_bwd_contract(_ptr(_f32(dwb)), n, K, _ptr(_f32(attn)), _ptr(_f32(bank)), o, i, k,
+                                              1 if packed else 0, _ptr(_f32(d_bank)), _ptr(_f32(d_attn)), _stream()),
+          "dyn_bwd_contract")
 
 
 # --------------------------------------------------------------------------------------------

@@ -608,3 +608,70 @@ def test_stem_zero_padded_odd_output(lib):
     got = to_nchw(y)
     assert_close_bf16(got[:, :, :19, :19], ref, "stem padded interior", rel=4e-3)
     assert torch.all(got[:, :, 19, :] == 0) and torch.all(got[:, :, :, 19] == 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# backward of the dynamic-kernel convolutions
+# ------------------------------------------------------------------------------------------------
+def _s2d(x):
+    return torch.cat([x[..., i::2, j::2] for i in range(2) for j in range(2)], dim=1)
+
+
+@pytest.mark.parametrize("per_sample", [False, True])
+@pytest.mark.parametrize("c,cout,hw", [(32, 64, 32), (64, 128, 16), (32, 32, 24)])
+def test_conv_dgrad_s2d_matches_autograd(lib, per_sample, c, cout, hw):
+    """Data gradient through the fused space-to-depth conv (DySOEM_SimFPN.py:71-91) incl. the skip-path
+    residual and the per-sample pooled-attention shift, against autograd of the materialised formulation."""
+    ops = _ops(lib)
+    n, k = 3, 3
+    g = torch.Generator().manual_seed(90 + c)
+    x = bf16_round(torch.randn(n, c, hw, hw, generator=g)).requires_grad_(True)
+    wts = bf16_round(torch.randn(n if per_sample else 1, cout, 4 * c, k, k, generator=g) / math.sqrt(36 * c))
+    dy = bf16_round(torch.randn(n, cout, hw // 2, hw // 2, generator=g))
+    res = bf16_round(torch.randn(n, c, hw, hw, generator=g))
+    shift = torch.randn(n, 4 * c, generator=g) * 0.1
+    f = _s2d(x)
+    y = torch.cat([F.conv2d(f[i:i + 1], wts[i if per_sample else 0], None, 1, 1) for i in range(n)])
+    extra = (f * shift.view(n, 4 * c, 1, 1)).sum()          # d/dx = shift broadcast over each parity class
+    ((y * dy).sum() + extra).backward()
+    ref = x.grad + res
+    wt = torch.stack([ops.pack_weight(w.to(DEV), transposed=True) for w in wts])
+    got = ops.conv_dgrad_s2d(nhwc(dy), wt if per_sample else wt[0], c, k, 1, w_batch=n if per_sample else 1,
+                             res=nhwc(res), shift=shift.to(DEV))
+    ops.check_device()
+    assert_close_bf16(to_nchw(got), ref, "dgrad s2d")
+
+
+def test_conv_dgrad_per_sample_shift(lib):
+    ops = _ops(lib)
+    n, cin, cout, hw = 3, 64, 96, 20
+    x, wt = _conv_case(n, cin, cout, 3, 2, hw, hw, seed=17)
+    g = torch.Generator().manual_seed(18)
+    dy = bf16_round(torch.randn(n, cout, hw // 2, hw // 2, generator=g))
+    shift = torch.randn(n, cin, generator=g)
+    x = x.requires_grad_(True)
+    (F.conv2d(x, wt, None, 2, 1) * dy).sum().backward()
+    ref = x.grad + shift.view(n, cin, 1, 1)
+    got = ops.conv_dgrad(nhwc(dy), ops.pack_weight(wt.to(DEV), transposed=True), cin, 3, 2, 1, (hw, hw),
+                         shift=shift.to(DEV), shift_per_sample=True)
+    ops.check_device()
+    assert_close_bf16(to_nchw(got), ref, "dgrad per-sample shift")
+
+
+@pytest.mark.parametrize("packed", [False, True])
+@pytest.mark.parametrize("K,O,I,k,n", [(4, 64, 32, 3, 5), (3, 32, 128, 3, 4), (4, 512, 1024, 1, 32), (4, 32, 3, 3, 6)])
+def test_dyn_bwd_contract(lib, packed, K, O, I, k, n):
+    """d_bank[k] = sum_b a[b,k] dW_b, d_attn[b,k] = <dW_b, bank[k]> (autograd of _base.py:65-66)."""
+    ops = _ops(lib)
+    g = torch.Generator().manual_seed(K * 100 + k)
+    bank = torch.randn(K, O, I, k, k, generator=g)
+    attn = torch.softmax(torch.randn(n, K, generator=g), dim=1)
+    dwb = torch.randn(n, O, I, k, k, generator=g)                         # OIHW per sample
+    want_bank = torch.einsum("bk,boihw->koihw", attn, dwb)
+    want_attn = torch.einsum("boihw,koihw->bk", dwb, bank)
+    src = dwb.permute(0, 1, 3, 4, 2).contiguous() if packed else dwb      # packed: [O][kh][kw][I]
+    d_bank = torch.zeros_like(bank).to(DEV)
+    d_attn = torch.zeros(n, K, device=DEV)
+    ops.dyn_bwd_contract(src.reshape(n, -1).to(DEV), attn.to(DEV), bank.to(DEV), d_bank, d_attn, packed=packed)
+    torch.testing.assert_close(d_bank.cpu(), want_bank, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(d_attn.cpu(), want_attn, rtol=1e-3, atol=1e-2)

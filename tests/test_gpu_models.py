@@ -373,3 +373,146 @@ def test_graphed_train_step_equals_eager(lib, train_bn):
     with torch.no_grad():
         out = model(xs[0])
     assert torch.isfinite(out[0].bbox).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# training of the dynamic-kernel models (DyYOLO, DySOEM_SimFPN)
+# ------------------------------------------------------------------------------------------------
+# every DyConv flavour of conf/model/dy-yolo.yaml on a short trunk: cin=3 stem, 3x3 stride 2, 1x1 after a scale
+# block and 1x1 on a route concat; routes at 2-repeat blocks
+DYMINI = [["DyConv", 32, 3, 1], ["DyConv", 64, 3, 2], ["B", 2], [128, 3, 2], ["DyConv", 64, 1, 1], [128, 3, 1], ["S"],
+          [32, 1, 1], ["U"], ["DyConv", 64, 1, 1], [128, 3, 1], ["S"]]
+
+
+def _grad_report(model, sd, tag):
+    grads = []
+    bn_params = {f"{mn}.{pn}" for mn, m in model.named_modules() if isinstance(m, torch.nn.BatchNorm2d)
+                 for pn, _ in m.named_parameters()}
+    for name, p in model.named_parameters():
+        ref = sd[name].grad
+        if p.grad is None:
+            assert ref is None or name in bn_params, name      # frozen BN: affine not trained
+            continue
+        assert ref is not None, name
+        grads.append((rel_l2(p.grad.cpu(), ref), cosine(p.grad.cpu(), ref), name))
+    grads.sort(reverse=True)
+    med = grads[len(grads) // 2][0]
+    print(f"{tag}: {len(grads)} tensors, grad rel_l2 median={med:.4f}; worst:", [(f"{g[0]:.3f}", f"{g[1]:.4f}", g[2]) for g in grads[:4]])
+    return med, grads
+
+
+@pytest.mark.parametrize("train_bn", [False, True])
+def test_dyyolo_train_step_matches_oracle_autograd(lib, train_bn):
+    """DyYOLO forward + loss + backward (attention MLP, expert-bank aggregation, per-sample kernels) against
+    autograd through the oracle's restatement of DyConvModule (_base.py:26-77).  Frozen BN: tight; batch-stat
+    BN: direction only (the unscaled randn expert bank makes bf16 drift 10x Baseline's)."""
+    from oracle import oracle as O
+    from multimodal_uav_det_b200.utils.datatype import BatchData
+    from multimodal_uav_det_b200 import ops
+    size, b, temp = 64, 8, 30.0
+    over = dict(anchors=[ANCHORS[1], ANCHORS[2]], head_scales=[4, 2], attn_temperature=temp,
+                loss_balancing=dict(obj_scales_w=[1.0, 2.0], bbox_w=4.0, objectness_w=1.0, no_obj_w=4.0))
+    model, hp = make("DyYOLO", DYMINI, **over)
+    model.route_repeats = 2
+    anchors = (torch.tensor(hp["anchors"]).float() * size / 640).tolist()
+    model.yolo_head.anchors = torch.tensor(anchors).float()
+    if not train_bn:
+        randomize_bn(model)
+    model.train(train_bn)
+    x = synth_input(b, size)
+    tg = _targets(hp, b, size, grids=[16, 32])
+    sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k)
+          for k, v in model.state_dict(keep_vars=False).items()}
+    with O.bf16_pipeline(True):
+        outs_ref = O.darknet_forward(x, sd, DYMINI, attn_temperature=temp, train=train_bn, route_repeats=2)
+        loss_ref, _, _ = O.yolo_loss(outs_ref, tg, anchors, hp["head_scales"], hp["loss_balancing"], "ciou")
+        loss_ref.backward()
+    model = model.to(DEV)
+    outs = model(x.to(DEV))
+    batch = BatchData(image=x.to(DEV), bbox=[[t.to(DEV) for t in per] for per in copy.deepcopy(tg)])
+    loss, _, _, _ = model.yolo_head.compute_metrics(outs, batch)
+    loss.backward()
+    ops.check_device()
+    fwd = [max(rel_l2(g.bbox.detach().cpu(), wb.detach()), rel_l2(g.obj.detach().cpu(), wo.detach()))
+           for g, (wb, wo) in zip(outs, outs_ref)]
+    print(f"dyyolo train_bn={train_bn}: loss ref={loss_ref.item():.5f} got={loss.item():.5f} fwd={fwd}")
+    med, grads = _grad_report(model, sd, f"dyyolo train_bn={train_bn}")
+    assert abs(loss.item() - loss_ref.item()) <= 0.02 * abs(loss_ref.item())
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+    dyn = [g for g in grads if ".weights" in g[2] or ".attention." in g[2]]
+    assert len(dyn) >= 12                                   # 4 sites x (bank, attention w1, w2, b2)
+    if not train_bn:
+        assert max(fwd) < 0.05
+        assert med < 0.06 and min(g[1] for g in grads) > 0.97, grads[:5]
+    else:
+        cos = sorted(g[1] for g in grads)
+        assert cos[len(cos) // 2] > 0.9
+
+
+@pytest.mark.parametrize("train_bn", [False, True])
+def test_dysoem_simfpn_train_step_matches_oracle_autograd(lib, train_bn):
+    """DySOEM_SimFPN forward + loss + backward (aggregate-first dynamic kernels through the space-to-depth view,
+    SimFPN skip algebra, fused head) against autograd through the oracle, which executes the reference's
+    K-convs-then-weighted-sum formulation.  The heads come out at size/2, size/4, size/8, so the
+    targets are encoded on those grids."""
+    from oracle import oracle as O
+    from multimodal_uav_det_b200.model import DySOEM_SimFPN
+    from multimodal_uav_det_b200.utils.datatype import BatchData, Config
+    from multimodal_uav_det_b200 import ops
+    size, b, temp = 64, 8, 30.0
+    hp = dict(DYSOEM_HP)
+    torch.manual_seed(0)
+    model = DySOEM_SimFPN(hparams=Config(hp))
+    anchors = (torch.tensor(hp["anchors"]).float() * size / 640).tolist()
+    model.yolo_head.anchors = torch.tensor(anchors).float()
+    if not train_bn:
+        randomize_bn(model)
+    model.train(train_bn)
+    x = synth_input(b, size)
+    tg = _targets(hp, b, size, grids=[size // 2, size // 4, size // 8])
+    sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k)
+          for k, v in model.state_dict(keep_vars=False).items()}
+    with O.bf16_pipeline(True):
+        outs_ref = O.dysoem_simfpn_forward(x, sd, temp, train=train_bn)
+        loss_ref, _, _ = O.yolo_loss(outs_ref, tg, anchors, hp["head_scales"], hp["loss_balancing"], "mse")
+        loss_ref.backward()
+    model = model.to(DEV)
+    outs = model(x.to(DEV), attn_temp=temp)
+    batch = BatchData(image=x.to(DEV), bbox=[[t.to(DEV) for t in per] for per in copy.deepcopy(tg)])
+    loss, _, _, _ = model.yolo_head.compute_metrics(outs, batch)
+    loss.backward()
+    ops.check_device()
+    fwd = [max(rel_l2(g.bbox.detach().cpu(), wb.detach()), rel_l2(g.obj.detach().cpu(), wo.detach()))
+           for g, (wb, wo) in zip(outs, outs_ref)]
+    print(f"dysoem train_bn={train_bn}: loss ref={loss_ref.item():.5f} got={loss.item():.5f} fwd={fwd}")
+    med, grads = _grad_report(model, sd, f"dysoem train_bn={train_bn}")
+    assert abs(loss.item() - loss_ref.item()) <= 0.01 * abs(loss_ref.item())
+    if not train_bn:
+        assert max(fwd) < 0.03
+        assert med < 0.05 and min(g[1] for g in grads) > 0.97, grads[:5]
+    else:
+        # the expert biases feed a batch-stat BN: their gradient is the residue of an almost exact cancellation
+        # (zero if the attention were constant over the batch), i.e. noise in both implementations
+        cos = sorted(g[1] for g in grads if not (".dy_convs." in g[2] and g[2].endswith(".bias")))
+        assert cos[len(cos) // 2] > 0.9 and cos[0] > 0.5
+
+
+def test_dysoem_graphed_train_step(lib):
+    """DySOEM_SimFPN through FlatSGDTrainer + GraphedTrainStep: the loss decreases over a few replays."""
+    from multimodal_uav_det_b200.model import DySOEM_SimFPN
+    from multimodal_uav_det_b200.parallel import FlatSGDTrainer, GraphedTrainStep
+    from multimodal_uav_det_b200.utils.datatype import Config
+    from multimodal_uav_det_b200 import ops
+    size, b = 64, 8
+    hp = dict(DYSOEM_HP)
+    torch.manual_seed(0)
+    model = DySOEM_SimFPN(hparams=Config(hp)).to(DEV).train()
+    trainer = FlatSGDTrainer(model, lr=1e-3, momentum=0.7)
+    x = synth_input(b, size).to(DEV)
+    per = _targets(hp, b, size, grids=[size // 2, size // 4, size // 8])
+    tg = [torch.stack([per[i][h] for i in range(b)]).to(DEV) for h in range(3)]
+    step = GraphedTrainStep(model, trainer, x, tg, warmup=1)
+    losses = [step(x, tg).item() for _ in range(6)]
+    ops.check_device()
+    print("dysoem graphed losses", losses)
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
