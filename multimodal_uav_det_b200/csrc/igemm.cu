@@ -197,7 +197,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           for (int kc = 0; kc < P.kc_per_tap; ++kc, ++g) {
             if ((g & pmask) == (uint32_t)warp) {
               const ConvTap tap = P.taps[t];
-              mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u, dead, P.watchdog, 0x1u);
+              mbar_wait<32>(smem_u32(&empty_bar[stage]), phase ^ 1u, dead, P.watchdog, 0x1u);
               const uint32_t fb = smem_u32(&full_bar[stage]);
               mbar_arrive_expect_tx(fb, (uint32_t)(a_tx + b_bytes));
               uint8_t* sa = smem + (size_t)stage * stage_bytes;
@@ -270,7 +270,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         const TileCoord tc = decode_tile(P, tile);
         const int oh = tc.oh0 + hl, ow = tc.ow0 + wl;
         const bool valid = (row < kp) && (oh < P.ho) && (ow < P.wo);
-        mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, dead, P.watchdog, 0x8u);
+        mbar_wait<64>(smem_u32(&tfull_bar[acc]), acc_phase, dead, P.watchdog, 0x8u);
         tc_fence_after();
         if (half == 0) {
           uint32_t r[16];
@@ -359,7 +359,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             P.res ? P.res + (size_t)tc.img * P.res_sn + (size_t)oh * P.res_sh + (size_t)ow * P.res_sw : nullptr;
         const float* shift = P.shift ? P.shift + (size_t)tc.img * P.shift_sn : nullptr;
         if (tr) P.trace[tl * 16 + 5] = clock64();
-        mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, dead, P.watchdog, 0x8u);
+        mbar_wait<64>(smem_u32(&tfull_bar[acc]), acc_phase, dead, P.watchdog, 0x8u);
         if (tr) P.trace[tl * 16 + 6] = clock64();
         tc_fence_after();
         const uint32_t tbase = tmem_base + (uint32_t)(acc * kAccStride) + ((uint32_t)(q * 32) << 16);
@@ -458,7 +458,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             P.res ? P.res + (size_t)tc.img * P.res_sn + (size_t)oh * P.res_sh + (size_t)ow * P.res_sw : nullptr;
         const float* shift = P.shift ? P.shift + (size_t)tc.img * P.shift_sn : nullptr;
         if (tr) P.trace[tl * 16 + 5] = clock64();
-        mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, dead, P.watchdog, 0x8u);
+        mbar_wait<64>(smem_u32(&tfull_bar[acc]), acc_phase, dead, P.watchdog, 0x8u);
         if (tr) P.trace[tl * 16 + 6] = clock64();
         tc_fence_after();
         const uint32_t tbase = tmem_base + (uint32_t)(acc * kAccStride) + ((uint32_t)(q * 32) << 16);

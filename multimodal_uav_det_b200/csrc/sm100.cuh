@@ -53,20 +53,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 
 // Bounded wait.  A correct pipeline never waits longer than microseconds; if a wait exceeds
-// ~1e9 cycles the kernel records `code` in the global watchdog word, raises the CTA-wide
+// ~2e9 cycles the kernel records `code` in the global watchdog word, raises the CTA-wide
 // `dead` flag (so every later wait returns at once) and carries on to a clean exit.  This
 // keeps a barrier bug from hanging the GPU box; results are garbage and the host reports it.
+// kSleepNs > 0: back off between polls — for roles that wait a long time by design (epilogue warps during the
+// main loop, producers on a full pipeline) so their polling does not steal issue slots from the MMA thread that
+// shares their scheduler.  The watchdog bookkeeping runs once per 1024 polls, off the hot path.
+template <int kSleepNs = 0>
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile uint32_t* dead,
                                           unsigned int* watchdog, uint32_t code) {
   if (mbar_try_wait(bar, parity)) return true;
-  const long long t0 = clock64();
+  uint32_t polls = 0;
+  long long t0 = 0;
   while (true) {
     if (mbar_try_wait(bar, parity)) return true;
-    if (*dead) return false;
-    if (clock64() - t0 > 1000000000ll) {
-      *dead = 1;
-      atomicOr(watchdog, code);
-      return false;
+    if (kSleepNs > 0) __nanosleep(kSleepNs);
+    if ((++polls & 1023u) == 0u) {
+      if (*dead) return false;
+      const long long now = clock64();
+      if (t0 == 0) {
+        t0 = now;
+      } else if (now - t0 > 2000000000ll) {
+        *dead = 1;
+        atomicOr(watchdog, code);
+        return false;
+      }
     }
   }
 }

@@ -15,45 +15,98 @@
 #include "common.cuh"
 #include "sm100.cuh"
 #include "igemm.h"
+#include <stdlib.h>
 
 namespace uavdet {
 using namespace sm100;
 
 constexpr int kWgradThreads = 192;
+constexpr int kMaxCols = 20;
+constexpr int kMaxSlots = 16;   // taps per CTA (512 TMEM columns / 32)
+
+// A "column" = the filter taps that differ only in their vertical offset (same channel block, same horizontal
+// offset, same row parity).  They read the same input pixels shifted by whole tile rows, so ONE TMA box of
+// (tile_h + nv - 1) x tile_w pixels feeds all nv of them: tap v starts v*tile_w smem rows further down (tile_w is a
+// multiple of 8, which keeps every start on a swizzle-atom boundary).  3x3 stride 1: 3 columns of 3 taps, i.e. 3
+// input boxes per pixel tile instead of 9.
+struct WgCol {
+  int c_off, dw, p, dh0;   // TMA coordinates of the box origin relative to the pixel tile (see ConvTap)
+  int nv;                  // taps in the column
+  int tap0;                // index of its first tap in WgradParams::koff
+  int map;                 // which X tensor map (box height tile_h + nv - 1) loads it
+  int off, blk;            // smem byte offset of its first channel block inside a stage / bytes per channel block
+};
 
 struct WgradParams {
   int n_img, ho, wo;                // dY grid
-  int tile_w, tile_h, tiles_w, tiles_h, kp;  // pixel tile (kp = tile_w*tile_h, multiple of 16)
+  int tile_w, tile_h, tiles_w, tiles_h;
+  int kp, kp_pad;                   // pixels per K tile, rounded up to the MMA K step (16); the pad rows stay zero
   int cout, cin_blk;                // cin_blk = N per tap (multiple of 32, <= 256)
   int a_width, b_width;             // channels per TMA box (64 | 32) for dY / X
-  int num_taps, group;              // taps total, taps per CTA
-  int ci_blocks, co_blocks, tap_groups, items;
+  int num_cols, num_groups, cols_per_group;
+  int ci_blocks, co_blocks, items;
   int k_splits, tiles_per_split, total_pixel_tiles;
   int per_sample;
   long long k_total;                // row length of packed dW
   long long sample_stride;          // elements between per-sample gradients
-  int stages;
+  int stages, stage_bytes, a_bytes;
   float* dw;
   unsigned int* watchdog;
-  ConvTap taps[kMaxTaps];
+  WgCol cols[kMaxCols];
+  int grp_x_bytes[kMaxCols];        // bytes of X one stage of column group g receives
+  int koff[kMaxTaps];               // K offset of every tap inside the packed weight row, column-major order
+  int tap_off[kMaxTaps];            // smem byte offset (inside a stage) of the first row each tap reads
+  int tap_lbo[kMaxTaps];            // bytes between the channel blocks of that tap's box
 };
 
+struct WgIssue {
+  uint32_t full_bar, empty_bar;     // smem addresses of the barrier arrays
+  int num_kb, ksteps, stages;
+  uint64_t a0;                      // dY descriptor of stage 0, K step 0
+  uint32_t a_step, b_step, stage_step;   // (bytes >> 4) added per K step / per stage
+  uint32_t tmem_base, cin_blk, idesc;
+  volatile uint32_t* dead;
+  unsigned int* watchdog;
+};
+
+// MMA issue loop of one CTA, specialised on the number of taps NS (accumulators) it owns.
+template <int NS>
+__device__ __forceinline__ void wgrad_issue(const WgIssue& is, const uint64_t (&bd)[kMaxSlots]) {
+  int stage = 0;
+  uint32_t phase = 0, soff = 0;
+  for (int kb = 0; kb < is.num_kb; ++kb) {
+    mbar_wait(is.full_bar + 8u * (uint32_t)stage, phase, is.dead, is.watchdog, 0x20u);
+    tc_fence_after();
+    for (int ks = 0; ks < is.ksteps; ++ks) {
+      const uint64_t ad = is.a0 + (uint64_t)(soff + ks * is.a_step);
+      const uint64_t boff = (uint64_t)(soff + ks * is.b_step);
+      const uint32_t accum = (kb | ks) != 0 ? 1u : 0u;
+#pragma unroll
+      for (int i = 0; i < NS; ++i)
+        tc_mma_bf16(is.tmem_base + (uint32_t)i * is.cin_blk, ad, bd[i] + boff, is.idesc, accum);
+    }
+    tc_commit(is.empty_bar + 8u * (uint32_t)stage);
+    soff += is.stage_step;
+    if (++stage == is.stages) { stage = 0; phase ^= 1u; soff = 0; }
+  }
+}
+
 __global__ void __launch_bounds__(kWgradThreads, 1)
-wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapX,
+wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapX0,
+             const __grid_constant__ CUtensorMap mapX1, const __grid_constant__ CUtensorMap mapX2,
              const __grid_constant__ WgradParams P) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ---- work decode -----------------------------------------------------------------------
   int item = blockIdx.x % P.items;
   const int split = blockIdx.x / P.items;
-  const int tg = item % P.tap_groups; item /= P.tap_groups;
+  const int grp = item % P.num_groups; item /= P.num_groups;
   const int cib = item % P.ci_blocks;
   const int cob = item / P.ci_blocks;
-  const int tap0 = tg * P.group;
-  const int ntap = min(P.group, P.num_taps - tap0);
-  const int img_only = P.per_sample ? blockIdx.y : -1;
+  const int col0 = grp * P.cols_per_group;
+  const int ncol = min(P.cols_per_group, P.num_cols - col0);
+  const int img_only = P.per_sample ? (int)blockIdx.y : -1;
   const int pt_begin = split * P.tiles_per_split;
   const int tiles_here_total = P.per_sample ? P.tiles_h * P.tiles_w : P.total_pixel_tiles;
   const int pt_end = min(pt_begin + P.tiles_per_split, tiles_here_total);
@@ -62,11 +115,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ 
   const int a_row = P.a_width * 2, b_row = P.b_width * 2;        // bytes per smem row
   const int a_blocks = 128 / P.a_width;                          // 64-/32-channel boxes covering M=128
   const int b_blocks = P.cin_blk / P.b_width;
-  const int a_blk_bytes = P.kp * a_row, b_blk_bytes = P.kp * b_row;
-  const int a_bytes = a_blocks * a_blk_bytes;
-  const int b_tap_bytes = b_blocks * b_blk_bytes;
-  const int stage_bytes = a_bytes + P.group * b_tap_bytes;
-  uint8_t* ctrl = smem + (size_t)P.stages * stage_bytes;
+  const int a_blk_bytes = P.kp_pad * a_row;
+  uint8_t* ctrl = smem + (size_t)P.stages * P.stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* done_bar = empty_bar + kMaxStages;
@@ -82,11 +132,19 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ 
     *dead = 0;
     fence_barrier_init();
     prefetch_tensormap(&mapDY);
-    prefetch_tensormap(&mapX);
+    prefetch_tensormap(&mapX0);
   }
   if (warp == 1) {
     tmem_alloc(smem_u32(tmem_ptr), 512);
     tmem_relinquish();
+  }
+  // The K padding rows (and the rows past a shared box that its last tap touches) are never written by TMA:
+  // zero the pipeline buffers once so they contribute exact zeros.
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const int n16 = P.stages * P.stage_bytes / 16;
+    for (int i = threadIdx.x; i < n16; i += kWgradThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
@@ -98,53 +156,73 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ 
   int a_live = (P.cout - co0 + P.a_width - 1) / P.a_width;
   if (a_live > a_blocks) a_live = a_blocks;
 
+  const int tx_bytes = a_live * P.kp * a_row + P.grp_x_bytes[grp];   // bytes one stage receives
+
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      int tw, th, img;
+      {
+        int pt = pt_begin;
+        tw = pt % P.tiles_w; pt /= P.tiles_w;
+        th = pt % P.tiles_h;
+        img = P.per_sample ? img_only : pt / P.tiles_h;
+      }
       for (int kb = 0; kb < num_kb; ++kb) {
-        int pt = pt_begin + kb;
-        const int tw = pt % P.tiles_w; pt /= P.tiles_w;
-        const int th = pt % P.tiles_h;
-        const int img = P.per_sample ? img_only : pt / P.tiles_h;
         const int ow0 = tw * P.tile_w, oh0 = th * P.tile_h;
-        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u, dead, P.watchdog, 0x10u);
+        mbar_wait<32>(smem_u32(&empty_bar[stage]), phase ^ 1u, dead, P.watchdog, 0x10u);
         const uint32_t fb = smem_u32(&full_bar[stage]);
-        mbar_arrive_expect_tx(fb, (uint32_t)(a_live * a_blk_bytes + ntap * b_tap_bytes));
-        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+        mbar_arrive_expect_tx(fb, (uint32_t)tx_bytes);
+        uint8_t* sa = smem + (size_t)stage * P.stage_bytes;
         for (int ab = 0; ab < a_live; ++ab)
           tma_load_5d(smem_u32(sa + ab * a_blk_bytes), &mapDY, fb, co0 + ab * P.a_width, ow0, 0, oh0, img);
-        for (int t = 0; t < ntap; ++t) {
-          const ConvTap tap = P.taps[tap0 + t];
-          uint8_t* sb = sa + a_bytes + t * b_tap_bytes;
+        for (int c = 0; c < ncol; ++c) {
+          const WgCol col = P.cols[col0 + c];
+          const CUtensorMap* mx = col.map == 0 ? &mapX0 : (col.map == 1 ? &mapX1 : &mapX2);
           for (int bb = 0; bb < b_blocks; ++bb)
-            tma_load_5d(smem_u32(sb + bb * b_blk_bytes), &mapX, fb,
-                        tap.c_off + cib * P.cin_blk + bb * P.b_width, ow0 + tap.dw, tap.p, oh0 + tap.dh, img);
+            tma_load_5d(smem_u32(sa + col.off + bb * col.blk), mx, fb, col.c_off + cib * P.cin_blk + bb * P.b_width,
+                        ow0 + col.dw, col.p, oh0 + col.dh0, img);
         }
+        if (++tw == P.tiles_w) { tw = 0; if (++th == P.tiles_h) { th = 0; ++img; } }
         if (++stage == P.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
+      // The single issuing thread must spend < 64 cycles per MMA (M128 x N128 x K16) to keep the tensor pipe
+      // busy, so everything that does not change inside the loop is hoisted: one 64-bit descriptor per tap
+      // (stage 0, K step 0) lives in registers; stage / K-step offsets are added in the (address >> 4) field.
       const uint32_t idesc = make_idesc_bf16(P.cin_blk, 1, 1);  // both operands MN-major
       const uint32_t a_layout = P.a_width == 64 ? 2u : 4u, b_layout = P.b_width == 64 ? 2u : 4u;
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(smem_u32(&full_bar[stage]), phase, dead, P.watchdog, 0x20u);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-        for (int ks = 0; ks < P.kp / 16; ++ks) {
-          // MN-major: LBO = stride between channel blocks, SBO = stride between 8-pixel groups
-          const uint64_t a_desc = make_smem_desc(sa + ks * 16 * a_row, a_blk_bytes, 8 * a_row, a_layout);
-          for (int t = 0; t < ntap; ++t) {
-            const uint64_t b_desc = make_smem_desc(sa + a_bytes + t * b_tap_bytes + ks * 16 * b_row,
-                                                   b_blk_bytes, 8 * b_row, b_layout);
-            tc_mma_bf16(tmem_base + (uint32_t)(t * P.cin_blk), a_desc, b_desc, idesc, (kb | ks) != 0 ? 1u : 0u);
-          }
-        }
-        tc_commit(smem_u32(&empty_bar[stage]));
-        if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+      const int ksteps = P.kp_pad / 16;
+      const uint32_t sa0 = smem_u32(smem);
+      const uint64_t a0 = make_smem_desc(sa0, a_blk_bytes, 8 * a_row, a_layout);
+      const int t0 = P.cols[col0].tap0;
+      int nslots = 0;
+      for (int c = 0; c < ncol; ++c) nslots += P.cols[col0 + c].nv;
+      uint64_t bd[kMaxSlots];
+#pragma unroll
+      for (int i = 0; i < kMaxSlots; ++i)
+        bd[i] = i < nslots ? make_smem_desc(sa0 + (uint32_t)P.tap_off[t0 + i], (uint32_t)P.tap_lbo[t0 + i], 8 * b_row, b_layout)
+                           : 0ull;
+      const uint32_t a_step = (uint32_t)(16 * a_row) >> 4, b_step = (uint32_t)(16 * b_row) >> 4;
+      const uint32_t stage_step = (uint32_t)P.stage_bytes >> 4;
+      WgIssue is;
+      is.full_bar = smem_u32(full_bar); is.empty_bar = smem_u32(empty_bar);
+      is.num_kb = num_kb; is.ksteps = ksteps; is.stages = P.stages;
+      is.a0 = a0; is.a_step = a_step; is.b_step = b_step; is.stage_step = stage_step;
+      is.tmem_base = tmem_base; is.cin_blk = (uint32_t)P.cin_blk; is.idesc = idesc;
+      is.dead = dead; is.watchdog = P.watchdog;
+      switch (nslots) {     // one specialisation per tap count: only live MMAs in the instruction stream
+        case 1: wgrad_issue<1>(is, bd); break;    case 2: wgrad_issue<2>(is, bd); break;
+        case 3: wgrad_issue<3>(is, bd); break;    case 4: wgrad_issue<4>(is, bd); break;
+        case 5: wgrad_issue<5>(is, bd); break;    case 6: wgrad_issue<6>(is, bd); break;
+        case 7: wgrad_issue<7>(is, bd); break;    case 8: wgrad_issue<8>(is, bd); break;
+        case 9: wgrad_issue<9>(is, bd); break;    case 10: wgrad_issue<10>(is, bd); break;
+        case 11: wgrad_issue<11>(is, bd); break;  case 12: wgrad_issue<12>(is, bd); break;
+        case 13: wgrad_issue<13>(is, bd); break;  case 14: wgrad_issue<14>(is, bd); break;
+        case 15: wgrad_issue<15>(is, bd); break;  default: wgrad_issue<16>(is, bd); break;
       }
       tc_commit(smem_u32(done_bar));
     }
@@ -155,23 +233,27 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ 
     // line) instead of 32 different rows.
     const int q = warp & 3;
     float* scratch = reinterpret_cast<float*>(tmem_ptr + 4) + (warp - 2) * (32 * 33);
-    mbar_wait(smem_u32(done_bar), 0, dead, P.watchdog, 0x40u);
+    mbar_wait<256>(smem_u32(done_bar), 0, dead, P.watchdog, 0x40u);
     tc_fence_after();
     const int row0 = co0 + q * 32;
     float* base = P.dw + (P.per_sample ? (long long)img_only * P.sample_stride : 0);
-    for (int t = 0; t < ntap; ++t) {
-      const long long koff = P.taps[tap0 + t].w_koff + (long long)cib * P.cin_blk;
-      for (int c0 = 0; c0 < P.cin_blk; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (uint32_t)(t * P.cin_blk + c0) + ((uint32_t)(q * 32) << 16), r);
-        tmem_ld_wait();
+    int slot = 0;
+    for (int c = 0; c < ncol; ++c) {
+      const WgCol col = P.cols[col0 + c];
+      for (int v = 0; v < col.nv; ++v, ++slot) {
+        const long long koff = P.koff[col.tap0 + v] + (long long)cib * P.cin_blk;
+        for (int c0 = 0; c0 < P.cin_blk; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (uint32_t)(slot * P.cin_blk + c0) + ((uint32_t)(q * 32) << 16), r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) scratch[lane * 33 + i] = __uint_as_float(r[i]);
-        __syncwarp();
-        const int nrows = min(32, P.cout - row0);
-        for (int rr = 0; rr < nrows; ++rr)
-          atomicAdd(base + (long long)(row0 + rr) * P.k_total + koff + c0 + lane, scratch[rr * 33 + lane]);
-        __syncwarp();
+          for (int i = 0; i < 32; ++i) scratch[lane * 33 + i] = __uint_as_float(r[i]);
+          __syncwarp();
+          const int nrows = min(32, P.cout - row0);
+          for (int rr = 0; rr < nrows; ++rr)
+            atomicAdd(base + (long long)(row0 + rr) * P.k_total + koff + c0 + lane, scratch[rr * 33 + lane]);
+          __syncwarp();
+        }
       }
     }
   }
@@ -184,21 +266,23 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ 
   }
 }
 
-// pixel tile for the K dimension: tile_w*tile_h must be an exact multiple of 16 (every smem row
-// feeds the reduction) and <= 64; pick the one wasting the fewest zero-filled pixels.
-static void choose_k_tile(int ho, int wo, int* tile_w, int* tile_h) {
+// Pixel tile of the K dimension: tile_w * tile_h <= 64 pixels, rounded up to a multiple of the MMA K step with
+// zero rows.  `share`: vertical taps share one box, which needs tile_w % 8 == 0 (tap v starts v*tile_w rows down).
+// Picks the tile wasting the fewest MMA rows; ties go to the larger tile.
+static bool choose_k_tile(int ho, int wo, bool share, int h_limit, int* tile_w, int* tile_h) {
   double best = -1.0;
-  int bw = 16, bh = 1, bkp = 0;
-  for (int tw = 1; tw <= (wo < 64 ? wo : 64); ++tw)
-    for (int th = 1; th <= ho && tw * th <= 64; ++th) {
-      const int kp = tw * th;
-      if (kp % 16) continue;
-      const double eff = (double)ho * wo / ((double)ceil_div(ho, th) * ceil_div(wo, tw) * kp);
+  int bw = 0, bh = 0, bkp = 0;
+  const int max_w = wo < 64 ? wo : 64;
+  for (int tw = share ? 8 : 1; tw <= max_w; tw += share ? 8 : 1)
+    for (int th = 1; th <= ho && th <= h_limit && tw * th <= 64; ++th) {
+      const int kp = tw * th, kp_pad = (kp + 15) / 16 * 16;
+      const double eff = (double)ho * wo / ((double)ceil_div(ho, th) * ceil_div(wo, tw) * kp_pad);
       if (eff > best + 1e-9 || (eff > best - 1e-9 && kp > bkp)) { best = eff; bw = tw; bh = th; bkp = kp; }
     }
-  if (best < 0) { bw = 16; bh = 1; }  // tiny maps: 16x1 with OOB fill
+  if (best < 0) return false;
   *tile_w = bw;
   *tile_h = bh;
+  return true;
 }
 
 }  // namespace uavdet
@@ -225,52 +309,132 @@ extern "C" int uavdet_conv_wgrad(const uavdet_act* x, const uavdet_act* dy, int 
   P.cout = cout;
   P.a_width = (cout % 64 == 0) ? 64 : 32;
   P.b_width = (c_blk % 64 == 0) ? 64 : 32;
-  // N per tap: largest multiple-of-32 divisor of the per-tap channel count that is <= 256
-  int nb = 32;
-  for (int cand = 256; cand >= 32; cand -= 32)
-    if (c_blk % cand == 0 && cand % P.b_width == 0) { nb = cand; break; }
-  P.cin_blk = nb;
-  P.ci_blocks = c_blk / nb;
+
+  // ---- filter taps, grouped into columns (same channel block / horizontal offset / row parity) ----
+  struct Tap { int c_off, dw, p, dh, koff; };
+  Tap taps[kMaxTaps];
   int nt = 0;
   for (int kh = 0; kh < k; ++kh)
     for (int kw = 0; kw < k; ++kw) {
       if (s2d) {
         for (int i = 0; i < 2; ++i)
-          for (int j = 0; j < 2; ++j)
-            P.taps[nt++] = ConvTap{j * x->ld, kw - pad, i, kh - pad, ((kh * k + kw) * 4 + (i * 2 + j)) * c_blk};
+          for (int j = 0; j < 2; ++j) {
+            UAVDET_CHECK_ARG(nt < kMaxTaps, "conv_wgrad: too many taps");
+            taps[nt++] = Tap{j * x->ld, kw - pad, i, kh - pad, ((kh * k + kw) * 4 + (i * 2 + j)) * c_blk};
+          }
       } else if (stride == 1) {
-        P.taps[nt++] = ConvTap{0, kw - pad, 0, kh - pad, (kh * k + kw) * cin};
+        UAVDET_CHECK_ARG(nt < kMaxTaps, "conv_wgrad: too many taps");
+        taps[nt++] = Tap{0, kw - pad, 0, kh - pad, (kh * k + kw) * cin};
       } else {
         const int th = kh - pad, tw = kw - pad;
         const int ph = ((th % 2) + 2) % 2, pw = ((tw % 2) + 2) % 2;
-        P.taps[nt++] = ConvTap{pw * x->ld, (tw - pw) / 2, ph, (th - ph) / 2, (kh * k + kw) * cin};
+        UAVDET_CHECK_ARG(nt < kMaxTaps, "conv_wgrad: too many taps");
+        taps[nt++] = Tap{pw * x->ld, (tw - pw) / 2, ph, (th - ph) / 2, (kh * k + kw) * cin};
       }
-      UAVDET_CHECK_ARG(nt <= kMaxTaps, "conv_wgrad: too many taps");
     }
-  P.num_taps = nt;
-  choose_k_tile(P.ho, P.wo, &P.tile_w, &P.tile_h);
+  // sharing needs the taller box (tile_h + nv - 1 rows) to fit the (parity) view of the input
+  const int nv_max = stride == 2 ? (k + 1) / 2 : k;
+  const int view_h = parity ? x->h / 2 : x->h;
+  static const bool no_share = getenv("UAVDET_WGRAD_NOSHARE") != nullptr;   // tuning/debug switch
+  const bool share = !no_share && k > 1 && P.wo >= 8 && view_h - (nv_max - 1) >= 1;
+  if (!choose_k_tile(P.ho, P.wo, share, share ? view_h - (nv_max - 1) : P.ho, &P.tile_w, &P.tile_h)) {
+    UAVDET_CHECK_ARG(false, "conv_wgrad: no pixel tile for a %dx%d map", P.ho, P.wo);
+  }
   P.kp = P.tile_w * P.tile_h;
-  P.tiles_w = ceil_div(P.wo, P.tile_w);
-  P.tiles_h = ceil_div(P.ho, P.tile_h);
-  P.total_pixel_tiles = P.n_img * P.tiles_h * P.tiles_w;
-  // taps per CTA: bounded by 512 TMEM columns and by shared memory (>= 3 stages)
+  P.kp_pad = (P.kp + 15) / 16 * 16;
+  const int pad_rows = P.kp_pad - P.kp;
+  int ncols = 0, ntaps_flat = 0;
+  bool used[kMaxTaps] = {false};
+  for (int t = 0; t < nt; ++t) {
+    if (used[t]) continue;
+    // gather the taps of this column in increasing dh; only runs of consecutive dh can share a box
+    int members[8], nm = 0;
+    for (int u = t; u < nt; ++u)
+      if (!used[u] && taps[u].c_off == taps[t].c_off && taps[u].dw == taps[t].dw && taps[u].p == taps[t].p) members[nm++] = u;
+    for (int a = 0; a < nm; ++a)
+      for (int b = a + 1; b < nm; ++b)
+        if (taps[members[b]].dh < taps[members[a]].dh) { int tmp = members[a]; members[a] = members[b]; members[b] = tmp; }
+    int a = 0;
+    while (a < nm) {
+      int b = a + 1;
+      if (share)
+        while (b < nm && taps[members[b]].dh == taps[members[b - 1]].dh + 1) ++b;
+      UAVDET_CHECK_ARG(ncols < kMaxCols, "conv_wgrad: too many tap columns");
+      WgCol& col = P.cols[ncols++];
+      col.c_off = taps[members[a]].c_off; col.dw = taps[members[a]].dw; col.p = taps[members[a]].p;
+      col.dh0 = taps[members[a]].dh; col.nv = b - a; col.tap0 = ntaps_flat;
+      for (int m = a; m < b; ++m) { P.koff[ntaps_flat++] = taps[members[m]].koff; used[members[m]] = true; }
+      a = b;
+    }
+  }
+  P.num_cols = ncols;
+  // distinct box heights -> X tensor maps
+  int map_nv[3] = {0, 0, 0}, nmaps = 0;
+  for (int c = 0; c < ncols; ++c) {
+    int m = -1;
+    for (int i = 0; i < nmaps; ++i) if (map_nv[i] == P.cols[c].nv) m = i;
+    if (m < 0) {
+      UAVDET_CHECK_ARG(nmaps < 3, "conv_wgrad: more than 3 distinct column heights");
+      m = nmaps; map_nv[nmaps++] = P.cols[c].nv;
+    }
+    P.cols[c].map = m;
+  }
+
+  // ---- N per tap, columns per CTA (TMEM: taps x cin_blk <= 512 columns; smem: >= 3 pipeline stages) ----
   const int max_smem = 227 * 1024;
   const int ctrl_bytes = 8 * (2 * kMaxStages + 1) + 16 + 4 * 32 * 33 * 4;   // barriers + per-warp transpose scratch
-  const int a_bytes = 128 * P.kp * 2;
-  int group = 512 / P.cin_blk;
-  if (group > nt) group = nt;
-  while (group > 1 && (max_smem - 1024 - ctrl_bytes) / (a_bytes + group * P.cin_blk * P.kp * 2) < 3) --group;
-  // balance groups (e.g. 9 taps, cap 8 -> 5+4 rather than 8+1)
-  P.tap_groups = ceil_div(nt, group);
-  group = ceil_div(nt, P.tap_groups);
-  P.group = group;
-  const int stage_bytes = a_bytes + group * P.cin_blk * P.kp * 2;
-  int stages = (max_smem - 1024 - ctrl_bytes) / stage_bytes;
+  P.a_bytes = 128 * P.kp_pad * 2;
+  int max_nv = 0;
+  for (int c = 0; c < ncols; ++c) max_nv = P.cols[c].nv > max_nv ? P.cols[c].nv : max_nv;
+  int nb = 32;
+  for (int cand = 256; cand >= 32; cand -= 32)
+    if (c_blk % cand == 0 && cand % P.b_width == 0 && cand * max_nv <= 512) { nb = cand; break; }
+  UAVDET_CHECK_ARG(nb * max_nv <= 512, "conv_wgrad: a tap column does not fit TMEM");
+  P.cin_blk = nb;
+  P.ci_blocks = c_blk / nb;
+  auto col_bytes = [&](int c) { return (long long)nb * 2 * ((P.tile_h + P.cols[c].nv - 1) * P.tile_w + pad_rows); };
+  int cpg = 1;
+  for (int cand = ncols; cand >= 1; --cand) {
+    if (ncols % cand) continue;
+    bool ok = true;
+    for (int g0 = 0; g0 < ncols && ok; g0 += cand) {
+      int tp = 0; long long bytes = P.a_bytes;
+      for (int c = g0; c < g0 + cand; ++c) { tp += P.cols[c].nv; bytes += col_bytes(c); }
+      if (tp * nb > 512 || tp > kMaxSlots || (max_smem - ctrl_bytes) / bytes < 3) ok = false;
+    }
+    if (ok) { cpg = cand; break; }
+  }
+  P.cols_per_group = cpg;
+  P.num_groups = ncols / cpg;
+  long long stage_bytes = 0;
+  for (int g = 0; g < P.num_groups; ++g) {
+    long long off = P.a_bytes; int xb = 0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      const int rows = (P.tile_h + P.cols[c].nv - 1) * P.tile_w;
+      P.cols[c].off = (int)off;
+      P.cols[c].blk = (rows + pad_rows) * P.b_width * 2;
+      for (int v = 0; v < P.cols[c].nv; ++v) {
+        P.tap_off[P.cols[c].tap0 + v] = (int)off + v * P.tile_w * P.b_width * 2;
+        P.tap_lbo[P.cols[c].tap0 + v] = P.cols[c].blk;
+      }
+      off += (long long)(nb / P.b_width) * P.cols[c].blk;
+      xb += (nb / P.b_width) * rows * P.b_width * 2;
+    }
+    P.grp_x_bytes[g] = xb;
+    if (off > stage_bytes) stage_bytes = off;
+  }
+  stage_bytes = (stage_bytes + 1023) / 1024 * 1024;
+  P.stage_bytes = (int)stage_bytes;
+  int stages = (int)((max_smem - ctrl_bytes) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   UAVDET_CHECK_ARG(stages >= 2, "conv_wgrad: stage does not fit shared memory");
   P.stages = stages;
+
+  P.tiles_w = ceil_div(P.wo, P.tile_w);
+  P.tiles_h = ceil_div(P.ho, P.tile_h);
+  P.total_pixel_tiles = P.n_img * P.tiles_h * P.tiles_w;
   P.co_blocks = ceil_div(cout, 128);
-  P.items = P.co_blocks * P.ci_blocks * P.tap_groups;
+  P.items = P.co_blocks * P.ci_blocks * P.num_groups;
   P.per_sample = per_sample ? 1 : 0;
   const int tiles_avail = per_sample ? P.tiles_h * P.tiles_w : P.total_pixel_tiles;
   const int samples = per_sample ? P.n_img : 1;
@@ -279,7 +443,7 @@ extern "C" int uavdet_conv_wgrad(const uavdet_act* x, const uavdet_act* dy, int 
   {
     long long best = -1;
     const int ctas_per_split = P.items * samples;
-    for (int s_ = 1; s_ <= 64 && s_ <= tiles_avail; ++s_) {
+    for (int s_ = 1; s_ <= 148 && s_ <= tiles_avail; ++s_) {
       const long long waves = ceil_div(ctas_per_split * s_, kNumSMs);
       const long long cost = waves * (ceil_div(tiles_avail, s_) + 6);   // +6: per-CTA prologue/epilogue in tile units
       if (best < 0 || cost < best) { best = cost; splits = s_; }
@@ -292,18 +456,21 @@ extern "C" int uavdet_conv_wgrad(const uavdet_act* x, const uavdet_act* dy, int 
   P.dw = dw_packed;
   P.watchdog = watchdog_word();
 
-  CUtensorMap mapDY, mapX;
+  CUtensorMap mapDY, mapX[3];
   int rc = make_act_map(&mapDY, dy, 0, P.a_width, P.tile_w, P.tile_h);
   if (rc) return rc;
-  rc = make_act_map(&mapX, x, parity, P.b_width, P.tile_w, P.tile_h);
-  if (rc) return rc;
+  for (int m = 0; m < 3; ++m) {
+    const int nv = m < nmaps ? map_nv[m] : map_nv[0];
+    rc = make_act_map(&mapX[m], x, parity, P.b_width, P.tile_w, P.tile_h + nv - 1);
+    if (rc) return rc;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     UAVDET_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     attr_set = true;
   }
   dim3 grid((unsigned)(P.items * P.k_splits), (unsigned)samples);
-  wgrad_kernel<<<grid, kWgradThreads, max_smem, (cudaStream_t)stream>>>(mapDY, mapX, P);
+  wgrad_kernel<<<grid, kWgradThreads, max_smem, (cudaStream_t)stream>>>(mapDY, mapX[0], mapX[1], mapX[2], P);
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }

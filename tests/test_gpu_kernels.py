@@ -374,7 +374,10 @@ def test_conv_dgrad(lib, case):
 
 WGRAD_CASES = [(2, 64, 64, 1, 1, 16, 16), (2, 64, 128, 3, 1, 16, 16), (2, 32, 64, 3, 2, 32, 32),
                (1, 128, 256, 3, 2, 20, 20), (2, 256, 128, 1, 1, 20, 20), (1, 64, 32, 1, 1, 32, 32),
-               (4, 512, 1024, 3, 1, 20, 20), (2, 64, 128, 1, 2, 16, 16)]
+               (4, 512, 1024, 3, 1, 20, 20), (2, 64, 128, 1, 2, 16, 16),
+               (3, 32, 64, 3, 1, 40, 40), (2, 64, 64, 3, 1, 8, 8), (2, 32, 32, 3, 1, 4, 4), (2, 128, 128, 3, 1, 24, 24),
+               (2, 256, 512, 3, 1, 40, 40), (2, 32, 64, 3, 2, 80, 80), (2, 64, 96, 5, 1, 16, 16), (2, 32, 64, 5, 2, 32, 32),
+               (3, 96, 160, 3, 1, 12, 20), (2, 512, 256, 1, 1, 20, 20), (5, 64, 32, 1, 1, 40, 40)]
 
 
 @pytest.mark.parametrize("case", WGRAD_CASES, ids=lambda c: "x".join(map(str, c)))
