@@ -167,25 +167,28 @@ def run_reference(args, rank, world):
 # our arm
 # ------------------------------------------------------------------------------------------------
 class ConvTimer:
-    """Live per-launch timing of the implicit-GEMM kernel (CUDA events on the launching stream):
-    wraps ops.conv_fwd / ops.conv_dgrad for ONE instrumented step after the timed region."""
+    """Per-launch duration of the convolution kernels INSIDE the replayed step: while the step is captured into
+    a (second, instrumented) CUDA graph, every ops.conv_fwd / conv_dgrad / conv_wgrad call is bracketed by a
+    one-thread kernel that writes the device global timer in stream order; one replay fills the stamps.  The
+    bracket adds one launch gap (~1-2 us) to each measured duration, i.e. the figures are slightly pessimistic."""
 
-    def __init__(self, ops, torch):
+    def __init__(self, ops, torch, device, max_records=1024):
         self.ops, self.torch = ops, torch
-        self.records = []   # (kind, flops, start_event, end_event)
+        self.records = []   # (kind, flops, slot)
+        self.stamps = torch.zeros(2 * max_records, dtype=torch.int64, device=device)
 
     def __enter__(self):
-        ops, torch = self.ops, self.torch
+        ops = self.ops
         self._orig = (ops.conv_fwd, ops.conv_dgrad, ops.conv_wgrad)
-        rec = self.records
+        rec, stamps = self.records, self.stamps
 
         def timed(fn, kind, flops_of):
             def wrapper(*a, **k):
-                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s.record()
+                slot = 2 * len(rec)
+                ops.timestamp(stamps, slot)
                 out = fn(*a, **k)
-                e.record()
-                rec.append((kind, flops_of(a, k), s, e))
+                ops.timestamp(stamps, slot + 1)
+                rec.append((kind, flops_of(a, k), slot))
                 return out
             return wrapper
 
@@ -218,14 +221,15 @@ class ConvTimer:
 
     def summary(self):
         self.torch.cuda.synchronize()
+        t = self.stamps.cpu().tolist()
         agg = {}
-        if os.environ.get("UAVDET_BENCH_DEBUG"):
-            for i, (kind, fl, s, e) in enumerate(self.records):
-                print(f"[convtimer] {i} {kind} {s.elapsed_time(e) * 1e3:.0f} us {fl / 1e9:.1f} GFLOP", file=sys.stderr)
-        for kind, fl, s, e in self.records:
+        for i, (kind, fl, slot) in enumerate(self.records):
+            sec = (t[slot + 1] - t[slot]) * 1e-9
+            if os.environ.get("UAVDET_BENCH_DEBUG"):
+                print(f"[convtimer] {i} {kind} {sec * 1e6:.0f} us {fl / 1e9:.1f} GFLOP", file=sys.stderr)
             a = agg.setdefault(kind, [0.0, 0.0, 0])
             a[0] += fl
-            a[1] += s.elapsed_time(e) * 1e-3
+            a[1] += sec
             a[2] += 1
         return {k: {"flops": v[0], "seconds": v[1], "launches": v[2]} for k, v in agg.items()}
 
@@ -343,12 +347,17 @@ def run_ours(args, rank, world, local_rank):
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
 
-    # ---- roofline of the dominant kernel: one instrumented eager step.  A device-side sleep is queued first
-    # so the host runs ahead and the kernels execute back to back (as they do inside the graph); each conv
-    # launch is bracketed by CUDA events on its stream. ----
-    with ConvTimer(ops, torch) as ct:
-        torch.cuda._sleep(int(1.5e8))
-        step(x_dev, tg_dev)
+    # ---- roofline of the dominant kernel: the same step captured once more with device-timer stamps around every
+    # convolution launch, replayed (warm) and read back ----
+    with ConvTimer(ops, torch, dev) as ct:
+        if args.eager:
+            torch.cuda.synchronize()
+            step(x_dev, tg_dev)
+        else:
+            instrumented = GraphedTrainStep(model, trainer, x_dev, tg_dev, warmup=0)
+            instrumented()
+            ct.stamps.zero_()
+            instrumented()
     ksum = ct.summary()
     ops.check_device()
 

@@ -50,6 +50,11 @@ uint64_t uavdet_launch_count(void);
  * Synchronises `stream`. */
 int uavdet_check_device(void* stream, int* flag_host);
 
+/* Measurement aid: a one-thread kernel writes the device's %globaltimer (ns) to *slot_dev in stream order.
+ * Captured into a CUDA graph around a kernel it gives that kernel's duration inside the replayed step
+ * (bench.py `roofline`).  Not counted by uavdet_launch_count. */
+int uavdet_timestamp(unsigned long long* slot_dev, void* stream);
+
 /* NHWC bf16 activation view. */
 typedef struct {
   void* ptr;   /* bf16 */

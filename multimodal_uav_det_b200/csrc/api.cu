@@ -24,7 +24,21 @@ unsigned int* watchdog_word() {
   return p;
 }
 
+__global__ void stamp_kernel(unsigned long long* slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  *slot = t;
+}
+
 }  // namespace uavdet
+
+extern "C" int uavdet_timestamp(unsigned long long* slot_dev, void* stream) {
+  UAVDET_CHECK_ARG(slot_dev, "timestamp: null slot");
+  uavdet::stamp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(slot_dev);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { uavdet::set_error("timestamp launch failed: %s", cudaGetErrorString(e)); return UAVDET_ERR_CUDA; }
+  return UAVDET_OK;   // not counted in uavdet_launch_count: a measurement aid, not part of the path
+}
 
 extern "C" const char* uavdet_last_error(void) { return uavdet::g_err; }
 extern "C" int uavdet_version(void) { return 100; }

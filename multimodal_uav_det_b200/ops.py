@@ -67,6 +67,11 @@ def check_device() -> None:
     check(_lib.load().uavdet_check_device(_stream(), C.byref(flag)), "device watchdog")
 
 
+def timestamp(slots: torch.Tensor, index: int) -> None:
+    """Write the device global timer (ns) into slots[index] (int64 tensor) in stream order."""
+    check(_lib.load().uavdet_timestamp(C.c_void_p(slots.data_ptr() + 8 * index), _stream()), "timestamp")
+
+
 # --------------------------------------------------------------------------------------------
 # NMS / decode
 # --------------------------------------------------------------------------------------------
