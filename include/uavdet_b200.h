@@ -150,9 +150,23 @@ int uavdet_conv_dgrad_s2d(const uavdet_act* dy, const void* w_packed_t, int w_ba
 int uavdet_conv_wgrad(const uavdet_act* x, const uavdet_act* dy, int k, int stride, int pad,
                       int s2d, float* dw_packed, int per_sample, void* stream);
 
-/* OIHW fp32 -> packed bf16.  transposed=0: [O][kh][kw][I]; transposed=1: [I][kh][kw][O].   */
-int uavdet_pack_weight(const float* w_oihw, int O, int I, int k, int transposed, void* out_bf16,
+/* fp32 conv weight -> packed bf16.  flags bit 0: 0 -> [O][kh][kw][I], 1 (transposed) -> [I][kh][kw][O];
+ * flags bit 1: the fp32 source is stored channels-last ([O][kh][kw][I], torch.channels_last — how the flat
+ * trainer keeps conv weights so that the weight gradient needs no re-layout) instead of OIHW.             */
+int uavdet_pack_weight(const float* w_oihw, int O, int I, int k, int flags, void* out_bf16,
                        void* stream);
+/* The same for a whole model in one launch (weights change every optimiser step: 2 packs per conv).
+ * jobs_dev: device array of n_jobs descriptors.                                                           */
+typedef struct {
+  const float* src; /* fp32 weight                    */
+  void* dst;        /* bf16 packed output             */
+  int O, I, k;
+  int flags;        /* as uavdet_pack_weight          */
+  long long chunk0; /* index of this job's first 4096-element chunk: prefix sum of ceil(O*I*k*k / 4096) */
+} uavdet_pack_job;
+#define UAVDET_PACK_CHUNK 4096
+int uavdet_pack_weights_batched(const uavdet_pack_job* jobs_dev, int n_jobs, long long total_chunks,
+                                void* stream);
 /* packed fp32 grad [O][kh][kw][I] -> OIHW fp32 (accumulate != 0: +=).                      */
 int uavdet_unpack_wgrad(const float* dw_packed, int O, int I, int k, float* grad_oihw,
                         int accumulate, void* stream);

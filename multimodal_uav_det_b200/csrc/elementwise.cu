@@ -417,16 +417,46 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int n, int hw, 
 }
 
 // ---- weights ---------------------------------------------------------------------------------------
-// out[o][tap][i] (transposed: out[i][tap][o]) = w[o][i][tap]
-__global__ void pack_weight_kernel(const float* __restrict__ w, int O, int I, int kk, int transposed,
-                                   __nv_bfloat16* __restrict__ out) {
+// out[o][tap][i] (transposed: out[i][tap][o]) = w[o][i][tap]   (src_nhwc: the source is stored [o][tap][i])
+__device__ __forceinline__ void pack_weight_elems(const float* __restrict__ w, int O, int I, int kk, int transposed,
+                                                  int src_nhwc, __nv_bfloat16* __restrict__ out, long long first,
+                                                  long long stride) {
   const long long total = (long long)O * I * kk;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
+  for (long long idx = first; idx < total; idx += stride) {
     int o, i, t;
     if (!transposed) { i = (int)(idx % I); long long r = idx / I; t = (int)(r % kk); o = (int)(r / kk); }
     else { o = (int)(idx % O); long long r = idx / O; t = (int)(r % kk); i = (int)(r / kk); }
-    out[idx] = __float2bfloat16(__ldg(w + ((long long)o * I + i) * kk + t));
+    const long long src = src_nhwc ? ((long long)o * kk + t) * I + i : ((long long)o * I + i) * kk + t;
+    out[idx] = __float2bfloat16(__ldg(w + src));
+  }
+}
+__global__ void pack_weight_kernel(const float* __restrict__ w, int O, int I, int kk, int transposed, int src_nhwc,
+                                   __nv_bfloat16* __restrict__ out) {
+  pack_weight_elems(w, O, I, kk, transposed, src_nhwc, out, blockIdx.x * (long long)blockDim.x + threadIdx.x,
+                    (long long)gridDim.x * blockDim.x);
+}
+// every conv weight of a model (both orientations) in ONE launch: a block = one 4096-element chunk of one job
+constexpr int kPackChunk = 4096;
+__global__ void __launch_bounds__(256)
+pack_weights_batched_kernel(const uavdet_pack_job* __restrict__ jobs, int n_jobs) {
+  int lo = 0, hi = n_jobs - 1;                       // last job whose first chunk is <= blockIdx.x
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].chunk0 <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const uavdet_pack_job j = jobs[lo];
+  const int kk = j.k * j.k, transposed = j.flags & 1, src_nhwc = (j.flags >> 1) & 1;
+  const long long total = (long long)j.O * j.I * kk;
+  const long long base = ((long long)blockIdx.x - j.chunk0) * kPackChunk;
+  __nv_bfloat16* out = (__nv_bfloat16*)j.dst;
+  for (int e = threadIdx.x; e < kPackChunk; e += 256) {
+    const long long idx = base + e;
+    if (idx >= total) break;
+    int o, i, t;
+    if (!transposed) { i = (int)(idx % j.I); long long r = idx / j.I; t = (int)(r % kk); o = (int)(r / kk); }
+    else { o = (int)(idx % j.O); long long r = idx / j.O; t = (int)(r % kk); i = (int)(r / kk); }
+    const long long src = src_nhwc ? ((long long)o * kk + t) * j.I + i : ((long long)o * j.I + i) * kk + t;
+    out[idx] = __float2bfloat16(__ldg(j.src + src));
   }
 }
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int O, int I, int kk, float* __restrict__ g,
@@ -821,11 +851,20 @@ extern "C" int uavdet_nchw_f32_to_nhwc(const float* x_nchw, const uavdet_act* y,
   return UAVDET_OK;
 }
 
-extern "C" int uavdet_pack_weight(const float* w_oihw, int O, int I, int k, int transposed, void* out_bf16,
+extern "C" int uavdet_pack_weight(const float* w_oihw, int O, int I, int k, int flags, void* out_bf16,
                                   void* stream) {
   UAVDET_CHECK_ARG(w_oihw && out_bf16 && O > 0 && I > 0 && k > 0, "pack_weight: bad arguments");
-  long long total = (long long)O * I * k * k;
-  pack_weight_kernel<<<ew_grid(total, 256), 256, 0, ST>>>(w_oihw, O, I, k * k, transposed, (__nv_bfloat16*)out_bf16);
+  pack_weight_kernel<<<ew_grid((long long)O * I * k * k, 256), 256, 0, ST>>>(w_oihw, O, I, k * k, flags & 1,
+                                                                          (flags >> 1) & 1, (__nv_bfloat16*)out_bf16);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+extern "C" int uavdet_pack_weights_batched(const uavdet_pack_job* jobs_dev, int n_jobs, long long total_chunks,
+                                           void* stream) {
+  UAVDET_CHECK_ARG(jobs_dev && n_jobs >= 0 && total_chunks >= 0 && total_chunks < (1ll << 31),
+                   "pack_weights_batched: bad arguments");
+  if (n_jobs == 0 || total_chunks == 0) return UAVDET_OK;
+  pack_weights_batched_kernel<<<(unsigned)total_chunks, 256, 0, ST>>>(jobs_dev, n_jobs);
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }

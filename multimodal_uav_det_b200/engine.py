@@ -40,14 +40,20 @@ def param_epoch() -> int:
 
 class PackCache:
     """bf16 kernel-layout copies of conv weights, invalidated by the parameter's version counter
-    (torch-side updates) or the global parameter epoch (raw-pointer updates)."""
+    (torch-side updates) or the global parameter epoch (raw-pointer updates).  `prepack` refreshes a whole
+    model's weights (both orientations) with ONE kernel launch — they all change at every optimiser step."""
 
     def __init__(self):
-        self._store: Dict[Tuple[int, bool], Tuple[int, torch.Tensor]] = {}
+        self._store: Dict[Tuple[int, bool], Tuple[tuple, torch.Tensor]] = {}
+        self._table = None        # (key, device table, n_jobs, total_chunks, [(weight, transposed)])
+
+    @staticmethod
+    def _ver(w: torch.Tensor) -> tuple:
+        return (w._version, _PARAM_EPOCH, w.data_ptr())
 
     def get(self, w: torch.Tensor, transposed: bool = False, rows: Optional[int] = None) -> torch.Tensor:
         key = (id(w), transposed)
-        ver = (w._version, _PARAM_EPOCH, w.data_ptr())
+        ver = self._ver(w)
         hit = self._store.get(key)
         if hit is not None and hit[0] == ver and hit[1].device == w.device:
             return hit[1]
@@ -55,8 +61,42 @@ class PackCache:
         self._store[key] = (ver, packed)
         return packed
 
+    def prepack(self, weights, with_transposed: bool) -> None:
+        """Make the packed copies of `weights` (4-D conv weights with cin % 32 == 0) current."""
+        if not weights:
+            return
+        orient = (False, True) if with_transposed else (False,)
+        stale = False
+        for w in weights:
+            ver = self._ver(w)
+            for t in orient:
+                hit = self._store.get((id(w), t))
+                if hit is None or hit[0] != ver or hit[1].device != w.device:
+                    stale = True
+                    break
+            if stale:
+                break
+        if not stale:
+            return
+        key = (tuple(w.data_ptr() for w in weights), with_transposed, weights[0].device)
+        if self._table is None or self._table[0] != key:
+            jobs, outs = [], []
+            for w in weights:
+                o, i, k, _ = w.shape
+                for t in orient:
+                    out = torch.empty((i if t else o, k * k * (o if t else i)), dtype=torch.bfloat16, device=w.device)
+                    jobs.append((w.detach(), out, t))
+                    outs.append((w, t, out))
+            table, n_jobs, chunks = ops.build_pack_table(jobs)
+            self._table = (key, table, n_jobs, chunks, outs)
+        _, table, n_jobs, chunks, outs = self._table
+        ops.pack_weights_batched(table, n_jobs, chunks)
+        for w, t, out in outs:
+            self._store[(id(w), t)] = (self._ver(w), out)
+
     def clear(self):
         self._store.clear()
+        self._table = None
 
 
 def grad_buffer(p: torch.Tensor) -> Tuple[torch.Tensor, bool]:
@@ -158,9 +198,36 @@ class Executor:
 
     def __init__(self):
         self.packs = PackCache()
+        self._zero_arena: Optional[torch.Tensor] = None
+        self._zero_cursor = 0
+        self._zero_need = 0
         self._bn_grads: List[Tuple[torch.Tensor, torch.Tensor]] = []
         self._bn_counters: List[torch.Tensor] = []
         self.grad_ready_hook: Optional[Callable[[torch.Tensor], None]] = None
+
+    # ---- per-step zeroed fp32 scratch ---------------------------------------------------------------
+    def begin_step(self, device) -> None:
+        """Zero the scratch arena the step's small accumulators (BN sums, BN-backward sums) are carved from:
+        one fill launch instead of one per layer.  Sized from the previous step's demand."""
+        need = max(self._zero_need, 1 << 16)
+        if self._zero_arena is None or self._zero_arena.device != device or self._zero_arena.numel() < need:
+            self._zero_arena = torch.zeros(need + need // 4, dtype=torch.float32, device=device)
+        else:
+            self._zero_arena.zero_()
+        self._zero_cursor = 0
+        self._zero_need = 0
+
+    def zeros(self, rows: int, cols: int, device) -> torch.Tensor:
+        """(rows, cols) fp32 zeros: a 128-byte-aligned slice of the arena zeroed by begin_step, else a fresh fill."""
+        n = rows * cols
+        n_al = (n + 31) // 32 * 32
+        self._zero_need += n_al
+        a = self._zero_arena
+        if a is not None and a.device == device and self._zero_cursor + n_al <= a.numel():
+            out = a[self._zero_cursor:self._zero_cursor + n].view(rows, cols)
+            self._zero_cursor += n_al
+            return out
+        return torch.zeros((rows, cols), dtype=torch.float32, device=device)
 
     # ---- forward ---------------------------------------------------------------------------------
     def conv_forward(self, u: ConvUnit, x: torch.Tensor, train: bool, tape: Optional[list],
@@ -171,7 +238,7 @@ class Executor:
         dev = w.device
         if u.bn is not None and train:
             c = u.cout
-            sums = torch.zeros((2, c), dtype=torch.float32, device=dev)
+            sums = self.zeros(2, c, dev)
             if u.stem:
                 raw = ops.stem_fwd(x, w.detach(), u.k, u.stride, u.pad, epi=EPI_STATS, sum_=sums[0], sumsq=sums[1])
             else:
@@ -241,7 +308,7 @@ class Executor:
         train_bn = rec.mean is not None
         if train_bn:
             d_raw, dgamma, dbeta = ops.bn_act_bwd(dy, rec.raw, rec.scale, rec.shift, rec.mean, rec.invstd,
-                                                  u.bn.weight.detach(), u.act)
+                                                  u.bn.weight.detach(), u.act, buf=self.zeros(6, u.cout, dy.device))
             self._bn_grads.append((u.bn.weight, dgamma))
             self._bn_grads.append((u.bn.bias, dbeta))
         else:
@@ -261,8 +328,15 @@ class Executor:
                 g = ops.stem_wgrad(rec.x, d_raw, u.k, u.stride, u.pad)
                 gbuf.add_(g)
             else:
-                dwp = ops.conv_wgrad(rec.x, d_raw, u.k, u.stride, u.pad, s2d=u.s2d)
-                ops.unpack_wgrad(dwp, w.shape[0], w.shape[1], u.k, grad=gbuf, accumulate=True)
+                packed_view = gbuf.permute(0, 2, 3, 1)
+                if packed_view.is_contiguous():
+                    # the gradient buffer already has the kernel's [O][kh][kw][I] layout (1x1 convs; conv
+                    # weights the flat trainer keeps channels-last): accumulate straight into it
+                    ops.conv_wgrad(rec.x, d_raw, u.k, u.stride, u.pad, s2d=u.s2d,
+                                   out=packed_view.reshape(w.shape[0], -1))
+                else:
+                    dwp = ops.conv_wgrad(rec.x, d_raw, u.k, u.stride, u.pad, s2d=u.s2d)
+                    ops.unpack_wgrad(dwp, w.shape[0], w.shape[1], u.k, grad=gbuf, accumulate=True)
             if self.grad_ready_hook is not None:
                 self.grad_ready_hook(w)
         if not need_dx or u.stem:
@@ -292,7 +366,7 @@ class Executor:
         bn, k, s, p, co = sp.bn, sp.k, sp.stride, sp.pad, sp.cout
         in_hw = (x.shape[2], x.shape[3]) if sp.stem else (x.shape[1], x.shape[2])
         if train:
-            sums = torch.zeros((2, co), dtype=torch.float32, device=attn.device)
+            sums = self.zeros(2, co, attn.device)
             if sp.stem:
                 raw = ops.stem_fwd(x, w_b, k, s, p, epi=EPI_STATS, sum_=sums[0], sumsq=sums[1], per_sample_w=True)
             else:
@@ -348,7 +422,7 @@ class Executor:
         n = rec.attn.shape[0]
         if rec.mean is not None:
             d_raw, dgamma, dbeta = ops.bn_act_bwd(dy, rec.raw, rec.scale, rec.shift, rec.mean, rec.invstd,
-                                                  sp.bn.weight.detach(), sp.act)
+                                                  sp.bn.weight.detach(), sp.act, buf=self.zeros(6, sp.cout, dy.device))
             self._bn_grads.append((sp.bn.weight, dgamma))
             self._bn_grads.append((sp.bn.bias, dbeta))
         else:

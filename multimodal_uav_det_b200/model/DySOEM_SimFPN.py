@@ -192,8 +192,19 @@ class DySOEM_SimFPN(BaseModel):
             return [DetectionResults(bbox=flat[2 * i], obj=flat[2 * i + 1]) for i in range(len(flat) // 2)]
         return self._forward_program(x, None)
 
+    def _igemm_weights(self):
+        n = self.neck
+        return [n.x2_in_down.weight, n.center_down.weight, n.x0_out_up.weight, n.x1_out_up.weight,
+                n.x0_conv_out.conv[0].weight, n.x1_conv_out.conv[0].weight, n.x2_conv_out.conv[0].weight]
+
+    def prepare_for_capture(self):
+        self._exec.begin_step(self.neck.x2_in_down.weight.device)
+        self._exec.packs.prepack(self._igemm_weights(), with_transposed=True)
+
     def _forward_program(self, x, tape):
         ex, train, temp = self._exec, self.training, self._attn_temp
+        ex.begin_step(x.device)
+        ex.packs.prepack(self._igemm_weights(), with_transposed=tape is not None)
         h = ex.conv_forward(self.input_stem.conv.unit(stem=True), x, train, tape)
         feats = []
         for soem in self.backbone:

@@ -151,6 +151,7 @@ class DarknetDetector(BaseModel):
         self.training_graph = True       # record the tape when grad is enabled
         self._anchor = None
         self._debug_taps = None          # tests: dict receiving every intermediate activation
+        self._igemm_w = None
 
     # ---- public API ------------------------------------------------------------------------------
     def forward(self, x) -> List[DetectionResults]:
@@ -180,9 +181,24 @@ class DarknetDetector(BaseModel):
         return loss
 
     # ---- program ---------------------------------------------------------------------------------
+    def _igemm_weights(self):
+        """Conv weights the implicit-GEMM kernels read (everything but the cin=3 stem): re-packed to bf16 in one
+        launch per step."""
+        if self._igemm_w is None:
+            self._igemm_w = [m.conv.weight for m in self.modules()
+                             if isinstance(m, CNNBlock) and m.conv.in_channels % 32 == 0]
+        return self._igemm_w
+
+    def prepare_for_capture(self):
+        """Build the host-side tables a CUDA-graph capture must not create (they need host->device copies)."""
+        self._exec.begin_step(self._igemm_weights()[0].device)
+        self._exec.packs.prepack(self._igemm_weights(), with_transposed=True)
+
     def _forward_program(self, x, tape: Optional[list]) -> List[DetectionResults]:
         ex = self._exec
         train = self.training
+        ex.begin_step(x.device)
+        ex.packs.prepack(self._igemm_weights(), with_transposed=tape is not None)
         feats = []
         routes = []            # (tensor, index of the tape entry that produced it)
         h = x                   # NCHW fp32 until the first (stem) conv

@@ -146,20 +146,56 @@ def cxcywh_to_xyxy(t: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------
 # weights
 # --------------------------------------------------------------------------------------------
+def _weight_layout(w: torch.Tensor) -> int:
+    """0: OIHW-contiguous fp32, 2: channels-last ([O][kh][kw][I]) fp32 — the `flags` bit 1 of uavdet_pack_weight."""
+    if w.dtype != torch.float32 or w.dim() != 4:
+        raise UavdetError("expected a 4-D float32 conv weight")
+    if w.is_contiguous():
+        return 0
+    if w.permute(0, 2, 3, 1).is_contiguous():
+        return 2
+    raise UavdetError("conv weight must be OIHW-contiguous or channels-last")
+
+
 def pack_weight(w: torch.Tensor, transposed: bool = False, rows: Optional[int] = None) -> torch.Tensor:
-    """OIHW fp32 -> bf16 [O][kh*kw*I] (or [I][kh*kw*O]).  rows > O zero-pads (head convs)."""
+    """Conv weight fp32 (OIHW or channels-last storage) -> bf16 [O][kh*kw*I] (or [I][kh*kw*O]).
+    rows > O zero-pads (head convs)."""
     _require_cuda(w)
-    w = _f32(w)
     o, i, kh, kw = w.shape
     assert kh == kw
+    flags = (1 if transposed else 0) | _weight_layout(w)
     r = i if transposed else o
     kt = kh * kw * (o if transposed else i)
     rows = rows or r
     out = torch.zeros((rows, kt), dtype=torch.bfloat16, device=w.device) if rows != r else \
         torch.empty((rows, kt), dtype=torch.bfloat16, device=w.device)
-    check(_lib.load().uavdet_pack_weight(_ptr(w), o, i, kh, 1 if transposed else 0, _ptr(out), _stream()),
-          "pack_weight")
+    check(_lib.load().uavdet_pack_weight(_ptr(w), o, i, kh, flags, _ptr(out), _stream()), "pack_weight")
     return out
+
+
+class _PackJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("O", C.c_int), ("I", C.c_int), ("k", C.c_int),
+                ("flags", C.c_int), ("chunk0", C.c_longlong)]
+
+
+PACK_CHUNK = 4096
+
+
+def build_pack_table(jobs):
+    """jobs: [(weight fp32 (O,I,k,k), out bf16, transposed)] -> (device table, n_jobs, total_chunks) for
+    pack_weights_batched.  Holds raw pointers: rebuild when a tensor is re-allocated."""
+    arr = (_PackJob * len(jobs))()
+    chunk = 0
+    for j, (w, out, transposed) in enumerate(jobs):
+        o, i, k, _ = w.shape
+        arr[j] = _PackJob(w.data_ptr(), out.data_ptr(), o, i, k, (1 if transposed else 0) | _weight_layout(w), chunk)
+        chunk += (o * i * k * k + PACK_CHUNK - 1) // PACK_CHUNK
+    table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(jobs[0][0].device)
+    return table, len(jobs), chunk
+
+
+def pack_weights_batched(table, n_jobs: int, total_chunks: int) -> None:
+    check(_lib.load().uavdet_pack_weights_batched(_ptr(table), n_jobs, total_chunks, _stream()), "pack_weights_batched")
 
 
 def unpack_wgrad(dw_packed: torch.Tensor, o: int, i: int, k: int, grad: Optional[torch.Tensor] = None,
@@ -342,12 +378,13 @@ def bn_act_fwd(raw, scale, shift, act, res=None, out=None):
     return out
 
 
-def bn_act_bwd(dy, raw, scale, shift, mean, invstd, gamma, act):
+def bn_act_bwd(dy, raw, scale, shift, mean, invstd, gamma, act, buf=None):
     """Train-mode BN(+act) backward.  Returns (d_raw bf16, dgamma fp32, dbeta fp32).
     `gamma` is unused (scale = gamma*invstd already carries it); kept for call-site symmetry."""
     c = raw.shape[3]
     a = ACT[act] if not isinstance(act, int) else act
-    buf = torch.zeros((6, c), dtype=torch.float32, device=raw.device)   # sum_dz, sum_dzr, dgamma, dbeta, k1, k0
+    if buf is None:                                                      # (6, c) zeros: sum_dz, sum_dzr, dgamma, dbeta, k1, k0
+        buf = torch.zeros((6, c), dtype=torch.float32, device=raw.device)
     dv, rv = act_view(dy), act_view(raw)
     lib = _lib.load()
     check(lib.uavdet_bn_act_bwd_reduce(C.byref(dv), C.byref(rv), _ptr(scale), _ptr(shift), a, _ptr(buf[0]),

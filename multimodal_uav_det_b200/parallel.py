@@ -36,10 +36,24 @@ class _Bucket:
         self.pending = 0
         self.work = None
         for p, o in zip(params, self.offsets):
-            view = self.param[o:o + p.numel()].view(p.shape)
+            p.data, p.grad = self._views(p, o)
+
+    def _views(self, p, o):
+        """Parameter / gradient views into the arenas.  Conv weights of the implicit-GEMM layers are stored
+        channels-last ([O][kh][kw][I] — the layout the weight-gradient kernel accumulates in and the bf16
+        pack reads), exposed through a permuted (O,I,kh,kw) view: values, shapes and `state_dict` keys are
+        unchanged, only the strides differ (torch.channels_last)."""
+        n = p.numel()
+        flat_p, flat_g = self.param[o:o + n], self.grad[o:o + n]
+        if p.dim() == 4 and p.shape[2] * p.shape[3] > 1 and p.shape[1] % 32 == 0:
+            oc, ic, kh, kw = p.shape
+            view = flat_p.view(oc, kh, kw, ic).permute(0, 3, 1, 2)
+            gview = flat_g.view(oc, kh, kw, ic).permute(0, 3, 1, 2)
+        else:
+            view, gview = flat_p.view(p.shape), flat_g.view(p.shape)
+        if p.data.data_ptr() != view.data_ptr():
             view.copy_(p.data)
-            p.data = view
-            p.grad = self.grad[o:o + p.numel()].view(p.shape)
+        return view, gview
 
 
 class FlatSGDTrainer:
@@ -85,7 +99,7 @@ class FlatSGDTrainer:
             b.grad.zero_()
             for p, o in zip(b.params, b.offsets):      # re-attach if someone set grads to None
                 if p.grad is None or p.grad.data_ptr() != b.grad.data_ptr() + 4 * o:
-                    p.grad = b.grad[o:o + p.numel()].view(p.shape)
+                    p.grad = b._views(p, o)[1]
         self._arm()
 
     def _on_grad_ready(self, p):
@@ -157,6 +171,8 @@ class GraphedTrainStep:
         head = model.yolo_head
         for h in range(len(self.targets)):
             head._scaled_anchors(h, self.x.device)      # host->device constants must exist before capture
+        if hasattr(model, "prepare_for_capture"):
+            model.prepare_for_capture()
         prev_mut = head.mutate_targets
         head.mutate_targets = False            # targets are inputs of the graph, never rewritten in place
 
@@ -181,6 +197,34 @@ class GraphedTrainStep:
             self.loss, self.bbox_loss, self.obj_loss = body()
         head.mutate_targets = prev_mut
         bump_param_epoch()
+        self._stage = None
+
+    # ---- input pipeline: overlap the next batch's host->device copy with the current step ------------------
+    def prefetch(self, x: torch.Tensor, targets) -> None:
+        """Start copying the NEXT batch (pinned host or device tensors) into staging buffers on a side stream;
+        the following `run_prefetched()` consumes it.  The copy overlaps whatever the main stream is running."""
+        if self._stage is None:
+            self._stage = (torch.empty_like(self.x), [torch.empty_like(t) for t in self.targets])
+            self._copy_stream = torch.cuda.Stream(device=self.x.device)
+            self._staged = torch.cuda.Event()
+            self._consumed = torch.cuda.Event()
+            self._consumed.record()
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._consumed)     # the previous staged batch has been taken over
+            self._stage[0].copy_(x, non_blocking=True)
+            for dst, src in zip(self._stage[1], targets):
+                dst.copy_(src, non_blocking=True)
+            self._staged.record()
+
+    def run_prefetched(self) -> torch.Tensor:
+        """Replay the step on the batch staged by `prefetch` (device-to-device hand-over, then replay)."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._staged)
+        self.x.copy_(self._stage[0], non_blocking=True)
+        for dst, src in zip(self.targets, self._stage[1]):
+            dst.copy_(src, non_blocking=True)
+        self._consumed.record()
+        return self()
 
     def load(self, x: torch.Tensor, targets) -> None:
         """Stage a batch into the static buffers (asynchronous on the current stream)."""

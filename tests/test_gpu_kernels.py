@@ -678,3 +678,26 @@ def test_dyn_bwd_contract(lib, packed, K, O, I, k, n):
     ops.dyn_bwd_contract(src.reshape(n, -1).to(DEV), attn.to(DEV), bank.to(DEV), d_bank, d_attn, packed=packed)
     torch.testing.assert_close(d_bank.cpu(), want_bank, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(d_attn.cpu(), want_attn, rtol=1e-3, atol=1e-2)
+
+
+def test_pack_weight_layouts_and_batched(lib):
+    """bf16 weight pack from OIHW and channels-last fp32 storage, both orientations, single and batched launch."""
+    ops = _ops(lib)
+    g = torch.Generator().manual_seed(77)
+    shapes = [(64, 32, 3), (128, 64, 1), (96, 160, 3), (32, 64, 5), (1024, 512, 3)]
+    ws = [torch.randn(o, i, k, k, generator=g).to(DEV) for o, i, k in shapes]
+    ws_cl = [w.contiguous(memory_format=torch.channels_last) if w.shape[-1] > 1 else w for w in ws]
+    jobs = []
+    for w, wcl in zip(ws, ws_cl):
+        o, i, k, _ = w.shape
+        ref_n = w.permute(0, 2, 3, 1).reshape(o, -1).contiguous().to(torch.bfloat16)
+        ref_t = w.permute(1, 2, 3, 0).reshape(i, -1).contiguous().to(torch.bfloat16)
+        for src in (w, wcl):
+            assert torch.equal(ops.pack_weight(src), ref_n)
+            assert torch.equal(ops.pack_weight(src, transposed=True), ref_t)
+        jobs.append((wcl, torch.empty_like(ref_n), False, ref_n))
+        jobs.append((w, torch.empty_like(ref_t), True, ref_t))
+    table, n, chunks = ops.build_pack_table([(w, out, t) for w, out, t, _ in jobs])
+    ops.pack_weights_batched(table, n, chunks)
+    for _, out, _, ref in jobs:
+        assert torch.equal(out, ref)

@@ -516,3 +516,36 @@ def test_dysoem_graphed_train_step(lib):
     ops.check_device()
     print("dysoem graphed losses", losses)
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+def test_flat_trainer_channels_last_storage_gives_same_gradients(lib):
+    """FlatSGDTrainer keeps conv weights / gradients channels-last (wgrad accumulates in place, no unpack):
+    same gradients as the plain OIHW path, and state_dict values are unchanged."""
+    from multimodal_uav_det_b200.parallel import FlatSGDTrainer
+    from multimodal_uav_det_b200.utils.datatype import BatchData
+    size, b = 128, 4
+    grads = {}
+    for mode in ("plain", "flat"):
+        model, hp = make("BaselineModel", SHALLOW)
+        model.route_repeats = 2
+        randomize_bn(model)
+        model = model.to(DEV).eval()
+        sd_before = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        if mode == "flat":
+            trainer = FlatSGDTrainer(model, lr=1e-3, momentum=0.7)
+            trainer.zero_grad()
+            w = model.layers[1].conv.weight
+            assert not w.is_contiguous() and w.permute(0, 2, 3, 1).is_contiguous()
+            for k, v in model.state_dict().items():
+                assert torch.equal(v.detach().cpu(), sd_before[k]), k
+        x = synth_input(b, size).to(DEV)
+        per = _targets(hp, b, size, grids=[16, 32, 64])
+        tg = [torch.stack([per[i][h] for i in range(b)]).to(DEV) for h in range(3)]
+        outs = model(x)
+        loss, _, _, _ = model.yolo_head.compute_metrics(outs, BatchData(image=x, bbox=tg))
+        loss.backward()
+        grads[mode] = {k: p.grad.detach().float().cpu().clone() for k, p in model.named_parameters() if p.grad is not None}
+    assert grads["plain"].keys() == grads["flat"].keys()
+    worst = max(rel_l2(grads["flat"][k], grads["plain"][k]) for k in grads["plain"])
+    print("channels-last vs OIHW gradient rel_l2 (worst)", worst)
+    assert worst < 2e-3
