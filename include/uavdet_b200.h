@@ -178,6 +178,12 @@ int uavdet_unpack_wgrad(const float* dw_packed, int O, int I, int k, float* grad
 int uavdet_stem_fwd(const float* x_nchw, int n, int cin, int h, int w, const float* w_oihw,
                     int cout, int k, int stride, int pad, const uavdet_act* y,
                     const uavdet_epilogue* epi, void* stream);
+/* im2col of the cin<=3 input: (n,cin,h,w) fp32 NCHW -> (n,ho,wo,32) bf16 NHWC whose channel (ci*k+kh)*k+kw holds
+ * the tap (zero outside the image, channels >= cin*k*k are zero).  The stem conv then IS a 1x1 convolution over
+ * 32 channels with the weight matrix w.flatten(1) zero-padded to 32 columns: uavdet_conv_fwd / uavdet_conv_wgrad
+ * (tcgen05) serve BaselineModel.py:89-97's first layer, its DyConv variant and their weight gradients.        */
+int uavdet_im2col_stem(const float* x_nchw, int n, int cin, int h, int w, int k, int stride, int pad,
+                       const uavdet_act* y, void* stream);
 int uavdet_stem_wgrad(const float* x_nchw, int n, int cin, int h, int w, const uavdet_act* dy,
                       int k, int stride, int pad, float* grad_oihw, void* stream);
 

@@ -202,6 +202,44 @@ __global__ void __launch_bounds__(kSwThreads) stem_wgrad_kernel(const float* __r
   }
 }
 
+// im2col of the cin<=3 network input: y[n][oy][ox][(ci*k + kh)*k + kw] = x[n][ci][oy*s+kh-p][ox*s+kw-p] (zero outside
+// the image and for the pad channels K..31), bf16 NHWC with 32 channels = 64 B per pixel.  With it the stem
+// convolution, its per-sample dynamic variant and their weight gradients run on the same tcgen05 kernels as
+// every other layer (a 1x1 conv over 32 "channels") instead of CUDA-core direct kernels.
+template <int CIN, int KS>
+__global__ void __launch_bounds__(256)
+im2col_stem_kernel(const float* __restrict__ x, int h, int w, int stride, int pad, int ho, int wo,
+                   __nv_bfloat16* __restrict__ y, long long y_ld) {
+  const int img = blockIdx.y;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (long long)ho * wo) return;
+  const int oy = (int)(p / wo), ox = (int)(p - (long long)oy * wo);
+  const float* xin = x + (long long)img * CIN * h * w;
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+  for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+    for (int kh = 0; kh < KS; ++kh) {
+      const int iy = oy * stride + kh - pad;
+      const bool row_ok = iy >= 0 && iy < h;
+#pragma unroll
+      for (int kw = 0; kw < KS; ++kw) {
+        const int ix = ox * stride + kw - pad;
+        if (row_ok && ix >= 0 && ix < w) v[(ci * KS + kh) * KS + kw] = __ldg(xin + ((long long)ci * h + iy) * w + ix);
+      }
+    }
+  __nv_bfloat16* yp = y + ((long long)img * ho * wo + p) * y_ld;
+#pragma unroll
+  for (int c = 0; c < 32; c += 8) {
+    uint4 o;
+    o.x = pack_bf16x2(v[c], v[c + 1]); o.y = pack_bf16x2(v[c + 2], v[c + 3]);
+    o.z = pack_bf16x2(v[c + 4], v[c + 5]); o.w = pack_bf16x2(v[c + 6], v[c + 7]);
+    *reinterpret_cast<uint4*>(yp + c) = o;
+  }
+}
+
 }  // namespace uavdet
 
 using namespace uavdet;
@@ -268,6 +306,29 @@ extern "C" int uavdet_stem_wgrad(const float* x_nchw, int n, int cin, int h, int
     default: UAVDET_SW_LAUNCH(5); break;
   }
 #undef UAVDET_SW_LAUNCH
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_im2col_stem(const float* x_nchw, int n, int cin, int h, int w, int k, int stride, int pad,
+                                  const uavdet_act* y, void* stream) {
+  UAVDET_CHECK_ARG(x_nchw && y && y->ptr, "im2col_stem: null pointer");
+  UAVDET_CHECK_ARG(cin >= 1 && cin * k * k <= 32 && (stride == 1 || stride == 2), "im2col_stem: cin*k*k must be <= 32");
+  const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
+  UAVDET_CHECK_ARG(y->n == n && y->h == ho && y->w == wo && y->c == 32, "im2col_stem: output view must be (n,%d,%d,32)", ho, wo);
+  UAVDET_CHECK_ARG(y->ld % 8 == 0 && ((uintptr_t)y->ptr & 15) == 0, "im2col_stem: output alignment");
+  dim3 grid((unsigned)ceil_div64((long long)ho * wo, 256), (unsigned)n);
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* yp = (__nv_bfloat16*)y->ptr;
+#define UAVDET_I2C(CI, KS) im2col_stem_kernel<CI, KS><<<grid, 256, 0, st>>>(x_nchw, h, w, stride, pad, ho, wo, yp, y->ld)
+  if (cin == 3 && k == 3) UAVDET_I2C(3, 3);
+  else if (cin == 1 && k == 3) UAVDET_I2C(1, 3);
+  else if (cin == 3 && k == 1) UAVDET_I2C(3, 1);
+  else if (cin == 1 && k == 1) UAVDET_I2C(1, 1);
+  else if (cin == 1 && k == 5) UAVDET_I2C(1, 5);
+  else if (cin == 2 && k == 3) UAVDET_I2C(2, 3);
+  else { UAVDET_CHECK_ARG(false, "im2col_stem: (cin=%d, k=%d) not instantiated", cin, k); }
+#undef UAVDET_I2C
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }

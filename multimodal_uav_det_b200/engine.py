@@ -230,20 +230,46 @@ class Executor:
         return torch.zeros((rows, cols), dtype=torch.float32, device=device)
 
     # ---- forward ---------------------------------------------------------------------------------
+    @staticmethod
+    def stem_as_gemm(cin: int, cout: int, k: int) -> bool:
+        """cin<=3 stems whose taps fit 32 channels run as im2col + 1x1 implicit GEMM on the tensor cores; the
+        others (RTMUAVDet's 5x5 stem: 75 taps; DySOEM's 1x1: nothing to gather) keep the direct kernel."""
+        return cout % 32 == 0 and k > 1 and cin * k * k <= 32
+
+    def _stem_pack(self, w: torch.Tensor) -> torch.Tensor:
+        """(O, cin, k, k) fp32 -> bf16 [O][32]: w.flatten(1) zero-padded to the 32 im2col channels."""
+        key = (id(w), "stem")
+        ver = self.packs._ver(w)
+        hit = self.packs._store.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        flat = w.detach().flatten(1)
+        packed = torch.nn.functional.pad(flat, (0, 32 - flat.shape[1])).to(torch.bfloat16).contiguous()
+        self.packs._store[key] = (ver, packed)
+        return packed
+
     def conv_forward(self, u: ConvUnit, x: torch.Tensor, train: bool, tape: Optional[list],
                      res: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """y = act(bn(conv(x))) (+ res).  train=True uses batch statistics (two-phase BN) and records
         what backward needs; train=False folds BN into the conv epilogue (one kernel)."""
         w = u.conv.weight
         dev = w.device
+        in_hw = self._in_hw(u, x)
+        direct_stem = u.stem
+        k, stride, pad, s2d = u.k, u.stride, u.pad, u.s2d
+        if u.stem and self.stem_as_gemm(w.shape[1], u.cout, u.k):
+            x = ops.stem_im2col(x, u.k, u.stride, u.pad)          # (n, ho, wo, 32) bf16 patches
+            wp = self._stem_pack(w)
+            k, stride, pad, s2d, direct_stem = 1, 1, 0, False, False
+        elif not u.stem:
+            wp = self.packs.get(w)
         if u.bn is not None and train:
             c = u.cout
             sums = self.zeros(2, c, dev)
-            if u.stem:
-                raw = ops.stem_fwd(x, w.detach(), u.k, u.stride, u.pad, epi=EPI_STATS, sum_=sums[0], sumsq=sums[1])
+            if direct_stem:
+                raw = ops.stem_fwd(x, w.detach(), k, stride, pad, epi=EPI_STATS, sum_=sums[0], sumsq=sums[1])
             else:
-                raw = ops.conv_fwd(x, self.packs.get(w), c, u.k, u.stride, u.pad, s2d=u.s2d, epi=EPI_STATS,
-                                   sum_=sums[0], sumsq=sums[1])
+                raw = ops.conv_fwd(x, wp, c, k, stride, pad, s2d=s2d, epi=EPI_STATS, sum_=sums[0], sumsq=sums[1])
             n, ho, wo, _ = raw.shape
             bn = u.bn
             mom = 0.1 if bn.momentum is None else bn.momentum
@@ -255,7 +281,7 @@ class Executor:
                 self._bn_counters.append(bn.num_batches_tracked)
             y = ops.bn_act_fwd(raw, scale, shift, u.act, res=res, out=out)
             if tape is not None:
-                tape.append(ConvRecord(u, x, raw, scale, shift, mean, invstd, res is not None, self._in_hw(u, x)))
+                tape.append(ConvRecord(u, x, raw, scale, shift, mean, invstd, res is not None, in_hw))
             return y
         # ---- single-kernel path: eval-mode BN folded / bias-only conv ----
         if u.bn is not None:
@@ -270,23 +296,22 @@ class Executor:
         need_raw = tape is not None and u.act not in ("none", None)
         if need_raw:
             # training through a non-BN activation: keep the pre-activation for act'(z)
-            if u.stem:
-                raw = ops.stem_fwd(x, w.detach(), u.k, u.stride, u.pad, scale=scale, shift=shift)
+            if direct_stem:
+                raw = ops.stem_fwd(x, w.detach(), k, stride, pad, scale=scale, shift=shift)
             else:
-                raw = ops.conv_fwd(x, self.packs.get(w), u.cout, u.k, u.stride, u.pad, s2d=u.s2d, scale=scale,
-                                   shift=shift)
+                raw = ops.conv_fwd(x, wp, u.cout, k, stride, pad, s2d=s2d, scale=scale, shift=shift)
             y = ops.bn_act_fwd(raw, None, None, u.act, res=res, out=out)
-            tape.append(ConvRecord(u, x, raw, scale, None, None, None, res is not None, self._in_hw(u, x)))
+            tape.append(ConvRecord(u, x, raw, scale, None, None, None, res is not None, in_hw))
             return y
-        if u.stem:
-            y = ops.stem_fwd(x, w.detach(), u.k, u.stride, u.pad, act=u.act, scale=scale, shift=shift)
+        if direct_stem:
+            y = ops.stem_fwd(x, w.detach(), k, stride, pad, act=u.act, scale=scale, shift=shift)
             if res is not None or out is not None:
                 y = ops.add(y, res, out=out)
         else:
-            y = ops.conv_fwd(x, self.packs.get(w), u.cout, u.k, u.stride, u.pad, s2d=u.s2d, act=u.act, scale=scale,
-                             shift=shift, res=res, out=out)
+            y = ops.conv_fwd(x, wp, u.cout, k, stride, pad, s2d=s2d, act=u.act, scale=scale, shift=shift, res=res,
+                             out=out)
         if tape is not None:
-            tape.append(ConvRecord(u, x, None, scale, None, None, None, res is not None, self._in_hw(u, x)))
+            tape.append(ConvRecord(u, x, None, scale, None, None, None, res is not None, in_hw))
         return y
 
     @staticmethod
@@ -324,7 +349,12 @@ class Executor:
         # weight gradient
         if w.requires_grad:
             gbuf, _ = grad_buffer(w)
-            if u.stem:
+            if u.stem and rec.x.dtype == torch.bfloat16:
+                # im2col stem: a 1x1 weight gradient over the 32 patch channels; the first cin*k*k columns are dW
+                dwp = ops.conv_wgrad(rec.x, d_raw, 1, 1, 0)
+                kk = w.shape[1] * u.k * u.k
+                gbuf.add_(dwp[:, :kk].reshape(w.shape))
+            elif u.stem:
                 g = ops.stem_wgrad(rec.x, d_raw, u.k, u.stride, u.pad)
                 gbuf.add_(g)
             else:
@@ -358,16 +388,25 @@ class Executor:
         n = attn.shape[0]
         bank = sp.bank()
         bias_bank = sp.bias_bank() if sp.bias_bank is not None else None
+        in_hw = (x.shape[2], x.shape[3]) if sp.stem else (x.shape[1], x.shape[2])
+        bn, k, s, p, co = sp.bn, sp.k, sp.stride, sp.pad, sp.cout
+        direct_stem = sp.stem
         if sp.stem:
-            w_b = torch.mm(attn, bank.flatten(1)).view(n, *bank.shape[1:])        # fp32 kernels for the direct stem
+            w_b = torch.mm(attn, bank.flatten(1))                                  # (n, O*cin*k*k) fp32 per-sample kernels
             bias_b = None
+            if self.stem_as_gemm(sp.cin, co, k):
+                # im2col + batched 1x1 implicit GEMM: per-sample [O][32] bf16 kernels (taps zero-padded to 32)
+                x = ops.stem_im2col(x, k, s, p)
+                kk = sp.cin * k * k
+                w_b = torch.nn.functional.pad(w_b.view(n, co, kk), (0, 32 - kk)).to(torch.bfloat16).contiguous()
+                k, s, p, direct_stem = 1, 1, 0, False
+            else:
+                w_b = w_b.view(n, *bank.shape[1:])
         else:
             w_b, bias_b = ops.dyn_aggregate(attn, bank, bias_bank=bias_bank)
-        bn, k, s, p, co = sp.bn, sp.k, sp.stride, sp.pad, sp.cout
-        in_hw = (x.shape[2], x.shape[3]) if sp.stem else (x.shape[1], x.shape[2])
         if train:
             sums = self.zeros(2, co, attn.device)
-            if sp.stem:
+            if direct_stem:
                 raw = ops.stem_fwd(x, w_b, k, s, p, epi=EPI_STATS, sum_=sums[0], sumsq=sums[1], per_sample_w=True)
             else:
                 raw = ops.conv_fwd(x, w_b, co, k, s, p, s2d=sp.s2d, w_batch=n, epi=EPI_STATS, shift=bias_b,
@@ -389,7 +428,7 @@ class Executor:
             shift = (shift.unsqueeze(0) + bias_b * scale.unsqueeze(0)).contiguous()
         if tape is not None:
             # frozen-BN training: keep z = scale*conv + shift for act'(z)
-            if sp.stem:
+            if direct_stem:
                 z = ops.stem_fwd(x, w_b, k, s, p, scale=scale, shift=shift, per_sample_w=True)
             else:
                 z = ops.conv_fwd(x, w_b, co, k, s, p, s2d=sp.s2d, w_batch=n, scale=scale, shift=shift,
@@ -397,7 +436,7 @@ class Executor:
             y = ops.bn_act_fwd(z, None, None, sp.act)
             tape.append(DynRecord(sp, x, pooled, hidden, attn, bank, bias_bank, z, scale, None, None, None, in_hw))
             return y
-        if sp.stem:
+        if direct_stem:
             return ops.stem_fwd(x, w_b, k, s, p, act=sp.act, scale=scale, shift=shift, per_sample_w=True)
         return ops.conv_fwd(x, w_b, co, k, s, p, s2d=sp.s2d, w_batch=n, act=sp.act, scale=scale, shift=shift,
                             shift_per_sample=per_sample_shift)
@@ -429,7 +468,10 @@ class Executor:
             d_pre = ops.act_bwd(dy, rec.raw, None, None, sp.act)
             d_raw = ops.bn_act_fwd(d_pre, rec.scale, None, "none")
         # per-sample kernel gradient -> expert-bank gradient + attention gradient
-        if sp.stem:
+        if sp.stem and rec.x.dtype == torch.bfloat16:
+            kk = sp.cin * sp.k * sp.k                              # im2col stem: per-sample 1x1 wgrad, first kk columns
+            dwb = ops.conv_wgrad(rec.x, d_raw, 1, 1, 0, per_sample=True)[:, :, :kk].contiguous()
+        elif sp.stem:
             dwb = ops.stem_wgrad(rec.x, d_raw, sp.k, sp.stride, sp.pad, per_sample=True)
         else:
             dwb = ops.conv_wgrad(rec.x, d_raw, sp.k, sp.stride, sp.pad, s2d=sp.s2d, per_sample=True)

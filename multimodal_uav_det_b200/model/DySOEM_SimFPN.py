@@ -23,7 +23,7 @@ from torch import nn
 
 from .. import ops
 from .._lib import EPI_STATS
-from ..engine import ConvUnit, DynSpec, Executor
+from ..engine import ConvUnit, DynSpec, Executor, bump_param_epoch
 from ..utils.datatype import BatchData, DetectionResults
 from ._base import BaseModel, ConvModule, LightningModule, YOLOHead, to_nchw, to_nhwc
 
@@ -75,7 +75,7 @@ class DynamicSOEM(LightningModule):
     def dyn_spec(self, attn_temp) -> DynSpec:
         lin1, lin2 = self.attention[2], self.attention[4]
         convs = list(self.dy_convs)
-        return DynSpec(bank=lambda: torch.stack([c.weight.detach() for c in convs]),
+        return DynSpec(bank=lambda: torch.stack([c.weight.detach() for c in convs]).contiguous(),
                        bias_bank=lambda: torch.stack([c.bias.detach() for c in convs]).contiguous(),
                        bank_params=lambda: [(c.weight, i, False) for i, c in enumerate(convs)] +
                                            [(c.bias, i, True) for i, c in enumerate(convs)],
@@ -200,6 +200,7 @@ class DySOEM_SimFPN(BaseModel):
     def prepare_for_capture(self):
         self._exec.begin_step(self.neck.x2_in_down.weight.device)
         self._exec.packs.prepack(self._igemm_weights(), with_transposed=True)
+        bump_param_epoch()      # the captured step must re-pack: the weights change at every replay
 
     def _forward_program(self, x, tape):
         ex, train, temp = self._exec, self.training, self._attn_temp

@@ -18,7 +18,7 @@ import torch
 from torch import nn
 
 from .. import ops
-from ..engine import ConvUnit, DynRecord, Executor
+from ..engine import ConvUnit, DynRecord, Executor, bump_param_epoch
 from ..utils.datatype import BatchData, DetectionResults
 from ._base import BaseModel, DyConvModule, LightningModule, YOLOHead, to_nhwc, to_nchw
 
@@ -193,6 +193,7 @@ class DarknetDetector(BaseModel):
         """Build the host-side tables a CUDA-graph capture must not create (they need host->device copies)."""
         self._exec.begin_step(self._igemm_weights()[0].device)
         self._exec.packs.prepack(self._igemm_weights(), with_transposed=True)
+        bump_param_epoch()      # ... but the captured step must re-pack: the weights change at every replay
 
     def _forward_program(self, x, tape: Optional[list]) -> List[DetectionResults]:
         ex = self._exec

@@ -339,6 +339,19 @@ def stem_fwd(x_nchw: torch.Tensor, w: torch.Tensor, k: int, stride: int, pad: in
     return out
 
 
+def stem_im2col(x_nchw: torch.Tensor, k: int, stride: int, pad: int) -> torch.Tensor:
+    """(n,cin,h,w) fp32 -> (n,ho,wo,32) bf16 patches, channel (ci*k+kh)*k+kw, zero padded (cin*k*k <= 32)."""
+    _require_cuda(x_nchw)
+    x_nchw = _f32(x_nchw)
+    n, cin, h, w = x_nchw.shape
+    ho, wo = conv_out_hw(h, w, k, stride, pad)
+    out = empty_act(n, ho, wo, 32, x_nchw.device)
+    yv = act_view(out)
+    check(_lib.load().uavdet_im2col_stem(_ptr(x_nchw), n, cin, h, w, k, stride, pad, C.byref(yv), _stream()),
+          "im2col_stem")
+    return out
+
+
 def stem_wgrad(x_nchw: torch.Tensor, dy: torch.Tensor, k: int, stride: int, pad: int,
                per_sample: bool = False) -> torch.Tensor:
     _require_cuda(x_nchw, dy)

@@ -224,8 +224,10 @@ def _bn(x, sd, p, train, eps=1e-5, momentum=0.1):
 def cnn_block(x, sd, p, stride=1, pad=0, train=False, res=None):
     """CNNBlock: conv(no bias) -> BN -> LeakyReLU(0.1)   (BaselineModel.py:10-22) (+ res)."""
     w = sd[p + ".conv.weight"]
-    stem = w.shape[1] < 32          # the product's stem kernel reads fp32 input and fp32 weights
-    raw = F.conv2d(x if stem else qb(x), w if stem else qf(w), None, stride, pad)
+    stem = w.shape[1] < 32          # network input: no gradient flows back, but it is a bf16 storage point too
+    # (the product's stem reads bf16 im2col patches and bf16 weights when cin*k*k <= 32, i.e. for k > 1)
+    stem_fp32 = stem and not (w.shape[-1] > 1 and w.shape[1] * w.shape[-1] * w.shape[-1] <= 32)
+    raw = F.conv2d(x if stem_fp32 else (qf(x) if stem else qb(x)), w if stem_fp32 else qf(w), None, stride, pad)
     y = F.leaky_relu(_bn(qf(qb(raw)), sd, p + ".bn", train), 0.1)
     if res is not None:
         y = y + res

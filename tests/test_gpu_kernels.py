@@ -701,3 +701,30 @@ def test_pack_weight_layouts_and_batched(lib):
     ops.pack_weights_batched(table, n, chunks)
     for _, out, _, ref in jobs:
         assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("cin,k,stride,pad,h,w", [(3, 3, 1, 1, 40, 56), (1, 3, 2, 1, 32, 32), (3, 1, 1, 0, 16, 24),
+                                                  (1, 5, 2, 1, 33, 47)])
+def test_stem_im2col_then_gemm_equals_conv(lib, cin, k, stride, pad, h, w):
+    """im2col of the cin<=3 input (bit-exact vs F.unfold in bf16) and the stem conv as a 1x1 tcgen05 GEMM over the
+    32 patch channels, incl. its weight gradient, against F.conv2d / conv2d_weight."""
+    ops = _ops(lib)
+    n, cout = 3, 32
+    g = torch.Generator().manual_seed(300 + k)
+    x = torch.rand(n, cin, h, w, generator=g)
+    wt = bf16_round(torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k))
+    cols = ops.stem_im2col(x.to(DEV), k, stride, pad)
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    kk = cin * k * k
+    ref_cols = F.unfold(x, k, padding=pad, stride=stride).view(n, kk, ho, wo).permute(0, 2, 3, 1)
+    assert torch.equal(cols[..., :kk].float().cpu(), bf16_round(ref_cols))
+    assert torch.all(cols[..., kk:] == 0)
+    wp = F.pad(wt.flatten(1), (0, 32 - kk)).to(torch.bfloat16).to(DEV).contiguous()
+    y = ops.conv_fwd(cols, wp, cout, 1, 1, 0)
+    ref = F.conv2d(bf16_round(x), wt, None, stride, pad)
+    assert_close_bf16(to_nchw(y), ref, "stem as gemm")
+    dy = bf16_round(torch.randn(n, cout, ho, wo, generator=g))
+    dwp = ops.conv_wgrad(cols, nhwc(dy), 1, 1, 0)
+    ops.check_device()
+    ref_dw = torch.nn.grad.conv2d_weight(bf16_round(x), wt.shape, dy, stride, pad)
+    assert rel_l2(dwp[:, :kk].reshape(wt.shape).cpu(), ref_dw) < 2e-3

@@ -530,6 +530,7 @@ def test_flat_trainer_channels_last_storage_gives_same_gradients(lib):
         model.route_repeats = 2
         randomize_bn(model)
         model = model.to(DEV).eval()
+        model.yolo_head.mutate_targets = False
         sd_before = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
         if mode == "flat":
             trainer = FlatSGDTrainer(model, lr=1e-3, momentum=0.7)
@@ -545,7 +546,7 @@ def test_flat_trainer_channels_last_storage_gives_same_gradients(lib):
         loss, _, _, _ = model.yolo_head.compute_metrics(outs, BatchData(image=x, bbox=tg))
         loss.backward()
         grads[mode] = {k: p.grad.detach().float().cpu().clone() for k, p in model.named_parameters() if p.grad is not None}
-    assert grads["plain"].keys() == grads["flat"].keys()
+    assert set(grads["plain"]) <= set(grads["flat"])        # the flat arenas give every parameter a (zero) grad
     worst = max(rel_l2(grads["flat"][k], grads["plain"][k]) for k in grads["plain"])
     print("channels-last vs OIHW gradient rel_l2 (worst)", worst)
     assert worst < 2e-3
