@@ -212,6 +212,17 @@ int uavdet_bn_bwd_finalize(const float* sum_dz, const float* sum_dzr, const floa
 int uavdet_bn_act_bwd_apply(const uavdet_act* dy, const uavdet_act* raw, const float* scale,
                             const float* shift, const float* k1, const float* k0, int act,
                             const uavdet_act* d_raw, void* stream);
+/* The same two phases with the per-channel finalize folded into the streaming kernel (one launch less per layer
+ * and direction): uavdet_bn_train_fwd = bn_finalize + bn_act_fwd (publishes mean/invstd/scale/shift, updates the
+ * running statistics); uavdet_bn_act_bwd_apply_fused = bn_bwd_finalize + bn_act_bwd_apply (publishes dgamma/dbeta). */
+int uavdet_bn_train_fwd(const uavdet_act* raw, const float* sum, const float* sumsq, double count, float eps,
+                        float momentum, const float* gamma, const float* beta, float* running_mean,
+                        float* running_var, float* mean, float* invstd, float* scale, float* shift, int act,
+                        const uavdet_act* res, const uavdet_act* y, void* stream);
+int uavdet_bn_act_bwd_apply_fused(const uavdet_act* dy, const uavdet_act* raw, const float* scale,
+                                  const float* shift, const float* sum_dz, const float* sum_dzr, const float* mean,
+                                  const float* invstd, double count, int act, float* dgamma, float* dbeta,
+                                  const uavdet_act* d_raw, void* stream);
 /* eval-mode / bias-only activation backward: dx = dy*act'(raw*scale+shift)*scale.         */
 int uavdet_act_bwd(const uavdet_act* dy, const uavdet_act* raw, const float* scale,
                    const float* shift, int act, const uavdet_act* dx, void* stream);

@@ -63,6 +63,8 @@ SIGNATURES = {
     "uavdet_bn_act_bwd_reduce": (_i, [_AP, _AP, _P, _P, _i, _P, _P, _P]),
     "uavdet_bn_bwd_finalize": (_i, [_P, _P, _P, _P, _P, _i, _d, _P, _P, _P, _P, _P]),
     "uavdet_bn_act_bwd_apply": (_i, [_AP, _AP, _P, _P, _P, _P, _i, _AP, _P]),
+    "uavdet_bn_train_fwd": (_i, [_AP, _P, _P, _d, _f, _f, _P, _P, _P, _P, _P, _P, _P, _P, _i, _AP, _AP, _P]),
+    "uavdet_bn_act_bwd_apply_fused": (_i, [_AP, _AP, _P, _P, _P, _P, _P, _P, _d, _i, _P, _P, _AP, _P]),
     "uavdet_act_bwd": (_i, [_AP, _AP, _P, _P, _i, _AP, _P]),
     "uavdet_upsample2x_fwd": (_i, [_AP, _AP, _P]),
     "uavdet_upsample2x_bwd": (_i, [_AP, _AP, _i, _P]),

@@ -154,6 +154,87 @@ bn_act_fwd_kernel(View raw, const float* __restrict__ scale, const float* __rest
   }
 }
 
+// ---- train-mode BN in one pass over the activations: finalize folded in --------------------------------
+// Every thread derives scale/shift of its 8 channels from the batch sums (a few flops); the threads of the first
+// pixel lane of block column 0 also publish mean / invstd / scale / shift (backward needs them) and update the
+// running statistics (momentum, unbiased variance — nn.BatchNorm2d, BaselineModel.py:14).
+template <bool HAS_RES>
+__global__ void __launch_bounds__(256)
+bn_train_fwd_kernel(View raw, const float* __restrict__ sum, const float* __restrict__ sumsq, double count, float eps,
+                    float momentum, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ mean_out,
+                    float* __restrict__ invstd_out, float* __restrict__ scale_out, float* __restrict__ shift_out, int act,
+                    const __nv_bfloat16* __restrict__ res, int res_ld, View y) {
+  const PixLane L = pix_lane(raw.c);
+  if (!L.active) return;
+  float s[8], t[8];
+  {
+    float su[8], sq[8], g[8], b[8];
+    load8f(sum + L.c, su);
+    load8f(sumsq + L.c, sq);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { g[j] = 1.f; b[j] = 0.f; }
+    if (gamma) load8f(gamma + L.c, g);
+    if (beta) load8f(beta + L.c, b);
+    const bool publish = blockIdx.x == 0 && threadIdx.x < (raw.c >> 3 < 32 ? raw.c >> 3 : 32);
+    const double inv_count = 1.0 / count;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // E[x^2] - E[x]^2 cancels in fp32, so those three operations stay in double; the reciprocal square root is
+      // a single fp32 instruction (every thread of the grid runs this preamble: no fp64 divide / sqrt here)
+      const double m = (double)su[j] * inv_count;
+      double var = fma(-m, m, (double)sq[j] * inv_count);
+      if (var < 0.0) var = 0.0;
+      const float is = rsqrtf((float)var + eps);
+      s[j] = g[j] * is;
+      t[j] = b[j] - (float)m * g[j] * is;
+      if (publish) {
+        const int c = L.c + j;
+        if (mean_out) mean_out[c] = (float)m;
+        if (invstd_out) invstd_out[c] = is;
+        scale_out[c] = s[j];
+        shift_out[c] = t[j];
+        if (running_mean) {
+          const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+          running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+          running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+        }
+      }
+    }
+  }
+  auto body = [&](const uint4& in, const uint4& rin, long long px) {
+    float v[8];
+    unpack8(in, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = act_fwd_rt(act, fmaf(v[j], s[j], t[j]));
+    if (HAS_RES) {
+      float r[8];
+      unpack8(rin, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+    *reinterpret_cast<uint4*>(y.p + px * y.ld + L.c) = pack8(v);
+  };
+  long long px = L.px0;
+  for (; px + 3 * L.step < raw.npix; px += 4 * L.step) {
+    uint4 a[4], r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      a[u] = __ldg(reinterpret_cast<const uint4*>(raw.p + (px + u * L.step) * raw.ld + L.c));
+      if (HAS_RES) r[u] = __ldg(reinterpret_cast<const uint4*>(res + (px + u * L.step) * res_ld + L.c));
+      else r[u] = make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) body(a[u], r[u], px + u * L.step);
+  }
+  for (; px < raw.npix; px += L.step) {
+    uint4 a = __ldg(reinterpret_cast<const uint4*>(raw.p + px * raw.ld + L.c));
+    uint4 r = make_uint4(0, 0, 0, 0);
+    if (HAS_RES) r = __ldg(reinterpret_cast<const uint4*>(res + px * res_ld + L.c));
+    body(a, r, px);
+  }
+}
+
 // ---- BN backward, phase 1: per-channel sums of dz and dz*raw ---------------------------------
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(View dy, View raw, const float* __restrict__ scale, const float* __restrict__ shift, int act,
@@ -237,6 +318,59 @@ bn_bwd_apply_kernel(View dy, View raw, const float* __restrict__ scale, const fl
   load8f(shift + L.c, t);
   load8f(k1 + L.c, a1);
   load8f(k0 + L.c, a0);
+  auto body = [&](const uint4& din, const uint4& rin, long long px) {
+    float d[8], r[8];
+    unpack8(din, d);
+    unpack8(rin, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float dz = d[j] * act_grad_rt(act, fmaf(r[j], s[j], t[j]));
+      d[j] = fmaf(s[j], dz, fmaf(a1[j], r[j], a0[j]));
+    }
+    *reinterpret_cast<uint4*>(dr.p + px * dr.ld + L.c) = pack8(d);
+  };
+  long long px = L.px0;
+  for (; px + 3 * L.step < dy.npix; px += 4 * L.step) {
+    uint4 a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      a[u] = __ldg(reinterpret_cast<const uint4*>(dy.p + (px + u * L.step) * dy.ld + L.c));
+      b[u] = __ldg(reinterpret_cast<const uint4*>(raw.p + (px + u * L.step) * raw.ld + L.c));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) body(a[u], b[u], px + u * L.step);
+  }
+  for (; px < dy.npix; px += L.step)
+    body(__ldg(reinterpret_cast<const uint4*>(dy.p + px * dy.ld + L.c)),
+         __ldg(reinterpret_cast<const uint4*>(raw.p + px * raw.ld + L.c)), px);
+}
+
+// ---- BN backward, phase 2 with the per-channel finalize folded in -------------------------------------------------
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_fused_kernel(View dy, View raw, const float* __restrict__ scale, const float* __restrict__ shift,
+                          const float* __restrict__ sum_dz, const float* __restrict__ sum_dzr,
+                          const float* __restrict__ mean, const float* __restrict__ invstd, float inv_count, int act,
+                          float* __restrict__ dgamma, float* __restrict__ dbeta, View dr) {
+  const PixLane L = pix_lane(dy.c);
+  if (!L.active) return;
+  float s[8], t[8], a1[8], a0[8];
+  load8f(scale + L.c, s);
+  load8f(shift + L.c, t);
+  {
+    float sd[8], sdr[8], mu[8], is[8];
+    load8f(sum_dz + L.c, sd);
+    load8f(sum_dzr + L.c, sdr);
+    load8f(mean + L.c, mu);
+    load8f(invstd + L.c, is);
+    const bool publish = blockIdx.x == 0 && threadIdx.x < (dy.c >> 3 < 32 ? dy.c >> 3 : 32);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float dg = is[j] * (sdr[j] - mu[j] * sd[j]);
+      a1[j] = -s[j] * is[j] * dg * inv_count;
+      a0[j] = -s[j] * sd[j] * inv_count - a1[j] * mu[j];
+      if (publish) { dgamma[L.c + j] = dg; dbeta[L.c + j] = sd[j]; }
+    }
+  }
   auto body = [&](const uint4& din, const uint4& rin, long long px) {
     float d[8], r[8];
     unpack8(din, d);
@@ -768,6 +902,48 @@ extern "C" int uavdet_bn_act_bwd_apply(const uavdet_act* dy, const uavdet_act* r
   UAVDET_CHECK_ARG(scale && shift && k1 && k0, "bn_bwd_apply: null coefficients");
   bn_bwd_apply_kernel<<<stream_grid(dy, 8), 256, 0, ST>>>(mkview(dy), mkview(raw), scale, shift, k1, k0, act,
                                                           mkview(d_raw));
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_bn_train_fwd(const uavdet_act* raw, const float* sum, const float* sumsq, double count, float eps,
+                                   float momentum, const float* gamma, const float* beta, float* running_mean,
+                                   float* running_var, float* mean, float* invstd, float* scale, float* shift, int act,
+                                   const uavdet_act* res, const uavdet_act* y, void* stream) {
+  int rc;
+  if ((rc = check_view(raw, "bn_train_fwd raw")) || (rc = check_view(y, "bn_train_fwd y")) ||
+      (rc = same_shape(raw, y, "bn_train_fwd")))
+    return rc;
+  UAVDET_CHECK_ARG(sum && sumsq && scale && shift && count > 0, "bn_train_fwd: sums / outputs missing");
+  dim3 grid = stream_grid(raw, 4);
+  if (res) {
+    if ((rc = check_view(res, "bn_train_fwd res")) || (rc = same_shape(raw, res, "bn_train_fwd res"))) return rc;
+    bn_train_fwd_kernel<true><<<grid, 256, 0, ST>>>(mkview(raw), sum, sumsq, count, eps, momentum, gamma, beta,
+                                                   running_mean, running_var, mean, invstd, scale, shift, act,
+                                                   (const __nv_bfloat16*)res->ptr, res->ld, mkview(y));
+  } else {
+    bn_train_fwd_kernel<false><<<grid, 256, 0, ST>>>(mkview(raw), sum, sumsq, count, eps, momentum, gamma, beta,
+                                                    running_mean, running_var, mean, invstd, scale, shift, act, nullptr,
+                                                    0, mkview(y));
+  }
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_bn_act_bwd_apply_fused(const uavdet_act* dy, const uavdet_act* raw, const float* scale,
+                                             const float* shift, const float* sum_dz, const float* sum_dzr,
+                                             const float* mean, const float* invstd, double count, int act,
+                                             float* dgamma, float* dbeta, const uavdet_act* d_raw, void* stream) {
+  int rc;
+  if ((rc = check_view(dy, "bn_bwd_apply_fused dy")) || (rc = check_view(raw, "bn_bwd_apply_fused raw")) ||
+      (rc = check_view(d_raw, "bn_bwd_apply_fused d_raw")) || (rc = same_shape(dy, raw, "bn_bwd_apply_fused")) ||
+      (rc = same_shape(dy, d_raw, "bn_bwd_apply_fused")))
+    return rc;
+  UAVDET_CHECK_ARG(scale && shift && sum_dz && sum_dzr && mean && invstd && dgamma && dbeta && count > 0,
+                   "bn_bwd_apply_fused: null argument");
+  bn_bwd_apply_fused_kernel<<<stream_grid(dy, 4), 256, 0, ST>>>(mkview(dy), mkview(raw), scale, shift, sum_dz, sum_dzr,
+                                                               mean, invstd, (float)(1.0 / count), act, dgamma, dbeta,
+                                                               mkview(d_raw));
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }

@@ -273,13 +273,12 @@ class Executor:
             n, ho, wo, _ = raw.shape
             bn = u.bn
             mom = 0.1 if bn.momentum is None else bn.momentum
-            mean, invstd, scale, shift = ops.bn_finalize(
-                sums[0], sums[1], n * ho * wo, bn.eps, mom, bn.weight.detach(), bn.bias.detach(),
+            y, mean, invstd, scale, shift = ops.bn_train_fwd(
+                raw, sums[0], sums[1], n * ho * wo, bn.eps, mom, bn.weight.detach(), bn.bias.detach(),
                 bn.running_mean if bn.track_running_stats else None,
-                bn.running_var if bn.track_running_stats else None)
+                bn.running_var if bn.track_running_stats else None, u.act, res=res, out=out)
             if bn.track_running_stats and bn.num_batches_tracked is not None:
                 self._bn_counters.append(bn.num_batches_tracked)
-            y = ops.bn_act_fwd(raw, scale, shift, u.act, res=res, out=out)
             if tape is not None:
                 tape.append(ConvRecord(u, x, raw, scale, shift, mean, invstd, res is not None, in_hw))
             return y
@@ -413,11 +412,11 @@ class Executor:
                                    shift_per_sample=bias_b is not None, sum_=sums[0], sumsq=sums[1])
             _, ho, wo, _ = raw.shape
             mom = 0.1 if bn.momentum is None else bn.momentum
-            mean, invstd, scale, shift = ops.bn_finalize(sums[0], sums[1], n * ho * wo, bn.eps, mom, bn.weight.detach(),
-                                                         bn.bias.detach(), bn.running_mean, bn.running_var)
+            y, mean, invstd, scale, shift = ops.bn_train_fwd(raw, sums[0], sums[1], n * ho * wo, bn.eps, mom,
+                                                             bn.weight.detach(), bn.bias.detach(), bn.running_mean,
+                                                             bn.running_var, sp.act)
             if bn.num_batches_tracked is not None:
                 self._bn_counters.append(bn.num_batches_tracked)
-            y = ops.bn_act_fwd(raw, scale, shift, sp.act)
             if tape is not None:
                 tape.append(DynRecord(sp, x, pooled, hidden, attn, bank, bias_bank, raw, scale, shift, mean, invstd, in_hw))
             return y

@@ -17,6 +17,11 @@ from . import _lib
 from ._lib import ACT, EPI_AFFINE, EPI_HEAD, EPI_STATS, Act, Epilogue, UavdetError, check
 
 
+import os as _os
+_NO_BN_FUSE = not bool(_os.environ.get("UAVDET_BN_FUSE_FWD"))      # A/B switches for tuning
+_NO_BN_FUSE_BWD = bool(_os.environ.get("UAVDET_NO_BN_FUSE_BWD"))
+
+
 def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -380,6 +385,27 @@ def bn_finalize(sum_, sumsq, count: float, eps: float, momentum: float, gamma, b
     return mean, invstd, scale, shift
 
 
+def bn_train_fwd(raw, sum_, sumsq, count: float, eps: float, momentum: float, gamma, beta, running_mean, running_var,
+                 act, res=None, out=None):
+    """Train-mode BN + activation (+ residual) in one pass; returns (y, mean, invstd, scale, shift)."""
+    if _NO_BN_FUSE:
+        mean, invstd, scale, shift = bn_finalize(sum_, sumsq, count, eps, momentum, gamma, beta, running_mean, running_var)
+        return bn_act_fwd(raw, scale, shift, act, res=res, out=out), mean, invstd, scale, shift
+    c = raw.shape[3]
+    stats = torch.empty((4, c), dtype=torch.float32, device=raw.device)      # mean, invstd, scale, shift
+    if out is None:
+        out = torch.empty(raw.shape, dtype=torch.bfloat16, device=raw.device)
+    rv, yv = act_view(raw), act_view(out)
+    resv = act_view(res) if res is not None else None
+    check(_lib.load().uavdet_bn_train_fwd(C.byref(rv), _ptr(sum_), _ptr(sumsq), float(count), float(eps), float(momentum),
+                                          _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), _ptr(stats[0]),
+                                          _ptr(stats[1]), _ptr(stats[2]), _ptr(stats[3]),
+                                          ACT[act] if not isinstance(act, int) else act,
+                                          C.byref(resv) if resv is not None else None, C.byref(yv), _stream()),
+          "bn_train_fwd")
+    return out, stats[0], stats[1], stats[2], stats[3]
+
+
 def bn_act_fwd(raw, scale, shift, act, res=None, out=None):
     if out is None:
         out = torch.empty(raw.shape, dtype=torch.bfloat16, device=raw.device)
@@ -403,13 +429,18 @@ def bn_act_bwd(dy, raw, scale, shift, mean, invstd, gamma, act, buf=None):
     check(lib.uavdet_bn_act_bwd_reduce(C.byref(dv), C.byref(rv), _ptr(scale), _ptr(shift), a, _ptr(buf[0]),
                                        _ptr(buf[1]), _stream()), "bn_act_bwd_reduce")
     count = raw.shape[0] * raw.shape[1] * raw.shape[2]
-    check(lib.uavdet_bn_bwd_finalize(_ptr(buf[0]), _ptr(buf[1]), _ptr(mean), _ptr(invstd), _ptr(scale), c,
-                                     float(count), _ptr(buf[2]), _ptr(buf[3]), _ptr(buf[4]), _ptr(buf[5]), _stream()),
-          "bn_bwd_finalize")
     d_raw = torch.empty(raw.shape, dtype=torch.bfloat16, device=raw.device)
     ov = act_view(d_raw)
-    check(lib.uavdet_bn_act_bwd_apply(C.byref(dv), C.byref(rv), _ptr(scale), _ptr(shift), _ptr(buf[4]), _ptr(buf[5]),
-                                      a, C.byref(ov), _stream()), "bn_act_bwd_apply")
+    if _NO_BN_FUSE_BWD:
+        check(lib.uavdet_bn_bwd_finalize(_ptr(buf[0]), _ptr(buf[1]), _ptr(mean), _ptr(invstd), _ptr(scale), c,
+                                         float(count), _ptr(buf[2]), _ptr(buf[3]), _ptr(buf[4]), _ptr(buf[5]), _stream()),
+              "bn_bwd_finalize")
+        check(lib.uavdet_bn_act_bwd_apply(C.byref(dv), C.byref(rv), _ptr(scale), _ptr(shift), _ptr(buf[4]), _ptr(buf[5]),
+                                          a, C.byref(ov), _stream()), "bn_act_bwd_apply")
+        return d_raw, buf[2], buf[3]
+    check(lib.uavdet_bn_act_bwd_apply_fused(C.byref(dv), C.byref(rv), _ptr(scale), _ptr(shift), _ptr(buf[0]), _ptr(buf[1]),
+                                            _ptr(mean), _ptr(invstd), float(count), a, _ptr(buf[2]), _ptr(buf[3]),
+                                            C.byref(ov), _stream()), "bn_act_bwd_apply_fused")
     return d_raw, buf[2], buf[3]
 
 

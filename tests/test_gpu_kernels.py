@@ -472,6 +472,13 @@ def test_bn_act_train_fwd_bwd(lib, act, c):
     torch.testing.assert_close(rv_d.cpu(), rv, rtol=1e-4, atol=1e-5)
     y = ops.bn_act_fwd(raw_d, scale, shift, act, res=nhwc(res))
     assert_close_bf16(to_nchw(y), out_ref.detach(), "bn_act_fwd")
+    # fused single-pass variant (finalize folded into the streaming kernel): same outputs, same running stats
+    rm_f, rv_f = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    y_f, mean_f, invstd_f, scale_f, shift_f = ops.bn_train_fwd(raw_d, s1, s2, n * h * w, 1e-5, 0.1, gamma.detach().to(DEV),
+                                                               beta.detach().to(DEV), rm_f, rv_f, act, res=nhwc(res))
+    assert_close_bf16(to_nchw(y_f), to_nchw(y), "fused bn fwd vs two-kernel", rel=1e-3)
+    for a_, b_ in ((mean_f, mean), (invstd_f, invstd), (scale_f, scale), (shift_f, shift), (rm_f, rm_d), (rv_f, rv_d)):
+        torch.testing.assert_close(a_, b_, rtol=1e-5, atol=1e-6)
     d_raw, dgamma, dbeta = ops.bn_act_bwd(nhwc(dy), raw_d, scale, shift, mean, invstd, gamma.detach().to(DEV), act)
     assert_close_bf16(to_nchw(d_raw), raw.grad, "bn d_raw", rel=1e-2, frac=2.0 ** -5)
     torch.testing.assert_close(dgamma.cpu(), gamma.grad, rtol=5e-3, atol=5e-2)
