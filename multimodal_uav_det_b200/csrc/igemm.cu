@@ -130,6 +130,48 @@ __device__ __forceinline__ void stage_chunk(const IgemmParams& P, uint32_t taddr
   }
 }
 
+// MMA issue loop of one CTA (single elected thread), KSTEPS = block_k / 16.
+template <int KSTEPS>
+__device__ __forceinline__ void mma_issue_loop(const IgemmParams& P, uint32_t smem_base, uint32_t full_bar,
+                                               uint32_t empty_bar, uint32_t tfull_bar, uint32_t tempty_bar,
+                                               uint32_t tmem_base, int a_bytes, int stage_bytes, int num_kb,
+                                               volatile uint32_t* dead) {
+  const uint32_t idesc = make_idesc_bf16(P.block_n, 0, 0);
+  const uint32_t layout = (KSTEPS == 4) ? 2u : 4u;            // SWIZZLE_128B : SWIZZLE_64B
+  const uint32_t sbo = 8u * (uint32_t)(KSTEPS * 16) * 2u;     // 8 rows of one swizzle atom
+  const uint64_t a0 = make_smem_desc(smem_base, 16, sbo, layout);
+  const uint64_t b0 = make_smem_desc(smem_base + (uint32_t)a_bytes, 16, sbo, layout);
+  const uint32_t stage_step = (uint32_t)stage_bytes >> 4;
+  const uint32_t last_stage = (uint32_t)P.stages - 1u;
+  uint32_t stage = 0, phase = 0, soff = 0;
+  uint32_t acc = 0, acc_phase = 0;
+  for (int tile = blockIdx.x, tl = 0; tile < P.total_tiles; tile += gridDim.x, ++tl) {
+    const bool tr = P.trace && blockIdx.x == 0 && tl < P.trace_tiles;
+    if (tr) P.trace[tl * 16 + 2] = clock64();
+    mbar_wait(tempty_bar + 8u * acc, acc_phase ^ 1u, dead, P.watchdog, 0x2u);
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + acc * (uint32_t)kAccStride;
+    uint32_t accumulate = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(full_bar + 8u * stage, phase, dead, P.watchdog, 0x4u);
+      tc_fence_after();
+      const uint64_t ad = a0 + (uint64_t)soff, bd = b0 + (uint64_t)soff;
+#pragma unroll
+      for (int k = 0; k < KSTEPS; ++k) {
+        // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the >>4 field
+        tc_mma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, accumulate);
+        accumulate = 1u;
+      }
+      tc_commit(empty_bar + 8u * stage);
+      if (stage == last_stage) { stage = 0; phase ^= 1u; soff = 0; } else { ++stage; soff += stage_step; }
+    }
+    tc_commit(tfull_bar + 8u * acc);
+    if (tr) P.trace[tl * 16 + 4] = clock64();
+    acc ^= 1u;
+    if (acc == 0) acc_phase ^= 1u;
+  }
+}
+
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
              const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapOutTail,
@@ -185,69 +227,43 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     // multiple of prod_warps, so a pipeline stage is always refilled by the same warp (program order keeps the
     // two uses of its empty barrier apart).
     if (warp < P.prod_warps && elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t g = 0;
-      const uint32_t pmask = (uint32_t)P.prod_warps - 1u;
-      for (int tile = blockIdx.x, tl = 0; tile < P.total_tiles; tile += gridDim.x, ++tl) {
-        const TileCoord tc = decode_tile(P, tile);
-        const bool tr = P.trace && blockIdx.x == 0 && tl < P.trace_tiles && warp == 0;
-        if (tr) P.trace[tl * 16 + 0] = clock64();
-        for (int t = 0; t < P.num_taps; ++t) {
-          for (int kc = 0; kc < P.kc_per_tap; ++kc, ++g) {
-            if ((g & pmask) == (uint32_t)warp) {
-              const ConvTap tap = P.taps[t];
-              mbar_wait<32>(smem_u32(&empty_bar[stage]), phase ^ 1u, dead, P.watchdog, 0x1u);
-              const uint32_t fb = smem_u32(&full_bar[stage]);
-              mbar_arrive_expect_tx(fb, (uint32_t)(a_tx + b_bytes));
-              uint8_t* sa = smem + (size_t)stage * stage_bytes;
-              tma_load_5d(smem_u32(sa), &mapA, fb, tap.c_off + kc * P.block_k, tc.ow0 + tap.dw, tap.p,
-                          tc.oh0 + tap.dh, tc.img);
-              tma_load_3d(smem_u32(sa + a_bytes), &mapB, fb, tap.w_koff + kc * P.block_k, tc.n0,
-                          P.w_batch > 1 ? tc.img : 0);
-            }
-            if (++stage == P.stages) { stage = 0; phase ^= 1u; }
-          }
-        }
-        if (tr) P.trace[tl * 16 + 1] = clock64();
+      const int pw = P.prod_warps;
+      const int kcpt = P.kc_per_tap;
+      int tile = blockIdx.x;
+      int kb = warp;                      // k-block inside the tile (may run past num_kb: normalised below)
+      uint32_t stage = (uint32_t)warp, phase = 0;
+      int cur_tile = -1;
+      TileCoord tc{0, 0, 0, 0};
+      while (true) {
+        while (kb >= num_kb) { kb -= num_kb; tile += gridDim.x; }
+        if (tile >= P.total_tiles) break;
+        if (tile != cur_tile) { tc = decode_tile(P, tile); cur_tile = tile; }
+        const int t = kcpt == 1 ? kb : kb / kcpt;
+        const int kc = kb - t * kcpt;
+        const ConvTap tap = P.taps[t];
+        mbar_wait<32>(smem_u32(&empty_bar[stage]), phase ^ 1u, dead, P.watchdog, 0x1u);
+        const uint32_t fb = smem_u32(&full_bar[stage]);
+        mbar_arrive_expect_tx(fb, (uint32_t)(a_tx + b_bytes));
+        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+        tma_load_5d(smem_u32(sa), &mapA, fb, tap.c_off + kc * P.block_k, tc.ow0 + tap.dw, tap.p, tc.oh0 + tap.dh,
+                    tc.img);
+        tma_load_3d(smem_u32(sa + a_bytes), &mapB, fb, tap.w_koff + kc * P.block_k, tc.n0, P.w_batch > 1 ? tc.img : 0);
+        kb += pw;
+        stage += (uint32_t)pw;
+        if (stage >= (uint32_t)P.stages) { stage -= (uint32_t)P.stages; phase ^= 1u; }
       }
     }
   } else if (warp == kMmaWarp) {
     // ============================ MMA issuer ==============================
+    // One thread feeds the tensor pipe; at N = 64..128 an MMA takes only 32..64 cycles, so the per-k-block
+    // instruction path must be minimal: descriptors are built once (stage 0) and advanced by adding the stage /
+    // K-step offset in their (address >> 4) field, barrier addresses advance incrementally, the K-step loop is
+    // unrolled at compile time.
     if (elect_one()) {
-      const uint32_t idesc = make_idesc_bf16(P.block_n, 0, 0);
-      const uint32_t layout = (P.block_k == 64) ? 2u : 4u;      // SWIZZLE_128B : SWIZZLE_64B
-      const uint32_t sbo = 8u * (uint32_t)P.block_k * 2u;        // 8 rows of one swizzle atom
-      const int ksteps = P.block_k / 16;
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x, tl = 0; tile < P.total_tiles; tile += gridDim.x, ++tl) {
-        const bool tr = P.trace && blockIdx.x == 0 && tl < P.trace_tiles;
-        if (tr) P.trace[tl * 16 + 2] = clock64();
-        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u, dead, P.watchdog, 0x2u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(smem_u32(&full_bar[stage]), phase, dead, P.watchdog, 0x4u);
-          if (tr && kb == 0) P.trace[tl * 16 + 3] = clock64();
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint64_t a_desc = make_smem_desc(sa, 16, sbo, layout);
-          const uint64_t b_desc = make_smem_desc(sa + a_bytes, 16, sbo, layout);
-          for (int k = 0; k < ksteps; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the >>4 field
-            tc_mma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                        (kb | k) != 0 ? 1u : 0u);
-          }
-          tc_commit(smem_u32(&empty_bar[stage]));
-          if (++stage == P.stages) { stage = 0; phase ^= 1u; }
-        }
-        tc_commit(smem_u32(&tfull_bar[acc]));
-        if (tr) P.trace[tl * 16 + 4] = clock64();
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-      }
+      if (P.block_k == 64) mma_issue_loop<4>(P, smem_u32(smem), smem_u32(full_bar), smem_u32(empty_bar), smem_u32(tfull_bar),
+                                             smem_u32(tempty_bar), tmem_base, a_bytes, stage_bytes, num_kb, dead);
+      else mma_issue_loop<2>(P, smem_u32(smem), smem_u32(full_bar), smem_u32(empty_bar), smem_u32(tfull_bar),
+                             smem_u32(tempty_bar), tmem_base, a_bytes, stage_bytes, num_kb, dead);
     }
   } else {
     // ============================ epilogue (8 warps) =======================
@@ -753,7 +769,7 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
   int stages = (max_smem - ctrl_bytes - P.staging_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   UAVDET_CHECK_ARG(stages >= 2, "igemm: tile does not fit shared memory");
-  if (stages >= 8) { stages = 8; P.prod_warps = 4; }
+  if (stages >= 8) { stages &= ~3; P.prod_warps = 4; }
   else if (stages >= 4) { P.prod_warps = (stages % 4 == 0) ? 4 : 2; stages &= ~1; }
   else { P.prod_warps = 1; }
   P.stages = stages;

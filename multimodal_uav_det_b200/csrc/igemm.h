@@ -6,7 +6,7 @@
 namespace uavdet {
 
 constexpr int kMaxTaps = 36;   // 3x3 taps x 4 space-to-depth blocks, or 5x5
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 16;   // thin layers (12 KB stages) need many in flight to cover the memory latency
 
 // One filter tap = one shifted TMA box of the activation tensor map.
 struct ConvTap {
