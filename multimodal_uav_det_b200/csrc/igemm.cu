@@ -84,7 +84,9 @@ __device__ __forceinline__ void affine_act(float (&v)[32], const IgemmParams& P,
 
 // One 32-column chunk of one accumulator row: TMEM -> fp32 -> epilogue math -> bf16 -> swizzled staging row.
 // `chunk_in_slab` = which 32-column half of the (64-wide) slab; `sw_mask` = the row's swizzle XOR.
-__device__ __forceinline__ void stage_chunk(const IgemmParams& P, uint32_t taddr, int cg, bool valid, const float* shift,
+// Deliberately NOT inlined: it is called from 13 sites and carries the 5-way activation switch; inlined, the kernel
+// grew to 37,000 instructions (595 KB) and the epilogue warps thrashed the instruction cache.
+__device__ __noinline__ void stage_chunk(const IgemmParams& P, uint32_t taddr, int cg, bool valid, const float* shift,
                                             const __nv_bfloat16* res_px, uint8_t* srow, int chunk_in_slab, int sw_mask,
                                             bool release, uint32_t tempty, int lane) {
   uint32_t r[32];
@@ -202,7 +204,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);
-      mbar_init(smem_u32(&tempty_bar[a]), kEpiWarps);
+      // arrivals per tile: all 8 epilogue warps, or only the 4 that own the accumulator buffer when a tile is a
+      // single slab (warp-private modes: the two warps of a lane quarter then take alternate TILES)
+      mbar_init(smem_u32(&tempty_bar[a]),
+                (P.epi != UAVDET_EPI_HEAD && P.epi_mode != 0 && P.block_n == P.slab_w) ? kEpiWarps / 2 : kEpiWarps);
     }
     *dead = 0;
     fence_barrier_init();
@@ -362,11 +367,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f;
         }
       };
-      for (int tile = blockIdx.x, tl = 0; tile < P.total_tiles; tile += gridDim.x, ++tl) {
+      // single-slab tiles: this warp owns accumulator buffer `half` and visits every second tile
+      const int tstep = single ? 2 : 1;
+      if (single) acc = half;
+      for (int tile = blockIdx.x + (single ? half * (int)gridDim.x : 0), tl = single ? half : 0; tile < P.total_tiles;
+           tile += tstep * (int)gridDim.x, tl += tstep) {
         const TileCoord tc = decode_tile(P, tile);
         const int oh = tc.oh0 + hl, ow = tc.ow0 + wl;
         const bool valid = (row < kp) && (oh < P.ho) && (ow < P.wo);
-        const bool tr = P.trace && blockIdx.x == 0 && tl < P.trace_tiles && ew == 0 && lane == 0;
+        const bool tr = P.trace && blockIdx.x == 0 && tl < P.trace_tiles && (ew & 3) == 0 && lane == 0;
         if (P.epi == UAVDET_EPI_STATS && tc.n0 != cur_n0) {
           if (cur_n0 >= 0) flush_stats(cur_n0);
           cur_n0 = tc.n0;
@@ -380,13 +389,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         tc_fence_after();
         const uint32_t tbase = tmem_base + (uint32_t)(acc * kAccStride) + ((uint32_t)(q * 32) << 16);
         const uint32_t tempty = smem_u32(&tempty_bar[acc]);
-        const bool mine = !single || ((tl & 1) == half);
-        if (!mine) {
-          // nothing to read from this accumulator: still one arrival per warp per tile
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty);
-        } else {
+        {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int sl = single ? 0 : half + 2 * j;
@@ -395,10 +398,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
               uint8_t* wbuf = wbuf0 + (P.epi_bufs == 2 ? (ucount & 1u) * wbuf_bytes : 0);
               ++ucount;
               // the TMA store that last read this buffer must be done reading it
+              if (tr) P.trace[tl * 16 + 8] = clock64();
               if (lane == 0) {
                 if (P.epi_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
               }
               __syncwarp();
+              if (tr) P.trace[tl * 16 + 9] = clock64();
               const bool last = single || (sl + 2 >= n_slabs);
               uint8_t* srow = wbuf + lane * row_bytes;
               const int c0 = sl * P.slab_w;                          // accumulator column of the slab
@@ -411,8 +416,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                 stage_chunk(P, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, srow, 0, sw_mask, last, tempty,
                             lane);
               }
+              if (tr) P.trace[tl * 16 + 10] = clock64();
               fence_proxy_async();
               __syncwarp();
+              if (tr) P.trace[tl * 16 + 11] = clock64();
               if (lane == 0) {
                 if (P.epi_mode == 1) {
                   if (rows_here > 0) {
@@ -424,6 +431,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                   tma_store_commit();
                 }
               }
+              if (tr) P.trace[tl * 16 + 12] = clock64();
               if (P.epi == UAVDET_EPI_STATS) {
                 // column sums of the staged (bf16-rounded) rows: exactly the values the BatchNorm that follows
                 // will normalise.  Conflict-free: a row is one 128-byte line (slab 64) / two rows are (slab 32).
@@ -453,7 +461,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           }
         }
         if (tr) P.trace[tl * 16 + 7] = clock64();
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (single) acc_phase ^= 1u;
+        else if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
       if (P.epi == UAVDET_EPI_STATS && cur_n0 >= 0) flush_stats(cur_n0);
       if (lane == 0) tma_store_wait_all();   // smem must stay valid until the last store has read it

@@ -9,8 +9,9 @@ lib.uavdet_debug_set_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
 lib.uavdet_debug_set_trace.restype = None
 NT = 6
 trace = torch.zeros(NT * 16, dtype=torch.int64, device="cuda")
-for (n, cin, cout, k, s, hw, stats) in [(32, 256, 128, 1, 1, 80, True), (32, 128, 256, 3, 1, 80, True), (32, 128, 256, 3, 1, 80, False),
-                                        (32, 64, 32, 1, 1, 320, True)]:
+NT = 10
+trace = torch.zeros(NT * 16, dtype=torch.int64, device="cuda")
+for (n, cin, cout, k, s, hw, stats) in [(8, 32, 32, 1, 1, 640, True), (32, 64, 32, 1, 1, 320, True), (32, 32, 64, 3, 1, 320, True)]:
     x = torch.randn(n, hw, hw, cin, device="cuda").bfloat16()
     w = ops.pack_weight(torch.randn(cout, cin, k, k, device="cuda") * 0.05)
     s1 = torch.zeros(cout, device="cuda"); s2 = torch.zeros(cout, device="cuda")
@@ -25,12 +26,13 @@ for (n, cin, cout, k, s, hw, stats) in [(32, 256, 128, 1, 1, 80, True), (32, 128
     torch.cuda.synchronize()
     lib.uavdet_debug_set_trace(None, 0)
     t = trace.cpu().view(NT, 16)
-    t0 = int(t[0, 0])
+    t0 = int(t[0, 2])
     print(f"=== {cin}->{cout} k{k} s{s} @{hw} stats={stats}: kernel {e0.elapsed_time(e1)*1000:.0f} us; cycles rel. to first TMA issue")
     print(" tile | prod_start prod_end | mma_wait_tempty mma_first_full mma_commit | epi_wait epi_start epi_end")
     for i in range(NT):
-        if int(t[i, 0]) == 0: break
+        if int(t[i, 2]) == 0: break
         r = [int(v) - t0 for v in t[i]]
         e = r[6]
-        fine = " ".join(f"{(r[j] - e) if int(t[i, j]) else -1:6d}" for j in range(8, 16))
-        print(f" {i:4d} | {r[0]:9d} {r[1]:9d} | {r[2]:9d} {r[3]:9d} {r[4]:9d} | {r[5]:9d} {r[6]:9d} {r[7]:9d} | rel epi_start: slab0: start waitrd bar2 tmemld sts fence bar3 storeissue: {fine}")
+        e = r[6]
+        fine = " ".join(f"{(r[j] - e) if int(t[i, j]) else -1:6d}" for j in range(8, 13))
+        print(f" {i:4d} | {r[2]:9d} {r[4]:9d} | {r[5]:9d} {r[6]:9d} {r[7]:9d} (unit {r[7]-r[6]}) | rel epi_start: unit_begin after_waitrd after_sts after_fence after_store: {fine}")
