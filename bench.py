@@ -382,6 +382,15 @@ def run_ours(args, rank, world, local_rank):
     frames = B * world
     value = frames / step_s
     e2e_value = frames / (ms_e2e / args.steps * 1e-3)
+    # DRAM traffic of the dominant kernel over one step, from the committed ncu capture (profiles/, same command);
+    # reported next to the algorithmic bytes so re-reads show up
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_conv_dram_traffic_per_step.json")) as f:
+            k = json.load(f)["kernels"][dom_name]
+        traffic = k["dram_read_bytes"] + k["dram_write_bytes"]
+    except Exception:
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -397,7 +406,10 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": dom_name, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak_tf, "traffic": traffic,
+                     "traffic_note": "DRAM bytes of all launches of this kernel in one step (ncu, profiles/r01_conv_dram_traffic_per_step.json); "
+                                     "achieved = FLOPs of those launches / their summed in-graph duration",
+                     "peak_source": peak_src,
                      "launches_per_step": dom["launches"], "kernel_seconds_per_step": dom["seconds"],
                      "other_kernel": {"name": "wgrad_kernel" if dom_name == "igemm_kernel" else "igemm_kernel",
                                       "achieved": (wg if dom_name == "igemm_kernel" else ig)["flops"] /

@@ -39,6 +39,21 @@ def detect(model, x: torch.Tensor, iou_threshold: float = 0.5, score_floor: floa
                        score_floor)
 
 
+@torch.no_grad()
+def detect_rtm(model, x: torch.Tensor, iou_threshold: float = 0.5, score_floor: float = float("-inf")) -> Detections:
+    """RTMUAVDet: the heads already return sigmoid objectness and decoded cxcywh boxes (RTMUAVDet.py:274-310,
+    one fused sigmoid+decode kernel per scale); candidates of both scales are concatenated per image, converted to
+    xyxy and suppressed by the batched NMS kernel.  The reference never calls NMS on this model:
+    semantics = torchvision.ops.nms per image on the candidates with score > score_floor."""
+    outs = model(x)
+    b = outs[0].bbox.shape[0]
+    boxes = torch.cat([o.bbox.reshape(b, -1, 4) for o in outs], dim=1).contiguous()
+    scores = torch.cat([o.obj.reshape(b, -1) for o in outs], dim=1).contiguous()
+    boxes = ops.cxcywh_to_xyxy(boxes)
+    keep, count = ops.nms_batched(boxes, scores, iou_threshold, score_floor)
+    return Detections(boxes, scores, keep, count)
+
+
 def kept_lists(det: Detections) -> List[torch.Tensor]:
     counts = det.keep_count.tolist()
     return [det.keep[b, :c] for b, c in enumerate(counts)]
