@@ -94,6 +94,22 @@ int uavdet_decode_rtm(const float* bbox_sig, int batch, int A, int S_h, int S_w,
 /* cxcywh (.., 4) -> xyxy, torchvision box_convert arithmetic (_base.py:246). */
 int uavdet_cxcywh_to_xyxy(const float* in, float* out, int64_t count, void* stream);
 
+/* ---- detection loss ----------------------------------------------------- */
+/* One head scale of YOLOHead.compute_metrics (model/_base.py:155-192 with utils/metrics.py:8-84,
+ * utils/postprocess.py:51-85, _base.py:214-270) for the whole batch, forward AND gradient:
+ *   out2[0] = bbox_w * sum_b mean_{positives of b} box_loss      (ciou != 0: complete-IoU, else MSE)
+ *   out2[1] = sum_b [ objectness_w*obj_scale_w * mean_pos BCE(obj, iou_vs_first_target * t_obj)
+ *                     + no_obj_w * mean_neg BCE(obj, t_obj) ]
+ *   d_bbox / d_obj = d out2[0] / d p_bbox, d out2[1] / d p_obj   (same shapes as the logits)
+ *   new_t (optional) = the target boxes as the reference rewrites them in place (_base.py:257,266-267).
+ * p_bbox (B,A,H,W,4), p_obj (B,A,H,W,1), tgt (B,A,H,W,5) fp32; anchors_scaled_host: A*(w,h) / head scale.
+ * workspace: uavdet_yolo_head_loss_workspace_bytes(B) bytes of device scratch.                            */
+size_t uavdet_yolo_head_loss_workspace_bytes(int B);
+int uavdet_yolo_head_loss(const float* p_bbox, const float* p_obj, const float* tgt, int B, int A, int H, int W,
+                          const float* anchors_scaled_host, int ciou, float bbox_w, float objectness_w,
+                          float obj_scale_w, float no_obj_w, float* d_bbox, float* d_obj, float* new_t,
+                          void* workspace, float* out2, void* stream);
+
 /* ---- K1/K2: implicit-GEMM convolution on tcgen05 ------------------------------------ */
 /* Epilogue of the implicit GEMM. */
 #define UAVDET_EPI_AFFINE 0 /* y = act(acc*scale[c]+shift[c]) (+res) -> bf16 NHWC        */

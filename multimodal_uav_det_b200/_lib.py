@@ -48,6 +48,8 @@ SIGNATURES = {
     "uavdet_decode_yolo": (_i, [_P, _P, _i, _i, _i, _i, C.POINTER(_f), _i, _P, _P, _i, _i, _P]),
     "uavdet_decode_rtm": (_i, [_P, _i, _i, _i, _i, C.POINTER(_f), _P, _P]),
     "uavdet_cxcywh_to_xyxy": (_i, [_P, _P, _i64, _P]),
+    "uavdet_yolo_head_loss_workspace_bytes": (_sz, [_i]),
+    "uavdet_yolo_head_loss": (_i, [_P, _P, _P, _i, _i, _i, _i, C.POINTER(_f), _i, _f, _f, _f, _f, _P, _P, _P, _P, _P, _P]),
     "uavdet_conv_fwd": (_i, [_AP, _P, _i, _i, _i, _i, _i, _i, _AP, _EP, _P]),
     "uavdet_conv_dgrad": (_i, [_AP, _P, _i, _i, _i, _i, _i, _AP, _EP, _P]),
     "uavdet_conv_dgrad_s2d": (_i, [_AP, _P, _i, _i, _i, _i, _AP, _EP, _P]),

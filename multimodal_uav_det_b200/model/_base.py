@@ -19,7 +19,7 @@ from torch import nn
 from .. import ops
 from ..engine import ConvUnit, DynSpec, Executor, param_epoch
 from ..utils.datatype import BatchData, DetectionResults
-from ..utils.metrics import yolo_head_loss
+from ..utils.metrics import yolo_head_loss, yolo_head_loss_fused
 
 try:  # Lightning is optional: subclass it when importable (train.py drives it), else a no-op shim
     import pytorch_lightning as pl
@@ -161,6 +161,7 @@ class YOLOHead(LightningModule):
         self.no_obj_w = loss_balancing.no_obj_w
         self.bbox_loss_fn = bbox_loss_fn
         self.mutate_targets = True  # the reference rewrites batch.bbox in place (_base.py:257,266)
+        self.fused_loss = True      # CUDA tensors: loss + gradient by the fused kernel (False: batched torch math)
         for c in x_channels:
             self.detection_head.append(nn.ModuleDict(dict(obj=ObjectnessHead(c, n_anchors),
                                                           bbox=BBoxHead(c, n_anchors))))
@@ -259,9 +260,15 @@ class YOLOHead(LightningModule):
                 tgt = torch.stack([targets[i][h] for i in range(bsz)]).to(out.bbox.device)
             else:
                 tgt = targets[h].to(out.bbox.device)
-            sa = self._scaled_anchors(h, out.bbox.device)
-            bl, ol, new_t = yolo_head_loss(out.bbox.float(), out.obj.float(), tgt, sa, self.obj_scales_w[h], weights,
-                                           self.bbox_loss_fn)
+            if out.bbox.is_cuda and self.fused_loss:
+                # value + gradient of the head scale in three launches (csrc/loss.cu)
+                bl, ol, new_t = yolo_head_loss_fused(out.bbox.float(), out.obj.float(), tgt.float(),
+                                                     self.anchors[h] / self.head_scales[h], self.obj_scales_w[h],
+                                                     weights, self.bbox_loss_fn, want_new_t=self.mutate_targets)
+            else:
+                sa = self._scaled_anchors(h, out.bbox.device)
+                bl, ol, new_t = yolo_head_loss(out.bbox.float(), out.obj.float(), tgt, sa, self.obj_scales_w[h],
+                                               weights, self.bbox_loss_fn)
             bbox_losses = bbox_losses + bl
             obj_losses = obj_losses + ol
             if self.mutate_targets:

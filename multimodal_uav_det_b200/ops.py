@@ -148,6 +148,28 @@ def cxcywh_to_xyxy(t: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def yolo_head_loss(p_bbox, p_obj, tgt, anchors_scaled, ciou: bool, bbox_w: float, objectness_w: float,
+                   obj_scale_w: float, no_obj_w: float, want_new_t: bool):
+    """Fused loss + gradient of one head scale.  Returns (out2 [bbox_sum, obj_sum], d_bbox, d_obj, new_t|None)."""
+    _require_cuda(p_bbox, p_obj, tgt)
+    p_bbox, p_obj, tgt = _f32(p_bbox), _f32(p_obj), _f32(tgt)
+    b, a, h, w, _ = p_bbox.shape
+    lib = _lib.load()
+    dev = p_bbox.device
+    d_bbox = torch.empty_like(p_bbox)
+    d_obj = torch.empty_like(p_obj)
+    new_t = torch.empty_like(p_bbox) if want_new_t else None
+    out2 = torch.empty(2, dtype=torch.float32, device=dev)
+    ws = torch.empty(lib.uavdet_yolo_head_loss_workspace_bytes(b), dtype=torch.uint8, device=dev)
+    anc = [float(v) for v in anchors_scaled]
+    arr = (C.c_float * len(anc))(*anc)
+    check(lib.uavdet_yolo_head_loss(_ptr(p_bbox), _ptr(p_obj), _ptr(tgt), b, a, h, w, arr, 1 if ciou else 0,
+                                    float(bbox_w), float(objectness_w), float(obj_scale_w), float(no_obj_w),
+                                    _ptr(d_bbox), _ptr(d_obj), _ptr(new_t), _ptr(ws), _ptr(out2), _stream()),
+          "yolo_head_loss")
+    return out2, d_bbox, d_obj, new_t
+
+
 # --------------------------------------------------------------------------------------------
 # weights
 # --------------------------------------------------------------------------------------------

@@ -127,3 +127,34 @@ def yolo_head_loss(p_bbox, p_obj, tgt, scaled_anchors, obj_scale_w, weights, bbo
     nl = (bce_neg * (1 - cellf)).sum(dim=(1, 2, 3)) / (a * h * w - npos)
     obj_sum = objectness_w * obj_scale_w * ol.sum() + no_obj_w * nl.sum()
     return bbox_sum, obj_sum, new_t
+
+
+class _FusedHeadLoss(torch.autograd.Function):
+    """One head scale of the loss on the CUDA kernel (csrc/loss.cu): value and gradient come out of the same
+    launch, so backward is two scalings."""
+
+    @staticmethod
+    def forward(ctx, p_bbox, p_obj, tgt, anchors_scaled, obj_scale_w, weights, ciou, want_new_t):
+        from .. import ops
+        bbox_w, objectness_w, no_obj_w = weights
+        out2, d_bbox, d_obj, new_t = ops.yolo_head_loss(p_bbox, p_obj, tgt, anchors_scaled, ciou, bbox_w, objectness_w,
+                                                        obj_scale_w, no_obj_w, want_new_t)
+        ctx.save_for_backward(d_bbox, d_obj)
+        if new_t is None:
+            new_t = out2.new_empty(0)
+        ctx.mark_non_differentiable(new_t)
+        return out2[0], out2[1], new_t
+
+    @staticmethod
+    def backward(ctx, g_bbox, g_obj, _g_new_t):
+        d_bbox, d_obj = ctx.saved_tensors
+        return d_bbox * g_bbox, d_obj * g_obj, None, None, None, None, None, None
+
+
+def yolo_head_loss_fused(p_bbox, p_obj, tgt, scaled_anchors, obj_scale_w, weights, bbox_loss_fn, want_new_t=True):
+    """Same contract as `yolo_head_loss`, evaluated by the fused CUDA kernel (CUDA fp32 tensors)."""
+    anc = [float(v) for v in scaled_anchors.flatten().tolist()]
+    bl, ol, new_t = _FusedHeadLoss.apply(p_bbox.contiguous(), p_obj.contiguous(), tgt.contiguous(), anc,
+                                         float(obj_scale_w), tuple(float(w) for w in weights), bbox_loss_fn == "ciou",
+                                         want_new_t)
+    return bl, ol, (new_t if want_new_t else None)

@@ -735,3 +735,45 @@ def test_stem_im2col_then_gemm_equals_conv(lib, cin, k, stride, pad, h, w):
     ops.check_device()
     ref_dw = torch.nn.grad.conv2d_weight(bf16_round(x), wt.shape, dy, stride, pad)
     assert rel_l2(dwp[:, :kk].reshape(wt.shape).cpu(), ref_dw) < 2e-3
+
+
+@pytest.mark.parametrize("loss_fn", ["ciou", "mse"])
+@pytest.mark.parametrize("grid", [20, 37])
+def test_fused_yolo_head_loss_matches_batched_torch_loss(lib, loss_fn, grid):
+    """csrc/loss.cu (value + analytic gradient, 3 launches) against utils.metrics.yolo_head_loss under torch
+    autograd — which tests/test_host.py pins to the reference's per-sample loop and the golden fixture."""
+    from oracle import oracle as O
+    from multimodal_uav_det_b200.utils import metrics as M
+    b, a = 6, 3
+    anchors = [[[199, 73], [315, 92], [268, 182]], [[91, 54], [120, 75], [157, 60]], [[29, 23], [48, 30], [67, 38]]]
+    g = torch.Generator().manual_seed(500 + grid)
+    tg = []
+    for i in range(b):
+        nbox = 1 + i % 3                                   # several targets in some samples
+        cxy = torch.rand(nbox, 2, generator=g) * 400 + 120
+        wh = torch.rand(nbox, 2, generator=g) * 60 + 20
+        boxes = torch.cat([cxy - wh / 2, cxy + wh / 2], 1)
+        per = None
+        for k in range(nbox):
+            t = O.encode_targets(boxes[k:k + 1], anchors, [32, 16, 8], 640, grids=[grid, grid, grid])[2]
+            per = t if per is None else torch.where(t[..., :1] == 1.0, t, per)
+        tg.append(per)
+    tgt = torch.stack(tg).to(DEV)
+    assert tgt.shape == (b, a, grid, grid, 5) and (tgt[..., 0] == 1).sum() >= b
+    sa = torch.tensor(anchors[2]).float() / 8
+    p_bbox = (torch.randn(b, a, grid, grid, 4, generator=g) * 1.5).to(DEV).requires_grad_(True)
+    p_obj = (torch.randn(b, a, grid, grid, 1, generator=g) * 2).to(DEV).requires_grad_(True)
+    weights = (4.0, 1.0, 4.0)
+    bl_ref, ol_ref, nt_ref = M.yolo_head_loss(p_bbox, p_obj, tgt, sa.to(DEV), 2.0, weights, loss_fn)
+    (bl_ref * 0.7 + ol_ref * 1.3).backward()
+    gb_ref, go_ref = p_bbox.grad.clone(), p_obj.grad.clone()
+    p_bbox.grad = None
+    p_obj.grad = None
+    bl, ol, nt = M.yolo_head_loss_fused(p_bbox, p_obj, tgt, sa, 2.0, weights, loss_fn)
+    (bl * 0.7 + ol * 1.3).backward()
+    torch.testing.assert_close(bl, bl_ref, rtol=2e-5, atol=1e-5)
+    torch.testing.assert_close(ol, ol_ref, rtol=2e-5, atol=1e-5)
+    torch.testing.assert_close(nt, nt_ref, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(p_obj.grad, go_ref, rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(p_bbox.grad, gb_ref, rtol=2e-4, atol=1e-6)
+    assert (p_bbox.grad != 0).sum() > 0
