@@ -25,41 +25,79 @@ static inline int rtm_grid(long long items, int threads) {
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// Thread layout of the streaming kernels below: blockDim 256 = Gb channel groups (8 channels = 16 B) x PL pixel
+// lanes; a thread keeps its channel group, so per-channel parameters are loaded once and no index needs a divide.
+struct Lanes { int g, pl, Gb, PL; bool active; };
+__device__ __forceinline__ Lanes lanes_of(int c) {
+  const int G = c >> 3;
+  Lanes L;
+  L.Gb = G < 32 ? G : 32;
+  L.PL = 256 / L.Gb;
+  L.g = threadIdx.x % L.Gb + blockIdx.y * L.Gb;
+  L.pl = threadIdx.x / L.Gb;
+  L.active = L.g < G && L.pl < L.PL;
+  return L;
+}
+
 // out[b,y,x,c] = x[b,y,x,c] + channel_w[b,c] * sum_t kernel_w[b,t] * x[b,y+dy,x+dx,c]
-__global__ void dwdynconv_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int n, int h, int w, int c,
-                                 const float* __restrict__ channel_w, const float* __restrict__ kernel_w, int k,
-                                 int pad, __nv_bfloat16* __restrict__ y, int y_ld) {
-  const int c8 = c >> 3;
-  const long long total = (long long)n * h * w * c8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    long long px = i / c8;
-    const int cc = (int)(i - px * c8) << 3;
-    const int ox = (int)(px % w); long long t = px / w;
-    const int oy = (int)(t % h);
-    const int b = (int)(t / h);
+// A thread walks a vertical strip of `rows` output pixels of one column; for k = 3 the 3x3 window lives in
+// registers and rolls down the strip, so each output pixel costs 3 new 16-byte loads instead of 9.
+template <int KS>
+__global__ void __launch_bounds__(256)
+dwdynconv_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int h, int w, int c,
+                 const float* __restrict__ channel_w, const float* __restrict__ kernel_w, int xblocks, int rows,
+                 __nv_bfloat16* __restrict__ y, int y_ld) {
+  const Lanes L = lanes_of(c);
+  if (!L.active) return;
+  const int b = blockIdx.z;
+  const int xb = blockIdx.x % xblocks, strip = blockIdx.x / xblocks;
+  const int ox = xb * L.PL + L.pl;
+  if (ox >= w) return;
+  const int cc = L.g << 3;
+  const int y0 = strip * rows, y1 = min(h, y0 + rows);
+  constexpr int PAD = KS / 2;
+  float kw[KS * KS], cw[8];
+#pragma unroll
+  for (int t = 0; t < KS * KS; ++t) kw[t] = __ldg(kernel_w + b * KS * KS + t);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) cw[j] = __ldg(channel_w + (long long)b * c + cc + j);
+  const __nv_bfloat16* xb_ = x + (long long)b * h * w * x_ld + cc;
+  __nv_bfloat16* yb_ = y + (long long)b * h * w * y_ld + cc;
+  auto load_row = [&](int iy, uint4 (&r)[KS]) {
+#pragma unroll
+    for (int kx = 0; kx < KS; ++kx) {
+      const int ix = ox + kx - PAD;
+      r[kx] = (iy >= 0 && iy < h && ix >= 0 && ix < w)
+                  ? __ldg(reinterpret_cast<const uint4*>(xb_ + ((long long)iy * w + ix) * x_ld))
+                  : make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  uint4 win[KS][KS];                      // win[r] = input row (oy - PAD + r)
+#pragma unroll
+  for (int r = 0; r < KS - 1; ++r) load_row(y0 - PAD + r, win[r + 1]);
+  for (int oy = y0; oy < y1; ++oy) {
+#pragma unroll
+    for (int r = 0; r < KS - 1; ++r)
+#pragma unroll
+      for (int kx = 0; kx < KS; ++kx) win[r][kx] = win[r + 1][kx];
+    load_row(oy + PAD, win[KS - 1]);
     float acc[8], centre[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    unpack8r(__ldg(reinterpret_cast<const uint4*>(x + px * x_ld + cc)), centre);
-    const float* kw = kernel_w + (long long)b * k * k;
-    for (int kh = 0; kh < k; ++kh) {
-      const int iy = oy + kh - pad;
-      if (iy < 0 || iy >= h) continue;
-      for (int kx = 0; kx < k; ++kx) {
-        const int ix = ox + kx - pad;
-        if (ix < 0 || ix >= w) continue;
-        const float wt = __ldg(kw + kh * k + kx);
+#pragma unroll
+    for (int r = 0; r < KS; ++r)
+#pragma unroll
+      for (int kx = 0; kx < KS; ++kx) {
         float v[8];
-        unpack8r(__ldg(reinterpret_cast<const uint4*>(x + (((long long)b * h + iy) * w + ix) * x_ld + cc)), v);
+        unpack8r(win[r][kx], v);
+        const float wt = kw[r * KS + kx];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(wt, v[j], acc[j]);
       }
-    }
-    const float* cw = channel_w + (long long)b * c + cc;
+    unpack8r(win[PAD][PAD], centre);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = fmaf(__ldg(cw + j), acc[j], centre[j]);
-    *reinterpret_cast<uint4*>(y + px * y_ld + cc) = pack8r(acc);
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(cw[j], acc[j], centre[j]);
+    *reinterpret_cast<uint4*>(yb_ + ((long long)oy * w + ox) * y_ld) = pack8r(acc);
   }
 }
 
@@ -76,96 +114,124 @@ __global__ void linear_kernel(const float* __restrict__ in, int rows, int c, con
 }
 
 // per-sample sum / sum of squares of (a + b) over h*w*c
-__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ a, int a_ld, const __nv_bfloat16* __restrict__ b2,
-                                int b_ld, long long hw, int c, float* __restrict__ stats) {
-  const int img = blockIdx.y;
-  const int c8 = c >> 3;
-  const long long total = hw * c8;
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const __nv_bfloat16* __restrict__ a, int a_ld, const __nv_bfloat16* __restrict__ b2, int b_ld, int hw,
+                int c, float* __restrict__ stats) {
+  const Lanes L = lanes_of(c);
+  const int img = blockIdx.z;
   float s1 = 0.f, s2 = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long px = i / c8 + (long long)img * hw;
-    const int cc = (int)(i % c8) << 3;
-    float v[8];
-    unpack8r(__ldg(reinterpret_cast<const uint4*>(a + px * a_ld + cc)), v);
-    if (b2) {
-      float u[8];
-      unpack8r(__ldg(reinterpret_cast<const uint4*>(b2 + px * b_ld + cc)), u);
+  if (L.active) {
+    const int cc = L.g << 3;
+    const __nv_bfloat16* ap = a + (long long)img * hw * a_ld + cc;
+    const __nv_bfloat16* bp = b2 ? b2 + (long long)img * hw * b_ld + cc : nullptr;
+    const int step = gridDim.x * L.PL;
+    auto body = [&](const uint4& ua, const uint4& ub) {
+      float v[8], u[8];
+      unpack8r(ua, v);
+      unpack8r(ub, u);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += u[j];
+      for (int j = 0; j < 8; ++j) { const float t = v[j] + u[j]; s1 += t; s2 = fmaf(t, t, s2); }
+    };
+    int px = blockIdx.x * L.PL + L.pl;
+    for (; px + 3 * step < hw; px += 4 * step) {
+      uint4 ua[4], ub[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        ua[q] = __ldg(reinterpret_cast<const uint4*>(ap + (long long)(px + q * step) * a_ld));
+        ub[q] = bp ? __ldg(reinterpret_cast<const uint4*>(bp + (long long)(px + q * step) * b_ld)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) body(ua[q], ub[q]);
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
+    for (; px < hw; px += step)
+      body(__ldg(reinterpret_cast<const uint4*>(ap + (long long)px * a_ld)),
+           bp ? __ldg(reinterpret_cast<const uint4*>(bp + (long long)px * b_ld)) : make_uint4(0u, 0u, 0u, 0u));
   }
-  __shared__ float red[2][32];
+  __shared__ float red[2][8];
   for (int off = 16; off; off >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, off); s2 += __shfl_xor_sync(0xffffffffu, s2, off); }
   if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
   __syncthreads();
   if (threadIdx.x < 32) {
-    s1 = threadIdx.x < (blockDim.x >> 5) ? red[0][threadIdx.x] : 0.f;
-    s2 = threadIdx.x < (blockDim.x >> 5) ? red[1][threadIdx.x] : 0.f;
-    for (int off = 16; off; off >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, off); s2 += __shfl_xor_sync(0xffffffffu, s2, off); }
+    s1 = threadIdx.x < 8 ? red[0][threadIdx.x] : 0.f;
+    s2 = threadIdx.x < 8 ? red[1][threadIdx.x] : 0.f;
+    for (int off = 4; off; off >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, off); s2 += __shfl_xor_sync(0xffffffffu, s2, off); }
     if (threadIdx.x == 0) { atomicAdd(stats + 2 * img, s1); atomicAdd(stats + 2 * img + 1, s2); }
   }
 }
 
-__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ a, int a_ld, const __nv_bfloat16* __restrict__ b2,
-                                int b_ld, long long hw, int c, const float* __restrict__ stats, float eps,
-                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                __nv_bfloat16* __restrict__ y, int y_ld) {
-  const int img = blockIdx.y;
-  const int c8 = c >> 3;
-  const long long total = hw * c8;
-  const double cnt = (double)hw * c;
-  const double m = (double)stats[2 * img] / cnt;
-  double var = (double)stats[2 * img + 1] / cnt - m * m;
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const __nv_bfloat16* __restrict__ a, int a_ld, const __nv_bfloat16* __restrict__ b2, int b_ld, int hw,
+                int c, const float* __restrict__ stats, float eps, const float* __restrict__ gamma,
+                const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int y_ld) {
+  const Lanes L = lanes_of(c);
+  if (!L.active) return;
+  const int img = blockIdx.z;
+  const int cc = L.g << 3;
+  // E[x^2] - E[x]^2 in double (cancellation), one fp32 rsqrt
+  const double inv_cnt = 1.0 / ((double)hw * c);
+  const double m = (double)stats[2 * img] * inv_cnt;
+  double var = fma(-m, m, (double)stats[2 * img + 1] * inv_cnt);
   if (var < 0) var = 0;
-  const float mean = (float)m, invstd = (float)(1.0 / sqrt(var + (double)eps));
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long px = i / c8 + (long long)img * hw;
-    const int cc = (int)(i % c8) << 3;
-    float v[8];
-    unpack8r(__ldg(reinterpret_cast<const uint4*>(a + px * a_ld + cc)), v);
-    if (b2) {
-      float u[8];
-      unpack8r(__ldg(reinterpret_cast<const uint4*>(b2 + px * b_ld + cc)), u);
+  const float mean = (float)m, invstd = rsqrtf((float)var + eps);
+  float sc[8], sh[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += u[j];
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = invstd * __ldg(gamma + cc + j);
+    sh[j] = fmaf(-mean, sc[j], __ldg(beta + cc + j));
+  }
+  const __nv_bfloat16* ap = a + (long long)img * hw * a_ld + cc;
+  const __nv_bfloat16* bp = b2 ? b2 + (long long)img * hw * b_ld + cc : nullptr;
+  __nv_bfloat16* yp = y + (long long)img * hw * y_ld + cc;
+  const int step = gridDim.x * L.PL;
+  auto body = [&](const uint4& ua, const uint4& ub, int px) {
+    float v[8], u[8];
+    unpack8r(ua, v);
+    unpack8r(ub, u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j] + u[j], sc[j], sh[j]);
+    *reinterpret_cast<uint4*>(yp + (long long)px * y_ld) = pack8r(v);
+  };
+  int px = blockIdx.x * L.PL + L.pl;
+  for (; px + 3 * step < hw; px += 4 * step) {
+    uint4 ua[4], ub[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      ua[q] = __ldg(reinterpret_cast<const uint4*>(ap + (long long)(px + q * step) * a_ld));
+      ub[q] = bp ? __ldg(reinterpret_cast<const uint4*>(bp + (long long)(px + q * step) * b_ld)) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = (v[j] - mean) * invstd * __ldg(gamma + cc + j) + __ldg(beta + cc + j);
-    *reinterpret_cast<uint4*>(y + px * y_ld + cc) = pack8r(v);
+    for (int q = 0; q < 4; ++q) body(ua[q], ub[q], px + q * step);
   }
+  for (; px < hw; px += step)
+    body(__ldg(reinterpret_cast<const uint4*>(ap + (long long)px * a_ld)),
+         bp ? __ldg(reinterpret_cast<const uint4*>(bp + (long long)px * b_ld)) : make_uint4(0u, 0u, 0u, 0u), px);
 }
 
-// nn.Upsample(scale_factor=2, mode='bilinear') (align_corners=False)
-__global__ void bilinear2x_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int n, int h, int w, int c,
-                                  __nv_bfloat16* __restrict__ y, int y_ld) {
-  const int c8 = c >> 3;
+// nn.Upsample(scale_factor=2, mode='bilinear') (align_corners=False).  blockIdx.z = image, blockIdx.x covers
+// (output row, column block): no divides per element.
+__global__ void __launch_bounds__(256)
+bilinear2x_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int h, int w, int c, int xblocks,
+                  __nv_bfloat16* __restrict__ y, int y_ld) {
+  const Lanes L = lanes_of(c);
+  if (!L.active) return;
   const int H = 2 * h, W = 2 * w;
-  const long long total = (long long)n * H * W * c8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    long long px = i / c8;
-    const int cc = (int)(i - px * c8) << 3;
-    const int ox = (int)(px % W); long long t = px / W;
-    const int oy = (int)(t % H);
-    const int b = (int)(t / H);
-    const float sy = fmaxf((oy + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((ox + 0.5f) * 0.5f - 0.5f, 0.f);
-    const int y0 = (int)sy, x0 = (int)sx;
-    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
-    const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
-    const long long base = (long long)b * h * w;
-    float v00[8], v01[8], v10[8], v11[8], o[8];
-    unpack8r(__ldg(reinterpret_cast<const uint4*>(x + (base + (long long)y0 * w + x0) * x_ld + cc)), v00);
-    unpack8r(__ldg(reinterpret_cast<const uint4*>(x + (base + (long long)y0 * w + x1) * x_ld + cc)), v01);
-    unpack8r(__ldg(reinterpret_cast<const uint4*>(x + (base + (long long)y1 * w + x0) * x_ld + cc)), v10);
-    unpack8r(__ldg(reinterpret_cast<const uint4*>(x + (base + (long long)y1 * w + x1) * x_ld + cc)), v11);
+  const int b = blockIdx.z;
+  const int oy = blockIdx.x / xblocks, ox = (blockIdx.x % xblocks) * L.PL + L.pl;
+  if (ox >= W || oy >= H) return;
+  const int cc = L.g << 3;
+  const float sy = fmaxf((oy + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((ox + 0.5f) * 0.5f - 0.5f, 0.f);
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+  const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
+  const __nv_bfloat16* xb_ = x + (long long)b * h * w * x_ld + cc;
+  float v00[8], v01[8], v10[8], v11[8], o[8];
+  unpack8r(__ldg(reinterpret_cast<const uint4*>(xb_ + ((long long)y0 * w + x0) * x_ld)), v00);
+  unpack8r(__ldg(reinterpret_cast<const uint4*>(xb_ + ((long long)y0 * w + x1) * x_ld)), v01);
+  unpack8r(__ldg(reinterpret_cast<const uint4*>(xb_ + ((long long)y1 * w + x0) * x_ld)), v10);
+  unpack8r(__ldg(reinterpret_cast<const uint4*>(xb_ + ((long long)y1 * w + x1) * x_ld)), v11);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = hy * (hx * v00[j] + lx * v01[j]) + ly * (hx * v10[j] + lx * v11[j]);
-    *reinterpret_cast<uint4*>(y + px * y_ld + cc) = pack8r(o);
-  }
+  for (int j = 0; j < 8; ++j) o[j] = hy * (hx * v00[j] + lx * v01[j]) + ly * (hx * v10[j] + lx * v11[j]);
+  *reinterpret_cast<uint4*>(y + (((long long)b * H + oy) * W + ox) * y_ld + cc) = pack8r(o);
 }
 
 struct RtmAnchors { float w[8]; float h[8]; };
@@ -209,9 +275,21 @@ extern "C" int uavdet_dwdynconv_fwd(const uavdet_act* x, const float* channel_w,
   if ((rc = chk(x, "dwdynconv x")) || (rc = chk(y, "dwdynconv y"))) return rc;
   UAVDET_CHECK_ARG(channel_w && kernel_w && k >= 1 && k <= 7 && 2 * pad == k - 1, "dwdynconv: bad arguments (k=%d pad=%d)", k, pad);
   UAVDET_CHECK_ARG(x->n == y->n && x->h == y->h && x->w == y->w && x->c == y->c, "dwdynconv: shape mismatch");
-  long long total = (long long)x->n * x->h * x->w * (x->c / 8);
-  dwdynconv_kernel<<<rtm_grid(total, 256), 256, 0, ST>>>((const __nv_bfloat16*)x->ptr, x->ld, x->n, x->h, x->w, x->c,
-                                                        channel_w, kernel_w, k, pad, (__nv_bfloat16*)y->ptr, y->ld);
+  const int G = x->c / 8, Gb = G < 32 ? G : 32, PL = 256 / Gb;
+  const int xblocks = ceil_div(x->w, PL);
+  int rows = 16;
+  while (rows > 4 && (long long)xblocks * ceil_div(x->h, rows) * ceil_div(G, Gb) * x->n < 4 * kNumSMs) rows >>= 1;
+  dim3 grid((unsigned)(xblocks * ceil_div(x->h, rows)), (unsigned)ceil_div(G, Gb), (unsigned)x->n);
+  const __nv_bfloat16* xp = (const __nv_bfloat16*)x->ptr;
+  __nv_bfloat16* yp = (__nv_bfloat16*)y->ptr;
+#define UAVDET_DW(KS) dwdynconv_kernel<KS><<<grid, 256, 0, ST>>>(xp, x->ld, x->h, x->w, x->c, channel_w, kernel_w, xblocks, rows, yp, y->ld)
+  switch (k) {
+    case 1: UAVDET_DW(1); break;
+    case 3: UAVDET_DW(3); break;
+    case 5: UAVDET_DW(5); break;
+    default: UAVDET_DW(7); break;
+  }
+#undef UAVDET_DW
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }
@@ -234,12 +312,15 @@ extern "C" int uavdet_groupnorm1(const uavdet_act* a, const uavdet_act* b, const
   UAVDET_CHECK_ARG(a->n == y->n && a->h == y->h && a->w == y->w && a->c == y->c, "groupnorm: shape mismatch");
   if (b) UAVDET_CHECK_ARG(a->n == b->n && a->h == b->h && a->w == b->w && a->c == b->c, "groupnorm: residual shape mismatch");
   UAVDET_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * a->n, ST));
-  const long long hw = (long long)a->h * a->w;
-  long long bx = (hw * (a->c / 8) + 256 * 8 - 1) / (256 * 8);
-  long long cap = (kNumSMs * 8) / (a->n > 0 ? a->n : 1) + 1;
+  const long long hw64 = (long long)a->h * a->w;
+  UAVDET_CHECK_ARG(hw64 < (1ll << 30), "groupnorm: map too large");
+  const int hw = (int)hw64;
+  const int G = a->c / 8, Gb = G < 32 ? G : 32, PL = 256 / Gb, gy = ceil_div(G, Gb);
+  long long bx = ceil_div(hw, PL * 4);
+  long long cap = ((long long)kNumSMs * 16) / ((long long)a->n * gy) + 1;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
-  dim3 grid((unsigned)bx, (unsigned)a->n);
+  dim3 grid((unsigned)bx, (unsigned)gy, (unsigned)a->n);
   const __nv_bfloat16* bp = b ? (const __nv_bfloat16*)b->ptr : nullptr;
   gn_stats_kernel<<<grid, 256, 0, ST>>>((const __nv_bfloat16*)a->ptr, a->ld, bp, b ? b->ld : 0, hw, a->c, stats_ws);
   UAVDET_LAUNCH_CHECK();
@@ -253,9 +334,11 @@ extern "C" int uavdet_bilinear2x_fwd(const uavdet_act* x, const uavdet_act* y, v
   int rc;
   if ((rc = chk(x, "bilinear2x x")) || (rc = chk(y, "bilinear2x y"))) return rc;
   UAVDET_CHECK_ARG(y->n == x->n && y->h == 2 * x->h && y->w == 2 * x->w && y->c == x->c, "bilinear2x: shapes");
-  long long total = (long long)y->n * y->h * y->w * (y->c / 8);
-  bilinear2x_kernel<<<rtm_grid(total, 256), 256, 0, ST>>>((const __nv_bfloat16*)x->ptr, x->ld, x->n, x->h, x->w, x->c,
-                                                         (__nv_bfloat16*)y->ptr, y->ld);
+  const int G = x->c / 8, Gb = G < 32 ? G : 32, PL = 256 / Gb;
+  const int xblocks = ceil_div(y->w, PL);
+  dim3 grid((unsigned)(xblocks * y->h), (unsigned)ceil_div(G, Gb), (unsigned)y->n);
+  bilinear2x_kernel<<<grid, 256, 0, ST>>>((const __nv_bfloat16*)x->ptr, x->ld, x->h, x->w, x->c, xblocks,
+                                          (__nv_bfloat16*)y->ptr, y->ld);
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }
