@@ -134,15 +134,18 @@ __device__ __noinline__ void stage_chunk(const IgemmParams& P, uint32_t taddr, i
 
 // MMA issue loop of one CTA (single elected thread), KSTEPS = block_k / 16.
 template <int KSTEPS>
-__device__ __forceinline__ void mma_issue_loop(const IgemmParams& P, uint32_t smem_base, uint32_t full_bar,
-                                               uint32_t empty_bar, uint32_t tfull_bar, uint32_t tempty_bar,
-                                               uint32_t tmem_base, int a_bytes, int stage_bytes, int num_kb,
-                                               volatile uint32_t* dead) {
+__device__ __forceinline__ void mma_issue_loop(const IgemmParams& P, uint32_t ring_base, uint32_t bres_base,
+                                               uint32_t full_bar, uint32_t empty_bar, uint32_t tfull_bar,
+                                               uint32_t tempty_bar, uint32_t tmem_base, int a_bytes, int b_bytes,
+                                               int stage_bytes, int num_kb, volatile uint32_t* dead) {
   const uint32_t idesc = make_idesc_bf16(P.block_n, 0, 0);
   const uint32_t layout = (KSTEPS == 4) ? 2u : 4u;            // SWIZZLE_128B : SWIZZLE_64B
   const uint32_t sbo = 8u * (uint32_t)(KSTEPS * 16) * 2u;     // 8 rows of one swizzle atom
-  const uint64_t a0 = make_smem_desc(smem_base, 16, sbo, layout);
-  const uint64_t b0 = make_smem_desc(smem_base + (uint32_t)a_bytes, 16, sbo, layout);
+  const bool bres = P.bres_bytes > 0;
+  const uint64_t a0 = make_smem_desc(ring_base, 16, sbo, layout);
+  // B: inside the stage (after A), or tile kb of the resident weight region
+  const uint64_t b0 = make_smem_desc(bres ? bres_base : ring_base + (uint32_t)a_bytes, 16, sbo, layout);
+  const uint32_t b_step = (uint32_t)b_bytes >> 4;
   const uint32_t stage_step = (uint32_t)stage_bytes >> 4;
   const uint32_t last_stage = (uint32_t)P.stages - 1u;
   uint32_t stage = 0, phase = 0, soff = 0;
@@ -157,7 +160,7 @@ __device__ __forceinline__ void mma_issue_loop(const IgemmParams& P, uint32_t sm
     for (int kb = 0; kb < num_kb; ++kb) {
       mbar_wait(full_bar + 8u * stage, phase, dead, P.watchdog, 0x4u);
       tc_fence_after();
-      const uint64_t ad = a0 + (uint64_t)soff, bd = b0 + (uint64_t)soff;
+      const uint64_t ad = a0 + (uint64_t)soff, bd = b0 + (uint64_t)(bres ? (uint32_t)kb * b_step : soff);
 #pragma unroll
       for (int k = 0; k < KSTEPS; ++k) {
         // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the >>4 field
@@ -186,15 +189,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 
   const int a_bytes = 128 * P.block_k * 2;             // smem reserved for A per stage
   const int b_bytes = P.block_n * P.block_k * 2;
-  const int stage_bytes = a_bytes + b_bytes;
+  // Weights small enough to stay in shared memory for the whole kernel (thin layers, 1x1 convs up to 256->128) are
+  // loaded once: [resident B: one tile per k-block][stages x A]; otherwise every stage carries its B tile.
+  const bool bres = P.bres_bytes > 0;
+  const int stage_bytes = bres ? a_bytes : a_bytes + b_bytes;
   const int a_tx = P.tile_w * P.tile_h * P.block_k * 2;  // bytes the A box actually delivers
-  uint8_t* staging = smem + (size_t)P.stages * stage_bytes;  // output staging, 1024-aligned (stage_bytes is)
+  uint8_t* ring = smem + P.bres_bytes;                   // pipeline stages (1024-aligned: tiles are multiples of 1 KB)
+  uint8_t* staging = ring + (size_t)P.stages * stage_bytes;  // output staging
   uint8_t* ctrl = staging + P.staging_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* bres_bar = tempty_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
   volatile uint32_t* dead = tmem_ptr + 1;
 
   if (threadIdx.x == 0) {
@@ -202,6 +210,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
+    mbar_init(smem_u32(bres_bar), 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);
       // arrivals per tile: all 8 epilogue warps, or only the 4 that own the accumulator buffer when a tile is a
@@ -239,6 +248,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       uint32_t stage = (uint32_t)warp, phase = 0;
       int cur_tile = -1;
       TileCoord tc{0, 0, 0, 0};
+      if (bres && warp == 0) {
+        // resident weights: every (tap, channel chunk) tile once (n_tiles == 1, one weight matrix for all images)
+        const uint32_t bb = smem_u32(bres_bar);
+        mbar_arrive_expect_tx(bb, (uint32_t)P.bres_bytes);
+        for (int t = 0, kbi = 0; t < P.num_taps; ++t)
+          for (int kc = 0; kc < kcpt; ++kc, ++kbi)
+            tma_load_3d(smem_u32(smem + (size_t)kbi * b_bytes), &mapB, bb, P.taps[t].w_koff + kc * P.block_k, 0, 0);
+      }
       while (true) {
         while (kb >= num_kb) { kb -= num_kb; tile += gridDim.x; }
         if (tile >= P.total_tiles) break;
@@ -248,11 +265,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         const ConvTap tap = P.taps[t];
         mbar_wait<32>(smem_u32(&empty_bar[stage]), phase ^ 1u, dead, P.watchdog, 0x1u);
         const uint32_t fb = smem_u32(&full_bar[stage]);
-        mbar_arrive_expect_tx(fb, (uint32_t)(a_tx + b_bytes));
-        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+        mbar_arrive_expect_tx(fb, (uint32_t)(bres ? a_tx : a_tx + b_bytes));
+        uint8_t* sa = ring + (size_t)stage * stage_bytes;
         tma_load_5d(smem_u32(sa), &mapA, fb, tap.c_off + kc * P.block_k, tc.ow0 + tap.dw, tap.p, tc.oh0 + tap.dh,
                     tc.img);
-        tma_load_3d(smem_u32(sa + a_bytes), &mapB, fb, tap.w_koff + kc * P.block_k, tc.n0, P.w_batch > 1 ? tc.img : 0);
+        if (!bres)
+          tma_load_3d(smem_u32(sa + a_bytes), &mapB, fb, tap.w_koff + kc * P.block_k, tc.n0, P.w_batch > 1 ? tc.img : 0);
         kb += pw;
         stage += (uint32_t)pw;
         if (stage >= (uint32_t)P.stages) { stage -= (uint32_t)P.stages; phase ^= 1u; }
@@ -265,10 +283,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     // K-step offset in their (address >> 4) field, barrier addresses advance incrementally, the K-step loop is
     // unrolled at compile time.
     if (elect_one()) {
-      if (P.block_k == 64) mma_issue_loop<4>(P, smem_u32(smem), smem_u32(full_bar), smem_u32(empty_bar), smem_u32(tfull_bar),
-                                             smem_u32(tempty_bar), tmem_base, a_bytes, stage_bytes, num_kb, dead);
-      else mma_issue_loop<2>(P, smem_u32(smem), smem_u32(full_bar), smem_u32(empty_bar), smem_u32(tfull_bar),
-                             smem_u32(tempty_bar), tmem_base, a_bytes, stage_bytes, num_kb, dead);
+      if (bres) {
+        mbar_wait(smem_u32(bres_bar), 0, dead, P.watchdog, 0x80u);      // resident weights have landed
+        tc_fence_after();
+      }
+      if (P.block_k == 64) mma_issue_loop<4>(P, smem_u32(ring), smem_u32(smem), smem_u32(full_bar), smem_u32(empty_bar),
+                                             smem_u32(tfull_bar), smem_u32(tempty_bar), tmem_base, a_bytes, b_bytes,
+                                             stage_bytes, num_kb, dead);
+      else mma_issue_loop<2>(P, smem_u32(ring), smem_u32(smem), smem_u32(full_bar), smem_u32(empty_bar), smem_u32(tfull_bar),
+                             smem_u32(tempty_bar), tmem_base, a_bytes, b_bytes, stage_bytes, num_kb, dead);
     }
   } else {
     // ============================ epilogue (8 warps) =======================
@@ -764,18 +787,23 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
   P.fd_w = make_fast_div(P.tiles_w);
   P.fd_h = make_fast_div(P.tiles_h);
   P.w_batch = w_batch;
-  // shared memory: [stages x (A + B)] [output staging] [barriers]
-  const int stage_bytes = 128 * P.block_k * 2 + P.block_n * P.block_k * 2;
-  const int ctrl_bytes = 8 * (2 * kMaxStages + 4) + 64;
+  // shared memory: [resident weights] [stages x (A [+ B])] [output staging] [barriers]
+  const int a_stage = 128 * P.block_k * 2, b_tile = P.block_n * P.block_k * 2;
+  const long long b_total = (long long)P.num_taps * P.kc_per_tap * b_tile;
+  P.bres_bytes = 0;
+  if (w_batch == 1 && P.n_tiles == 1 && b_total <= 80 * 1024 && P.total_tiles > 2 * kNumSMs) P.bres_bytes = (int)b_total;
+  const int stage_bytes = P.bres_bytes ? a_stage : a_stage + b_tile;
+  const int ctrl_bytes = 8 * (2 * kMaxStages + 5) + 64;
   const int max_smem = 227 * 1024;
+  const int avail = max_smem - P.bres_bytes;
   const int staging1 = 2 * 128 * P.slab_w * 2;      // CTA-wide: 2 slabs; warp-private: 8 warps x 1 buffer
   P.epi_bufs = 1;
   P.staging_bytes = (P.epi == UAVDET_EPI_HEAD) ? 0 : staging1;
-  if (P.epi_mode != 0 && (max_smem - ctrl_bytes - 2 * staging1) / stage_bytes >= 4) {
+  if (P.epi_mode != 0 && (avail - ctrl_bytes - 2 * staging1) / stage_bytes >= 4) {
     P.epi_bufs = 2;
     P.staging_bytes = 2 * staging1;
   }
-  int stages = (max_smem - ctrl_bytes - P.staging_bytes) / stage_bytes;
+  int stages = (avail - ctrl_bytes - P.staging_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   UAVDET_CHECK_ARG(stages >= 2, "igemm: tile does not fit shared memory");
   if (stages >= 8) { stages &= ~3; P.prod_warps = 4; }

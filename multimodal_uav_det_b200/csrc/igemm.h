@@ -44,6 +44,7 @@ struct IgemmParams {
   int epi_bufs;         // staging buffers per epilogue warp (modes 1/2)
   int staging_bytes;    // shared memory reserved for output staging
   int prod_warps;       // active TMA producer warps (1 | 2 | 4), divides `stages`
+  int bres_bytes;       // > 0: the whole weight matrix stays resident in shared memory (bytes); stages hold A only
   FastDiv fd_n, fd_w, fd_h;   // dividers for the tile decode (n_tiles, tiles_w, tiles_h)
   int epi, act;
   const float* scale;
