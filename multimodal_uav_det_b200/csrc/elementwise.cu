@@ -866,6 +866,19 @@ extern "C" int uavdet_bn_act_fwd(const uavdet_act* raw, const float* scale, cons
   return UAVDET_OK;
 }
 
+
+// The BatchNorm-backward kernels run concurrently with the weight-gradient kernel of the previous layer (another
+// stream).  Two kernels share an SM only if they agree on its L1 / shared-memory split, so these streaming kernels
+// ask for the maximum-shared-memory carveout the tensor-core kernels use (they do not need the L1).
+static void prefer_max_smem_carveout_once() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(bn_bwd_apply_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(bn_bwd_apply_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 extern "C" int uavdet_bn_act_bwd_reduce(const uavdet_act* dy, const uavdet_act* raw, const float* scale,
                                         const float* shift, int act, float* sum_dz, float* sum_dzr,
                                         void* stream) {
@@ -874,6 +887,7 @@ extern "C" int uavdet_bn_act_bwd_reduce(const uavdet_act* dy, const uavdet_act* 
       (rc = same_shape(dy, raw, "bn_bwd_reduce")))
     return rc;
   UAVDET_CHECK_ARG(scale && shift && sum_dz && sum_dzr, "bn_bwd_reduce: null stats");
+  prefer_max_smem_carveout_once();
   bn_bwd_reduce_kernel<<<stream_grid(dy, 16), 256, 0, ST>>>(mkview(dy), mkview(raw), scale, shift, act, sum_dz,
                                                             sum_dzr);
   UAVDET_LAUNCH_CHECK();

@@ -381,7 +381,10 @@ extern "C" int uavdet_conv_wgrad(const uavdet_act* x, const uavdet_act* dy, int 
   }
 
   // ---- N per tap, columns per CTA (TMEM: taps x cin_blk <= 512 columns; smem: >= 3 pipeline stages) ----
-  const int max_smem = 227 * 1024;
+  // The kernel asks for only ~176 KB so that HBM-bound blocks of another stream (the BatchNorm backward of the
+  // next layer, which the engine runs concurrently) can share the SM: tensor work and streaming work overlap.
+  static const int smem_budget_kb = getenv("UAVDET_WGRAD_SMEM_KB") ? atoi(getenv("UAVDET_WGRAD_SMEM_KB")) : 176;
+  const int max_smem = smem_budget_kb * 1024;
   const int ctrl_bytes = 8 * (2 * kMaxStages + 1) + 16 + 4 * 32 * 33 * 4;   // barriers + per-warp transpose scratch
   P.a_bytes = 128 * P.kp_pad * 2;
   int max_nv = 0;
@@ -466,11 +469,15 @@ extern "C" int uavdet_conv_wgrad(const uavdet_act* x, const uavdet_act* dy, int 
   }
   static bool attr_set = false;
   if (!attr_set) {
-    UAVDET_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    UAVDET_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    // same L1 / shared-memory split as the streaming kernels that share the SM with this one (see elementwise.cu)
+    UAVDET_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
   dim3 grid((unsigned)(P.items * P.k_splits), (unsigned)samples);
-  wgrad_kernel<<<grid, kWgradThreads, max_smem, (cudaStream_t)stream>>>(mapDY, mapX[0], mapX[1], mapX[2], P);
+  const int smem_bytes = P.stages * P.stage_bytes + ctrl_bytes;
+  wgrad_kernel<<<grid, kWgradThreads, smem_bytes, (cudaStream_t)stream>>>(mapDY, mapX[0], mapX[1], mapX[2], P);
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }

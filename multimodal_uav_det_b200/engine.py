@@ -11,6 +11,7 @@ would, so torch optimizers / Lightning / the DP bucket reducer all see ordinary 
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Tuple
 
@@ -198,6 +199,10 @@ class Executor:
 
     def __init__(self):
         self.packs = PackCache()
+        # weight gradients on a side stream (joined in end_backward); UAVDET_NO_WGRAD_OVERLAP=1 keeps them in line
+        self.overlap_wgrad = not os.environ.get("UAVDET_NO_WGRAD_OVERLAP")
+        self._side: Optional[torch.cuda.Stream] = None
+        self._side_keep: list = []
         self._zero_arena: Optional[torch.Tensor] = None
         self._zero_cursor = 0
         self._zero_need = 0
@@ -345,8 +350,39 @@ class Executor:
                 d_raw = ops.bn_act_fwd(d_pre, rec.scale, None, "none")
             else:
                 d_raw = d_pre
-        # weight gradient
+        # data gradient first (it is the critical path of backward) ...
+        dx = None
+        if need_dx and not u.stem:
+            if u.s2d:
+                raise NotImplementedError("dgrad through the fused space-to-depth gather")
+            wt = self.packs.get(w, transposed=True)
+            dx = ops.conv_dgrad(d_raw, wt, w.shape[1], u.k, u.stride, u.pad, rec.in_hw, res=res, out=out)
+        # ... then the weight gradient: nothing downstream in backward depends on it, so it goes to a side stream
+        # where its tensor-core work overlaps the HBM-bound BatchNorm backward of the next layer (the kernel
+        # leaves shared memory for those blocks to share the SM)
         if w.requires_grad:
+            side = self._wgrad_stream(d_raw.device)
+            if side is not None:
+                side.wait_stream(torch.cuda.current_stream())
+                self._side_keep.append((rec.x, d_raw))          # keep the operands alive until the join
+                with torch.cuda.stream(side):
+                    self._weight_grad(rec, u, w, d_raw)
+            else:
+                self._weight_grad(rec, u, w, d_raw)
+        return dx
+
+    def _wgrad_stream(self, device):
+        if not self.overlap_wgrad or device.type != "cuda":
+            return None
+        if self._side is None or self._side.device != device:
+            # high priority: when its CTAs and the (thousands of) BatchNorm blocks of the main stream are both
+            # pending, the block scheduler must place the weight-gradient CTAs first or they would only start
+            # once the streaming kernel has drained
+            self._side = torch.cuda.Stream(device=device, priority=-1)
+        return self._side
+
+    def _weight_grad(self, rec: ConvRecord, u: ConvUnit, w: torch.Tensor, d_raw: torch.Tensor) -> None:
+        if True:    # (block kept at this indentation: it runs under the side-stream context of the caller)
             gbuf, _ = grad_buffer(w)
             if u.stem and rec.x.dtype == torch.bfloat16:
                 # im2col stem: a 1x1 weight gradient over the 32 patch channels; the first cin*k*k columns are dW
@@ -368,12 +404,6 @@ class Executor:
                     ops.unpack_wgrad(dwp, w.shape[0], w.shape[1], u.k, grad=gbuf, accumulate=True)
             if self.grad_ready_hook is not None:
                 self.grad_ready_hook(w)
-        if not need_dx or u.stem:
-            return None
-        if u.s2d:
-            raise NotImplementedError("dgrad through the fused space-to-depth gather")
-        wt = self.packs.get(w, transposed=True)
-        return ops.conv_dgrad(d_raw, wt, w.shape[1], u.k, u.stride, u.pad, rec.in_hw, res=res, out=out)
 
     # ---- dynamic-kernel convolution ----------------------------------------------------------------
     def dyn_forward(self, sp: DynSpec, x: torch.Tensor, train: bool, tape: Optional[list]) -> torch.Tensor:
@@ -513,7 +543,11 @@ class Executor:
         return t.float().sum(dim=(0, 1, 2))
 
     def end_backward(self):
-        """Flush the small per-channel gradients (BN affine, biases) in one multi-tensor pass."""
+        """Join the weight-gradient stream, then flush the small per-channel gradients (BN affine, biases) in one
+        multi-tensor pass."""
+        if self._side is not None and self._side_keep:
+            torch.cuda.current_stream().wait_stream(self._side)
+        self._side_keep = []
         if not self._bn_grads:
             return
         acc_p, acc_g = [], []
