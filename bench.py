@@ -357,7 +357,11 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
             step(x_dev, tg_dev)
         else:
+            # kernels are timed one at a time: the weight gradients stay in line for this capture (in the timed
+            # graph they run on a side stream under the BatchNorm backward, which would smear the stamps)
+            model._exec.overlap_wgrad = False
             instrumented = GraphedTrainStep(model, trainer, x_dev, tg_dev, warmup=0)
+            model._exec.overlap_wgrad = True
             instrumented()
             ct.stamps.zero_()
             instrumented()

@@ -4,6 +4,7 @@
 // Reference sites: BaselineModel.py:14-22 (BN+LeakyReLU), _base.py:19-20,50,75 (BN+SiLU/ReLU),
 // BaselineModel.py:43 (residual), BaselineModel.py:86,120-122 (Upsample+cat), _base.py:292 (SGD).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace uavdet {
 
@@ -98,11 +99,11 @@ __device__ __forceinline__ PixLane pix_lane(int channels) {
   L.active = g < G && pl < PL;
   return L;
 }
-static dim3 stream_grid(const uavdet_act* v, int unroll) {
+static dim3 stream_grid(const uavdet_act* v, int unroll, int blocks_per_sm = 16) {
   int G = v->c / 8, Gb = G < 32 ? G : 32, PL = 256 / Gb;
   long long npix = (long long)v->n * v->h * v->w;
   long long bx = (npix + (long long)PL * unroll - 1) / ((long long)PL * unroll);
-  long long cap = ((long long)kNumSMs * 16) / ceil_div(G, Gb);
+  long long cap = ((long long)kNumSMs * blocks_per_sm) / ceil_div(G, Gb);
   if (cap < kNumSMs) cap = kNumSMs;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
@@ -888,7 +889,10 @@ extern "C" int uavdet_bn_act_bwd_reduce(const uavdet_act* dy, const uavdet_act* 
     return rc;
   UAVDET_CHECK_ARG(scale && shift && sum_dz && sum_dzr, "bn_bwd_reduce: null stats");
   prefer_max_smem_carveout_once();
-  bn_bwd_reduce_kernel<<<stream_grid(dy, 16), 256, 0, ST>>>(mkview(dy), mkview(raw), scale, shift, act, sum_dz,
+  // few long-lived blocks: every block ends with one atomic per channel sum, and thousands of blocks hammering
+  // the same 2*c addresses serialise in L2 (the kernel ran at 1.5 TB/s with 1,600 blocks)
+  static const int bps = getenv("UAVDET_BN_REDUCE_BPS") ? atoi(getenv("UAVDET_BN_REDUCE_BPS")) : 2;
+  bn_bwd_reduce_kernel<<<stream_grid(dy, 16, bps), 256, 0, ST>>>(mkview(dy), mkview(raw), scale, shift, act, sum_dz,
                                                             sum_dzr);
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
