@@ -21,7 +21,6 @@
 #include "common.cuh"
 #include "sm100.cuh"
 #include "igemm.h"
-#include <stdlib.h>
 
 namespace uavdet {
 using namespace sm100;
@@ -178,72 +177,8 @@ __device__ __forceinline__ void mma_issue_loop(const IgemmParams& P, uint32_t ri
   }
 }
 
-// Shared-column variant: one A stage (a column box) feeds nv taps; weight tiles come from their own ring (or the
-// resident region).  Same hoisting rules as mma_issue_loop.
-template <int KSTEPS>
-__device__ __forceinline__ void mma_issue_loop_share(const IgemmParams& P, uint32_t ring_a, uint32_t ring_b,
-                                                     uint32_t bres_base, uint32_t afull, uint32_t aempty,
-                                                     uint32_t bfull, uint32_t bempty, uint32_t tfull_bar,
-                                                     uint32_t tempty_bar, uint32_t tmem_base, int b_bytes,
-                                                     volatile uint32_t* dead) {
-  const uint32_t idesc = make_idesc_bf16(P.block_n, 0, 0);
-  const uint32_t layout = (KSTEPS == 4) ? 2u : 4u;
-  const uint32_t row_bytes = (uint32_t)(KSTEPS * 16) * 2u;
-  const uint32_t sbo = 8u * row_bytes;
-  const bool bres = P.bres_bytes > 0;
-  const uint64_t a0 = make_smem_desc(ring_a, 16, sbo, layout);
-  const uint64_t b0 = make_smem_desc(bres ? bres_base : ring_b, 16, sbo, layout);
-  const uint32_t b_step = (uint32_t)b_bytes >> 4;
-  const uint32_t a_step = (uint32_t)P.a_stage_bytes >> 4;
-  const uint32_t v_step = ((uint32_t)P.tile_w * row_bytes) >> 4;     // one tile row of pixels further down
-  const uint32_t last_a = (uint32_t)P.a_stages - 1u, last_b = (uint32_t)P.stages - 1u;
-  const int kcpt = P.kc_per_tap;
-  uint32_t sa = 0, pa = 0, aoff = 0, sb = 0, pb = 0, boff = 0;
-  uint32_t acc = 0, acc_phase = 0;
-  for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-    mbar_wait(tempty_bar + 8u * acc, acc_phase ^ 1u, dead, P.watchdog, 0x2u);
-    tc_fence_after();
-    const uint32_t d_tmem = tmem_base + acc * (uint32_t)kAccStride;
-    uint32_t accumulate = 0;
-    for (int c = 0; c < P.num_cols; ++c) {
-      const int nv = P.cols[c].nv, tap0 = P.cols[c].tap0;
-      for (int kc = 0; kc < kcpt; ++kc) {
-        mbar_wait(afull + 8u * sa, pa, dead, P.watchdog, 0x4u);
-        tc_fence_after();
-        uint64_t ad = a0 + (uint64_t)aoff;
-        for (int v = 0; v < nv; ++v) {
-          uint64_t bd;
-          if (bres) {
-            bd = b0 + (uint64_t)((uint32_t)((tap0 + v) * kcpt + kc) * b_step);
-          } else {
-            mbar_wait(bfull + 8u * sb, pb, dead, P.watchdog, 0x100u);
-            tc_fence_after();
-            bd = b0 + (uint64_t)boff;
-          }
-#pragma unroll
-          for (int k = 0; k < KSTEPS; ++k) {
-            tc_mma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, accumulate);
-            accumulate = 1u;
-          }
-          if (!bres) {
-            tc_commit(bempty + 8u * sb);
-            if (sb == last_b) { sb = 0; pb ^= 1u; boff = 0; } else { ++sb; boff += b_step; }
-          }
-          ad += (uint64_t)v_step;
-        }
-        tc_commit(aempty + 8u * sa);
-        if (sa == last_a) { sa = 0; pa ^= 1u; aoff = 0; } else { ++sa; aoff += a_step; }
-      }
-    }
-    tc_commit(tfull_bar + 8u * acc);
-    acc ^= 1u;
-    if (acc == 0) acc_phase ^= 1u;
-  }
-}
-
 __global__ void __launch_bounds__(kIgemmThreads, 1)
-igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA1,
-             const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB,
+igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
              const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapOutTail,
              const __grid_constant__ IgemmParams P) {
   // 1024-byte alignment is what SWIZZLE_128B needs for TMA and UMMA; no static shared memory is used,
@@ -259,19 +194,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   const bool bres = P.bres_bytes > 0;
   const int stage_bytes = bres ? a_bytes : a_bytes + b_bytes;
   const int a_tx = P.tile_w * P.tile_h * P.block_k * 2;  // bytes the A box actually delivers
-  // shared-column mode: [resident B][A ring: a_stages column boxes][B ring: stages weight tiles]
   uint8_t* ring = smem + P.bres_bytes;                   // pipeline stages (1024-aligned: tiles are multiples of 1 KB)
-  uint8_t* ring_b = ring + (size_t)P.a_stages * P.a_stage_bytes;
-  uint8_t* staging = P.share ? ring_b + (size_t)P.stages * b_bytes : ring + (size_t)P.stages * stage_bytes;
+  uint8_t* staging = ring + (size_t)P.stages * stage_bytes;  // output staging
   uint8_t* ctrl = staging + P.staging_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* bres_bar = tempty_bar + 2;
-  uint64_t* afull_bar = bres_bar + 1;      // A ring of the shared-column mode (<= kMaxStages stages)
-  uint64_t* aempty_bar = afull_bar + kMaxStages;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aempty_bar + kMaxStages);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
   volatile uint32_t* dead = tmem_ptr + 1;
 
   if (threadIdx.x == 0) {
@@ -280,10 +211,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     mbar_init(smem_u32(bres_bar), 1);
-    for (int s2 = 0; s2 < P.a_stages; ++s2) {
-      mbar_init(smem_u32(&afull_bar[s2]), 1);
-      mbar_init(smem_u32(&aempty_bar[s2]), 1);
-    }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);
       // arrivals per tile: all 8 epilogue warps, or only the 4 that own the accumulator buffer when a tile is a
@@ -313,55 +240,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     // k-block g (counted across this CTA's tiles) belongs to producer warp g % prod_warps; `stages` is a
     // multiple of prod_warps, so a pipeline stage is always refilled by the same warp (program order keeps the
     // two uses of its empty barrier apart).
-    if (P.share) {
-      if (warp < 2 && elect_one()) {
-        const int kcpt = P.kc_per_tap;
-        if (warp == 0) {
-          // ---- A producer: one column box per (column, channel chunk) ----
-          if (bres) {
-            const uint32_t bb = smem_u32(bres_bar);
-            mbar_arrive_expect_tx(bb, (uint32_t)P.bres_bytes);
-            for (int t = 0, kbi = 0; t < P.num_taps; ++t)
-              for (int kc = 0; kc < kcpt; ++kc, ++kbi)
-                tma_load_3d(smem_u32(smem + (size_t)kbi * b_bytes), &mapB, bb, P.taps[t].w_koff + kc * P.block_k, 0, 0);
-          }
-          uint32_t sa = 0, pa = 0;
-          for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-            const TileCoord tc = decode_tile(P, tile);
-            for (int c = 0; c < P.num_cols; ++c) {
-              const ConvCol col = P.cols[c];
-              const CUtensorMap* ma = col.map == 0 ? &mapA : (col.map == 1 ? &mapA1 : &mapA2);
-              for (int kc = 0; kc < kcpt; ++kc) {
-                mbar_wait<32>(smem_u32(&aempty_bar[sa]), pa ^ 1u, dead, P.watchdog, 0x1u);
-                const uint32_t fb = smem_u32(&afull_bar[sa]);
-                mbar_arrive_expect_tx(fb, (uint32_t)col.tx);
-                tma_load_5d(smem_u32(ring + (size_t)sa * P.a_stage_bytes), ma, fb, col.c_off + kc * P.block_k,
-                            tc.ow0 + col.dw, col.p, tc.oh0 + col.dh0, tc.img);
-                if (++sa == (uint32_t)P.a_stages) { sa = 0; pa ^= 1u; }
-              }
-            }
-          }
-        } else if (!bres) {
-          // ---- B producer: one weight tile per (tap, channel chunk), in the order the MMA thread consumes them ----
-          uint32_t sb = 0, pb = 0;
-          for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-            const TileCoord tc = decode_tile(P, tile);
-            for (int c = 0; c < P.num_cols; ++c) {
-              const int nv = P.cols[c].nv, tap0 = P.cols[c].tap0;
-              for (int kc = 0; kc < kcpt; ++kc)
-                for (int v = 0; v < nv; ++v) {
-                  mbar_wait<32>(smem_u32(&empty_bar[sb]), pb ^ 1u, dead, P.watchdog, 0x200u);
-                  const uint32_t fb = smem_u32(&full_bar[sb]);
-                  mbar_arrive_expect_tx(fb, (uint32_t)b_bytes);
-                  tma_load_3d(smem_u32(ring_b + (size_t)sb * b_bytes), &mapB, fb, P.taps[tap0 + v].w_koff + kc * P.block_k,
-                              tc.n0, P.w_batch > 1 ? tc.img : 0);
-                  if (++sb == (uint32_t)P.stages) { sb = 0; pb ^= 1u; }
-                }
-            }
-          }
-        }
-      }
-    } else if (warp < P.prod_warps && elect_one()) {
+    if (warp < P.prod_warps && elect_one()) {
       const int pw = P.prod_warps;
       const int kcpt = P.kc_per_tap;
       int tile = blockIdx.x;
@@ -408,16 +287,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         mbar_wait(smem_u32(bres_bar), 0, dead, P.watchdog, 0x80u);      // resident weights have landed
         tc_fence_after();
       }
-      if (P.share) {
-        if (P.block_k == 64)
-          mma_issue_loop_share<4>(P, smem_u32(ring), smem_u32(ring_b), smem_u32(smem), smem_u32(afull_bar),
-                                  smem_u32(aempty_bar), smem_u32(full_bar), smem_u32(empty_bar), smem_u32(tfull_bar),
-                                  smem_u32(tempty_bar), tmem_base, b_bytes, dead);
-        else
-          mma_issue_loop_share<2>(P, smem_u32(ring), smem_u32(ring_b), smem_u32(smem), smem_u32(afull_bar),
-                                  smem_u32(aempty_bar), smem_u32(full_bar), smem_u32(empty_bar), smem_u32(tfull_bar),
-                                  smem_u32(tempty_bar), tmem_base, b_bytes, dead);
-      } else if (P.block_k == 64) mma_issue_loop<4>(P, smem_u32(ring), smem_u32(smem), smem_u32(full_bar), smem_u32(empty_bar),
+      if (P.block_k == 64) mma_issue_loop<4>(P, smem_u32(ring), smem_u32(smem), smem_u32(full_bar), smem_u32(empty_bar),
                                              smem_u32(tfull_bar), smem_u32(tempty_bar), tmem_base, a_bytes, b_bytes,
                                              stage_bytes, num_kb, dead);
       else mma_issue_loop<2>(P, smem_u32(ring), smem_u32(smem), smem_u32(full_bar), smem_u32(empty_bar), smem_u32(tfull_bar),
@@ -870,62 +740,9 @@ static int pick_block_n(int cout) {
 int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int w_rows, int k_total,
                  int w_batch, IgemmParams& P, cudaStream_t st, int w_batch_rows = 0) {
   if (w_batch_rows <= 0) w_batch_rows = w_rows;   // rows between the weight matrices of consecutive samples
-  CUtensorMap mapA, mapA1, mapA2, mapB, mapOut, mapOutTail;
-  int rc = 0;
-  // ---- shared tap columns: taps that differ only in their vertical offset read one taller A box ----
-  static const bool no_share = getenv("UAVDET_IGEMM_NOSHARE") != nullptr;   // tuning / debug switch
-  P.share = 0; P.num_cols = 0; P.a_stages = 0; P.a_stage_bytes = 0;
-  int map_nv[3] = {1, 1, 1}, nmaps = 0, max_nv = 1;
-  if (!no_share && P.epi != UAVDET_EPI_HEAD && P.num_taps > 1 && P.tile_w % 8 == 0) {
-    ConvTap sorted[kMaxTaps];
-    bool used[kMaxTaps] = {false};
-    int ns = 0, ncols = 0;
-    bool ok = true;
-    for (int t = 0; t < P.num_taps && ok; ++t) {
-      if (used[t]) continue;
-      int members[kMaxTaps], nm = 0;
-      for (int u = t; u < P.num_taps; ++u)
-        if (!used[u] && P.taps[u].c_off == P.taps[t].c_off && P.taps[u].dw == P.taps[t].dw && P.taps[u].p == P.taps[t].p)
-          members[nm++] = u;
-      for (int a = 0; a < nm; ++a)
-        for (int b = a + 1; b < nm; ++b)
-          if (P.taps[members[b]].dh < P.taps[members[a]].dh) { int tmp = members[a]; members[a] = members[b]; members[b] = tmp; }
-      int a = 0;
-      while (a < nm) {
-        int b = a + 1;
-        while (b < nm && P.taps[members[b]].dh == P.taps[members[b - 1]].dh + 1) ++b;
-        if (ncols >= kMaxTapCols) { ok = false; break; }
-        ConvCol& col = P.cols[ncols++];
-        col.c_off = P.taps[members[a]].c_off; col.dw = P.taps[members[a]].dw; col.p = P.taps[members[a]].p;
-        col.dh0 = P.taps[members[a]].dh; col.nv = b - a; col.tap0 = ns;
-        col.tx = (P.tile_h + col.nv - 1) * P.tile_w * P.block_k * 2;
-        int m = -1;
-        for (int i = 0; i < nmaps; ++i) if (map_nv[i] == col.nv) m = i;
-        if (m < 0) { if (nmaps >= 3) { ok = false; break; } m = nmaps; map_nv[nmaps++] = col.nv; }
-        col.map = m;
-        if (col.nv > max_nv) max_nv = col.nv;
-        for (int i = a; i < b; ++i) { sorted[ns++] = P.taps[members[i]]; used[members[i]] = true; }
-        a = b;
-      }
-    }
-    const int view_h = parity ? a_src->h / 2 : a_src->h;
-    if (ok && max_nv > 1 && P.tile_h + max_nv - 1 <= view_h && P.tile_h + max_nv - 1 <= 256) {
-      for (int t = 0; t < P.num_taps; ++t) P.taps[t] = sorted[t];   // column-major order
-      P.num_cols = ncols;
-      P.share = 1;
-    }
-  }
-  if (P.share) {
-    for (int m = 0; m < 3; ++m) {
-      CUtensorMap* dst = m == 0 ? &mapA : (m == 1 ? &mapA1 : &mapA2);
-      rc = make_act_map(dst, a_src, parity, P.block_k, P.tile_w, P.tile_h + map_nv[m < nmaps ? m : 0] - 1);
-      if (rc) return rc;
-    }
-  } else {
-    rc = make_act_map(&mapA, a_src, parity, P.block_k, P.tile_w, P.tile_h);
-    if (rc) return rc;
-    mapA1 = mapA; mapA2 = mapA;
-  }
+  CUtensorMap mapA, mapB, mapOut, mapOutTail;
+  int rc = make_act_map(&mapA, a_src, parity, P.block_k, P.tile_w, P.tile_h);
+  if (rc) return rc;
   P.slab_w = (P.block_n % 64 == 0) ? 64 : 32;
   const int kp = P.tile_w * P.tile_h;
   if (P.epi == UAVDET_EPI_HEAD) {
@@ -976,7 +793,7 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
   P.bres_bytes = 0;
   if (w_batch == 1 && P.n_tiles == 1 && b_total <= 80 * 1024 && P.total_tiles > 2 * kNumSMs) P.bres_bytes = (int)b_total;
   const int stage_bytes = P.bres_bytes ? a_stage : a_stage + b_tile;
-  const int ctrl_bytes = 8 * (4 * kMaxStages + 5) + 64;
+  const int ctrl_bytes = 8 * (2 * kMaxStages + 5) + 64;
   const int max_smem = 227 * 1024;
   const int avail = max_smem - P.bres_bytes;
   const int staging1 = 2 * 128 * P.slab_w * 2;      // CTA-wide: 2 slabs; warp-private: 8 warps x 1 buffer
@@ -989,33 +806,7 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
   int stages = (avail - ctrl_bytes - P.staging_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   UAVDET_CHECK_ARG(stages >= 2, "igemm: tile does not fit shared memory");
-  if (P.share) {
-    // A ring of column boxes (the last tap of a column reads (nv-1)*tile_w rows further down) + B ring of weight tiles
-    P.a_stage_bytes = (((max_nv - 1) * P.tile_w + 128) * P.block_k * 2 + 1023) / 1024 * 1024;
-    int room = avail - ctrl_bytes - P.staging_bytes;
-    if (P.bres_bytes) {
-      int as = room / P.a_stage_bytes;
-      if (as > kMaxStages) as = kMaxStages;
-      if (as >= 2) { P.a_stages = as; stages = 0; } else P.share = 0;
-    } else {
-      int as = 3;
-      if ((room - as * P.a_stage_bytes) / b_tile < 4 && P.epi_bufs == 2) {
-        // deep weight-tile prefetch matters more than double-buffered output staging
-        P.epi_bufs = 1; P.staging_bytes = staging1; room = avail - ctrl_bytes - P.staging_bytes;
-      }
-      if ((room - as * P.a_stage_bytes) / b_tile < 4) as = 2;
-      int bs = (room - as * P.a_stage_bytes) / b_tile;
-      if (bs > kMaxStages) bs = kMaxStages;
-      if (bs >= 3) { P.a_stages = as; stages = bs; } else P.share = 0;
-    }
-    if (!P.share) {   // does not fit: fall back to one box per tap (taps stay in column-major order, which is fine)
-      P.a_stages = 0; P.a_stage_bytes = 0; P.num_cols = 0;
-      rc = make_act_map(&mapA, a_src, parity, P.block_k, P.tile_w, P.tile_h);
-      if (rc) return rc;
-    }
-  }
-  if (P.share) { P.prod_warps = 2; }
-  else if (stages >= 8) { stages &= ~3; P.prod_warps = 4; }
+  if (stages >= 8) { stages &= ~3; P.prod_warps = 4; }
   else if (stages >= 4) { P.prod_warps = (stages % 4 == 0) ? 4 : 2; stages &= ~1; }
   else { P.prod_warps = 1; }
   P.stages = stages;
@@ -1031,7 +822,7 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
   }
   if (P.total_tiles <= 0) return UAVDET_OK;
   int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
-  igemm_kernel<<<grid, kIgemmThreads, smem_bytes, st>>>(mapA, mapA1, mapA2, mapB, mapOut, mapOutTail, P);
+  igemm_kernel<<<grid, kIgemmThreads, smem_bytes, st>>>(mapA, mapB, mapOut, mapOutTail, P);
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }

@@ -33,17 +33,6 @@ inline FastDiv make_fast_div(int d) {
   return f;
 }
 
-constexpr int kMaxTapCols = 20;
-// A column = the filter taps that differ only in their vertical offset: one A box of (tile_h + nv - 1) x tile_w
-// pixels serves all nv of them (tap v reads from smem row v * tile_w on; tile_w % 8 == 0 keeps that on a swizzle-atom
-// boundary).  Used by the "shared column" main loop of igemm_kernel (and, in its own form, by wgrad_kernel).
-struct ConvCol {
-  int c_off, dw, p, dh0;   // TMA coordinates of the box origin relative to the output tile
-  int nv, tap0;            // taps in the column, index of the first one in IgemmParams::taps (column-major order)
-  int map;                 // which A tensor map (box height) loads it
-  int tx;                  // bytes the box delivers per channel chunk
-};
-
 struct IgemmParams {
   int n_img, ho, wo;
   int tile_w, tile_h, tiles_w, tiles_h;
@@ -56,8 +45,6 @@ struct IgemmParams {
   int staging_bytes;    // shared memory reserved for output staging
   int prod_warps;       // active TMA producer warps (1 | 2 | 4), divides `stages`
   int bres_bytes;       // > 0: the whole weight matrix stays resident in shared memory (bytes); stages hold A only
-  int share;            // 1: shared-column main loop — A ring of column boxes + B ring of per-tap weight tiles
-  int num_cols, a_stages, a_stage_bytes;
   FastDiv fd_n, fd_w, fd_h;   // dividers for the tile decode (n_tiles, tiles_w, tiles_h)
   int epi, act;
   const float* scale;
@@ -76,7 +63,6 @@ struct IgemmParams {
   long long* trace;     // debug: per-tile role timestamps of CTA 0 (NULL = off), 8 slots per tile
   int trace_tiles;
   ConvTap taps[kMaxTaps];
-  ConvCol cols[kMaxTapCols];
 };
 
 int encode_tensor_map(CUtensorMap* m, void* base, int rank, const uint64_t* dims,
