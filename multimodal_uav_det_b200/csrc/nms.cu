@@ -42,6 +42,13 @@ __device__ __forceinline__ float box_area(const float4& b) {
 }
 
 // i = the kept (earlier) box, j = the candidate.  torchvision/csrc/ops/cpu/nms_kernel.cpp
+// The reference decides `fl(inter / (ai + aj - inter)) > thr` with an IEEE division.  The division is ~30
+// instructions and almost every pair does not overlap at all, so the exact quotient is only formed when the
+// outcome is not already certain:
+//   * inter == 0 (no overlap): the quotient is 0, -0 or NaN -> never > thr for thr >= 0;
+//   * otherwise compare inter with p = fl(thr * u): |fl(x) - x| <= 2^-24 |x| for the product and for the
+//     quotient, so inter > p (1 + 2^-20) implies fl(inter / u) > thr and inter < p (1 - 2^-20) implies the
+//     opposite; only the sliver in between (and non-finite / denormal operands, thr < 0) takes the division.
 __device__ __forceinline__ bool iou_exceeds(const float4& bi, float ai, const float4& bj, float aj,
                                             float thr) {
   float xx1 = std_max(bi.x, bj.x);
@@ -51,7 +58,14 @@ __device__ __forceinline__ bool iou_exceeds(const float4& bi, float ai, const fl
   float w = std_max(0.f, __fsub_rn(xx2, xx1));
   float h = std_max(0.f, __fsub_rn(yy2, yy1));
   float inter = __fmul_rn(w, h);
-  float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, aj), inter));
+  if (inter == 0.f && thr >= 0.f) return false;
+  float u = __fsub_rn(__fadd_rn(ai, aj), inter);
+  if (thr > 0.f && inter > 1e-30f && inter < 1e30f && u > 1e-30f && u < 1e30f) {
+    const float p = __fmul_rn(thr, u);
+    if (inter > __fmul_rn(p, 1.00000095367431640625f)) return true;     // 1 + 2^-20
+    if (inter < __fmul_rn(p, 0.99999904632568359375f)) return false;    // 1 - 2^-20
+  }
+  float ovr = __fdiv_rn(inter, u);
   return ovr > thr;
 }
 

@@ -54,6 +54,40 @@ def detect_rtm(model, x: torch.Tensor, iou_threshold: float = 0.5, score_floor: 
     return Detections(boxes, scores, keep, count)
 
 
+class GraphedDetect:
+    """`detect` / `detect_rtm` for a fixed batch shape, captured into one CUDA graph: at batch 1 the eager path is
+    launch-bound (~90 launches from Python for 7 ms of forward on a 154 GFLOP model).
+
+        run = GraphedDetect(model, x_example, iou_threshold=0.5)
+        det = run(x)            # Detections in static buffers, overwritten by the next call
+    """
+
+    def __init__(self, model, x: torch.Tensor, iou_threshold: float = 0.5, score_floor: float = float("-inf"),
+                 warmup: int = 2):
+        self.x = x.detach().clone().float().contiguous()
+        fn = detect if hasattr(model, "yolo_head") else detect_rtm
+        if hasattr(model, "prepare_for_capture"):
+            model.prepare_for_capture()
+        body = lambda: fn(model, self.x, iou_threshold, score_floor)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=self.x.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                body()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.x.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = body()
+
+    def __call__(self, x: torch.Tensor) -> Detections:
+        if x is not self.x:
+            self.x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
 def kept_lists(det: Detections) -> List[torch.Tensor]:
     counts = det.keep_count.tolist()
     return [det.keep[b, :c] for b, c in enumerate(counts)]

@@ -550,3 +550,22 @@ def test_flat_trainer_channels_last_storage_gives_same_gradients(lib):
     worst = max(rel_l2(grads["flat"][k], grads["plain"][k]) for k in grads["plain"])
     print("channels-last vs OIHW gradient rel_l2 (worst)", worst)
     assert worst < 2e-3
+
+
+def test_graphed_detect_equals_eager_detect(lib):
+    """inference.GraphedDetect (forward + decode + NMS replayed from one CUDA graph) returns exactly what the eager
+    `detect` returns, on fresh inputs copied into its static buffer."""
+    from multimodal_uav_det_b200 import inference
+    model, _ = make("BaselineModel", SHALLOW)
+    model.route_repeats = 2
+    randomize_bn(model)
+    model = model.to(DEV).eval()
+    xs = [synth_input(2, 128, seed=900 + i).to(DEV) for i in range(3)]
+    run = inference.GraphedDetect(model, xs[0])
+    for x in xs:
+        want = inference.detect(model, x)
+        got = run(x)
+        assert torch.equal(got.keep_count, want.keep_count)
+        for b, c in enumerate(want.keep_count.tolist()):
+            assert torch.equal(got.keep[b, :c], want.keep[b, :c])
+        assert torch.equal(got.boxes, want.boxes) and torch.equal(got.scores, want.scores)
