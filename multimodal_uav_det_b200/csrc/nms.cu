@@ -1,16 +1,17 @@
 // K9 — greedy NMS, bit-exact with torchvision.ops.nms (CPU kernel semantics).
 // Replaces the call at reference model/_base.py:203.
 //
-// One CTA (1024 threads) per image runs the whole pipeline for that image:
+// One thread-block cluster (1-8 CTAs of 1024 threads, chosen from the batch size) per image:
 //   1. key build      : key = ~orderable(score)  (NaN first, -0 == +0), value = index
-//   2. stable LSD radix sort, 4 x 8-bit passes, ping-pong in the workspace
+//   2. stable LSD radix sort, 4 x 8-bit passes, ping-pong in the workspace             (CTA 0)
 //      (warp match_any ranking keeps equal keys in index order == torch stable sort)
-//   3. gather boxes into score order (float4, coalesced afterwards)
-//   4. chunked greedy suppression: 64 sorted candidates at a time
-//        a. 64x64 pair mask by warp ballot (each warp: 2 rows x 64 columns)
-//        b. serial resolve of the chunk against its own mask (lane 0 of warp 0)
-//        c. every later, still-alive candidate is tested against the <=64 boxes the
-//           chunk kept; suppressed ones are marked in a shared-memory bit array
+//   3. gather boxes into score order (float4, coalesced afterwards)                      (CTA 0)
+//   4. chunked greedy suppression, 64 sorted candidates at a time; chunk c is owned by CTA c mod cluster size
+//        a. 64x64 pair mask by warp ballot (each warp: 2 rows x 64 columns)             (owner)
+//        b. serial resolve of the chunk against its own mask                            (owner)
+//        c. the <=64 kept boxes are stored into every CTA's shared memory (DSMEM), one cluster barrier
+//        d. every CTA tests the still-alive candidates of its own later chunks against them; suppressed ones
+//           are marked in the CTA's shared-memory bit array
 // All IoU arithmetic uses explicit round-to-nearest intrinsics so no FMA contraction can
 // change a rounding relative to the CPU reference.
 #include "common.cuh"
@@ -75,13 +76,44 @@ struct NmsSmem {
   float4 cbox[kChunk];
   float carea[kChunk];
   unsigned long long cmask[kChunk];
-  float4 kbox[kChunk];
-  float karea[kChunk];
-  int nk;
-  int kept_total;
+  float4 kbox[2][kChunk];         // kept boxes of chunk c live in buffer c & 1 (written by the chunk's owner CTA
+  float karea[2][kChunk];         //  into every CTA of the cluster through distributed shared memory)
+  int nk[2];
   int n_valid;
 };
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t dsmem_addr(const void* p, uint32_t rank) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(p), r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void dsmem_st_f4(uint32_t addr, const float4& v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void dsmem_st_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// One image per thread-block CLUSTER (1, 2, 4 or 8 CTAs).  CTA 0 sorts; the suppression sweep -- the O(n * kept)
+// part -- is split over the CTAs by 64-candidate chunk (chunk c belongs to CTA c mod cluster size, which keeps
+// that chunk's `removed` bits in its own shared memory).  Per chunk: the owner resolves it and stores the kept
+// boxes into every CTA's shared memory, one cluster barrier, then every CTA sweeps its own later chunks.
 __global__ void __launch_bounds__(kNmsThreads, 1)
 nms_image_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, int n,
                  float thr, float score_floor, int64_t* __restrict__ keep,
@@ -91,7 +123,9 @@ nms_image_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
   NmsSmem& S = *reinterpret_cast<NmsSmem*>(smem_raw);
   uint32_t* removed = reinterpret_cast<uint32_t*>(smem_raw + sizeof(NmsSmem));
 
-  const int img = blockIdx.x;
+  const uint32_t ncta = cluster_nctarank();
+  const uint32_t rank = cluster_ctarank();
+  const int img = blockIdx.x / ncta;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
@@ -108,23 +142,25 @@ nms_image_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
   uint32_t* valB = valA + n_pad;
   float4* sbox = reinterpret_cast<float4*>(valB + n_pad);
 
-  // ---- 1. keys ------------------------------------------------------------------------
-  if (tid == 0) { S.n_valid = 0; S.kept_total = 0; }
+  // ---- 1. keys (CTA 0) and the count of candidates above the floor (every CTA) ------------
+  if (tid == 0) S.n_valid = 0;
   __syncthreads();
   int local_valid = 0;
   for (int i = tid; i < n; i += kNmsThreads) {
     float s = scores[i];
-    keyA[i] = score_key(s);
-    valA[i] = (uint32_t)i;
+    if (rank == 0) {
+      keyA[i] = score_key(s);
+      valA[i] = (uint32_t)i;
+    }
     local_valid += (s != s || s > score_floor) ? 1 : 0;
   }
   local_valid = __reduce_add_sync(0xffffffffu, local_valid);
   if (lane == 0 && local_valid) atomicAdd(&S.n_valid, local_valid);
 
-  // ---- 2. stable LSD radix sort -------------------------------------------------------
+  // ---- 2. stable LSD radix sort (CTA 0) ---------------------------------------------------
   uint32_t* kin = keyA; uint32_t* kout = keyB;
   uint32_t* vin = valA; uint32_t* vout = valB;
-  for (int pass = 0; pass < 4; ++pass) {
+  for (int pass = 0; pass < 4 && rank == 0; ++pass) {
     const int shift = pass * 8;
     if (tid < 256) S.bin[tid] = 0;
     __syncthreads();  // also orders the previous pass' global writes within the CTA
@@ -188,87 +224,110 @@ nms_image_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
     t = vin; vin = vout; vout = t;
   }
   __syncthreads();
-  const uint32_t* order = vin;  // after 4 passes the result is back in the A buffers
+  const uint32_t* order = valA;  // after 4 passes the result is back in the A buffers
 
-  // ---- 3. gather boxes into score order -------------------------------------------------
+  // ---- 3. gather boxes into score order (CTA 0), clear the removed bits --------------------
   const int nv = S.n_valid;
   const float4* boxes4 = reinterpret_cast<const float4*>(boxes);
-  for (int i = tid; i < nv; i += kNmsThreads) sbox[i] = boxes4[order[i]];
+  if (rank == 0)
+    for (int i = tid; i < nv; i += kNmsThreads) sbox[i] = boxes4[order[i]];
   const int n_words = (nv + 31) >> 5;
   for (int i = tid; i < n_words; i += kNmsThreads) removed[i] = 0;
-  __syncthreads();
+  // makes CTA 0's sorted boxes / order visible to the other CTAs, and guarantees every CTA of the cluster is
+  // running before any distributed-shared-memory store below
+  if (ncta > 1) cluster_sync_all(); else __syncthreads();
 
   // ---- 4. chunked greedy suppression ------------------------------------------------------
-  for (int c0 = 0; c0 < nv; c0 += kChunk) {
-    const int cn = min(kChunk, nv - c0);
-    const unsigned long long rem_in =
-        (unsigned long long)removed[c0 >> 5] |
-        ((c0 + 32 < nv) ? ((unsigned long long)removed[(c0 >> 5) + 1] << 32) : 0ull);
-    const unsigned long long live_mask = (cn == 64) ? ~0ull : ((1ull << cn) - 1ull);
-    if ((~rem_in & live_mask) == 0ull) continue;  // whole chunk already suppressed (uniform)
-
-    if (tid < cn) {
-      float4 b = sbox[c0 + tid];
-      S.cbox[tid] = b;
-      S.carea[tid] = box_area(b);
-    }
-    __syncthreads();
-    // a. pair mask: warp w owns rows 2w and 2w+1; lanes cover columns lane and lane+32
+  const int n_chunks = (nv + kChunk - 1) / kChunk;
+  int kept_total = 0;  // identical in every CTA of the cluster
+  for (int c = 0; c < n_chunks; ++c) {
+    const int c0 = c * kChunk;
+    const int buf = c & 1;
+    const uint32_t owner = (uint32_t)c % ncta;
+    if (rank == owner) {
+      __syncthreads();  // this CTA's sweep of the previous chunk has updated removed[]
+      const int cn = min(kChunk, nv - c0);
+      const unsigned long long rem_in =
+          (unsigned long long)removed[c0 >> 5] |
+          ((c0 + 32 < nv) ? ((unsigned long long)removed[(c0 >> 5) + 1] << 32) : 0ull);
+      const unsigned long long live_mask = (cn == 64) ? ~0ull : ((1ull << cn) - 1ull);
+      if ((~rem_in & live_mask) == 0ull) {  // whole chunk already suppressed (CTA-uniform)
+        if (ncta == 1) continue;
+        if (tid < (int)ncta) dsmem_st_u32(dsmem_addr(&S.nk[buf], tid), 0u);
+      } else {
+        if (tid < cn) {
+          float4 b = sbox[c0 + tid];
+          S.cbox[tid] = b;
+          S.carea[tid] = box_area(b);
+        }
+        __syncthreads();
+        // a. pair mask: warp w owns rows 2w and 2w+1; lanes cover columns lane and lane+32
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const int r = warp * 2 + rr;
-      bool hit0 = false, hit1 = false;
-      if (r < cn) {
-        const float4 bi = S.cbox[r];
-        const float ai = S.carea[r];
-        if (lane > r && lane < cn) hit0 = iou_exceeds(bi, ai, S.cbox[lane], S.carea[lane], thr);
-        if (lane + 32 > r && lane + 32 < cn)
-          hit1 = iou_exceeds(bi, ai, S.cbox[lane + 32], S.carea[lane + 32], thr);
-      }
-      uint32_t m0 = __ballot_sync(0xffffffffu, hit0);
-      uint32_t m1 = __ballot_sync(0xffffffffu, hit1);
-      if (lane == 0) S.cmask[r] = (unsigned long long)m0 | ((unsigned long long)m1 << 32);
-    }
-    __syncthreads();
-    // b. serial resolve (one thread; the masks are independent loads, the chain is 1 OR/step)
-    if (tid == 0) {
-      unsigned long long rem = rem_in | ~live_mask;
-      unsigned long long kept = 0ull;
+        for (int rr = 0; rr < 2; ++rr) {
+          const int r = warp * 2 + rr;
+          bool hit0 = false, hit1 = false;
+          if (r < cn) {
+            const float4 bi = S.cbox[r];
+            const float ai = S.carea[r];
+            if (lane > r && lane < cn) hit0 = iou_exceeds(bi, ai, S.cbox[lane], S.carea[lane], thr);
+            if (lane + 32 > r && lane + 32 < cn)
+              hit1 = iou_exceeds(bi, ai, S.cbox[lane + 32], S.carea[lane + 32], thr);
+          }
+          uint32_t m0 = __ballot_sync(0xffffffffu, hit0);
+          uint32_t m1 = __ballot_sync(0xffffffffu, hit1);
+          if (lane == 0) S.cmask[r] = (unsigned long long)m0 | ((unsigned long long)m1 << 32);
+        }
+        __syncthreads();
+        // b. serial resolve, redundantly by lane 0 of every warp (no broadcast + barrier afterwards)
+        unsigned long long kept = 0ull;
+        if (lane == 0) {
+          unsigned long long rem = rem_in | ~live_mask;
 #pragma unroll 8
-      for (int r = 0; r < kChunk; ++r) {
-        unsigned long long m = S.cmask[r];
-        bool alive = !((rem >> r) & 1ull);
-        if (alive) { kept |= (1ull << r); rem |= m; }
+          for (int r = 0; r < kChunk; ++r) {
+            unsigned long long m = S.cmask[r];
+            bool alive = !((rem >> r) & 1ull);
+            if (alive) { kept |= (1ull << r); rem |= m; }
+          }
+        }
+        kept = __shfl_sync(0xffffffffu, kept, 0);
+        const int nk = __popcll(kept);
+        // c. kept boxes -> every CTA's buffer; indices -> keep[]
+        {
+          const int src = tid & (kChunk - 1);
+          const uint32_t q = (uint32_t)tid >> 6;  // destination CTA (1024 / 64 = 16 >= cluster size)
+          if (q < ncta && src < cn && ((kept >> src) & 1ull)) {
+            const int slot = __popcll(kept & ((1ull << src) - 1ull));
+            dsmem_st_f4(dsmem_addr(&S.kbox[buf][slot], q), S.cbox[src]);
+            dsmem_st_u32(dsmem_addr(&S.karea[buf][slot], q), __float_as_uint(S.carea[src]));
+            if (q == 0) keep[kept_total + slot] = (int64_t)order[c0 + src];
+          }
+          if (tid < (int)ncta) dsmem_st_u32(dsmem_addr(&S.nk[buf], tid), (uint32_t)nk);
+        }
       }
-      S.cmask[0] = kept;
-      S.nk = __popcll(kept);
     }
-    __syncthreads();
-    const unsigned long long kept = S.cmask[0];
-    const int nk = S.nk;
-    const int kept_before = S.kept_total;
-    if (tid < cn && ((kept >> tid) & 1ull)) {
-      int slot = __popcll(kept & ((1ull << tid) - 1ull));
-      S.kbox[slot] = S.cbox[tid];
-      S.karea[slot] = S.carea[tid];
-      keep[kept_before + slot] = (int64_t)order[c0 + tid];
-    }
-    __syncthreads();
-    if (tid == 0) S.kept_total = kept_before + nk;
-    // c. suppress later candidates
-    for (int j = c0 + kChunk + tid; j < nv; j += kNmsThreads) {
-      if ((removed[j >> 5] >> (j & 31)) & 1u) continue;
-      const float4 bj = sbox[j];
-      const float aj = box_area(bj);
+    if (ncta > 1) cluster_sync_all(); else __syncthreads();
+    const int nk = S.nk[buf];
+    kept_total += nk;
+    if (nk == 0) continue;
+    // d. suppress this CTA's later candidates: own chunks c' > c, c' == rank (mod ncta); a warp covers one
+    //    32-bit word of removed[] per trip and is the only writer of that word during this sweep
+    const int first = c + 1 + (int)((rank + ncta - (uint32_t)(c + 1) % ncta) % ncta);
+    for (int cc = first + (tid >> 6) * (int)ncta; cc < n_chunks; cc += (kNmsThreads / kChunk) * (int)ncta) {
+      const int j = cc * kChunk + (tid & (kChunk - 1));
+      const uint32_t word = removed[j >> 5];
       bool hit = false;
-      for (int k = 0; k < nk; ++k) {
-        if (iou_exceeds(S.kbox[k], S.karea[k], bj, aj, thr)) { hit = true; break; }
+      if (j < nv && !((word >> (j & 31)) & 1u)) {
+        const float4 bj = sbox[j];
+        const float aj = box_area(bj);
+        for (int k = 0; k < nk; ++k) {
+          if (iou_exceeds(S.kbox[buf][k], S.karea[buf][k], bj, aj, thr)) { hit = true; break; }
+        }
       }
-      if (hit) atomicOr(&removed[j >> 5], 1u << (j & 31));
+      const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0 && hits) removed[j >> 5] = word | hits;
     }
-    __syncthreads();
   }
-  if (tid == 0) keep_count[img] = S.kept_total;
+  if (rank == 0 && tid == 0) keep_count[img] = kept_total;
   // tail of `keep` beyond keep_count is left untouched (caller slices by count)
 }
 
@@ -315,9 +374,27 @@ extern "C" int uavdet_nms(const float* boxes, const float* scores, int batch, in
                                      227 * 1024));
     attr_set = true;
   }
-  nms_image_kernel<<<batch, kNmsThreads, smem, st>>>(boxes, scores, n, thr_f, score_floor, keep,
-                                                     keep_count, (uint8_t*)workspace,
-                                                     nms_ws_per_image(n));
+  // CTAs per image: as many as keep the whole batch co-resident (about 16 clusters of 8 fit on 148 SMs)
+  int ncta = 1;
+  if (n >= 4096) ncta = batch <= 16 ? 8 : batch <= 32 ? 4 : batch <= 64 ? 2 : 1;
+  if (const char* e = getenv("UAVDET_NMS_CLUSTER")) {
+    int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4 || v == 8) ncta = v;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)batch * ncta);
+  cfg.blockDim = dim3(kNmsThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = ncta;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  UAVDET_CUDA(cudaLaunchKernelEx(&cfg, nms_image_kernel, boxes, scores, n, thr_f, score_floor, keep, keep_count,
+                                 (uint8_t*)workspace, nms_ws_per_image(n)));
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }
