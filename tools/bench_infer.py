@@ -39,7 +39,14 @@ def c1():
         run = inference.GraphedDetect(model, x)
         ms_g, det_g = timed(lambda: run(x), 10)
         assert torch.equal(det_g.keep_count, det.keep_count)
-        res[b] = dict(ms_total=ms, ms_forward=ms_f, ms_total_graphed=ms_g, fps=b / ms * 1e3, fps_graphed=b / ms_g * 1e3,
+        nms_ms = {}
+        for c in (1, 2, 4, 8, 0):
+            if c:
+                os.environ["UAVDET_NMS_CLUSTER"] = str(c)
+            else:
+                os.environ.pop("UAVDET_NMS_CLUSTER", None)
+            nms_ms["auto" if c == 0 else f"cluster{c}"], _ = timed(lambda: ops.nms_batched(det.boxes, det.scores, 0.5), 10)
+        res[b] = dict(ms_total=ms, ms_forward=ms_f, ms_total_graphed=ms_g, ms_nms=nms_ms, fps=b / ms * 1e3, fps_graphed=b / ms_g * 1e3,
                       kept=det.keep_count.float().mean().item())
     line = {"config": "C1 BaselineModel forward+decode+NMS (25,200 candidates/frame, no threshold)", "gpu": res}
     if "--cpu" in sys.argv:
