@@ -2,16 +2,20 @@
 // Replaces the call at reference model/_base.py:203.
 //
 // One thread-block cluster (1-8 CTAs of 1024 threads, chosen from the batch size) per image:
-//   1. key build      : key = ~orderable(score)  (NaN first, -0 == +0), value = index
-//   2. stable LSD radix sort, 4 x 8-bit passes, ping-pong in the workspace             (CTA 0)
+//   1. key build      : key = ~orderable(score)  (NaN first, -0 == +0), value = index          (CTA 0)
+//   2. stable LSD radix sort, 4 x 8-bit passes, ping-pong in the workspace                     (CTA 0)
 //      (warp match_any ranking keeps equal keys in index order == torch stable sort)
-//   3. gather boxes into score order (float4, coalesced afterwards)                      (CTA 0)
-//   4. chunked greedy suppression, 64 sorted candidates at a time; chunk c is owned by CTA c mod cluster size
-//        a. 64x64 pair mask by warp ballot (each warp: 2 rows x 64 columns)             (owner)
-//        b. serial resolve of the chunk against its own mask                            (owner)
-//        c. the <=64 kept boxes are stored into every CTA's shared memory (DSMEM), one cluster barrier
-//        d. every CTA tests the still-alive candidates of its own later chunks against them; suppressed ones
-//           are marked in the CTA's shared-memory bit array
+//   3. every warp of the cluster gathers ITS candidates (boxes + sorted position) into a private list:
+//      chunk c (64 consecutive sorted positions) belongs to CTA c % ncta, warp (c / ncta) % 16
+//   4. greedy suppression as a warp-level data flow, no CTA- or cluster-wide barrier:
+//        * the kept boxes of chunk c ("list c") reach every CTA through slot c % 8 of a shared-memory ring
+//          (st.async + the receiver's mbarrier; an empty-barrier in the owner CTA recycles the slot);
+//        * a warp sweeps its private list against list c and compacts the survivors in place, so its lanes
+//          stay densely occupied as candidates die;
+//        * the survivors of chunk c + 1 sit at the front of their owner warp's list: right after the first
+//          trip of that sweep the owner resolves the chunk inside the warp (hop from survivor to survivor,
+//          one ballot per hop), publishes list c + 1, and only then finishes its own sweep -- the serial
+//          chain of the greedy algorithm overlaps the bulk sweeps of everybody else.
 // All IoU arithmetic uses explicit round-to-nearest intrinsics so no FMA contraction can
 // change a rounding relative to the CPU reference.
 #include "common.cuh"
@@ -19,9 +23,19 @@
 
 namespace uavdet {
 
-constexpr int kNmsThreads = 1024;
+#ifndef UAVDET_NMS_THREADS
+#define UAVDET_NMS_THREADS 512
+#endif
+constexpr int kNmsThreads = UAVDET_NMS_THREADS;
 constexpr int kNmsWarps = kNmsThreads / 32;
 constexpr int kChunk = 64;
+#ifndef UAVDET_NMS_SWEEP_WARPS
+#define UAVDET_NMS_SWEEP_WARPS 16
+#endif
+static_assert(UAVDET_NMS_SWEEP_WARPS * 32 <= UAVDET_NMS_THREADS, "more sweeping warps than warps");
+// warps per CTA that hold candidate lists and run step 4 (the others only help with the sort): fewer warps per
+// scheduler means the warp that is resolving the next chunk -- the serial chain -- waits less for an issue slot
+constexpr int kSweepWarps = UAVDET_NMS_SWEEP_WARPS;
 
 __device__ __forceinline__ uint32_t score_key(float s) {
   uint32_t b = __float_as_uint(s);
@@ -44,21 +58,28 @@ __device__ __forceinline__ float box_area(const float4& b) {
 }
 
 // i = the kept (earlier) box, j = the candidate.  torchvision/csrc/ops/cpu/nms_kernel.cpp
-// The reference decides `fl(inter / (ai + aj - inter)) > thr` with an IEEE division.  The division is ~30
-// instructions, so the exact quotient is only formed when the outcome is not already certain.  With
-// p = fl(thr * u) and u > 0, |fl(x) - x| <= 2^-24 |x| for the product and for the quotient (rounding is monotone),
-// so inter > fl(p (1 + 2^-20)) implies fl(inter / u) > thr and inter < fl(p (1 - 2^-20)) implies the opposite
-// (inter == 0 falls in the second case).  That needs p to be a normal, positive, finite float -- the exponent
-// range check below, which also rejects NaN and u <= 0 -- and a sane threshold: the caller passes thr_fast = thr
-// when thr is in [1e-6, 1e6] and NaN otherwise, which sends every pair down the exact path.
-// kNaN = false (no NaN coordinate among the candidates of this image, established once per launch) lets the
-// std::max / std::min selects collapse to single FMNMX instructions: the two only differ on NaN operands
-// (signed zeros change at most the sign of a zero width, never `inter`).
-template <bool kNaN>
-__device__ __forceinline__ bool iou_exceeds(const float4& bi, float ai, const float4& bj, float aj,
-                                            float thr, float thr_fast) {
+// The reference decides `fl(inter / fl(fl(ai + aj) - inter)) > thr` with an IEEE division.  The division is ~30
+// instructions, so the exact quotient (iou_exact) is only formed when the outcome is not already certain; iou_code
+// returns bit 0 = the outcome if certain, bit 1 = uncertain.  Rounding is monotone and every fl() is within
+// 2^-24 relative, which gives two sufficient tests, selected per launch from a property of the image's boxes:
+//
+// kMode 0 ("benign": every candidate box is finite with x2 >= x1, y2 >= y1 and an area that is 0 or within
+//   [2^-90, 2^90]).  Then 0 <= inter <= min(ai, aj), s = fl(ai + aj) is exactly the reference's sum, u = s - inter > 0
+//   whenever s > 0, and  inter / u > t  <=>  inter > s t / (1 + t).  With the host-made constants
+//   T_hi >= th / (1 + th) (1 + 2^-22), th = thr (1 + 2^-21), and T_lo <= tl / (1 + tl) (1 - 2^-22), tl = thr (1 - 2^-21):
+//     inter > fl(T_hi s)  =>  inter / u >= th  =>  fl(inter / fl(u)) > thr,
+//     inter < fl(T_lo s)  =>  inter / u <= tl  =>  fl(inter / fl(u)) <= thr;
+//   anything in between (a sliver 2^-20 wide around the threshold, and s == 0) is uncertain.  14 instructions.
+// kMode 1 (finite or not, but no NaN coordinate) and kMode 2 (NaN present): compare inter with p = fl(thr u),
+//   u = fl(fl(ai + aj) - inter):  inter > fl(p (1 + 2^-20)) => exceeds, inter < fl(p (1 - 2^-20)) => does not, valid
+//   when p is a normal positive float (the exponent-range check, which also rejects NaN and u <= 0) and thr is in
+//   [1e-6, 1e6] (else the caller passes NaN as t_a and every pair is uncertain).  kMode 2 additionally keeps
+//   std::max / std::min's operand order, which differs from FMNMX only on NaN operands (signed zeros change at most
+//   the sign of a zero width, never `inter`).
+template <int kMode>
+__device__ __forceinline__ uint32_t iou_code(const float4& bi, float ai, const float4& bj, float aj, float t_a, float t_b) {
   float xx1, yy1, xx2, yy2;
-  if (kNaN) {
+  if (kMode == 2) {
     xx1 = std_max(bi.x, bj.x);
     yy1 = std_max(bi.y, bj.y);
     xx2 = std_min(bi.z, bj.z);
@@ -73,34 +94,49 @@ __device__ __forceinline__ bool iou_exceeds(const float4& bi, float ai, const fl
   const float w = fmaxf(0.f, __fsub_rn(xx2, xx1));
   const float h = fmaxf(0.f, __fsub_rn(yy2, yy1));
   const float inter = __fmul_rn(w, h);
-  const float u = __fsub_rn(__fadd_rn(ai, aj), inter);
-  const float p = __fmul_rn(thr_fast, u);
-  const bool in_range = (__float_as_uint(p) - 0x0D800000u) < 0x64000000u;       // 2^-100 <= p < 2^100
-  const bool hi = inter > __fmul_rn(p, 1.00000095367431640625f);                // 1 + 2^-20
-  const bool lo = inter < __fmul_rn(p, 0.99999904632568359375f);                // 1 - 2^-20
-  if (in_range && (hi || lo)) return hi;
-  return __fdiv_rn(inter, u) > thr;
+  if (kMode == 0) {
+    const float s = __fadd_rn(ai, aj);
+    const bool hi = inter > __fmul_rn(t_a, s);
+    const bool lo = inter < __fmul_rn(t_b, s);
+    return (hi ? 1u : 0u) | ((hi || lo) ? 0u : 2u);
+  } else {
+    const float u = __fsub_rn(__fadd_rn(ai, aj), inter);
+    const float p = __fmul_rn(t_a, u);
+    const bool in_range = (__float_as_uint(p) - 0x0D800000u) < 0x64000000u;  // 2^-100 <= p < 2^100
+    const bool hi = inter > __fmul_rn(p, 1.00000095367431640625f);           // 1 + 2^-20
+    const bool lo = inter < __fmul_rn(p, 0.99999904632568359375f);           // 1 - 2^-20
+    return (hi ? 1u : 0u) | ((in_range && (hi || lo)) ? 0u : 2u);
+  }
+}
+// the reference arithmetic itself, for the pairs iou_code could not decide
+__device__ __noinline__ bool iou_exact(float4 bi, float ai, float4 bj, float aj, float thr) {
+  const float xx1 = std_max(bi.x, bj.x);
+  const float yy1 = std_max(bi.y, bj.y);
+  const float xx2 = std_min(bi.z, bj.z);
+  const float yy2 = std_min(bi.w, bj.w);
+  const float w = std_max(0.f, __fsub_rn(xx2, xx1));
+  const float h = std_max(0.f, __fsub_rn(yy2, yy1));
+  const float inter = __fmul_rn(w, h);
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, aj), inter)) > thr;
+}
+__device__ __forceinline__ bool iou_decide(uint32_t code, float4 bi, float ai, float4 bj, float aj, float thr) {
+  if (code & 2u) return iou_exact(bi, ai, bj, aj, thr);
+  return code & 1u;
 }
 
+// list entries beyond n: each of the <= 8 x 32 warps rounds its capacity up to whole 64-entry trips
+constexpr size_t kListSlack = 8 * kNmsWarps * kChunk + 1024;
 constexpr int kSlots = 8;  // ring of kept-box lists; slot = chunk % 8, so a slot always has the same owner CTA
-// bytes one owner sends into one CTA's slot: 64 boxes + 64 areas + the count (always the full slot, so that the
-// receiving mbarrier's transaction count is a constant)
-constexpr uint32_t kSlotTxBytes = kChunk * 16 + kChunk * 4 + 4;
 
 struct NmsSmem {
   uint32_t bin[256];              // digit histogram / running offsets
   uint32_t warp_off[kNmsWarps][256];  // per-warp digit counts, then scatter offsets
-  float4 cbox[kChunk];
-  float carea[kChunk];
-  unsigned long long cmask[kChunk];
   float4 kbox[kSlots][kChunk];    // kept boxes of chunk c live in slot c % 8 of EVERY CTA of the cluster (st.async
-  float karea[kSlots][kChunk];    //  by the chunk's owner, completion counted on the receiver's full[] barrier)
+  float karea[kSlots][kChunk];    //  by the chunk's owner warp, completion counted on the receiver's full[] barrier)
   uint32_t nk[kSlots];
-  unsigned long long full[kSlots];   // armed with kSlotTxBytes by thread 0, completed by the owner's st.async
+  unsigned long long full[kSlots];   // 1 arrival (+ the byte count) per use, both made by the sending warp
   unsigned long long empty[kSlots];  // in the slot's owner CTA: one arrival per warp of the cluster when it is done
   int n_valid;
-  int has_nan;
-  unsigned long long kept_mask;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -137,11 +173,15 @@ __device__ __forceinline__ void st_async_u32(uint32_t addr, uint32_t v, uint32_t
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx_remote(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
 // Bounded wait: a barrier bug traps (the host sees a launch error) instead of hanging the GPU.
 __device__ __forceinline__ void nms_mbar_wait(uint32_t bar, uint32_t parity) {
   if (sm100::mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
   while (!sm100::mbar_try_wait(bar, parity)) {
+    __nanosleep(20);
     if (clock64() - t0 > 4000000000ll) __trap();
   }
 }
@@ -152,241 +192,215 @@ __device__ __forceinline__ void nms_mbar_wait(uint32_t bar, uint32_t parity) {
 #define NMS_PROF(acc) do { } while (0)
 #endif
 
-// The fast part of iou_exceeds: bit 0 = the outcome if certain, bit 1 = uncertain (take the exact path).  Kept
-// separate so that several tests can be in flight per thread without a branch between them.
-template <bool kNaN>
-__device__ __forceinline__ uint32_t iou_code(const float4& bi, float ai, const float4& bj, float aj, float thr_fast) {
-  float xx1, yy1, xx2, yy2;
-  if (kNaN) {
-    xx1 = std_max(bi.x, bj.x);
-    yy1 = std_max(bi.y, bj.y);
-    xx2 = std_min(bi.z, bj.z);
-    yy2 = std_min(bi.w, bj.w);
-  } else {
-    xx1 = fmaxf(bi.x, bj.x);
-    yy1 = fmaxf(bi.y, bj.y);
-    xx2 = fminf(bi.z, bj.z);
-    yy2 = fminf(bi.w, bj.w);
-  }
-  const float w = fmaxf(0.f, __fsub_rn(xx2, xx1));
-  const float h = fmaxf(0.f, __fsub_rn(yy2, yy1));
-  const float inter = __fmul_rn(w, h);
-  const float u = __fsub_rn(__fadd_rn(ai, aj), inter);
-  const float p = __fmul_rn(thr_fast, u);
-  const bool in_range = (__float_as_uint(p) - 0x0D800000u) < 0x64000000u;
-  const bool hi = inter > __fmul_rn(p, 1.00000095367431640625f);
-  const bool lo = inter < __fmul_rn(p, 0.99999904632568359375f);
-  return (hi ? 1u : 0u) | ((in_range && (hi || lo)) ? 0u : 2u);
+// entries per warp list: the warp's share of the (at most) ceil(n / 64) chunks, in whole 64-entry trips
+__host__ __device__ inline int list_capacity(int n, int ncta) {
+  const int n_chunks = (n + kChunk - 1) / kChunk;
+  return (((n_chunks + ncta - 1) / ncta + kSweepWarps - 1) / kSweepWarps) * kChunk;
 }
-// exact reference arithmetic, for the pairs iou_code could not decide
-template <bool kNaN>
-__device__ __noinline__ bool iou_exact(const float4& bi, float ai, const float4& bj, float aj, float thr) {
-  const float xx1 = std_max(bi.x, bj.x);
-  const float yy1 = std_max(bi.y, bj.y);
-  const float xx2 = std_min(bi.z, bj.z);
-  const float yy2 = std_min(bi.w, bj.w);
-  const float w = std_max(0.f, __fsub_rn(xx2, xx1));
-  const float h = std_max(0.f, __fsub_rn(yy2, yy1));
-  const float inter = __fmul_rn(w, h);
-  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, aj), inter)) > thr;
-}
+constexpr size_t kSmemListOffset = (sizeof(NmsSmem) + 15) & ~(size_t)15;
 
-// Step 4 of the kernel below.  Returns the number of kept boxes (identical in every CTA of the cluster).
-//
-// Candidates are split over the cluster by 64-candidate chunk: chunk c belongs to CTA c % ncta, and inside that
-// CTA own chunk number i (= c / ncta) belongs for good to the two warps of thread group i % 16, so a word of the
-// removed[] bit array is only ever touched by one warp and the sweeps need no CTA-wide barrier.  The kept boxes
-// of chunk c travel through slot c % 8 of a ring present in every CTA: the owner waits for the slot's empty
-// barrier (every warp of the cluster has finished with its previous content), st.async's the list into every
-// CTA, and each warp waits on its CTA's full barrier before sweeping.  No cluster-wide barrier in the loop.
-template <bool kNaN>
-__device__ __noinline__ int suppress(NmsSmem& S, uint32_t* removed, const float4* sbox, const uint32_t* order,
-                                     int64_t* keep, int nv, float thr, float thr_fast, uint32_t ncta,
+// Step 4 of the kernel below, run by every warp on its own list `lbox/lpos[0..L)` (sorted-position order).
+// Returns the number of kept boxes (every warp of the cluster ends with the same count).
+template <int kMode>
+__device__ __noinline__ int suppress(NmsSmem& S, float4* lbox, uint32_t* lpos, int L, const uint32_t* order,
+                                     int64_t* keep, int n_chunks, float thr, float t_a, float t_b, uint32_t ncta,
                                      uint32_t rank) {
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int warp = tid >> 5;
-  const int grp = tid >> 6;            // thread group: 64 threads = one chunk wide
-  const int off = tid & (kChunk - 1);
-  constexpr int kGroups = kNmsThreads / kChunk;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
 #ifdef UAVDET_NMS_PROFILE
-  long long pt0 = clock64(), p_o1 = 0, p_o2 = 0, p_o3 = 0, p_o4 = 0, p_bar = 0, p_sweep = 0, pt;
+  long long pt0 = clock64(), p_wait = 0, p_sweep = 0, p_res = 0, p_hops = 0, p_empty = 0, p_send = 0, p_t0 = 0, pt; int n_trips = 0, n_iters = 0, n_lists = 0; long long sumL = 0, p_k = 0, p_ld = 0;
 #endif
-  const int n_chunks = (nv + kChunk - 1) / kChunk;
   int kept_total = 0;
-  // the boxes / original indices of this CTA's next own chunk, fetched one own-chunk ahead (threads 0..63)
-  float4 pf_box = make_float4(0.f, 0.f, 0.f, 0.f);
-  uint32_t pf_ord = 0;
-  if (tid < kChunk && (int)rank * kChunk + tid < nv) {
-    pf_box = sbox[rank * kChunk + tid];
-    pf_ord = order[rank * kChunk + tid];
-  }
-  for (int c = 0; c < n_chunks; ++c) {
-    const int c0 = c * kChunk;
+  // "list -1" is empty: the owner of chunk 0 resolves it straight away
+  for (int c = -1; c < n_chunks; ++c) {
     const int slot = c & (kSlots - 1);
-    const uint32_t use = (uint32_t)c / kSlots;
-    const uint32_t owner = (uint32_t)c % ncta;
-    if (rank == owner) {
-      const int cn = min(kChunk, nv - c0);
-      const uint32_t my_ord = pf_ord;
-      if (tid < kChunk) {
-        S.cbox[tid] = pf_box;
-        S.carea[tid] = box_area(pf_box);
-        const int nj = c0 + (int)ncta * kChunk + tid;
-        if (nj < nv) {
-          pf_box = sbox[nj];
-          pf_ord = order[nj];
+    int nk = 0;
+    if (c >= 0) {
+      nms_mbar_wait(sm100::smem_u32(&S.full[slot]), ((uint32_t)c / kSlots) & 1u);
+      nk = (int)S.nk[slot];
+      kept_total += nk;
+    }
+    NMS_PROF(p_wait);
+    // does this warp own chunk c + 1?
+    const int cn = c + 1;
+    const bool owner = cn < n_chunks && (uint32_t)cn % ncta == rank && (((uint32_t)cn / ncta) & (kSweepWarps - 1)) == (uint32_t)warp;
+    if (nk != 0 || owner) {
+      int out = 0;
+      for (int in = 0; in < L || (owner && in == 0); in += kChunk) {
+#ifdef UAVDET_NMS_PROFILE
+        ++n_trips; if (in == 0) { sumL += L; }
+#endif
+        // two entries per lane: A = in + lane, B = in + 32 + lane
+        const int eA = in + lane, eB = in + 32 + lane;
+        bool liveA = eA < L, liveB = eB < L;
+        float4 bA = make_float4(0.f, 0.f, 0.f, 0.f), bB = bA;
+        uint32_t pA = 0, pB = 0;
+        if (liveA) { bA = lbox[eA]; pA = lpos[eA]; }
+        if (liveB) { bB = lbox[eB]; pB = lpos[eB]; }
+        const float aA = box_area(bA), aB = box_area(bB);
+        const uint32_t validA = __ballot_sync(0xffffffffu, liveA), validB = __ballot_sync(0xffffffffu, liveB);
+        NMS_PROF(p_ld);
+        // sweep against list c, two kept boxes x two candidates in flight
+        int k = 0;
+        for (; k + 2 <= nk; k += 2) {
+          if (!(liveA | liveB)) break;
+#ifdef UAVDET_NMS_PROFILE
+          ++n_iters;
+#endif
+          const float4 k0 = S.kbox[slot][k], k1 = S.kbox[slot][k + 1];
+          const float a0 = S.karea[slot][k], a1 = S.karea[slot][k + 1];
+          const uint32_t cA0 = iou_code<kMode>(k0, a0, bA, aA, t_a, t_b), cA1 = iou_code<kMode>(k1, a1, bA, aA, t_a, t_b);
+          const uint32_t cB0 = iou_code<kMode>(k0, a0, bB, aB, t_a, t_b), cB1 = iou_code<kMode>(k1, a1, bB, aB, t_a, t_b);
+          bool hA, hB;
+          if ((cA0 | cA1 | cB0 | cB1) & 2u) {
+#ifdef UAVDET_NMS_PROFILE
+            ++n_lists;
+#endif
+            hA = iou_decide(cA0, k0, a0, bA, aA, thr) || iou_decide(cA1, k1, a1, bA, aA, thr);
+            hB = iou_decide(cB0, k0, a0, bB, aB, thr) || iou_decide(cB1, k1, a1, bB, aB, thr);
+          } else {
+            hA = (cA0 | cA1) & 1u;
+            hB = (cB0 | cB1) & 1u;
+          }
+          liveA = liveA && !hA;
+          liveB = liveB && !hB;
         }
-      }
-      __syncthreads();  // cbox ready; every warp's sweep of the previous chunks has updated removed[]
-      const unsigned long long rem_in =
-          (unsigned long long)removed[c0 >> 5] | ((unsigned long long)removed[(c0 >> 5) + 1] << 32);
-      const unsigned long long live_mask = (cn == 64) ? ~0ull : ((1ull << cn) - 1ull);
-      const unsigned long long alive_in = ~rem_in & live_mask;
-      NMS_PROF(p_o1);
-      unsigned long long kept = 0ull;
-      if (alive_in != 0ull) {  // (CTA-uniform) otherwise the whole chunk is already suppressed
-        // a. pair mask over the still-alive candidates: warp w owns rows 2w and 2w+1, lanes cover columns lane
-        //    and lane + 32
-        const float4 bc0 = S.cbox[lane], bc1 = S.cbox[lane + 32];
-        const float ac0 = S.carea[lane], ac1 = S.carea[lane + 32];
-        uint32_t code[4];
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-          const int r = warp * 2 + rr;
-          const float4 bi = S.cbox[r];
-          const float ai = S.carea[r];
-          const bool row_alive = (alive_in >> r) & 1ull;
-          const bool t0 = row_alive && lane > r && ((alive_in >> lane) & 1ull);
-          const bool t1 = row_alive && lane + 32 > r && ((alive_in >> (lane + 32)) & 1ull);
-          code[rr * 2 + 0] = t0 ? iou_code<kNaN>(bi, ai, bc0, ac0, thr_fast) : 0u;
-          code[rr * 2 + 1] = t1 ? iou_code<kNaN>(bi, ai, bc1, ac1, thr_fast) : 0u;
+        if (k < nk && (liveA | liveB)) {
+          const float4 k0 = S.kbox[slot][k];
+          const float a0 = S.karea[slot][k];
+          const uint32_t cA0 = iou_code<kMode>(k0, a0, bA, aA, t_a, t_b), cB0 = iou_code<kMode>(k0, a0, bB, aB, t_a, t_b);
+          liveA = liveA && !iou_decide(cA0, k0, a0, bA, aA, thr);
+          liveB = liveB && !iou_decide(cB0, k0, a0, bB, aB, thr);
         }
-        if ((code[0] | code[1] | code[2] | code[3]) & 2u) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (code[q] & 2u) {
-              const int r = warp * 2 + (q >> 1);
-              code[q] = iou_exact<kNaN>(S.cbox[r], S.carea[r], (q & 1) ? bc1 : bc0, (q & 1) ? ac1 : ac0, thr) ? 1u : 0u;
-            }
-        }
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-          const uint32_t m0 = __ballot_sync(0xffffffffu, code[rr * 2 + 0] & 1u);
-          const uint32_t m1 = __ballot_sync(0xffffffffu, code[rr * 2 + 1] & 1u);
-          if (lane == 0) S.cmask[warp * 2 + rr] = (unsigned long long)m0 | ((unsigned long long)m1 << 32);
-        }
-        __syncthreads();
-        NMS_PROF(p_o2);
-        // b. serial resolve by warp 0 (warp-uniform): hop from one surviving candidate to the next
-        if (warp == 0) {
-          unsigned long long alive = alive_in;
+        __syncwarp();
+        if (owner && in == 0) NMS_PROF(p_t0); else NMS_PROF(p_k);
+        if (owner && in == 0) {
+          // ---- resolve chunk c + 1: its survivors are exactly the live entries of this trip with that chunk number
+          const bool memA = liveA && (int)(pA >> 6) == cn, memB = liveB && (int)(pB >> 6) == cn;
+          unsigned long long alive =
+              (unsigned long long)__ballot_sync(0xffffffffu, memA) | ((unsigned long long)__ballot_sync(0xffffffffu, memB) << 32);
+          unsigned long long kept = 0ull;
+          // Greedy in rounds: the (up to) four lowest surviving members are tested against all members at once
+          // -- one latency for four candidates -- then accepted in order with bit operations only (a later one
+          // of the four may have been suppressed by an earlier one; its test results are then simply unused).
           while (alive) {
-            const int r = __ffsll((long long)alive) - 1;
-            kept |= 1ull << r;
-            alive &= ~(S.cmask[r] | (1ull << r));  // rows only hold columns > r
-          }
-          if (lane == 0) S.kept_mask = kept;
-        }
-        __syncthreads();
-        kept = S.kept_mask;
-        NMS_PROF(p_o3);
-      }
-      const int nk = __popcll(kept);
-      // c. the slot must be free in every CTA, then: kept boxes -> every CTA's slot; indices -> keep[]
-      nms_mbar_wait(sm100::smem_u32(&S.empty[slot]), (use & 1u) ^ 1u);
-      {
-        const uint32_t q = (uint32_t)grp;  // destination CTA (16 thread groups >= cluster size)
-        if (q < ncta) {
-          const uint32_t bar = dsmem_addr(&S.full[slot], q);
-          // entry `off` of the slot: the off-th kept box (entries >= nk are never read; any bytes will do)
-          int src = off;
-          if (off < nk) {
-            unsigned long long m = kept;
-            for (int t = 0; t < off; ++t) m &= m - 1;  // drop the `off` lowest set bits
-            src = __ffsll((long long)m) - 1;
-          }
-          st_async_f4(dsmem_addr(&S.kbox[slot][off], q), S.cbox[src], bar);
-          st_async_u32(dsmem_addr(&S.karea[slot][off], q), __float_as_uint(S.carea[src]), bar);
-          if (off == 0) st_async_u32(dsmem_addr(&S.nk[slot], q), (uint32_t)nk, bar);
-        }
-        if (tid < kChunk && ((kept >> tid) & 1ull))
-          keep[kept_total + __popcll(kept & ((1ull << tid) - 1ull))] = (int64_t)my_ord;
-      }
-      NMS_PROF(p_o4);
-    }
-    const uint32_t full_bar = sm100::smem_u32(&S.full[slot]);
-    nms_mbar_wait(full_bar, use & 1u);
-    if (tid == 0) sm100::mbar_arrive_expect_tx(full_bar, kSlotTxBytes);  // arm the slot's next use
-    NMS_PROF(p_bar);
-    const int nk = (int)S.nk[slot];
-    kept_total += nk;
-    if (nk != 0) {
-      // d. suppress this warp's later candidates: own chunks i = grp (mod 16) with chunk number > c
-      const int i_min = (c >= (int)rank) ? (c - (int)rank) / (int)ncta + 1 : 0;
-      int i = i_min + ((grp - i_min) & (kGroups - 1));
-      const int stride = kGroups * (int)ncta * kChunk;
-      int j = ((int)rank + i * (int)ncta) * kChunk + off;
-      const int j_end = n_chunks * kChunk;
-      float4 nb = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j < nv) nb = sbox[j];
-      for (; j < j_end; j += stride) {
-        const float4 bj = nb;
-        if (j + stride < nv) nb = sbox[j + stride];
-        const uint32_t word = removed[j >> 5];
-        bool hit = false;
-        if (j < nv && !((word >> (j & 31)) & 1u)) {
-          const float aj = box_area(bj);
-          int k = 0;
-          for (; k + 4 <= nk; k += 4) {
-            const uint32_t q0 = iou_code<kNaN>(S.kbox[slot][k + 0], S.karea[slot][k + 0], bj, aj, thr_fast);
-            const uint32_t q1 = iou_code<kNaN>(S.kbox[slot][k + 1], S.karea[slot][k + 1], bj, aj, thr_fast);
-            const uint32_t q2 = iou_code<kNaN>(S.kbox[slot][k + 2], S.karea[slot][k + 2], bj, aj, thr_fast);
-            const uint32_t q3 = iou_code<kNaN>(S.kbox[slot][k + 3], S.karea[slot][k + 3], bj, aj, thr_fast);
-            uint32_t any = q0 | q1 | q2 | q3;
-            if (any & 2u) {
-              any = 0u;
-              const uint32_t qq[4] = {q0, q1, q2, q3};
+            int r[4];
+            unsigned long long rest = alive;
 #pragma unroll
-              for (int t = 0; t < 4; ++t)
-                any |= (qq[t] & 2u) ? (iou_exact<kNaN>(S.kbox[slot][k + t], S.karea[slot][k + t], bj, aj, thr) ? 1u : 0u)
-                                    : qq[t];
+            for (int t = 0; t < 4; ++t) {
+              r[t] = rest ? __ffsll((long long)rest) - 1 : -1;
+              rest &= rest - 1;
             }
-            if (any & 1u) { hit = true; break; }
+            // absent candidates (fewer than four left) re-use lane 0's entry; their results are never looked at
+            float4 br[4];
+            float ar[4];
+            uint32_t cA[4], cB[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int rr = max(r[t], 0);
+              const bool fromB = rr >= 32;
+              br[t].x = __shfl_sync(0xffffffffu, fromB ? bB.x : bA.x, rr & 31);
+              br[t].y = __shfl_sync(0xffffffffu, fromB ? bB.y : bA.y, rr & 31);
+              br[t].z = __shfl_sync(0xffffffffu, fromB ? bB.z : bA.z, rr & 31);
+              br[t].w = __shfl_sync(0xffffffffu, fromB ? bB.w : bA.w, rr & 31);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              ar[t] = box_area(br[t]);
+              cA[t] = iou_code<kMode>(br[t], ar[t], bA, aA, t_a, t_b);
+              cB[t] = iou_code<kMode>(br[t], ar[t], bB, aB, t_a, t_b);
+            }
+            if ((cA[0] | cA[1] | cA[2] | cA[3] | cB[0] | cB[1] | cB[2] | cB[3]) & 2u) {
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                cA[t] = iou_decide(cA[t], br[t], ar[t], bA, aA, thr) ? 1u : 0u;
+                cB[t] = iou_decide(cB[t], br[t], ar[t], bB, aB, thr) ? 1u : 0u;
+              }
+            }
+            unsigned long long H[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              H[t] = (unsigned long long)__ballot_sync(0xffffffffu, memA && (cA[t] & 1u)) |
+                     ((unsigned long long)__ballot_sync(0xffffffffu, memB && (cB[t] & 1u)) << 32);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              if (r[t] >= 0 && ((alive >> r[t]) & 1ull)) {
+                kept |= 1ull << r[t];
+                // a member never suppresses an earlier one that was kept (the test is symmetric), and `alive`
+                // no longer holds the kept ones, so clearing every hit is safe; bit r itself goes too
+                alive &= ~(H[t] | (1ull << r[t]));
+              }
+            }
           }
-          if (!hit)
-            for (; k < nk; ++k)
-              if (iou_exceeds<kNaN>(S.kbox[slot][k], S.karea[slot][k], bj, aj, thr, thr_fast)) { hit = true; break; }
+          NMS_PROF(p_hops);
+          const int nk_new = __popcll(kept);
+          const bool keptA = (kept >> lane) & 1ull, keptB = (kept >> (lane + 32)) & 1ull;
+          const int slotA = __popcll(kept & (unsigned long long)lt_mask);
+          const int slotB = __popc((uint32_t)kept) + __popc((uint32_t)(kept >> 32) & lt_mask);
+          // ---- publish list c + 1: wait until every warp of the cluster is done with the slot's previous content
+          const int nslot = cn & (kSlots - 1);
+          nms_mbar_wait(sm100::smem_u32(&S.empty[nslot]), (((uint32_t)cn / kSlots) & 1u) ^ 1u);
+          NMS_PROF(p_empty);
+          for (uint32_t q = 0; q < ncta; ++q) {
+            const uint32_t bar = dsmem_addr(&S.full[nslot], q);
+            if (keptA) {
+              st_async_f4(dsmem_addr(&S.kbox[nslot][slotA], q), bA, bar);
+              st_async_u32(dsmem_addr(&S.karea[nslot][slotA], q), __float_as_uint(aA), bar);
+            }
+            if (keptB) {
+              st_async_f4(dsmem_addr(&S.kbox[nslot][slotB], q), bB, bar);
+              st_async_u32(dsmem_addr(&S.karea[nslot][slotB], q), __float_as_uint(aB), bar);
+            }
+            if (lane == 0) {
+              st_async_u32(dsmem_addr(&S.nk[nslot], q), (uint32_t)nk_new, bar);
+              mbar_arrive_expect_tx_remote(bar, (uint32_t)nk_new * 20u + 4u);
+            }
+          }
+          NMS_PROF(p_send);
+          if (keptA) keep[kept_total + slotA] = (int64_t)order[pA];
+          if (keptB) keep[kept_total + slotB] = (int64_t)order[pB];
+          // the chunk is finished: its members leave the list
+          liveA = liveA && !memA;
+          liveB = liveB && !memB;
+          NMS_PROF(p_res);
         }
-        const uint32_t hits = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0 && hits) removed[j >> 5] = word | hits;
+        // ---- compact the survivors in place (A entries precede B entries, as in the list)
+        const uint32_t mA = __ballot_sync(0xffffffffu, liveA), mB = __ballot_sync(0xffffffffu, liveB);
+        if (out != in || mA != validA || mB != validB) {
+          const int oA = out + __popc(mA & lt_mask), oB = out + __popc(mA) + __popc(mB & lt_mask);
+          if (liveA) { lbox[oA] = bA; lpos[oA] = pA; }
+          if (liveB) { lbox[oB] = bB; lpos[oB] = pB; }
+        }
+        out += __popc(mA) + __popc(mB);
+        __syncwarp();  // the stores above are read back by other lanes of this warp in the next sweep
       }
+      L = out;
     }
-    // this warp is done with the slot: tell the slot's owner (every lane has read what it needed)
-    __syncwarp();
-    if (lane == 0) mbar_arrive_remote(dsmem_addr(&S.empty[slot], (uint32_t)slot % ncta));
+    // this warp is done with list c: tell the slot's owner CTA
+    if (c >= 0) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(dsmem_addr(&S.empty[slot], (uint32_t)slot % ncta));
+    }
     NMS_PROF(p_sweep);
   }
 #ifdef UAVDET_NMS_PROFILE
-  if (tid == 0 && blockIdx.x < ncta)
-    printf("nms rank %u/%u: o1 %lld mask %lld resolve %lld bcast %lld wait %lld sweep %lld cycles, chunks %d\n",
-           rank, ncta, p_o1, p_o2, p_o3, p_o4, p_bar, p_sweep, n_chunks);
+  const int n_iters_max = __reduce_max_sync(0xffffffffu, n_iters); n_lists = __reduce_add_sync(0xffffffffu, n_lists);
+  if (lane == 0 && (warp == 0 || warp == 5) && blockIdx.x < ncta && (rank == 0 || rank == 3))
+    printf("nms rank %u/%u warp %d: wait %lld sweep %lld | own: trip0 %lld hops %lld empty %lld send %lld keep %lld cycles, chunks %d; slow-path lane-iterations %d trips %d iters(max lane) %d avgL %lld; load %lld kloop %lld\n", rank, ncta, warp, p_wait,
+           p_sweep, p_t0, p_hops, p_empty, p_send, p_res, n_chunks, n_lists, n_trips, n_iters_max, sumL / max(n_lists, 1), p_ld, p_k);
 #endif
   return kept_total;
 }
 
-// One image per thread-block CLUSTER (1, 2, 4 or 8 CTAs).  CTA 0 sorts; the suppression sweep -- the O(n * kept)
-// part -- is split over the CTAs by 64-candidate chunk (chunk c belongs to CTA c mod cluster size, which keeps
-// that chunk's `removed` bits in its own shared memory).  Per chunk: the owner resolves it and stores the kept
-// boxes into every CTA's shared memory, one cluster barrier, then every CTA sweeps its own later chunks.
+// One image per thread-block CLUSTER (1, 2, 4 or 8 CTAs); see the file header for the pipeline.
 __global__ void __launch_bounds__(kNmsThreads, 1)
 nms_image_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, int n,
                  float thr, float score_floor, int64_t* __restrict__ keep,
                  int32_t* __restrict__ keep_count, uint8_t* __restrict__ workspace,
-                 size_t ws_per_image) {
+                 size_t ws_per_image, int lists_in_smem, float t_hi, float t_lo) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   NmsSmem& S = *reinterpret_cast<NmsSmem*>(smem_raw);
-  uint32_t* removed = reinterpret_cast<uint32_t*>(smem_raw + sizeof(NmsSmem));
 
   const uint32_t ncta = cluster_nctarank();
   const uint32_t rank = cluster_ctarank();
@@ -398,14 +412,17 @@ nms_image_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
   scores += (size_t)img * n;
   keep += (size_t)img * n;
 
-  // workspace carve-up (per image): keys A/B, vals A/B, sorted boxes
+  // workspace carve-up (per image): keys A/B, vals A/B, the per-warp candidate lists, the box-property flags
   uint8_t* ws = workspace + (size_t)img * ws_per_image;
   const size_t n_pad = ((size_t)n + 3) & ~(size_t)3;
   uint32_t* keyA = reinterpret_cast<uint32_t*>(ws);
   uint32_t* keyB = keyA + n_pad;
   uint32_t* valA = keyB + n_pad;
   uint32_t* valB = valA + n_pad;
-  float4* sbox = reinterpret_cast<float4*>(valB + n_pad);
+  const size_t n_list = n_pad + kListSlack;
+  float4* lists_box = reinterpret_cast<float4*>(valB + n_pad);
+  uint32_t* lists_pos = reinterpret_cast<uint32_t*>(lists_box + n_list);
+  uint32_t* nan_flag = lists_pos + n_list;
 
 #ifdef UAVDET_NMS_PROFILE
   long long pt0 = clock64(), p_sort = 0, p_loop = 0, pt;
@@ -415,10 +432,10 @@ nms_image_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
     S.n_valid = 0;
     for (int q = 0; q < kSlots; ++q) {
       sm100::mbar_init(sm100::smem_u32(&S.full[q]), 1);
-      sm100::mbar_init(sm100::smem_u32(&S.empty[q]), ncta * kNmsWarps);
+      sm100::mbar_init(sm100::smem_u32(&S.empty[q]), ncta * kSweepWarps);
     }
     sm100::fence_barrier_init();
-    for (int q = 0; q < kSlots; ++q) sm100::mbar_arrive_expect_tx(sm100::smem_u32(&S.full[q]), kSlotTxBytes);
+    if (rank == 0) *nan_flag = 0u;
   }
   __syncthreads();
   int local_valid = 0;
@@ -502,51 +519,76 @@ nms_image_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
   __syncthreads();
   const uint32_t* order = valA;  // after 4 passes the result is back in the A buffers
 
-  // ---- 3. gather boxes into score order (CTA 0), clear the removed bits --------------------
+  // ---- 3. every warp gathers its own candidates ------------------------------------------------
+  // CTA 0's sort result must be visible to the whole cluster (and every CTA must be running before the first
+  // distributed-shared-memory access below)
+  if (ncta > 1) cluster_sync_all(); else __syncthreads();
   const int nv = S.n_valid;
-  const float4* boxes4 = reinterpret_cast<const float4*>(boxes);
-  uint32_t* nan_flag = reinterpret_cast<uint32_t*>(sbox + n_pad);
-  if (rank == 0) {
-    if (tid == 0) S.has_nan = 0;
-    __syncthreads();
-    bool nan = false;
-    for (int i = tid; i < nv; i += kNmsThreads) {
-      const float4 b = boxes4[order[i]];
-      sbox[i] = b;
-      nan |= (b.x != b.x) | (b.y != b.y) | (b.z != b.z) | (b.w != b.w);
-    }
-    if (__any_sync(0xffffffffu, nan) && lane == 0) S.has_nan = 1;
-    __syncthreads();
-    if (tid == 0) *nan_flag = (uint32_t)S.has_nan;
+  const int n_chunks = (nv + kChunk - 1) / kChunk;
+  const int cap = list_capacity(n, (int)ncta);  // entries per warp
+  float4* lbox = lists_box + (size_t)(rank * kSweepWarps + warp) * cap;
+  uint32_t* lpos = lists_pos + (size_t)(rank * kSweepWarps + warp) * cap;
+  if (lists_in_smem) {  // the CTA's lists fit behind NmsSmem (decided by the host from n and the cluster size)
+    float4* base = reinterpret_cast<float4*>(smem_raw + kSmemListOffset);
+    lbox = base + (size_t)warp * cap;
+    lpos = reinterpret_cast<uint32_t*>(base + (size_t)kSweepWarps * cap) + (size_t)warp * cap;
   }
-  const int n_words = (nv + 31) >> 5;
-  for (int i = tid; i < n_words + 2; i += kNmsThreads) removed[i] = 0;
-  // makes CTA 0's sorted boxes / order / flag visible to the other CTAs, and guarantees every CTA of the cluster
-  // is running before any distributed-shared-memory store below
+  const float4* boxes4 = reinterpret_cast<const float4*>(boxes);
+  int L = 0;
+  bool nan = false, odd = false;  // odd: not "benign" in the sense of iou_code's kMode 0
+  for (int t = 0; warp < kSweepWarps; ++t) {
+    const int c = (int)rank + (t * kSweepWarps + warp) * (int)ncta;
+    if (c >= n_chunks) break;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int p = c * kChunk + h * 32 + lane;
+      if (p < nv) {
+        const float4 b = boxes4[order[p]];
+        lbox[t * kChunk + h * 32 + lane] = b;
+        lpos[t * kChunk + h * 32 + lane] = (uint32_t)p;
+        nan |= (b.x != b.x) | (b.y != b.y) | (b.z != b.z) | (b.w != b.w);
+        const float a = box_area(b);
+        const bool area_ok = a == 0.f || (a >= 0x1p-90f && a <= 0x1p90f);
+        const bool finite = fabsf(b.x) < INFINITY && fabsf(b.y) < INFINITY && fabsf(b.z) < INFINITY && fabsf(b.w) < INFINITY;
+        odd |= !(finite && b.z >= b.x && b.w >= b.y && area_ok);
+      }
+    }
+    L += min(kChunk, nv - c * kChunk);
+  }
+  if (__any_sync(0xffffffffu, nan) && lane == 0) atomicOr(nan_flag, 1u);
+  if (__any_sync(0xffffffffu, odd) && lane == 0) atomicOr(nan_flag, 2u);
   if (ncta > 1) cluster_sync_all(); else __syncthreads();
   NMS_PROF(p_sort);
 
-  // ---- 4. chunked greedy suppression ------------------------------------------------------
-  const float thr_fast = (thr >= 1e-6f && thr <= 1e6f) ? thr : __int_as_float(0x7fc00000);
-  int kept_total;
-  if (*nan_flag)
-    kept_total = suppress<true>(S, removed, sbox, order, keep, nv, thr, thr_fast, ncta, rank);
-  else
-    kept_total = suppress<false>(S, removed, sbox, order, keep, nv, thr, thr_fast, ncta, rank);
+  // ---- 4. greedy suppression --------------------------------------------------------------
+  const bool thr_ok = thr >= 1e-6f && thr <= 1e6f;
+  const float thr_fast = thr_ok ? thr : __int_as_float(0x7fc00000);
+  const uint32_t flags = *reinterpret_cast<volatile uint32_t*>(nan_flag);
+  int kept_total = 0;
+  if (warp >= kSweepWarps) {
+  } else if (flags & 1u) {
+    kept_total = suppress<2>(S, lbox, lpos, L, order, keep, n_chunks, thr, thr_fast, 0.f, ncta, rank);
+  } else if ((flags & 2u) || !thr_ok) {
+    kept_total = suppress<1>(S, lbox, lpos, L, order, keep, n_chunks, thr, thr_fast, 0.f, ncta, rank);
+  } else {
+    kept_total = suppress<0>(S, lbox, lpos, L, order, keep, n_chunks, thr, t_hi, t_lo, ncta, rank);
+  }
   if (rank == 0 && tid == 0) keep_count[img] = kept_total;
   // tail of `keep` beyond keep_count is left untouched (caller slices by count)
-  // no CTA may leave while another can still arrive on its barriers
-  if (ncta > 1) cluster_sync_all();
 #ifdef UAVDET_NMS_PROFILE
   NMS_PROF(p_loop);
   if (tid == 0 && img == 0)
-    printf("nms rank %u/%u: sort %lld loop %lld cycles, kept %d\n", rank, ncta, p_sort, p_loop, kept_total);
+    printf("nms rank %u/%u: sort+gather %lld loop %lld cycles, kept %d\n", rank, ncta, p_sort, p_loop, kept_total);
 #endif
+  // no CTA may leave while another can still arrive on its barriers
+  if (ncta > 1) cluster_sync_all();
 }
 
 static size_t nms_ws_per_image(int n) {
   size_t n_pad = ((size_t)n + 3) & ~(size_t)3;
-  size_t bytes = n_pad * 4 * sizeof(uint32_t) + n_pad * sizeof(float4) + 16;  // + the has-NaN flag
+  // keys/values ping-pong, the per-warp lists (box + sorted position; every warp's capacity is rounded up to
+  // whole 64-entry trips, hence the slack), the has-NaN flag
+  size_t bytes = n_pad * 4 * sizeof(uint32_t) + (n_pad + kListSlack) * (sizeof(float4) + sizeof(uint32_t)) + 16;
   return (bytes + 255) & ~(size_t)255;
 }
 
@@ -579,8 +621,7 @@ extern "C" int uavdet_nms(const float* boxes, const float* scores, int batch, in
   // largest float <= thr gives the identical predicate in fp32.
   float thr_f = (float)iou_thr;
   if ((double)thr_f > iou_thr) thr_f = nextafterf(thr_f, -INFINITY);
-  size_t smem = sizeof(NmsSmem) + (((size_t)n + 31) / 32) * 4 + 32;
-  UAVDET_CHECK_ARG(smem <= 227 * 1024, "nms: n=%d too large for the shared bit array", n);
+  size_t smem = kSmemListOffset + 16;
   static bool attr_set = false;
   if (!attr_set) {
     UAVDET_CUDA(cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -594,6 +635,17 @@ extern "C" int uavdet_nms(const float* boxes, const float* scores, int batch, in
     int v = atoi(e);
     if (v == 1 || v == 2 || v == 4 || v == 8) ncta = v;
   }
+  // candidate lists in shared memory when the CTA's share fits, else in the workspace
+  const size_t list_bytes = (size_t)kSweepWarps * list_capacity(n, ncta) * (sizeof(float4) + sizeof(uint32_t));
+  int lists_in_smem = (kSmemListOffset + list_bytes + 16 <= 227 * 1024) ? 1 : 0;
+  if (const char* e = getenv("UAVDET_NMS_SMEM_LISTS")) lists_in_smem = lists_in_smem && atoi(e) != 0;
+  if (lists_in_smem) smem += list_bytes;
+  // iou_code's kMode 0 constants (see there), rounded away from the threshold
+  const double th = (double)thr_f * (1.0 + 0x1p-21), tl = (double)thr_f * (1.0 - 0x1p-21);
+  const double t_hi_d = th / (1.0 + th) * (1.0 + 0x1p-22), t_lo_d = tl / (1.0 + tl) * (1.0 - 0x1p-22);
+  float t_hi = (float)t_hi_d, t_lo = (float)t_lo_d;
+  if ((double)t_hi < t_hi_d) t_hi = nextafterf(t_hi, INFINITY);
+  if ((double)t_lo > t_lo_d) t_lo = nextafterf(t_lo, -INFINITY);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)batch * ncta);
   cfg.blockDim = dim3(kNmsThreads);
@@ -607,7 +659,7 @@ extern "C" int uavdet_nms(const float* boxes, const float* scores, int batch, in
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   UAVDET_CUDA(cudaLaunchKernelEx(&cfg, nms_image_kernel, boxes, scores, n, thr_f, score_floor, keep, keep_count,
-                                 (uint8_t*)workspace, nms_ws_per_image(n)));
+                                 (uint8_t*)workspace, nms_ws_per_image(n), lists_in_smem, t_hi, t_lo));
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }

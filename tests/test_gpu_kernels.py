@@ -73,6 +73,46 @@ def test_nms_matches_oracle_bit_exact(lib, n, quant, thr):
     assert np.array_equal(got, want), f"n={n}: kept {len(got)} vs {len(want)}"
 
 
+@pytest.mark.parametrize("thr", [0.5, 1.0 / 3.0, 0.2, 0.6, 0.25])
+@pytest.mark.parametrize("scale", [1.0, 2.0 ** -60, 2.0 ** 50, 2.0 ** -47, 3e18])
+def test_nms_threshold_ties(lib, thr, scale):
+    """Small-integer boxes: a large share of the pairs has an IoU exactly on (or one rounding away from) the
+    threshold, which is where the division-free tests must hand over to the exact quotient.  The scales move the
+    areas towards / past the bounds of the fast tests' validity range (subnormal and overflowing areas)."""
+    from oracle import oracle as O
+    ops = _ops(lib)
+    g = torch.Generator().manual_seed(int(thr * 1000) + 7)
+    n = 3000
+    xy = torch.randint(0, 10, (n, 2), generator=g).float()
+    wh = torch.randint(1, 7, (n, 2), generator=g).float()
+    boxes = (torch.cat([xy, xy + wh], 1) * scale).float()
+    scores = torch.randn(n, generator=g)
+    want = O.nms(boxes.numpy(), scores.numpy(), thr)
+    got = ops.nms(boxes.to(DEV), scores.to(DEV), thr).cpu().numpy()
+    ops.check_device()
+    assert np.array_equal(got, want), f"kept {len(got)} vs {len(want)}"
+
+
+def test_nms_odd_boxes(lib):
+    """Boxes that leave the benign class: inverted extents, infinities and NaN coordinates mixed into ordinary ones
+    (each variant selects another arithmetic mode of the kernel)."""
+    from oracle import oracle as O
+    import torchvision
+    ops = _ops(lib)
+    g = torch.Generator().manual_seed(11)
+    base, scores = _random_boxes(4000, g)
+    variants = {}
+    b = base.clone(); b[::7, [0, 2]] = b[::7, [2, 0]]; variants["inverted"] = b
+    b = base.clone(); b[::11, 2] = float("inf"); b[5::13, 0] = float("-inf"); variants["inf"] = b
+    b = base.clone(); b[::9, 1] = float("nan"); b[3::17, 2] = float("nan"); variants["nan"] = b
+    b = base.clone(); b[::5] *= 1e-30; variants["tiny"] = b
+    for name, b in variants.items():
+        want = torchvision.ops.nms(b, scores, 0.5).numpy()
+        assert np.array_equal(O.nms(b.numpy(), scores.numpy(), 0.5), want), name
+        got = ops.nms(b.to(DEV), scores.to(DEV), 0.5).cpu().numpy()
+        assert np.array_equal(got, want), f"{name}: kept {len(got)} vs {len(want)}"
+
+
 def test_nms_edge_cases(lib):
     from oracle import oracle as O
     ops = _ops(lib)

@@ -1,6 +1,9 @@
-"""Phase breakdown of the NMS kernel (needs a library built with -DUAVDET_NMS_PROFILE; see below) on the C1
-candidate distribution.  Usage on the GPU box:
-  nvcc ... -DUAVDET_NMS_PROFILE (tools/prof_nms.py --build does it into a scratch library and restores the product one)"""
+"""Phase breakdown of the NMS kernel on the C1 candidate distribution (25,200 candidates, no score floor).
+Needs the library built with the kernel's cycle counters compiled in:
+  cd multimodal_uav_det_b200 && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC \
+     --expt-relaxed-constexpr -DUAVDET_NMS_PROFILE -c csrc/nms.cu -o build/nms.o && \
+     nvcc -shared -o libuavdet_b200.so build/*.o -gencode arch=compute_100a,code=sm_100a
+(then `python -m multimodal_uav_det_b200.build --force` restores the product library).  Arguments: cluster sizes."""
 import os, sys, subprocess
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
