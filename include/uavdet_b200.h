@@ -94,6 +94,20 @@ int uavdet_decode_rtm(const float* bbox_sig, int batch, int A, int S_h, int S_w,
 /* cxcywh (.., 4) -> xyxy, torchvision box_convert arithmetic (_base.py:246). */
 int uavdet_cxcywh_to_xyxy(const float* in, float* out, int64_t count, void* stream);
 
+/* ---- target encoder ----------------------------------------------------- */
+/* AntiUAVDataset.__generate_yolo_bboxes (dataset/AntiUAVDataset.py:141-185) with calculate_anchor_iou
+ * (dataset/_helper.py:308-330) for a batch: boxes_xyxy (batch,4) fp32 pixels on the device, one target per
+ * frame; valid (batch) bytes or NULL (0 = frame without target -> all-zero targets, :142-143);
+ * anchors_norm_host (heads, num_anchors, 2) = anchors / input_size evaluated by the caller in fp32
+ * (AntiUAVDataset.py:27); grids_host (heads) = S per head; targets_host = `heads` DEVICE pointers to
+ * (batch, num_anchors, S, S, 5) fp32 [obj, cx_off, cy_off, w_cells, h_cells], fully written (zero-filled
+ * first).  out_of_grid (device u32) counts frames whose centre falls outside the grid -- the reference raises
+ * IndexError there; such frames get all-zero targets.  Bit-identical to the CPU encoder.               */
+int uavdet_encode_targets(const float* boxes_xyxy, const uint8_t* valid, int batch,
+                          const float* anchors_norm_host, int heads, int num_anchors,
+                          const int* grids_host, float input_size, float* const* targets_host,
+                          unsigned int* out_of_grid, void* stream);
+
 /* ---- detection loss ----------------------------------------------------- */
 /* One head scale of YOLOHead.compute_metrics (model/_base.py:155-192 with utils/metrics.py:8-84,
  * utils/postprocess.py:51-85, _base.py:214-270) for the whole batch, forward AND gradient:

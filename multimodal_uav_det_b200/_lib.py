@@ -46,6 +46,7 @@ SIGNATURES = {
     "uavdet_nms_workspace_bytes": (_sz, [_i, _i]),
     "uavdet_nms": (_i, [_P, _P, _i, _i, _d, _f, _P, _P, _P, _sz, _P]),
     "uavdet_decode_yolo": (_i, [_P, _P, _i, _i, _i, _i, C.POINTER(_f), _i, _P, _P, _i, _i, _P]),
+    "uavdet_encode_targets": (_i, [_P, _P, _i, C.POINTER(_f), _i, _i, C.POINTER(_i), _f, C.POINTER(_P), _P, _P]),
     "uavdet_decode_rtm": (_i, [_P, _i, _i, _i, _i, C.POINTER(_f), _P, _P]),
     "uavdet_cxcywh_to_xyxy": (_i, [_P, _P, _i64, _P]),
     "uavdet_yolo_head_loss_workspace_bytes": (_sz, [_i]),

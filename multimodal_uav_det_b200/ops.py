@@ -128,6 +128,43 @@ def decode_yolo(outs: Sequence, anchors, head_scales, ciou: bool) -> Tuple[torch
     return boxes, scores
 
 
+def encode_targets(boxes_xyxy: torch.Tensor, anchors, grids: Sequence[int], input_size: int = 640,
+                   valid: torch.Tensor = None, check_grid: bool = True, out: list = None) -> list:
+    """GPU form of AntiUAVDataset.__generate_yolo_bboxes (dataset/AntiUAVDataset.py:141-185) for a batch with one
+    target box per frame: boxes_xyxy (B,4) fp32 pixels on the device -> per head (B,A,S,S,5) fp32
+    [obj, cx_off, cy_off, w_cells, h_cells], bit-identical to the CPU encoder.  `anchors` are the pixel anchors
+    (heads, A, 2) of the model config; `grids` the S of every head; `valid` (B,) bool marks frames that have a
+    target.  check_grid=True reads back the out-of-grid counter (one sync) and raises IndexError like the reference;
+    pass False inside CUDA graphs / latency-critical loops.  `out`: preallocated per-head tensors to write into."""
+    lib = _lib.load()
+    boxes_xyxy = _f32(boxes_xyxy)
+    _require_cuda(boxes_xyxy)
+    b = boxes_xyxy.shape[0]
+    assert boxes_xyxy.shape == (b, 4), f"Expected bbox shape (B,4), got {tuple(boxes_xyxy.shape)}"
+    anc = torch.tensor(anchors).float() / input_size   # fp32, exactly as the data set normalises them (:27)
+    heads, a = anc.shape[0], anc.shape[1]
+    assert len(grids) == heads
+    dev = boxes_xyxy.device
+    outs = out if out is not None else [torch.empty((b, a, s, s, 5), dtype=torch.float32, device=dev) for s in grids]
+    for o, s_ in zip(outs, grids):
+        assert o.shape == (b, a, s_, s_, 5) and o.dtype == torch.float32 and o.is_contiguous() and o.device == dev
+    counter = torch.empty(1, dtype=torch.int32, device=dev)
+    flat = anc.flatten().tolist()
+    anc_arr = (C.c_float * len(flat))(*flat)
+    grid_arr = (C.c_int * heads)(*[int(s) for s in grids])
+    ptrs = (C.c_void_p * heads)(*[o.data_ptr() for o in outs])
+    v = None
+    if valid is not None:
+        v = valid.to(device=dev, dtype=torch.uint8).contiguous()
+    check(lib.uavdet_encode_targets(_ptr(boxes_xyxy), _ptr(v) if v is not None else None, b, anc_arr, heads, a, grid_arr,
+                                    float(input_size), ptrs, _ptr(counter), _stream()), "encode_targets")
+    if check_grid and b:
+        bad = int(counter.item())
+        if bad:
+            raise IndexError(f"{bad} target centre(s) outside the grid (the reference encoder raises here too)")
+    return outs
+
+
 def decode_rtm(bbox_sig: torch.Tensor, anchors_head) -> torch.Tensor:
     lib = _lib.load()
     _require_cuda(bbox_sig)

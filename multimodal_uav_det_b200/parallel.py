@@ -161,13 +161,23 @@ class GraphedTrainStep:
     The graph holds the per-step activation memory in its private pool.  Capturing needs a few eager
     warm-up steps first (lazy initialisation, cuTensorMap entry point, allocator warm-up); they are run
     here on a side stream and DO update the parameters (they are ordinary training steps on the example
-    batch) unless `warmup=0`."""
+    batch) unless `warmup=0`.
 
-    def __init__(self, model, trainer: FlatSGDTrainer, x: torch.Tensor, targets, warmup: int = 2):
+    With `encoder` (a `utils.targets.YoloTargetEncoder`) the step takes the raw `(B, 4)` pixel boxes instead of the
+    dense per-head targets: `targets` is then that box tensor everywhere (constructor, `load`, `prefetch`,
+    `__call__`) and the dense targets are produced on the device right before the replay."""
+
+    def __init__(self, model, trainer: FlatSGDTrainer, x: torch.Tensor, targets, warmup: int = 2, encoder=None):
         from .utils.datatype import BatchData
         self.model, self.trainer = model, trainer
         self.x = x.detach().clone().float().contiguous()
-        self.targets = [t.detach().clone() for t in targets]
+        self.encoder = encoder
+        if encoder is not None:
+            self.boxes = targets.detach().clone().float().contiguous()
+            self.targets = encoder(self.boxes)
+        else:
+            self.boxes = None
+            self.targets = [t.detach().clone() for t in targets]
         head = model.yolo_head
         for h in range(len(self.targets)):
             head._scaled_anchors(h, self.x.device)      # host->device constants must exist before capture
@@ -204,7 +214,8 @@ class GraphedTrainStep:
         """Start copying the NEXT batch (pinned host or device tensors) into staging buffers on a side stream;
         the following `run_prefetched()` consumes it.  The copy overlaps whatever the main stream is running."""
         if self._stage is None:
-            self._stage = (torch.empty_like(self.x), [torch.empty_like(t) for t in self.targets])
+            self._stage = (torch.empty_like(self.x),
+                           [torch.empty_like(self.boxes)] if self.encoder is not None else [torch.empty_like(t) for t in self.targets])
             self._copy_stream = torch.cuda.Stream(device=self.x.device)
             self._staged = torch.cuda.Event()
             self._consumed = torch.cuda.Event()
@@ -212,7 +223,7 @@ class GraphedTrainStep:
         with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_event(self._consumed)     # the previous staged batch has been taken over
             self._stage[0].copy_(x, non_blocking=True)
-            for dst, src in zip(self._stage[1], targets):
+            for dst, src in zip(self._stage[1], [targets] if self.encoder is not None else targets):
                 dst.copy_(src, non_blocking=True)
             self._staged.record()
 
@@ -221,8 +232,12 @@ class GraphedTrainStep:
         cur = torch.cuda.current_stream()
         cur.wait_event(self._staged)
         self.x.copy_(self._stage[0], non_blocking=True)
-        for dst, src in zip(self.targets, self._stage[1]):
-            dst.copy_(src, non_blocking=True)
+        if self.encoder is not None:
+            self.boxes.copy_(self._stage[1][0], non_blocking=True)
+            self.encoder(self.boxes, check_grid=False, out=self.targets)
+        else:
+            for dst, src in zip(self.targets, self._stage[1]):
+                dst.copy_(src, non_blocking=True)
         self._consumed.record()
         return self()
 
@@ -230,13 +245,18 @@ class GraphedTrainStep:
         """Stage a batch into the static buffers (asynchronous on the current stream)."""
         if x is not self.x:
             self.x.copy_(x, non_blocking=True)
+        if self.encoder is not None:
+            if targets is not self.boxes:
+                self.boxes.copy_(targets, non_blocking=True)
+            self.encoder(self.boxes, check_grid=False, out=self.targets)
+            return
         for dst, src in zip(self.targets, targets):
             if src is not dst:
                 dst.copy_(src, non_blocking=True)
 
     def __call__(self, x: Optional[torch.Tensor] = None, targets=None) -> torch.Tensor:
         if x is not None:
-            self.load(x, targets if targets is not None else self.targets)
+            self.load(x, targets if targets is not None else (self.boxes if self.encoder is not None else self.targets))
         self.graph.replay()
         bump_param_epoch()      # parameters were rewritten on the device: packed-weight caches are stale
         return self.loss

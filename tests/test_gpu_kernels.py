@@ -817,3 +817,40 @@ def test_fused_yolo_head_loss_matches_batched_torch_loss(lib, loss_fn, grid):
     torch.testing.assert_close(p_obj.grad, go_ref, rtol=1e-4, atol=1e-7)
     torch.testing.assert_close(p_bbox.grad, gb_ref, rtol=2e-4, atol=1e-6)
     assert (p_bbox.grad != 0).sum() > 0
+
+
+# ------------------------------------------------------------------------------------------------
+# target encoder
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("grids,anchors", [
+    ([20, 40, 80], [[[116, 90], [156, 198], [373, 326]], [[30, 61], [62, 45], [59, 119]], [[10, 13], [16, 30], [33, 23]]]),
+    ([320, 160, 80], [[[10, 13], [16, 30], [33, 23]], [[30, 61], [62, 45], [59, 119]], [[116, 90], [156, 198], [373, 326]]]),
+])
+def test_encode_targets_matches_cpu_encoder_bit_exact(lib, grids, anchors):
+    """GPU target encoder vs the oracle's restatement of AntiUAVDataset.__generate_yolo_bboxes (itself pinned to
+    the reference encoder by tests/test_oracle.py), bit for bit, on boxes that cover every branch: tiny
+    targets (best anchor only), targets matching one or several anchors with IoU >= 0.5, centres on cell edges."""
+    from oracle import oracle as O
+    ops = _ops(lib)
+    g = torch.Generator().manual_seed(3)
+    n = 256
+    c = torch.rand(n, 2, generator=g) * 600 + 20
+    wh = torch.cat([torch.rand(n // 2, 2, generator=g) * 60 + 4, torch.rand(n // 2, 2, generator=g) * 380 + 20])
+    boxes = torch.cat([c - wh / 2, c + wh / 2], 1).clamp(0, 639.5)
+    boxes[:8, :2] = torch.tensor([32.0, 64.0]); boxes[:8, 2:] = torch.tensor([96.0, 128.0])   # centre exactly on a cell edge
+    boxes[8:16] = torch.tensor([100.0, 100.0, 216.0, 190.0])                                   # == an anchor's size
+    valid = torch.ones(n, dtype=torch.bool); valid[5::17] = False
+    got = ops.encode_targets(boxes.to(DEV), anchors, grids, 640, valid=valid.to(DEV))
+    ops.check_device()
+    multi = 0
+    for i in range(n):
+        want = O.encode_targets(boxes[i:i + 1], anchors, None, 640, grids=grids) if valid[i] else \
+            [torch.zeros(3, s, s, 5) for s in grids]
+        for h in range(len(grids)):
+            assert torch.equal(got[h][i].cpu(), want[h]), f"frame {i} head {h}"
+            multi += int(want[h][..., 0].sum() > 1)
+    assert multi > 0, "no target matched several anchors; the test lost a branch"
+    # out-of-grid centre: the reference raises IndexError
+    bad = torch.tensor([[630.0, 10.0, 660.0, 40.0]])
+    with pytest.raises(IndexError):
+        ops.encode_targets(bad.to(DEV), anchors, grids, 640)
