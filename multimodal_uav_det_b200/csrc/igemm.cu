@@ -52,12 +52,12 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& P, int tile)
 
 // 32 accumulator columns of this lane's row -> (scale, shift, act, residual), in place.
 template <int ACT>
-__device__ __forceinline__ void affine_act(float (&v)[32], const IgemmParams& P, int cg, const float* shift,
-                                           const __nv_bfloat16* res_px) {
-  if (P.scale) {
+__device__ __forceinline__ void affine_act(float (&v)[32], const float* scale, int cg, const float* shift,
+                                           const uint4 (&res)[4], bool have_res) {
+  if (scale) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      float4 s = __ldg(reinterpret_cast<const float4*>(P.scale + cg + i));
+      float4 s = __ldg(reinterpret_cast<const float4*>(scale + cg + i));
       v[i] *= s.x; v[i + 1] *= s.y; v[i + 2] *= s.z; v[i + 3] *= s.w;
     }
   }
@@ -70,10 +70,10 @@ __device__ __forceinline__ void affine_act(float (&v)[32], const IgemmParams& P,
   }
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = act_fwd<ACT>(v[i]);
-  if (res_px) {
+  if (have_res) {
 #pragma unroll
     for (int i = 0; i < 32; i += 8) {
-      uint4 rr = __ldg(reinterpret_cast<const uint4*>(res_px + cg + i));
+      const uint4 rr = res[i >> 3];
       v[i] += bf16_lo(rr.x); v[i + 1] += bf16_hi(rr.x);
       v[i + 2] += bf16_lo(rr.y); v[i + 3] += bf16_hi(rr.y);
       v[i + 4] += bf16_lo(rr.z); v[i + 5] += bf16_hi(rr.z);
@@ -86,22 +86,20 @@ __device__ __forceinline__ void affine_act(float (&v)[32], const IgemmParams& P,
 // `chunk_in_slab` = which 32-column half of the (64-wide) slab; `sw_mask` = the row's swizzle XOR.
 // Deliberately NOT inlined: it is called from 13 sites and carries the 5-way activation switch; inlined, the kernel
 // grew to 37,000 instructions (595 KB) and the epilogue warps thrashed the instruction cache.
-__device__ __noinline__ void stage_chunk(const IgemmParams& P, uint32_t taddr, int cg, bool valid, const float* shift,
-                                            const __nv_bfloat16* res_px, uint8_t* srow, int chunk_in_slab, int sw_mask,
-                                            bool release, uint32_t tempty, int lane) {
-  uint32_t r[32];
-  tmem_ld_32x32(taddr, r);
-  tmem_ld_wait();
-  if (release) {
-    // last TMEM read of this tile by this warp: hand the accumulator buffer back to the MMA warp
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(tempty);
-  }
+// Everything it needs from the kernel parameters arrives in registers (`cfg`, `scale`): read through a reference,
+// the fields became a chain of control-dependent generic loads from the parameter bank (~1,000 cycles per call).
+//   cfg bit 0: statistics epilogue; bits 1-3: activation; bit 4: residual operand; bit 5: it is in the staging row
+__device__ __forceinline__ uint32_t chunk_cfg(const IgemmParams& P) {
+  return (P.epi == UAVDET_EPI_STATS ? 1u : 0u) | ((uint32_t)P.act << 1) | (P.res ? 16u : 0u) | (P.res_tma ? 32u : 0u);
+}
+// epilogue math of one 32-column chunk (accumulator values in r) + bf16 pack + swizzled staging store
+__device__ __forceinline__ void finish_chunk(uint32_t cfg, const float* scale, const uint32_t (&r)[32], int cg, bool valid,
+                                             const float* shift, const __nv_bfloat16* res_px, uint8_t* srow,
+                                             int chunk_in_slab, int sw_mask) {
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-  if (P.epi == UAVDET_EPI_STATS) {
+  if (cfg & 1u) {
     if (shift) {
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
@@ -110,12 +108,29 @@ __device__ __noinline__ void stage_chunk(const IgemmParams& P, uint32_t taddr, i
       }
     }
   } else if (valid) {
-    switch (P.act) {
-      case UAVDET_ACT_LEAKY: affine_act<UAVDET_ACT_LEAKY>(v, P, cg, shift, res_px); break;
-      case UAVDET_ACT_SILU: affine_act<UAVDET_ACT_SILU>(v, P, cg, shift, res_px); break;
-      case UAVDET_ACT_RELU: affine_act<UAVDET_ACT_RELU>(v, P, cg, shift, res_px); break;
-      case UAVDET_ACT_GELU: affine_act<UAVDET_ACT_GELU>(v, P, cg, shift, res_px); break;
-      default: affine_act<UAVDET_ACT_NONE>(v, P, cg, shift, res_px); break;
+    // residual operand of these 32 columns: already in the staging row (a TMA load put the residual tile exactly
+    // where the result is about to be written, see `res_tma`), or fetched from global memory
+    uint4 rr[4];
+    const bool have_res = (cfg & 16u) != 0u;
+    if (have_res) {
+      if (cfg & 32u) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          rr[j] = *reinterpret_cast<const uint4*>(srow + ((chunk_in_slab * 4 + j) ^ sw_mask) * 16);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rr[j] = __ldg(reinterpret_cast<const uint4*>(res_px + cg + 8 * j));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rr[j] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    switch ((cfg >> 1) & 7u) {
+      case UAVDET_ACT_LEAKY: affine_act<UAVDET_ACT_LEAKY>(v, scale, cg, shift, rr, have_res); break;
+      case UAVDET_ACT_SILU: affine_act<UAVDET_ACT_SILU>(v, scale, cg, shift, rr, have_res); break;
+      case UAVDET_ACT_RELU: affine_act<UAVDET_ACT_RELU>(v, scale, cg, shift, rr, have_res); break;
+      case UAVDET_ACT_GELU: affine_act<UAVDET_ACT_GELU>(v, scale, cg, shift, rr, have_res); break;
+      default: affine_act<UAVDET_ACT_NONE>(v, scale, cg, shift, rr, have_res); break;
     }
   }
   // rows outside the image / tile carry garbage or bias only: stage zeros (the clipped TMA store skips them and
@@ -130,6 +145,22 @@ __device__ __noinline__ void stage_chunk(const IgemmParams& P, uint32_t taddr, i
     const int chunk = (chunk_in_slab * 4 + j) ^ sw_mask;
     *reinterpret_cast<uint4*>(srow + chunk * 16) = o;
   }
+}
+
+
+__device__ __noinline__ void stage_chunk(uint32_t cfg, const float* scale, uint32_t taddr, int cg, bool valid,
+                                            const float* shift, const __nv_bfloat16* res_px, uint8_t* srow,
+                                            int chunk_in_slab, int sw_mask, bool release, uint32_t tempty, int lane) {
+  uint32_t r[32];
+  tmem_ld_32x32(taddr, r);
+  tmem_ld_wait();
+  if (release) {
+    // last TMEM read of this tile by this warp: hand the accumulator buffer back to the MMA warp
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty);
+  }
+  finish_chunk(cfg, scale, r, cg, valid, shift, res_px, srow, chunk_in_slab, sw_mask);
 }
 
 // MMA issue loop of one CTA (single elected thread), KSTEPS = block_k / 16.
@@ -180,6 +211,7 @@ __device__ __forceinline__ void mma_issue_loop(const IgemmParams& P, uint32_t ri
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
              const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapOutTail,
+             const __grid_constant__ CUtensorMap mapRes, const __grid_constant__ CUtensorMap mapResTail,
              const __grid_constant__ IgemmParams P) {
   // 1024-byte alignment is what SWIZZLE_128B needs for TMA and UMMA; no static shared memory is used,
   // so the dynamic window starts at the (aligned) base of the CTA's shared memory.
@@ -204,8 +236,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   uint64_t* bres_bar = tempty_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
   volatile uint32_t* dead = tmem_ptr + 1;
+  // residual-tile loads of the warp-private epilogues: one barrier per (epilogue warp, staging buffer)
+  uint64_t* rres_bar = reinterpret_cast<uint64_t*>(ctrl + 8 * (2 * kMaxStages + 5) + 16);
 
   if (threadIdx.x == 0) {
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(smem_u32(&rres_bar[i]), 1);
     for (int s = 0; s < P.stages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
@@ -223,6 +258,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     prefetch_tensormap(&mapA);
     prefetch_tensormap(&mapB);
     if (P.epi != UAVDET_EPI_HEAD) prefetch_tensormap(&mapOut);
+    if (P.res_tma) prefetch_tensormap(&mapRes);
   }
   if (warp == kMmaWarp) {
     tmem_alloc(smem_u32(tmem_ptr), 512);
@@ -307,6 +343,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const int row_bytes = P.slab_w * 2;
     const int sw_mask = (P.slab_w == 64) ? (row & 7) : ((row >> 1) & 3);
     int acc = 0;
+    const uint32_t ccfg = chunk_cfg(P);
     uint32_t acc_phase = 0;
 
     if (P.epi == UAVDET_EPI_HEAD) {
@@ -367,6 +404,31 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       for (int j = 0; j < 4; ++j) { st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f; }
       int cur_n0 = -1;
       uint32_t ucount = 0;
+      uint32_t rphase = 0;                 // bit b: parity of the next residual load into staging buffer b
+      // Take the next staging buffer (its last TMA store must be done reading it) and, when the layer adds a
+      // residual, start the TMA load of the residual tile for (tile tc, slab starting at channel cs) into it --
+      // same map geometry as the store, so the bytes land where the result will be written.  Issued before the
+      // wait for the accumulator: the load's latency hides behind the tile's main loop.
+      auto acquire = [&](const TileCoord& tc, int cs) -> uint8_t* {
+        const uint32_t b = (P.epi_bufs == 2) ? (ucount & 1u) : 0u;
+        uint8_t* wbuf = wbuf0 + b * wbuf_bytes;
+        ++ucount;
+        if (lane == 0) {
+          if (P.epi_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+          if (P.res_tma && rows_here > 0) {
+            const uint32_t bar = smem_u32(&rres_bar[ew * 2 + b]);
+            if (P.epi_mode == 1) {
+              mbar_arrive_expect_tx(bar, (uint32_t)(32 * row_bytes));
+              tma_load_5d(smem_u32(wbuf), &mapRes, bar, cs, tc.ow0 + q_ow, 0, tc.oh0 + q_oh, tc.img);
+            } else {
+              mbar_arrive_expect_tx(bar, (uint32_t)(rows_here * row_bytes));
+              tma_load_3d(smem_u32(wbuf), use_tail ? &mapResTail : &mapRes, bar, cs, tc.oh0 * P.wo + q * 32, tc.img);
+            }
+          }
+        }
+        __syncwarp();
+        return wbuf;
+      };
       auto flush_stats = [&](int n0) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -407,6 +469,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             P.res ? P.res + (size_t)tc.img * P.res_sn + (size_t)oh * P.res_sh + (size_t)ow * P.res_sw : nullptr;
         const float* shift = P.shift ? P.shift + (size_t)tc.img * P.shift_sn : nullptr;
         if (tr) P.trace[tl * 16 + 5] = clock64();
+        // this warp's first slab of the tile: buffer + residual load before the accumulator is awaited
+        const int sl_first = single ? 0 : half;
+        uint8_t* wbuf_first = (sl_first < n_slabs) ? acquire(tc, tc.n0 + sl_first * P.slab_w) : nullptr;
         mbar_wait<64>(smem_u32(&tfull_bar[acc]), acc_phase, dead, P.watchdog, 0x8u);
         if (tr) P.trace[tl * 16 + 6] = clock64();
         tc_fence_after();
@@ -418,25 +483,24 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             const int sl = single ? 0 : half + 2 * j;
             if (sl < n_slabs && (!single || j == 0)) {
               const int cs = tc.n0 + sl * P.slab_w;                  // first global channel of the slab
-              uint8_t* wbuf = wbuf0 + (P.epi_bufs == 2 ? (ucount & 1u) * wbuf_bytes : 0);
-              ++ucount;
-              // the TMA store that last read this buffer must be done reading it
               if (tr) P.trace[tl * 16 + 8] = clock64();
-              if (lane == 0) {
-                if (P.epi_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+              uint8_t* wbuf = (j == 0) ? wbuf_first : acquire(tc, cs);
+              if (P.res_tma && rows_here > 0) {
+                const uint32_t b = (uint32_t)(wbuf != wbuf0);
+                mbar_wait<0>(smem_u32(&rres_bar[ew * 2 + b]), (rphase >> b) & 1u, dead, P.watchdog, 0x10u);
+                rphase ^= 1u << b;
               }
-              __syncwarp();
               if (tr) P.trace[tl * 16 + 9] = clock64();
               const bool last = single || (sl + 2 >= n_slabs);
               uint8_t* srow = wbuf + lane * row_bytes;
               const int c0 = sl * P.slab_w;                          // accumulator column of the slab
               if (P.slab_w == 64) {
-                stage_chunk(P, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, srow, 0, sw_mask, false,
+                stage_chunk(ccfg, P.scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, srow, 0, sw_mask, false,
                             tempty, lane);
-                stage_chunk(P, tbase + (uint32_t)(c0 + 32), tc.n0 + c0 + 32, valid, shift, res_px, srow, 1, sw_mask,
+                stage_chunk(ccfg, P.scale, tbase + (uint32_t)(c0 + 32), tc.n0 + c0 + 32, valid, shift, res_px, srow, 1, sw_mask,
                             last, tempty, lane);
               } else {
-                stage_chunk(P, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, srow, 0, sw_mask, last, tempty,
+                stage_chunk(ccfg, P.scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, srow, 0, sw_mask, last, tempty,
                             lane);
               }
               if (tr) P.trace[tl * 16 + 10] = clock64();
@@ -519,7 +583,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           const bool last = sl == n_slabs - 1;
           if (half < chunks_per_slab) {
             const int c0 = sl * P.slab_w + half * 32;
-            stage_chunk(P, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, sbuf + row * row_bytes, half,
+            stage_chunk(ccfg, P.scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, sbuf + row * row_bytes, half,
                         sw_mask, last, tempty, lane);
             fence_proxy_async();
           } else if (last) {
@@ -730,6 +794,16 @@ int fill_plane(const IgemmParams& P, cudaStream_t st) {
   return UAVDET_OK;
 }
 
+// UAVDET_IGEMM_RES_TMA=0 keeps the residual operand on the per-lane global loads (debug / A-B switch)
+static bool res_tma_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UAVDET_IGEMM_RES_TMA");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 static int pick_block_n(int cout) {
   if (cout <= 16) return 16;
   for (int bn = 256; bn >= 32; bn -= 32)
@@ -740,9 +814,10 @@ static int pick_block_n(int cout) {
 int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int w_rows, int k_total,
                  int w_batch, IgemmParams& P, cudaStream_t st, int w_batch_rows = 0) {
   if (w_batch_rows <= 0) w_batch_rows = w_rows;   // rows between the weight matrices of consecutive samples
-  CUtensorMap mapA, mapB, mapOut, mapOutTail;
+  CUtensorMap mapA, mapB, mapOut, mapOutTail, mapRes, mapResTail;
   int rc = make_act_map(&mapA, a_src, parity, P.block_k, P.tile_w, P.tile_h);
   if (rc) return rc;
+  P.res_tma = 0;
   P.slab_w = (P.block_n % 64 == 0) ? 64 : 32;
   const int kp = P.tile_w * P.tile_h;
   if (P.epi == UAVDET_EPI_HEAD) {
@@ -754,6 +829,14 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
     rc = make_out_map(&mapOut, P.out, P.n_img, P.ho, P.wo, P.cout, P.out_sn, P.out_sh, P.out_sw, P.slab_w, bw, 32 / bw);
     if (rc) return rc;
     mapOutTail = mapOut;
+    if (P.res && res_tma_enabled()) {
+      // the residual tile comes in through the same box as the result goes out
+      rc = make_out_map(&mapRes, const_cast<__nv_bfloat16*>(P.res), P.n_img, P.ho, P.wo, P.cout, P.res_sn, P.res_sh,
+                        P.res_sw, P.slab_w, bw, 32 / bw);
+      if (rc) return rc;
+      mapResTail = mapRes;
+      P.res_tma = 1;
+    }
   } else if (P.epi_mode == 2) {
     uint64_t dims[3] = {(uint64_t)P.cout, (uint64_t)P.ho * P.wo, (uint64_t)P.n_img};
     uint64_t str[2] = {(uint64_t)P.out_sw * 2, (uint64_t)P.out_sn * 2};
@@ -765,6 +848,19 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
       box[1] = (uint32_t)(kp % 32);
       rc = encode_tensor_map(&mapOutTail, P.out, 3, dims, str, box, P.slab_w * 2);
       if (rc) return rc;
+    }
+    if (P.res && res_tma_enabled() && P.res_sh == (long long)P.wo * P.res_sw) {   // pixel-dense residual
+      uint64_t rstr[2] = {(uint64_t)P.res_sw * 2, (uint64_t)P.res_sn * 2};
+      box[1] = 32u;
+      rc = encode_tensor_map(&mapRes, const_cast<__nv_bfloat16*>(P.res), 3, dims, rstr, box, P.slab_w * 2);
+      if (rc) return rc;
+      mapResTail = mapRes;
+      if (kp % 32) {
+        box[1] = (uint32_t)(kp % 32);
+        rc = encode_tensor_map(&mapResTail, const_cast<__nv_bfloat16*>(P.res), 3, dims, rstr, box, P.slab_w * 2);
+        if (rc) return rc;
+      }
+      P.res_tma = 1;
     }
   } else {
     rc = make_out_map(&mapOut, P.out, P.n_img, P.ho, P.wo, P.cout, P.out_sn, P.out_sh, P.out_sw, P.slab_w, P.tile_w,
@@ -793,7 +889,7 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
   P.bres_bytes = 0;
   if (w_batch == 1 && P.n_tiles == 1 && b_total <= 80 * 1024 && P.total_tiles > 2 * kNumSMs) P.bres_bytes = (int)b_total;
   const int stage_bytes = P.bres_bytes ? a_stage : a_stage + b_tile;
-  const int ctrl_bytes = 8 * (2 * kMaxStages + 5) + 64;
+  const int ctrl_bytes = 8 * (2 * kMaxStages + 5) + 64 + 8 * 2 * kEpiWarps;   // + the residual-load barriers
   const int max_smem = 227 * 1024;
   const int avail = max_smem - P.bres_bytes;
   const int staging1 = 2 * 128 * P.slab_w * 2;      // CTA-wide: 2 slabs; warp-private: 8 warps x 1 buffer
@@ -822,7 +918,8 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
   }
   if (P.total_tiles <= 0) return UAVDET_OK;
   int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
-  igemm_kernel<<<grid, kIgemmThreads, smem_bytes, st>>>(mapA, mapB, mapOut, mapOutTail, P);
+  if (!P.res_tma) { mapRes = mapOut; mapResTail = mapOutTail; }
+  igemm_kernel<<<grid, kIgemmThreads, smem_bytes, st>>>(mapA, mapB, mapOut, mapOutTail, mapRes, mapResTail, P);
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }

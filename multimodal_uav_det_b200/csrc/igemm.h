@@ -50,6 +50,7 @@ struct IgemmParams {
   const float* scale;
   const float* shift;
   long long shift_sn;   // per-image stride of `shift` (0 = shared)
+  int res_tma;          // 1: the warp-private epilogues TMA-load the residual tile into their staging buffer
   const __nv_bfloat16* res;
   long long res_sn, res_sh, res_sw;
   __nv_bfloat16* out;

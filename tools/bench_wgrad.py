@@ -29,7 +29,8 @@ for (n, cin, cout, k, s, hw) in SHAPES:
     else:
         wt = ops.pack_weight(torch.randn(cout, cin, k, k, device="cuda") * 0.05, transposed=True)
         dx = torch.empty(n, hw, hw, cin, device="cuda", dtype=torch.bfloat16)
-        fn = lambda: ops.conv_dgrad(dy, wt, cin, k, s, k // 2, (hw, hw), out=dx)
+        res = torch.randn(n, hw, hw, cin, device="cuda").bfloat16() if which == "dgradres" else None
+        fn = lambda: ops.conv_dgrad(dy, wt, cin, k, s, k // 2, (hw, hw), out=dx, res=res)
     for _ in range(2):
         fn()
     torch.cuda.synchronize()
