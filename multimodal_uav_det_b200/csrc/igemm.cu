@@ -93,13 +93,16 @@ __device__ __forceinline__ uint32_t chunk_cfg(const IgemmParams& P) {
   return (P.epi == UAVDET_EPI_STATS ? 1u : 0u) | ((uint32_t)P.act << 1) | (P.res ? 16u : 0u) | (P.res_tma ? 32u : 0u);
 }
 // epilogue math of one 32-column chunk (accumulator values in r) + bf16 pack + swizzled staging store
+// kKind: the kernel instance (see igemm_kernel): 0 statistics epilogue, 1 affine without activation, 2 affine with
+// any activation.  Each instance only carries its own epilogue code.
+template <int kKind>
 __device__ __forceinline__ void finish_chunk(uint32_t cfg, const float* scale, const uint32_t (&r)[32], int cg, bool valid,
                                              const float* shift, const __nv_bfloat16* res_px, uint8_t* srow,
                                              int chunk_in_slab, int sw_mask) {
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-  if (cfg & 1u) {
+  if (kKind == 0) {
     if (shift) {
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
@@ -125,12 +128,16 @@ __device__ __forceinline__ void finish_chunk(uint32_t cfg, const float* scale, c
 #pragma unroll
       for (int j = 0; j < 4; ++j) rr[j] = make_uint4(0u, 0u, 0u, 0u);
     }
-    switch ((cfg >> 1) & 7u) {
-      case UAVDET_ACT_LEAKY: affine_act<UAVDET_ACT_LEAKY>(v, scale, cg, shift, rr, have_res); break;
-      case UAVDET_ACT_SILU: affine_act<UAVDET_ACT_SILU>(v, scale, cg, shift, rr, have_res); break;
-      case UAVDET_ACT_RELU: affine_act<UAVDET_ACT_RELU>(v, scale, cg, shift, rr, have_res); break;
-      case UAVDET_ACT_GELU: affine_act<UAVDET_ACT_GELU>(v, scale, cg, shift, rr, have_res); break;
-      default: affine_act<UAVDET_ACT_NONE>(v, scale, cg, shift, rr, have_res); break;
+    if (kKind == 1) {
+      affine_act<UAVDET_ACT_NONE>(v, scale, cg, shift, rr, have_res);
+    } else {
+      switch ((cfg >> 1) & 7u) {
+        case UAVDET_ACT_LEAKY: affine_act<UAVDET_ACT_LEAKY>(v, scale, cg, shift, rr, have_res); break;
+        case UAVDET_ACT_SILU: affine_act<UAVDET_ACT_SILU>(v, scale, cg, shift, rr, have_res); break;
+        case UAVDET_ACT_RELU: affine_act<UAVDET_ACT_RELU>(v, scale, cg, shift, rr, have_res); break;
+        case UAVDET_ACT_GELU: affine_act<UAVDET_ACT_GELU>(v, scale, cg, shift, rr, have_res); break;
+        default: affine_act<UAVDET_ACT_NONE>(v, scale, cg, shift, rr, have_res); break;
+      }
     }
   }
   // rows outside the image / tile carry garbage or bias only: stage zeros (the clipped TMA store skips them and
@@ -148,6 +155,7 @@ __device__ __forceinline__ void finish_chunk(uint32_t cfg, const float* scale, c
 }
 
 
+template <int kKind>
 __device__ __noinline__ void stage_chunk(uint32_t cfg, const float* scale, uint32_t taddr, int cg, bool valid,
                                             const float* shift, const __nv_bfloat16* res_px, uint8_t* srow,
                                             int chunk_in_slab, int sw_mask, bool release, uint32_t tempty, int lane) {
@@ -160,7 +168,7 @@ __device__ __noinline__ void stage_chunk(uint32_t cfg, const float* scale, uint3
     __syncwarp();
     if (lane == 0) mbar_arrive(tempty);
   }
-  finish_chunk(cfg, scale, r, cg, valid, shift, res_px, srow, chunk_in_slab, sw_mask);
+  finish_chunk<kKind>(cfg, scale, r, cg, valid, shift, res_px, srow, chunk_in_slab, sw_mask);
 }
 
 // MMA issue loop of one CTA (single elected thread), KSTEPS = block_k / 16.
@@ -208,6 +216,10 @@ __device__ __forceinline__ void mma_issue_loop(const IgemmParams& P, uint32_t ri
   }
 }
 
+// kKind selects the epilogue the instance is compiled with: 0 = batch statistics (training forward), 1 = affine
+// without activation (data gradients), 2 = affine with any activation (fused inference epilogues), 3 = detection
+// head.  One kernel holding all of them was 160 KB of code, and the step time follows the kernel's code size.
+template <int kKind>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
              const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapOutTail,
@@ -251,13 +263,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       // arrivals per tile: all 8 epilogue warps, or only the 4 that own the accumulator buffer when a tile is a
       // single slab (warp-private modes: the two warps of a lane quarter then take alternate TILES)
       mbar_init(smem_u32(&tempty_bar[a]),
-                (P.epi != UAVDET_EPI_HEAD && P.epi_mode != 0 && P.block_n == P.slab_w) ? kEpiWarps / 2 : kEpiWarps);
+                (kKind != 3 && P.epi_mode != 0 && P.block_n == P.slab_w) ? kEpiWarps / 2 : kEpiWarps);
     }
     *dead = 0;
     fence_barrier_init();
     prefetch_tensormap(&mapA);
     prefetch_tensormap(&mapB);
-    if (P.epi != UAVDET_EPI_HEAD) prefetch_tensormap(&mapOut);
+    if (kKind != 3) prefetch_tensormap(&mapOut);
     if (P.res_tma) prefetch_tensormap(&mapRes);
   }
   if (warp == kMmaWarp) {
@@ -346,7 +358,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const uint32_t ccfg = chunk_cfg(P);
     uint32_t acc_phase = 0;
 
-    if (P.epi == UAVDET_EPI_HEAD) {
+    if (kKind == 3) {
       for (int tile = blockIdx.x, tl = 0; tile < P.total_tiles; tile += gridDim.x, ++tl) {
         const TileCoord tc = decode_tile(P, tile);
         const int oh = tc.oh0 + hl, ow = tc.ow0 + wl;
@@ -461,7 +473,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         const int oh = tc.oh0 + hl, ow = tc.ow0 + wl;
         const bool valid = (row < kp) && (oh < P.ho) && (ow < P.wo);
         const bool tr = P.trace && blockIdx.x == 0 && tl < P.trace_tiles && (ew & 3) == 0 && lane == 0;
-        if (P.epi == UAVDET_EPI_STATS && tc.n0 != cur_n0) {
+        if (kKind == 0 && tc.n0 != cur_n0) {
           if (cur_n0 >= 0) flush_stats(cur_n0);
           cur_n0 = tc.n0;
         }
@@ -495,12 +507,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
               uint8_t* srow = wbuf + lane * row_bytes;
               const int c0 = sl * P.slab_w;                          // accumulator column of the slab
               if (P.slab_w == 64) {
-                stage_chunk(ccfg, P.scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, srow, 0, sw_mask, false,
+                stage_chunk<(kKind == 3 ? 1 : kKind)>(ccfg, P.scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, srow, 0, sw_mask, false,
                             tempty, lane);
-                stage_chunk(ccfg, P.scale, tbase + (uint32_t)(c0 + 32), tc.n0 + c0 + 32, valid, shift, res_px, srow, 1, sw_mask,
+                stage_chunk<(kKind == 3 ? 1 : kKind)>(ccfg, P.scale, tbase + (uint32_t)(c0 + 32), tc.n0 + c0 + 32, valid, shift, res_px, srow, 1, sw_mask,
                             last, tempty, lane);
               } else {
-                stage_chunk(ccfg, P.scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, srow, 0, sw_mask, last, tempty,
+                stage_chunk<(kKind == 3 ? 1 : kKind)>(ccfg, P.scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, srow, 0, sw_mask, last, tempty,
                             lane);
               }
               if (tr) P.trace[tl * 16 + 10] = clock64();
@@ -519,7 +531,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                 }
               }
               if (tr) P.trace[tl * 16 + 12] = clock64();
-              if (P.epi == UAVDET_EPI_STATS) {
+              if (kKind == 0) {
                 // column sums of the staged (bf16-rounded) rows: exactly the values the BatchNorm that follows
                 // will normalise.  Conflict-free: a row is one 128-byte line (slab 64) / two rows are (slab 32).
                 float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
@@ -551,7 +563,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         if (single) acc_phase ^= 1u;
         else if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
-      if (P.epi == UAVDET_EPI_STATS && cur_n0 >= 0) flush_stats(cur_n0);
+      if (kKind == 0 && cur_n0 >= 0) flush_stats(cur_n0);
       if (lane == 0) tma_store_wait_all();   // smem must stay valid until the last store has read it
     } else {
       // ---- CTA-wide epilogue (tiles whose 32-row groups are not rectangles) ------------------------------
@@ -583,7 +595,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           const bool last = sl == n_slabs - 1;
           if (half < chunks_per_slab) {
             const int c0 = sl * P.slab_w + half * 32;
-            stage_chunk(ccfg, P.scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, sbuf + row * row_bytes, half,
+            stage_chunk<(kKind == 3 ? 1 : kKind)>(ccfg, P.scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, sbuf + row * row_bytes, half,
                         sw_mask, last, tempty, lane);
             fence_proxy_async();
           } else if (last) {
@@ -596,7 +608,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             tma_store_5d(&mapOut, smem_u32(sbuf), cs, tc.ow0, 0, tc.oh0, tc.img);
             tma_store_commit();
           }
-          if (P.epi == UAVDET_EPI_STATS) {
+          if (kKind == 0) {
             // warp -> `ppw` column pairs, lane -> (pair, row group g) with rows g, g+groups, ... so the 32
             // lanes of a load hit 32 different banks; row groups are folded with xor-shuffles.
             const int ppw = P.slab_w >> 4;                    // 4 (slab 64) | 2 (slab 32)
@@ -911,15 +923,26 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
   // Always request (almost) the whole shared memory so exactly one CTA is resident per SM:
   // each CTA allocates all 512 TMEM columns.
   const int smem_bytes = max_smem;
-  static bool attr_set = false;
-  if (!attr_set) {
-    UAVDET_CUDA(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    attr_set = true;
-  }
   if (P.total_tiles <= 0) return UAVDET_OK;
   int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
   if (!P.res_tma) { mapRes = mapOut; mapResTail = mapOutTail; }
-  igemm_kernel<<<grid, kIgemmThreads, smem_bytes, st>>>(mapA, mapB, mapOut, mapOutTail, mapRes, mapResTail, P);
+  const int kind = (P.epi == UAVDET_EPI_HEAD) ? 3 : (P.epi == UAVDET_EPI_STATS) ? 0 : (P.act == UAVDET_ACT_NONE ? 1 : 2);
+  static bool attr_set[4] = {false, false, false, false};
+#define UAVDET_LAUNCH_IGEMM(K)                                                                                         \
+  do {                                                                                                                 \
+    if (!attr_set[K]) {                                                                                                \
+      UAVDET_CUDA(cudaFuncSetAttribute(igemm_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));       \
+      attr_set[K] = true;                                                                                              \
+    }                                                                                                                  \
+    igemm_kernel<K><<<grid, kIgemmThreads, smem_bytes, st>>>(mapA, mapB, mapOut, mapOutTail, mapRes, mapResTail, P);  \
+  } while (0)
+  switch (kind) {
+    case 0: UAVDET_LAUNCH_IGEMM(0); break;
+    case 1: UAVDET_LAUNCH_IGEMM(1); break;
+    case 2: UAVDET_LAUNCH_IGEMM(2); break;
+    default: UAVDET_LAUNCH_IGEMM(3); break;
+  }
+#undef UAVDET_LAUNCH_IGEMM
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }
