@@ -140,7 +140,7 @@ bn_act_fwd_kernel(View raw, const float* __restrict__ scale, const float* __rest
     uint4 a[4], r[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      a[u] = __ldg(reinterpret_cast<const uint4*>(raw.p + (px + u * L.step) * raw.ld + L.c));
+      a[u] = __ldcs(reinterpret_cast<const uint4*>(raw.p + (px + u * L.step) * raw.ld + L.c));
       if (HAS_RES) r[u] = __ldg(reinterpret_cast<const uint4*>(res + (px + u * L.step) * res_ld + L.c));
       else r[u] = make_uint4(0, 0, 0, 0);
     }
@@ -148,7 +148,7 @@ bn_act_fwd_kernel(View raw, const float* __restrict__ scale, const float* __rest
     for (int u = 0; u < 4; ++u) body(a[u], r[u], px + u * L.step);
   }
   for (; px < raw.npix; px += L.step) {
-    uint4 a = __ldg(reinterpret_cast<const uint4*>(raw.p + px * raw.ld + L.c));
+    uint4 a = __ldcs(reinterpret_cast<const uint4*>(raw.p + px * raw.ld + L.c));
     uint4 r = make_uint4(0, 0, 0, 0);
     if (HAS_RES) r = __ldg(reinterpret_cast<const uint4*>(res + px * res_ld + L.c));
     body(a, r, px);
@@ -388,15 +388,15 @@ bn_bwd_apply_fused_kernel(View dy, View raw, const float* __restrict__ scale, co
     uint4 a[4], b[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      a[u] = __ldg(reinterpret_cast<const uint4*>(dy.p + (px + u * L.step) * dy.ld + L.c));
-      b[u] = __ldg(reinterpret_cast<const uint4*>(raw.p + (px + u * L.step) * raw.ld + L.c));
+      a[u] = __ldcs(reinterpret_cast<const uint4*>(dy.p + (px + u * L.step) * dy.ld + L.c));
+      b[u] = __ldcs(reinterpret_cast<const uint4*>(raw.p + (px + u * L.step) * raw.ld + L.c));
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) body(a[u], b[u], px + u * L.step);
   }
   for (; px < dy.npix; px += L.step)
-    body(__ldg(reinterpret_cast<const uint4*>(dy.p + px * dy.ld + L.c)),
-         __ldg(reinterpret_cast<const uint4*>(raw.p + px * raw.ld + L.c)), px);
+    body(__ldcs(reinterpret_cast<const uint4*>(dy.p + px * dy.ld + L.c)),
+         __ldcs(reinterpret_cast<const uint4*>(raw.p + px * raw.ld + L.c)), px);
 }
 
 __global__ void act_bwd_kernel(View dy, View raw, const float* __restrict__ scale,
