@@ -25,12 +25,12 @@
 namespace uavdet {
 using namespace sm100;
 
-constexpr int kProdWarps = 4;      // TMA producer warps (P.prod_warps of them active)
-constexpr int kMmaWarp = 4;        // tcgen05.mma issuer (+ TMEM alloc)
-constexpr int kEpiWarp0 = 5;       // first of the 8 epilogue warps
+constexpr int kProdWarps = 3;      // TMA producer warps (P.prod_warps of them active)
+constexpr int kMmaWarp = 3;        // tcgen05.mma issuer (+ TMEM alloc)
+constexpr int kEpiWarp0 = 4;       // first of the 8 epilogue warps (12 warps = 3 per scheduler: 168 registers/thread)
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kIgemmThreads = (kProdWarps + 1 + kEpiWarps) * 32;   // 416
+constexpr int kIgemmThreads = (kProdWarps + 1 + kEpiWarps) * 32;   // 384
 constexpr int kAccStride = 256;    // TMEM columns per accumulator buffer
 
 // n / d for 0 <= n < 2^31 without a hardware divide (d fixed per launch, constants from the host).
@@ -914,8 +914,8 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
   int stages = (avail - ctrl_bytes - P.staging_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   UAVDET_CHECK_ARG(stages >= 2, "igemm: tile does not fit shared memory");
-  if (stages >= 8) { stages &= ~3; P.prod_warps = 4; }
-  else if (stages >= 4) { P.prod_warps = (stages % 4 == 0) ? 4 : 2; stages &= ~1; }
+  if (stages >= 6) { stages = (stages / 3) * 3; P.prod_warps = 3; }
+  else if (stages >= 4) { P.prod_warps = 2; stages &= ~1; }
   else { P.prod_warps = 1; }
   P.stages = stages;
   P.watchdog = watchdog_word();
