@@ -421,12 +421,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       // residual, start the TMA load of the residual tile for (tile tc, slab starting at channel cs) into it --
       // same map geometry as the store, so the bytes land where the result will be written.  Issued before the
       // wait for the accumulator: the load's latency hides behind the tile's main loop.
-      auto acquire = [&](const TileCoord& tc, int cs) -> uint8_t* {
+      // `early`: called in the middle of the previous unit, whose buffer is the other one -- every store committed
+      // so far must then be done reading (the latest one read the buffer being taken).
+      auto acquire = [&](const TileCoord& tc, int cs, bool early = false) -> uint8_t* {
         const uint32_t b = (P.epi_bufs == 2) ? (ucount & 1u) : 0u;
         uint8_t* wbuf = wbuf0 + b * wbuf_bytes;
         ++ucount;
         if (lane == 0) {
-          if (P.epi_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+          if (P.epi_bufs == 2 && !early) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
           if (P.res_tma && rows_here > 0) {
             const uint32_t bar = smem_u32(&rres_bar[ew * 2 + b]);
             if (P.epi_mode == 1) {
@@ -483,6 +485,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         if (tr) P.trace[tl * 16 + 5] = clock64();
         // this warp's first slab of the tile: buffer + residual load before the accumulator is awaited
         const int sl_first = single ? 0 : half;
+        uint8_t* wbuf_next = nullptr;
         uint8_t* wbuf_first = (sl_first < n_slabs) ? acquire(tc, tc.n0 + sl_first * P.slab_w) : nullptr;
         mbar_wait<64>(smem_u32(&tfull_bar[acc]), acc_phase, dead, P.watchdog, 0x8u);
         if (tr) P.trace[tl * 16 + 6] = clock64();
@@ -496,7 +499,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             if (sl < n_slabs && (!single || j == 0)) {
               const int cs = tc.n0 + sl * P.slab_w;                  // first global channel of the slab
               if (tr) P.trace[tl * 16 + 8] = clock64();
-              uint8_t* wbuf = (j == 0) ? wbuf_first : acquire(tc, cs);
+              uint8_t* wbuf = (j == 0) ? wbuf_first : (wbuf_next ? wbuf_next : acquire(tc, cs));
+              wbuf_next = nullptr;
               if (P.res_tma && rows_here > 0) {
                 const uint32_t b = (uint32_t)(wbuf != wbuf0);
                 mbar_wait<0>(smem_u32(&rres_bar[ew * 2 + b]), (rphase >> b) & 1u, dead, P.watchdog, 0x10u);
@@ -509,6 +513,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
               if (P.slab_w == 64) {
                 stage_chunk<(kKind == 3 ? 1 : kKind)>(ccfg, P.scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, srow, 0, sw_mask, false,
                             tempty, lane);
+                // the residual tile of this warp's next slab of the tile starts travelling now (other buffer)
+                if (P.res_tma && P.epi_bufs == 2 && !last) wbuf_next = acquire(tc, cs + 2 * P.slab_w, true);
                 stage_chunk<(kKind == 3 ? 1 : kKind)>(ccfg, P.scale, tbase + (uint32_t)(c0 + 32), tc.n0 + c0 + 32, valid, shift, res_px, srow, 1, sw_mask,
                             last, tempty, lane);
               } else {
