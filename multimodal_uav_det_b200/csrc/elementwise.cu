@@ -584,13 +584,54 @@ pack_weights_batched_kernel(const uavdet_pack_job* __restrict__ jobs, int n_jobs
   const long long total = (long long)j.O * j.I * kk;
   const long long base = ((long long)blockIdx.x - j.chunk0) * kPackChunk;
   __nv_bfloat16* out = (__nv_bfloat16*)j.dst;
-  for (int e = threadIdx.x; e < kPackChunk; e += 256) {
-    const long long idx = base + e;
-    if (idx >= total) break;
-    int o, i, t;
-    if (!transposed) { i = (int)(idx % j.I); long long r = idx / j.I; t = (int)(r % kk); o = (int)(r / kk); }
-    else { o = (int)(idx % j.O); long long r = idx / j.O; t = (int)(r % kk); i = (int)(r / kk); }
-    const long long src = src_nhwc ? ((long long)o * kk + t) * j.I + i : ((long long)o * j.I + i) * kk + t;
+  const int n_here = (int)((total - base) < kPackChunk ? (total - base) : kPackChunk);
+  if (!transposed && (src_nhwc || kk == 1)) {
+    // same element order in source and destination: a straight fp32 -> bf16 conversion, 8 elements per thread
+    const float* src = j.src + base;
+    if ((((uintptr_t)src | (uintptr_t)(out + base)) & 15) == 0) {
+      for (int e = threadIdx.x * 8; e + 8 <= n_here; e += 256 * 8) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src + e));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(src + e + 4));
+        uint4 o;
+        o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+        o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+        *reinterpret_cast<uint4*>(out + base + e) = o;
+      }
+      for (int e = (n_here & ~7) + threadIdx.x; e < n_here; e += 256) out[base + e] = __float2bfloat16(__ldg(src + e));
+      return;
+    }
+  }
+  const uint32_t I = (uint32_t)j.I, O = (uint32_t)j.O, ukk = (uint32_t)kk;
+  if (transposed && (src_nhwc || kk == 1) && (O & 31u) == 0 && (I & 31u) == 0) {
+    // per tap a 2-D transpose [O][I] -> [I][O]: 32 x 32 tiles through shared memory, reads contiguous along I,
+    // writes contiguous along O; this block's 4096 output elements are four tiles
+    __shared__ float tile[32][33];
+    const uint32_t tiles_o = O >> 5, tiles_i = I >> 5;
+    const uint32_t n_tiles = ukk * tiles_i * tiles_o;
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (uint32_t q = 0; q < kPackChunk / 1024; ++q) {
+      const uint32_t tile_id = (uint32_t)(base >> 10) + q;
+      if (tile_id >= n_tiles) break;
+      const uint32_t to = tile_id % tiles_o, r = tile_id / tiles_o, ti = r % tiles_i, t = r / tiles_i;
+      const uint32_t o0 = to << 5, i0 = ti << 5;
+#pragma unroll
+      for (uint32_t rr = ty; rr < 32; rr += 8)
+        tile[rr][tx] = __ldg(j.src + ((size_t)(o0 + rr) * ukk + t) * I + i0 + tx);
+      __syncthreads();
+#pragma unroll
+      for (uint32_t rr = ty; rr < 32; rr += 8)
+        out[((size_t)(i0 + rr) * ukk + t) * O + o0 + tx] = __float2bfloat16(tile[tx][rr]);
+      __syncthreads();
+    }
+    return;
+  }
+  // general case; a weight tensor has < 2^31 elements, so the index arithmetic stays in 32 bits
+  for (int e = threadIdx.x; e < n_here; e += 256) {
+    const uint32_t idx = (uint32_t)base + (uint32_t)e;
+    uint32_t o, i, t;
+    if (!transposed) { i = idx % I; const uint32_t r = idx / I; t = r % ukk; o = r / ukk; }
+    else { o = idx % O; const uint32_t r = idx / O; t = r % ukk; i = r / ukk; }
+    const uint32_t src = src_nhwc ? (o * ukk + t) * I + i : (o * I + i) * ukk + t;
     out[idx] = __float2bfloat16(__ldg(j.src + src));
   }
 }
