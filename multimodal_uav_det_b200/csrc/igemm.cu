@@ -16,8 +16,9 @@
 //     dynamic-kernel convs) fetched by a 3-D map;
 //   * 128 x block_n fp32 accumulators live in TMEM, double buffered so the epilogue of tile
 //     i overlaps the MMAs of tile i+1; persistent CTAs, one per SM;
-//   * warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps 2-5 =
-//     epilogue (tcgen05.ld -> BN-stat partial sums / affine+activation+residual -> bf16).
+//   * warp roles: warps 0-2 = TMA producers, warp 3 = MMA issuer (+TMEM alloc), warps 4-11 =
+//     epilogue (tcgen05.ld -> BN-stat partial sums / affine+activation+residual -> bf16 ->
+//     swizzled staging -> TMA store); one kernel instance per epilogue kind (igemm_kernel<kKind>).
 #include "common.cuh"
 #include "sm100.cuh"
 #include "igemm.h"

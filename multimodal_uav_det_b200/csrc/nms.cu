@@ -1,7 +1,7 @@
 // K9 — greedy NMS, bit-exact with torchvision.ops.nms (CPU kernel semantics).
 // Replaces the call at reference model/_base.py:203.
 //
-// One thread-block cluster (1-8 CTAs of 1024 threads, chosen from the batch size) per image:
+// One thread-block cluster (1-8 CTAs of 512 threads, chosen from the batch size) per image:
 //   1. key build      : key = ~orderable(score)  (NaN first, -0 == +0), value = index          (CTA 0)
 //   2. stable LSD radix sort, 4 x 8-bit passes, ping-pong in the workspace                     (CTA 0)
 //      (warp match_any ranking keeps equal keys in index order == torch stable sort)
