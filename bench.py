@@ -172,7 +172,7 @@ class ConvTimer:
     one-thread kernel that writes the device global timer in stream order; one replay fills the stamps.  The
     bracket adds one launch gap (~1-2 us) to each measured duration, i.e. the figures are slightly pessimistic."""
 
-    def __init__(self, ops, torch, device, max_records=1024):
+    def __init__(self, ops, torch, device, max_records=2048):
         self.ops, self.torch = ops, torch
         self.records = []   # (kind, flops, slot)
         self.stamps = torch.zeros(2 * max_records, dtype=torch.int64, device=device)
@@ -214,10 +214,20 @@ class ConvTimer:
         ops.conv_fwd = timed(self._orig[0], "igemm", fwd_flops)
         ops.conv_dgrad = timed(self._orig[1], "igemm", dgrad_flops)
         ops.conv_wgrad = timed(self._orig[2], "wgrad", wgrad_flops)
+        self._orig_bn = None
+        if os.environ.get("UAVDET_BENCH_DEBUG"):
+            # debug table only: the BatchNorm passes too, with their algorithmic bytes in place of flops
+            # (forward: read raw [+ residual] + write y; backward: reduce reads dy, raw; apply reads both, writes d_raw)
+            self._orig_bn = (ops.bn_act_fwd, ops.bn_act_bwd)
+            ops.bn_act_fwd = timed(self._orig_bn[0], "bn_fwd",
+                                   lambda a, kw: (3.0 if kw.get("res") is not None else 2.0) * a[0].numel() * 2)
+            ops.bn_act_bwd = timed(self._orig_bn[1], "bn_bwd", lambda a, kw: 5.0 * a[0].numel() * 2)
         return self
 
     def __exit__(self, *exc):
         self.ops.conv_fwd, self.ops.conv_dgrad, self.ops.conv_wgrad = self._orig
+        if self._orig_bn is not None:
+            self.ops.bn_act_fwd, self.ops.bn_act_bwd = self._orig_bn
 
     def summary(self):
         self.torch.cuda.synchronize()
@@ -226,7 +236,10 @@ class ConvTimer:
         for i, (kind, fl, slot) in enumerate(self.records):
             sec = (t[slot + 1] - t[slot]) * 1e-9
             if os.environ.get("UAVDET_BENCH_DEBUG"):
-                print(f"[convtimer] {i} {kind} {sec * 1e6:.0f} us {fl / 1e9:.1f} GFLOP", file=sys.stderr)
+                if kind.startswith("bn_"):
+                    print(f"[convtimer] {i} {kind} {sec * 1e6:.0f} us {fl / 1e6:.0f} MB {fl / sec / 1e12:.2f} TB/s", file=sys.stderr)
+                else:
+                    print(f"[convtimer] {i} {kind} {sec * 1e6:.0f} us {fl / 1e9:.1f} GFLOP", file=sys.stderr)
             a = agg.setdefault(kind, [0.0, 0.0, 0])
             a[0] += fl
             a[1] += sec
