@@ -1000,7 +1000,10 @@ extern "C" int uavdet_bn_act_bwd_apply_fused(const uavdet_act* dy, const uavdet_
     return rc;
   UAVDET_CHECK_ARG(scale && shift && sum_dz && sum_dzr && mean && invstd && dgamma && dbeta && count > 0,
                    "bn_bwd_apply_fused: null argument");
-  bn_bwd_apply_fused_kernel<<<stream_grid(dy, 4), 256, 0, ST>>>(mkview(dy), mkview(raw), scale, shift, sum_dz, sum_dzr,
+  // pixels per thread: every thread first derives the coefficients of its 8 channels from six per-channel vectors,
+  // so very short threads spend more on that prologue than on their data
+  static const int ppt = getenv("UAVDET_BN_APPLY_PPT") ? atoi(getenv("UAVDET_BN_APPLY_PPT")) : 4;
+  bn_bwd_apply_fused_kernel<<<stream_grid(dy, ppt), 256, 0, ST>>>(mkview(dy), mkview(raw), scale, shift, sum_dz, sum_dzr,
                                                                mean, invstd, (float)(1.0 / count), act, dgamma, dbeta,
                                                                mkview(d_raw));
   UAVDET_LAUNCH_CHECK();
