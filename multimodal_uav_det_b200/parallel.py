@@ -202,9 +202,12 @@ class GraphedTrainStep:
                 body()
         cur.wait_stream(side)
         torch.cuda.synchronize(self.x.device)
+        from . import ops as _ops
         self.graph = torch.cuda.CUDAGraph()
+        l0 = _ops.launch_count()
         with torch.cuda.graph(self.graph):
             self.loss, self.bbox_loss, self.obj_loss = body()
+        self.captured_launches = _ops.launch_count() - l0     # this library's kernels inside one replay
         head.mutate_targets = prev_mut
         bump_param_epoch()
         self._stage = None
