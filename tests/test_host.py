@@ -38,6 +38,18 @@ def test_library_exports_every_symbol_declared_in_the_header(lib):
     assert lib.uavdet_last_error() is not None
 
 
+def test_public_header_is_plain_c():
+    """include/uavdet_b200.h is the drop-in boundary: it must compile on its own as C11 and as C++ (no torch, no
+    CUDA types in the signatures)."""
+    hdr = os.path.join(ROOT, "include", "uavdet_b200.h")
+    for cmd in (["gcc", "-x", "c", "-std=c11", "-fsyntax-only", "-Wall", "-Werror", hdr],
+                ["g++", "-x", "c++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", hdr]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    code = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)      # declarations only, comments stripped
+    assert "torch" not in code.lower() and "cudaStream_t" not in code and "#include <cuda" not in code
+
+
 def test_library_is_cuda_only_sm100a(lib):
     from multimodal_uav_det_b200 import _lib
     out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
@@ -55,6 +67,8 @@ def test_no_cpu_fallback():
         model(torch.rand(1, 3, 64, 64))
     with pytest.raises(UavdetError):
         ops.nms(torch.zeros(4, 4), torch.zeros(4), 0.5)
+    with pytest.raises(UavdetError):
+        ops.encode_targets(torch.tensor([[10.0, 10.0, 50.0, 40.0]]), gold["hp"]["anchors"], [2, 4, 8], 64)
     # the product package must never import the oracle
     for dirpath, _, files in os.walk(os.path.join(ROOT, "multimodal_uav_det_b200")):
         for f in files:
