@@ -163,6 +163,112 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+
+# ------------------------------------------------------------------------------------------------
+# stock PyTorch on the same GPU (the "existing Blackwell kernels" bar)
+# ------------------------------------------------------------------------------------------------
+def run_torch_gpu(args, rank, world, local_rank):
+    """The same training step through stock PyTorch on the GPU: the oracle's functional BaselineModel forward
+    (F.conv2d -> cuDNN, F.batch_norm, leaky_relu) under torch.autocast(bf16) with channels_last activations and
+    weights, the batched torch loss, autograd backward and torch.optim.SGD(foreach).  This is the library path the
+    reference's `precision: 16` Lightning run dispatches to (params.yaml:28-29, train.py:42-56) — with bf16 in
+    place of fp16 and the reference's per-sample loss loop replaced by the batched loss, both in its favour."""
+    import torch
+    from oracle import oracle as O
+    from multimodal_uav_det_b200.model import BaselineModel
+    from multimodal_uav_det_b200.utils.datatype import Config
+    from multimodal_uav_det_b200.utils.metrics import yolo_head_loss
+    if rank != 0:
+        return
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    torch.backends.cudnn.benchmark = True
+    B = args.batch
+    torch.manual_seed(0)
+    model = BaselineModel(hparams=Config(HPARAMS))
+    sd = {}
+    for k, v in model.state_dict().items():
+        v = v.detach().clone().to(dev)
+        if v.dim() == 4:
+            v = v.contiguous(memory_format=torch.channels_last)
+        if v.dtype.is_floating_point and "running" not in k:
+            v.requires_grad_(True)
+        sd[k] = v
+    params = [v for v in sd.values() if v.requires_grad]
+    opt = torch.optim.SGD(params, lr=HPARAMS["lr"], momentum=0.7, foreach=True)
+    x_host, boxes = synth_batch(B)
+    x_pin = x_host.pin_memory()
+    tg_host = [t.pin_memory() for t in encode_targets_stacked(boxes)]
+    x_dev = x_pin.to(dev).contiguous(memory_format=torch.channels_last)
+    tg_dev = [t.to(dev) for t in tg_host]
+    anc = torch.tensor(ANCHORS).float()
+    sas = [(anc[h] / HEAD_SCALES[h]).to(dev) for h in range(3)]
+    wts = (LOSS_BAL["bbox_w"], LOSS_BAL["objectness_w"], LOSS_BAL["no_obj_w"])
+
+    def step(x, tg):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            outs = O.darknet_forward(x, sd, DARKNET53, train=True)
+        bl = ol = 0.0
+        for h, (bbox, obj) in enumerate(outs):
+            b_, o_, _ = yolo_head_loss(bbox.float(), obj.float(), tg[h], sas[h], LOSS_BAL["obj_scales_w"][h], wts, "ciou")
+            bl, ol = bl + b_, ol + o_
+        loss = (bl + ol) / B
+        loss.backward()
+        opt.step()
+        return loss.detach()
+
+    def timed(fn, iters):
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e)
+
+    for _ in range(max(args.warmup, 3)):
+        loss = step(x_dev, tg_dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = timed(lambda: step(x_dev, tg_dev), args.steps)
+    clocks = sampler.stop()
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        xd = x_pin.to(dev, non_blocking=True).contiguous(memory_format=torch.channels_last)
+        td = [t.to(dev, non_blocking=True) for t in tg_host]
+        loss_host.copy_(step(xd, td), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    step_s = ms / args.steps * 1e-3
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    line = {
+        "impl": "torch-gpu", "metric": METRIC, "value": B / step_s, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"BaselineModel (Darknet-53) training step through stock PyTorch {torch.__version__} / cuDNN "
+                               f"{torch.backends.cudnn.version()}: autocast(bf16), channels_last, cudnn.benchmark, batched torch "
+                               f"loss, autograd, SGD(foreach); batch {B}, 3x640x640",
+                   "per_gpu_batch": B, "final_loss": float(loss.item()), "launch": "eager"},
+        "clocks": clocks,
+        "e2e": {"value": B / (ms_e2e / args.steps * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": x_pin.numel() * 4 + sum(t.numel() * 4 for t in tg_host), "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": 0,
+        "model_flops_utilisation": 3 * FWD_GFLOP_PER_FRAME * 1e9 * B / step_s / 1e12 / peak_tf,
+    }
+    print(json.dumps(line), flush=True)
+
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
@@ -453,7 +559,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-gpu"])
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch the step from Python instead of replaying its CUDA graph")
@@ -464,6 +570,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.impl == "torch-gpu":
+        run_torch_gpu(args, rank, world, local_rank)
         return
     if world > 1:
         import torch.distributed as dist

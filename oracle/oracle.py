@@ -314,6 +314,13 @@ def conv_module(x, sd, p, stride=1, pad=0, act="silu", train=False, eps=1e-5, mo
     return F.silu(y) if act == "silu" else F.relu(y)
 
 
+def adaptive_stem(x, sd, p, train=False):
+    """AdaptiveStemLayer.forward (DySOEM_SimFPN.py:14-25): a 1-channel input goes through `gray_conv`, anything
+    else through `rgb_conv`; each is a 1x1 ConvModule(bias=False, SiLU)."""
+    branch = "gray_conv" if x.size(1) == 1 else "rgb_conv"
+    return conv_module(x, sd, f"{p}.{branch}" if p else branch, 1, 0, "silu", train)
+
+
 def space_to_depth2(x):
     """DySOEM_SimFPN.py:71-75: cat of the four stride-2 phase slices, phase n = i*2 + j."""
     return torch.cat([x[..., i::2, j::2] for i in range(2) for j in range(2)], dim=1)

@@ -1,0 +1,241 @@
+"""GPU parity at the REAL shapes of BASELINE.json's configurations (640x640 inputs): the dynamic models' full-size
+layers (1024->512 k1 DyConv @20^2, 512->256 k3 space-to-depth SOEM @80^2, the 320^2 heads), RTMUAVDet's decode + NMS
+path, the per-modality stem, the fused loss against the oracle's restatement of `compute_metrics` directly, and the
+loss-curve agreement SURVEY.md §8a(iii) prescribes in place of element-wise train-mode parity."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from test_gpu_models import (ANCHORS, BASE_HP, DARKNET53, DYSOEM_HP, DYYOLO, SHALLOW, DEV, _targets, make, randomize_bn,
+                             rel_l2, synth_input)
+
+pytestmark = pytest.mark.gpu
+
+
+def test_dyyolo_eval_forward_640_matches_oracle(lib):
+    """conf/model/dy-yolo.yaml at 640^2: all five DyConv sites at their real sizes (3->32 k3 @640^2, 32->64 k3 s2,
+    1024->512 k1 @20^2, 768->256 k1 @40^2, 384->128 k1 @80^2).  Tolerance = 2 x the reference's own fp32->bf16 drift on
+    this model (2.4 %, SURVEY §8a: the unscaled randn expert banks)."""
+    from oracle import oracle as O
+    from multimodal_uav_det_b200 import ops
+    model, hp = make("DyYOLO", DYYOLO, bbox_loss_fn="mse", attn_temperature=30.0)
+    randomize_bn(model)
+    model.eval()
+    sd = copy.deepcopy(model.state_dict())
+    x = synth_input(2, 640)
+    with torch.no_grad():
+        want = O.darknet_forward(x, sd, DYYOLO, 30.0)
+        got = model.to(DEV)(x.to(DEV))
+    ops.check_device()
+    for s, (g, (wb, wo)) in enumerate(zip(got, want)):
+        assert g.bbox.shape == wb.shape and g.obj.shape == wo.shape
+        rb, ro = rel_l2(g.bbox.cpu(), wb), rel_l2(g.obj.cpu(), wo)
+        print(f"dyyolo 640 eval scale {s}: rel_l2 bbox={rb:.4f} obj={ro:.4f}")
+        assert rb < 0.05 and ro < 0.05
+
+
+def test_dysoem_simfpn_eval_forward_640_matches_oracle(lib):
+    """conf/model/dy-soem_fpn.yaml at 640^2: SOEM sites 32@640^2 -> 64@320^2 -> 128@160^2 -> 256@80^2 (the 512->256 k3
+    space-to-depth conv), SimFPN and the 320/160/80 heads (403,200 candidates per frame).  ~2 x 0.77 % self-drift."""
+    from oracle import oracle as O
+    from multimodal_uav_det_b200 import ops
+    from multimodal_uav_det_b200.model import DySOEM_SimFPN
+    from multimodal_uav_det_b200.utils.datatype import Config
+    torch.manual_seed(0)
+    model = DySOEM_SimFPN(hparams=Config(DYSOEM_HP))
+    randomize_bn(model)
+    model.eval()
+    sd = copy.deepcopy(model.state_dict())
+    x = synth_input(2, 640)
+    with torch.no_grad():
+        want = O.dysoem_simfpn_forward(x, sd, 30.0)
+        got = model.to(DEV)(x.to(DEV), attn_temp=30.0)
+    ops.check_device()
+    assert [tuple(g.bbox.shape[2:4]) for g in got] == [(320, 320), (160, 160), (80, 80)]
+    for s, (g, (wb, wo)) in enumerate(zip(got, want)):
+        assert g.bbox.shape == wb.shape
+        rb, ro = rel_l2(g.bbox.cpu(), wb), rel_l2(g.obj.cpu(), wo)
+        print(f"dysoem 640 eval scale {s}: rel_l2 bbox={rb:.4f} obj={ro:.4f}")
+        assert rb < 0.02 and ro < 0.02
+
+
+def _rtm(seed=0):
+    from multimodal_uav_det_b200.model import RTMUAVDet
+    anchors = torch.tensor([[[29, 23], [48, 30], [67, 38]], [[91, 54], [120, 75], [157, 60]]]).float()
+    torch.manual_seed(seed)
+    model = RTMUAVDet([3, 640, 640], anchors, 1e-4)
+    randomize_bn(model)
+    return model.eval(), anchors
+
+
+@pytest.mark.parametrize("floor", [float("-inf"), 0.5])
+def test_detect_rtm_640_decode_and_nms_bit_exact(lib, floor):
+    """C5 path: `inference.detect_rtm` at 640^2 (96,000 candidates per frame).  Boxes = cxcywh->xyxy of the model's
+    decoded outputs (bit-exact against the oracle's box_convert restatement); kept indices bit-identical to the oracle
+    NMS on the same fp32 boxes / scores, with and without the score floor (floor semantics: torchvision.ops.nms on the
+    subset with score > floor, indices mapped back)."""
+    from oracle import oracle as O
+    from multimodal_uav_det_b200 import inference, ops
+    model, _ = _rtm()
+    model = model.to(DEV)
+    b = 1 if floor == float("-inf") else 2
+    x = synth_input(b, 640).to(DEV)
+    det = inference.detect_rtm(model, x, 0.5, floor)
+    ops.check_device()
+    assert det.boxes.shape == (b, 96000, 4) and det.scores.shape == (b, 96000)
+    with torch.no_grad():
+        outs = model(x)
+    cx = torch.cat([o.bbox.reshape(b, -1, 4) for o in outs], dim=1).cpu()
+    sc = torch.cat([o.obj.reshape(b, -1) for o in outs], dim=1).cpu()
+    assert torch.equal(det.boxes.cpu(), O.cxcywh_to_xyxy(cx))
+    assert torch.equal(det.scores.cpu(), sc)
+    for i, kept in enumerate(inference.kept_lists(det)):
+        boxes, scores = det.boxes[i].cpu().numpy(), det.scores[i].cpu().numpy()
+        if floor == float("-inf"):
+            want = O.nms(boxes, scores, 0.5)
+        else:
+            idx = np.nonzero(scores > floor)[0]
+            want = idx[O.nms(boxes[idx], scores[idx], 0.5)]
+        print(f"rtm 640 floor={floor} image {i}: kept {len(want)} of {len(scores)}")
+        assert np.array_equal(kept.cpu().numpy(), want)
+
+
+def test_graphed_detect_rtm_equals_eager(lib):
+    """`inference.GraphedDetect` on RTMUAVDet (forward + sigmoid/decode + batched NMS replayed from one CUDA graph)
+    returns exactly what the eager `detect_rtm` returns, on fresh inputs copied into its static buffer."""
+    from multimodal_uav_det_b200 import inference, ops
+    model, _ = _rtm()
+    model = model.to(DEV)
+    xs = [synth_input(2, 640, seed=700 + i).to(DEV) for i in range(2)]
+    run = inference.GraphedDetect(model, xs[0], score_floor=0.5)
+    for x in xs:
+        want = inference.detect_rtm(model, x, 0.5, 0.5)
+        got = run(x)
+        assert torch.equal(got.keep_count, want.keep_count)
+        for b, c in enumerate(want.keep_count.tolist()):
+            assert torch.equal(got.keep[b, :c], want.keep[b, :c])
+        assert torch.equal(got.boxes, want.boxes) and torch.equal(got.scores, want.scores)
+    ops.check_device()
+
+
+def test_adaptive_stem_matches_golden_and_oracle(lib):
+    """AdaptiveStemLayer (reference DySOEM_SimFPN.py:14-25): the 1-channel (IR) and 3-channel (RGB) 1x1 stems, eval
+    and train mode, against the fixture generated from the reference class, then at 640^2 against the oracle."""
+    from oracle import oracle as O
+    from multimodal_uav_det_b200 import ops
+    from multimodal_uav_det_b200.model.DySOEM_SimFPN import AdaptiveStemLayer
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "adaptive_stem.pt"), weights_only=False)
+    for c in g["cases"]:
+        m = AdaptiveStemLayer(32)
+        m.load_state_dict(g["sd"], strict=True)
+        m.train(c["train"]).to(DEV)
+        with torch.no_grad():
+            y = m(c["x"].to(DEV))
+        assert y.shape == c["y"].shape and y.dtype == torch.float32
+        r = rel_l2(y.cpu(), c["y"])
+        print(f"adaptive stem cin={c['x'].shape[1]} train={c['train']}: rel_l2={r:.5f}")
+        assert r < 0.01                                   # one bf16 rounding of the output (2^-9 relative)
+        if c["train"]:                                    # running statistics follow torch's update rule
+            branch = m.gray_conv if c["x"].shape[1] == 1 else m.rgb_conv
+            ref_sd = {k: v.clone() for k, v in g["sd"].items()}
+            import torch.nn.functional as F
+            p = "gray_conv" if c["x"].shape[1] == 1 else "rgb_conv"
+            raw = F.conv2d(c["x"], ref_sd[p + ".conv.0.weight"])
+            F.batch_norm(raw, ref_sd[p + ".conv.1.running_mean"], ref_sd[p + ".conv.1.running_var"], None, None, True, 0.1, 1e-5)
+            torch.testing.assert_close(branch.conv[1].running_mean.cpu(), ref_sd[p + ".conv.1.running_mean"], rtol=2e-2, atol=2e-3)
+            torch.testing.assert_close(branch.conv[1].running_var.cpu(), ref_sd[p + ".conv.1.running_var"], rtol=2e-2, atol=2e-3)
+    m = AdaptiveStemLayer(32)
+    m.load_state_dict(g["sd"], strict=True)
+    m.eval().to(DEV)
+    for cin in (1, 3):
+        x = torch.rand(2, cin, 640, 640, generator=torch.Generator().manual_seed(3 + cin))
+        with torch.no_grad():
+            y = m(x.to(DEV))
+        want = O.adaptive_stem(x, g["sd"], "")
+        assert rel_l2(y.cpu(), want) < 0.01
+    ops.check_device()
+
+
+@pytest.mark.parametrize("loss_fn", ["ciou", "mse"])
+def test_fused_yolo_head_loss_matches_oracle_directly(lib, loss_fn):
+    """`YOLOHead.compute_metrics` on CUDA (csrc/loss.cu: value + analytic gradient) against `O.yolo_loss` — the
+    oracle's restatement of the reference's per-sample loop (_base.py:155-212), itself pinned to the reference's
+    golden loss — with autograd through it on the CPU.  Real BaselineModel grids (20/40/80, 25,200 candidates)."""
+    from oracle import oracle as O
+    from multimodal_uav_det_b200.model._base import YOLOHead
+    from multimodal_uav_det_b200.utils.datatype import BatchData, Config, DetectionResults
+    hp = dict(BASE_HP, bbox_loss_fn=loss_fn)
+    b, grids = 4, [20, 40, 80]
+    head = YOLOHead([32, 32, 32], hp["anchors"], hp["head_scales"], Config(hp["loss_balancing"]), loss_fn)
+    g = torch.Generator().manual_seed(77)
+    logits = [(torch.randn(b, 3, s, s, 4, generator=g), torch.randn(b, 3, s, s, 1, generator=g)) for s in grids]
+    tg = _targets(hp, b, 640, seed=5)
+    ref_in = [(bb.clone().requires_grad_(True), oo.clone().requires_grad_(True)) for bb, oo in logits]
+    loss_ref, bl_ref, ol_ref = O.yolo_loss(ref_in, tg, hp["anchors"], hp["head_scales"], hp["loss_balancing"], loss_fn)
+    loss_ref.backward()
+    outs = [DetectionResults(bbox=bb.to(DEV).requires_grad_(True), obj=oo.to(DEV).requires_grad_(True)) for bb, oo in logits]
+    batch = BatchData(image=torch.zeros(b, 3, 8, 8, device=DEV), bbox=[[t.to(DEV) for t in per] for per in copy.deepcopy(tg)])
+    assert head.fused_loss
+    loss, _, bl, ol = head.compute_metrics(outs, batch)
+    loss.backward()
+    print(f"fused loss [{loss_fn}]: ref={loss_ref.item():.6f} got={loss.item():.6f}")
+    torch.testing.assert_close(loss.cpu(), loss_ref, rtol=2e-5, atol=1e-6)
+    torch.testing.assert_close(bl.cpu(), bl_ref, rtol=2e-5, atol=1e-6)
+    torch.testing.assert_close(ol.cpu(), ol_ref, rtol=2e-5, atol=1e-6)
+    for o, (rb, ro) in zip(outs, ref_in):
+        torch.testing.assert_close(o.bbox.grad.cpu(), rb.grad, rtol=2e-4, atol=1e-7)
+        torch.testing.assert_close(o.obj.grad.cpu(), ro.grad, rtol=2e-4, atol=1e-7)
+
+
+def test_loss_curve_agreement_20_sgd_steps(lib):
+    """end-to-end train-mode bf16 is not an element-wise parity test — check loss-curve agreement.
+    20 SGD(momentum 0.7, lr 1e-3) steps of the SHALLOW trunk (every op of the layer DSL, ~24 batch-stat BN layers) on
+    four rotating batches: the CUDA product (bf16 storage, FlatSGDTrainer) against the oracle in fp32 with
+    torch.optim.SGD.  Band: 10 % per step — the oracle's own bf16-storage-point emulation deviates from its fp32 run by
+    up to 3.2 % on this trajectory (measured on CPU; the loss falls 21.8 -> 13.7)."""
+    from oracle import oracle as O
+    from multimodal_uav_det_b200 import ops
+    from multimodal_uav_det_b200.parallel import FlatSGDTrainer
+    from multimodal_uav_det_b200.utils.datatype import BatchData
+    size, b, lr, steps = 128, 16, 1e-3, 20
+    model, hp = make("BaselineModel", SHALLOW, lr=lr)
+    model.route_repeats = 2
+    anchors = (torch.tensor(hp["anchors"]).float() * size / 640).tolist()
+    model.yolo_head.anchors = torch.tensor(anchors).float()
+    model.yolo_head.mutate_targets = False
+    sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k)
+          for k, v in model.state_dict().items()}
+    xs = [synth_input(b, size, seed=100 + i) for i in range(4)]
+    tgs = [_targets(hp, b, size, seed=1 + i, grids=[16, 32, 64]) for i in range(4)]
+    opt = torch.optim.SGD([v for v in sd.values() if v.requires_grad], lr=lr, momentum=0.7)
+    ref = []
+    for it in range(steps):
+        opt.zero_grad()
+        outs = O.darknet_forward(xs[it % 4], sd, SHALLOW, train=True, route_repeats=2)
+        loss, _, _ = O.yolo_loss(outs, tgs[it % 4], anchors, hp["head_scales"], hp["loss_balancing"], "ciou")
+        loss.backward()
+        opt.step()
+        ref.append(loss.item())
+    model = model.to(DEV).train()
+    trainer = FlatSGDTrainer(model, lr=lr, momentum=0.7)
+    xd = [x.to(DEV) for x in xs]
+    td = [[torch.stack([per[i][h] for i in range(b)]).to(DEV) for h in range(3)] for per in tgs]
+    got = []
+    for it in range(steps):
+        trainer.zero_grad()
+        outs = model(xd[it % 4])
+        loss, _, _, _ = model.yolo_head.compute_metrics(outs, BatchData(image=xd[it % 4], bbox=td[it % 4]))
+        loss.backward()
+        trainer.step()
+        got.append(loss.item())
+    ops.check_device()
+    print("loss curve ref:", ["%.3f" % v for v in ref])
+    print("loss curve got:", ["%.3f" % v for v in got])
+    dev = max(abs(a - r) / r for a, r in zip(got, ref))
+    print(f"max per-step deviation {dev:.4f}")
+    assert ref[-1] < 0.75 * ref[0] and got[-1] < 0.75 * got[0]        # both actually train
+    assert dev < 0.10
+    assert abs(got[-1] - ref[-1]) < 0.10 * ref[-1]

@@ -122,6 +122,18 @@ def test_block_restatements_match_golden():
                                rtol=1e-5, atol=1e-5)
 
 
+def test_adaptive_stem_matches_golden():
+    """AdaptiveStemLayer (DySOEM_SimFPN.py:14-25): 1-channel -> gray_conv, 3-channel -> rgb_conv; fixture generated
+    from the reference class by tools/make_golden.py::gen_adaptive_stem."""
+    g = load("adaptive_stem.pt")
+    seen = set()
+    for c in g["cases"]:
+        y = O.adaptive_stem(c["x"], g["sd"], "", c["train"])
+        torch.testing.assert_close(y, c["y"], rtol=1e-5, atol=1e-6)
+        seen.add((c["x"].shape[1], c["train"]))
+    assert seen == {(1, False), (1, True), (3, False), (3, True)}
+
+
 def test_bf16_pipeline_switch_is_off_by_default_and_only_rounds():
     g = load("blocks.pt")["resblock"]
     sd = {"m." + k: v for k, v in g["sd"].items()}
@@ -211,3 +223,8 @@ def test_golden_fixtures_are_reproducible_from_the_reference(tmp_path):
     b = load("nms_cases.pt")
     for x, y in zip(a["cases"], b["cases"]):
         assert torch.equal(x["keep"], y["keep"]) and torch.equal(x["boxes"], y["boxes"])
+    make_golden.gen_adaptive_stem()
+    a = torch.load(os.path.join(str(tmp_path), "adaptive_stem.pt"), weights_only=False)
+    b = load("adaptive_stem.pt")
+    for x, y in zip(a["cases"], b["cases"]):
+        assert torch.equal(x["x"], y["x"]) and torch.equal(x["y"], y["y"])

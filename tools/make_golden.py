@@ -166,6 +166,32 @@ def gen_blocks():
     torch.save(out, os.path.join(OUT, "blocks.pt"))
 
 
+def gen_adaptive_stem():
+    """AdaptiveStemLayer (DySOEM_SimFPN.py:14-25; dead code in the reference model) on a 1-channel (IR)
+    and a 3-channel (RGB) input, eval and train mode."""
+    ns = R.load()
+    g = torch.Generator().manual_seed(51)
+    torch.manual_seed(9)
+    m = ns.dysoem.AdaptiveStemLayer(32)
+    for bn in (m.gray_conv.conv[1], m.rgb_conv.conv[1]):      # non-trivial statistics / affine
+        bn.running_mean.copy_(torch.randn(32, generator=g) * 0.1)
+        bn.running_var.copy_(torch.rand(32, generator=g) * 0.5 + 0.75)
+        bn.weight.data.copy_(torch.rand(32, generator=g) * 0.5 + 0.75)
+        bn.bias.data.copy_(torch.randn(32, generator=g) * 0.1)
+    sd = copy.deepcopy(m.state_dict())
+    out = dict(sd=sd, cases=[])
+    for cin in (1, 3):
+        x = torch.rand(2, cin, 12, 12, generator=g)
+        for train in (False, True):
+            mm = ns.dysoem.AdaptiveStemLayer(32)
+            mm.load_state_dict(sd)
+            mm.train(train)
+            with torch.no_grad():
+                y = mm(x)
+            out["cases"].append(dict(x=x, train=train, y=y))
+    torch.save(out, os.path.join(OUT, "adaptive_stem.pt"))
+
+
 if __name__ == "__main__":
     if not R.available():
         raise SystemExit("reference not found; golden fixtures can only be generated in the build container")
@@ -174,5 +200,6 @@ if __name__ == "__main__":
     gen_head_loss_decode()
     gen_models()
     gen_blocks()
+    gen_adaptive_stem()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
