@@ -49,6 +49,10 @@ uint64_t uavdet_launch_count(void);
 /* reads and clears the device-side watchdog word (non-zero = a pipeline wait timed out).
  * Synchronises `stream`. */
 int uavdet_check_device(void* stream, int* flag_host);
+/* Data-parallel training (new work, SURVEY.md D6 / §8e — the reference has no collective call site): reserve `margin`
+ * SMs for the NCCL all-reduce kernels that overlap backward; the persistent tensor-core kernels launched from now on
+ * fill (148 - margin) SMs.  Returns the previous margin.  Process-wide; 0 = use every SM. */
+int uavdet_set_sm_margin(int margin);
 
 /* Measurement aid: a one-thread kernel writes the device's %globaltimer (ns) to *slot_dev in stream order.
  * Captured into a CUDA graph around a kernel it gives that kernel's duration inside the replayed step
@@ -244,7 +248,9 @@ int uavdet_bn_act_bwd_apply(const uavdet_act* dy, const uavdet_act* raw, const f
                             const uavdet_act* d_raw, void* stream);
 /* The same two phases with the per-channel finalize folded into the streaming kernel (one launch less per layer
  * and direction): uavdet_bn_train_fwd = bn_finalize + bn_act_fwd (publishes mean/invstd/scale/shift, updates the
- * running statistics); uavdet_bn_act_bwd_apply_fused = bn_bwd_finalize + bn_act_bwd_apply (publishes dgamma/dbeta). */
+ * running statistics); uavdet_bn_act_bwd_apply_fused = bn_bwd_finalize + bn_act_bwd_apply (publishes dgamma/dbeta;
+ * accumulate != 0 adds them into the buffers instead — `param.grad` of bn.weight / bn.bias, as autograd's
+ * AccumulateGrad would, so a data-parallel trainer can reduce the bucket as soon as the layer is done). */
 int uavdet_bn_train_fwd(const uavdet_act* raw, const float* sum, const float* sumsq, double count, float eps,
                         float momentum, const float* gamma, const float* beta, float* running_mean,
                         float* running_var, float* mean, float* invstd, float* scale, float* shift, int act,
@@ -252,7 +258,7 @@ int uavdet_bn_train_fwd(const uavdet_act* raw, const float* sum, const float* su
 int uavdet_bn_act_bwd_apply_fused(const uavdet_act* dy, const uavdet_act* raw, const float* scale,
                                   const float* shift, const float* sum_dz, const float* sum_dzr, const float* mean,
                                   const float* invstd, double count, int act, float* dgamma, float* dbeta,
-                                  const uavdet_act* d_raw, void* stream);
+                                  int accumulate, const uavdet_act* d_raw, void* stream);
 /* eval-mode / bias-only activation backward: dx = dy*act'(raw*scale+shift)*scale.         */
 int uavdet_act_bwd(const uavdet_act* dy, const uavdet_act* raw, const float* scale,
                    const float* shift, int act, const uavdet_act* dx, void* stream);
@@ -321,6 +327,11 @@ int uavdet_rtm_head_post(const float* bbox_logits, const float* obj_logits, int 
  * buf = momentum*buf + grad*grad_scale; p -= lr*buf   (first_step: buf = grad).            */
 int uavdet_sgd_momentum(float* param, const float* grad, float* momentum_buf, int64_t count,
                         float lr, float momentum, float grad_scale, int first_step, void* stream);
+/* The same step with the hyper-parameters read from device memory at execution time: hyper_dev = {lr, momentum,
+ * grad_scale} (3 floats).  A step captured into a CUDA graph then follows a learning-rate scheduler (the optional
+ * CyclicLR of _base.py:299-309) without re-capture: the host rewrites hyper_dev before the replay.            */
+int uavdet_sgd_momentum_dev(float* param, const float* grad, float* momentum_buf, int64_t count,
+                            const float* hyper_dev, int first_step, void* stream);
 
 #ifdef __cplusplus
 }

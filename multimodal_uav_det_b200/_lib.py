@@ -42,6 +42,7 @@ SIGNATURES = {
     "uavdet_version": (_i, []),
     "uavdet_launch_count": (C.c_uint64, []),
     "uavdet_check_device": (_i, [_P, C.POINTER(_i)]),
+    "uavdet_set_sm_margin": (_i, [_i]),
     "uavdet_timestamp": (_i, [_P, _P]),
     "uavdet_nms_workspace_bytes": (_sz, [_i, _i]),
     "uavdet_nms": (_i, [_P, _P, _i, _i, _d, _f, _P, _P, _P, _sz, _P]),
@@ -67,7 +68,7 @@ SIGNATURES = {
     "uavdet_bn_bwd_finalize": (_i, [_P, _P, _P, _P, _P, _i, _d, _P, _P, _P, _P, _P]),
     "uavdet_bn_act_bwd_apply": (_i, [_AP, _AP, _P, _P, _P, _P, _i, _AP, _P]),
     "uavdet_bn_train_fwd": (_i, [_AP, _P, _P, _d, _f, _f, _P, _P, _P, _P, _P, _P, _P, _P, _i, _AP, _AP, _P]),
-    "uavdet_bn_act_bwd_apply_fused": (_i, [_AP, _AP, _P, _P, _P, _P, _P, _P, _d, _i, _P, _P, _AP, _P]),
+    "uavdet_bn_act_bwd_apply_fused": (_i, [_AP, _AP, _P, _P, _P, _P, _P, _P, _d, _i, _P, _P, _i, _AP, _P]),
     "uavdet_act_bwd": (_i, [_AP, _AP, _P, _P, _i, _AP, _P]),
     "uavdet_upsample2x_fwd": (_i, [_AP, _AP, _P]),
     "uavdet_upsample2x_bwd": (_i, [_AP, _AP, _i, _P]),
@@ -86,6 +87,7 @@ SIGNATURES = {
     "uavdet_bilinear2x_fwd": (_i, [_AP, _AP, _P]),
     "uavdet_rtm_head_post": (_i, [_P, _P, _i, _i, _i, _i, C.POINTER(_f), _P, _P, _P]),
     "uavdet_sgd_momentum": (_i, [_P, _P, _P, _i64, _f, _f, _f, _i, _P]),
+    "uavdet_sgd_momentum_dev": (_i, [_P, _P, _P, _i64, _P, _i, _P]),
 }
 
 _lib = None

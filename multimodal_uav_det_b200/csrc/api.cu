@@ -24,6 +24,12 @@ unsigned int* watchdog_word() {
   return p;
 }
 
+static std::atomic<int> g_sm_margin{0};
+int sm_budget() {
+  const int b = kNumSMs - g_sm_margin.load(std::memory_order_relaxed);
+  return b < 1 ? 1 : b;
+}
+
 __global__ void stamp_kernel(unsigned long long* slot) {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -38,6 +44,12 @@ extern "C" int uavdet_timestamp(unsigned long long* slot_dev, void* stream) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { uavdet::set_error("timestamp launch failed: %s", cudaGetErrorString(e)); return UAVDET_ERR_CUDA; }
   return UAVDET_OK;   // not counted in uavdet_launch_count: a measurement aid, not part of the path
+}
+
+extern "C" int uavdet_set_sm_margin(int margin) {
+  if (margin < 0) margin = 0;
+  if (margin > uavdet::kNumSMs - 1) margin = uavdet::kNumSMs - 1;
+  return uavdet::g_sm_margin.exchange(margin);
 }
 
 extern "C" const char* uavdet_last_error(void) { return uavdet::g_err; }

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <atomic>
+#include <mutex>
 
 #include "../../include/uavdet_b200.h"
 
@@ -48,6 +49,29 @@ unsigned int* watchdog_word();
   } while (0)
 
 constexpr int kNumSMs = 148;  // B200
+
+// SMs the persistent tensor-core kernels may fill: kNumSMs minus the margin a data-parallel trainer reserves for the
+// NCCL all-reduce kernels that run beside backward (uavdet_set_sm_margin; a persistent CTA that cannot be placed
+// because a collective's CTA holds the SM would otherwise start a second wave).
+int sm_budget();
+
+// "first launch on this device" latch for per-device function attributes (cudaFuncSetAttribute is per device).
+struct PerDeviceOnce {
+  std::mutex mu;
+  unsigned long long done = 0;
+  template <typename F>
+  cudaError_t run(F&& f) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    std::lock_guard<std::mutex> lock(mu);
+    if (done & bit) return cudaSuccess;
+    e = f();
+    if (e == cudaSuccess) done |= bit;
+    return e;
+  }
+};
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

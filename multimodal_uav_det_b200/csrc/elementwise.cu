@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_fused_kernel(View dy, View raw, const float* __restrict__ scale, const float* __restrict__ shift,
                           const float* __restrict__ sum_dz, const float* __restrict__ sum_dzr,
                           const float* __restrict__ mean, const float* __restrict__ invstd, float inv_count, int act,
-                          float* __restrict__ dgamma, float* __restrict__ dbeta, View dr) {
+                          float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate, View dr) {
   const PixLane L = pix_lane(dy.c);
   if (!L.active) return;
   float s[8], t[8], a1[8], a0[8];
@@ -369,7 +369,11 @@ bn_bwd_apply_fused_kernel(View dy, View raw, const float* __restrict__ scale, co
       const float dg = is[j] * (sdr[j] - mu[j] * sd[j]);
       a1[j] = -s[j] * is[j] * dg * inv_count;
       a0[j] = -s[j] * sd[j] * inv_count - a1[j] * mu[j];
-      if (publish) { dgamma[L.c + j] = dg; dbeta[L.c + j] = sd[j]; }
+      // one thread per channel publishes; `accumulate` adds into a live gradient buffer (param.grad) instead
+      if (publish) {
+        dgamma[L.c + j] = accumulate ? dgamma[L.c + j] + dg : dg;
+        dbeta[L.c + j] = accumulate ? dbeta[L.c + j] + sd[j] : sd[j];
+      }
     }
   }
   auto body = [&](const uint4& din, const uint4& rin, long long px) {
@@ -850,7 +854,13 @@ __global__ void attn_mlp_softmax_kernel(const float* __restrict__ pooled, int c,
 
 // ---- SGD ------------------------------------------------------------------------------------------
 __global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                    long long count, float lr, float momentum, float grad_scale, int first) {
+                                    long long count, float lr, float momentum, float grad_scale, int first,
+                                    const float* __restrict__ hyper) {
+  if (hyper) {      // learning rate / momentum / gradient scale live on the device (CUDA-graph replay, schedulers)
+    lr = __ldg(hyper);
+    momentum = __ldg(hyper + 1);
+    grad_scale = __ldg(hyper + 2);
+  }
   const long long n4 = count >> 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
@@ -913,12 +923,13 @@ extern "C" int uavdet_bn_act_fwd(const uavdet_act* raw, const float* scale, cons
 // stream).  Two kernels share an SM only if they agree on its L1 / shared-memory split, so these streaming kernels
 // ask for the maximum-shared-memory carveout the tensor-core kernels use (they do not need the L1).
 static void prefer_max_smem_carveout_once() {
-  static bool done = false;
-  if (done) return;
-  done = true;
-  cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  cudaFuncSetAttribute(bn_bwd_apply_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  cudaFuncSetAttribute(bn_bwd_apply_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  static PerDeviceOnce once;
+  once.run([] {
+    cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(bn_bwd_apply_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return cudaFuncSetAttribute(bn_bwd_apply_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared);
+  });
 }
 
 extern "C" int uavdet_bn_act_bwd_reduce(const uavdet_act* dy, const uavdet_act* raw, const float* scale,
@@ -992,7 +1003,8 @@ extern "C" int uavdet_bn_train_fwd(const uavdet_act* raw, const float* sum, cons
 extern "C" int uavdet_bn_act_bwd_apply_fused(const uavdet_act* dy, const uavdet_act* raw, const float* scale,
                                              const float* shift, const float* sum_dz, const float* sum_dzr,
                                              const float* mean, const float* invstd, double count, int act,
-                                             float* dgamma, float* dbeta, const uavdet_act* d_raw, void* stream) {
+                                             float* dgamma, float* dbeta, int accumulate, const uavdet_act* d_raw,
+                                             void* stream) {
   int rc;
   if ((rc = check_view(dy, "bn_bwd_apply_fused dy")) || (rc = check_view(raw, "bn_bwd_apply_fused raw")) ||
       (rc = check_view(d_raw, "bn_bwd_apply_fused d_raw")) || (rc = same_shape(dy, raw, "bn_bwd_apply_fused")) ||
@@ -1005,7 +1017,7 @@ extern "C" int uavdet_bn_act_bwd_apply_fused(const uavdet_act* dy, const uavdet_
   static const int ppt = getenv("UAVDET_BN_APPLY_PPT") ? atoi(getenv("UAVDET_BN_APPLY_PPT")) : 4;
   bn_bwd_apply_fused_kernel<<<stream_grid(dy, ppt), 256, 0, ST>>>(mkview(dy), mkview(raw), scale, shift, sum_dz, sum_dzr,
                                                                mean, invstd, (float)(1.0 / count), act, dgamma, dbeta,
-                                                               mkview(d_raw));
+                                                               accumulate, mkview(d_raw));
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }
@@ -1186,7 +1198,18 @@ extern "C" int uavdet_sgd_momentum(float* param, const float* grad, float* momen
   UAVDET_CHECK_ARG((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)momentum_buf) & 15) == 0, "sgd: 16-byte alignment");
   if (count == 0) return UAVDET_OK;
   sgd_momentum_kernel<<<ew_grid(count / 4 + 1, 256), 256, 0, ST>>>(param, grad, momentum_buf, count, lr, momentum,
-                                                                   grad_scale, first_step);
+                                                                   grad_scale, first_step, nullptr);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_sgd_momentum_dev(float* param, const float* grad, float* momentum_buf, int64_t count,
+                                       const float* hyper_dev, int first_step, void* stream) {
+  UAVDET_CHECK_ARG(param && grad && momentum_buf && hyper_dev && count >= 0, "sgd_dev: bad arguments");
+  UAVDET_CHECK_ARG((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)momentum_buf) & 15) == 0, "sgd_dev: 16-byte alignment");
+  if (count == 0) return UAVDET_OK;
+  sgd_momentum_kernel<<<ew_grid(count / 4 + 1, 256), 256, 0, ST>>>(param, grad, momentum_buf, count, 0.f, 0.f, 1.f,
+                                                                   first_step, hyper_dev);
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }

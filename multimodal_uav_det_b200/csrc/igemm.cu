@@ -931,16 +931,16 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
   // each CTA allocates all 512 TMEM columns.
   const int smem_bytes = max_smem;
   if (P.total_tiles <= 0) return UAVDET_OK;
-  int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
+  const int sms = sm_budget();
+  int grid = P.total_tiles < sms ? P.total_tiles : sms;
   if (!P.res_tma) { mapRes = mapOut; mapResTail = mapOutTail; }
   const int kind = (P.epi == UAVDET_EPI_HEAD) ? 3 : (P.epi == UAVDET_EPI_STATS) ? 0 : (P.act == UAVDET_ACT_NONE ? 1 : 2);
-  static bool attr_set[4] = {false, false, false, false};
+  static PerDeviceOnce attr_once[4];   // the dynamic-shared-memory opt-in is per device
 #define UAVDET_LAUNCH_IGEMM(K)                                                                                         \
   do {                                                                                                                 \
-    if (!attr_set[K]) {                                                                                                \
-      UAVDET_CUDA(cudaFuncSetAttribute(igemm_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));       \
-      attr_set[K] = true;                                                                                              \
-    }                                                                                                                  \
+    UAVDET_CUDA(attr_once[K].run([] {                                                                                  \
+      return cudaFuncSetAttribute(igemm_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);           \
+    }));                                                                                                               \
     igemm_kernel<K><<<grid, kIgemmThreads, smem_bytes, st>>>(mapA, mapB, mapOut, mapOutTail, mapRes, mapResTail, P);  \
   } while (0)
   switch (kind) {

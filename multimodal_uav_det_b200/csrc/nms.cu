@@ -622,12 +622,10 @@ extern "C" int uavdet_nms(const float* boxes, const float* scores, int batch, in
   float thr_f = (float)iou_thr;
   if ((double)thr_f > iou_thr) thr_f = nextafterf(thr_f, -INFINITY);
   size_t smem = kSmemListOffset + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    UAVDET_CUDA(cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     227 * 1024));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;     // the opt-in is per device
+  UAVDET_CUDA(attr_once.run([] {
+    return cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  }));
   // CTAs per image: as many as keep the whole batch co-resident (about 16 clusters of 8 fit on 148 SMs)
   int ncta = 1;
   if (n >= 4096) ncta = batch <= 16 ? 8 : batch <= 32 ? 4 : batch <= 64 ? 2 : 1;

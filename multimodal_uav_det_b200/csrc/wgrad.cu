@@ -447,7 +447,7 @@ extern "C" int uavdet_conv_wgrad(const uavdet_act* x, const uavdet_act* dy, int 
     long long best = -1;
     const int ctas_per_split = P.items * samples;
     for (int s_ = 1; s_ <= 148 && s_ <= tiles_avail; ++s_) {
-      const long long waves = ceil_div(ctas_per_split * s_, kNumSMs);
+      const long long waves = ceil_div(ctas_per_split * s_, sm_budget());
       const long long cost = waves * (ceil_div(tiles_avail, s_) + 6);   // +6: per-CTA prologue/epilogue in tile units
       if (best < 0 || cost < best) { best = cost; splits = s_; }
     }
@@ -467,14 +467,13 @@ extern "C" int uavdet_conv_wgrad(const uavdet_act* x, const uavdet_act* dy, int 
     rc = make_act_map(&mapX[m], x, parity, P.b_width, P.tile_w, P.tile_h + nv - 1);
     if (rc) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    UAVDET_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  static PerDeviceOnce attr_once;     // function attributes are per device
+  UAVDET_CUDA(attr_once.run([] {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
     // same L1 / shared-memory split as the streaming kernels that share the SM with this one (see elementwise.cu)
-    UAVDET_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
-  }
+    return cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  }));
   dim3 grid((unsigned)(P.items * P.k_splits), (unsigned)samples);
   const int smem_bytes = P.stages * P.stage_bytes + ctrl_bytes;
   wgrad_kernel<<<grid, kWgradThreads, smem_bytes, (cudaStream_t)stream>>>(mapDY, mapX[0], mapX[1], mapX[2], P);

@@ -206,9 +206,15 @@ class Executor:
         self._zero_arena: Optional[torch.Tensor] = None
         self._zero_cursor = 0
         self._zero_need = 0
-        self._bn_grads: List[Tuple[torch.Tensor, torch.Tensor]] = []
         self._bn_counters: List[torch.Tensor] = []
+        self._const: Dict[Tuple[str, int, str], torch.Tensor] = {}
+        self._bn_fold: Dict[int, Tuple[tuple, torch.Tensor, torch.Tensor]] = {}
         self.grad_ready_hook: Optional[Callable[[torch.Tensor], None]] = None
+
+    def producer_streams(self) -> list:
+        """Streams that gradient writes of the current backward may be pending on besides the caller's current stream:
+        the weight-gradient side stream.  A bucket reducer must wait on all of them before it reads a gradient arena."""
+        return [self._side] if (self._side is not None and self._side_keep) else []
 
     # ---- per-step zeroed fp32 scratch ---------------------------------------------------------------
     def begin_step(self, device) -> None:
@@ -269,6 +275,11 @@ class Executor:
         elif not u.stem:
             wp = self.packs.get(w)
         if u.bn is not None and train:
+            if u.conv.bias is not None:
+                raise NotImplementedError("conv bias in front of a train-mode BatchNorm (the bias would have to enter the "
+                                          "batch statistics and receive a gradient); the reference never builds one")
+            if u.bn.momentum is None:
+                raise NotImplementedError("BatchNorm2d(momentum=None) (cumulative moving average) is not implemented")
             c = u.cout
             sums = self.zeros(2, c, dev)
             if direct_stem:
@@ -277,7 +288,7 @@ class Executor:
                 raw = ops.conv_fwd(x, wp, c, k, stride, pad, s2d=s2d, epi=EPI_STATS, sum_=sums[0], sumsq=sums[1])
             n, ho, wo, _ = raw.shape
             bn = u.bn
-            mom = 0.1 if bn.momentum is None else bn.momentum
+            mom = bn.momentum
             y, mean, invstd, scale, shift = ops.bn_train_fwd(
                 raw, sums[0], sums[1], n * ho * wo, bn.eps, mom, bn.weight.detach(), bn.bias.detach(),
                 bn.running_mean if bn.track_running_stats else None,
@@ -289,11 +300,7 @@ class Executor:
             return y
         # ---- single-kernel path: eval-mode BN folded / bias-only conv ----
         if u.bn is not None:
-            bn = u.bn
-            scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
-            shift = bn.bias.detach() - bn.running_mean * scale
-            if u.conv.bias is not None:
-                shift = shift + u.conv.bias.detach() * scale
+            scale, shift = self.bn_fold(u.bn, u.conv.bias)
         else:
             scale = None
             shift = u.conv.bias.detach() if u.conv.bias is not None else None
@@ -318,6 +325,30 @@ class Executor:
             tape.append(ConvRecord(u, x, None, scale, None, None, None, res is not None, in_hw))
         return y
 
+    def bn_fold(self, bn: nn.BatchNorm2d, conv_bias: Optional[torch.Tensor] = None):
+        """Eval-mode BatchNorm folded to (scale, shift) = (gamma*rsqrt(var+eps), beta - mean*scale [+ bias*scale]),
+        cached until a parameter / running statistic of the layer changes (version counters; the parameter epoch covers
+        raw-pointer updates by the fused optimiser)."""
+        ver = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version, _PARAM_EPOCH,
+               bn.weight.data_ptr(), bn.running_var.data_ptr(), None if conv_bias is None else conv_bias._version)
+        hit = self._bn_fold.get(id(bn))
+        if hit is not None and hit[0] == ver:
+            return hit[1], hit[2]
+        scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
+        shift = bn.bias.detach() - bn.running_mean * scale
+        if conv_bias is not None:
+            shift = shift + conv_bias.detach() * scale
+        self._bn_fold[id(bn)] = (ver, scale, shift)
+        return scale, shift
+
+    def _constant(self, kind: str, c: int, device) -> torch.Tensor:
+        key = (kind, c, str(device))
+        t = self._const.get(key)
+        if t is None:
+            t = (torch.ones if kind == "ones" else torch.zeros)(c, dtype=torch.float32, device=device)
+            self._const[key] = t
+        return t
+
     @staticmethod
     def _in_hw(u: ConvUnit, x: torch.Tensor) -> Tuple[int, int]:
         return (x.shape[2], x.shape[3]) if u.stem else (x.shape[1], x.shape[2])
@@ -336,15 +367,15 @@ class Executor:
         w = u.conv.weight
         train_bn = rec.mean is not None
         if train_bn:
-            d_raw, dgamma, dbeta = ops.bn_act_bwd(dy, rec.raw, rec.scale, rec.shift, rec.mean, rec.invstd,
-                                                  u.bn.weight.detach(), u.act, buf=self.zeros(6, u.cout, dy.device))
-            self._bn_grads.append((u.bn.weight, dgamma))
-            self._bn_grads.append((u.bn.bias, dbeta))
+            d_raw = self._bn_backward(u.bn, dy, rec, u.act, u.cout)
         else:
             # eval-BN / bias-only conv: dz = dy * act'(raw); raw already holds scale*conv+shift
             d_pre = ops.act_bwd(dy, rec.raw, None, None, u.act) if rec.raw is not None else dy
             if u.conv.bias is not None and u.conv.bias.requires_grad:
-                self._bn_grads.append((u.conv.bias, self._channel_sum(d_pre)))
+                dbias = self._channel_sum(d_pre)
+                self._accumulate(u.conv.bias, dbias * rec.scale if rec.scale is not None else dbias)
+            if u.bn is not None:
+                self._frozen_bn_affine_grads(u.bn, d_pre, rec.raw, u.conv.bias)
             if rec.scale is not None:
                 # frozen-BN scale folded into the conv: d_conv = d_pre * scale
                 d_raw = ops.bn_act_fwd(d_pre, rec.scale, None, "none")
@@ -370,6 +401,46 @@ class Executor:
             else:
                 self._weight_grad(rec, u, w, d_raw)
         return dx
+
+    def _bn_backward(self, bn: nn.BatchNorm2d, dy: torch.Tensor, rec, act: str, cout: int) -> torch.Tensor:
+        """Train-mode BN(+activation) backward of one layer.  dgamma / dbeta are added straight into `bn.weight.grad` /
+        `bn.bias.grad` by the kernel and the gradient-ready hook fires right away, so a bucketed all-reduce can start
+        while backward continues (it used to wait for one flush at the end of backward)."""
+        gw = gb = None
+        if bn.weight.requires_grad and bn.bias.requires_grad:
+            gw, _ = grad_buffer(bn.weight)
+            gb, _ = grad_buffer(bn.bias)
+            if not (gw.is_contiguous() and gb.is_contiguous() and gw.dtype == torch.float32):
+                gw = gb = None
+        d_raw, dgamma, dbeta = ops.bn_act_bwd(dy, rec.raw, rec.scale, rec.shift, rec.mean, rec.invstd, bn.weight.detach(),
+                                              act, buf=self.zeros(6, cout, dy.device), grad_gamma=gw, grad_beta=gb)
+        if gw is None:
+            self._accumulate(bn.weight, dgamma)
+            self._accumulate(bn.bias, dbeta)
+        elif self.grad_ready_hook is not None:
+            self.grad_ready_hook(bn.weight)
+            self.grad_ready_hook(bn.bias)
+        return d_raw
+
+    def _frozen_bn_affine_grads(self, bn: nn.BatchNorm2d, d_pre: torch.Tensor, z: Optional[torch.Tensor],
+                                conv_bias: Optional[torch.Tensor]) -> None:
+        """Eval-mode BatchNorm with trainable affine parameters (frozen-statistics fine-tuning): torch's autograd
+        still produces dgamma = sum(dz * xhat) and dbeta = sum(dz).  `z` = gamma*xhat + beta is what the tape keeps, so
+        xhat = (z - beta) / gamma (a zero gamma gets a zero gradient: xhat is not recoverable from z there)."""
+        if not (bn.weight.requires_grad or bn.bias.requires_grad):
+            return
+        c = bn.num_features
+        if z is None:       # activation-free layer: the forward kept no pre-activation, nothing to correlate with
+            raise NotImplementedError("gradient of frozen-BatchNorm affine parameters of an activation-free layer")
+        sums = self.zeros(2, c, d_pre.device)
+        ops.bn_bwd_reduce(d_pre, z, self._constant("ones", c, d_pre.device), self._constant("zeros", c, d_pre.device),
+                          "none", sums[0], sums[1])
+        gamma, beta = bn.weight.detach(), bn.bias.detach()
+        if bn.bias.requires_grad:
+            self._accumulate(bn.bias, sums[0].clone())
+        if bn.weight.requires_grad:
+            safe = torch.where(gamma == 0, torch.ones_like(gamma), gamma)
+            self._accumulate(bn.weight, torch.where(gamma == 0, torch.zeros_like(gamma), (sums[1] - beta * sums[0]) / safe))
 
     def _wgrad_stream(self, device):
         if not self.overlap_wgrad or device.type != "cuda":
@@ -441,7 +512,9 @@ class Executor:
                 raw = ops.conv_fwd(x, w_b, co, k, s, p, s2d=sp.s2d, w_batch=n, epi=EPI_STATS, shift=bias_b,
                                    shift_per_sample=bias_b is not None, sum_=sums[0], sumsq=sums[1])
             _, ho, wo, _ = raw.shape
-            mom = 0.1 if bn.momentum is None else bn.momentum
+            if bn.momentum is None:
+                raise NotImplementedError("BatchNorm2d(momentum=None) (cumulative moving average) is not implemented")
+            mom = bn.momentum
             y, mean, invstd, scale, shift = ops.bn_train_fwd(raw, sums[0], sums[1], n * ho * wo, bn.eps, mom,
                                                              bn.weight.detach(), bn.bias.detach(), bn.running_mean,
                                                              bn.running_var, sp.act)
@@ -450,8 +523,7 @@ class Executor:
             if tape is not None:
                 tape.append(DynRecord(sp, x, pooled, hidden, attn, bank, bias_bank, raw, scale, shift, mean, invstd, in_hw))
             return y
-        scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
-        shift = bn.bias.detach() - bn.running_mean * scale
+        scale, shift = self.bn_fold(bn)
         per_sample_shift = bias_b is not None
         if per_sample_shift:
             shift = (shift.unsqueeze(0) + bias_b * scale.unsqueeze(0)).contiguous()
@@ -489,12 +561,10 @@ class Executor:
         sp = rec.spec
         n = rec.attn.shape[0]
         if rec.mean is not None:
-            d_raw, dgamma, dbeta = ops.bn_act_bwd(dy, rec.raw, rec.scale, rec.shift, rec.mean, rec.invstd,
-                                                  sp.bn.weight.detach(), sp.act, buf=self.zeros(6, sp.cout, dy.device))
-            self._bn_grads.append((sp.bn.weight, dgamma))
-            self._bn_grads.append((sp.bn.bias, dbeta))
+            d_raw = self._bn_backward(sp.bn, dy, rec, sp.act, sp.cout)
         else:
             d_pre = ops.act_bwd(dy, rec.raw, None, None, sp.act)
+            self._frozen_bn_affine_grads(sp.bn, d_pre, rec.raw, None)
             d_raw = ops.bn_act_fwd(d_pre, rec.scale, None, "none")
         # per-sample kernel gradient -> expert-bank gradient + attention gradient
         if sp.stem and rec.x.dtype == torch.bfloat16:
@@ -543,25 +613,7 @@ class Executor:
         return t.float().sum(dim=(0, 1, 2))
 
     def end_backward(self):
-        """Join the weight-gradient stream, then flush the small per-channel gradients (BN affine, biases) in one
-        multi-tensor pass."""
+        """Join the weight-gradient stream (every per-channel gradient was already written and announced per layer)."""
         if self._side is not None and self._side_keep:
             torch.cuda.current_stream().wait_stream(self._side)
         self._side_keep = []
-        if not self._bn_grads:
-            return
-        acc_p, acc_g = [], []
-        for p, g in self._bn_grads:
-            if not p.requires_grad:
-                continue
-            if p.grad is None:
-                p.grad = g.clone().reshape(p.shape)
-            else:
-                acc_p.append(p.grad)
-                acc_g.append(g.reshape(p.shape))
-        if acc_p:
-            torch._foreach_add_(acc_p, acc_g)
-        if self.grad_ready_hook is not None:
-            for p, _ in self._bn_grads:
-                self.grad_ready_hook(p)
-        self._bn_grads = []

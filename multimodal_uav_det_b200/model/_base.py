@@ -36,10 +36,13 @@ except Exception:  # pragma: no cover - depends on the environment
 _ACT_LAYERS = {"silu": lambda: nn.SiLU(inplace=True), "relu": lambda: nn.ReLU(inplace=True)}
 
 
-def to_nhwc(x: torch.Tensor) -> torch.Tensor:
-    """API edge: NCHW fp32 -> NHWC bf16 (already-NHWC bf16 passes through)."""
-    if x.dtype == torch.bfloat16:
-        return x
+def to_nhwc(x: torch.Tensor, channels: Optional[int] = None) -> torch.Tensor:
+    """API edge: NCHW (fp32, or bf16/fp16 under autocast) -> NHWC bf16.  A bf16 tensor is taken as the package's own
+    NHWC activation only if its shape says so (`channels` = the consumer's input channels, when known): an NCHW bf16
+    tensor handed in under autocast is converted, not misread."""
+    if x.dtype == torch.bfloat16 and x.dim() == 4:
+        if channels is None or (x.shape[3] == channels and (x.shape[1] != channels or x.stride(3) == 1)):
+            return x
     return ops.nchw_f32_to_nhwc(x.float().contiguous())
 
 
@@ -67,7 +70,8 @@ class ConvModule(LightningModule):
     def forward(self, x):
         cin = self.conv[0].in_channels
         stem = cin < 32
-        y = self._exec.conv_forward(self.unit(stem=stem), x if stem else to_nhwc(x), self.training, None)
+        y = self._exec.conv_forward(self.unit(stem=stem), x.float().contiguous() if stem else to_nhwc(x, cin),
+                                    self.training, None)
         self._exec.end_forward()
         return to_nchw(y)
 
@@ -120,7 +124,7 @@ class DyConvModule(LightningModule):
 
     def forward(self, x, attn_temp):
         stem = self.in_channels < 32
-        return to_nchw(self.forward_nhwc(x.float().contiguous() if stem else to_nhwc(x), attn_temp))
+        return to_nchw(self.forward_nhwc(x.float().contiguous() if stem else to_nhwc(x, self.in_channels), attn_temp))
 
 
 class ObjectnessHead(LightningModule):
@@ -246,9 +250,6 @@ class YOLOHead(LightningModule):
     def compute_metrics(self, outs: List[DetectionResults], batch: BatchData, return_ap=False):
         """-> (total_loss, ap|None, bbox_loss, obj_loss), reference _base.py:155-212, evaluated as
         batched tensor math per head (no per-sample loop, no device sync)."""
-        if return_ap:
-            raise NotImplementedError("mAP needs torchmetrics (CPU evaluation, out of scope); use "
-                                      "postprocess via multimodal_uav_det_b200.inference.detect for NMS")
         bsz = len(batch.image)
         targets = batch.bbox
         per_sample = isinstance(targets, (list, tuple)) and isinstance(targets[0], (list, tuple))
@@ -264,7 +265,8 @@ class YOLOHead(LightningModule):
                 # value + gradient of the head scale in three launches (csrc/loss.cu)
                 bl, ol, new_t = yolo_head_loss_fused(out.bbox.float(), out.obj.float(), tgt.float(),
                                                      self.anchors[h] / self.head_scales[h], self.obj_scales_w[h],
-                                                     weights, self.bbox_loss_fn, want_new_t=self.mutate_targets)
+                                                     weights, self.bbox_loss_fn,
+                                                     want_new_t=self.mutate_targets or return_ap)
             else:
                 sa = self._scaled_anchors(h, out.bbox.device)
                 bl, ol, new_t = yolo_head_loss(out.bbox.float(), out.obj.float(), tgt, sa, self.obj_scales_w[h],
@@ -279,7 +281,31 @@ class YOLOHead(LightningModule):
                     targets[h][..., 1:] = new_t.detach()
         bbox_losses = bbox_losses / bsz
         obj_losses = obj_losses / bsz
-        return bbox_losses + obj_losses, None, bbox_losses, obj_losses
+        ap = self._average_precision(outs, new_t, bsz) if return_ap else None
+        return bbox_losses + obj_losses, ap, bbox_losses, obj_losses
+
+    def _average_precision(self, outs: List[DetectionResults], last_head_targets: Optional[torch.Tensor], bsz: int):
+        """The `return_ap` branch (reference _base.py:194-204): per image, decode every head, flatten `(a h w)`,
+        cxcywh->xyxy, concatenate the heads, `nms(boxes, logits, 0.5)` and hand the kept boxes to `calculate_ap`.
+        Decode and NMS run batched on the CUDA kernels (3 decode launches + 1 NMS launch for the whole batch); the kept
+        detections stay in `self.last_detections`.  mAP itself is torchmetrics' CPU evaluation (out of scope): it is
+        called when torchmetrics is importable — with the reference's arguments, including its quirk of passing the
+        LAST head's rebuilt target tensor — otherwise the per-image kept detections are returned in the `ap` slot."""
+        from .. import inference
+        with torch.no_grad():
+            det = inference.postprocess([DetectionResults(bbox=o.bbox.detach(), obj=o.obj.detach()) for o in outs],
+                                        self.anchors.tolist(), self.head_scales.tolist(), self.bbox_loss_fn, 0.5)
+        self.last_detections = det
+        kept = inference.kept_lists(det)
+        try:
+            from ..utils.metrics import calculate_ap
+            import torchmetrics  # noqa: F401
+        except Exception:
+            return [dict(boxes=det.boxes[i][k], scores=det.scores[i][k], keep=k) for i, k in enumerate(kept)]
+        total = torch.zeros((), device=det.boxes.device)
+        for i, k in enumerate(kept):
+            total = total + calculate_ap(det.boxes[i][k], det.scores[i][k], last_head_targets[i])["map"].to(total.device)
+        return total / bsz
 
 
 class BaseModel(LightningModule):

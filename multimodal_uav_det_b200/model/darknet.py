@@ -42,7 +42,8 @@ class CNNBlock(LightningModule):
 
     def forward(self, x):
         u = self.unit()
-        y = self._exec.conv_forward(u, x.float().contiguous() if u.stem else to_nhwc(x), self.training, None)
+        y = self._exec.conv_forward(u, x.float().contiguous() if u.stem else to_nhwc(x, self.conv.in_channels),
+                                    self.training, None)
         self._exec.end_forward()
         return to_nchw(y)
 

@@ -66,10 +66,21 @@ def launch_count() -> int:
     return int(_lib.load().uavdet_launch_count())
 
 
+def set_sm_margin(margin: int) -> int:
+    """Reserve `margin` SMs for collectives that overlap the tensor-core kernels; returns the previous margin."""
+    return int(_lib.load().uavdet_set_sm_margin(int(margin)))
+
+
 def check_device() -> None:
     """Synchronise and raise if a kernel's pipeline watchdog tripped."""
     flag = C.c_int(0)
     check(_lib.load().uavdet_check_device(_stream(), C.byref(flag)), "device watchdog")
+
+
+def poll_watchdog() -> None:
+    """check_device() for training loops: raises UavdetError if a bounded pipeline wait of a tensor-core kernel expired
+    since the last poll (the kernel drains instead of hanging; its results are then garbage)."""
+    check_device()
 
 
 def timestamp(slots: torch.Tensor, index: int) -> None:
@@ -476,9 +487,11 @@ def bn_act_fwd(raw, scale, shift, act, res=None, out=None):
     return out
 
 
-def bn_act_bwd(dy, raw, scale, shift, mean, invstd, gamma, act, buf=None):
+def bn_act_bwd(dy, raw, scale, shift, mean, invstd, gamma, act, buf=None, grad_gamma=None, grad_beta=None):
     """Train-mode BN(+act) backward.  Returns (d_raw bf16, dgamma fp32, dbeta fp32).
-    `gamma` is unused (scale = gamma*invstd already carries it); kept for call-site symmetry."""
+    `gamma` is unused (scale = gamma*invstd already carries it); kept for call-site symmetry.
+    grad_gamma / grad_beta: live fp32 gradient buffers (`bn.weight.grad`, `bn.bias.grad`) the kernel ADDS dgamma / dbeta
+    into (returned as such), so no separate accumulation pass is needed."""
     c = raw.shape[3]
     a = ACT[act] if not isinstance(act, int) else act
     if buf is None:                                                      # (6, c) zeros: sum_dz, sum_dzr, dgamma, dbeta, k1, k0
@@ -496,11 +509,26 @@ def bn_act_bwd(dy, raw, scale, shift, mean, invstd, gamma, act, buf=None):
               "bn_bwd_finalize")
         check(lib.uavdet_bn_act_bwd_apply(C.byref(dv), C.byref(rv), _ptr(scale), _ptr(shift), _ptr(buf[4]), _ptr(buf[5]),
                                           a, C.byref(ov), _stream()), "bn_act_bwd_apply")
+        if grad_gamma is not None and grad_beta is not None:
+            grad_gamma.add_(buf[2])
+            grad_beta.add_(buf[3])
+            return d_raw, grad_gamma, grad_beta
         return d_raw, buf[2], buf[3]
+    into = grad_gamma is not None and grad_beta is not None
+    dg, db = (_f32(grad_gamma), _f32(grad_beta)) if into else (buf[2], buf[3])
     check(lib.uavdet_bn_act_bwd_apply_fused(C.byref(dv), C.byref(rv), _ptr(scale), _ptr(shift), _ptr(buf[0]), _ptr(buf[1]),
-                                            _ptr(mean), _ptr(invstd), float(count), a, _ptr(buf[2]), _ptr(buf[3]),
+                                            _ptr(mean), _ptr(invstd), float(count), a, _ptr(dg), _ptr(db), 1 if into else 0,
                                             C.byref(ov), _stream()), "bn_act_bwd_apply_fused")
-    return d_raw, buf[2], buf[3]
+    return d_raw, dg, db
+
+
+def bn_bwd_reduce(dy, raw, scale, shift, act, sum_dz, sum_dzr) -> None:
+    """sum_dz[c] += sum_p dz, sum_dzr[c] += sum_p dz*raw with dz = dy * act'(raw*scale + shift) (phase 1 of the
+    BatchNorm backward; also the per-channel sums behind the affine gradients of a frozen BatchNorm)."""
+    dv, rv = act_view(dy), act_view(raw)
+    check(_lib.load().uavdet_bn_act_bwd_reduce(C.byref(dv), C.byref(rv), _ptr(_f32(scale)), _ptr(_f32(shift)),
+                                               ACT[act] if not isinstance(act, int) else act, _ptr(sum_dz), _ptr(sum_dzr),
+                                               _stream()), "bn_act_bwd_reduce")
 
 
 def act_bwd(dy, raw, scale, shift, act):
@@ -676,3 +704,9 @@ def sgd_momentum(param, grad, buf, lr, momentum, grad_scale=1.0, first_step=Fals
     check(_lib.load().uavdet_sgd_momentum(_ptr(param), _ptr(grad), _ptr(buf), param.numel(), float(lr),
                                           float(momentum), float(grad_scale), 1 if first_step else 0, _stream()),
           "sgd_momentum")
+
+
+def sgd_momentum_dev(param, grad, buf, hyper, first_step=False):
+    """SGD(momentum) step with {lr, momentum, grad_scale} read from the 3-float device tensor `hyper` at run time."""
+    check(_lib.load().uavdet_sgd_momentum_dev(_ptr(param), _ptr(grad), _ptr(buf), param.numel(), _ptr(_f32(hyper)),
+                                              1 if first_step else 0, _stream()), "sgd_momentum_dev")

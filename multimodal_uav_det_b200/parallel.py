@@ -12,6 +12,8 @@ One process per GPU.  Parameters and gradients are re-homed into a few large fla
 """
 from __future__ import annotations
 
+import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -57,14 +59,25 @@ class _Bucket:
 
 
 class FlatSGDTrainer:
-    """Flat-arena SGD(momentum) + bucketed gradient all-reduce for one model replica."""
+    """Flat-arena SGD(momentum) + bucketed gradient all-reduce for one model replica.
+
+    accumulate_grad_batches = k (reference params.yaml:23 trains with 2): `step()` is called after k backward passes;
+    gradients accumulate in the arenas, a bucket is all-reduced once — when its last gradient of the k-th (boundary)
+    micro-batch has been written, so the reduce still overlaps that backward — and the optimiser sees the mean over
+    the k micro-batches and the world (Lightning divides each micro-batch loss by k; here 1/(k*world) is folded into
+    the fused SGD kernel).
+
+    Learning rate and momentum live in a 3-float device tensor read by the SGD kernel at run time, so a step captured
+    into a CUDA graph follows `trainer.lr = ...` / `cyclic_lr` (reference _base.py:299-309) without re-capture."""
 
     def __init__(self, model: torch.nn.Module, lr: float, momentum: float, bucket_mb: float = 32.0,
-                 process_group=None):
+                 process_group=None, accumulate_grad_batches: int = 1, sm_margin: Optional[int] = None):
         self.model = model
-        self.lr, self.momentum = lr, momentum
         self.group = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.accumulate = int(accumulate_grad_batches)
+        if self.accumulate < 1:
+            raise ValueError("accumulate_grad_batches must be >= 1")
         params = [p for p in model.parameters() if p.requires_grad]
         device = params[0].device
         cap = int(bucket_mb * 1024 * 1024 / 4)
@@ -79,19 +92,78 @@ class FlatSGDTrainer:
         if cur:
             self.buckets.append(_Bucket(cur, device))
         self._bucket_of: Dict[int, _Bucket] = {id(p): b for b in self.buckets for p in b.params}
-        self._first = True
-        self._comm_stream = torch.cuda.Stream(device=device) if (self.world > 1 and device.type == "cuda") else None
         self._device = device
+        self._hyper = torch.zeros(3, dtype=torch.float32, device=device)
+        self._hyper_host = torch.zeros(3, dtype=torch.float32)
+        if device.type == "cuda":
+            self._hyper_host = self._hyper_host.pin_memory()
+        self._lr, self._momentum = float(lr), float(momentum)
+        self._hyper_dirty = True
+        self.steps_done = 0
+        # the all-reduce runs beside backward on a high-priority stream: its CTAs must get an SM as soon as one frees
+        self._comm_stream = torch.cuda.Stream(device=device, priority=-1) if (self.world > 1 and device.type == "cuda") else None
+        # SMs left to the collective's CTAs while reduces are in flight (the persistent conv kernels fill the rest)
+        if sm_margin is None:
+            sm_margin = int(os.environ.get("UAVDET_DP_SM_MARGIN", "8"))
+        self.sm_margin = sm_margin if (self.world > 1 and device.type == "cuda") else 0
+        self._margin_on = False
         bump_param_epoch()
-        execs = [m._exec for m in model.modules() if hasattr(m, "_exec") and hasattr(m, "_forward_program")]
-        for ex in execs:
+        self._execs = [m._exec for m in model.modules() if hasattr(m, "_exec") and hasattr(m, "_forward_program")]
+        for ex in self._execs:
             ex.grad_ready_hook = self._on_grad_ready
         self._arm()
+
+    # ---- hyper-parameters ---------------------------------------------------------------------
+    @property
+    def lr(self) -> float:
+        return self._lr
+
+    @lr.setter
+    def lr(self, value: float) -> None:
+        self._lr = float(value)
+        self._hyper_dirty = True
+
+    @property
+    def momentum(self) -> float:
+        return self._momentum
+
+    @momentum.setter
+    def momentum(self, value: float) -> None:
+        self._momentum = float(value)
+        self._hyper_dirty = True
+
+    def sync_hyper(self) -> None:
+        """Publish lr / momentum / gradient scale to the device tensor the SGD kernel reads (stream-ordered copy from
+        pinned memory; a no-op when nothing changed).  Called by `step()` and before every graph replay."""
+        if not self._hyper_dirty:
+            return
+        self._hyper_host[0] = self._lr
+        self._hyper_host[1] = self._momentum
+        self._hyper_host[2] = 1.0 / (self.world * self.accumulate)
+        self._hyper.copy_(self._hyper_host, non_blocking=True)
+        self._hyper_dirty = False
+
+    @staticmethod
+    def cyclic_lr(step: int, base_lr: float, max_lr: float, step_size_up: int = 4000, mode: str = "triangular2") -> float:
+        """torch.optim.lr_scheduler.CyclicLR(base_lr, max_lr, step_size_up, mode, cycle_momentum=False) evaluated at
+        `step` scheduler steps (reference _base.py:299-309 uses base = lr/10, max = lr, 4000, 'triangular2')."""
+        total = 2.0 * step_size_up
+        cycle = math.floor(1 + step / total)
+        x = 1.0 + step / total - cycle
+        scale = x / 0.5 if x <= 0.5 else (x - 1) / (0.5 - 1)
+        height = (max_lr - base_lr) * scale
+        if mode == "triangular":
+            factor = 1.0
+        elif mode == "triangular2":
+            factor = 1.0 / (2.0 ** (cycle - 1))
+        else:
+            raise ValueError("cyclic_lr: mode must be 'triangular' or 'triangular2'")
+        return base_lr + height * factor
 
     # ---- gradient lifecycle ------------------------------------------------------------------
     def _arm(self):
         for b in self.buckets:
-            b.pending = len(b.params)
+            b.pending = len(b.params) * self.accumulate
             b.work = None
 
     def zero_grad(self):
@@ -106,22 +178,37 @@ class FlatSGDTrainer:
         b = self._bucket_of.get(id(p))
         if b is None:
             return
+        if b.work is not None or b.pending <= 0:
+            raise RuntimeError("FlatSGDTrainer: a gradient arrived for a bucket that is already being reduced — more "
+                               f"backward passes than accumulate_grad_batches={self.accumulate} before step()")
         b.pending -= 1
         if b.pending == 0 and self.world > 1:
             self._launch_reduce(b)
 
     def _launch_reduce(self, b: _Bucket):
         if self._comm_stream is not None:
+            if self.sm_margin and not self._margin_on:
+                ops.set_sm_margin(self.sm_margin)
+                self._margin_on = True
+            # gradients of the bucket were written on the caller's stream and on the executors' weight-gradient
+            # side streams: the collective waits for all of them
             self._comm_stream.wait_stream(torch.cuda.current_stream())
+            for ex in self._execs:
+                for s in ex.producer_streams():
+                    self._comm_stream.wait_stream(s)
             with torch.cuda.stream(self._comm_stream):
                 b.work = dist.all_reduce(b.grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         else:  # gloo / CPU tests
             b.work = dist.all_reduce(b.grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def finish_reduce(self):
-        """Reduce any bucket whose hook did not fire (unused parameters) and join the side stream."""
+        """Reduce any bucket whose hooks did not all fire (unused parameters) and join the side stream."""
         if self.world == 1:
             return
+        if self._comm_stream is not None:       # a late bucket must see every write of backward
+            for ex in self._execs:
+                for s in ex.producer_streams():
+                    torch.cuda.current_stream().wait_stream(s)
         for b in self.buckets:
             if b.work is None:
                 self._launch_reduce(b)
@@ -129,22 +216,30 @@ class FlatSGDTrainer:
             b.work.wait()
         if self._comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self._comm_stream)
+        if self._margin_on:
+            ops.set_sm_margin(0)
+            self._margin_on = False
 
     # ---- optimiser ----------------------------------------------------------------------------
     def step(self):
         """All-reduce join + fused SGD(momentum) on every bucket (torch.optim.SGD semantics,
-        reference _base.py:292-293; gradient averaged over the data-parallel world)."""
+        reference _base.py:292-293; gradient averaged over the data-parallel world and the accumulated
+        micro-batches).  The momentum buffers start at zero, so the first step's `buf = grad` of torch is the
+        ordinary update."""
         self.finish_reduce()
-        scale = 1.0 / self.world
+        scale = 1.0 / (self.world * self.accumulate)
+        if self.buckets and self.buckets[0].param.is_cuda:
+            self.sync_hyper()
         for b in self.buckets:
             if b.param.is_cuda:
-                ops.sgd_momentum(b.param, b.grad, b.momentum, self.lr, self.momentum, grad_scale=scale,
-                                 first_step=self._first)
+                ops.sgd_momentum_dev(b.param, b.grad, b.momentum, self._hyper)
             else:  # host-side logic tests (gloo): same arithmetic in torch
                 g = b.grad * scale
-                b.momentum.copy_(g if self._first else self.momentum * b.momentum + g)
-                b.param.add_(b.momentum, alpha=-self.lr)
-        self._first = False
+                b.momentum.mul_(self._momentum).add_(g)
+                b.param.add_(b.momentum, alpha=-self._lr)
+        self.steps_done += 1
+        if self.steps_done % 64 == 1 and self.buckets[0].param.is_cuda and not torch.cuda.is_current_stream_capturing():
+            ops.poll_watchdog()     # a tripped pipeline wait must not train on silently (costs one 4-byte read)
         bump_param_epoch()
         self._arm()
 
@@ -186,6 +281,11 @@ class GraphedTrainStep:
         prev_mut = head.mutate_targets
         head.mutate_targets = False            # targets are inputs of the graph, never rewritten in place
 
+        if trainer.accumulate != 1:
+            raise NotImplementedError("GraphedTrainStep captures one micro-batch per optimiser step; use the eager "
+                                      "FlatSGDTrainer loop for accumulate_grad_batches > 1")
+        trainer.sync_hyper()                   # the H2D copy of the hyper-parameters must not be captured
+
         def body():
             trainer.zero_grad()
             outs = model(self.x)
@@ -208,6 +308,8 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.loss, self.bbox_loss, self.obj_loss = body()
         self.captured_launches = _ops.launch_count() - l0     # this library's kernels inside one replay
+        trainer.steps_done -= 1                                # the capture itself executed nothing
+        self.replays = 0
         head.mutate_targets = prev_mut
         bump_param_epoch()
         self._stage = None
@@ -260,6 +362,12 @@ class GraphedTrainStep:
     def __call__(self, x: Optional[torch.Tensor] = None, targets=None) -> torch.Tensor:
         if x is not None:
             self.load(x, targets if targets is not None else (self.boxes if self.encoder is not None else self.targets))
+        self.trainer.sync_hyper()     # lr / momentum set since the last replay reach the captured SGD kernels
         self.graph.replay()
+        self.trainer.steps_done += 1
+        self.replays += 1
+        if self.replays % 64 == 1:
+            from . import ops as _ops
+            _ops.poll_watchdog()
         bump_param_epoch()      # parameters were rewritten on the device: packed-weight caches are stale
         return self.loss

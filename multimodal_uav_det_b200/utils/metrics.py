@@ -1,7 +1,9 @@
 """Detection losses of the hot path (reference utils/metrics.py:8-84), written as batched,
 sync-free tensor math so the B x 3 Python loop of `YOLOHead.compute_metrics`
 (model/_base.py:163-192) collapses into a handful of launches.
-mAP (`calculate_ap`, metrics.py:88-135) is CPU-side evaluation and out of scope."""
+mAP (`calculate_ap`, metrics.py:88-135) is torchmetrics' CPU-side evaluation and out of scope; the thin
+wrapper below only exists so that `YOLOHead.compute_metrics(return_ap=True)` can hand it the NMS survivors when
+torchmetrics is installed."""
 import math
 
 import torch
@@ -158,3 +160,17 @@ def yolo_head_loss_fused(p_bbox, p_obj, tgt, scaled_anchors, obj_scale_w, weight
                                          float(obj_scale_w), tuple(float(w) for w in weights), bbox_loss_fn == "ciou",
                                          want_new_t)
     return bl, ol, (new_t if want_new_t else None)
+
+
+def calculate_ap(pred_boxes, pred_obj, target_boxes, max_det=300, iou_th=None):
+    """reference utils/metrics.py:88-135: torchmetrics MeanAveragePrecision(box_format='cxcywh') on one image's
+    predictions (single class).  Needs torchmetrics (absent from the build image: the caller gates on the import)."""
+    from torchmetrics.detection import MeanAveragePrecision
+    if iou_th is None:
+        iou_th = [0.5 + 0.05 * i for i in range(10)]
+    metric = MeanAveragePrecision(box_format="cxcywh", iou_thresholds=iou_th, max_detection_thresholds=[max_det] * 3)
+    device = target_boxes.device
+    preds = [dict(boxes=pred_boxes, scores=pred_obj, labels=torch.ones(len(pred_boxes), dtype=torch.int64, device=device))]
+    target = [dict(boxes=target_boxes, labels=torch.ones(len(target_boxes), dtype=torch.int64, device=device))]
+    metric.update(preds, target)
+    return metric.compute()

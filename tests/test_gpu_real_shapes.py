@@ -239,3 +239,36 @@ def test_loss_curve_agreement_20_sgd_steps(lib):
     assert ref[-1] < 0.75 * ref[0] and got[-1] < 0.75 * got[0]        # both actually train
     assert dev < 0.10
     assert abs(got[-1] - ref[-1]) < 0.10 * ref[-1]
+
+
+def test_compute_metrics_return_ap_runs_decode_and_nms_on_the_kernels(lib):
+    """`YOLOHead.compute_metrics(outs, batch, return_ap=True)` — the reference's only decode -> `__prepare_nms_preds`
+    -> cat -> `nms(…, 0.5)` call site (_base.py:194-204).  The loss equals the return_ap=False value; the kept
+    detections per image are bit-identical to the oracle's decode + NMS on the same logits.  (mAP itself is torchmetrics'
+    CPU evaluation: called when importable, else the kept detections come back in the `ap` slot.)"""
+    from oracle import oracle as O
+    from multimodal_uav_det_b200.model._base import YOLOHead
+    from multimodal_uav_det_b200.utils.datatype import BatchData, Config, DetectionResults
+    hp = dict(BASE_HP)
+    b, grids = 2, [20, 40, 80]
+    head = YOLOHead([32, 32, 32], hp["anchors"], hp["head_scales"], Config(hp["loss_balancing"]), "ciou")
+    g = torch.Generator().manual_seed(78)
+    logits = [(torch.randn(b, 3, s, s, 4, generator=g), torch.randn(b, 3, s, s, 1, generator=g)) for s in grids]
+    tg = _targets(hp, b, 640, seed=6)
+    outs = [DetectionResults(bbox=bb.to(DEV), obj=oo.to(DEV)) for bb, oo in logits]
+    mk = lambda: BatchData(image=torch.zeros(b, 3, 8, 8, device=DEV), bbox=[[t.to(DEV) for t in per] for per in copy.deepcopy(tg)])
+    loss0, ap0, _, _ = head.compute_metrics(outs, mk())
+    loss1, ap1, _, _ = head.compute_metrics(outs, mk(), return_ap=True)
+    assert ap0 is None and ap1 is not None
+    assert torch.equal(loss0, loss1)
+    det = head.last_detections
+    wb, ws = O.decode_yolo(logits, hp["anchors"], hp["head_scales"], True)
+    torch.testing.assert_close(det.boxes.cpu(), wb, rtol=2e-6, atol=2e-5)
+    assert torch.equal(det.scores.cpu(), ws)
+    for i in range(b):
+        want = O.nms(det.boxes[i].cpu().numpy(), det.scores[i].cpu().numpy(), 0.5)
+        got = det.keep[i, : int(det.keep_count[i])].cpu().numpy()
+        assert np.array_equal(got, want)
+        if isinstance(ap1, list):       # torchmetrics absent: kept detections in the ap slot
+            assert torch.equal(ap1[i]["keep"].cpu(), torch.from_numpy(want))
+            assert torch.equal(ap1[i]["boxes"], det.boxes[i][ap1[i]["keep"]])

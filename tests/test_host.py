@@ -223,3 +223,157 @@ def test_flat_sgd_trainer_single_process_matches_torch_sgd():
         torch.testing.assert_close(p.detach(), q.detach(), rtol=1e-6, atol=1e-7)
     # state_dict still works on the re-homed parameters
     assert set(model.state_dict()) == set(twin.state_dict())
+
+
+# ---- gradient accumulation (reference params.yaml:23 accumulate_grad_batches: 2) -----------------------------------
+_WORKER_ACCUM = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from multimodal_uav_det_b200.parallel import FlatSGDTrainer
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=2)
+torch.manual_seed(0)
+model = torch.nn.Sequential(torch.nn.Linear(23, 17), torch.nn.Linear(17, 5))
+ref = [p.detach().clone() for p in model.parameters()]
+K = 2
+trainer = FlatSGDTrainer(model, lr=0.1, momentum=0.7, bucket_mb=0.0005, accumulate_grad_batches=K)
+assert len(trainer.buckets) > 1
+bufs = [torch.zeros_like(p) for p in ref]
+seed = lambda step, micro, r: 1000 * step + 10 * micro + r
+for step in range(3):
+    trainer.zero_grad()
+    for micro in range(K):
+        g = torch.Generator().manual_seed(seed(step, micro, rank))
+        for p in reversed(list(model.parameters())):
+            pass
+        for p in model.parameters():
+            p.grad.add_(torch.randn(p.shape, generator=g))
+            trainer._on_grad_ready(p)
+        launched = [b.work is not None for b in trainer.buckets]
+        # reduce only on the boundary micro-batch
+        assert all(launched) if micro == K - 1 else not any(launched), (micro, launched)
+    trainer.step()
+    gens = {{(m, r): torch.Generator().manual_seed(seed(step, m, r)) for m in range(K) for r in range(2)}}
+    for i in range(len(ref)):
+        mean_g = sum(torch.randn(ref[i].shape, generator=gens[(m, r)]) for m in range(K) for r in range(2)) / (2 * K)
+        bufs[i] = 0.7 * bufs[i] + mean_g
+        ref[i] = ref[i] - 0.1 * bufs[i]
+for p, r in zip(model.parameters(), ref):
+    assert torch.allclose(p.detach(), r, rtol=1e-5, atol=1e-6), (p.detach() - r).abs().max()
+# a third backward before step() is an error, not a silent race with the in-flight reduce
+trainer.zero_grad()
+for micro in range(K):
+    for p in model.parameters():
+        trainer._on_grad_ready(p)
+try:
+    trainer._on_grad_ready(next(iter(model.parameters())))
+    raise SystemExit("missing guard")
+except RuntimeError as e:
+    assert "accumulate_grad_batches" in str(e)
+trainer.step()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_flat_sgd_trainer_gradient_accumulation_gloo_world_size_2(tmp_path):
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker_accum.py"
+    script.write_text(_WORKER_ACCUM.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(os.environ, RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, f"rank {r} failed:\n{o}"
+        assert f"rank {r} ok" in o
+
+
+def test_flat_sgd_trainer_accumulation_single_process_matches_torch_sgd_on_mean_gradient():
+    from multimodal_uav_det_b200.parallel import FlatSGDTrainer
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(11, 7), torch.nn.Linear(7, 3))
+    twin = copy.deepcopy(model)
+    opt = torch.optim.SGD(twin.parameters(), lr=0.05, momentum=0.78)
+    trainer = FlatSGDTrainer(model, lr=0.05, momentum=0.78, accumulate_grad_batches=2)
+    for step in range(3):
+        trainer.zero_grad()
+        opt.zero_grad()
+        for micro in range(2):
+            g = torch.Generator().manual_seed(10 * step + micro)
+            for p, q in zip(model.parameters(), twin.parameters()):
+                gr = torch.randn(p.shape, generator=g)
+                p.grad.add_(gr)
+                trainer._on_grad_ready(p)
+                q.grad = gr / 2 if q.grad is None else q.grad + gr / 2      # Lightning: loss / accumulate_grad_batches
+        trainer.step()
+        opt.step()
+    for p, q in zip(model.parameters(), twin.parameters()):
+        torch.testing.assert_close(p.detach(), q.detach(), rtol=1e-6, atol=1e-7)
+
+
+def test_cyclic_lr_matches_torch_scheduler_and_trainer_lr_is_settable():
+    """FlatSGDTrainer.cyclic_lr == torch.optim.lr_scheduler.CyclicLR as configured by the reference
+    (_base.py:299-309: base lr/10, max lr, step_size_up 4000, triangular2, cycle_momentum False)."""
+    from multimodal_uav_det_b200.parallel import FlatSGDTrainer
+    lr = 1e-4
+    w = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([w], lr=lr, momentum=0.7)
+    sched = torch.optim.lr_scheduler.CyclicLR(opt, base_lr=lr / 10, max_lr=lr, step_size_up=40, mode="triangular2",
+                                              cycle_momentum=False)
+    for step in range(400):
+        want = opt.param_groups[0]["lr"]
+        got = FlatSGDTrainer.cyclic_lr(step, lr / 10, lr, 40, "triangular2")
+        assert abs(got - want) <= 1e-12 + 1e-9 * want, (step, got, want)
+        opt.step()
+        sched.step()
+    model = torch.nn.Linear(3, 2)
+    tr = FlatSGDTrainer(model, lr=0.5, momentum=0.0)
+    before = model.weight.detach().clone()
+    tr.zero_grad()
+    model.weight.grad.add_(1.0)
+    tr.lr = 0.25                       # a scheduler changes the rate between steps
+    tr.step()
+    torch.testing.assert_close(model.weight.detach(), before - 0.25)
+
+
+def test_reference_named_state_dict_loads_strict_into_a_trainer_wrapped_model():
+    """SURVEY 8f-4: a checkpoint `state_dict` (reference key scheme, pinned by tests/test_oracle.py against the
+    reference's key list) loads with strict=True AFTER FlatSGDTrainer re-homed the parameters into flat arenas with
+    channels-last conv weights: values land in the arenas, the views stay attached, state_dict() round-trips."""
+    from multimodal_uav_det_b200.model import BaselineModel
+    from multimodal_uav_det_b200.parallel import FlatSGDTrainer
+    from multimodal_uav_det_b200.utils.datatype import Config
+    cfg = [[32, 3, 1], [64, 3, 2], ["B", 1], [128, 3, 2], ["S"]]
+    hp = dict(anchors=[[[29, 23], [48, 30], [67, 38]]], head_scales=[4], lr=1e-4, lr_scheduler=False, bbox_loss_fn="ciou",
+              loss_balancing=dict(obj_scales_w=[1.0], bbox_w=4.0, objectness_w=1.0, no_obj_w=4.0),
+              optim=dict(name="SGD", momentum=0.7), layer_config=cfg)
+    torch.manual_seed(3)
+    ckpt_model = BaselineModel(hparams=Config(hp))
+    for m in ckpt_model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_()
+            m.num_batches_tracked.fill_(7)
+    ckpt = {k: v.clone() for k, v in ckpt_model.state_dict().items()}
+    torch.manual_seed(4)
+    model = BaselineModel(hparams=Config(hp))
+    trainer = FlatSGDTrainer(model, lr=1e-4, momentum=0.7)
+    w = model.layers[1].conv.weight
+    assert not w.is_contiguous() and w.permute(0, 2, 3, 1).is_contiguous()        # channels-last storage in the arena
+    missing, unexpected = model.load_state_dict(ckpt, strict=True)
+    assert not missing and not unexpected
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, ckpt[k]), k
+    lo = {id(b): (b.param.data_ptr(), b.param.data_ptr() + 4 * b.numel) for b in trainer.buckets}
+    for p in model.parameters():
+        b = trainer._bucket_of[id(p)]
+        assert lo[id(b)][0] <= p.data_ptr() < lo[id(b)][1]                          # still a view of its arena
+    assert not w.is_contiguous() and w.permute(0, 2, 3, 1).is_contiguous()
+    # the arena itself carries the loaded values (what the fused optimiser and the weight pack read)
+    b = trainer._bucket_of[id(w)]
+    off = (w.data_ptr() - b.param.data_ptr()) // 4
+    torch.testing.assert_close(b.param[off:off + w.numel()].view(w.shape[0], 3, 3, w.shape[1]).permute(0, 3, 1, 2),
+                               ckpt["layers.1.conv.weight"])

@@ -228,3 +228,26 @@ def test_golden_fixtures_are_reproducible_from_the_reference(tmp_path):
     b = load("adaptive_stem.pt")
     for x, y in zip(a["cases"], b["cases"]):
         assert torch.equal(x["x"], y["x"]) and torch.equal(x["y"], y["y"])
+
+
+@pytest.mark.needs_reference
+def test_reference_built_state_dict_loads_strict_after_flat_trainer_rehoming():
+    """A `state_dict` produced by the UNMODIFIED reference DyYOLO (what train.py's ModelCheckpoint saves) loads with
+    strict=True into the product model after FlatSGDTrainer moved its parameters into flat channels-last arenas."""
+    from oracle import ref_import as R
+    from multimodal_uav_det_b200.model import DyYOLO
+    from multimodal_uav_det_b200.parallel import FlatSGDTrainer
+    from multimodal_uav_det_b200.utils.datatype import Config
+    ns = R.load()
+    cfg, hp = R.hparams("dy-yolo")
+    torch.manual_seed(5)
+    ref_sd = {k: v.clone() for k, v in ns.dyyolo.DyYOLO(hparams=cfg).state_dict().items()}
+    torch.manual_seed(6)
+    model = DyYOLO(hparams=Config(hp))
+    FlatSGDTrainer(model, lr=1e-4, momentum=0.7)
+    missing, unexpected = model.load_state_dict(ref_sd, strict=True)
+    assert not missing and not unexpected
+    got = model.state_dict()
+    assert list(got.keys()) == list(ref_sd.keys())
+    for k in ref_sd:
+        assert torch.equal(got[k], ref_sd[k]), k
