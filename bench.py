@@ -6,7 +6,12 @@ Anti-UAV-shaped pairs": one step = forward (train-mode BN) + YOLO loss + backwar
 update on 32 frames (16 RGB+IR pairs) of 3x640x640.  N>1: same per-GPU batch (weak scaling), data
 parallel with bucketed NCCL gradient all-reduce overlapped with backward.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|torch-gpu] [--batch B]
+                  [--model baseline|dyyolo|dysoem|rtm-infer]
+
+`--model` selects another configuration of BASELINE.json (the default, `baseline`, is configs[1], the one the metric
+is quoted on): `dyyolo` = configs[2] (DyYOLO training, data parallel), `dysoem` = configs[3] (DySOEM_SimFPN training,
+batch 64/GPU), `rtm-infer` = configs[4] (RTMUAVDet inference incl. fused decode + NMS, batch 128/GPU, replicas only).
 
 Prints ONE JSON line (rank 0).  `--impl reference` times the reference's CPU implementation of the
 same step (oracle port of the reference's ATen-CPU path; the reference itself is pure Python on
@@ -33,10 +38,34 @@ DARKNET53 = [[32, 3, 1], [64, 3, 2], ["B", 1], [128, 3, 2], ["B", 2], [256, 3, 2
              ["S"], [128, 1, 1], ["U"], [128, 1, 1], [256, 3, 1], ["S"]]
 HPARAMS = dict(anchors=ANCHORS, head_scales=HEAD_SCALES, lr=1e-4, lr_scheduler=False, loss_balancing=LOSS_BAL,
                bbox_loss_fn="ciou", optim=dict(name="SGD", momentum=0.7), layer_config=DARKNET53)
+DYYOLO = [["DyConv", 32, 3, 1], ["DyConv", 64, 3, 2]] + DARKNET53[2:11] + [["DyConv", 512, 1, 1]] + DARKNET53[12:16] + \
+         [["DyConv", 256, 1, 1]] + DARKNET53[17:21] + [["DyConv", 128, 1, 1]] + DARKNET53[22:]
+DYYOLO_HP = dict(HPARAMS, layer_config=DYYOLO, attn_temperature=30.0, bbox_loss_fn="mse",
+                 optim=dict(name="SGD", momentum=0.78))                     # conf/model/dy-yolo.yaml
+DYSOEM_HP = dict(anchors=[ANCHORS[2], ANCHORS[1], ANCHORS[0]], head_scales=[32, 16, 8], lr=1e-4, lr_scheduler=False,
+                 attention_temperature=30, num_dy_conv=[3, 3, 3], dy_kernel_size=[3, 3, 3], bbox_loss_fn="mse",
+                 loss_balancing=dict(obj_scales_w=[2.0, 1.0, 0.5], bbox_w=4.0, objectness_w=1.0, no_obj_w=4.0),
+                 optim=dict(name="SGD", momentum=0.7))                      # conf/model/dy-soem_fpn.yaml
+RTM_ANCHORS = [[[29, 23], [48, 30], [67, 38]], [[91, 54], [120, 75], [157, 60]]]
+RTM_SCORE_FLOOR = 0.5
 IMG = 640
 FWD_GFLOP_PER_FRAME = 154.52          # SURVEY.md §6 [probe], 2*MAC, BaselineModel forward
 METRIC = "train_frames_per_sec"
 UNIT = "frames/s"
+# model -> (default per-GPU batch, forward GFLOP/frame of the minimal-math formulation, grids of the
+# dense targets, workload text)
+WORKLOADS = {
+    "baseline": dict(batch=32, gflop=154.52, grids=[20, 40, 80], hp=HPARAMS, loss="ciou", momentum=0.7,
+                     text="BaselineModel (Darknet-53) training step: fwd(batch-stat BN)+YOLO ciou loss+bwd+SGD"),
+    "dyyolo": dict(batch=32, gflop=154.53, grids=[20, 40, 80], hp=DYYOLO_HP, loss="mse", momentum=0.78,
+                   text="DyYOLO (conf/model/dy-yolo.yaml, 5 DyConv sites) training step: fwd+YOLO mse loss+bwd+SGD"),
+    "dysoem": dict(batch=64, gflop=72.57, grids=[320, 160, 80], hp=DYSOEM_HP, loss="mse", momentum=0.7,
+                   text="DySOEM_SimFPN (conf/model/dy-soem_fpn.yaml, heads at 320/160/80) training step: fwd+YOLO mse "
+                        "loss+bwd+SGD"),
+    "rtm-infer": dict(batch=128, gflop=38.32, grids=None, hp=None, loss=None, momentum=None,
+                      text="RTMUAVDet inference: forward + fused sigmoid/decode + cxcywh->xyxy + batched NMS "
+                           f"(96,000 candidates/frame, IoU 0.5, score floor {RTM_SCORE_FLOOR})"),
+}
 
 
 def synth_batch(b, seed=1234):
@@ -112,56 +141,119 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference / CPU arm
 # ------------------------------------------------------------------------------------------------
-def cpu_train_step_rate(batch, steps, warmup):
-    """The reference's CPU path for the same step (fp32, ATen/MKL-DNN through the oracle's functional
-    restatement of BaselineModel + YOLOHead.compute_metrics + torch.optim.SGD), all host threads."""
+def _model_container(name):
+    """Parameter container with the reference's seeded initialisation for `name` (never run forward on the CPU)."""
+    import torch
+    from multimodal_uav_det_b200.model import BaselineModel, DyYOLO, DySOEM_SimFPN, RTMUAVDet
+    from multimodal_uav_det_b200.utils.datatype import Config
+    torch.manual_seed(0)
+    if name == "baseline":
+        return BaselineModel(hparams=Config(HPARAMS))
+    if name == "dyyolo":
+        return DyYOLO(hparams=Config(DYYOLO_HP))
+    if name == "dysoem":
+        return DySOEM_SimFPN(hparams=Config(DYSOEM_HP))
+    return RTMUAVDet([3, IMG, IMG], torch.tensor(RTM_ANCHORS).float(), 1e-4)
+
+
+def cpu_step_rate(name, batch, steps, warmup):
+    """The reference's CPU path for one step of workload `name` (fp32, ATen/MKL-DNN through the oracle's functional
+    restatement of the model + YOLOHead.compute_metrics + torch.optim.SGD, or forward + decode + NMS for `rtm-infer`),
+    all host threads.  Returns (frames/s, seconds/step, last loss or kept count)."""
     import torch
     from oracle import oracle as O
-    from multimodal_uav_det_b200.model import BaselineModel
-    from multimodal_uav_det_b200.utils.datatype import Config
     torch.set_num_threads(os.cpu_count() or 1)
-    torch.manual_seed(0)
-    model = BaselineModel(hparams=Config(HPARAMS))          # parameter container only (same init)
+    wl = WORKLOADS[name]
+    model = _model_container(name)
+    x, boxes = synth_batch(batch)
+    times = []
+    if name == "rtm-infer":
+        sd = {k: v.detach().clone() for k, v in model.eval().state_dict().items()}
+        anchors = torch.tensor(RTM_ANCHORS).float()
+        last = 0
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                outs = O.rtm_forward(x, sd, anchors)
+                b = x.shape[0]
+                cx = torch.cat([o[0].reshape(b, -1, 4) for o in outs], dim=1)
+                sc = torch.cat([o[1].reshape(b, -1) for o in outs], dim=1)
+                xyxy = O.cxcywh_to_xyxy(cx)
+                for i in range(b):
+                    idx = torch.nonzero(sc[i] > RTM_SCORE_FLOOR).squeeze(1)
+                    last = len(O.nms(xyxy[i][idx].numpy(), sc[i][idx].numpy(), 0.5))
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+        total = sum(times)
+        return batch * len(times) / total, total / len(times), float(last)
+    hp = wl["hp"]
     sd = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone())
           for k, v in model.state_dict().items()}
     params = [v for v in sd.values() if v.requires_grad]
-    opt = torch.optim.SGD(params, lr=HPARAMS["lr"], momentum=0.7)
-    x, boxes = synth_batch(batch)
-    tg = [O.encode_targets(boxes[i:i + 1], ANCHORS, HEAD_SCALES, IMG) for i in range(batch)]
-    times = []
+    opt = torch.optim.SGD(params, lr=hp["lr"], momentum=wl["momentum"])
+    tg = [O.encode_targets(boxes[i:i + 1], hp["anchors"], hp["head_scales"], IMG, grids=wl["grids"]) for i in range(batch)]
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
-        outs = O.darknet_forward(x, sd, DARKNET53, train=True)
-        loss, _, _ = O.yolo_loss(outs, tg, ANCHORS, HEAD_SCALES, LOSS_BAL, "ciou")
+        if name == "dysoem":
+            outs = O.dysoem_simfpn_forward(x, sd, 30.0, train=True)
+        else:
+            outs = O.darknet_forward(x, sd, hp["layer_config"], hp.get("attn_temperature"), train=True)
+        loss, _, _ = O.yolo_loss(outs, tg, hp["anchors"], hp["head_scales"], hp["loss_balancing"], wl["loss"])
         loss.backward()
         opt.step()
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
     total = sum(times)
-    return batch * len(times) / total, total / len(times), float(loss)
+    return batch * len(times) / total, total / len(times), float(loss.detach())
+
+
+# CPU seconds per frame of one step (fwd+loss+bwd+SGD, or fwd+decode+NMS) and fp32 autograd memory per frame, measured on
+# the 16-core GPU-box host in round 1/2: used only to bound the reference arm's batch so the run ends in minutes
+_CPU_S_PER_FRAME = {"baseline": 0.33, "dyyolo": 0.40, "dysoem": 0.80, "rtm-infer": 0.30}
+_CPU_GB_PER_FRAME = {"baseline": 2.8, "dyyolo": 2.9, "dysoem": 5.5, "rtm-infer": 0.6}
+
+
+def reference_batch(name, want, steps, warmup, budget_s=330.0):
+    """Largest batch <= `want` (halving) whose (warmup + steps) CPU steps fit the time budget and host memory."""
+    try:
+        import psutil
+        avail_gb = psutil.virtual_memory().available / 2 ** 30
+    except Exception:
+        avail_gb = 64.0
+    b = want
+    while b > 1 and ((warmup + steps) * b * _CPU_S_PER_FRAME[name] > budget_s or b * _CPU_GB_PER_FRAME[name] > 0.6 * avail_gb):
+        b //= 2
+    return b
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    batch = 4
-    fps, sec_per_step, _ = cpu_train_step_rate(batch, args.steps, max(1, min(args.warmup, 1)))
+    wl = WORKLOADS[args.model]
+    want = args.batch or wl["batch"]
+    warm = max(1, min(args.warmup, 1))          # the CPU path has no lazy initialisation worth more than one step
+    batch = reference_batch(args.model, want, args.steps, warm)
+    fps, sec_per_step, _ = cpu_step_rate(args.model, batch, args.steps, warm)
     cores = os.cpu_count() or 1
+    metric = "inference_frames_per_sec" if args.model == "rtm-infer" else METRIC
+    sample = (f"the full per-GPU batch of {batch}" if batch == want else
+              f"batch {batch} per step (bounded sample of the batch-{want} workload: {args.steps}+{warm} CPU steps of the "
+              f"full batch would not end within minutes)")
     line = {
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": max(1, min(args.warmup, 1)), "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
+        "impl": "reference", "metric": metric, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": warm, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BaselineModel train step (fwd+loss+bwd+SGD), 640x640, CPU fp32",
-                   "per_step_batch": batch, "sample": f"batch {batch} per step (bounded sample of the batch-32 workload)"},
+        "config": {"workload": wl["text"] + f", 3x{IMG}x{IMG}, CPU fp32 (oracle port of the reference's ATen-CPU path)",
+                   "model": args.model, "per_step_batch": batch, "same_batch_as_gpu_arm": batch == want, "sample": sample},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps of batch {batch} (fwd+loss+bwd+SGD), fp32, {cores} threads"},
+                         "sample": f"{args.steps} steps of batch {batch}, fp32, {cores} threads"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
-
 
 
 # ------------------------------------------------------------------------------------------------
@@ -183,7 +275,9 @@ def run_torch_gpu(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     torch.backends.cudnn.benchmark = True
-    B = args.batch
+    if args.model != "baseline":
+        raise SystemExit("--impl torch-gpu times the BaselineModel step (configs[1])")
+    B = args.batch or WORKLOADS["baseline"]["batch"]
     torch.manual_seed(0)
     model = BaselineModel(hparams=Config(HPARAMS))
     sd = {}
@@ -285,7 +379,7 @@ class ConvTimer:
 
     def __enter__(self):
         ops = self.ops
-        self._orig = (ops.conv_fwd, ops.conv_dgrad, ops.conv_wgrad)
+        self._orig = (ops.conv_fwd, ops.conv_dgrad, ops.conv_wgrad, ops.conv_dgrad_s2d)
         rec, stamps = self.records, self.stamps
 
         def timed(fn, kind, flops_of):
@@ -320,6 +414,13 @@ class ConvTimer:
         ops.conv_fwd = timed(self._orig[0], "igemm", fwd_flops)
         ops.conv_dgrad = timed(self._orig[1], "igemm", dgrad_flops)
         ops.conv_wgrad = timed(self._orig[2], "wgrad", wgrad_flops)
+
+        def dgrad_s2d_flops(a, kw):
+            dy, c, k = a[0], a[2], a[3]
+            n, ho, wo, cout = dy.shape
+            return 2.0 * n * ho * wo * cout * 4 * c * k * k
+
+        ops.conv_dgrad_s2d = timed(self._orig[3], "igemm", dgrad_s2d_flops)
         self._orig_bn = None
         if os.environ.get("UAVDET_BENCH_DEBUG"):
             # debug table only: the BatchNorm passes too, with their algorithmic bytes in place of flops
@@ -331,7 +432,7 @@ class ConvTimer:
         return self
 
     def __exit__(self, *exc):
-        self.ops.conv_fwd, self.ops.conv_dgrad, self.ops.conv_wgrad = self._orig
+        self.ops.conv_fwd, self.ops.conv_dgrad, self.ops.conv_wgrad, self.ops.conv_dgrad_s2d = self._orig
         if self._orig_bn is not None:
             self.ops.bn_act_fwd, self.ops.bn_act_bwd = self._orig_bn
 
@@ -357,7 +458,6 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from multimodal_uav_det_b200 import build, ops
-    from multimodal_uav_det_b200.model import BaselineModel
     from multimodal_uav_det_b200.parallel import FlatSGDTrainer, GraphedTrainStep
     from multimodal_uav_det_b200.utils.datatype import BatchData, Config
     from multimodal_uav_det_b200.utils.targets import YoloTargetEncoder
@@ -370,16 +470,18 @@ def run_ours(args, rank, world, local_rank):
         build.build_library()
     if world > 1:
         dist.barrier()
-    B = args.batch
-    torch.manual_seed(0)
-    model = BaselineModel(hparams=Config(HPARAMS)).to(dev).train()
+    wl = WORKLOADS[args.model]
+    hp = wl["hp"]
+    B = args.batch or wl["batch"]
+    model = _model_container(args.model).to(dev).train()
     model.yolo_head.mutate_targets = False      # targets are re-supplied every step (fresh copies)
-    trainer = FlatSGDTrainer(model, lr=HPARAMS["lr"], momentum=0.7)
+    fkw = {"attn_temp": 30.0} if args.model == "dysoem" else {}
+    trainer = FlatSGDTrainer(model, lr=hp["lr"], momentum=wl["momentum"])
     x_host, boxes = synth_batch(B, seed=1234 + rank)
     # the loader's product is the frame batch plus ONE pixel box per frame; the dense per-head YOLO targets the
     # reference builds in its CPU data set (dataset/AntiUAVDataset.py:141-185) are produced on the device
     # (utils.targets.YoloTargetEncoder, bit-identical), so a step receives 16 bytes of target per frame
-    encoder = YoloTargetEncoder.for_head_scales(ANCHORS, HEAD_SCALES, IMG)
+    encoder = YoloTargetEncoder(hp["anchors"], wl["grids"], IMG)
     x_pin = x_host.pin_memory()
     boxes_pin = boxes.float().contiguous().pin_memory()
     x_dev = x_pin.to(dev, non_blocking=True)
@@ -389,7 +491,7 @@ def run_ours(args, rank, world, local_rank):
 
     def step(x, tg):
         trainer.zero_grad()
-        outs = model(x)
+        outs = model(x, **fkw)
         loss, _, _, _ = model.yolo_head.compute_metrics(outs, BatchData(image=x, bbox=tg))
         loss.backward()
         trainer.step()
@@ -436,7 +538,7 @@ def run_ours(args, rank, world, local_rank):
     launches_per_step = None
     if not args.eager:
         l0 = ops.launch_count()
-        graphed = GraphedTrainStep(model, trainer, x_dev, boxes_dev, warmup=0, encoder=encoder)
+        graphed = GraphedTrainStep(model, trainer, x_dev, boxes_dev, warmup=0, encoder=encoder, forward_kwargs=fkw)
         launches_per_step = graphed.captured_launches          # our kernels recorded into the graph
         for _ in range(max(args.warmup, 3)):
             loss = graphed()
@@ -484,7 +586,7 @@ def run_ours(args, rank, world, local_rank):
             # kernels are timed one at a time: the weight gradients stay in line for this capture (in the timed
             # graph they run on a side stream under the BatchNorm backward, which would smear the stamps)
             model._exec.overlap_wgrad = False
-            instrumented = GraphedTrainStep(model, trainer, x_dev, tg_dev, warmup=0)
+            instrumented = GraphedTrainStep(model, trainer, x_dev, tg_dev, warmup=0, forward_kwargs=fkw)
             model._exec.overlap_wgrad = True
             instrumented()
             ct.stamps.zero_()
@@ -510,22 +612,29 @@ def run_ours(args, rank, world, local_rank):
     frames = B * world
     value = frames / step_s
     e2e_value = frames / (ms_e2e / args.steps * 1e-3)
-    # DRAM traffic of the dominant kernel over one step, from the committed ncu capture (profiles/, same command);
-    # reported next to the algorithmic bytes so re-reads show up
-    traffic = None
+    # DRAM traffic of the dominant kernel over one step: ncu cannot run inside this process, so the figure comes from
+    # the committed ncu pass over the same step (tools/conv_traffic_from_ncu.py) — and only if that pass saw exactly
+    # the launches the timed binary issues (a stale capture reports null, not somebody else's bytes)
+    traffic, traffic_note = None, "not measured in-run (no ncu capture matching this binary's launch count)"
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_conv_dram_traffic_per_step.json")) as f:
-            k = json.load(f)["kernels"][dom_name]
-        traffic = k["dram_read_bytes"] + k["dram_write_bytes"]
+        if args.model == "baseline" and B == 32:
+            with open(os.path.join(ROOT, "profiles", "r02_conv_dram_traffic_per_step.json")) as f:
+                k = json.load(f)["kernels"][dom_name]
+            if int(k["launches"]) == int(dom["launches"]):
+                traffic = k["dram_read_bytes"] + k["dram_write_bytes"]
+                traffic_note = ("DRAM bytes of all launches of this kernel in one step (ncu, "
+                                "profiles/r02_conv_dram_traffic_per_step.json, same launch count as the timed step)")
+            else:
+                traffic_note = (f"stale ncu capture ignored: it holds {k['launches']} launches of {dom_name}, the timed "
+                                f"step issues {dom['launches']}")
     except Exception:
         pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"BaselineModel (Darknet-53) training step: fwd(batch-stat BN)+YOLO ciou loss+bwd+SGD, "
-                               f"batch {B}/GPU ({B // 2} RGB+IR pairs), 3x640x640",
-                   "per_gpu_batch": B, "global_batch": frames, "pairs_per_sec": value / 2,
+        "config": {"workload": f"{wl['text']}, batch {B}/GPU ({B // 2} RGB+IR pairs), 3x640x640",
+                   "model": args.model, "per_gpu_batch": B, "global_batch": frames, "pairs_per_sec": value / 2,
                    "l2_policy": "inputs larger than L2: every layer streams >126 MB of activations per step",
                    "parallelism": f"dp{world}", "final_loss": final_loss,
                    "launch": "eager" if graphed is None else "one CUDA graph per step (captured fwd+loss+bwd+all-reduce+SGD)"},
@@ -534,24 +643,164 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": dom_name, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved / peak_tf, "traffic": traffic,
-                     "traffic_note": "DRAM bytes of all launches of this kernel in one step (ncu, profiles/r01_conv_dram_traffic_per_step.json); "
-                                     "achieved = FLOPs of those launches / their summed in-graph duration",
+                     "frac": achieved / peak_tf, "traffic": traffic, "traffic_note": traffic_note,
+                     "achieved_note": "algorithmic FLOPs (2*M*N*K) of this kernel's launches in one step / their summed "
+                                      "in-graph duration (device-timer stamps around every launch)",
                      "peak_source": peak_src,
                      "launches_per_step": dom["launches"], "kernel_seconds_per_step": dom["seconds"],
                      "other_kernel": {"name": "wgrad_kernel" if dom_name == "igemm_kernel" else "igemm_kernel",
                                       "achieved": (wg if dom_name == "igemm_kernel" else ig)["flops"] /
                                                   (wg if dom_name == "igemm_kernel" else ig)["seconds"] / 1e12,
                                       "seconds_per_step": (wg if dom_name == "igemm_kernel" else ig)["seconds"]},
-                     "model_flops_utilisation": 3 * FWD_GFLOP_PER_FRAME * 1e9 * B / step_s / 1e12 / peak_tf},
+                     "model_flops_utilisation": 3 * wl["gflop"] * 1e9 * B / step_s / 1e12 / peak_tf},
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        fps, sec, _ = cpu_train_step_rate(2, 1, 1)
+        fps, sec, _ = cpu_step_rate(args.model, 2, 1, 1)
         line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"1 warm + 1 timed step of batch 2 (fwd+loss+bwd+SGD), fp32, {cores} threads, "
                                           f"{sec:.1f} s/step"}
     print(json.dumps(line), flush=True)
+
+
+def run_ours_infer(args, rank, world, local_rank):
+    """configs[4]: RTMUAVDet inference incl. fused decode + NMS, batch 128 per GPU.  Inference shards by frames with no
+    exchange step: N independent replicas, value = frames of all ranks / max-over-ranks time."""
+    import torch
+    import torch.distributed as dist
+    from multimodal_uav_det_b200 import build, inference, ops
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if rank == 0:
+        build.build_library()
+    if world > 1:
+        dist.barrier()
+    wl = WORKLOADS["rtm-infer"]
+    B = args.batch or wl["batch"]
+    model = _model_container("rtm-infer").to(dev).eval()
+    x_host, _ = synth_batch(B, seed=1234 + rank)
+    x_pin = x_host.pin_memory()
+    x_dev = x_pin.to(dev, non_blocking=True)
+    TOP = 300                                   # detections read back per frame (calculate_ap's max_det, metrics.py:88)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, iters):
+        sync_all()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters):
+            fn()
+        e.record()
+        sync_all()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        det = inference.detect_rtm(model, x_dev, 0.5, RTM_SCORE_FLOOR)
+    ops.check_device()
+    l0 = ops.launch_count()
+    inference.detect_rtm(model, x_dev, 0.5, RTM_SCORE_FLOOR)
+    launches_per_step = ops.launch_count() - l0
+    run = inference.GraphedDetect(model, x_dev, 0.5, RTM_SCORE_FLOOR)
+    for _ in range(max(args.warmup, 3)):
+        det = run(run.x)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms = timed(lambda: run(run.x), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    kept_mean = float(det.keep_count.float().mean().item())
+    above = float((det.scores > RTM_SCORE_FLOOR).float().sum(dim=1).mean().item())
+
+    # ---- end to end: frames from pinned host memory every step, kept counts + top detections read back ----
+    stage = torch.empty_like(x_dev)
+    copy_stream = torch.cuda.Stream(device=dev)
+    staged, consumed = torch.cuda.Event(), torch.cuda.Event()
+    kc_host = torch.zeros(B, dtype=torch.int32).pin_memory()
+    top_host = torch.zeros((B, TOP), dtype=torch.int64).pin_memory()
+
+    def prefetch():
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed)
+            stage.copy_(x_pin, non_blocking=True)
+            staged.record()
+
+    def e2e_step():
+        cur = torch.cuda.current_stream()
+        cur.wait_event(staged)
+        run.x.copy_(stage, non_blocking=True)
+        consumed.record()
+        d = run(run.x)
+        prefetch()                                  # next batch's H2D overlaps this batch's forward
+        kc_host.copy_(d.keep_count, non_blocking=True)
+        top_host.copy_(d.keep[:, :TOP], non_blocking=True)
+        cur.synchronize()
+
+    consumed.record()
+    prefetch()
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+
+    # ---- roofline of the implicit-GEMM launches (eager pass with device-timer stamps) ----
+    with ConvTimer(ops, torch, dev) as ct:
+        torch.cuda.synchronize()
+        inference.detect_rtm(model, x_dev, 0.5, RTM_SCORE_FLOOR)
+        ct.stamps.zero_()
+        ct.records.clear()
+        inference.detect_rtm(model, x_dev, 0.5, RTM_SCORE_FLOOR)
+    ksum = ct.summary()
+    ops.check_device()
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    ig = ksum.get("igemm", {"flops": 0.0, "seconds": 1.0, "launches": 0})
+    step_s = ms / args.steps * 1e-3
+    frames = B * world
+    line = {
+        "metric": "inference_frames_per_sec", "value": frames / step_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{wl['text']}, batch {B}/GPU ({B // 2} RGB+IR pairs), 3x640x640", "model": "rtm-infer",
+                   "per_gpu_batch": B, "global_batch": frames, "pairs_per_sec": frames / step_s / 2,
+                   "l2_policy": "inputs larger than L2: every layer streams >126 MB of activations per batch",
+                   "parallelism": f"replicas x{world} (no collective)", "candidates_above_floor_per_frame": above,
+                   "kept_per_frame": kept_mean, "launch": "one CUDA graph per batch (forward + decode + NMS)"},
+        "clocks": clocks,
+        "e2e": {"value": frames / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": x_pin.numel() * 4,
+                "d2h_bytes_per_step": B * 4 + B * TOP * 8, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "roofline": {"bound": "tensor", "kernel": "igemm_kernel", "achieved": ig["flops"] / ig["seconds"] / 1e12,
+                     "peak": peak_tf, "unit": "TFLOP/s", "frac": ig["flops"] / ig["seconds"] / 1e12 / peak_tf, "traffic": None,
+                     "launches_per_step": ig["launches"], "kernel_seconds_per_step": ig["seconds"],
+                     "note": "the model as a whole is memory-dominated (SURVEY §8d: 54 us/frame HBM bound vs 27 us compute); "
+                             "per-kernel HBM fractions of the streaming kernels: profiles/r02_ncu_full_membound_kernels.txt",
+                     "model_flops_utilisation": wl["gflop"] * 1e9 * B / step_s / 1e12 / peak_tf},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        fps, sec, _ = cpu_step_rate("rtm-infer", 2, 1, 1)
+        line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"1 warm + 1 timed batch of 2 frames (forward + decode + NMS), fp32, {cores} threads, "
+                                          f"{sec:.1f} s/batch"}
+    print(json.dumps(line), flush=True)
+
 
 
 def main():
@@ -560,7 +809,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-gpu"])
-    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the configuration's own)")
+    ap.add_argument("--model", default="baseline", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch the step from Python instead of replaying its CUDA graph")
     ap.add_argument("--profile-step", action="store_true", help="run one step inside cudaProfilerStart/Stop and exit")
@@ -577,9 +827,16 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the gradient all-reduce overlaps backward on the SMs the persistent conv kernels leave free (parallel.py):
+        # keep the collective's CTA count at that margin
+        if int(os.environ.get("UAVDET_DP_SM_MARGIN", "8")) > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("UAVDET_DP_SM_MARGIN", "8"))
         dist.init_process_group("nccl", device_id=None)
     try:
-        run_ours(args, rank, world, local_rank)
+        if args.model == "rtm-infer":
+            run_ours_infer(args, rank, world, local_rank)
+        else:
+            run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -45,7 +45,12 @@ def detect_rtm(model, x: torch.Tensor, iou_threshold: float = 0.5, score_floor: 
     one fused sigmoid+decode kernel per scale); candidates of both scales are concatenated per image, converted to
     xyxy and suppressed by the batched NMS kernel.  The reference never calls NMS on this model:
     semantics = torchvision.ops.nms per image on the candidates with score > score_floor."""
-    outs = model(x)
+    return postprocess_rtm(model(x), iou_threshold, score_floor)
+
+
+@torch.no_grad()
+def postprocess_rtm(outs, iou_threshold: float = 0.5, score_floor: float = float("-inf")) -> Detections:
+    """RTMHead outputs (decoded cxcywh boxes + sigmoid objectness per scale) -> xyxy candidates + batched NMS."""
     b = outs[0].bbox.shape[0]
     boxes = torch.cat([o.bbox.reshape(b, -1, 4) for o in outs], dim=1).contiguous()
     scores = torch.cat([o.obj.reshape(b, -1) for o in outs], dim=1).contiguous()

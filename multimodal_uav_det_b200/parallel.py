@@ -262,7 +262,8 @@ class GraphedTrainStep:
     dense per-head targets: `targets` is then that box tensor everywhere (constructor, `load`, `prefetch`,
     `__call__`) and the dense targets are produced on the device right before the replay."""
 
-    def __init__(self, model, trainer: FlatSGDTrainer, x: torch.Tensor, targets, warmup: int = 2, encoder=None):
+    def __init__(self, model, trainer: FlatSGDTrainer, x: torch.Tensor, targets, warmup: int = 2, encoder=None,
+                 forward_kwargs: Optional[dict] = None):
         from .utils.datatype import BatchData
         self.model, self.trainer = model, trainer
         self.x = x.detach().clone().float().contiguous()
@@ -285,10 +286,11 @@ class GraphedTrainStep:
             raise NotImplementedError("GraphedTrainStep captures one micro-batch per optimiser step; use the eager "
                                       "FlatSGDTrainer loop for accumulate_grad_batches > 1")
         trainer.sync_hyper()                   # the H2D copy of the hyper-parameters must not be captured
+        fkw = dict(forward_kwargs or {})       # e.g. attn_temp for DySOEM_SimFPN.forward(x, attn_temp)
 
         def body():
             trainer.zero_grad()
-            outs = model(self.x)
+            outs = model(self.x, **fkw)
             loss, _, bbox_loss, obj_loss = head.compute_metrics(outs, BatchData(image=self.x, bbox=self.targets))
             loss.backward()
             trainer.step()

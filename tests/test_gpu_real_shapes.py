@@ -83,11 +83,15 @@ def test_detect_rtm_640_decode_and_nms_bit_exact(lib, floor):
     model = model.to(DEV)
     b = 1 if floor == float("-inf") else 2
     x = synth_input(b, 640).to(DEV)
-    det = inference.detect_rtm(model, x, 0.5, floor)
-    ops.check_device()
-    assert det.boxes.shape == (b, 96000, 4) and det.scores.shape == (b, 96000)
+    # one forward, then the post-processing half of `detect_rtm` on exactly those outputs (two forwards differ in the
+    # last bf16 bit: the attention pooling accumulates with fp32 atomics)
     with torch.no_grad():
         outs = model(x)
+    det = inference.postprocess_rtm(outs, 0.5, floor)
+    ops.check_device()
+    assert det.boxes.shape == (b, 96000, 4) and det.scores.shape == (b, 96000)
+    want_all = inference.detect_rtm(model, x, 0.5, floor)          # the public entry point: same shapes, same semantics
+    assert want_all.boxes.shape == det.boxes.shape and (want_all.boxes - det.boxes).abs().max() < 0.5
     cx = torch.cat([o.bbox.reshape(b, -1, 4) for o in outs], dim=1).cpu()
     sc = torch.cat([o.obj.reshape(b, -1) for o in outs], dim=1).cpu()
     assert torch.equal(det.boxes.cpu(), O.cxcywh_to_xyxy(cx))
@@ -105,7 +109,10 @@ def test_detect_rtm_640_decode_and_nms_bit_exact(lib, floor):
 
 def test_graphed_detect_rtm_equals_eager(lib):
     """`inference.GraphedDetect` on RTMUAVDet (forward + sigmoid/decode + batched NMS replayed from one CUDA graph)
-    returns exactly what the eager `detect_rtm` returns, on fresh inputs copied into its static buffer."""
+    follows the eager `detect_rtm` on fresh inputs copied into its static buffer: candidates agree to bf16 noise (two
+    forwards are not bit-identical — the attention pooling accumulates with fp32 atomics) and the kept indices are
+    bit-identical to the oracle NMS on the graph's OWN candidates."""
+    from oracle import oracle as O
     from multimodal_uav_det_b200 import inference, ops
     model, _ = _rtm()
     model = model.to(DEV)
@@ -114,10 +121,12 @@ def test_graphed_detect_rtm_equals_eager(lib):
     for x in xs:
         want = inference.detect_rtm(model, x, 0.5, 0.5)
         got = run(x)
-        assert torch.equal(got.keep_count, want.keep_count)
-        for b, c in enumerate(want.keep_count.tolist()):
-            assert torch.equal(got.keep[b, :c], want.keep[b, :c])
-        assert torch.equal(got.boxes, want.boxes) and torch.equal(got.scores, want.scores)
+        assert got.boxes.shape == want.boxes.shape == (2, 96000, 4)
+        assert rel_l2(got.boxes.cpu(), want.boxes.cpu()) < 5e-3 and rel_l2(got.scores.cpu(), want.scores.cpu()) < 5e-3
+        for i, kept in enumerate(inference.kept_lists(got)):
+            boxes, scores = got.boxes[i].cpu().numpy(), got.scores[i].cpu().numpy()
+            idx = np.nonzero(scores > 0.5)[0]
+            assert np.array_equal(kept.cpu().numpy(), idx[O.nms(boxes[idx], scores[idx], 0.5)])
     ops.check_device()
 
 
