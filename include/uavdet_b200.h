@@ -51,8 +51,9 @@ uint64_t uavdet_launch_count(void);
 int uavdet_check_device(void* stream, int* flag_host);
 /* Data-parallel training (new work, SURVEY.md D6 / §8e — the reference has no collective call site): reserve `margin`
  * SMs for the NCCL all-reduce kernels that overlap backward; the persistent tensor-core kernels launched from now on
- * fill (148 - margin) SMs.  Returns the previous margin.  Process-wide; 0 = use every SM. */
-int uavdet_set_sm_margin(int margin);
+ * fill (148 - margin) SMs — for the next `launches` of them (the time a bucket's all-reduce is in flight), or until
+ * reset when launches < 0.  Returns the previous margin.  Process-wide; margin 0 = use every SM. */
+int uavdet_set_sm_margin(int margin, int launches);
 
 /* Measurement aid: a one-thread kernel writes the device's %globaltimer (ns) to *slot_dev in stream order.
  * Captured into a CUDA graph around a kernel it gives that kernel's duration inside the replayed step

@@ -42,7 +42,7 @@ SIGNATURES = {
     "uavdet_version": (_i, []),
     "uavdet_launch_count": (C.c_uint64, []),
     "uavdet_check_device": (_i, [_P, C.POINTER(_i)]),
-    "uavdet_set_sm_margin": (_i, [_i]),
+    "uavdet_set_sm_margin": (_i, [_i, _i]),
     "uavdet_timestamp": (_i, [_P, _P]),
     "uavdet_nms_workspace_bytes": (_sz, [_i, _i]),
     "uavdet_nms": (_i, [_P, _P, _i, _i, _d, _f, _P, _P, _P, _sz, _P]),

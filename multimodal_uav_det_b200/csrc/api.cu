@@ -25,8 +25,14 @@ unsigned int* watchdog_word() {
 }
 
 static std::atomic<int> g_sm_margin{0};
+static std::atomic<int> g_sm_margin_launches{-1};    // < 0: until reset; >= 0: persistent-kernel launches it still covers
 int sm_budget() {
-  const int b = kNumSMs - g_sm_margin.load(std::memory_order_relaxed);
+  const int m = g_sm_margin.load(std::memory_order_relaxed);
+  if (m == 0) return kNumSMs;
+  const int left = g_sm_margin_launches.load(std::memory_order_relaxed);
+  if (left == 0) return kNumSMs;
+  if (left > 0) g_sm_margin_launches.fetch_sub(1, std::memory_order_relaxed);
+  const int b = kNumSMs - m;
   return b < 1 ? 1 : b;
 }
 
@@ -46,9 +52,10 @@ extern "C" int uavdet_timestamp(unsigned long long* slot_dev, void* stream) {
   return UAVDET_OK;   // not counted in uavdet_launch_count: a measurement aid, not part of the path
 }
 
-extern "C" int uavdet_set_sm_margin(int margin) {
+extern "C" int uavdet_set_sm_margin(int margin, int launches) {
   if (margin < 0) margin = 0;
   if (margin > uavdet::kNumSMs - 1) margin = uavdet::kNumSMs - 1;
+  uavdet::g_sm_margin_launches.store(launches < 0 ? -1 : launches);
   return uavdet::g_sm_margin.exchange(margin);
 }
 

@@ -66,9 +66,10 @@ def launch_count() -> int:
     return int(_lib.load().uavdet_launch_count())
 
 
-def set_sm_margin(margin: int) -> int:
-    """Reserve `margin` SMs for collectives that overlap the tensor-core kernels; returns the previous margin."""
-    return int(_lib.load().uavdet_set_sm_margin(int(margin)))
+def set_sm_margin(margin: int, launches: int = -1) -> int:
+    """Reserve `margin` SMs for collectives that overlap the tensor-core kernels, for the next `launches` persistent
+    kernel launches (< 0: until reset); returns the previous margin."""
+    return int(_lib.load().uavdet_set_sm_margin(int(margin), int(launches)))
 
 
 def check_device() -> None:

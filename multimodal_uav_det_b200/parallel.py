@@ -106,6 +106,8 @@ class FlatSGDTrainer:
         if sm_margin is None:
             sm_margin = int(os.environ.get("UAVDET_DP_SM_MARGIN", "8"))
         self.sm_margin = sm_margin if (self.world > 1 and device.type == "cuda") else 0
+        # ... for this many conv-kernel launches after a bucket's all-reduce was enqueued (< 0: all of backward)
+        self.sm_margin_hold = int(os.environ.get("UAVDET_DP_SM_MARGIN_HOLD", "8"))
         self._margin_on = False
         bump_param_epoch()
         self._execs = [m._exec for m in model.modules() if hasattr(m, "_exec") and hasattr(m, "_forward_program")]
@@ -187,8 +189,9 @@ class FlatSGDTrainer:
 
     def _launch_reduce(self, b: _Bucket):
         if self._comm_stream is not None:
-            if self.sm_margin and not self._margin_on:
-                ops.set_sm_margin(self.sm_margin)
+            if self.sm_margin:
+                # the persistent conv kernels launched while this bucket is on the wire leave SMs to the collective
+                ops.set_sm_margin(self.sm_margin, self.sm_margin_hold)
                 self._margin_on = True
             # gradients of the bucket were written on the caller's stream and on the executors' weight-gradient
             # side streams: the collective waits for all of them
