@@ -296,6 +296,16 @@ int uavdet_attn_mlp_softmax(const float* pooled, int n, int c, const float* w1, 
 int uavdet_dyn_aggregate(const float* attn, int n, int K, const float* bank, int O, int I, int k,
                          int transposed, void* out_bf16, const float* bias_bank, float* bias_out,
                          void* stream);
+/* transposed == 2: the cin <= 3 stem sites (DyYOLO's 3 -> 32 k3, _base.py:36-39) that run as im2col + 1x1 GEMM:
+ * out bf16 [n][O][32] = OIHW-flattened aggregated kernels (I*k*k <= 32 columns) zero-padded to the 32 patch channels. */
+/* Backward of uavdet_attn_mlp_softmax (autograd of _base.py:41-46,60-62 / DySOEM_SimFPN.py:46-52,78-79):
+ * g = a*(d_attn - <a,d_attn>)/T; dh = (g @ w2)*[hidden>0]; dW2 += g^T hidden; db2 += sum g; dW1 += dh^T pooled;
+ * db1 += sum dh (NULL: no first-layer bias); d_pooled = out_scale * dh @ w1 (NULL: not needed).  The parameter
+ * gradients ACCUMULATE (they are `param.grad` buffers).  workspace: n*(K+hid) floats.                          */
+int uavdet_attn_mlp_bwd(const float* attn, const float* d_attn, const float* hidden, const float* pooled, int n,
+                        int c, const float* w1, int hid, const float* w2, int K, float temperature,
+                        float out_scale, float* workspace, float* dw1, float* db1, float* dw2, float* db2,
+                        float* d_pooled, void* stream);
 
 /* Backward of the aggregation: from the per-sample kernel gradients dwb [n][O*I*k*k] fp32
  * (packed != 0: the [O][k*k][I] layout uavdet_conv_wgrad(per_sample=1) writes, I may be 4*c for s2d;

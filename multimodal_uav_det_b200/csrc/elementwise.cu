@@ -669,6 +669,23 @@ __global__ void dyn_aggregate_kernel(const float* __restrict__ attn, int n, int 
     out[idx] = __float2bfloat16(acc);
   }
 }
+// cin <= 3 stem sites that run as im2col + 1x1 GEMM: out[b][o][32] = sum_k attn[b][k] * bank[k][o][j] for the
+// j < I*kk taps of the OIHW-flattened kernel (the im2col channel order), zero for the padding columns.
+__global__ void dyn_aggregate_stem_kernel(const float* __restrict__ attn, int n, int K, const float* __restrict__ bank,
+                                          int O, int taps, __nv_bfloat16* __restrict__ out) {
+  const long long total = (long long)n * O * 32;
+  const long long per = (long long)O * taps;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx & 31);
+    const long long bo = idx >> 5;
+    const int o = (int)(bo % O), b = (int)(bo / O);
+    float acc = 0.f;
+    if (j < taps)
+      for (int k = 0; k < K; ++k) acc += __ldg(attn + b * K + k) * __ldg(bank + (long long)k * per + (long long)o * taps + j);
+    out[idx] = __float2bfloat16(acc);
+  }
+}
 __global__ void dyn_bias_kernel(const float* __restrict__ attn, int n, int K, const float* __restrict__ bias_bank,
                                 int O, float* __restrict__ bias_out) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -849,6 +866,75 @@ __global__ void attn_mlp_softmax_kernel(const float* __restrict__ pooled, int c,
     float den = 0.f;
     for (int k = 0; k < K; ++k) { float e = expf(slog[k] - mx); slog[k] = e; den += e; }
     for (int k = 0; k < K; ++k) attn[(long long)b * K + k] = slog[k] / den;
+  }
+}
+
+// ---- backward of the attention MLP + softmax(./T) ------------------------------------------------------------------
+// step 1, one block per sample: g = a * (d_a - <a, d_a>) / T (softmax backward), dh = (g @ w2) * [hidden > 0]
+__global__ void attn_bwd_dh_kernel(const float* __restrict__ attn, const float* __restrict__ d_attn,
+                                   const float* __restrict__ hidden, const float* __restrict__ w2, int hid, int K,
+                                   float inv_t, float* __restrict__ g_out, float* __restrict__ dh_out) {
+  __shared__ float sg[32];
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    float dot = 0.f;
+    for (int k = 0; k < K; ++k) dot += attn[b * K + k] * d_attn[b * K + k];
+    for (int k = 0; k < K; ++k) {
+      const float g = attn[b * K + k] * (d_attn[b * K + k] - dot) * inv_t;
+      sg[k] = g;
+      g_out[b * K + k] = g;
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < hid; j += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) s += sg[k] * __ldg(w2 + (long long)k * hid + j);
+    dh_out[(long long)b * hid + j] = hidden[(long long)b * hid + j] > 0.f ? s : 0.f;
+  }
+}
+// step 2: dW1[j][c] += sum_b dh[b][j] pooled[b][c];  d_pooled[b][c] = out_scale * sum_j dh[b][j] w1[j][c];
+//         block 0 also: dW2[k][j] += sum_b g[b][k] hidden[b][j], db2[k] += sum_b g[b][k], db1[j] += sum_b dh[b][j]
+__global__ void attn_bwd_params_kernel(const float* __restrict__ g, const float* __restrict__ dh,
+                                       const float* __restrict__ hidden, const float* __restrict__ pooled,
+                                       const float* __restrict__ w1, int n, int c, int hid, int K, float out_scale,
+                                       float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw2,
+                                       float* __restrict__ db2, float* __restrict__ d_pooled) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (dw1) {
+    for (long long e = t0; e < (long long)hid * c; e += stride) {
+      const int j = (int)(e / c), cc = (int)(e - (long long)j * c);
+      float acc = 0.f;
+      for (int b = 0; b < n; ++b) acc += __ldg(dh + (long long)b * hid + j) * __ldg(pooled + (long long)b * c + cc);
+      dw1[e] += acc;
+    }
+  }
+  if (d_pooled) {
+    for (long long e = t0; e < (long long)n * c; e += stride) {
+      const int b = (int)(e / c), cc = (int)(e - (long long)b * c);
+      float acc = 0.f;
+      for (int j = 0; j < hid; ++j) acc += __ldg(dh + (long long)b * hid + j) * __ldg(w1 + (long long)j * c + cc);
+      d_pooled[e] = acc * out_scale;
+    }
+  }
+  if (blockIdx.x == 0) {
+    for (int e = threadIdx.x; e < K * hid; e += blockDim.x) {
+      const int k = e / hid, j = e - k * hid;
+      float acc = 0.f;
+      for (int b = 0; b < n; ++b) acc += g[b * K + k] * hidden[(long long)b * hid + j];
+      if (dw2) dw2[e] += acc;
+    }
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      float acc = 0.f;
+      for (int b = 0; b < n; ++b) acc += g[b * K + k];
+      if (db2) db2[k] += acc;
+    }
+    if (db1)
+      for (int j = threadIdx.x; j < hid; j += blockDim.x) {
+        float acc = 0.f;
+        for (int b = 0; b < n; ++b) acc += dh[(long long)b * hid + j];
+        db1[j] += acc;
+      }
   }
 }
 
@@ -1131,6 +1217,13 @@ extern "C" int uavdet_dyn_aggregate(const float* attn, int n, int K, const float
                                     int transposed, void* out_bf16, const float* bias_bank, float* bias_out,
                                     void* stream) {
   UAVDET_CHECK_ARG(attn && bank && out_bf16 && n > 0 && K > 0, "dyn_aggregate: bad arguments");
+  if (transposed == 2) {      // stem layout: OIHW-flat rows zero-padded to the 32 im2col channels
+    UAVDET_CHECK_ARG(I * k * k <= 32, "dyn_aggregate: the stem layout holds at most 32 taps");
+    dyn_aggregate_stem_kernel<<<ew_grid((long long)n * O * 32, 256), 256, 0, ST>>>(attn, n, K, bank, O, I * k * k,
+                                                                                   (__nv_bfloat16*)out_bf16);
+    UAVDET_LAUNCH_CHECK();
+    return UAVDET_OK;
+  }
   long long total = (long long)n * O * I * k * k;
   dyn_aggregate_kernel<<<ew_grid(total, 256), 256, 0, ST>>>(attn, n, K, bank, O, I, k * k, transposed,
                                                             (__nv_bfloat16*)out_bf16);
@@ -1188,6 +1281,24 @@ extern "C" int uavdet_attn_mlp_softmax(const float* pooled, int n, int c, const 
   size_t sh = sizeof(float) * (size_t)(c + hid + K);
   UAVDET_CHECK_ARG(sh <= 48 * 1024, "attn_mlp_softmax: c+hid+K too large");
   attn_mlp_softmax_kernel<<<n, 256, sh, ST>>>(pooled, c, w1, b1, hid, w2, b2, K, 1.f / temperature, attn, hidden);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_attn_mlp_bwd(const float* attn, const float* d_attn, const float* hidden, const float* pooled, int n,
+                                   int c, const float* w1, int hid, const float* w2, int K, float temperature,
+                                   float out_scale, float* workspace, float* dw1, float* db1, float* dw2, float* db2,
+                                   float* d_pooled, void* stream) {
+  UAVDET_CHECK_ARG(attn && d_attn && hidden && pooled && w1 && w2 && workspace && n > 0 && c > 0 && hid > 0 && K > 0 &&
+                       K <= 32 && temperature != 0.f,
+                   "attn_mlp_bwd: bad arguments (K <= 32)");
+  float* g = workspace;
+  float* dh = workspace + (size_t)n * K;
+  attn_bwd_dh_kernel<<<n, 128, 0, ST>>>(attn, d_attn, hidden, w2, hid, K, 1.f / temperature, g, dh);
+  UAVDET_LAUNCH_CHECK();
+  const long long work = (long long)(hid > n ? hid : n) * c;
+  attn_bwd_params_kernel<<<ew_grid(work, 256), 256, 0, ST>>>(g, dh, hidden, pooled, w1, n, c, hid, K, out_scale, dw1, db1,
+                                                            dw2, db2, d_pooled);
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }

@@ -51,6 +51,32 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& P, int tile)
   return t;
 }
 
+// Tile of the `it`-th iteration of this CTA's persistent loop, or -1 when the loop is over.
+//   one CTA per tile:  tile = blockIdx.x + it * gridDim.x
+//   CTA pair (kTwo):   the pair works on two consecutive pixel tiles (2*mp + rank) of the same channel block n, so
+//                      that both CTAs share one B tile (each loads half); both leave the loop in the same iteration.
+//                      With an odd number of pixel tiles the last pair's second tile lies past the last image: its
+//                      loads are zero-filled and its stores clipped by TMA.
+template <bool kTwo>
+__device__ __forceinline__ int tile_at(const IgemmParams& P, int it, uint32_t rank) {
+  if (!kTwo) {
+    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+    return tile < P.total_tiles ? tile : -1;
+  }
+  const int pt = (int)(blockIdx.x >> 1) + it * (int)(gridDim.x >> 1);
+  if (pt >= P.total_pairs) return -1;
+  const int mp = fast_div(pt, P.fd_n);
+  const int n = pt - mp * P.n_tiles;
+  return (2 * mp + (int)rank) * P.n_tiles + n;
+}
+template <bool kTwo>
+__device__ __forceinline__ int num_iters(const IgemmParams& P) {
+  const int first = kTwo ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int step = kTwo ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int total = kTwo ? P.total_pairs : P.total_tiles;
+  return total > first ? (total - first + step - 1) / step : 0;
+}
+
 // 32 accumulator columns of this lane's row -> (scale, shift, act, residual), in place.
 template <int ACT>
 __device__ __forceinline__ void affine_act(float (&v)[32], const float* scale, int cg, const float* shift,
@@ -156,7 +182,7 @@ __device__ __forceinline__ void finish_chunk(uint32_t cfg, const float* scale, c
 }
 
 
-template <int kKind>
+template <int kKind, bool kTwo>
 __device__ __noinline__ void stage_chunk(uint32_t cfg, const float* scale, uint32_t taddr, int cg, bool valid,
                                             const float* shift, const __nv_bfloat16* res_px, uint8_t* srow,
                                             int chunk_in_slab, int sw_mask, bool release, uint32_t tempty, int lane) {
@@ -164,21 +190,22 @@ __device__ __noinline__ void stage_chunk(uint32_t cfg, const float* scale, uint3
   tmem_ld_32x32(taddr, r);
   tmem_ld_wait();
   if (release) {
-    // last TMEM read of this tile by this warp: hand the accumulator buffer back to the MMA warp
+    // last TMEM read of this tile by this warp: hand the accumulator buffer back to the MMA warp (of the leader CTA:
+    // `tempty` is then a shared::cluster address)
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(tempty);
+    if (lane == 0) { if (kTwo) mbar_arrive_cluster(tempty); else mbar_arrive(tempty); }
   }
   finish_chunk<kKind>(cfg, scale, r, cg, valid, shift, res_px, srow, chunk_in_slab, sw_mask);
 }
 
 // MMA issue loop of one CTA (single elected thread), KSTEPS = block_k / 16.
-template <int KSTEPS>
+template <int KSTEPS, bool kTwo>
 __device__ __forceinline__ void mma_issue_loop(const IgemmParams& P, uint32_t ring_base, uint32_t bres_base,
                                                uint32_t full_bar, uint32_t empty_bar, uint32_t tfull_bar,
                                                uint32_t tempty_bar, uint32_t tmem_base, int a_bytes, int b_bytes,
                                                int stage_bytes, int num_kb, volatile uint32_t* dead) {
-  const uint32_t idesc = make_idesc_bf16(P.block_n, 0, 0);
+  const uint32_t idesc = make_idesc_bf16(P.block_n, 0, 0, kTwo ? 256 : 128);
   const uint32_t layout = (KSTEPS == 4) ? 2u : 4u;            // SWIZZLE_128B : SWIZZLE_64B
   const uint32_t sbo = 8u * (uint32_t)(KSTEPS * 16) * 2u;     // 8 rows of one swizzle atom
   const bool bres = P.bres_bytes > 0;
@@ -190,7 +217,8 @@ __device__ __forceinline__ void mma_issue_loop(const IgemmParams& P, uint32_t ri
   const uint32_t last_stage = (uint32_t)P.stages - 1u;
   uint32_t stage = 0, phase = 0, soff = 0;
   uint32_t acc = 0, acc_phase = 0;
-  for (int tile = blockIdx.x, tl = 0; tile < P.total_tiles; tile += gridDim.x, ++tl) {
+  const int iters = num_iters<kTwo>(P);
+  for (int tl = 0; tl < iters; ++tl) {
     const bool tr = P.trace && blockIdx.x == 0 && tl < P.trace_tiles;
     if (tr) P.trace[tl * 16 + 2] = clock64();
     mbar_wait(tempty_bar + 8u * acc, acc_phase ^ 1u, dead, P.watchdog, 0x2u);
@@ -204,13 +232,15 @@ __device__ __forceinline__ void mma_issue_loop(const IgemmParams& P, uint32_t ri
 #pragma unroll
       for (int k = 0; k < KSTEPS; ++k) {
         // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the >>4 field
-        tc_mma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, accumulate);
+        if (kTwo) tc_mma_bf16_2sm(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, accumulate);
+        else tc_mma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, accumulate);
         accumulate = 1u;
       }
-      tc_commit(empty_bar + 8u * stage);
+      // the stage is free again in BOTH CTAs of a pair (the MMA read both shared memories)
+      if (kTwo) tc_commit_2sm(empty_bar + 8u * stage, 3); else tc_commit(empty_bar + 8u * stage);
       if (stage == last_stage) { stage = 0; phase ^= 1u; soff = 0; } else { ++stage; soff += stage_step; }
     }
-    tc_commit(tfull_bar + 8u * acc);
+    if (kTwo) tc_commit_2sm(tfull_bar + 8u * acc, 3); else tc_commit(tfull_bar + 8u * acc);
     if (tr) P.trace[tl * 16 + 4] = clock64();
     acc ^= 1u;
     if (acc == 0) acc_phase ^= 1u;
@@ -220,7 +250,11 @@ __device__ __forceinline__ void mma_issue_loop(const IgemmParams& P, uint32_t ri
 // kKind selects the epilogue the instance is compiled with: 0 = batch statistics (training forward), 1 = affine
 // without activation (data gradients), 2 = affine with any activation (fused inference epilogues), 3 = detection
 // head.  One kernel holding all of them was 160 KB of code, and the step time follows the kernel's code size.
-template <int kKind>
+// kTwo: the CTA-pair variant (cluster of two CTAs on one TPC, tcgen05.mma.cta_group::2): a 256-pixel x block_n tile per
+// pair, every CTA stages its own 128 pixel rows of A and HALF of the weight tile, so the shared-memory traffic per MMA
+// (what bounds the one-CTA kernel on the K >= 1152 layers: operand reads + TMA fill = 96 KB per 512-cycle k-block
+// against 128 B/clk) drops by a third.  The epilogue is unchanged: every CTA drains its own 128 accumulator rows.
+template <int kKind, bool kTwo>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
              const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapOutTail,
@@ -232,8 +266,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  const uint32_t rank = kTwo ? cluster_ctarank() : 0u;
   const int a_bytes = 128 * P.block_k * 2;             // smem reserved for A per stage
-  const int b_bytes = P.block_n * P.block_k * 2;
+  const int b_bytes = (kTwo ? P.block_n / 2 : P.block_n) * P.block_k * 2;   // this CTA's part of the B tile
   // Weights small enough to stay in shared memory for the whole kernel (thin layers, 1x1 convs up to 256->128) are
   // loaded once: [resident B: one tile per k-block][stages x A]; otherwise every stage carries its B tile.
   const bool bres = P.bres_bytes > 0;
@@ -261,10 +296,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     mbar_init(smem_u32(bres_bar), 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);
-      // arrivals per tile: all 8 epilogue warps, or only the 4 that own the accumulator buffer when a tile is a
-      // single slab (warp-private modes: the two warps of a lane quarter then take alternate TILES)
+      // arrivals per tile: all 8 epilogue warps (of both CTAs of a pair, on the leader's barrier), or only the 4
+      // that own the accumulator buffer when a tile is a single slab (warp-private modes: the two warps of a lane
+      // quarter then take alternate TILES)
       mbar_init(smem_u32(&tempty_bar[a]),
-                (kKind != 3 && P.epi_mode != 0 && P.block_n == P.slab_w) ? kEpiWarps / 2 : kEpiWarps);
+                kTwo ? 2 * kEpiWarps : (kKind != 3 && P.epi_mode != 0 && P.block_n == P.slab_w) ? kEpiWarps / 2 : kEpiWarps);
     }
     *dead = 0;
     fence_barrier_init();
@@ -274,11 +310,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     if (P.res_tma) prefetch_tensormap(&mapRes);
   }
   if (warp == kMmaWarp) {
-    tmem_alloc(smem_u32(tmem_ptr), 512);
-    tmem_relinquish();
+    if (kTwo) { tmem_alloc_2sm(smem_u32(tmem_ptr), 512); tmem_relinquish_2sm(); }
+    else { tmem_alloc(smem_u32(tmem_ptr), 512); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  // a pair must see each other's initialised barriers before the first remote arrive / TMA completion
+  if (kTwo) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -292,11 +329,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     if (warp < P.prod_warps && elect_one()) {
       const int pw = P.prod_warps;
       const int kcpt = P.kc_per_tap;
-      int tile = blockIdx.x;
+      int it = 0, tile = tile_at<kTwo>(P, 0, rank);
       int kb = warp;                      // k-block inside the tile (may run past num_kb: normalised below)
       uint32_t stage = (uint32_t)warp, phase = 0;
       int cur_tile = -1;
       TileCoord tc{0, 0, 0, 0};
+      // CTA pair: every transaction byte of both CTAs is counted on the leader's full barrier
+      const uint32_t full0 = kTwo ? mapa_shared(smem_u32(&full_bar[0]), 0) : smem_u32(&full_bar[0]);
       if (bres && warp == 0) {
         // resident weights: every (tap, channel chunk) tile once (n_tiles == 1, one weight matrix for all images)
         const uint32_t bb = smem_u32(bres_bar);
@@ -306,20 +345,28 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             tma_load_3d(smem_u32(smem + (size_t)kbi * b_bytes), &mapB, bb, P.taps[t].w_koff + kc * P.block_k, 0, 0);
       }
       while (true) {
-        while (kb >= num_kb) { kb -= num_kb; tile += gridDim.x; }
-        if (tile >= P.total_tiles) break;
+        while (kb >= num_kb) { kb -= num_kb; tile = tile_at<kTwo>(P, ++it, rank); if (tile < 0) break; }
+        if (tile < 0) break;
         if (tile != cur_tile) { tc = decode_tile(P, tile); cur_tile = tile; }
         const int t = kcpt == 1 ? kb : kb / kcpt;
         const int kc = kb - t * kcpt;
         const ConvTap tap = P.taps[t];
         mbar_wait<32>(smem_u32(&empty_bar[stage]), phase ^ 1u, dead, P.watchdog, 0x1u);
-        const uint32_t fb = smem_u32(&full_bar[stage]);
-        mbar_arrive_expect_tx(fb, (uint32_t)(bres ? a_tx : a_tx + b_bytes));
+        const uint32_t fb = full0 + 8u * stage;
         uint8_t* sa = ring + (size_t)stage * stage_bytes;
-        tma_load_5d(smem_u32(sa), &mapA, fb, tap.c_off + kc * P.block_k, tc.ow0 + tap.dw, tap.p, tc.oh0 + tap.dh,
-                    tc.img);
-        if (!bres)
-          tma_load_3d(smem_u32(sa + a_bytes), &mapB, fb, tap.w_koff + kc * P.block_k, tc.n0, P.w_batch > 1 ? tc.img : 0);
+        if (kTwo) {
+          if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[stage]), (uint32_t)(2 * (a_tx + b_bytes)));
+          tma_load_5d_2sm(smem_u32(sa), &mapA, fb, tap.c_off + kc * P.block_k, tc.ow0 + tap.dw, tap.p, tc.oh0 + tap.dh,
+                          tc.img);
+          tma_load_3d_2sm(smem_u32(sa + a_bytes), &mapB, fb, tap.w_koff + kc * P.block_k,
+                          tc.n0 + (int)rank * (P.block_n / 2), 0);
+        } else {
+          mbar_arrive_expect_tx(fb, (uint32_t)(bres ? a_tx : a_tx + b_bytes));
+          tma_load_5d(smem_u32(sa), &mapA, fb, tap.c_off + kc * P.block_k, tc.ow0 + tap.dw, tap.p, tc.oh0 + tap.dh,
+                      tc.img);
+          if (!bres)
+            tma_load_3d(smem_u32(sa + a_bytes), &mapB, fb, tap.w_koff + kc * P.block_k, tc.n0, P.w_batch > 1 ? tc.img : 0);
+        }
         kb += pw;
         stage += (uint32_t)pw;
         if (stage >= (uint32_t)P.stages) { stage -= (uint32_t)P.stages; phase ^= 1u; }
@@ -331,16 +378,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     // instruction path must be minimal: descriptors are built once (stage 0) and advanced by adding the stage /
     // K-step offset in their (address >> 4) field, barrier addresses advance incrementally, the K-step loop is
     // unrolled at compile time.
-    if (elect_one()) {
+    if (rank == 0 && elect_one()) {      // a pair's MMAs are issued by its leader CTA only
       if (bres) {
         mbar_wait(smem_u32(bres_bar), 0, dead, P.watchdog, 0x80u);      // resident weights have landed
         tc_fence_after();
       }
-      if (P.block_k == 64) mma_issue_loop<4>(P, smem_u32(ring), smem_u32(smem), smem_u32(full_bar), smem_u32(empty_bar),
-                                             smem_u32(tfull_bar), smem_u32(tempty_bar), tmem_base, a_bytes, b_bytes,
-                                             stage_bytes, num_kb, dead);
-      else mma_issue_loop<2>(P, smem_u32(ring), smem_u32(smem), smem_u32(full_bar), smem_u32(empty_bar), smem_u32(tfull_bar),
-                             smem_u32(tempty_bar), tmem_base, a_bytes, b_bytes, stage_bytes, num_kb, dead);
+      if (P.block_k == 64) mma_issue_loop<4, kTwo>(P, smem_u32(ring), smem_u32(smem), smem_u32(full_bar), smem_u32(empty_bar),
+                                                   smem_u32(tfull_bar), smem_u32(tempty_bar), tmem_base, a_bytes, b_bytes,
+                                                   stage_bytes, num_kb, dead);
+      else mma_issue_loop<2, kTwo>(P, smem_u32(ring), smem_u32(smem), smem_u32(full_bar), smem_u32(empty_bar),
+                                   smem_u32(tfull_bar), smem_u32(tempty_bar), tmem_base, a_bytes, b_bytes, stage_bytes,
+                                   num_kb, dead);
     }
   } else {
     // ============================ epilogue (8 warps) =======================
@@ -360,7 +408,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     uint32_t acc_phase = 0;
 
     if (kKind == 3) {
-      for (int tile = blockIdx.x, tl = 0; tile < P.total_tiles; tile += gridDim.x, ++tl) {
+      for (int tl = 0, tile; (tile = tile_at<kTwo>(P, tl, rank)) >= 0; ++tl) {
         const TileCoord tc = decode_tile(P, tile);
         const int oh = tc.oh0 + hl, ow = tc.ow0 + wl;
         const bool valid = (row < kp) && (oh < P.ho) && (ow < P.wo);
@@ -470,11 +518,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       // single-slab tiles: this warp owns accumulator buffer `half` and visits every second tile
       const int tstep = single ? 2 : 1;
       if (single) acc = half;
-      for (int tile = blockIdx.x + (single ? half * (int)gridDim.x : 0), tl = single ? half : 0; tile < P.total_tiles;
-           tile += tstep * (int)gridDim.x, tl += tstep) {
+      for (int tl = single ? half : 0, tile; (tile = tile_at<kTwo>(P, tl, rank)) >= 0; tl += tstep) {
         const TileCoord tc = decode_tile(P, tile);
         const int oh = tc.oh0 + hl, ow = tc.ow0 + wl;
-        const bool valid = (row < kp) && (oh < P.ho) && (ow < P.wo);
+        const bool valid = (row < kp) && (oh < P.ho) && (ow < P.wo) && (tc.img < P.n_img);
         const bool tr = P.trace && blockIdx.x == 0 && tl < P.trace_tiles && (ew & 3) == 0 && lane == 0;
         if (kKind == 0 && tc.n0 != cur_n0) {
           if (cur_n0 >= 0) flush_stats(cur_n0);
@@ -492,7 +539,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         if (tr) P.trace[tl * 16 + 6] = clock64();
         tc_fence_after();
         const uint32_t tbase = tmem_base + (uint32_t)(acc * kAccStride) + ((uint32_t)(q * 32) << 16);
-        const uint32_t tempty = smem_u32(&tempty_bar[acc]);
+        const uint32_t tempty = kTwo ? mapa_shared(smem_u32(&tempty_bar[acc]), 0) : smem_u32(&tempty_bar[acc]);
         {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -512,14 +559,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
               uint8_t* srow = wbuf + lane * row_bytes;
               const int c0 = sl * P.slab_w;                          // accumulator column of the slab
               if (P.slab_w == 64) {
-                stage_chunk<(kKind == 3 ? 1 : kKind)>(ccfg, P.scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, srow, 0, sw_mask, false,
+                stage_chunk<(kKind == 3 ? 1 : kKind), kTwo>(ccfg, P.scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, srow, 0, sw_mask, false,
                             tempty, lane);
                 // the residual tile of this warp's next slab of the tile starts travelling now (other buffer)
                 if (P.res_tma && P.epi_bufs == 2 && !last) wbuf_next = acquire(tc, cs + 2 * P.slab_w, true);
-                stage_chunk<(kKind == 3 ? 1 : kKind)>(ccfg, P.scale, tbase + (uint32_t)(c0 + 32), tc.n0 + c0 + 32, valid, shift, res_px, srow, 1, sw_mask,
+                stage_chunk<(kKind == 3 ? 1 : kKind), kTwo>(ccfg, P.scale, tbase + (uint32_t)(c0 + 32), tc.n0 + c0 + 32, valid, shift, res_px, srow, 1, sw_mask,
                             last, tempty, lane);
               } else {
-                stage_chunk<(kKind == 3 ? 1 : kKind)>(ccfg, P.scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, srow, 0, sw_mask, last, tempty,
+                stage_chunk<(kKind == 3 ? 1 : kKind), kTwo>(ccfg, P.scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, srow, 0, sw_mask, last, tempty,
                             lane);
               }
               if (tr) P.trace[tl * 16 + 10] = clock64();
@@ -580,10 +627,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       const int slab_bytes = 128 * row_bytes;
       const int chunks_per_slab = P.slab_w / 32;              // 2 (slab 64) or 1 (slab 32)
       uint32_t slab_counter = 0;
-      for (int tile = blockIdx.x, tl = 0; tile < P.total_tiles; tile += gridDim.x, ++tl) {
+      for (int tl = 0, tile; (tile = tile_at<kTwo>(P, tl, rank)) >= 0; ++tl) {
         const TileCoord tc = decode_tile(P, tile);
         const int oh = tc.oh0 + hl, ow = tc.ow0 + wl;
-        const bool valid = (row < kp) && (oh < P.ho) && (ow < P.wo);
+        const bool valid = (row < kp) && (oh < P.ho) && (ow < P.wo) && (tc.img < P.n_img);
         const bool tr = P.trace && blockIdx.x == 0 && tl < P.trace_tiles && ew == 0 && lane == 0;
         const __nv_bfloat16* res_px =
             P.res ? P.res + (size_t)tc.img * P.res_sn + (size_t)oh * P.res_sh + (size_t)ow * P.res_sw : nullptr;
@@ -593,7 +640,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         if (tr) P.trace[tl * 16 + 6] = clock64();
         tc_fence_after();
         const uint32_t tbase = tmem_base + (uint32_t)(acc * kAccStride) + ((uint32_t)(q * 32) << 16);
-        const uint32_t tempty = smem_u32(&tempty_bar[acc]);
+        const uint32_t tempty = kTwo ? mapa_shared(smem_u32(&tempty_bar[acc]), 0) : smem_u32(&tempty_bar[acc]);
         for (int sl = 0; sl < n_slabs; ++sl, ++slab_counter) {
           const int cs = tc.n0 + sl * P.slab_w;
           uint8_t* sbuf = staging + (slab_counter & 1u) * slab_bytes;
@@ -602,13 +649,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           const bool last = sl == n_slabs - 1;
           if (half < chunks_per_slab) {
             const int c0 = sl * P.slab_w + half * 32;
-            stage_chunk<(kKind == 3 ? 1 : kKind)>(ccfg, P.scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, sbuf + row * row_bytes, half,
+            stage_chunk<(kKind == 3 ? 1 : kKind), kTwo>(ccfg, P.scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, sbuf + row * row_bytes, half,
                         sw_mask, last, tempty, lane);
             fence_proxy_async();
           } else if (last) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty);
+            if (lane == 0) { if (kTwo) mbar_arrive_cluster(tempty); else mbar_arrive(tempty); }
           }
           asm volatile("bar.sync 3, 256;" ::: "memory");
           if (e_tid == 0) {
@@ -652,10 +699,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   }
 
   tc_fence_before();
-  __syncthreads();
+  // a pair leaves together: the leader's MMAs read the peer's shared memory and both signal each other's barriers
+  if (kTwo) cluster_sync_all(); else __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (kTwo) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -823,6 +871,17 @@ static bool res_tma_enabled() {
   return v != 0;
 }
 
+// UAVDET_IGEMM_2CTA: 0 = never use the CTA-pair kernel, 1 (default) = where it applies, 2 = wherever it is legal
+static int two_cta_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UAVDET_IGEMM_2CTA");
+    v = e ? atoi(e) : 1;
+    if (v < 0 || v > 2) v = 1;
+  }
+  return v;
+}
+
 static int pick_block_n(int cout) {
   if (cout <= 16) return 16;
   for (int bn = 256; bn >= 32; bn -= 32)
@@ -887,26 +946,34 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
     if (rc) return rc;
     mapOutTail = mapOut;
   }
-  {
-    uint64_t dims[3] = {(uint64_t)k_total, (uint64_t)w_rows, (uint64_t)w_batch};
-    uint64_t str[2] = {(uint64_t)k_total * 2, (uint64_t)k_total * 2 * w_batch_rows};
-    uint32_t box[3] = {(uint32_t)P.block_k, (uint32_t)P.block_n, 1u};
-    rc = encode_tensor_map(&mapB, const_cast<void*>(w_packed), 3, dims, str, box, P.block_k * 2);
-    if (rc) return rc;
-  }
   P.tiles_w = ceil_div(P.wo, P.tile_w);
   P.tiles_h = ceil_div(P.ho, P.tile_h);
   P.n_tiles = ceil_div(P.cout, P.block_n);
-  P.total_tiles = P.n_img * P.tiles_h * P.tiles_w * P.n_tiles;
+  const int m_tiles = P.n_img * P.tiles_h * P.tiles_w;
+  P.total_tiles = m_tiles * P.n_tiles;
+  P.total_pairs = ceil_div(m_tiles, 2) * P.n_tiles;
+  // CTA-pair kernel (cta_group::2): one weight matrix for all images, a B tile whose halves are legal MMA widths, and
+  // enough K per tile for the main loop (not the epilogue) to be what is being sped up
+  const int k_blocks = P.num_taps * P.kc_per_tap;
+  bool two = two_cta_mode() != 0 && P.epi != UAVDET_EPI_HEAD && w_batch == 1 && P.block_n % 32 == 0 && P.block_n >= 64 &&
+             P.cout % P.block_n == 0 && m_tiles >= 2 && !(P.epi_mode != 0 && P.block_n == P.slab_w);
+  if (two && two_cta_mode() == 1) two = P.block_n >= 128 && k_blocks >= 9;
+  {
+    uint64_t dims[3] = {(uint64_t)k_total, (uint64_t)w_rows, (uint64_t)w_batch};
+    uint64_t str[2] = {(uint64_t)k_total * 2, (uint64_t)k_total * 2 * w_batch_rows};
+    uint32_t box[3] = {(uint32_t)P.block_k, (uint32_t)(two ? P.block_n / 2 : P.block_n), 1u};
+    rc = encode_tensor_map(&mapB, const_cast<void*>(w_packed), 3, dims, str, box, P.block_k * 2);
+    if (rc) return rc;
+  }
   P.fd_n = make_fast_div(P.n_tiles);
   P.fd_w = make_fast_div(P.tiles_w);
   P.fd_h = make_fast_div(P.tiles_h);
   P.w_batch = w_batch;
   // shared memory: [resident weights] [stages x (A [+ B])] [output staging] [barriers]
-  const int a_stage = 128 * P.block_k * 2, b_tile = P.block_n * P.block_k * 2;
+  const int a_stage = 128 * P.block_k * 2, b_tile = (two ? P.block_n / 2 : P.block_n) * P.block_k * 2;
   const long long b_total = (long long)P.num_taps * P.kc_per_tap * b_tile;
   P.bres_bytes = 0;
-  if (w_batch == 1 && P.n_tiles == 1 && b_total <= 80 * 1024 && P.total_tiles > 2 * kNumSMs) P.bres_bytes = (int)b_total;
+  if (!two && w_batch == 1 && P.n_tiles == 1 && b_total <= 80 * 1024 && P.total_tiles > 2 * kNumSMs) P.bres_bytes = (int)b_total;
   const int stage_bytes = P.bres_bytes ? a_stage : a_stage + b_tile;
   const int ctrl_bytes = 8 * (2 * kMaxStages + 5) + 64 + 8 * 2 * kEpiWarps;   // + the residual-load barriers
   const int max_smem = 227 * 1024;
@@ -933,21 +1000,44 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
   if (P.total_tiles <= 0) return UAVDET_OK;
   const int sms = sm_budget();
   int grid = P.total_tiles < sms ? P.total_tiles : sms;
+  if (two) {
+    const int pairs = sms / 2;           // a CTA pair occupies the two SMs of one TPC
+    grid = 2 * (P.total_pairs < pairs ? P.total_pairs : pairs);
+  }
   if (!P.res_tma) { mapRes = mapOut; mapResTail = mapOutTail; }
   const int kind = (P.epi == UAVDET_EPI_HEAD) ? 3 : (P.epi == UAVDET_EPI_STATS) ? 0 : (P.act == UAVDET_ACT_NONE ? 1 : 2);
-  static PerDeviceOnce attr_once[4];   // the dynamic-shared-memory opt-in is per device
-#define UAVDET_LAUNCH_IGEMM(K)                                                                                         \
+  static PerDeviceOnce attr_once[4][2];   // the dynamic-shared-memory opt-in is per device
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kIgemmThreads);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute cattr[1];
+  cattr[0].id = cudaLaunchAttributeClusterDimension;
+  cattr[0].val.clusterDim.x = 2; cattr[0].val.clusterDim.y = 1; cattr[0].val.clusterDim.z = 1;
+  cfg.attrs = cattr;
+  cfg.numAttrs = two ? 1 : 0;
+#define UAVDET_LAUNCH_IGEMM(K, T)                                                                                      \
   do {                                                                                                                 \
-    UAVDET_CUDA(attr_once[K].run([] {                                                                                  \
-      return cudaFuncSetAttribute(igemm_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);           \
+    UAVDET_CUDA(attr_once[K][T].run([] {                                                                               \
+      return cudaFuncSetAttribute(igemm_kernel<K, (T) != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
     }));                                                                                                               \
-    igemm_kernel<K><<<grid, kIgemmThreads, smem_bytes, st>>>(mapA, mapB, mapOut, mapOutTail, mapRes, mapResTail, P);  \
+    UAVDET_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<K, (T) != 0>, mapA, mapB, mapOut, mapOutTail, mapRes, mapResTail, \
+                                   P));                                                                                \
   } while (0)
-  switch (kind) {
-    case 0: UAVDET_LAUNCH_IGEMM(0); break;
-    case 1: UAVDET_LAUNCH_IGEMM(1); break;
-    case 2: UAVDET_LAUNCH_IGEMM(2); break;
-    default: UAVDET_LAUNCH_IGEMM(3); break;
+  if (two) {
+    switch (kind) {
+      case 0: UAVDET_LAUNCH_IGEMM(0, 1); break;
+      case 1: UAVDET_LAUNCH_IGEMM(1, 1); break;
+      default: UAVDET_LAUNCH_IGEMM(2, 1); break;
+    }
+  } else {
+    switch (kind) {
+      case 0: UAVDET_LAUNCH_IGEMM(0, 0); break;
+      case 1: UAVDET_LAUNCH_IGEMM(1, 0); break;
+      case 2: UAVDET_LAUNCH_IGEMM(2, 0); break;
+      default: UAVDET_LAUNCH_IGEMM(3, 0); break;
+    }
   }
 #undef UAVDET_LAUNCH_IGEMM
   UAVDET_LAUNCH_CHECK();

@@ -39,6 +39,7 @@ struct IgemmParams {
   int cout, block_n, n_tiles;
   int num_taps, kc_per_tap, block_k;
   int w_batch, stages, total_tiles;
+  int total_pairs;      // CTA-pair kernel: (pairs of consecutive pixel tiles) x channel blocks
   int slab_w;           // columns per TMA-store slab of the bf16 epilogues (64 | 32)
   int epi_mode;         // 0 = CTA-wide slab, 1 = per-warp rectangle (5-D map), 2 = per-warp pixel run (flat 3-D map)
   int epi_bufs;         // staging buffers per epilogue warp (modes 1/2)

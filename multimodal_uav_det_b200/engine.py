@@ -492,16 +492,16 @@ class Executor:
         bn, k, s, p, co = sp.bn, sp.k, sp.stride, sp.pad, sp.cout
         direct_stem = sp.stem
         if sp.stem:
-            w_b = torch.mm(attn, bank.flatten(1))                                  # (n, O*cin*k*k) fp32 per-sample kernels
             bias_b = None
             if self.stem_as_gemm(sp.cin, co, k):
-                # im2col + batched 1x1 implicit GEMM: per-sample [O][32] bf16 kernels (taps zero-padded to 32)
+                # im2col + batched 1x1 implicit GEMM: per-sample [O][32] bf16 kernels (taps zero-padded to 32),
+                # mixed from the expert bank by the aggregation kernel
                 x = ops.stem_im2col(x, k, s, p)
-                kk = sp.cin * k * k
-                w_b = torch.nn.functional.pad(w_b.view(n, co, kk), (0, 32 - kk)).to(torch.bfloat16).contiguous()
+                w_b = ops.dyn_aggregate_stem(attn, bank)
                 k, s, p, direct_stem = 1, 1, 0, False
             else:
-                w_b = w_b.view(n, *bank.shape[1:])
+                # direct CUDA-core stem (no shipped configuration takes this branch): fp32 per-sample kernels
+                w_b = torch.mm(attn, bank.flatten(1)).view(n, *bank.shape[1:])
         else:
             w_b, bias_b = ops.dyn_aggregate(attn, bank, bias_bank=bias_bank)
         if train:
@@ -574,38 +574,60 @@ class Executor:
             dwb = ops.stem_wgrad(rec.x, d_raw, sp.k, sp.stride, sp.pad, per_sample=True)
         else:
             dwb = ops.conv_wgrad(rec.x, d_raw, sp.k, sp.stride, sp.pad, s2d=sp.s2d, per_sample=True)
-        d_attn = torch.zeros_like(rec.attn)
-        d_bank = torch.zeros_like(rec.bank)
+        d_attn = self.zeros(n, rec.attn.shape[1], dy.device)
+        bank_params = sp.bank_params()
+        # one parameter holds the whole bank (DyConvModule.weights): its gradient buffer IS d_bank
+        whole = (len(bank_params) == 1 and bank_params[0][1] is None and not bank_params[0][2]
+                 and bank_params[0][0].requires_grad)
+        if whole:
+            d_bank, _ = grad_buffer(bank_params[0][0])
+            whole = d_bank.is_contiguous() and d_bank.dtype == torch.float32 and d_bank.shape == rec.bank.shape
+        if not whole:
+            d_bank = torch.zeros_like(rec.bank)
         ops.dyn_bwd_contract(dwb.view(n, -1), rec.attn, rec.bank, d_bank, d_attn, packed=not sp.stem)
         d_bias_bank = None
         if rec.bias_bank is not None:
             dsum = ops.gap(d_raw) * float(d_raw.shape[1] * d_raw.shape[2])         # (n, O) per-sample channel sums
             d_bias_bank = rec.attn.t() @ dsum
             d_attn = d_attn + dsum @ rec.bias_bank.t()
-        for p, idx, is_bias in sp.bank_params():
-            src = d_bias_bank if is_bias else d_bank
-            self._accumulate(p, src if idx is None else src[idx])
-        # attention MLP backward (softmax(s/T), Linear/conv1x1, ReLU, Linear/conv1x1)
+        if whole:
+            if self.grad_ready_hook is not None:
+                self.grad_ready_hook(bank_params[0][0])
+        else:
+            for p, idx, is_bias in bank_params:
+                src = d_bias_bank if is_bias else d_bank
+                self._accumulate(p, src if idx is None else src[idx])
+        # attention MLP backward (softmax(s/T), Linear/conv1x1, ReLU, Linear/conv1x1): two launches that add the
+        # parameter gradients straight into their `.grad` buffers and return the pooled-input gradient, already
+        # divided by the pool size
         a = rec.attn
-        g = a * (d_attn - (a * d_attn).sum(dim=1, keepdim=True)) / float(sp.temperature)
         w1 = sp.w1.detach().flatten(1)
         w2 = sp.w2.detach().flatten(1)
-        self._accumulate(sp.w2, g.t() @ rec.hidden)
-        self._accumulate(sp.b2, g.sum(dim=0))
-        dh = (g @ w2) * (rec.hidden > 0).to(g.dtype)
-        self._accumulate(sp.w1, dh.t() @ rec.pooled)
-        if sp.b1 is not None:
-            self._accumulate(sp.b1, dh.sum(dim=0))
-        if not need_dx or sp.stem:
-            return None
-        d_pooled = dh @ w1                                                            # (n, C) or (n, 4C)
         h, w = rec.in_hw
+        want_dx = need_dx and not sp.stem
+        mlp_params = [sp.w1, sp.b1, sp.w2, sp.b2]
+        bufs = []
+        for p in mlp_params:
+            if p is None or not p.requires_grad:
+                bufs.append(None)
+                continue
+            gb, _ = grad_buffer(p)
+            if not (gb.is_contiguous() and gb.dtype == torch.float32):
+                raise RuntimeError("attention-MLP gradient buffers must be contiguous float32")
+            bufs.append(gb)
+        d_pooled = ops.attn_mlp_bwd(a, d_attn.contiguous(), rec.hidden, rec.pooled, w1, w2, float(sp.temperature),
+                                    (4.0 if sp.s2d else 1.0) / (h * w), bufs[0], bufs[1], bufs[2], bufs[3],
+                                    want_d_pooled=want_dx)
+        if self.grad_ready_hook is not None:
+            for p, gb in zip(mlp_params, bufs):
+                if gb is not None:
+                    self.grad_ready_hook(p)
+        if not want_dx:
+            return None
         wt, _ = ops.dyn_aggregate(a, rec.bank, transposed=True)
         if sp.s2d:
-            shift = (d_pooled * (4.0 / (h * w))).contiguous()
-            return ops.conv_dgrad_s2d(d_raw, wt, sp.cin, sp.k, sp.pad, w_batch=n, res=res, shift=shift)
-        shift = (d_pooled * (1.0 / (h * w))).contiguous()
-        return ops.conv_dgrad(d_raw, wt, sp.cin, sp.k, sp.stride, sp.pad, rec.in_hw, w_batch=n, res=res, shift=shift,
+            return ops.conv_dgrad_s2d(d_raw, wt, sp.cin, sp.k, sp.pad, w_batch=n, res=res, shift=d_pooled)
+        return ops.conv_dgrad(d_raw, wt, sp.cin, sp.k, sp.stride, sp.pad, rec.in_hw, w_batch=n, res=res, shift=d_pooled,
                               shift_per_sample=True)
 
     @staticmethod

@@ -626,6 +626,33 @@ def attn_mlp_softmax(pooled, w1, b1, w2, b2, temperature, want_hidden=False):
     return (attn, hidden) if want_hidden else attn
 
 
+def attn_mlp_bwd(attn, d_attn, hidden, pooled, w1, w2, temperature, out_scale, dw1, db1, dw2, db2, want_d_pooled=True):
+    """Backward of attn_mlp_softmax.  dw1/db1/dw2/db2: fp32 gradient buffers to ACCUMULATE into (db1 may be None).
+    Returns d_pooled (n, c) * out_scale, or None."""
+    n, c = pooled.shape
+    hid, K = w1.shape[0], w2.shape[0]
+    dev = pooled.device
+    ws = torch.empty(n * (K + hid), dtype=torch.float32, device=dev)
+    d_pooled = torch.empty((n, c), dtype=torch.float32, device=dev) if want_d_pooled else None
+    check(_lib.load().uavdet_attn_mlp_bwd(_ptr(_f32(attn)), _ptr(_f32(d_attn)), _ptr(_f32(hidden)), _ptr(_f32(pooled)), n, c,
+                                          _ptr(_f32(w1)), hid, _ptr(_f32(w2)), K, float(temperature), float(out_scale),
+                                          _ptr(ws), _ptr(dw1), _ptr(db1), _ptr(dw2), _ptr(db2), _ptr(d_pooled), _stream()),
+          "attn_mlp_bwd")
+    return d_pooled
+
+
+def dyn_aggregate_stem(attn, bank):
+    """attn (n,K), bank (K,O,I,k,k) with I*k*k <= 32 -> bf16 (n, O, 32): per-sample OIHW-flat kernels zero-padded to the
+    32 im2col channels (the B operand of the stem-as-GEMM path)."""
+    n, kk_ = attn.shape
+    K, o, i, k, _ = bank.shape
+    assert K == kk_ and i * k * k <= 32
+    out = torch.empty((n, o, 32), dtype=torch.bfloat16, device=attn.device)
+    check(_lib.load().uavdet_dyn_aggregate(_ptr(_f32(attn)), n, K, _ptr(_f32(bank.contiguous())), o, i, k, 2, _ptr(out),
+                                           None, None, _stream()), "dyn_aggregate_stem")
+    return out
+
+
 def dyn_aggregate(attn, bank, transposed=False, bias_bank=None):
     """attn (n,K) fp32, bank (K,O,I,k,k) fp32 -> bf16 (n, O, k*k*I) [or (n, I, k*k*O)], bias (n,O)|None."""
     n, kk_ = attn.shape

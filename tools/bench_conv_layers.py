@@ -41,6 +41,7 @@ def timed(fn, iters=10, warm=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--ours-only", action="store_true", help="skip the cuDNN side (A/B runs of this repo's kernels)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.backends.cudnn.benchmark = True
@@ -77,7 +78,8 @@ def main():
             return torch.ops.aten.convolution_backward(dys_t[it[0] % nbuf], xs_t[it[0] % nbuf], w_cl, None, (s, s), (pad, pad),
                                                        (1, 1), False, (0, 0), 1, (False, True, False))[1]
 
-        cud = dict(fwd=timed(t_fwd), dgrad=timed(t_dgrad), wgrad=timed(t_wgrad))
+        cud = dict(fwd=float("nan"), dgrad=float("nan"), wgrad=float("nan")) if args.ours_only else \
+            dict(fwd=timed(t_fwd), dgrad=timed(t_dgrad), wgrad=timed(t_wgrad))
         # ---- ours ----
         wp = ops.pack_weight(w)
         wt = ops.pack_weight(w, transposed=True)
