@@ -298,6 +298,12 @@ int uavdet_dyn_aggregate(const float* attn, int n, int K, const float* bank, int
                          void* stream);
 /* transposed == 2: the cin <= 3 stem sites (DyYOLO's 3 -> 32 k3, _base.py:36-39) that run as im2col + 1x1 GEMM:
  * out bf16 [n][O][32] = OIHW-flattened aggregated kernels (I*k*k <= 32 columns) zero-padded to the 32 patch channels. */
+/* Gradients of the detection-head outputs (the `(B,A,H,W,1)` / `(B,A,H,W,4)` fp32 tensors of _base.py:91-94,112-115,
+ * either may be NULL) gathered into the NHWC bf16 operand of the head's backward GEMMs: dyh (n,h,w,32) with channels
+ * [A obj | 4A bbox | zero padding]; the bias gradients (sums over n*h*w) are ACCUMULATED into bias_obj_grad[A] /
+ * bias_bbox_grad[4A] (NULL: skipped).  anchors <= 3.                                                           */
+int uavdet_head_grad_pack(const float* d_obj, const float* d_bbox, int n, int anchors, int h, int w,
+                          const uavdet_act* dyh, float* bias_obj_grad, float* bias_bbox_grad, void* stream);
 /* Backward of uavdet_attn_mlp_softmax (autograd of _base.py:41-46,60-62 / DySOEM_SimFPN.py:46-52,78-79):
  * g = a*(d_attn - <a,d_attn>)/T; dh = (g @ w2)*[hidden>0]; dW2 += g^T hidden; db2 += sum g; dW1 += dh^T pooled;
  * db1 += sum dh (NULL: no first-layer bias); d_pooled = out_scale * dh @ w1 (NULL: not needed).  The parameter

@@ -79,6 +79,7 @@ SIGNATURES = {
     "uavdet_gap": (_i, [_AP, _i, _P, _P]),
     "uavdet_gap_nchw": (_i, [_P, _i, _i, _i, _P, _P]),
     "uavdet_attn_mlp_softmax": (_i, [_P, _i, _i, _P, _P, _i, _P, _P, _i, _f, _P, _P, _P]),
+    "uavdet_head_grad_pack": (_i, [_P, _P, _i, _i, _i, _i, _AP, _P, _P, _P]),
     "uavdet_attn_mlp_bwd": (_i, [_P, _P, _P, _P, _i, _i, _P, _i, _P, _i, _f, _f, _P, _P, _P, _P, _P, _P, _P]),
     "uavdet_dyn_aggregate": (_i, [_P, _i, _i, _P, _i, _i, _i, _i, _P, _P, _P, _P]),
     "uavdet_dyn_bwd_contract": (_i, [_P, _i, _i, _P, _P, _i, _i, _i, _i, _P, _P, _P]),

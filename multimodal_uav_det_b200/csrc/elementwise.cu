@@ -347,7 +347,8 @@ bn_bwd_apply_kernel(View dy, View raw, const float* __restrict__ scale, const fl
 }
 
 // ---- BN backward, phase 2 with the per-channel finalize folded in -------------------------------------------------
-__global__ void __launch_bounds__(256)
+template <int U, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 bn_bwd_apply_fused_kernel(View dy, View raw, const float* __restrict__ scale, const float* __restrict__ shift,
                           const float* __restrict__ sum_dz, const float* __restrict__ sum_dzr,
                           const float* __restrict__ mean, const float* __restrict__ invstd, float inv_count, int act,
@@ -388,15 +389,15 @@ bn_bwd_apply_fused_kernel(View dy, View raw, const float* __restrict__ scale, co
     *reinterpret_cast<uint4*>(dr.p + px * dr.ld + L.c) = pack8(d);
   };
   long long px = L.px0;
-  for (; px + 3 * L.step < dy.npix; px += 4 * L.step) {
-    uint4 a[4], b[4];
+  for (; px + (U - 1) * L.step < dy.npix; px += U * L.step) {
+    uint4 a[U], b[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       a[u] = __ldcs(reinterpret_cast<const uint4*>(dy.p + (px + u * L.step) * dy.ld + L.c));
       b[u] = __ldcs(reinterpret_cast<const uint4*>(raw.p + (px + u * L.step) * raw.ld + L.c));
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) body(a[u], b[u], px + u * L.step);
+    for (int u = 0; u < U; ++u) body(a[u], b[u], px + u * L.step);
   }
   for (; px < dy.npix; px += L.step)
     body(__ldcs(reinterpret_cast<const uint4*>(dy.p + px * dy.ld + L.c)),
@@ -669,6 +670,61 @@ __global__ void dyn_aggregate_kernel(const float* __restrict__ attn, int n, int 
     out[idx] = __float2bfloat16(acc);
   }
 }
+// Tiled form for k*k <= 9: a block stages the K experts of a 16 (cout) x 16 (cin) x k*k tile of the bank in shared
+// memory with coalesced reads — ONCE, not once per sample — and then writes that tile of every sample's aggregated
+// kernel in 32-byte runs of the packed layout (cin fastest, or cout fastest for the transposed pack).  The one-thread-
+// per-output kernel above re-read the bank n times with a 36-byte stride (2 ms per DySOEM step).
+constexpr int kAggT = 16;
+__global__ void __launch_bounds__(256)
+dyn_aggregate_tiled_kernel(const float* __restrict__ attn, int n, int K, const float* __restrict__ bank, int O, int I,
+                           int kk, int transposed, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float agg_sm[];
+  const int row = kAggT * kk + 1;                    // floats per (k, oo) row of the tile, padded against bank conflicts
+  float* tile = agg_sm;                              // [K][16 oo][16 ii][kk] (+1 pad per oo)
+  float* sattn = agg_sm + (size_t)K * kAggT * row;   // [n][K]
+  const int o0 = blockIdx.y * kAggT, i0 = blockIdx.x * kAggT;
+  const long long per = (long long)O * I * kk;
+  for (int idx = threadIdx.x; idx < K * kAggT * kAggT * kk; idx += 256) {
+    const int k = idx / (kAggT * kAggT * kk), r = idx - k * (kAggT * kAggT * kk);
+    const int oo = r / (kAggT * kk), rr = r - oo * (kAggT * kk);
+    const int ii = rr / kk;
+    float v = 0.f;
+    if (o0 + oo < O && i0 + ii < I) v = __ldg(bank + (long long)k * per + ((long long)(o0 + oo) * I + i0) * kk + rr);
+    tile[(k * kAggT + oo) * row + rr] = v;
+  }
+  for (int idx = threadIdx.x; idx < n * K; idx += 256) sattn[idx] = attn[idx];
+  __syncthreads();
+  // this thread's (at most 9) elements of the tile: shared-memory offset and offset inside one sample's output
+  int soff[9];
+  long long doff[9];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) {
+    const int e = threadIdx.x + 256 * j;
+    soff[j] = -1;
+    doff[j] = 0;
+    if (e < kAggT * kAggT * kk) {
+      int oo, ii, t;
+      if (!transposed) { ii = e % kAggT; t = (e / kAggT) % kk; oo = e / (kAggT * kk); }
+      else { oo = e % kAggT; t = (e / kAggT) % kk; ii = e / (kAggT * kk); }
+      if (o0 + oo < O && i0 + ii < I) {
+        soff[j] = oo * row + ii * kk + t;
+        doff[j] = !transposed ? ((long long)(o0 + oo) * kk + t) * I + i0 + ii : ((long long)(i0 + ii) * kk + t) * O + o0 + oo;
+      }
+    }
+  }
+  for (int b = 0; b < n; ++b) {
+    __nv_bfloat16* ob = out + (long long)b * per;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      if (soff[j] >= 0) {
+        float acc = 0.f;
+        for (int k = 0; k < K; ++k) acc += sattn[b * K + k] * tile[k * kAggT * row + soff[j]];
+        ob[doff[j]] = __float2bfloat16(acc);
+      }
+    }
+  }
+}
+
 // cin <= 3 stem sites that run as im2col + 1x1 GEMM: out[b][o][32] = sum_k attn[b][k] * bank[k][o][j] for the
 // j < I*kk taps of the OIHW-flattened kernel (the im2col channel order), zero for the padding columns.
 __global__ void dyn_aggregate_stem_kernel(const float* __restrict__ attn, int n, int K, const float* __restrict__ bank,
@@ -788,14 +844,34 @@ __global__ void gap_kernel(const __nv_bfloat16* __restrict__ x, int ld, int h, i
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     if (g < G && pl < PL) {
-      const int cc = g << 3;
-      for (long long p = (long long)blockIdx.x * PL + pl; p < hw; p += (long long)gridDim.x * PL) {
-        if (s2d) {
-          const int py = (int)(p / w), px = (int)(p - (long long)py * w);
-          if (((py & 1) * 2 + (px & 1)) != q) continue;
+      // pixels of class q, four independent 16-byte loads in flight per thread (the first version kept one load in
+      // flight and walked ALL pixels once per class with a 64-bit divide each: 38 % / 15 % of the HBM rate)
+      const __nv_bfloat16* xb_ = x + (long long)b * hw * ld + (g << 3);
+      const int w2 = w >> 1;
+      const int total = s2d ? (h >> 1) * w2 : (int)hw;
+      const int qy = q >> 1, qx = q & 1;
+      auto pixel = [&](int i) -> long long {
+        if (!s2d) return i;
+        const int yy = i / w2, xx = i - yy * w2;
+        return (long long)(2 * yy + qy) * w + 2 * xx + qx;
+      };
+      int i = blockIdx.x * PL + pl;
+      const int istep = gridDim.x * PL;
+      for (; i + 3 * istep < total; i += 4 * istep) {
+        uint4 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = __ldcs(reinterpret_cast<const uint4*>(xb_ + pixel(i + k * istep) * ld));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float v[8];
+          unpack8(u[k], v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += v[j];
         }
+      }
+      for (; i < total; i += istep) {
         float v[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(x + ((long long)b * hw + p) * ld + cc)), v);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(xb_ + pixel(i) * ld)), v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] += v[j];
       }
@@ -815,10 +891,16 @@ __global__ void gap_kernel(const __nv_bfloat16* __restrict__ x, int ld, int h, i
   }
 }
 __global__ void gap_nchw_kernel(const float* __restrict__ x, int hw, float* __restrict__ out) {
-  // one block per (n, c) plane
+  // blockIdx.x = (n, c) plane, blockIdx.y = slice of the plane (a plane per block left 96 blocks for a 3-channel batch
+  // of 32: 0.7 ms for 157 MB); float4 loads, partial sums combined with one atomic per block (out is zeroed first)
   const float* p = x + (long long)blockIdx.x * hw;
   float s = 0.f;
-  for (int i = threadIdx.x; i < hw; i += blockDim.x) s += p[i];
+  const int hw4 = (hw & 3) == 0 ? hw >> 2 : 0;
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < hw4; i += gridDim.y * blockDim.x) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(p) + i);
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  for (int i = 4 * hw4 + blockIdx.y * blockDim.x + threadIdx.x; i < hw; i += gridDim.y * blockDim.x) s += p[i];
   __shared__ float red[32];
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -826,7 +908,7 @@ __global__ void gap_nchw_kernel(const float* __restrict__ x, int hw, float* __re
   if (threadIdx.x < 32) {
     s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0) out[blockIdx.x] = s / (float)hw;
+    if (threadIdx.x == 0) atomicAdd(out + blockIdx.x, s / (float)hw);
   }
 }
 
@@ -866,6 +948,61 @@ __global__ void attn_mlp_softmax_kernel(const float* __restrict__ pooled, int c,
     float den = 0.f;
     for (int k = 0; k < K; ++k) { float e = expf(slog[k] - mx); slog[k] = e; den += e; }
     for (int k = 0; k < K; ++k) attn[(long long)b * K + k] = slog[k] / den;
+  }
+}
+
+// ---- detection-head gradients -> the A operand of the head's data / weight gradient GEMMs ------------------------------
+// d_obj (n,A,H,W,1), d_bbox (n,A,H,W,4) fp32 (the layouts YOLOHead returns, _base.py:91-94,112-115) -> dyh (n,H,W,32)
+// bf16 with channels [A obj | 4A bbox | zero pad], and the bias gradients sum_p d_obj / d_bbox (fp32, accumulated).
+// One thread per pixel: 5A coalesced fp32 reads, one 64-byte row written.
+__global__ void __launch_bounds__(256)
+head_grad_pack_kernel(const float* __restrict__ d_obj, const float4* __restrict__ d_bbox, int n, int A, long long hw,
+                      __nv_bfloat16* __restrict__ dyh, long long dyh_ld, float* __restrict__ gb_obj,
+                      float* __restrict__ gb_bbox) {
+  __shared__ float red[8][16];
+  const long long total = (long long)n * hw;
+  float bs[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) bs[j] = 0.f;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    const long long img = p / hw, px = p - img * hw;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (a < A) {
+        if (d_obj) v[a] = __ldcs(d_obj + (img * A + a) * hw + px);
+        if (d_bbox) {
+          const float4 t = __ldcs(d_bbox + (img * A + a) * hw + px);
+          v[A + 4 * a + 0] = t.x; v[A + 4 * a + 1] = t.y; v[A + 4 * a + 2] = t.z; v[A + 4 * a + 3] = t.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) bs[j] += v[j];
+    uint4* dst = reinterpret_cast<uint4*>(dyh + p * dyh_ld);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 o;
+      o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]); o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+      o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+      dst[j] = o;
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float s = bs[j];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) red[warp][j] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5 * A) {
+    float s = 0.f;
+    for (int wi = 0; wi < 8; ++wi) s += red[wi][threadIdx.x];
+    if (threadIdx.x < A) { if (gb_obj) atomicAdd(gb_obj + threadIdx.x, s); }
+    else if (gb_bbox) atomicAdd(gb_bbox + (threadIdx.x - A), s);
   }
 }
 
@@ -1013,7 +1150,10 @@ static void prefer_max_smem_carveout_once() {
   once.run([] {
     cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(bn_bwd_apply_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    return cudaFuncSetAttribute(bn_bwd_apply_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(bn_bwd_apply_fused_kernel<4, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(bn_bwd_apply_fused_kernel<4, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(bn_bwd_apply_fused_kernel<2, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return cudaFuncSetAttribute(bn_bwd_apply_fused_kernel<2, 3>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                 cudaSharedmemCarveoutMaxShared);
   });
 }
@@ -1101,9 +1241,20 @@ extern "C" int uavdet_bn_act_bwd_apply_fused(const uavdet_act* dy, const uavdet_
   // pixels per thread: every thread first derives the coefficients of its 8 channels from six per-channel vectors,
   // so very short threads spend more on that prologue than on their data
   static const int ppt = getenv("UAVDET_BN_APPLY_PPT") ? atoi(getenv("UAVDET_BN_APPLY_PPT")) : 4;
-  bn_bwd_apply_fused_kernel<<<stream_grid(dy, ppt), 256, 0, ST>>>(mkview(dy), mkview(raw), scale, shift, sum_dz, sum_dzr,
-                                                               mean, invstd, (float)(1.0 / count), act, dgamma, dbeta,
-                                                               accumulate, mkview(d_raw));
+  // register budget / unroll variants (occupancy against loads in flight per thread): A/B switch
+  static const int variant = getenv("UAVDET_BN_APPLY_VARIANT") ? atoi(getenv("UAVDET_BN_APPLY_VARIANT")) : 3;
+  prefer_max_smem_carveout_once();
+#define UAVDET_BN_APPLY(U, MINB, BPS)                                                                                       \
+  bn_bwd_apply_fused_kernel<U, MINB><<<stream_grid(dy, ppt, BPS), 256, 0, ST>>>(                                            \
+      mkview(dy), mkview(raw), scale, shift, sum_dz, sum_dzr, mean, invstd, (float)(1.0 / count), act, dgamma, dbeta,      \
+      accumulate, mkview(d_raw))
+  switch (variant) {
+    case 1: UAVDET_BN_APPLY(4, 3, 24); break;
+    case 2: UAVDET_BN_APPLY(2, 4, 32); break;
+    case 3: UAVDET_BN_APPLY(2, 3, 24); break;
+    default: UAVDET_BN_APPLY(4, 1, 16); break;
+  }
+#undef UAVDET_BN_APPLY
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }
@@ -1225,8 +1376,15 @@ extern "C" int uavdet_dyn_aggregate(const float* attn, int n, int K, const float
     return UAVDET_OK;
   }
   long long total = (long long)n * O * I * k * k;
-  dyn_aggregate_kernel<<<ew_grid(total, 256), 256, 0, ST>>>(attn, n, K, bank, O, I, k * k, transposed,
-                                                            (__nv_bfloat16*)out_bf16);
+  const size_t agg_smem = sizeof(float) * ((size_t)K * kAggT * (kAggT * k * k + 1) + (size_t)n * K);
+  if (k * k <= 9 && agg_smem <= 48 * 1024) {
+    dim3 grid((unsigned)ceil_div(I, kAggT), (unsigned)ceil_div(O, kAggT));
+    dyn_aggregate_tiled_kernel<<<grid, 256, agg_smem, ST>>>(attn, n, K, bank, O, I, k * k, transposed ? 1 : 0,
+                                                           (__nv_bfloat16*)out_bf16);
+  } else {
+    dyn_aggregate_kernel<<<ew_grid(total, 256), 256, 0, ST>>>(attn, n, K, bank, O, I, k * k, transposed,
+                                                              (__nv_bfloat16*)out_bf16);
+  }
   UAVDET_LAUNCH_CHECK();
   if (bias_bank && bias_out) {
     dyn_bias_kernel<<<ceil_div(n * O, 256), 256, 0, ST>>>(attn, n, K, bias_bank, O, bias_out);
@@ -1258,7 +1416,7 @@ extern "C" int uavdet_gap(const uavdet_act* x, int s2d, float* out, void* stream
   int G = x->c / 8, Gb = G < 32 ? G : 32, PL = 256 / Gb;
   long long hw = (long long)x->h * x->w;
   long long bx = (hw + (long long)PL * 8 - 1) / ((long long)PL * 8);
-  long long cap = (kNumSMs * 4) / (x->n > 0 ? x->n : 1) + 1;
+  long long cap = (kNumSMs * 8) / ((long long)(x->n > 0 ? x->n : 1) * ceil_div(G, Gb)) + 1;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   dim3 grid((unsigned)bx, (unsigned)ceil_div(G, Gb), (unsigned)x->n);
@@ -1269,7 +1427,13 @@ extern "C" int uavdet_gap(const uavdet_act* x, int s2d, float* out, void* stream
 }
 extern "C" int uavdet_gap_nchw(const float* x_nchw, int n, int c, int hw, float* out, void* stream) {
   UAVDET_CHECK_ARG(x_nchw && out && n > 0 && c > 0 && hw > 0, "gap_nchw: bad arguments");
-  gap_nchw_kernel<<<n * c, 256, 0, ST>>>(x_nchw, hw, out);
+  UAVDET_CHECK_ARG(((uintptr_t)x_nchw & 15) == 0, "gap_nchw: input must be 16-byte aligned");
+  UAVDET_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n * c, ST));
+  int slices = (kNumSMs * 8) / (n * c) + 1;
+  const int max_slices = (hw / 4 + 255) / 256;
+  if (slices > max_slices) slices = max_slices;
+  if (slices < 1) slices = 1;
+  gap_nchw_kernel<<<dim3((unsigned)(n * c), (unsigned)slices), 256, 0, ST>>>(x_nchw, hw, out);
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }
@@ -1281,6 +1445,21 @@ extern "C" int uavdet_attn_mlp_softmax(const float* pooled, int n, int c, const 
   size_t sh = sizeof(float) * (size_t)(c + hid + K);
   UAVDET_CHECK_ARG(sh <= 48 * 1024, "attn_mlp_softmax: c+hid+K too large");
   attn_mlp_softmax_kernel<<<n, 256, sh, ST>>>(pooled, c, w1, b1, hid, w2, b2, K, 1.f / temperature, attn, hidden);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_head_grad_pack(const float* d_obj, const float* d_bbox, int n, int anchors, int h, int w,
+                                     const uavdet_act* dyh, float* bias_obj_grad, float* bias_bbox_grad, void* stream) {
+  int rc;
+  if ((rc = check_view(dyh, "head_grad_pack dyh"))) return rc;
+  UAVDET_CHECK_ARG((d_obj || d_bbox) && n > 0 && anchors >= 1 && anchors <= 3 && h > 0 && w > 0,
+                   "head_grad_pack: bad arguments (anchors <= 3)");
+  UAVDET_CHECK_ARG(dyh->n == n && dyh->h == h && dyh->w == w && dyh->c == 32, "head_grad_pack: dyh must be (n,h,w,32)");
+  UAVDET_CHECK_ARG(((uintptr_t)d_bbox & 15) == 0, "head_grad_pack: d_bbox must be 16-byte aligned");
+  const long long hw = (long long)h * w, total = hw * n;
+  head_grad_pack_kernel<<<ew_grid(total, 256), 256, 0, ST>>>(d_obj, (const float4*)d_bbox, n, anchors, hw,
+                                                            (__nv_bfloat16*)dyh->ptr, dyh->ld, bias_obj_grad, bias_bbox_grad);
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }

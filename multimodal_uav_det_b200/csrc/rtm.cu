@@ -207,31 +207,74 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ a, int a_ld, const __nv_bfloat
          bp ? __ldg(reinterpret_cast<const uint4*>(bp + (long long)px * b_ld)) : make_uint4(0u, 0u, 0u, 0u), px);
 }
 
-// nn.Upsample(scale_factor=2, mode='bilinear') (align_corners=False).  blockIdx.z = image, blockIdx.x covers
-// (output row, column block): no divides per element.
+// nn.Upsample(scale_factor=2, mode='bilinear') (align_corners=False).
+// A thread owns 8 channels of a run of kBilinearRun input columns of one input row i and writes the 2 x (2 * run)
+// output pixels that row produces.  The 3 x 3 input neighbourhood rolls along the run in registers, so an input pixel
+// is fetched 3 x (run + 2) / run times per thread instead of 4 times per OUTPUT pixel (the first version was bound by
+// the L2 -> SM traffic of those re-reads: 6.7 GB for 1.6 GB written).  Arithmetic is the textbook expression
+// hy*(hx*v00 + lx*v01) + ly*(hx*v10 + lx*v11) with torch's source-index rule, unchanged.
+constexpr int kBilinearRun = 8;
 __global__ void __launch_bounds__(256)
-bilinear2x_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int h, int w, int c, int xblocks,
+bilinear2x_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int h, int w, int c, int gy,
                   __nv_bfloat16* __restrict__ y, int y_ld) {
-  const Lanes L = lanes_of(c);
-  if (!L.active) return;
-  const int H = 2 * h, W = 2 * w;
+  const int G = c >> 3;
+  const int Gb = G < 32 ? G : 32;
+  const int PL = 256 / Gb;
+  const int i = blockIdx.y / gy;                              // input row
+  const int g = threadIdx.x % Gb + (blockIdx.y - i * gy) * Gb;
+  const int pl = threadIdx.x / Gb;
+  const int j0 = (blockIdx.x * PL + pl) * kBilinearRun;       // first input column of the run
+  if (g >= G || pl >= PL || j0 >= w) return;
   const int b = blockIdx.z;
-  const int oy = blockIdx.x / xblocks, ox = (blockIdx.x % xblocks) * L.PL + L.pl;
-  if (ox >= W || oy >= H) return;
-  const int cc = L.g << 3;
-  const float sy = fmaxf((oy + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((ox + 0.5f) * 0.5f - 0.5f, 0.f);
-  const int y0 = (int)sy, x0 = (int)sx;
-  const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
-  const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
+  const int cc = g << 3;
+  const int W = 2 * w;
   const __nv_bfloat16* xb_ = x + (long long)b * h * w * x_ld + cc;
-  float v00[8], v01[8], v10[8], v11[8], o[8];
-  unpack8r(__ldg(reinterpret_cast<const uint4*>(xb_ + ((long long)y0 * w + x0) * x_ld)), v00);
-  unpack8r(__ldg(reinterpret_cast<const uint4*>(xb_ + ((long long)y0 * w + x1) * x_ld)), v01);
-  unpack8r(__ldg(reinterpret_cast<const uint4*>(xb_ + ((long long)y1 * w + x0) * x_ld)), v10);
-  unpack8r(__ldg(reinterpret_cast<const uint4*>(xb_ + ((long long)y1 * w + x1) * x_ld)), v11);
+  __nv_bfloat16* yb_ = y + (long long)b * (2 * h) * W * y_ld + cc;
+  const int ym = i > 0 ? i - 1 : 0, yp = i < h - 1 ? i + 1 : i;
+  // vertical weights of the two output rows 2i and 2i+1 (torch: src = max((dst + 0.5) / 2 - 0.5, 0))
+  float ly[2], hy[2];
+  int top[2];                                                 // window row holding y0 (0 = row ym, 1 = row i)
 #pragma unroll
-  for (int j = 0; j < 8; ++j) o[j] = hy * (hx * v00[j] + lx * v01[j]) + ly * (hx * v10[j] + lx * v11[j]);
-  *reinterpret_cast<uint4*>(y + (((long long)b * H + oy) * W + ox) * y_ld + cc) = pack8r(o);
+  for (int r = 0; r < 2; ++r) {
+    const float sy = fmaxf((2 * i + r + 0.5f) * 0.5f - 0.5f, 0.f);
+    const int y0 = (int)sy;
+    ly[r] = sy - y0;
+    hy[r] = 1.f - ly[r];
+    top[r] = (r == 0) ? 0 : 1;
+  }
+  float win[3][3][8];                                         // [row ym, i, yp][column j-1, j, j+1][channel]
+  auto load_col = [&](int col, int slot) {
+    const int jc = col < 0 ? 0 : (col > w - 1 ? w - 1 : col);
+    unpack8r(__ldg(reinterpret_cast<const uint4*>(xb_ + ((long long)ym * w + jc) * x_ld)), win[0][slot]);
+    unpack8r(__ldg(reinterpret_cast<const uint4*>(xb_ + ((long long)i * w + jc) * x_ld)), win[1][slot]);
+    unpack8r(__ldg(reinterpret_cast<const uint4*>(xb_ + ((long long)yp * w + jc) * x_ld)), win[2][slot]);
+  };
+  load_col(j0 - 1, 0);
+  load_col(j0, 1);
+  const int j_end = min(w, j0 + kBilinearRun);
+  for (int j = j0; j < j_end; ++j) {
+    load_col(j + 1, 2);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {                              // output column 2j + q
+      const float sx = fmaxf((2 * j + q + 0.5f) * 0.5f - 0.5f, 0.f);
+      const int x0 = (int)sx;
+      const float lx = sx - x0, hx = 1.f - lx;
+      const int left = q == 0 ? 0 : 1;                        // window column holding x0
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          o[e] = hy[r] * (hx * win[top[r]][left][e] + lx * win[top[r]][left + 1][e]) +
+                 ly[r] * (hx * win[top[r] + 1][left][e] + lx * win[top[r] + 1][left + 1][e]);
+        *reinterpret_cast<uint4*>(yb_ + ((long long)(2 * i + r) * W + 2 * j + q) * y_ld) = pack8r(o);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { win[r][0][e] = win[r][1][e]; win[r][1][e] = win[r][2][e]; }
+  }
 }
 
 struct RtmAnchors { float w[8]; float h[8]; };
@@ -334,10 +377,10 @@ extern "C" int uavdet_bilinear2x_fwd(const uavdet_act* x, const uavdet_act* y, v
   int rc;
   if ((rc = chk(x, "bilinear2x x")) || (rc = chk(y, "bilinear2x y"))) return rc;
   UAVDET_CHECK_ARG(y->n == x->n && y->h == 2 * x->h && y->w == 2 * x->w && y->c == x->c, "bilinear2x: shapes");
-  const int G = x->c / 8, Gb = G < 32 ? G : 32, PL = 256 / Gb;
-  const int xblocks = ceil_div(y->w, PL);
-  dim3 grid((unsigned)(xblocks * y->h), (unsigned)ceil_div(G, Gb), (unsigned)y->n);
-  bilinear2x_kernel<<<grid, 256, 0, ST>>>((const __nv_bfloat16*)x->ptr, x->ld, x->h, x->w, x->c, xblocks,
+  const int G = x->c / 8, Gb = G < 32 ? G : 32, PL = 256 / Gb, gy = ceil_div(G, Gb);
+  UAVDET_CHECK_ARG((long long)x->h * gy <= 65535, "bilinear2x: map too tall");
+  dim3 grid((unsigned)ceil_div(ceil_div(x->w, kBilinearRun), PL), (unsigned)(x->h * gy), (unsigned)x->n);
+  bilinear2x_kernel<<<grid, 256, 0, ST>>>((const __nv_bfloat16*)x->ptr, x->ld, x->h, x->w, x->c, gy,
                                           (__nv_bfloat16*)y->ptr, y->ld);
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;

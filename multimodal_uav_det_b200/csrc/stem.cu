@@ -202,6 +202,195 @@ __global__ void __launch_bounds__(kSwThreads) stem_wgrad_kernel(const float* __r
   }
 }
 
+// ---- 1x1 stems (DySOEM_SimFPN.py:14-33: 1- or 3-channel input -> 32 channels) --------------------------------------
+// Pure streaming layers (12 B in, 64 B out per pixel).  Four lanes share a pixel, each owning 8 output channels, so a
+// warp writes (or, for the weight gradient, reads) 512 contiguous bytes per instruction; a thread walks pixels with a
+// grid-stride loop and keeps its statistics / gradient partial sums in registers until the end.  (The generic kernels
+// above — a pixel and all 32 channels per thread, a full warp-wide butterfly of the statistics per pixel; a 32x8 tile
+// with 16 tap slots of which a 1x1 kernel fills 3 — ran this layer at 25 % / 10 % of the HBM rate.)
+template <int CIN>
+__global__ void __launch_bounds__(256) stem1x1_fwd_kernel(StemParams P) {
+  __shared__ float red[2][8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cg = (lane & 3) << 3;                    // first of this thread's 8 output channels
+  float wr[8][CIN], sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) wr[j][ci] = __ldg(P.wgt + (cg + j) * CIN + ci);
+    sc[j] = P.scale ? __ldg(P.scale + cg + j) : 1.f;
+    sh[j] = P.shift ? __ldg(P.shift + cg + j) : 0.f;
+  }
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  const long long hw = (long long)P.h * P.w, total = hw * P.n;
+  const bool stats = P.epi == UAVDET_EPI_STATS;
+  for (long long p = ((long long)blockIdx.x * 256 + threadIdx.x) >> 2; p < total; p += ((long long)gridDim.x * 256) >> 2) {
+    const long long img = p / hw, px = p - img * hw;
+    const float* xin = P.x + img * CIN * hw + px;
+    float xv[CIN];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) xv[ci] = __ldcs(xin + ci * hw);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) a = fmaf(xv[ci], wr[j][ci], a);
+      v[j] = a;
+    }
+    if (stats) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s1[j] += v[j]; s2[j] = fmaf(v[j], v[j], s2[j]); }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = act_fwd_rt(P.act, fmaf(v[j], sc[j], sh[j]));
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(P.y + p * P.y_ld + cg) = o;
+  }
+  if (stats) {
+    // lanes with equal (lane & 3) hold the same channels: fold the 8 pixel lanes, then the 8 warps
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = s1[j], b = s2[j];
+#pragma unroll
+      for (int off = 4; off < 32; off <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off);
+        b += __shfl_xor_sync(0xffffffffu, b, off);
+      }
+      if (lane < 4) { red[0][warp][cg + j] = a; red[1][warp][cg + j] = b; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      const int which = threadIdx.x >> 5, ch = threadIdx.x & 31;
+      float a = 0.f;
+      for (int wi = 0; wi < 8; ++wi) a += red[which][wi][ch];
+      atomicAdd((which ? P.sumsq : P.sum) + ch, a);
+    }
+  }
+}
+
+// dW[co][ci] += sum_p dy[p][co] * x[p][ci] for a 1x1 stem, same thread layout.
+template <int CIN>
+__global__ void __launch_bounds__(256)
+stem1x1_wgrad_kernel(const float* __restrict__ x, int n, long long hw, const __nv_bfloat16* __restrict__ dy,
+                     long long dy_ld, float* __restrict__ grad) {
+  __shared__ float red[8][32][CIN];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cg = (lane & 3) << 3;
+  float acc[8][CIN];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) acc[j][ci] = 0.f;
+  const long long total = hw * n;
+  for (long long p = ((long long)blockIdx.x * 256 + threadIdx.x) >> 2; p < total; p += ((long long)gridDim.x * 256) >> 2) {
+    const long long img = p / hw, px = p - img * hw;
+    const float* xin = x + img * CIN * hw + px;
+    float xv[CIN];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) xv[ci] = __ldcs(xin + ci * hw);
+    const uint4 g = __ldcs(reinterpret_cast<const uint4*>(dy + p * dy_ld + cg));
+    const float gv[8] = {bf16_lo(g.x), bf16_hi(g.x), bf16_lo(g.y), bf16_hi(g.y),
+                         bf16_lo(g.z), bf16_hi(g.z), bf16_lo(g.w), bf16_hi(g.w)};
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) acc[j][ci] = fmaf(gv[j], xv[ci], acc[j][ci]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      float a = acc[j][ci];
+#pragma unroll
+      for (int off = 4; off < 32; off <<= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+      if (lane < 4) red[warp][cg + j][ci] = a;
+    }
+  __syncthreads();
+  if (threadIdx.x < 32 * CIN) {
+    const int ch = threadIdx.x / CIN, ci = threadIdx.x - ch * CIN;
+    float a = 0.f;
+    for (int wi = 0; wi < 8; ++wi) a += red[wi][ch][ci];
+    atomicAdd(grad + ch * CIN + ci, a);
+  }
+}
+
+// ---- 5x5 stride-2 stem (RTMUAVDet.py:28-36: 3 -> 32, pad 1), inference epilogue ---------------------------------------
+// Two horizontally adjacent output pixels per thread: the 7 input columns they need are loaded once per filter row, and
+// every 16-byte read of the filter from shared memory feeds 8 FMAs (the one-pixel kernel above issued one 4-byte shared
+// load per FMA and ran at a quarter of the fp32 rate: 3.5 ms of the 24 ms batch-128 forward).
+__global__ void __launch_bounds__(256) stem5x5s2_fwd_kernel(StemParams P) {
+  __shared__ float4 sw4[75 * 8];          // [tap = (ci*5 + kh)*5 + kw][32 output channels]
+  const int img = blockIdx.y;
+  float* sw = reinterpret_cast<float*>(sw4);
+  for (int i = threadIdx.x; i < 75 * kStemCout; i += blockDim.x) {
+    const int co = i % kStemCout, kk = i / kStemCout;
+    sw[kk * kStemCout + co] = P.wgt[co * 75 + kk];
+  }
+  __syncthreads();
+  const int half_w = P.yw >> 1;
+  const long long pairs = (long long)P.yh * half_w;
+  const long long pp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pp >= pairs) return;
+  const int oy = (int)(pp / half_w), ox = 2 * (int)(pp - (long long)oy * half_w);
+  float acc[2][kStemCout];
+#pragma unroll
+  for (int c = 0; c < kStemCout; ++c) { acc[0][c] = 0.f; acc[1][c] = 0.f; }
+  const float* xin = P.x + (long long)img * 3 * P.h * P.w;
+  if (oy < P.ho) {
+    for (int ci = 0; ci < 3; ++ci)
+      for (int kh = 0; kh < 5; ++kh) {
+        const int iy = 2 * oy + kh - P.pad;
+        if (iy < 0 || iy >= P.h) continue;
+        const float* xrow = xin + ((long long)ci * P.h + iy) * P.w;
+        float col[7];
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+          const int ix = 2 * ox + c - P.pad;
+          col[c] = (ix >= 0 && ix < P.w) ? __ldg(xrow + ix) : 0.f;
+        }
+        const float4* wrow = sw4 + ((ci * 5 + kh) * 5) * 8;
+#pragma unroll
+        for (int kw = 0; kw < 5; ++kw) {
+          const float x0 = col[kw], x1 = col[kw + 2];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 w4 = wrow[kw * 8 + q];
+            acc[0][4 * q + 0] = fmaf(x0, w4.x, acc[0][4 * q + 0]); acc[1][4 * q + 0] = fmaf(x1, w4.x, acc[1][4 * q + 0]);
+            acc[0][4 * q + 1] = fmaf(x0, w4.y, acc[0][4 * q + 1]); acc[1][4 * q + 1] = fmaf(x1, w4.y, acc[1][4 * q + 1]);
+            acc[0][4 * q + 2] = fmaf(x0, w4.z, acc[0][4 * q + 2]); acc[1][4 * q + 2] = fmaf(x1, w4.z, acc[1][4 * q + 2]);
+            acc[0][4 * q + 3] = fmaf(x0, w4.w, acc[0][4 * q + 3]); acc[1][4 * q + 3] = fmaf(x1, w4.w, acc[1][4 * q + 3]);
+          }
+        }
+      }
+  }
+#pragma unroll
+  for (int px = 0; px < 2; ++px) {
+    const bool valid = oy < P.ho && ox + px < P.wo;     // the padded last row / column stays zero
+    __nv_bfloat16* yp = P.y + (((long long)img * P.yh + oy) * P.yw + ox + px) * P.y_ld;
+#pragma unroll
+    for (int c = 0; c < kStemCout; c += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float z = acc[px][c + j];
+        if (P.scale) z *= __ldg(P.scale + c + j);
+        if (P.shift) z += __ldg(P.shift + c + j);
+        v[j] = valid ? act_fwd_rt(P.act, z) : 0.f;
+      }
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(yp + c) = o;
+    }
+  }
+}
+
 // im2col of the cin<=3 network input: y[n][oy][ox][(ci*k + kh)*k + kw] = x[n][ci][oy*s+kh-p][ox*s+kw-p] (zero outside
 // the image and for the pad channels K..31), bf16 NHWC with 32 channels = 64 B per pixel.  With it the stem
 // convolution, its per-sample dynamic variant and their weight gradients run on the same tcgen05 kernels as
@@ -269,8 +458,25 @@ extern "C" int uavdet_stem_fwd(const float* x_nchw, int n, int cin, int h, int w
   if (P.epi == UAVDET_EPI_STATS) UAVDET_CHECK_ARG(P.sum && P.sumsq, "stem_fwd: STATS needs sum/sumsq");
   UAVDET_CHECK_ARG(P.epi != UAVDET_EPI_HEAD, "stem_fwd: HEAD epilogue unsupported");
   UAVDET_CHECK_ARG(!(padded && P.epi == UAVDET_EPI_STATS), "stem_fwd: zero-padded output needs the AFFINE epilogue");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (k == 1 && stride == 1 && pad == 0 && P.w_batch == 1 && !padded && (cin == 1 || cin == 3)) {
+    // streaming 1x1 stem: 4 lanes per pixel, grid-stride
+    long long blocks = ceil_div64((long long)n * h * w * 4, 256 * 8);
+    if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
+    if (blocks < 1) blocks = 1;
+    if (cin == 1) stem1x1_fwd_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(P);
+    else stem1x1_fwd_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(P);
+    UAVDET_LAUNCH_CHECK();
+    return UAVDET_OK;
+  }
+  if (k == 5 && stride == 2 && cin == 3 && P.w_batch == 1 && P.epi == UAVDET_EPI_AFFINE && (P.yw & 1) == 0) {
+    dim3 grid2((unsigned)ceil_div64((long long)P.yh * (P.yw / 2), 256), (unsigned)n);
+    stem5x5s2_fwd_kernel<<<grid2, 256, 0, st>>>(P);
+    UAVDET_LAUNCH_CHECK();
+    return UAVDET_OK;
+  }
   dim3 grid((unsigned)ceil_div64((long long)P.yh * P.yw, 256), (unsigned)n);
-  stem_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+  stem_fwd_kernel<<<grid, 256, 0, st>>>(P);
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }
@@ -285,6 +491,18 @@ extern "C" int uavdet_stem_wgrad(const float* x_nchw, int n, int cin, int h, int
   const int tpg = (K + 15) / 16;
   UAVDET_CHECK_ARG(tpg >= 1 && tpg <= kSwMaxTpg, "stem_wgrad: K=%d unsupported", K);
   UAVDET_CHECK_ARG(dy->ld % 8 == 0 && ((uintptr_t)dy->ptr & 15) == 0, "stem_wgrad: dy alignment");
+  if (k == 1 && stride == 1 && pad == 0 && !per_sample && (cin == 1 || cin == 3) && dy->h == h && dy->w == w) {
+    long long blocks = ceil_div64((long long)n * h * w * 4, 256 * 8);
+    if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
+    if (blocks < 1) blocks = 1;
+    const __nv_bfloat16* dyq = (const __nv_bfloat16*)dy->ptr;
+    if (cin == 1)
+      stem1x1_wgrad_kernel<1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x_nchw, n, (long long)h * w, dyq, dy->ld, grad_oihw);
+    else
+      stem1x1_wgrad_kernel<3><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x_nchw, n, (long long)h * w, dyq, dy->ld, grad_oihw);
+    UAVDET_LAUNCH_CHECK();
+    return UAVDET_OK;
+  }
   const int pw = (kSwTileW - 1) * stride + k, ph = (kSwTileH - 1) * stride + k;
   const size_t smem = sizeof(float) * (size_t)((cin * ph * pw + 3) & ~3) + (size_t)kSwTileW * kSwTileH * 64;
   UAVDET_CHECK_ARG(smem <= 48 * 1024, "stem_wgrad: patch does not fit shared memory");

@@ -205,14 +205,15 @@ class YOLOHead(LightningModule):
         a = self.n_anchors
         n, hh, ww, cin = feat.shape
         dev = feat.device
-        # (B,A,H,W,1|4) fp32 -> NHWC bf16 with 32 channels [A obj | 4A bbox | zero pad]
-        dyh = torch.zeros((n, hh, ww, 32), dtype=torch.bfloat16, device=dev)
-        if d_obj is not None:
-            dyh[..., :a] = d_obj.squeeze(-1).permute(0, 2, 3, 1)
-        if d_bbox is not None:
-            dyh[..., a:5 * a] = d_bbox.permute(0, 2, 3, 1, 4).reshape(n, hh, ww, 4 * a)
         conv_o = self.detection_head[s]["obj"].conv_obj
         conv_b = self.detection_head[s]["bbox"].conv_bbox
+        for conv in (conv_o, conv_b):
+            if conv.bias.grad is None:
+                conv.bias.grad = torch.zeros_like(conv.bias)
+        # (B,A,H,W,1|4) fp32 -> NHWC bf16 with 32 channels [A obj | 4A bbox | zero pad] + both bias gradients: one pass
+        dyh = ops.head_grad_pack(d_obj.contiguous() if d_obj is not None else None,
+                                 d_bbox.contiguous() if d_bbox is not None else None, n, a, hh, ww,
+                                 conv_o.bias.grad, conv_b.bias.grad)
         dwp = ops.conv_wgrad(feat, dyh, 1, 1, 0)              # packed [32][cin]
         for conv, lo, hi in ((conv_o, 0, a), (conv_b, a, 5 * a)):
             g = dwp[lo:hi].view(hi - lo, cin, 1, 1)
@@ -220,12 +221,6 @@ class YOLOHead(LightningModule):
                 conv.weight.grad = g.clone()
             else:
                 conv.weight.grad.add_(g)
-        bias_g = dyh.float().sum(dim=(0, 1, 2))
-        for conv, lo, hi in ((conv_o, 0, a), (conv_b, a, 5 * a)):
-            if conv.bias.grad is None:
-                conv.bias.grad = bias_g[lo:hi].clone()
-            else:
-                conv.bias.grad.add_(bias_g[lo:hi])
         if hook is not None:
             for conv in (conv_o, conv_b):
                 hook(conv.weight)

@@ -626,6 +626,17 @@ def attn_mlp_softmax(pooled, w1, b1, w2, b2, temperature, want_hidden=False):
     return (attn, hidden) if want_hidden else attn
 
 
+def head_grad_pack(d_obj, d_bbox, n, anchors, h, w, bias_obj_grad=None, bias_bbox_grad=None):
+    """(B,A,H,W,1) / (B,A,H,W,4) fp32 head-output gradients -> dyh (n,h,w,32) NHWC bf16 [A obj | 4A bbox | 0]; the bias
+    gradients are accumulated into the given fp32 buffers."""
+    dev = (d_obj if d_obj is not None else d_bbox).device
+    dyh = torch.empty((n, h, w, 32), dtype=torch.bfloat16, device=dev)
+    dv = act_view(dyh)
+    check(_lib.load().uavdet_head_grad_pack(_ptr(_f32(d_obj)), _ptr(_f32(d_bbox)), n, anchors, h, w, C.byref(dv),
+                                            _ptr(bias_obj_grad), _ptr(bias_bbox_grad), _stream()), "head_grad_pack")
+    return dyh
+
+
 def attn_mlp_bwd(attn, d_attn, hidden, pooled, w1, w2, temperature, out_scale, dw1, db1, dw2, db2, want_d_pooled=True):
     """Backward of attn_mlp_softmax.  dw1/db1/dw2/db2: fp32 gradient buffers to ACCUMULATE into (db1 may be None).
     Returns d_pooled (n, c) * out_scale, or None."""
