@@ -208,7 +208,7 @@ __device__ __forceinline__ void mma_issue_loop(const IgemmParams& P, uint32_t ri
   const uint32_t idesc = make_idesc_bf16(P.block_n, 0, 0, kTwo ? 256 : 128);
   const uint32_t layout = (KSTEPS == 4) ? 2u : 4u;            // SWIZZLE_128B : SWIZZLE_64B
   const uint32_t sbo = 8u * (uint32_t)(KSTEPS * 16) * 2u;     // 8 rows of one swizzle atom
-  const bool bres = P.bres_bytes > 0;
+  const bool bres = !kTwo && P.bres_bytes > 0;      // resident weights: one-CTA kernel only
   const uint64_t a0 = make_smem_desc(ring_base, 16, sbo, layout);
   // B: inside the stage (after A), or tile kb of the resident weight region
   const uint64_t b0 = make_smem_desc(bres ? bres_base : ring_base + (uint32_t)a_bytes, 16, sbo, layout);
@@ -271,7 +271,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   const int b_bytes = (kTwo ? P.block_n / 2 : P.block_n) * P.block_k * 2;   // this CTA's part of the B tile
   // Weights small enough to stay in shared memory for the whole kernel (thin layers, 1x1 convs up to 256->128) are
   // loaded once: [resident B: one tile per k-block][stages x A]; otherwise every stage carries its B tile.
-  const bool bres = P.bres_bytes > 0;
+  const bool bres = !kTwo && P.bres_bytes > 0;      // resident weights: one-CTA kernel only
   const int stage_bytes = bres ? a_bytes : a_bytes + b_bytes;
   const int a_tx = P.tile_w * P.tile_h * P.block_k * 2;  // bytes the A box actually delivers
   uint8_t* ring = smem + P.bres_bytes;                   // pipeline stages (1024-aligned: tiles are multiples of 1 KB)

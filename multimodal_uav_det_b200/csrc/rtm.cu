@@ -40,8 +40,11 @@ __device__ __forceinline__ Lanes lanes_of(int c) {
 }
 
 // out[b,y,x,c] = x[b,y,x,c] + channel_w[b,c] * sum_t kernel_w[b,t] * x[b,y+dy,x+dx,c]
-// A thread walks a vertical strip of `rows` output pixels of one column; for k = 3 the 3x3 window lives in
-// registers and rolls down the strip, so each output pixel costs 3 new 16-byte loads instead of 9.
+// A thread walks a vertical strip of `rows` output pixels of one column (8 channels).  Every INPUT row is loaded and
+// converted to fp32 once and scattered into the KS output rows it contributes to: a ring of KS accumulators whose slot
+// indices are compile-time constants because the row loop is unrolled by KS.  (The first version gathered a KS x KS
+// window per output row: KS x more bf16 -> fp32 conversions and a register shuffle of the window per row made it
+// instruction-bound — 18 % of the HBM rate for k = 5, 50 % for k = 3.)
 template <int KS>
 __global__ void __launch_bounds__(256)
 dwdynconv_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int h, int w, int c,
@@ -54,7 +57,8 @@ dwdynconv_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int h, int w, in
   const int ox = xb * L.PL + L.pl;
   if (ox >= w) return;
   const int cc = L.g << 3;
-  const int y0 = strip * rows, y1 = min(h, y0 + rows);
+  const int y0 = strip * rows;
+  const int nrows = min(h, y0 + rows) - y0;          // output rows of this strip
   constexpr int PAD = KS / 2;
   float kw[KS * KS], cw[8];
 #pragma unroll
@@ -63,41 +67,55 @@ dwdynconv_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int h, int w, in
   for (int j = 0; j < 8; ++j) cw[j] = __ldg(channel_w + (long long)b * c + cc + j);
   const __nv_bfloat16* xb_ = x + (long long)b * h * w * x_ld + cc;
   __nv_bfloat16* yb_ = y + (long long)b * h * w * y_ld + cc;
-  auto load_row = [&](int iy, uint4 (&r)[KS]) {
+  float acc[KS][8];
 #pragma unroll
-    for (int kx = 0; kx < KS; ++kx) {
-      const int ix = ox + kx - PAD;
-      r[kx] = (iy >= 0 && iy < h && ix >= 0 && ix < w)
-                  ? __ldg(reinterpret_cast<const uint4*>(xb_ + ((long long)iy * w + ix) * x_ld))
-                  : make_uint4(0u, 0u, 0u, 0u);
-    }
-  };
-  uint4 win[KS][KS];                      // win[r] = input row (oy - PAD + r)
+  for (int s_ = 0; s_ < KS; ++s_)
 #pragma unroll
-  for (int r = 0; r < KS - 1; ++r) load_row(y0 - PAD + r, win[r + 1]);
-  for (int oy = y0; oy < y1; ++oy) {
+    for (int j = 0; j < 8; ++j) acc[s_][j] = 0.f;
+  // local input row li <-> image row y0 - PAD + li; it feeds output rows y0 + li - r (r = filter row), ring slot
+  // (li - r) mod KS; output row y0 + li - (KS - 1) is complete after input row li
+  const int n_in = nrows + KS - 1;
+  for (int base = 0; base < n_in; base += KS) {
 #pragma unroll
-    for (int r = 0; r < KS - 1; ++r)
+    for (int u = 0; u < KS; ++u) {
+      const int li = base + u;
+      if (li < n_in) {
+        const int iy = y0 - PAD + li;
+        if (iy >= 0 && iy < h) {
+          float v[KS][8];
 #pragma unroll
-      for (int kx = 0; kx < KS; ++kx) win[r][kx] = win[r + 1][kx];
-    load_row(oy + PAD, win[KS - 1]);
-    float acc[8], centre[8];
+          for (int kx = 0; kx < KS; ++kx) {
+            const int ix = ox + kx - PAD;
+            const uint4 raw = (ix >= 0 && ix < w) ? __ldg(reinterpret_cast<const uint4*>(xb_ + ((long long)iy * w + ix) * x_ld))
+                                                  : make_uint4(0u, 0u, 0u, 0u);
+            unpack8r(raw, v[kx]);
+          }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+          for (int r = 0; r < KS; ++r) {
+            constexpr int dummy = 0; (void)dummy;
+            const int slot = ((u - r) % KS + KS) % KS;            // compile-time after unrolling
 #pragma unroll
-    for (int r = 0; r < KS; ++r)
+            for (int kx = 0; kx < KS; ++kx) {
+              const float wt = kw[r * KS + kx];
 #pragma unroll
-      for (int kx = 0; kx < KS; ++kx) {
-        float v[8];
-        unpack8r(win[r][kx], v);
-        const float wt = kw[r * KS + kx];
+              for (int j = 0; j < 8; ++j) acc[slot][j] = fmaf(wt, v[kx][j], acc[slot][j]);
+            }
+          }
+        }
+        const int done = li - (KS - 1);                           // local output row finished by this input row
+        const int dslot = (u + 1) % KS;
+        if (done >= 0) {
+          const int oy = y0 + done;
+          float centre[8], o[8];
+          unpack8r(__ldg(reinterpret_cast<const uint4*>(xb_ + ((long long)oy * w + ox) * x_ld)), centre);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(wt, v[j], acc[j]);
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(cw[j], acc[dslot][j], centre[j]);
+          *reinterpret_cast<uint4*>(yb_ + ((long long)oy * w + ox) * y_ld) = pack8r(o);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[dslot][j] = 0.f;          // the slot now belongs to output row done + KS
       }
-    unpack8r(win[PAD][PAD], centre);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = fmaf(cw[j], acc[j], centre[j]);
-    *reinterpret_cast<uint4*>(yb_ + ((long long)oy * w + ox) * y_ld) = pack8r(acc);
+    }
   }
 }
 
@@ -320,8 +338,8 @@ extern "C" int uavdet_dwdynconv_fwd(const uavdet_act* x, const float* channel_w,
   UAVDET_CHECK_ARG(x->n == y->n && x->h == y->h && x->w == y->w && x->c == y->c, "dwdynconv: shape mismatch");
   const int G = x->c / 8, Gb = G < 32 ? G : 32, PL = 256 / Gb;
   const int xblocks = ceil_div(x->w, PL);
-  int rows = 16;
-  while (rows > 4 && (long long)xblocks * ceil_div(x->h, rows) * ceil_div(G, Gb) * x->n < 4 * kNumSMs) rows >>= 1;
+  int rows = 32;
+  while (rows > 4 && (long long)xblocks * ceil_div(x->h, rows) * ceil_div(G, Gb) * x->n < 8 * kNumSMs) rows >>= 1;
   dim3 grid((unsigned)(xblocks * ceil_div(x->h, rows)), (unsigned)ceil_div(G, Gb), (unsigned)x->n);
   const __nv_bfloat16* xp = (const __nv_bfloat16*)x->ptr;
   __nv_bfloat16* yp = (__nv_bfloat16*)y->ptr;
