@@ -101,7 +101,10 @@ class ClockSampler:
 
     def __init__(self, index):
         self.proc = None
-        self.index = index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v.strip() for v in vis.split(",") if v.strip()]
+        # nvidia-smi numbers the physical GPUs: translate the process-local index when the job sees a subset
+        self.index = ids[index] if index < len(ids) else index
 
     def start(self):
         try:

@@ -67,39 +67,67 @@ dwdynconv_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int h, int w, in
   for (int j = 0; j < 8; ++j) cw[j] = __ldg(channel_w + (long long)b * c + cc + j);
   const __nv_bfloat16* xb_ = x + (long long)b * h * w * x_ld + cc;
   __nv_bfloat16* yb_ = y + (long long)b * h * w * y_ld + cc;
+  if (KS == 1) {
+    // 1x1: y = x * (1 + channel_w * kernel_w) — a pure stream, four loads in flight
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaf(cw[j], kw[0], 1.f);
+    for (int r0 = 0; r0 < nrows; r0 += 4) {
+      uint4 raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (r0 + u < nrows) raw[u] = __ldcs(reinterpret_cast<const uint4*>(xb_ + ((long long)(y0 + r0 + u) * w + ox) * x_ld));
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (r0 + u < nrows) {
+          float v[8], o[8];
+          unpack8r(raw[u], v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(fmaf(kw[0], v[j], 0.f), cw[j], v[j]);
+          *reinterpret_cast<uint4*>(yb_ + ((long long)(y0 + r0 + u) * w + ox) * y_ld) = pack8r(o);
+        }
+    }
+    (void)f;
+    return;
+  }
   float acc[KS][8];
 #pragma unroll
   for (int s_ = 0; s_ < KS; ++s_)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[s_][j] = 0.f;
   // local input row li <-> image row y0 - PAD + li; it feeds output rows y0 + li - r (r = filter row), ring slot
-  // (li - r) mod KS; output row y0 + li - (KS - 1) is complete after input row li
+  // (li - r) mod KS; output row y0 + li - (KS - 1) is complete after input row li.  The raw row li + 1 is requested
+  // before row li is consumed, so its latency hides behind the KS*KS*8 FMAs of the current row.
   const int n_in = nrows + KS - 1;
+  auto fetch = [&](int li, uint4 (&raw)[KS]) {
+    const int iy = y0 - PAD + li;
+    const bool row_ok = li < n_in && iy >= 0 && iy < h;
+#pragma unroll
+    for (int kx = 0; kx < KS; ++kx) {
+      const int ix = ox + kx - PAD;
+      raw[kx] = (row_ok && ix >= 0 && ix < w) ? __ldg(reinterpret_cast<const uint4*>(xb_ + ((long long)iy * w + ix) * x_ld))
+                                             : make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  uint4 cur[KS], nxt[KS];
+  fetch(0, cur);
   for (int base = 0; base < n_in; base += KS) {
 #pragma unroll
     for (int u = 0; u < KS; ++u) {
       const int li = base + u;
       if (li < n_in) {
-        const int iy = y0 - PAD + li;
-        if (iy >= 0 && iy < h) {
-          float v[KS][8];
+        fetch(li + 1, nxt);
+        float v[KS][8];
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) unpack8r(cur[kx], v[kx]);
+#pragma unroll
+        for (int r = 0; r < KS; ++r) {
+          const int slot = ((u - r) % KS + KS) % KS;            // compile-time after unrolling
 #pragma unroll
           for (int kx = 0; kx < KS; ++kx) {
-            const int ix = ox + kx - PAD;
-            const uint4 raw = (ix >= 0 && ix < w) ? __ldg(reinterpret_cast<const uint4*>(xb_ + ((long long)iy * w + ix) * x_ld))
-                                                  : make_uint4(0u, 0u, 0u, 0u);
-            unpack8r(raw, v[kx]);
-          }
+            const float wt = kw[r * KS + kx];
 #pragma unroll
-          for (int r = 0; r < KS; ++r) {
-            constexpr int dummy = 0; (void)dummy;
-            const int slot = ((u - r) % KS + KS) % KS;            // compile-time after unrolling
-#pragma unroll
-            for (int kx = 0; kx < KS; ++kx) {
-              const float wt = kw[r * KS + kx];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) acc[slot][j] = fmaf(wt, v[kx][j], acc[slot][j]);
-            }
+            for (int j = 0; j < 8; ++j) acc[slot][j] = fmaf(wt, v[kx][j], acc[slot][j]);
           }
         }
         const int done = li - (KS - 1);                           // local output row finished by this input row
@@ -114,6 +142,8 @@ dwdynconv_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int h, int w, in
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[dslot][j] = 0.f;          // the slot now belongs to output row done + KS
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) cur[kx] = nxt[kx];
       }
     }
   }

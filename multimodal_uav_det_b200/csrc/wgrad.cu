@@ -70,7 +70,7 @@ struct WgIssue {
 };
 
 // MMA issue loop of one CTA, specialised on the number of taps NS (accumulators) it owns.
-template <int NS>
+template <int NS, bool kTwo>
 __device__ __forceinline__ void wgrad_issue(const WgIssue& is, const uint64_t (&bd)[kMaxSlots]) {
   int stage = 0;
   uint32_t phase = 0, soff = 0;
@@ -82,15 +82,22 @@ __device__ __forceinline__ void wgrad_issue(const WgIssue& is, const uint64_t (&
       const uint64_t boff = (uint64_t)(soff + ks * is.b_step);
       const uint32_t accum = (kb | ks) != 0 ? 1u : 0u;
 #pragma unroll
-      for (int i = 0; i < NS; ++i)
-        tc_mma_bf16(is.tmem_base + (uint32_t)i * is.cin_blk, ad, bd[i] + boff, is.idesc, accum);
+      for (int i = 0; i < NS; ++i) {
+        if (kTwo) tc_mma_bf16_2sm(is.tmem_base + (uint32_t)i * is.cin_blk, ad, bd[i] + boff, is.idesc, accum);
+        else tc_mma_bf16(is.tmem_base + (uint32_t)i * is.cin_blk, ad, bd[i] + boff, is.idesc, accum);
+      }
     }
-    tc_commit(is.empty_bar + 8u * (uint32_t)stage);
+    if (kTwo) tc_commit_2sm(is.empty_bar + 8u * (uint32_t)stage, 3); else tc_commit(is.empty_bar + 8u * (uint32_t)stage);
     soff += is.stage_step;
     if (++stage == is.stages) { stage = 0; phase ^= 1u; soff = 0; }
   }
 }
 
+// kTwo: CTA-pair variant (cta_group::2).  The pair owns two adjacent 128-row cout blocks (M = 256) of the same (cin
+// block, tap group, pixel split): each CTA loads its own dY boxes and HALF of the channels of every X box, so the
+// L2 -> SM traffic per MMA — what bounds this kernel on the 20x20 / 40x40 maps (20 KB per 384-cycle tile step, twice
+// what the L2 delivers per SM) — drops by 30 %.  Accumulators, epilogue and atomics stay per CTA.
+template <bool kTwo>
 __global__ void __launch_bounds__(kWgradThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapX0,
              const __grid_constant__ CUtensorMap mapX1, const __grid_constant__ CUtensorMap mapX2,
@@ -99,11 +106,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ---- work decode -----------------------------------------------------------------------
-  int item = blockIdx.x % P.items;
-  const int split = blockIdx.x / P.items;
+  const uint32_t rank = kTwo ? cluster_ctarank() : 0u;
+  const int bid = kTwo ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int items = kTwo ? P.items / 2 : P.items;            // pairs of cout blocks
+  int item = bid % items;
+  const int split = bid / items;
   const int grp = item % P.num_groups; item /= P.num_groups;
   const int cib = item % P.ci_blocks;
-  const int cob = item / P.ci_blocks;
+  const int cob = kTwo ? 2 * (item / P.ci_blocks) + (int)rank : item / P.ci_blocks;
   const int col0 = grp * P.cols_per_group;
   const int ncol = min(P.cols_per_group, P.num_cols - col0);
   const int img_only = P.per_sample ? (int)blockIdx.y : -1;
@@ -114,7 +124,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ 
 
   const int a_row = P.a_width * 2, b_row = P.b_width * 2;        // bytes per smem row
   const int a_blocks = 128 / P.a_width;                          // 64-/32-channel boxes covering M=128
-  const int b_blocks = P.cin_blk / P.b_width;
+  const int cin_here = kTwo ? P.cin_blk / 2 : P.cin_blk;         // channels of every X box this CTA stages
+  const int b_blocks = cin_here / P.b_width;
   const int a_blk_bytes = P.kp_pad * a_row;
   uint8_t* ctrl = smem + (size_t)P.stages * P.stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
@@ -135,8 +146,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ 
     prefetch_tensormap(&mapX0);
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(tmem_ptr), 512);
-    tmem_relinquish();
+    if (kTwo) { tmem_alloc_2sm(smem_u32(tmem_ptr), 512); tmem_relinquish_2sm(); }
+    else { tmem_alloc(smem_u32(tmem_ptr), 512); tmem_relinquish(); }
   }
   // The K padding rows (and the rows past a shared box that its last tap touches) are never written by TMA:
   // zero the pipeline buffers once so they contribute exact zeros.
@@ -147,7 +158,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ 
     fence_proxy_async();
   }
   tc_fence_before();
-  __syncthreads();
+  if (kTwo) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -172,28 +183,34 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ 
       for (int kb = 0; kb < num_kb; ++kb) {
         const int ow0 = tw * P.tile_w, oh0 = th * P.tile_h;
         mbar_wait<32>(smem_u32(&empty_bar[stage]), phase ^ 1u, dead, P.watchdog, 0x10u);
-        const uint32_t fb = smem_u32(&full_bar[stage]);
-        mbar_arrive_expect_tx(fb, (uint32_t)tx_bytes);
+        // CTA pair: all bytes of both CTAs are counted on the leader's barrier, which the leader arms for both
+        const uint32_t fb = kTwo ? mapa_shared(smem_u32(&full_bar[stage]), 0) : smem_u32(&full_bar[stage]);
+        if (!kTwo) mbar_arrive_expect_tx(fb, (uint32_t)tx_bytes);
+        else if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[stage]), (uint32_t)(2 * tx_bytes));
         uint8_t* sa = smem + (size_t)stage * P.stage_bytes;
-        for (int ab = 0; ab < a_live; ++ab)
-          tma_load_5d(smem_u32(sa + ab * a_blk_bytes), &mapDY, fb, co0 + ab * P.a_width, ow0, 0, oh0, img);
+        for (int ab = 0; ab < a_live; ++ab) {
+          if (kTwo) tma_load_5d_2sm(smem_u32(sa + ab * a_blk_bytes), &mapDY, fb, co0 + ab * P.a_width, ow0, 0, oh0, img);
+          else tma_load_5d(smem_u32(sa + ab * a_blk_bytes), &mapDY, fb, co0 + ab * P.a_width, ow0, 0, oh0, img);
+        }
         for (int c = 0; c < ncol; ++c) {
           const WgCol col = P.cols[col0 + c];
           const CUtensorMap* mx = col.map == 0 ? &mapX0 : (col.map == 1 ? &mapX1 : &mapX2);
-          for (int bb = 0; bb < b_blocks; ++bb)
-            tma_load_5d(smem_u32(sa + col.off + bb * col.blk), mx, fb, col.c_off + cib * P.cin_blk + bb * P.b_width,
-                        ow0 + col.dw, col.p, oh0 + col.dh0, img);
+          for (int bb = 0; bb < b_blocks; ++bb) {
+            const int ch = col.c_off + cib * P.cin_blk + (int)rank * cin_here + bb * P.b_width;
+            if (kTwo) tma_load_5d_2sm(smem_u32(sa + col.off + bb * col.blk), mx, fb, ch, ow0 + col.dw, col.p, oh0 + col.dh0, img);
+            else tma_load_5d(smem_u32(sa + col.off + bb * col.blk), mx, fb, ch, ow0 + col.dw, col.p, oh0 + col.dh0, img);
+          }
         }
         if (++tw == P.tiles_w) { tw = 0; if (++th == P.tiles_h) { th = 0; ++img; } }
         if (++stage == P.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) {
+    if (rank == 0 && elect_one()) {      // a pair's MMAs are issued by its leader
       // The single issuing thread must spend < 64 cycles per MMA (M128 x N128 x K16) to keep the tensor pipe
       // busy, so everything that does not change inside the loop is hoisted: one 64-bit descriptor per tap
       // (stage 0, K step 0) lives in registers; stage / K-step offsets are added in the (address >> 4) field.
-      const uint32_t idesc = make_idesc_bf16(P.cin_blk, 1, 1);  // both operands MN-major
+      const uint32_t idesc = make_idesc_bf16(P.cin_blk, 1, 1, kTwo ? 256 : 128);  // both operands MN-major
       const uint32_t a_layout = P.a_width == 64 ? 2u : 4u, b_layout = P.b_width == 64 ? 2u : 4u;
       const int ksteps = P.kp_pad / 16;
       const uint32_t sa0 = smem_u32(smem);
@@ -215,16 +232,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ 
       is.tmem_base = tmem_base; is.cin_blk = (uint32_t)P.cin_blk; is.idesc = idesc;
       is.dead = dead; is.watchdog = P.watchdog;
       switch (nslots) {     // one specialisation per tap count: only live MMAs in the instruction stream
-        case 1: wgrad_issue<1>(is, bd); break;    case 2: wgrad_issue<2>(is, bd); break;
-        case 3: wgrad_issue<3>(is, bd); break;    case 4: wgrad_issue<4>(is, bd); break;
-        case 5: wgrad_issue<5>(is, bd); break;    case 6: wgrad_issue<6>(is, bd); break;
-        case 7: wgrad_issue<7>(is, bd); break;    case 8: wgrad_issue<8>(is, bd); break;
-        case 9: wgrad_issue<9>(is, bd); break;    case 10: wgrad_issue<10>(is, bd); break;
-        case 11: wgrad_issue<11>(is, bd); break;  case 12: wgrad_issue<12>(is, bd); break;
-        case 13: wgrad_issue<13>(is, bd); break;  case 14: wgrad_issue<14>(is, bd); break;
-        case 15: wgrad_issue<15>(is, bd); break;  default: wgrad_issue<16>(is, bd); break;
+        case 1: wgrad_issue<1, kTwo>(is, bd); break;    case 2: wgrad_issue<2, kTwo>(is, bd); break;
+        case 3: wgrad_issue<3, kTwo>(is, bd); break;    case 4: wgrad_issue<4, kTwo>(is, bd); break;
+        case 5: wgrad_issue<5, kTwo>(is, bd); break;    case 6: wgrad_issue<6, kTwo>(is, bd); break;
+        case 7: wgrad_issue<7, kTwo>(is, bd); break;    case 8: wgrad_issue<8, kTwo>(is, bd); break;
+        case 9: wgrad_issue<9, kTwo>(is, bd); break;    case 10: wgrad_issue<10, kTwo>(is, bd); break;
+        case 11: wgrad_issue<11, kTwo>(is, bd); break;  case 12: wgrad_issue<12, kTwo>(is, bd); break;
+        case 13: wgrad_issue<13, kTwo>(is, bd); break;  case 14: wgrad_issue<14, kTwo>(is, bd); break;
+        case 15: wgrad_issue<15, kTwo>(is, bd); break;  default: wgrad_issue<16, kTwo>(is, bd); break;
       }
-      tc_commit(smem_u32(done_bar));
+      if (kTwo) tc_commit_2sm(smem_u32(done_bar), 3); else tc_commit(smem_u32(done_bar));
     }
   } else if (num_kb > 0) {
     // ---- epilogue: TMEM -> fp32 atomics into the packed gradient ----------------------------
@@ -259,10 +276,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ 
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kTwo) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (kTwo) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -395,7 +412,12 @@ extern "C" int uavdet_conv_wgrad(const uavdet_act* x, const uavdet_act* dy, int 
   UAVDET_CHECK_ARG(nb * max_nv <= 512, "conv_wgrad: a tap column does not fit TMEM");
   P.cin_blk = nb;
   P.ci_blocks = c_blk / nb;
-  auto col_bytes = [&](int c) { return (long long)nb * 2 * ((P.tile_h + P.cols[c].nv - 1) * P.tile_w + pad_rows); };
+  // CTA-pair kernel: two cout blocks per pair, each CTA stages half of the channels of every X box
+  static const int two_mode = getenv("UAVDET_WGRAD_2CTA") ? atoi(getenv("UAVDET_WGRAD_2CTA")) : 1;
+  const bool two = two_mode != 0 && !per_sample && cout % 256 == 0 && nb >= 2 * P.b_width && (nb / 2) % P.b_width == 0 &&
+                   (nb / 2) % 16 == 0;
+  const int nbh = two ? nb / 2 : nb;                      // channels per X box and CTA
+  auto col_bytes = [&](int c) { return (long long)nbh * 2 * ((P.tile_h + P.cols[c].nv - 1) * P.tile_w + pad_rows); };
   int cpg = 1;
   for (int cand = ncols; cand >= 1; --cand) {
     if (ncols % cand) continue;
@@ -420,8 +442,8 @@ extern "C" int uavdet_conv_wgrad(const uavdet_act* x, const uavdet_act* dy, int 
         P.tap_off[P.cols[c].tap0 + v] = (int)off + v * P.tile_w * P.b_width * 2;
         P.tap_lbo[P.cols[c].tap0 + v] = P.cols[c].blk;
       }
-      off += (long long)(nb / P.b_width) * P.cols[c].blk;
-      xb += (nb / P.b_width) * rows * P.b_width * 2;
+      off += (long long)(nbh / P.b_width) * P.cols[c].blk;
+      xb += (nbh / P.b_width) * rows * P.b_width * 2;
     }
     P.grp_x_bytes[g] = xb;
     if (off > stage_bytes) stage_bytes = off;
@@ -469,14 +491,29 @@ extern "C" int uavdet_conv_wgrad(const uavdet_act* x, const uavdet_act* dy, int 
   }
   static PerDeviceOnce attr_once;     // function attributes are per device
   UAVDET_CUDA(attr_once.run([] {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     // same L1 / shared-memory split as the streaming kernels that share the SM with this one (see elementwise.cu)
-    return cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(wgrad_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(wgrad_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   }));
   dim3 grid((unsigned)(P.items * P.k_splits), (unsigned)samples);
   const int smem_bytes = P.stages * P.stage_bytes + ctrl_bytes;
-  wgrad_kernel<<<grid, kWgradThreads, smem_bytes, (cudaStream_t)stream>>>(mapDY, mapX[0], mapX[1], mapX[2], P);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kWgradThreads);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute cattr[1];
+  cattr[0].id = cudaLaunchAttributeClusterDimension;
+  cattr[0].val.clusterDim.x = 2; cattr[0].val.clusterDim.y = 1; cattr[0].val.clusterDim.z = 1;
+  cfg.attrs = cattr;
+  cfg.numAttrs = two ? 1 : 0;
+  if (two) UAVDET_CUDA(cudaLaunchKernelEx(&cfg, wgrad_kernel<true>, mapDY, mapX[0], mapX[1], mapX[2], P));
+  else UAVDET_CUDA(cudaLaunchKernelEx(&cfg, wgrad_kernel<false>, mapDY, mapX[0], mapX[1], mapX[2], P));
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }

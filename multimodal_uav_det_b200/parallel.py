@@ -37,6 +37,7 @@ class _Bucket:
         self.momentum = torch.zeros(off, dtype=torch.float32, device=device)
         self.pending = 0
         self.work = None
+        self.updated = False
         for p, o in zip(params, self.offsets):
             p.data, p.grad = self._views(p, o)
 
@@ -90,7 +91,16 @@ class FlatSGDTrainer:
             cur.append(p)
             cur_n += p.numel()
         if cur:
+            # the LAST bucket (the first layers of the model) completes only when backward ends, so its all-reduce is
+            # the one that cannot overlap anything: keep it small (tail_mb) by splitting the earliest layers off
+            tail_cap = int(float(os.environ.get("UAVDET_DP_TAIL_MB", "2")) * 1024 * 1024 / 4)
+            tail, tail_n = [], 0
+            while len(cur) > 1 and tail_n + cur[-1].numel() <= tail_cap:
+                tail_n += cur[-1].numel()
+                tail.insert(0, cur.pop())
             self.buckets.append(_Bucket(cur, device))
+            if tail:
+                self.buckets.append(_Bucket(tail, device))
         self._bucket_of: Dict[int, _Bucket] = {id(p): b for b in self.buckets for p in b.params}
         self._device = device
         self._hyper = torch.zeros(3, dtype=torch.float32, device=device)
@@ -109,6 +119,9 @@ class FlatSGDTrainer:
         # ... for this many conv-kernel launches after a bucket's all-reduce was enqueued (< 0: all of backward)
         self.sm_margin_hold = int(os.environ.get("UAVDET_DP_SM_MARGIN_HOLD", "8"))
         self._margin_on = False
+        # fused SGD of a bucket right behind its all-reduce on the communication stream (world > 1 only)
+        self.early_update = (self.world > 1 and device.type == "cuda"
+                             and os.environ.get("UAVDET_DP_EARLY_UPDATE", "1") != "0")
         bump_param_epoch()
         self._execs = [m._exec for m in model.modules() if hasattr(m, "_exec") and hasattr(m, "_forward_program")]
         for ex in self._execs:
@@ -201,6 +214,12 @@ class FlatSGDTrainer:
                     self._comm_stream.wait_stream(s)
             with torch.cuda.stream(self._comm_stream):
                 b.work = dist.all_reduce(b.grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                if self.early_update:
+                    # the bucket's layers are done with backward (their kernels read bf16 packs, not these fp32 master
+                    # copies): update it right behind its all-reduce, beside the rest of backward
+                    self.sync_hyper()
+                    ops.sgd_momentum_dev(b.param, b.grad, b.momentum, self._hyper)
+                    b.updated = True
         else:  # gloo / CPU tests
             b.work = dist.all_reduce(b.grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
@@ -234,6 +253,9 @@ class FlatSGDTrainer:
         if self.buckets and self.buckets[0].param.is_cuda:
             self.sync_hyper()
         for b in self.buckets:
+            if b.updated:           # already stepped on the communication stream, right behind its all-reduce
+                b.updated = False
+                continue
             if b.param.is_cuda:
                 ops.sgd_momentum_dev(b.param, b.grad, b.momentum, self._hyper)
             else:  # host-side logic tests (gloo): same arithmetic in torch

@@ -855,3 +855,32 @@ def test_encode_targets_matches_cpu_encoder_bit_exact(lib, grids, anchors):
     bad = torch.tensor([[630.0, 10.0, 660.0, 40.0]])
     with pytest.raises(IndexError):
         ops.encode_targets(bad.to(DEV), anchors, grids, 640)
+
+
+# ------------------------------------------------------------------------------------------------
+# hardware probe: shifted / non-atom-strided UMMA descriptors into a TMA-written swizzled tile
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bk", [64, 32])
+@pytest.mark.parametrize("shift,sbo_rows", [(0, 8), (1, 8), (3, 8), (8, 8), (0, 10), (1, 10), (11, 10), (22, 10), (0, 9), (4, 12)])
+def test_umma_descriptor_row_shift_and_group_stride(lib, bk, shift, sbo_rows):
+    """D[m] = A[shift + (m // 8) * sbo_rows + m % 8] @ B^T for a K-major swizzled A tile written by ONE TMA box: a start
+    address of whole rows (not whole 8-row atoms) and a group stride that is not a multiple of the atom.  This is what
+    a 'halo tile + nine descriptors' 3x3 implicit GEMM needs from the tensor core (csrc/umma_probe.cu)."""
+    import ctypes as C
+    rows_total = 192
+    g = torch.Generator().manual_seed(1000 + shift * 16 + sbo_rows)
+    a = bf16_round(torch.randn(rows_total, bk, generator=g))
+    b = bf16_round(torch.randn(64, bk, generator=g))
+    ad, bd = a.to(DEV).to(torch.bfloat16).contiguous(), b.to(DEV).to(torch.bfloat16).contiguous()
+    out = torch.full((128, 64), float("nan"), dtype=torch.float32, device=DEV)
+    fn = lib.uavdet_debug_umma_probe
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    rc = fn(ad.data_ptr(), bd.data_ptr(), rows_total, bk, shift, sbo_rows, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.uavdet_last_error()
+    torch.cuda.synchronize()
+    rows = torch.tensor([shift + (m // 8) * sbo_rows + m % 8 for m in range(128)])
+    want = a[rows] @ b.t()
+    err = (out.cpu() - want).abs().max().item()
+    print(f"bk={bk} shift={shift} sbo_rows={sbo_rows}: max |err| = {err:.3e}")
+    assert err < 1e-3
