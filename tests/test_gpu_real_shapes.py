@@ -269,7 +269,7 @@ def test_compute_metrics_return_ap_runs_decode_and_nms_on_the_kernels(lib):
     loss0, ap0, _, _ = head.compute_metrics(outs, mk())
     loss1, ap1, _, _ = head.compute_metrics(outs, mk(), return_ap=True)
     assert ap0 is None and ap1 is not None
-    assert torch.equal(loss0, loss1)
+    torch.testing.assert_close(loss0, loss1, rtol=1e-5, atol=1e-6)       # (the loss kernel reduces with atomics)
     det = head.last_detections
     wb, ws = O.decode_yolo(logits, hp["anchors"], hp["head_scales"], True)
     torch.testing.assert_close(det.boxes.cpu(), wb, rtol=2e-6, atol=2e-5)
