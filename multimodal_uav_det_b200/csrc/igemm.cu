@@ -518,6 +518,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       // single-slab tiles: this warp owns accumulator buffer `half` and visits every second tile
       const int tstep = single ? 2 : 1;
       if (single) acc = half;
+      uint8_t* wbuf_pending = nullptr;     // staging buffer (+ residual load in flight) already taken for the next tile
       for (int tl = single ? half : 0, tile; (tile = tile_at<kTwo>(P, tl, rank)) >= 0; tl += tstep) {
         const TileCoord tc = decode_tile(P, tile);
         const int oh = tc.oh0 + hl, ow = tc.ow0 + wl;
@@ -534,7 +535,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         // this warp's first slab of the tile: buffer + residual load before the accumulator is awaited
         const int sl_first = single ? 0 : half;
         uint8_t* wbuf_next = nullptr;
-        uint8_t* wbuf_first = (sl_first < n_slabs) ? acquire(tc, tc.n0 + sl_first * P.slab_w) : nullptr;
+        uint8_t* wbuf_first = wbuf_pending ? wbuf_pending
+                                           : ((sl_first < n_slabs) ? acquire(tc, tc.n0 + sl_first * P.slab_w) : nullptr);
+        wbuf_pending = nullptr;
         mbar_wait<64>(smem_u32(&tfull_bar[acc]), acc_phase, dead, P.watchdog, 0x8u);
         if (tr) P.trace[tl * 16 + 6] = clock64();
         tc_fence_after();
@@ -616,6 +619,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         if (tr) P.trace[tl * 16 + 7] = clock64();
         if (single) acc_phase ^= 1u;
         else if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        // The residual tile of this warp's first slab of its NEXT tile starts travelling now, into the other staging
+        // buffer: the 1x1 data gradients are one short k-block per tile, and the load's round trip (issued only after
+        // the tile had been awaited) was what their epilogue waited for.
+        if (kKind != 0 && P.res_tma == 2 && P.epi_bufs == 2 && sl_first < n_slabs) {
+          const int ntile = tile_at<kTwo>(P, tl + tstep, rank);
+          if (ntile >= 0) {
+            const TileCoord ntc = decode_tile(P, ntile);
+            wbuf_pending = acquire(ntc, ntc.n0 + sl_first * P.slab_w);
+          }
+        }
       }
       if (kKind == 0 && cur_n0 >= 0) flush_stats(cur_n0);
       if (lane == 0) tma_store_wait_all();   // smem must stay valid until the last store has read it
@@ -1005,6 +1018,10 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
     grid = 2 * (P.total_pairs < pairs ? P.total_pairs : pairs);
   }
   if (!P.res_tma) { mapRes = mapOut; mapResTail = mapOutTail; }
+  // res_tma == 2: the epilogue also requests the residual tile of its NEXT tile at the end of the current one
+  // (UAVDET_IGEMM_RES_PREFETCH=0 switches that off: A/B)
+  static const bool res_prefetch = !(getenv("UAVDET_IGEMM_RES_PREFETCH") && getenv("UAVDET_IGEMM_RES_PREFETCH")[0] == '0');
+  if (P.res_tma && res_prefetch) P.res_tma = 2;
   const int kind = (P.epi == UAVDET_EPI_HEAD) ? 3 : (P.epi == UAVDET_EPI_STATS) ? 0 : (P.act == UAVDET_ACT_NONE ? 1 : 2);
   static PerDeviceOnce attr_once[4][2];   // the dynamic-shared-memory opt-in is per device
   cudaLaunchConfig_t cfg{};

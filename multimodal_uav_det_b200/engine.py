@@ -542,14 +542,14 @@ class Executor:
         return ops.conv_fwd(x, w_b, co, k, s, p, s2d=sp.s2d, w_batch=n, act=sp.act, scale=scale, shift=shift,
                             shift_per_sample=per_sample_shift)
 
-    def _accumulate(self, p: torch.Tensor, g: torch.Tensor) -> None:
+    def _accumulate(self, p: torch.Tensor, g: torch.Tensor, fire: bool = True) -> None:
         if not p.requires_grad:
             return
         if p.grad is None:
             p.grad = g.reshape(p.shape).clone()
         else:
             p.grad.add_(g.reshape(p.shape))
-        if self.grad_ready_hook is not None:
+        if fire and self.grad_ready_hook is not None:
             self.grad_ready_hook(p)
 
     def dyn_backward(self, rec: DynRecord, dy: torch.Tensor, res: Optional[torch.Tensor] = None,
@@ -590,13 +590,16 @@ class Executor:
             dsum = ops.gap(d_raw) * float(d_raw.shape[1] * d_raw.shape[2])         # (n, O) per-sample channel sums
             d_bias_bank = rec.attn.t() @ dsum
             d_attn = d_attn + dsum @ rec.bias_bank.t()
+        # Gradient-ready hooks are fired at the END of this function: a data-parallel trainer may step a bucket right
+        # behind its all-reduce, and the expert bank / attention weights are still read below (fp32 masters, no pack)
+        ready = []
         if whole:
-            if self.grad_ready_hook is not None:
-                self.grad_ready_hook(bank_params[0][0])
+            ready.append(bank_params[0][0])
         else:
             for p, idx, is_bias in bank_params:
                 src = d_bias_bank if is_bias else d_bank
-                self._accumulate(p, src if idx is None else src[idx])
+                self._accumulate(p, src if idx is None else src[idx], fire=False)
+                ready.append(p)
         # attention MLP backward (softmax(s/T), Linear/conv1x1, ReLU, Linear/conv1x1): two launches that add the
         # parameter gradients straight into their `.grad` buffers and return the pooled-input gradient, already
         # divided by the pool size
@@ -618,17 +621,20 @@ class Executor:
         d_pooled = ops.attn_mlp_bwd(a, d_attn.contiguous(), rec.hidden, rec.pooled, w1, w2, float(sp.temperature),
                                     (4.0 if sp.s2d else 1.0) / (h * w), bufs[0], bufs[1], bufs[2], bufs[3],
                                     want_d_pooled=want_dx)
+        ready += [p for p, gb in zip(mlp_params, bufs) if gb is not None]
+        dx = None
+        if want_dx:
+            wt, _ = ops.dyn_aggregate(a, rec.bank, transposed=True)
+            if sp.s2d:
+                dx = ops.conv_dgrad_s2d(d_raw, wt, sp.cin, sp.k, sp.pad, w_batch=n, res=res, shift=d_pooled)
+            else:
+                dx = ops.conv_dgrad(d_raw, wt, sp.cin, sp.k, sp.stride, sp.pad, rec.in_hw, w_batch=n, res=res,
+                                    shift=d_pooled, shift_per_sample=True)
         if self.grad_ready_hook is not None:
-            for p, gb in zip(mlp_params, bufs):
-                if gb is not None:
+            for p in ready:
+                if p.requires_grad:
                     self.grad_ready_hook(p)
-        if not want_dx:
-            return None
-        wt, _ = ops.dyn_aggregate(a, rec.bank, transposed=True)
-        if sp.s2d:
-            return ops.conv_dgrad_s2d(d_raw, wt, sp.cin, sp.k, sp.pad, w_batch=n, res=res, shift=d_pooled)
-        return ops.conv_dgrad(d_raw, wt, sp.cin, sp.k, sp.stride, sp.pad, rec.in_hw, w_batch=n, res=res, shift=d_pooled,
-                              shift_per_sample=True)
+        return dx
 
     @staticmethod
     def _channel_sum(t: torch.Tensor) -> torch.Tensor:

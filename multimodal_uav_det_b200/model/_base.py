@@ -221,15 +221,18 @@ class YOLOHead(LightningModule):
                 conv.weight.grad = g.clone()
             else:
                 conv.weight.grad.add_(g)
-        if hook is not None:
-            for conv in (conv_o, conv_b):
-                hook(conv.weight)
-                hook(conv.bias)
         w = torch.zeros((32, cin, 1, 1), dtype=torch.float32, device=dev)
         w[:a] = conv_o.weight.detach()
         w[a:5 * a] = conv_b.weight.detach()
         wt = ops.pack_weight(w, transposed=True)              # W^T packed [cin][32]
-        return ops.conv_dgrad(dyh, wt, cin, 1, 1, 0, (hh, ww))
+        dx = ops.conv_dgrad(dyh, wt, cin, 1, 1, 0, (hh, ww))
+        # hooks last: a data-parallel trainer may update a bucket right behind its all-reduce, and the fp32 weights
+        # were still being read (packed) above
+        if hook is not None:
+            for conv in (conv_o, conv_b):
+                hook(conv.weight)
+                hook(conv.bias)
+        return dx
 
     def _scaled_anchors(self, h: int, device) -> torch.Tensor:
         """anchors[h] / head_scales[h] (reference _base.py:170) as a cached device tensor, so the loss does no

@@ -14,6 +14,7 @@ from multimodal_uav_det_b200.utils.datatype import Config
 dev = torch.device("cuda", 0)
 
 
+@torch.no_grad()          # inference timings: no tape, no autograd node for the trunk
 def timed(fn, iters, warm=3):
     for _ in range(warm):
         fn()
