@@ -213,6 +213,10 @@ int uavdet_unpack_wgrad(const float* dw_packed, int O, int I, int k, float* grad
 int uavdet_stem_fwd(const float* x_nchw, int n, int cin, int h, int w, const float* w_oihw,
                     int cout, int k, int stride, int pad, const uavdet_act* y,
                     const uavdet_epilogue* epi, void* stream);
+/* Space-to-depth(2) of the 3-channel NCHW fp32 input into NHWC bf16 (n, H/2, W/2, 32): channel (py*2+px)*3 + ci holds
+ * x[ci][2*by+py][2*bx+px], channels 12..31 are zero.  RTMUAVDet's 5x5 stride-2 pad-1 stem (RTMUAVDet.py:28-36) is a
+ * 3x3 pad-1 stride-1 convolution over this map (filter row kh = 2*tap_y + py - 1), i.e. an ordinary uavdet_conv_fwd.  */
+int uavdet_stem_s2d_pack(const float* x_nchw, int n, int h, int w, const uavdet_act* y, void* stream);
 /* im2col of the cin<=3 input: (n,cin,h,w) fp32 NCHW -> (n,ho,wo,32) bf16 NHWC whose channel (ci*k+kh)*k+kw holds
  * the tap (zero outside the image, channels >= cin*k*k are zero).  The stem conv then IS a 1x1 convolution over
  * 32 channels with the weight matrix w.flatten(1) zero-padded to 32 columns: uavdet_conv_fwd / uavdet_conv_wgrad

@@ -60,6 +60,7 @@ SIGNATURES = {
     "uavdet_pack_weights_batched": (_i, [_P, _i, C.c_longlong, _P]),
     "uavdet_unpack_wgrad": (_i, [_P, _i, _i, _i, _P, _i, _P]),
     "uavdet_stem_fwd": (_i, [_P, _i, _i, _i, _i, _P, _i, _i, _i, _i, _AP, _EP, _P]),
+    "uavdet_stem_s2d_pack": (_i, [_P, _i, _i, _i, _AP, _P]),
     "uavdet_im2col_stem": (_i, [_P, _i, _i, _i, _i, _i, _i, _i, _AP, _P]),
     "uavdet_stem_wgrad": (_i, [_P, _i, _i, _i, _i, _AP, _i, _i, _i, _P, _P]),
     "uavdet_bn_finalize": (_i, [_P, _P, _i, _d, _f, _f, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

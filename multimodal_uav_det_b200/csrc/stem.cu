@@ -226,8 +226,13 @@ __global__ void __launch_bounds__(256) stem1x1_fwd_kernel(StemParams P) {
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   const long long hw = (long long)P.h * P.w, total = hw * P.n;
   const bool stats = P.epi == UAVDET_EPI_STATS;
-  for (long long p = ((long long)blockIdx.x * 256 + threadIdx.x) >> 2; p < total; p += ((long long)gridDim.x * 256) >> 2) {
-    const long long img = p / hw, px = p - img * hw;
+  // (image, pixel) advance incrementally: a 64-bit divide per pixel cost more than the rest of the loop body
+  const long long step = ((long long)gridDim.x * 256) >> 2;
+  long long p = ((long long)blockIdx.x * 256 + threadIdx.x) >> 2;
+  long long img = p / hw, px = p - img * hw;
+  const long long step_img = step / hw, step_px = step - step_img * hw;
+  for (; p < total; p += step, img += step_img, px += step_px) {
+    if (px >= hw) { px -= hw; ++img; }
     const float* xin = P.x + img * CIN * hw + px;
     float xv[CIN];
 #pragma unroll
@@ -288,8 +293,12 @@ stem1x1_wgrad_kernel(const float* __restrict__ x, int n, long long hw, const __n
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci) acc[j][ci] = 0.f;
   const long long total = hw * n;
-  for (long long p = ((long long)blockIdx.x * 256 + threadIdx.x) >> 2; p < total; p += ((long long)gridDim.x * 256) >> 2) {
-    const long long img = p / hw, px = p - img * hw;
+  const long long step = ((long long)gridDim.x * 256) >> 2;
+  long long p = ((long long)blockIdx.x * 256 + threadIdx.x) >> 2;
+  long long img = p / hw, px = p - img * hw;
+  const long long step_img = step / hw, step_px = step - step_img * hw;
+  for (; p < total; p += step, img += step_img, px += step_px) {
+    if (px >= hw) { px -= hw; ++img; }
     const float* xin = x + img * CIN * hw + px;
     float xv[CIN];
 #pragma unroll
@@ -429,9 +438,53 @@ im2col_stem_kernel(const float* __restrict__ x, int h, int w, int stride, int pa
   }
 }
 
+// Space-to-depth(2) of the 3-channel NCHW fp32 network input into NHWC bf16 with 32 channels:
+//   y[n][by][bx][(py*2 + px)*3 + ci] = x[n][ci][2*by + py][2*bx + px]   (channels 12..31 zero).
+// A k x k stride-2 stem becomes a ceil(k/2)+1-tap stride-1 convolution over this map (RTMUAVDet's 5x5 s2 p1 stem =
+// a 3x3 pad-1 convolution with 12 live input channels), which runs on the implicit-GEMM kernel.
+__global__ void __launch_bounds__(256)
+stem_s2d_pack_kernel(const float* __restrict__ x, int h, int w, __nv_bfloat16* __restrict__ y, long long y_ld) {
+  const int img = blockIdx.y;
+  const int hs = h >> 1, ws = w >> 1;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (long long)hs * ws) return;
+  const int by = (int)(p / ws), bx = (int)(p - (long long)by * ws);
+  const float* xin = x + (long long)img * 3 * h * w;
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = 0.f;
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+    for (int py = 0; py < 2; ++py) {
+      const float2 t = __ldcs(reinterpret_cast<const float2*>(xin + ((long long)ci * h + 2 * by + py) * w + 2 * bx));
+      v[(py * 2 + 0) * 3 + ci] = t.x;
+      v[(py * 2 + 1) * 3 + ci] = t.y;
+    }
+  uint4* dst = reinterpret_cast<uint4*>(y + ((long long)img * hs * ws + p) * y_ld);
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  dst[0] = o;
+  o.x = pack_bf16x2(v[8], v[9]); o.y = pack_bf16x2(v[10], v[11]); o.z = 0u; o.w = 0u;
+  dst[1] = o;
+  dst[2] = make_uint4(0u, 0u, 0u, 0u);
+  dst[3] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 }  // namespace uavdet
 
 using namespace uavdet;
+
+extern "C" int uavdet_stem_s2d_pack(const float* x_nchw, int n, int h, int w, const uavdet_act* y, void* stream) {
+  UAVDET_CHECK_ARG(x_nchw && y && y->ptr && n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0,
+                   "stem_s2d_pack: bad arguments (even H, W)");
+  UAVDET_CHECK_ARG(y->n == n && y->h == h / 2 && y->w == w / 2 && y->c == 32, "stem_s2d_pack: output must be (n,H/2,W/2,32)");
+  UAVDET_CHECK_ARG(y->ld % 8 == 0 && ((uintptr_t)y->ptr & 15) == 0 && ((uintptr_t)x_nchw & 7) == 0, "stem_s2d_pack: alignment");
+  dim3 grid((unsigned)ceil_div64((long long)(h / 2) * (w / 2), 256), (unsigned)n);
+  stem_s2d_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, h, w, (__nv_bfloat16*)y->ptr, y->ld);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
 
 extern "C" int uavdet_stem_fwd(const float* x_nchw, int n, int cin, int h, int w, const float* w_oihw, int cout,
                                int k, int stride, int pad, const uavdet_act* y, const uavdet_epilogue* epi,

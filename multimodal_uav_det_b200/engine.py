@@ -638,7 +638,9 @@ class Executor:
 
     @staticmethod
     def _channel_sum(t: torch.Tensor) -> torch.Tensor:
-        return t.float().sum(dim=(0, 1, 2))
+        """Per-channel sum over (n, h, w) of an NHWC bf16 tensor: the streaming pool kernel (one read of t) and a
+        reduction of its (n, c) output — a cast to fp32 plus an ATen reduction moved the tensor three times."""
+        return ops.gap(t).sum(dim=0) * float(t.shape[1] * t.shape[2])
 
     def end_backward(self):
         """Join the weight-gradient stream (every per-channel gradient was already written and announced per layer)."""

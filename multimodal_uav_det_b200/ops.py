@@ -428,6 +428,40 @@ def stem_im2col(x_nchw: torch.Tensor, k: int, stride: int, pad: int) -> torch.Te
     return out
 
 
+def stem_s2d_pack(x_nchw: torch.Tensor) -> torch.Tensor:
+    """(n,3,H,W) fp32 -> (n,H/2,W/2,32) bf16 space-to-depth map, channel (py*2+px)*3+ci, channels 12..31 zero."""
+    _require_cuda(x_nchw)
+    x_nchw = _f32(x_nchw)
+    n, cin, h, w = x_nchw.shape
+    if cin != 3:
+        raise UavdetError("stem_s2d_pack expects a 3-channel input")
+    out = empty_act(n, h // 2, w // 2, 32, x_nchw.device)
+    yv = act_view(out)
+    check(_lib.load().uavdet_stem_s2d_pack(_ptr(x_nchw), n, h, w, C.byref(yv), _stream()), "stem_s2d_pack")
+    return out
+
+
+def s2d_stem_weight(w: torch.Tensor) -> torch.Tensor:
+    """(O,3,5,5) weight of a 5x5 stride-2 pad-1 stem -> the equivalent (O,32,3,3) weight over stem_s2d_pack's map:
+    filter row kh = 2*tap_y + py - 1 (tap_y in 0..2, py in 0..1), same for columns; rows / columns outside 0..4 and the
+    20 padding channels are zero."""
+    o = w.shape[0]
+    assert tuple(w.shape[1:]) == (3, 5, 5)
+    w3 = torch.zeros((o, 32, 3, 3), dtype=torch.float32, device=w.device)
+    for ty in range(3):
+        for py in range(2):
+            kh = 2 * ty + py - 1
+            if not 0 <= kh <= 4:
+                continue
+            for tx in range(3):
+                for px in range(2):
+                    kw = 2 * tx + px - 1
+                    if 0 <= kw <= 4:
+                        c0 = (py * 2 + px) * 3
+                        w3[:, c0:c0 + 3, ty, tx] = w[:, :, kh, kw]
+    return w3
+
+
 def stem_wgrad(x_nchw: torch.Tensor, dy: torch.Tensor, k: int, stride: int, pad: int,
                per_sample: bool = False) -> torch.Tensor:
     _require_cuda(x_nchw, dy)
