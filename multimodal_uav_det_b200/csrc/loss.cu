@@ -36,24 +36,26 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 // BCE-with-logits, the numerically stable form torch uses: max(x,0) - x*t + log1p(exp(-|x|))
 __device__ __forceinline__ float bce_logits(float x, float t) { return fmaxf(x, 0.f) - x * t + log1pf(expf(-fabsf(x))); }
 
+// Number of positive cells and index of the first one per sample.  blockIdx.x = sample, blockIdx.y = slice of its cells
+// (one block per sample left 64 blocks to scan 6 MB each on DySOEM's 320x320 head); slices combine with one atomicMin /
+// atomicAdd each into workspace words initialised by the host (first = 0x7f7f7f7f, npos = 0: cudaMemsetAsync).
 __global__ void __launch_bounds__(256) loss_prepass_kernel(LossParams P) {
   __shared__ int s_first;
   __shared__ int s_cnt;
   const int b = blockIdx.x;
   const int cells = P.A * P.H * P.W;
-  if (threadIdx.x == 0) { s_first = cells; s_cnt = 0; }
+  if (threadIdx.x == 0) { s_first = 0x7f7f7f7f; s_cnt = 0; }
   __syncthreads();
   const float* t = P.tgt + (long long)b * cells * 5;
-  int my_first = cells, my_cnt = 0;
-  for (int i = threadIdx.x; i < cells; i += blockDim.x) {
-    if (t[(long long)i * 5] == 1.0f) { ++my_cnt; if (i < my_first) my_first = i; }
+  int my_first = 0x7f7f7f7f, my_cnt = 0;
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < cells; i += gridDim.y * blockDim.x) {
+    if (__ldg(t + (long long)i * 5) == 1.0f) { ++my_cnt; if (i < my_first) my_first = i; }
   }
   if (my_cnt) { atomicAdd(&s_cnt, my_cnt); atomicMin(&s_first, my_first); }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    P.npos[b] = (float)s_cnt;
-    P.first[b] = s_first < cells ? s_first : 0;   // torch.argmax of an all-false mask is 0
-    P.acc[b * 3 + 0] = 0.f; P.acc[b * 3 + 1] = 0.f; P.acc[b * 3 + 2] = 0.f;
+  if (threadIdx.x == 0 && s_cnt) {
+    atomicAdd(P.npos + b, (float)s_cnt);          // exact: counts are small integers
+    atomicMin(P.first + b, s_first);
   }
 }
 
@@ -148,7 +150,8 @@ __global__ void __launch_bounds__(256) loss_main_kernel(LossParams P) {
         if (P.ciou) { cx += (float)gx; cy += (float)gy; w *= aw; h *= ah; }
         // calculate_iou: IoU with the sample's FIRST positive target as stored (before the rewrite)
         {
-          const float* t0 = P.tgt + ((long long)b * cells + P.first[b]) * 5;
+          const int first = P.first[b] < cells ? P.first[b] : 0;   // torch.argmax of an all-false mask is 0
+          const float* t0 = P.tgt + ((long long)b * cells + first) * 5;
           const Box4 tb = to_xyxy(t0[1], t0[2], t0[3], t0[4]);
           const Box4 pb = P.ciou ? to_xyxy(cx, cy, w, h) : to_xyxy(cx, cy, w * aw, h * ah);
           const float lx = fmaxf(pb.x1, tb.x1), ly = fmaxf(pb.y1, tb.y1), rx = fminf(pb.x2, tb.x2), ry = fminf(pb.y2, tb.y2);
@@ -252,7 +255,13 @@ extern "C" int uavdet_yolo_head_loss(const float* p_bbox, const float* p_obj, co
   P.acc = (float*)workspace + 2 * B;
   P.out = out2;
   cudaStream_t st = (cudaStream_t)stream;
-  loss_prepass_kernel<<<B, 256, 0, st>>>(P);
+  UAVDET_CUDA(cudaMemsetAsync(P.first, 0x7f, sizeof(int) * (size_t)B, st));
+  UAVDET_CUDA(cudaMemsetAsync(P.npos, 0, sizeof(float) * (size_t)B * 4, st));      // npos + acc
+  const int cells = A * H * W;
+  int slices = cells / 8192;
+  if (slices < 1) slices = 1;
+  if (slices > 64) slices = 64;
+  loss_prepass_kernel<<<dim3((unsigned)B, (unsigned)slices), 256, 0, st>>>(P);
   UAVDET_LAUNCH_CHECK();
   const long long total = (long long)B * A * H * W;
   long long blocks = (total + 255) / 256;

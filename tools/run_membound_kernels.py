@@ -115,6 +115,25 @@ def main():
         run(f"bn_bwd_reduce + bn_bwd_apply_fused C{c} @{hw} b32",
             lambda: ops.bn_act_bwd(dy, raw, sc, sh, mean, inv, sc, "leaky"), 5 * raw.numel() * 2)
         del raw, res, dy, out
+    xin = torch.rand(64, 3, 640, 640, device=dev)
+    w13 = torch.randn(32, 3, 1, 1, device=dev)
+    s1, s2 = torch.zeros(32, device=dev), torch.zeros(32, device=dev)
+    from multimodal_uav_det_b200._lib import EPI_STATS
+    run("stem1x1_fwd_kernel (3->32, batch statistics) @640 b64", lambda: ops.stem_fwd(xin, w13, 1, 1, 0, epi=EPI_STATS, sum_=s1, sumsq=s2),
+        xin.numel() * 4 + 64 * 640 * 640 * 64)
+    dy = act(64, 640, 640, 32)
+    run("stem1x1_wgrad_kernel (3->32) @640 b64", lambda: ops.stem_wgrad(xin, dy, 1, 1, 0), xin.numel() * 4 + dy.numel() * 2)
+    del dy
+    run("gap_nchw_kernel 3x640x640 b64", lambda: ops.gap_nchw(xin), xin.numel() * 4)
+    x128 = torch.rand(128, 3, 640, 640, device=dev)
+    run("stem_s2d_pack_kernel 3x640x640 -> 320x320x32 b128", lambda: ops.stem_s2d_pack(x128), x128.numel() * 4 + 128 * 320 * 320 * 64)
+    del x128, xin
+    dob = torch.randn(64, 3, 320, 320, 1, device=dev)
+    dbb = torch.randn(64, 3, 320, 320, 4, device=dev)
+    gbo, gbb = torch.zeros(3, device=dev), torch.zeros(12, device=dev)
+    run("head_grad_pack_kernel 320x320 head b64", lambda: ops.head_grad_pack(dob, dbb, 64, 3, 320, 320, gbo, gbb),
+        (dob.numel() + dbb.numel()) * 4 + 64 * 320 * 320 * 64)
+    del dob, dbb
     x = act(n, 40, 40, 256)
     out = ops.empty_act(n, 80, 80, 256, dev)
     run("upsample2x_fwd_kernel C256 40->80 b32", lambda: ops.upsample2x_fwd(x, out=out), (x.numel() + out.numel()) * 2)
