@@ -114,7 +114,7 @@ static dim3 stream_grid(const uavdet_act* v, int unroll, int blocks_per_sm = 16)
 template <bool HAS_RES>
 __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(View raw, const float* __restrict__ scale, const float* __restrict__ shift, int act,
-                  const __nv_bfloat16* __restrict__ res, int res_ld, View y) {
+                  const __nv_bfloat16* __restrict__ res, int res_ld, int reverse, View y) {
   const PixLane L = pix_lane(raw.c);
   if (!L.active) return;
   float s[8], t[8];
@@ -135,23 +135,28 @@ bn_act_fwd_kernel(View raw, const float* __restrict__ scale, const float* __rest
     }
     *reinterpret_cast<uint4*>(y.p + px * y.ld + L.c) = pack8(v);
   };
+  // reverse: pixels from the end — the convolution that produced `raw` wrote it front to back, so its tail is what the
+  // L2 still holds, and the head of y, written last here, is what the next convolution reads first
+  const long long last = raw.npix - 1;
   long long px = L.px0;
   for (; px + 3 * L.step < raw.npix; px += 4 * L.step) {
     uint4 a[4], r[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      a[u] = __ldcs(reinterpret_cast<const uint4*>(raw.p + (px + u * L.step) * raw.ld + L.c));
-      if (HAS_RES) r[u] = __ldg(reinterpret_cast<const uint4*>(res + (px + u * L.step) * res_ld + L.c));
+      const long long q = reverse ? last - (px + u * L.step) : px + u * L.step;
+      a[u] = __ldcs(reinterpret_cast<const uint4*>(raw.p + q * raw.ld + L.c));
+      if (HAS_RES) r[u] = __ldg(reinterpret_cast<const uint4*>(res + q * res_ld + L.c));
       else r[u] = make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) body(a[u], r[u], px + u * L.step);
+    for (int u = 0; u < 4; ++u) body(a[u], r[u], reverse ? last - (px + u * L.step) : px + u * L.step);
   }
   for (; px < raw.npix; px += L.step) {
-    uint4 a = __ldcs(reinterpret_cast<const uint4*>(raw.p + px * raw.ld + L.c));
+    const long long q = reverse ? last - px : px;
+    uint4 a = __ldcs(reinterpret_cast<const uint4*>(raw.p + q * raw.ld + L.c));
     uint4 r = make_uint4(0, 0, 0, 0);
-    if (HAS_RES) r = __ldg(reinterpret_cast<const uint4*>(res + px * res_ld + L.c));
-    body(a, r, px);
+    if (HAS_RES) r = __ldg(reinterpret_cast<const uint4*>(res + q * res_ld + L.c));
+    body(a, r, q);
   }
 }
 
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(256, MINB)
 bn_bwd_apply_fused_kernel(View dy, View raw, const float* __restrict__ scale, const float* __restrict__ shift,
                           const float* __restrict__ sum_dz, const float* __restrict__ sum_dzr,
                           const float* __restrict__ mean, const float* __restrict__ invstd, float inv_count, int act,
-                          float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate, View dr) {
+                          float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate, int reverse, View dr) {
   const PixLane L = pix_lane(dy.c);
   if (!L.active) return;
   float s[8], t[8], a1[8], a0[8];
@@ -388,20 +393,27 @@ bn_bwd_apply_fused_kernel(View dy, View raw, const float* __restrict__ scale, co
     }
     *reinterpret_cast<uint4*>(dr.p + px * dr.ld + L.c) = pack8(d);
   };
+  // reverse: walk the pixels from the end.  The reduction pass that ran just before read both tensors front to back,
+  // so what is still in the 126 MB L2 is their tail — and what this pass writes last (the head of d_raw) is what the
+  // data-gradient kernel that follows reads first.
+  const long long last = dy.npix - 1;
   long long px = L.px0;
   for (; px + (U - 1) * L.step < dy.npix; px += U * L.step) {
     uint4 a[U], b[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      a[u] = __ldcs(reinterpret_cast<const uint4*>(dy.p + (px + u * L.step) * dy.ld + L.c));
-      b[u] = __ldcs(reinterpret_cast<const uint4*>(raw.p + (px + u * L.step) * raw.ld + L.c));
+      const long long q = reverse ? last - (px + u * L.step) : px + u * L.step;
+      a[u] = __ldcs(reinterpret_cast<const uint4*>(dy.p + q * dy.ld + L.c));
+      b[u] = __ldcs(reinterpret_cast<const uint4*>(raw.p + q * raw.ld + L.c));
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) body(a[u], b[u], px + u * L.step);
+    for (int u = 0; u < U; ++u) body(a[u], b[u], reverse ? last - (px + u * L.step) : px + u * L.step);
   }
-  for (; px < dy.npix; px += L.step)
-    body(__ldcs(reinterpret_cast<const uint4*>(dy.p + px * dy.ld + L.c)),
-         __ldcs(reinterpret_cast<const uint4*>(raw.p + px * raw.ld + L.c)), px);
+  for (; px < dy.npix; px += L.step) {
+    const long long q = reverse ? last - px : px;
+    body(__ldcs(reinterpret_cast<const uint4*>(dy.p + q * dy.ld + L.c)),
+         __ldcs(reinterpret_cast<const uint4*>(raw.p + q * raw.ld + L.c)), q);
+  }
 }
 
 __global__ void act_bwd_kernel(View dy, View raw, const float* __restrict__ scale,
@@ -1133,10 +1145,11 @@ extern "C" int uavdet_bn_act_fwd(const uavdet_act* raw, const float* scale, cons
   View r = mkview(raw), o = mkview(y);
   if (r.npix == 0) return UAVDET_OK;
   dim3 grid = stream_grid(raw, 8);
+  static const int reverse = getenv("UAVDET_BN_FWD_REVERSE") ? atoi(getenv("UAVDET_BN_FWD_REVERSE")) : 1;
   if (res)
-    bn_act_fwd_kernel<true><<<grid, 256, 0, ST>>>(r, scale, shift, act, (const __nv_bfloat16*)res->ptr, res->ld, o);
+    bn_act_fwd_kernel<true><<<grid, 256, 0, ST>>>(r, scale, shift, act, (const __nv_bfloat16*)res->ptr, res->ld, reverse, o);
   else
-    bn_act_fwd_kernel<false><<<grid, 256, 0, ST>>>(r, scale, shift, act, nullptr, 0, o);
+    bn_act_fwd_kernel<false><<<grid, 256, 0, ST>>>(r, scale, shift, act, nullptr, 0, reverse, o);
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }
@@ -1243,11 +1256,12 @@ extern "C" int uavdet_bn_act_bwd_apply_fused(const uavdet_act* dy, const uavdet_
   static const int ppt = getenv("UAVDET_BN_APPLY_PPT") ? atoi(getenv("UAVDET_BN_APPLY_PPT")) : 4;
   // register budget / unroll variants (occupancy against loads in flight per thread): A/B switch
   static const int variant = getenv("UAVDET_BN_APPLY_VARIANT") ? atoi(getenv("UAVDET_BN_APPLY_VARIANT")) : 3;
+  static const int reverse = getenv("UAVDET_BN_APPLY_REVERSE") ? atoi(getenv("UAVDET_BN_APPLY_REVERSE")) : 1;
   prefer_max_smem_carveout_once();
 #define UAVDET_BN_APPLY(U, MINB, BPS)                                                                                       \
   bn_bwd_apply_fused_kernel<U, MINB><<<stream_grid(dy, ppt, BPS), 256, 0, ST>>>(                                            \
       mkview(dy), mkview(raw), scale, shift, sum_dz, sum_dzr, mean, invstd, (float)(1.0 / count), act, dgamma, dbeta,      \
-      accumulate, mkview(d_raw))
+      accumulate, reverse, mkview(d_raw))
   switch (variant) {
     case 1: UAVDET_BN_APPLY(4, 3, 24); break;
     case 2: UAVDET_BN_APPLY(2, 4, 32); break;
