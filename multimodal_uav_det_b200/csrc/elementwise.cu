@@ -1145,7 +1145,7 @@ extern "C" int uavdet_bn_act_fwd(const uavdet_act* raw, const float* scale, cons
   View r = mkview(raw), o = mkview(y);
   if (r.npix == 0) return UAVDET_OK;
   dim3 grid = stream_grid(raw, 8);
-  static const int reverse = getenv("UAVDET_BN_FWD_REVERSE") ? atoi(getenv("UAVDET_BN_FWD_REVERSE")) : 1;
+  static const int reverse = getenv("UAVDET_BN_FWD_REVERSE") ? atoi(getenv("UAVDET_BN_FWD_REVERSE")) : 0;
   if (res)
     bn_act_fwd_kernel<true><<<grid, 256, 0, ST>>>(r, scale, shift, act, (const __nv_bfloat16*)res->ptr, res->ld, reverse, o);
   else
@@ -1256,7 +1256,7 @@ extern "C" int uavdet_bn_act_bwd_apply_fused(const uavdet_act* dy, const uavdet_
   static const int ppt = getenv("UAVDET_BN_APPLY_PPT") ? atoi(getenv("UAVDET_BN_APPLY_PPT")) : 4;
   // register budget / unroll variants (occupancy against loads in flight per thread): A/B switch
   static const int variant = getenv("UAVDET_BN_APPLY_VARIANT") ? atoi(getenv("UAVDET_BN_APPLY_VARIANT")) : 3;
-  static const int reverse = getenv("UAVDET_BN_APPLY_REVERSE") ? atoi(getenv("UAVDET_BN_APPLY_REVERSE")) : 1;
+  static const int reverse = getenv("UAVDET_BN_APPLY_REVERSE") ? atoi(getenv("UAVDET_BN_APPLY_REVERSE")) : 0;
   prefer_max_smem_carveout_once();
 #define UAVDET_BN_APPLY(U, MINB, BPS)                                                                                       \
   bn_bwd_apply_fused_kernel<U, MINB><<<stream_grid(dy, ppt, BPS), 256, 0, ST>>>(                                            \
