@@ -424,6 +424,13 @@ class ConvTimer:
             return 2.0 * n * ho * wo * cout * 4 * c * k * k
 
         ops.conv_dgrad_s2d = timed(self._orig[3], "igemm", dgrad_s2d_flops)
+        # the tensor-core stem (stem_mma.cu) is HBM-bound: recorded with its algorithmic bytes (fp32 NCHW input read +
+        # NHWC bf16 tensor written / read), under kinds of its own so it stays out of the igemm / wgrad aggregates
+        self._orig_stem = (ops.stem_mma_fwd, ops.stem_mma_wgrad)
+        stem_bytes = lambda a, kw: a[0].numel() * 4.0 + a[0].shape[0] * 64.0 * (
+            ops.conv_out_hw(a[0].shape[2], a[0].shape[3], a[2], a[3], a[4])[0] * ops.conv_out_hw(a[0].shape[2], a[0].shape[3], a[2], a[3], a[4])[1])
+        ops.stem_mma_fwd = timed(self._orig_stem[0], "stem_fwd", stem_bytes)
+        ops.stem_mma_wgrad = timed(self._orig_stem[1], "stem_wgrad", stem_bytes)
         self._orig_bn = None
         if os.environ.get("UAVDET_BENCH_DEBUG"):
             # debug table only: the BatchNorm passes too, with their algorithmic bytes in place of flops
@@ -436,6 +443,7 @@ class ConvTimer:
 
     def __exit__(self, *exc):
         self.ops.conv_fwd, self.ops.conv_dgrad, self.ops.conv_wgrad, self.ops.conv_dgrad_s2d = self._orig
+        self.ops.stem_mma_fwd, self.ops.stem_mma_wgrad = self._orig_stem
         if self._orig_bn is not None:
             self.ops.bn_act_fwd, self.ops.bn_act_bwd = self._orig_bn
 
@@ -446,7 +454,7 @@ class ConvTimer:
         for i, (kind, fl, slot) in enumerate(self.records):
             sec = (t[slot + 1] - t[slot]) * 1e-9
             if os.environ.get("UAVDET_BENCH_DEBUG"):
-                if kind.startswith("bn_"):
+                if kind.startswith(("bn_", "stem_")):
                     print(f"[convtimer] {i} {kind} {sec * 1e6:.0f} us {fl / 1e6:.0f} MB {fl / sec / 1e12:.2f} TB/s", file=sys.stderr)
                 else:
                     print(f"[convtimer] {i} {kind} {sec * 1e6:.0f} us {fl / 1e9:.1f} GFLOP", file=sys.stderr)

@@ -225,6 +225,22 @@ int uavdet_im2col_stem(const float* x_nchw, int n, int cin, int h, int w, int k,
                        const uavdet_act* y, void* stream);
 int uavdet_stem_wgrad(const float* x_nchw, int n, int cin, int h, int w, const uavdet_act* dy,
                       int k, int stride, int pad, float* grad_oihw, void* stream);
+/* The 3x3 cin <= 3 stem on tcgen05 WITHOUT a patch tensor (BaselineModel.py:89-97 first layer; DyYOLO.py:89-100 with
+ * per-sample kernels): the im2col rows are built in shared memory from the NCHW fp32 input (one 64-byte bf16 row per
+ * output pixel, K = cin*9 zero-padded to 32) and consumed in place by the tensor core, so the layer moves its
+ * algorithmic bytes only (12 B in, 64 B out per pixel; the im2col route writes and re-reads 64 B more).
+ *   w_bf16: [w_batch][32][32] bf16 — w.flatten(1) rows zero-padded to 32 columns (uavdet_dyn_aggregate transposed == 2
+ *           writes exactly this for the dynamic stem); w_batch = 1 or n;
+ *   y:      (n, ho, wo, 32) NHWC bf16; epi: AFFINE (scale/shift/act) or STATS (raw output + batch sums);
+ *   wgrad:  dy (n, ho, wo, 32); dw_o32 fp32 [per_sample ? n : 1][32][32] (columns >= cin*9 stay untouched), ACCUMULATED
+ *           with atomics (caller-zeroed) — autograd of the same sites.
+ * uavdet_stem_mma_supported: 1 when (cin, cout, k) is instantiated (k = 3, cin in 1..3, cout = 32).                 */
+int uavdet_stem_mma_supported(int cin, int cout, int k);
+int uavdet_stem_mma_fwd(const float* x_nchw, int n, int cin, int h, int w, const void* w_bf16, int w_batch,
+                        int k, int stride, int pad, const uavdet_act* y, const uavdet_epilogue* epi,
+                        void* stream);
+int uavdet_stem_mma_wgrad(const float* x_nchw, int n, int cin, int h, int w, const uavdet_act* dy, int k,
+                          int stride, int pad, float* dw_o32, int per_sample, void* stream);
 
 /* ---- K5: batch-norm + activation (two-phase, train mode) ---------------------------- */
 /* From batch sums: mean/invstd, running-stat update (momentum, unbiased var —

@@ -63,6 +63,9 @@ SIGNATURES = {
     "uavdet_stem_s2d_pack": (_i, [_P, _i, _i, _i, _AP, _P]),
     "uavdet_im2col_stem": (_i, [_P, _i, _i, _i, _i, _i, _i, _i, _AP, _P]),
     "uavdet_stem_wgrad": (_i, [_P, _i, _i, _i, _i, _AP, _i, _i, _i, _P, _P]),
+    "uavdet_stem_mma_supported": (_i, [_i, _i, _i]),
+    "uavdet_stem_mma_fwd": (_i, [_P, _i, _i, _i, _i, _P, _i, _i, _i, _i, _AP, _EP, _P]),
+    "uavdet_stem_mma_wgrad": (_i, [_P, _i, _i, _i, _i, _AP, _i, _i, _i, _P, _i, _P]),
     "uavdet_bn_finalize": (_i, [_P, _P, _i, _d, _f, _f, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "uavdet_bn_act_fwd": (_i, [_AP, _P, _P, _i, _AP, _AP, _P]),
     "uavdet_bn_act_bwd_reduce": (_i, [_AP, _AP, _P, _P, _i, _P, _P, _P]),

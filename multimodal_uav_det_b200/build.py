@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libuavdet_b200.so")
-SOURCES = ["api.cu", "nms.cu", "decode.cu", "elementwise.cu", "stem.cu", "igemm.cu", "wgrad.cu", "rtm.cu", "loss.cu", "targets.cu", "umma_probe.cu"]
+SOURCES = ["api.cu", "nms.cu", "decode.cu", "elementwise.cu", "stem.cu", "stem_mma.cu", "igemm.cu", "wgrad.cu", "rtm.cu", "loss.cu", "targets.cu", "umma_probe.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -21,6 +21,8 @@ from torch import nn
 from . import ops
 from ._lib import EPI_AFFINE, EPI_STATS
 
+_STEM_IM2COL = bool(os.environ.get("UAVDET_STEM_IM2COL"))    # A/B switch: keep the im2col patch tensor of the 3x3 stems
+
 
 # ------------------------------------------------------------------------------------------------
 # packed-weight cache
@@ -247,6 +249,12 @@ class Executor:
         others (RTMUAVDet's 5x5 stem: 75 taps; DySOEM's 1x1: nothing to gather) keep the direct kernel."""
         return cout % 32 == 0 and k > 1 and cin * k * k <= 32
 
+    @staticmethod
+    def stem_in_smem(cin: int, cout: int, k: int) -> bool:
+        """3x3 cin<=3 -> 32 stems: the im2col rows are built in shared memory by the stem_mma kernels, nothing is
+        materialised (UAVDET_STEM_IM2COL=1 keeps the patch tensor: A/B switch)."""
+        return not _STEM_IM2COL and ops.stem_mma_supported(cin, cout, k)
+
     def _stem_pack(self, w: torch.Tensor) -> torch.Tensor:
         """(O, cin, k, k) fp32 -> bf16 [O][32]: w.flatten(1) zero-padded to the 32 im2col channels."""
         key = (id(w), "stem")
@@ -268,10 +276,15 @@ class Executor:
         in_hw = self._in_hw(u, x)
         direct_stem = u.stem
         k, stride, pad, s2d = u.k, u.stride, u.pad, u.s2d
+        stem_mma = False
         if u.stem and self.stem_as_gemm(w.shape[1], u.cout, u.k):
-            x = ops.stem_im2col(x, u.k, u.stride, u.pad)          # (n, ho, wo, 32) bf16 patches
             wp = self._stem_pack(w)
-            k, stride, pad, s2d, direct_stem = 1, 1, 0, False, False
+            direct_stem = False
+            if self.stem_in_smem(w.shape[1], u.cout, u.k):
+                stem_mma = True                                   # patch rows built in shared memory (stem_mma.cu)
+            else:
+                x = ops.stem_im2col(x, u.k, u.stride, u.pad)      # (n, ho, wo, 32) bf16 patches
+                k, stride, pad, s2d = 1, 1, 0, False
         elif not u.stem:
             wp = self.packs.get(w)
         if u.bn is not None and train:
@@ -284,6 +297,8 @@ class Executor:
             sums = self.zeros(2, c, dev)
             if direct_stem:
                 raw = ops.stem_fwd(x, w.detach(), k, stride, pad, epi=EPI_STATS, sum_=sums[0], sumsq=sums[1])
+            elif stem_mma:
+                raw = ops.stem_mma_fwd(x, wp, k, stride, pad, epi=EPI_STATS, sum_=sums[0], sumsq=sums[1])
             else:
                 raw = ops.conv_fwd(x, wp, c, k, stride, pad, s2d=s2d, epi=EPI_STATS, sum_=sums[0], sumsq=sums[1])
             n, ho, wo, _ = raw.shape
@@ -309,13 +324,18 @@ class Executor:
             # training through a non-BN activation: keep the pre-activation for act'(z)
             if direct_stem:
                 raw = ops.stem_fwd(x, w.detach(), k, stride, pad, scale=scale, shift=shift)
+            elif stem_mma:
+                raw = ops.stem_mma_fwd(x, wp, k, stride, pad, scale=scale, shift=shift)
             else:
                 raw = ops.conv_fwd(x, wp, u.cout, k, stride, pad, s2d=s2d, scale=scale, shift=shift)
             y = ops.bn_act_fwd(raw, None, None, u.act, res=res, out=out)
             tape.append(ConvRecord(u, x, raw, scale, None, None, None, res is not None, in_hw))
             return y
-        if direct_stem:
-            y = ops.stem_fwd(x, w.detach(), k, stride, pad, act=u.act, scale=scale, shift=shift)
+        if direct_stem or stem_mma:
+            if stem_mma:
+                y = ops.stem_mma_fwd(x, wp, k, stride, pad, act=u.act, scale=scale, shift=shift)
+            else:
+                y = ops.stem_fwd(x, w.detach(), k, stride, pad, act=u.act, scale=scale, shift=shift)
             if res is not None or out is not None:
                 y = ops.add(y, res, out=out)
         else:
@@ -460,6 +480,10 @@ class Executor:
                 dwp = ops.conv_wgrad(rec.x, d_raw, 1, 1, 0)
                 kk = w.shape[1] * u.k * u.k
                 gbuf.add_(dwp[:, :kk].reshape(w.shape))
+            elif u.stem and self.stem_as_gemm(w.shape[1], u.cout, u.k) and self.stem_in_smem(w.shape[1], u.cout, u.k):
+                kk = w.shape[1] * u.k * u.k
+                dwp = ops.stem_mma_wgrad(rec.x, d_raw, u.k, u.stride, u.pad, out=self.zeros(32, 32, d_raw.device))
+                gbuf.add_(dwp[:, :kk].reshape(w.shape))
             elif u.stem:
                 g = ops.stem_wgrad(rec.x, d_raw, u.k, u.stride, u.pad)
                 gbuf.add_(g)
@@ -491,14 +515,20 @@ class Executor:
         in_hw = (x.shape[2], x.shape[3]) if sp.stem else (x.shape[1], x.shape[2])
         bn, k, s, p, co = sp.bn, sp.k, sp.stride, sp.pad, sp.cout
         direct_stem = sp.stem
+        stem_mma = False
         if sp.stem:
             bias_b = None
             if self.stem_as_gemm(sp.cin, co, k):
-                # im2col + batched 1x1 implicit GEMM: per-sample [O][32] bf16 kernels (taps zero-padded to 32),
-                # mixed from the expert bank by the aggregation kernel
-                x = ops.stem_im2col(x, k, s, p)
+                # per-sample [O][32] bf16 kernels (taps zero-padded to 32), mixed from the expert bank by the
+                # aggregation kernel; the patch rows are built in shared memory (stem_mma) or, for shapes that kernel
+                # does not cover, materialised by im2col and fed to the batched 1x1 implicit GEMM
                 w_b = ops.dyn_aggregate_stem(attn, bank)
-                k, s, p, direct_stem = 1, 1, 0, False
+                direct_stem = False
+                if self.stem_in_smem(sp.cin, co, k):
+                    stem_mma = True
+                else:
+                    x = ops.stem_im2col(x, k, s, p)
+                    k, s, p = 1, 1, 0
             else:
                 # direct CUDA-core stem (no shipped configuration takes this branch): fp32 per-sample kernels
                 w_b = torch.mm(attn, bank.flatten(1)).view(n, *bank.shape[1:])
@@ -508,6 +538,8 @@ class Executor:
             sums = self.zeros(2, co, attn.device)
             if direct_stem:
                 raw = ops.stem_fwd(x, w_b, k, s, p, epi=EPI_STATS, sum_=sums[0], sumsq=sums[1], per_sample_w=True)
+            elif stem_mma:
+                raw = ops.stem_mma_fwd(x, w_b, k, s, p, epi=EPI_STATS, sum_=sums[0], sumsq=sums[1])
             else:
                 raw = ops.conv_fwd(x, w_b, co, k, s, p, s2d=sp.s2d, w_batch=n, epi=EPI_STATS, shift=bias_b,
                                    shift_per_sample=bias_b is not None, sum_=sums[0], sumsq=sums[1])
@@ -531,6 +563,8 @@ class Executor:
             # frozen-BN training: keep z = scale*conv + shift for act'(z)
             if direct_stem:
                 z = ops.stem_fwd(x, w_b, k, s, p, scale=scale, shift=shift, per_sample_w=True)
+            elif stem_mma:
+                z = ops.stem_mma_fwd(x, w_b, k, s, p, scale=scale, shift=shift)
             else:
                 z = ops.conv_fwd(x, w_b, co, k, s, p, s2d=sp.s2d, w_batch=n, scale=scale, shift=shift,
                                  shift_per_sample=per_sample_shift)
@@ -539,6 +573,8 @@ class Executor:
             return y
         if direct_stem:
             return ops.stem_fwd(x, w_b, k, s, p, act=sp.act, scale=scale, shift=shift, per_sample_w=True)
+        if stem_mma:
+            return ops.stem_mma_fwd(x, w_b, k, s, p, act=sp.act, scale=scale, shift=shift)
         return ops.conv_fwd(x, w_b, co, k, s, p, s2d=sp.s2d, w_batch=n, act=sp.act, scale=scale, shift=shift,
                             shift_per_sample=per_sample_shift)
 
@@ -570,6 +606,9 @@ class Executor:
         if sp.stem and rec.x.dtype == torch.bfloat16:
             kk = sp.cin * sp.k * sp.k                              # im2col stem: per-sample 1x1 wgrad, first kk columns
             dwb = ops.conv_wgrad(rec.x, d_raw, 1, 1, 0, per_sample=True)[:, :, :kk].contiguous()
+        elif sp.stem and self.stem_as_gemm(sp.cin, sp.cout, sp.k) and self.stem_in_smem(sp.cin, sp.cout, sp.k):
+            kk = sp.cin * sp.k * sp.k
+            dwb = ops.stem_mma_wgrad(rec.x, d_raw, sp.k, sp.stride, sp.pad, per_sample=True)[:, :, :kk].contiguous()
         elif sp.stem:
             dwb = ops.stem_wgrad(rec.x, d_raw, sp.k, sp.stride, sp.pad, per_sample=True)
         else:

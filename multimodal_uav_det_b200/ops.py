@@ -428,6 +428,44 @@ def stem_im2col(x_nchw: torch.Tensor, k: int, stride: int, pad: int) -> torch.Te
     return out
 
 
+def stem_mma_supported(cin: int, cout: int, k: int) -> bool:
+    return bool(_lib.load().uavdet_stem_mma_supported(int(cin), int(cout), int(k)))
+
+
+def stem_mma_fwd(x_nchw: torch.Tensor, w_o32: torch.Tensor, k: int, stride: int, pad: int, *, epi: int = EPI_AFFINE,
+                 act=None, scale=None, shift=None, sum_=None, sumsq=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """3x3 cin<=3 stem on the tensor cores, patch rows built in shared memory (no im2col tensor).
+    w_o32: bf16 (32, 32) or per-sample (n, 32, 32): w.flatten(1) zero-padded to 32 columns."""
+    _require_cuda(x_nchw, w_o32)
+    x_nchw = _f32(x_nchw)
+    if w_o32.dtype != torch.bfloat16 or not w_o32.is_contiguous() or tuple(w_o32.shape[-2:]) != (32, 32):
+        raise UavdetError("stem_mma_fwd expects contiguous bf16 weights (.., 32, 32)")
+    n, cin, h, w = x_nchw.shape
+    w_batch = w_o32.shape[0] if w_o32.dim() == 3 else 1
+    ho, wo = conv_out_hw(h, w, k, stride, pad)
+    if out is None:
+        out = empty_act(n, ho, wo, 32, x_nchw.device)
+    yv = act_view(out)
+    e = _epilogue(epi, act, _f32(scale), _f32(shift), None, _f32(sum_), _f32(sumsq))
+    check(_lib.load().uavdet_stem_mma_fwd(_ptr(x_nchw), n, cin, h, w, _ptr(w_o32), w_batch, k, stride, pad, C.byref(yv),
+                                          C.byref(e), _stream()), "stem_mma_fwd")
+    return out
+
+
+def stem_mma_wgrad(x_nchw: torch.Tensor, dy: torch.Tensor, k: int, stride: int, pad: int,
+                   per_sample: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 (32, 32) [or (n, 32, 32)] gradient of the zero-padded flattened stem kernel; columns < cin*k*k are dW."""
+    _require_cuda(x_nchw, dy)
+    x_nchw = _f32(x_nchw)
+    n, cin, h, w = x_nchw.shape
+    if out is None:
+        out = torch.zeros((n, 32, 32) if per_sample else (32, 32), dtype=torch.float32, device=dy.device)
+    dv = act_view(dy)
+    check(_lib.load().uavdet_stem_mma_wgrad(_ptr(x_nchw), n, cin, h, w, C.byref(dv), k, stride, pad, _ptr(out),
+                                            1 if per_sample else 0, _stream()), "stem_mma_wgrad")
+    return out
+
+
 def stem_s2d_pack(x_nchw: torch.Tensor) -> torch.Tensor:
     """(n,3,H,W) fp32 -> (n,H/2,W/2,32) bf16 space-to-depth map, channel (py*2+px)*3+ci, channels 12..31 zero."""
     _require_cuda(x_nchw)

@@ -778,6 +778,66 @@ def test_stem_im2col_then_gemm_equals_conv(lib, cin, k, stride, pad, h, w):
     assert rel_l2(dwp[:, :kk].reshape(wt.shape).cpu(), ref_dw) < 2e-3
 
 
+@pytest.mark.parametrize("cin,stride,pad,h,w,n", [(3, 1, 1, 40, 56, 3), (3, 1, 1, 64, 64, 2), (1, 2, 1, 32, 32, 3),
+                                                  (2, 1, 0, 21, 19, 2), (3, 2, 1, 33, 47, 5), (3, 1, 1, 128, 160, 6)])
+def test_stem_mma_fwd_and_wgrad_equal_conv(lib, cin, stride, pad, h, w, n):
+    """The 3x3 cin<=3 stem with its patch rows built in shared memory (stem_mma.cu): raw output + batch sums, the
+    affine/activation epilogue, shared and per-sample kernels, output into a channel slice, and the weight gradient
+    (shared and per-sample) against F.conv2d / conv2d_weight on the bf16-rounded operands.  Sizes cover tiles that end
+    inside an image row, a ragged last tile, stride 2 and more tiles than CTAs."""
+    ops = _ops(lib)
+    from multimodal_uav_det_b200._lib import EPI_STATS
+    k, cout = 3, 32
+    assert ops.stem_mma_supported(cin, cout, k) and not ops.stem_mma_supported(cin, 64, k) and not ops.stem_mma_supported(3, 32, 5)
+    g = torch.Generator().manual_seed(900 + h + cin)
+    x = torch.rand(n, cin, h, w, generator=g) - 0.3
+    kk = cin * k * k
+    wt = bf16_round(torch.randn(cout, cin, k, k, generator=g) / math.sqrt(kk))
+    wp = F.pad(wt.flatten(1), (0, 32 - kk)).to(torch.bfloat16).to(DEV).contiguous()
+    xb = bf16_round(x)
+    ref = F.conv2d(xb, wt, None, stride, pad)
+    s1 = torch.zeros(32, device=DEV)
+    s2 = torch.zeros(32, device=DEV)
+    y = ops.stem_mma_fwd(x.to(DEV), wp, k, stride, pad, epi=EPI_STATS, sum_=s1, sumsq=s2)
+    ops.check_device()
+    assert_close_bf16(to_nchw(y), ref, "stem_mma raw")
+    yr = to_nchw(y)
+    torch.testing.assert_close(s1.cpu(), yr.sum(dim=(0, 2, 3)), rtol=1e-3, atol=2e-2)
+    torch.testing.assert_close(s2.cpu(), (yr * yr).sum(dim=(0, 2, 3)), rtol=1e-3, atol=2e-2)
+    # affine + activation epilogue, written into a channel slice of a wider buffer (pixel stride 64)
+    scale = (torch.rand(32, generator=g) + 0.5).to(DEV)
+    shift = (torch.rand(32, generator=g) - 0.5).to(DEV)
+    wide = torch.full((n, ref.shape[2], ref.shape[3], 64), 7.0, dtype=torch.bfloat16, device=DEV)
+    y2 = ops.stem_mma_fwd(x.to(DEV), wp, k, stride, pad, act="leaky", scale=scale, shift=shift, out=wide[..., 32:])
+    ref2 = F.leaky_relu(ref * scale.cpu().view(1, -1, 1, 1) + shift.cpu().view(1, -1, 1, 1), 0.1)
+    assert_close_bf16(to_nchw(y2), ref2, "stem_mma affine slice")
+    assert torch.all(wide[..., :32] == 7.0)
+    y3 = ops.stem_mma_fwd(x.to(DEV), wp, k, stride, pad, act="leaky", scale=scale, shift=shift)
+    assert torch.equal(y3, y2)
+    # per-sample kernels
+    wts = bf16_round(torch.randn(n, cout, cin, k, k, generator=g) / math.sqrt(kk))
+    wps = F.pad(wts.flatten(2), (0, 32 - kk)).to(torch.bfloat16).to(DEV).contiguous()
+    y4 = ops.stem_mma_fwd(x.to(DEV), wps, k, stride, pad)
+    ref4 = torch.cat([F.conv2d(xb[i:i + 1], wts[i], None, stride, pad) for i in range(n)])
+    assert_close_bf16(to_nchw(y4), ref4, "stem_mma per-sample kernels")
+    # weight gradient
+    dy = bf16_round(torch.randn(ref.shape, generator=g))
+    dwp = ops.stem_mma_wgrad(x.to(DEV), nhwc(dy), k, stride, pad)
+    ops.check_device()
+    ref_dw = torch.nn.grad.conv2d_weight(xb, wt.shape, dy, stride, pad)
+    assert rel_l2(dwp[:, :kk].reshape(wt.shape).cpu(), ref_dw) < 2e-3
+    assert torch.all(dwp[:, kk:] == 0)
+    dws = ops.stem_mma_wgrad(x.to(DEV), nhwc(dy), k, stride, pad, per_sample=True)
+    ops.check_device()
+    for i in range(n):
+        ref_i = torch.nn.grad.conv2d_weight(xb[i:i + 1], wt.shape, dy[i:i + 1], stride, pad)
+        assert rel_l2(dws[i, :, :kk].reshape(wt.shape).cpu(), ref_i) < 2e-3, f"per-sample wgrad {i}"
+    # accumulation into a caller-provided buffer
+    acc = dwp.clone()
+    ops.stem_mma_wgrad(x.to(DEV), nhwc(dy), k, stride, pad, out=acc)
+    assert rel_l2(acc.cpu(), 2 * dwp.cpu()) < 1e-5
+
+
 @pytest.mark.parametrize("loss_fn", ["ciou", "mse"])
 @pytest.mark.parametrize("grid", [20, 37])
 def test_fused_yolo_head_loss_matches_batched_torch_loss(lib, loss_fn, grid):
