@@ -247,6 +247,63 @@ __device__ __forceinline__ void mma_issue_loop(const IgemmParams& P, uint32_t ri
   }
 }
 
+// Halo mode: the A operand of every k-block of a tile is a shifted view of the tile's halo box (P.kb_aoff), stages
+// carry the weight tile only (or nothing, when the weights are resident).
+template <int KSTEPS>
+__device__ __forceinline__ void mma_issue_loop_halo(const IgemmParams& P, uint32_t halo_base, uint32_t ring_base,
+                                                    uint32_t bres_base, uint32_t full_bar, uint32_t empty_bar,
+                                                    uint32_t afull_bar, uint32_t aempty_bar, uint32_t tfull_bar,
+                                                    uint32_t tempty_bar, uint32_t tmem_base, int b_bytes, int num_kb,
+                                                    volatile uint32_t* dead) {
+  const uint32_t idesc = make_idesc_bf16(P.block_n, 0, 0, 128);
+  const uint32_t a_layout = P.halo_row_bytes == 128 ? 2u : 4u;
+  const uint32_t b_layout = (KSTEPS == 4) ? 2u : 4u;
+  const bool bres = P.bres_bytes > 0;
+  const uint64_t a0 = make_smem_desc(halo_base, 16, (uint32_t)P.halo_sbo, a_layout);
+  const uint64_t b0 = make_smem_desc(bres ? bres_base : ring_base, 16, 8u * (uint32_t)(KSTEPS * 16) * 2u, b_layout);
+  const uint32_t b_step = (uint32_t)b_bytes >> 4;
+  const uint32_t abuf_step = (uint32_t)P.halo_buf_bytes >> 4;
+  const uint32_t last_stage = (uint32_t)P.stages - 1u, last_abuf = (uint32_t)P.halo_bufs - 1u;
+  uint32_t stage = 0, phase = 0, soff = 0;
+  uint32_t abuf = 0, aphase = 0, aoff = 0;
+  uint32_t acc = 0, acc_phase = 0;
+  const int iters = num_iters<false>(P);
+  for (int tl = 0; tl < iters; ++tl) {
+    const bool tr = P.trace && blockIdx.x == 0 && tl < P.trace_tiles;
+    if (tr) P.trace[tl * 16 + 2] = clock64();
+    mbar_wait(tempty_bar + 8u * acc, acc_phase ^ 1u, dead, P.watchdog, 0x2u);
+    if (tr) P.trace[tl * 16 + 3] = clock64();
+    mbar_wait(afull_bar + 8u * abuf, aphase, dead, P.watchdog, 0x400u);
+    if (tr) P.trace[tl * 16 + 13] = clock64();
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + acc * (uint32_t)kAccStride;
+    uint32_t accumulate = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      if (!bres) {
+        mbar_wait(full_bar + 8u * stage, phase, dead, P.watchdog, 0x4u);
+        tc_fence_after();
+      }
+      const uint64_t ad = a0 + (uint64_t)(aoff + P.kb_aoff[kb]);
+      const uint64_t bd = b0 + (uint64_t)(bres ? (uint32_t)kb * b_step : soff);
+#pragma unroll
+      for (int k = 0; k < KSTEPS; ++k) {
+        tc_mma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, accumulate);
+        accumulate = 1u;
+      }
+      if (!bres) {
+        tc_commit(empty_bar + 8u * stage);
+        if (stage == last_stage) { stage = 0; phase ^= 1u; soff = 0; } else { ++stage; soff += b_step; }
+      }
+    }
+    tc_commit(aempty_bar + 8u * abuf);
+    tc_commit(tfull_bar + 8u * acc);
+    if (tr) P.trace[tl * 16 + 4] = clock64();
+    if (abuf == last_abuf) { abuf = 0; aphase ^= 1u; aoff = 0; } else { ++abuf; aoff += abuf_step; }
+    acc ^= 1u;
+    if (acc == 0) acc_phase ^= 1u;
+  }
+}
+
 // kKind selects the epilogue the instance is compiled with: 0 = batch statistics (training forward), 1 = affine
 // without activation (data gradients), 2 = affine with any activation (fused inference epilogues), 3 = detection
 // head.  One kernel holding all of them was 160 KB of code, and the step time follows the kernel's code size.
@@ -267,7 +324,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   const int lane = threadIdx.x & 31;
 
   const uint32_t rank = kTwo ? cluster_ctarank() : 0u;
-  const int a_bytes = 128 * P.block_k * 2;             // smem reserved for A per stage
+  const bool halo = !kTwo && P.halo != 0;
+  const int a_bytes = halo ? 0 : 128 * P.block_k * 2;  // smem reserved for A per stage (halo mode: A has its own buffers)
   const int b_bytes = (kTwo ? P.block_n / 2 : P.block_n) * P.block_k * 2;   // this CTA's part of the B tile
   // Weights small enough to stay in shared memory for the whole kernel (thin layers, 1x1 convs up to 256->128) are
   // loaded once: [resident B: one tile per k-block][stages x A]; otherwise every stage carries its B tile.
@@ -275,7 +333,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   const int stage_bytes = bres ? a_bytes : a_bytes + b_bytes;
   const int a_tx = P.tile_w * P.tile_h * P.block_k * 2;  // bytes the A box actually delivers
   uint8_t* ring = smem + P.bres_bytes;                   // pipeline stages (1024-aligned: tiles are multiples of 1 KB)
-  uint8_t* staging = ring + (size_t)P.stages * stage_bytes;  // output staging
+  uint8_t* halo_buf = ring + (size_t)P.stages * stage_bytes; // halo mode: A buffers (1024-aligned like the stages)
+  uint8_t* staging = halo_buf + (halo ? (size_t)P.halo_bufs * P.halo_buf_bytes : 0);  // output staging
   uint8_t* ctrl = staging + P.staging_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* empty_bar = full_bar + kMaxStages;
@@ -286,6 +345,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   volatile uint32_t* dead = tmem_ptr + 1;
   // residual-tile loads of the warp-private epilogues: one barrier per (epilogue warp, staging buffer)
   uint64_t* rres_bar = reinterpret_cast<uint64_t*>(ctrl + 8 * (2 * kMaxStages + 5) + 16);
+  uint64_t* afull_bar = rres_bar + 2 * kEpiWarps;          // halo mode: one full / empty pair per A buffer
+  uint64_t* aempty_bar = afull_bar + kMaxHaloBufs;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(smem_u32(&rres_bar[i]), 1);
@@ -294,6 +355,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     mbar_init(smem_u32(bres_bar), 1);
+    for (int b = 0; b < kMaxHaloBufs; ++b) {
+      mbar_init(smem_u32(&afull_bar[b]), 1);
+      mbar_init(smem_u32(&aempty_bar[b]), 1);
+    }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);
       // arrivals per tile: all 8 epilogue warps (of both CTAs of a pair, on the leader's barrier), or only the 4
@@ -326,7 +391,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     // k-block g (counted across this CTA's tiles) belongs to producer warp g % prod_warps; `stages` is a
     // multiple of prod_warps, so a pipeline stage is always refilled by the same warp (program order keeps the
     // two uses of its empty barrier apart).
-    if (warp < P.prod_warps && elect_one()) {
+    if (halo && warp == kProdWarps - 1) {
+      // halo mode: this warp loads the tiles' A boxes (one per channel sub-block), the others the weight tiles
+      if (elect_one()) {
+        uint32_t abuf = 0, aphase = 0;
+        for (int it = 0, tile; (tile = tile_at<kTwo>(P, it, rank)) >= 0; ++it) {
+          const TileCoord tc = decode_tile(P, tile);
+          mbar_wait<32>(smem_u32(&aempty_bar[abuf]), aphase ^ 1u, dead, P.watchdog, 0x800u);
+          const uint32_t fb = smem_u32(&afull_bar[abuf]);
+          mbar_arrive_expect_tx(fb, (uint32_t)(P.halo_subs * P.halo_tx));
+          uint8_t* dst = halo_buf + (size_t)abuf * P.halo_buf_bytes;
+          for (int sb = 0; sb < P.halo_subs; ++sb)
+            tma_load_5d(smem_u32(dst + (size_t)sb * P.halo_sub_bytes), &mapA, fb, sb * P.halo_box_c, tc.ow0 + P.halo_w0,
+                        P.halo_p0, tc.oh0 + P.halo_h0, tc.img);
+          if (++abuf == (uint32_t)P.halo_bufs) { abuf = 0; aphase ^= 1u; }
+        }
+      }
+    } else if (warp < P.prod_warps && elect_one() && !(halo && bres && warp != 0)) {
       const int pw = P.prod_warps;
       const int kcpt = P.kc_per_tap;
       int it = 0, tile = tile_at<kTwo>(P, 0, rank);
@@ -344,7 +425,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           for (int kc = 0; kc < kcpt; ++kc, ++kbi)
             tma_load_3d(smem_u32(smem + (size_t)kbi * b_bytes), &mapB, bb, P.taps[t].w_koff + kc * P.block_k, 0, 0);
       }
-      while (true) {
+      while (!(halo && bres)) {        // halo mode with resident weights: nothing left to stream
         while (kb >= num_kb) { kb -= num_kb; tile = tile_at<kTwo>(P, ++it, rank); if (tile < 0) break; }
         if (tile < 0) break;
         if (tile != cur_tile) { tc = decode_tile(P, tile); cur_tile = tile; }
@@ -360,6 +441,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                           tc.img);
           tma_load_3d_2sm(smem_u32(sa + a_bytes), &mapB, fb, tap.w_koff + kc * P.block_k,
                           tc.n0 + (int)rank * (P.block_n / 2), 0);
+        } else if (halo) {
+          mbar_arrive_expect_tx(fb, (uint32_t)b_bytes);
+          tma_load_3d(smem_u32(sa), &mapB, fb, tap.w_koff + kc * P.block_k, tc.n0, P.w_batch > 1 ? tc.img : 0);
         } else {
           mbar_arrive_expect_tx(fb, (uint32_t)(bres ? a_tx : a_tx + b_bytes));
           tma_load_5d(smem_u32(sa), &mapA, fb, tap.c_off + kc * P.block_k, tc.ow0 + tap.dw, tap.p, tc.oh0 + tap.dh,
@@ -383,7 +467,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         mbar_wait(smem_u32(bres_bar), 0, dead, P.watchdog, 0x80u);      // resident weights have landed
         tc_fence_after();
       }
-      if (P.block_k == 64) mma_issue_loop<4, kTwo>(P, smem_u32(ring), smem_u32(smem), smem_u32(full_bar), smem_u32(empty_bar),
+      if (halo) {
+        if (P.block_k == 64)
+          mma_issue_loop_halo<4>(P, smem_u32(halo_buf), smem_u32(ring), smem_u32(smem), smem_u32(full_bar), smem_u32(empty_bar),
+                                 smem_u32(afull_bar), smem_u32(aempty_bar), smem_u32(tfull_bar), smem_u32(tempty_bar),
+                                 tmem_base, b_bytes, num_kb, dead);
+        else
+          mma_issue_loop_halo<2>(P, smem_u32(halo_buf), smem_u32(ring), smem_u32(smem), smem_u32(full_bar), smem_u32(empty_bar),
+                                 smem_u32(afull_bar), smem_u32(aempty_bar), smem_u32(tfull_bar), smem_u32(tempty_bar),
+                                 tmem_base, b_bytes, num_kb, dead);
+      } else if (P.block_k == 64) mma_issue_loop<4, kTwo>(P, smem_u32(ring), smem_u32(smem), smem_u32(full_bar), smem_u32(empty_bar),
                                                    smem_u32(tfull_bar), smem_u32(tempty_bar), tmem_base, a_bytes, b_bytes,
                                                    stage_bytes, num_kb, dead);
       else mma_issue_loop<2, kTwo>(P, smem_u32(ring), smem_u32(smem), smem_u32(full_bar), smem_u32(empty_bar),
@@ -482,7 +575,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             const uint32_t bar = smem_u32(&rres_bar[ew * 2 + b]);
             if (P.epi_mode == 1) {
               mbar_arrive_expect_tx(bar, (uint32_t)(32 * row_bytes));
-              tma_load_5d(smem_u32(wbuf), &mapRes, bar, cs, tc.ow0 + q_ow, 0, tc.oh0 + q_oh, tc.img);
+              const int pl = P.out_cspan ? cs / P.out_cspan : 0;
+              tma_load_5d(smem_u32(wbuf), &mapRes, bar, cs - pl * P.out_cspan, tc.ow0 + q_ow, pl, tc.oh0 + q_oh, tc.img);
             } else {
               mbar_arrive_expect_tx(bar, (uint32_t)(rows_here * row_bytes));
               tma_load_3d(smem_u32(wbuf), use_tail ? &mapResTail : &mapRes, bar, cs, tc.oh0 * P.wo + q * 32, tc.img);
@@ -533,6 +627,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         const float* shift = P.shift ? P.shift + (size_t)tc.img * P.shift_sn : nullptr;
         if (tr) P.trace[tl * 16 + 5] = clock64();
         // this warp's first slab of the tile: buffer + residual load before the accumulator is awaited
+        // (fused parity planes: the residual always arrives by TMA — launch_igemm guarantees it — so res_px is unused)
         const int sl_first = single ? 0 : half;
         uint8_t* wbuf_next = nullptr;
         uint8_t* wbuf_first = wbuf_pending ? wbuf_pending
@@ -579,7 +674,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
               if (lane == 0) {
                 if (P.epi_mode == 1) {
                   if (rows_here > 0) {
-                    tma_store_5d(&mapOut, smem_u32(wbuf), cs, tc.ow0 + q_ow, 0, tc.oh0 + q_oh, tc.img);
+                    const int pl = P.out_cspan ? cs / P.out_cspan : 0;
+                    tma_store_5d(&mapOut, smem_u32(wbuf), cs - pl * P.out_cspan, tc.ow0 + q_ow, pl, tc.oh0 + q_oh, tc.img);
                     tma_store_commit();
                   }
                 } else if (rows_here > 0) {
@@ -672,7 +768,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           }
           asm volatile("bar.sync 3, 256;" ::: "memory");
           if (e_tid == 0) {
-            tma_store_5d(&mapOut, smem_u32(sbuf), cs, tc.ow0, 0, tc.oh0, tc.img);
+            const int pl = P.out_cspan ? cs / P.out_cspan : 0;
+            tma_store_5d(&mapOut, smem_u32(sbuf), cs - pl * P.out_cspan, tc.ow0, pl, tc.oh0, tc.img);
             tma_store_commit();
           }
           if (kKind == 0) {
@@ -770,10 +867,10 @@ int encode_tensor_map(CUtensorMap* m, void* base, int rank, const uint64_t* dims
 }
 
 // 5-D activation map.  parity == 0: [C, W, 1, H, N];  parity == 1: [ld + C, W/2, 2, H/2, N].
-int make_act_map(CUtensorMap* m, const uavdet_act* x, int parity, int box_c, int box_w, int box_h) {
+int make_act_map(CUtensorMap* m, const uavdet_act* x, int parity, int box_c, int box_w, int box_h, int box_p) {
   const uint64_t eb = 2;
   uint64_t dims[5], str[4];
-  uint32_t box[5] = {(uint32_t)box_c, (uint32_t)box_w, 1u, (uint32_t)box_h, 1u};
+  uint32_t box[5] = {(uint32_t)box_c, (uint32_t)box_w, (uint32_t)box_p, (uint32_t)box_h, 1u};
   if (!parity) {
     dims[0] = x->c; dims[1] = x->w; dims[2] = 1; dims[3] = x->h; dims[4] = x->n;
     str[0] = (uint64_t)x->ld * eb;
@@ -797,9 +894,9 @@ void get_trace(long long** ptr, int* tiles) { *ptr = g_trace; *tiles = g_trace_t
 // 5-D output map for the TMA-store epilogue: [C, Wo, 1, Ho, N] with arbitrary pixel strides (elements), so the
 // same code writes plain NHWC tensors, channel slices and the parity planes of a stride-2 data gradient.
 int make_out_map(CUtensorMap* m, void* ptr, int n, int ho, int wo, int c, long long sn, long long sh, long long sw,
-                 int box_c, int box_w, int box_h) {
-  uint64_t dims[5] = {(uint64_t)c, (uint64_t)wo, 1, (uint64_t)ho, (uint64_t)n};
-  uint64_t str[4] = {(uint64_t)sw * 2, (uint64_t)sh * 2, (uint64_t)sh * 2, (uint64_t)sn * 2};
+                 int box_c, int box_w, int box_h, int planes, long long sp) {
+  uint64_t dims[5] = {(uint64_t)c, (uint64_t)wo, (uint64_t)planes, (uint64_t)ho, (uint64_t)n};
+  uint64_t str[4] = {(uint64_t)sw * 2, (uint64_t)(planes > 1 ? sp : sh) * 2, (uint64_t)sh * 2, (uint64_t)sn * 2};
   uint32_t box[5] = {(uint32_t)box_c, (uint32_t)box_w, 1u, (uint32_t)box_h, 1u};
   return encode_tensor_map(m, ptr, 5, dims, str, box, box_c * 2);
 }
@@ -895,6 +992,90 @@ static int two_cta_mode() {
   return v;
 }
 
+// UAVDET_IGEMM_HALO: 0 = never, 1 (default) = where it measured faster (below), 2 = the same rule without the
+// cout >= cin condition, 3 = wherever it is legal.
+// Measured on B200 (tools/trace_halo.py, batch 32 / 16 at 320x320): with the halo box the A operand is in shared memory
+// ~80 cycles after the tile starts, yet a tile still takes ~2,600 cycles of MMA time on the thin layers — the tensor
+// core needs ~72 cycles for every M128 x N x K16 instruction whose N is <= 128 (it re-reads the 4 KB A slice per
+// instruction) and ~144 when the rows are 64 bytes (SWIZZLE_64B, 32-channel layers).  So 32 -> 64 and 64 -> 32 3x3 layers
+// are bound by instruction count, not by L2 -> SM traffic, and the halo box only pays where the per-tap boxes were
+// the slower side: 64 input channels, >= 64 output channels, stride 1, one weight matrix (64 -> 64 at 320x320: 228 ->
+// 197 us; 64 -> 128 at 160x160 inside the training step: 141 -> 104 us; stride-2 and per-sample-weight layers lost
+// 7-35 %: two boxes per tile, and weight tiles that travel alone in 4 KB stages; 128 -> 64 data gradients at 160x160
+// lost 20 %, 128 -> 128 / 256 -> 256 layers gained — hence cout >= cin).
+static int halo_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UAVDET_IGEMM_HALO");
+    v = e ? atoi(e) : 1;
+    if (v < 0 || v > 3) v = 1;
+  }
+  return v;
+}
+
+// Halo-mode geometry of a launch (see IgemmParams): decides the box, the per-k-block A offsets and forces the 8 x 16
+// tile.  Returns false (P untouched except the halo fields) when the layer does not qualify.
+static bool plan_halo(IgemmParams& P, const uavdet_act* a_src, int parity, int w_batch) {
+  P.halo = 0;
+  const int mode = halo_mode();
+  if (mode == 0 || P.epi == UAVDET_EPI_HEAD || P.num_taps < 4) return false;
+  if (P.wo % 8 != 0 || P.ho < 8) return false;
+  const int C = a_src->c;
+  if (mode == 1 && P.cout < C) return false;
+  if (mode <= 2 && (C % 64 != 0 || parity || w_batch != 1 || P.block_n < 64)) return false;
+  if (parity && a_src->ld != C) return false;           // the two pixels of a parity pair must be contiguous
+  const int span = parity ? 2 * C : C;
+  const int box_c = span < 64 ? span : 64;
+  if (span % box_c != 0) return false;
+  const int subs = span / box_c;
+  const int num_kb = P.num_taps * P.kc_per_tap;
+  if (num_kb > kMaxKb) return false;
+  int dw0 = 1 << 30, dw1 = -(1 << 30), dh0 = 1 << 30, dh1 = -(1 << 30), p0 = 1 << 30, p1 = -(1 << 30);
+  for (int t = 0; t < P.num_taps; ++t) {
+    const ConvTap& tp = P.taps[t];
+    dw0 = tp.dw < dw0 ? tp.dw : dw0; dw1 = tp.dw > dw1 ? tp.dw : dw1;
+    dh0 = tp.dh < dh0 ? tp.dh : dh0; dh1 = tp.dh > dh1 ? tp.dh : dh1;
+    p0 = tp.p < p0 ? tp.p : p0; p1 = tp.p > p1 ? tp.p : p1;
+  }
+  const int tile_w = 8, tile_h = 16;
+  const int hw_w = tile_w + dw1 - dw0, hw_p = p1 - p0 + 1, hw_h = tile_h + dh1 - dh0;
+  if (hw_w > 256 || hw_h > 256) return false;
+  const int row_bytes = box_c * 2;
+  const long long rows = (long long)hw_w * hw_p * hw_h;
+  const long long sub_bytes = (rows * row_bytes + 1023) / 1024 * 1024;
+  {
+    // two A buffers, two weight stages, one staging set and the barriers must fit (launch_igemm hands out the rest)
+    const long long b_tile = (long long)P.block_n * P.block_k * 2;
+    const long long staging1 = 2ll * 128 * ((P.block_n % 64 == 0) ? 64 : 32) * 2;
+    if (2 * sub_bytes * subs + 2 * b_tile + staging1 + 1024 > 227 * 1024) return false;
+  }
+  for (int t = 0; t < P.num_taps; ++t) {
+    const ConvTap& tp = P.taps[t];
+    for (int kc = 0; kc < P.kc_per_tap; ++kc) {
+      const int cpos = tp.c_off + kc * P.block_k;
+      if (cpos < 0 || cpos + P.block_k > span) return false;
+      const int sub = cpos / box_c, inrow = cpos % box_c;
+      if (inrow + P.block_k > box_c) return false;
+      const long long row = ((long long)(tp.dh - dh0) * hw_p + (tp.p - p0)) * hw_w + (tp.dw - dw0);
+      P.kb_aoff[t * P.kc_per_tap + kc] = (uint32_t)((sub * sub_bytes + row * row_bytes + inrow * 2) >> 4);
+    }
+  }
+  P.halo = 1;
+  P.halo_subs = subs;
+  P.halo_sub_bytes = (int)sub_bytes;
+  P.halo_buf_bytes = (int)(sub_bytes * subs);
+  P.halo_tx = (int)(rows * row_bytes);
+  P.halo_row_bytes = row_bytes;
+  P.halo_sbo = hw_p * hw_w * row_bytes;
+  P.halo_box_c = box_c;
+  P.halo_w0 = dw0; P.halo_p0 = p0; P.halo_h0 = dh0;
+  P.halo_bufs = 2;
+  P.tile_w = tile_w; P.tile_h = tile_h; P.epi_mode = 1;
+  // scratch for launch_igemm (box geometry of the A map)
+  P.tiles_w = hw_w; P.tiles_h = hw_h; P.n_tiles = hw_p;
+  return true;
+}
+
 static int pick_block_n(int cout) {
   if (cout <= 16) return 16;
   for (int bn = 256; bn >= 32; bn -= 32)
@@ -906,7 +1087,9 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
                  int w_batch, IgemmParams& P, cudaStream_t st, int w_batch_rows = 0) {
   if (w_batch_rows <= 0) w_batch_rows = w_rows;   // rows between the weight matrices of consecutive samples
   CUtensorMap mapA, mapB, mapOut, mapOutTail, mapRes, mapResTail;
-  int rc = make_act_map(&mapA, a_src, parity, P.block_k, P.tile_w, P.tile_h);
+  int rc;
+  if (plan_halo(P, a_src, parity, w_batch)) rc = make_act_map(&mapA, a_src, parity, P.halo_box_c, P.tiles_w, P.tiles_h, P.n_tiles);
+  else rc = make_act_map(&mapA, a_src, parity, P.block_k, P.tile_w, P.tile_h);
   if (rc) return rc;
   P.res_tma = 0;
   P.slab_w = (P.block_n % 64 == 0) ? 64 : 32;
@@ -917,13 +1100,16 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
     mapOutTail = mapA;
   } else if (P.epi_mode == 1) {
     const int bw = P.tile_w < 32 ? P.tile_w : 32;
-    rc = make_out_map(&mapOut, P.out, P.n_img, P.ho, P.wo, P.cout, P.out_sn, P.out_sh, P.out_sw, P.slab_w, bw, 32 / bw);
+    const int planes = P.out_cspan ? P.cout / P.out_cspan : 1;
+    const int map_c = P.out_cspan ? P.out_cspan : P.cout;
+    rc = make_out_map(&mapOut, P.out, P.n_img, P.ho, P.wo, map_c, P.out_sn, P.out_sh, P.out_sw, P.slab_w, bw, 32 / bw,
+                      planes, P.out_sp);
     if (rc) return rc;
     mapOutTail = mapOut;
-    if (P.res && res_tma_enabled()) {
+    if (P.res && (res_tma_enabled() || P.out_cspan)) {
       // the residual tile comes in through the same box as the result goes out
-      rc = make_out_map(&mapRes, const_cast<__nv_bfloat16*>(P.res), P.n_img, P.ho, P.wo, P.cout, P.res_sn, P.res_sh,
-                        P.res_sw, P.slab_w, bw, 32 / bw);
+      rc = make_out_map(&mapRes, const_cast<__nv_bfloat16*>(P.res), P.n_img, P.ho, P.wo, map_c, P.res_sn, P.res_sh,
+                        P.res_sw, P.slab_w, bw, 32 / bw, planes, P.res_sp);
       if (rc) return rc;
       mapResTail = mapRes;
       P.res_tma = 1;
@@ -954,8 +1140,9 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
       P.res_tma = 1;
     }
   } else {
-    rc = make_out_map(&mapOut, P.out, P.n_img, P.ho, P.wo, P.cout, P.out_sn, P.out_sh, P.out_sw, P.slab_w, P.tile_w,
-                      P.tile_h);
+    UAVDET_CHECK_ARG(!(P.out_cspan && P.res), "igemm: fused parity planes with a residual need a warp-private tile");
+    rc = make_out_map(&mapOut, P.out, P.n_img, P.ho, P.wo, P.out_cspan ? P.out_cspan : P.cout, P.out_sn, P.out_sh, P.out_sw,
+                      P.slab_w, P.tile_w, P.tile_h, P.out_cspan ? P.cout / P.out_cspan : 1, P.out_sp);
     if (rc) return rc;
     mapOutTail = mapOut;
   }
@@ -971,6 +1158,7 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
   bool two = two_cta_mode() != 0 && P.epi != UAVDET_EPI_HEAD && w_batch == 1 && P.block_n % 32 == 0 && P.block_n >= 64 &&
              P.cout % P.block_n == 0 && m_tiles >= 2 && !(P.epi_mode != 0 && P.block_n == P.slab_w);
   if (two && two_cta_mode() == 1) two = P.block_n >= 128 && k_blocks >= 9;
+  if (P.halo) two = false;
   {
     uint64_t dims[3] = {(uint64_t)k_total, (uint64_t)w_rows, (uint64_t)w_batch};
     uint64_t str[2] = {(uint64_t)k_total * 2, (uint64_t)k_total * 2 * w_batch_rows};
@@ -986,12 +1174,33 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
   const int a_stage = 128 * P.block_k * 2, b_tile = (two ? P.block_n / 2 : P.block_n) * P.block_k * 2;
   const long long b_total = (long long)P.num_taps * P.kc_per_tap * b_tile;
   P.bres_bytes = 0;
+  const int ctrl_bytes = 8 * (2 * kMaxStages + 5) + 64 + 8 * 2 * kEpiWarps + 8 * 2 * kMaxHaloBufs;   // + residual-load / halo barriers
+  const int max_smem = 227 * 1024;
+  const int staging1 = 2 * 128 * P.slab_w * 2;      // CTA-wide: 2 slabs; warp-private: 8 warps x 1 buffer
+  if (P.halo) {
+    // [resident weights | B stages] [A halo buffers] [staging] [barriers]
+    const long long fixed = ctrl_bytes + staging1 + 2ll * P.halo_buf_bytes;
+    if (w_batch == 1 && P.n_tiles == 1 && b_total + fixed <= max_smem && P.total_tiles > 2 * kNumSMs) P.bres_bytes = (int)b_total;
+    long long left = max_smem - fixed - P.bres_bytes;
+    UAVDET_CHECK_ARG(P.bres_bytes || left >= 2ll * b_tile, "igemm: halo tile does not fit shared memory");
+    const long long b_min = P.bres_bytes ? 0 : 4ll * b_tile;        // weight stages kept while the rest is handed out
+    P.epi_bufs = 1;
+    P.staging_bytes = staging1;
+    if (left - b_min >= P.halo_buf_bytes) { P.halo_bufs = 3; left -= P.halo_buf_bytes; }
+    if (left - b_min >= staging1) { P.epi_bufs = 2; P.staging_bytes = 2 * staging1; left -= staging1; }
+    if (P.halo_bufs == 3 && left - 2 * b_min >= P.halo_buf_bytes) { P.halo_bufs = 4; left -= P.halo_buf_bytes; }
+    int stages = 1;
+    P.prod_warps = 1;
+    if (!P.bres_bytes) {
+      stages = (int)(left / b_tile);
+      if (stages > kMaxStages) stages = kMaxStages;
+      if (stages >= 4) { P.prod_warps = 2; stages &= ~1; }
+    }
+    P.stages = stages;
+  } else {
   if (!two && w_batch == 1 && P.n_tiles == 1 && b_total <= 80 * 1024 && P.total_tiles > 2 * kNumSMs) P.bres_bytes = (int)b_total;
   const int stage_bytes = P.bres_bytes ? a_stage : a_stage + b_tile;
-  const int ctrl_bytes = 8 * (2 * kMaxStages + 5) + 64 + 8 * 2 * kEpiWarps;   // + the residual-load barriers
-  const int max_smem = 227 * 1024;
   const int avail = max_smem - P.bres_bytes;
-  const int staging1 = 2 * 128 * P.slab_w * 2;      // CTA-wide: 2 slabs; warp-private: 8 warps x 1 buffer
   P.epi_bufs = 1;
   P.staging_bytes = (P.epi == UAVDET_EPI_HEAD) ? 0 : staging1;
   if (P.epi_mode != 0 && (avail - ctrl_bytes - 2 * staging1) / stage_bytes >= 4) {
@@ -1005,6 +1214,7 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
   else if (stages >= 4) { P.prod_warps = 2; stages &= ~1; }
   else { P.prod_warps = 1; }
   P.stages = stages;
+  }
   P.watchdog = watchdog_word();
   get_trace(&P.trace, &P.trace_tiles);
   // Always request (almost) the whole shared memory so exactly one CTA is resident per SM:
@@ -1117,10 +1327,29 @@ extern "C" int uavdet_conv_fwd(const uavdet_act* x, const void* w_packed, int w_
   P.block_k = (c_blk % 64 == 0) ? 64 : 32;
   P.block_n = pick_block_n(cout);
   P.kc_per_tap = c_blk / P.block_k;
+  // 32-channel inputs read through the parity view: the two pixels of a pair are one contiguous 128-byte row, and the
+  // filter taps that read them are neighbours in the packed weight row — one K = 64 k-block (SWIZZLE_128B) replaces
+  // two K = 32 ones (SWIZZLE_64B rows cost the tensor core twice the cycles per instruction, see halo_mode()).
+  //   s2d:      blocks (i, j = 0) and (i, j = 1) of a tap;
+  //   stride 2: (kh, kw = 1 | 2) = [even | odd] pixel of column ow; (kh, kw = 0) = the odd pixel of column ow - 1, read
+  //             as channels 32..95 of the pair row — TMA zero-fills 64..95, which meets the weights of (kh, 1).
+  static const bool no_pair = getenv("UAVDET_IGEMM_NOPAIR") != nullptr;
+  const bool pair = !no_pair && parity && c_blk == 32 && x->ld == 32 && (s2d || (k == 3 && pad == 1));
+  if (pair) { P.block_k = 64; P.kc_per_tap = 1; }
   int nt = 0;
   for (int kh = 0; kh < k; ++kh)
     for (int kw = 0; kw < k; ++kw) {
-      if (s2d) {
+      if (pair && s2d) {
+        for (int i = 0; i < 2; ++i) {
+          UAVDET_CHECK_ARG(nt < kMaxTaps, "conv_fwd: too many taps");
+          P.taps[nt++] = ConvTap{0, kw - pad, i, kh - pad, ((kh * k + kw) * 4 + i * 2) * c_blk};
+        }
+      } else if (pair) {
+        if (kw == 2) continue;                         // merged into the kw = 1 block
+        const int th = kh - pad;
+        const int ph = ((th % 2) + 2) % 2;
+        P.taps[nt++] = ConvTap{kw == 0 ? 32 : 0, kw == 0 ? -1 : 0, ph, (th - ph) / 2, (kh * k + kw) * cin};
+      } else if (s2d) {
         for (int i = 0; i < 2; ++i)
           for (int j = 0; j < 2; ++j) {
             UAVDET_CHECK_ARG(nt < kMaxTaps, "conv_fwd: too many taps");
@@ -1228,6 +1457,49 @@ extern "C" int uavdet_conv_dgrad_s2d(const uavdet_act* dy, const void* w_packed_
                    "conv_dgrad_s2d: spatial sizes inconsistent");
   cudaStream_t st = (cudaStream_t)stream;
   const long long k_total = (long long)k * k * cout;
+  // All four parity planes read the same dy taps and differ only in their weight rows (q*c .. q*c+c of the [4c][K]
+  // matrix) and in where they store: ONE implicit GEMM with N = 4c whose output map takes the row parity as its third
+  // dimension and the column parity as the upper half of a 2c-channel pixel-pair row.  A quarter of the MMAs (the
+  // tensor core needs as long for an N = 32 instruction as for an N = 128 one) and dy is read once instead of four times.
+  static const bool no_fuse = getenv("UAVDET_IGEMM_NOFUSE_PLANES") != nullptr;
+  if (!no_fuse && dx->ld == c && (!epi || !epi->res || epi->res_ld == c)) {
+    IgemmParams P{};
+    P.n_img = dy->n;
+    P.ho = dx->h / 2;
+    P.wo = dx->w / 2;
+    P.cout = 4 * c;
+    P.block_k = (cout % 64 == 0) ? 64 : 32;
+    P.block_n = pick_block_n(4 * c);
+    P.kc_per_tap = cout / P.block_k;
+    int nt = 0;
+    for (int kh = 0; kh < k; ++kh)
+      for (int kw = 0; kw < k; ++kw) {
+        UAVDET_CHECK_ARG(nt < kMaxTaps, "conv_dgrad_s2d: too many taps");
+        P.taps[nt++] = ConvTap{0, pad - kw, 0, pad - kh, (kh * k + kw) * cout};
+      }
+    P.num_taps = nt;
+    uavdet_act dxv = *dx;
+    dxv.h = P.ho; dxv.w = P.wo;
+    int rc = fill_epilogue(P, epi, &dxv, 4 * c);
+    if (rc) return rc;
+    UAVDET_CHECK_ARG(P.epi == UAVDET_EPI_AFFINE, "conv_dgrad_s2d: only the AFFINE epilogue is supported");
+    const long long ld = dx->ld;
+    P.out = (__nv_bfloat16*)dx->ptr;
+    P.out_sw = 2 * ld; P.out_sh = 2ll * dx->w * ld; P.out_sn = (long long)dx->h * dx->w * ld;
+    P.out_cspan = 2 * c; P.out_sp = (long long)dx->w * ld;
+    if (P.res) {
+      const long long rl = epi->res_ld;
+      P.res_sw = 2 * rl; P.res_sh = 2ll * dx->w * rl; P.res_sn = (long long)dx->h * dx->w * rl;
+      P.res_sp = (long long)dx->w * rl;
+    }
+    if (P.shift && epi->shift_per_sample) P.shift_sn = 4 * c;
+    choose_tile(P.ho, P.wo, false, &P.tile_w, &P.tile_h, &P.epi_mode);
+    // a store slab (64 | 32 columns) must not straddle two row-parity planes; a shared (not per-sample) shift is [c]
+    const bool slab_ok = (2 * c) % ((P.block_n % 64 == 0) ? 64 : 32) == 0;
+    const bool shift_ok = !P.shift || epi->shift_per_sample;
+    if (!(P.res && P.epi_mode == 0) && slab_ok && shift_ok)
+      return launch_igemm(dy, 0, w_packed_t, 4 * c, (int)k_total, w_batch, P, st, 4 * c);
+  }
   for (int q = 0; q < 4; ++q) {
     const int pi = q >> 1, pj = q & 1;   // row / column parity of this channel block (DySOEM_SimFPN.py:71-73)
     IgemmParams P{};

@@ -7,6 +7,8 @@ namespace uavdet {
 
 constexpr int kMaxTaps = 36;   // 3x3 taps x 4 space-to-depth blocks, or 5x5
 constexpr int kMaxStages = 16;   // thin layers (12 KB stages) need many in flight to cover the memory latency
+constexpr int kMaxKb = 72;       // k-blocks (tap x channel chunk) of a halo-mode tile
+constexpr int kMaxHaloBufs = 4;
 
 // One filter tap = one shifted TMA box of the activation tensor map.
 struct ConvTap {
@@ -46,6 +48,21 @@ struct IgemmParams {
   int staging_bytes;    // shared memory reserved for output staging
   int prod_warps;       // active TMA producer warps (1 | 2 | 4), divides `stages`
   int bres_bytes;       // > 0: the whole weight matrix stays resident in shared memory (bytes); stages hold A only
+  // Halo mode (tile 8 wide x 16 tall): ONE TMA box per tile and channel sub-block brings every input pixel any filter
+  // tap of the tile touches; tap t reads it through a UMMA descriptor whose start is shifted by whole pixel rows and
+  // whose 8-row group stride (SBO) is one halo line — the tensor core applies the swizzle to the absolute address, as
+  // TMA did when it wrote the box (probed: umma_probe.cu).  Stages then carry B only.
+  int halo;             // 0 | 1
+  int halo_bufs;        // A buffers in flight (2..kMaxHaloBufs)
+  int halo_buf_bytes;   // bytes per buffer = halo_subs * halo_sub_bytes
+  int halo_subs;        // boxes per tile (channel sub-blocks of <= 64 channels)
+  int halo_sub_bytes;   // 1024-aligned bytes of one box
+  int halo_tx;          // bytes one box delivers
+  int halo_row_bytes;   // 64 | 128 (= swizzle span of the box)
+  int halo_sbo;         // bytes between the halo rows of consecutive tile rows
+  int halo_box_c;       // channels per box
+  int halo_w0, halo_p0, halo_h0;   // box origin relative to the tile origin (dims 1, 2, 3)
+  uint32_t kb_aoff[kMaxKb];        // per k-block: (byte offset of its first row inside the A buffer) >> 4
   FastDiv fd_n, fd_w, fd_h;   // dividers for the tile decode (n_tiles, tiles_w, tiles_h)
   int epi, act;
   const float* scale;
@@ -56,6 +73,11 @@ struct IgemmParams {
   long long res_sn, res_sh, res_sw;
   __nv_bfloat16* out;
   long long out_sn, out_sh, out_sw;
+  // Fused parity planes (data gradient through the space-to-depth gather): the N columns are [row parity][2c] and the
+  // output / residual maps use their third dimension for the row parity: column n -> (plane n / out_cspan, channel
+  // n % out_cspan of the pixel-pair row).  0 = ordinary output.
+  int out_cspan;
+  long long out_sp, res_sp;     // element stride between the row-parity planes
   float* sum;
   float* sumsq;
   float* head_obj;
@@ -69,9 +91,9 @@ struct IgemmParams {
 
 int encode_tensor_map(CUtensorMap* m, void* base, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
-int make_act_map(CUtensorMap* m, const uavdet_act* x, int parity, int box_c, int box_w, int box_h);
+int make_act_map(CUtensorMap* m, const uavdet_act* x, int parity, int box_c, int box_w, int box_h, int box_p = 1);
 int make_out_map(CUtensorMap* m, void* ptr, int n, int ho, int wo, int c, long long sn, long long sh, long long sw,
-                 int box_c, int box_w, int box_h);
+                 int box_c, int box_w, int box_h, int planes = 1, long long sp = 0);
 void choose_tile(int ho, int wo, bool dense_rows, int* tile_w, int* tile_h, int* epi_mode);
 int fill_plane(const IgemmParams& P, cudaStream_t st);
 void get_trace(long long** ptr, int* tiles);

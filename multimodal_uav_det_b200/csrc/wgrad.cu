@@ -316,8 +316,8 @@ extern "C" int uavdet_conv_wgrad(const uavdet_act* x, const uavdet_act* dy, int 
   UAVDET_CHECK_ARG(x->n == dy->n, "conv_wgrad: batch mismatch");
   const int parity = (stride == 2 || s2d) ? 1 : 0;
   if (parity) UAVDET_CHECK_ARG(x->h % 2 == 0 && x->w % 2 == 0, "conv_wgrad: stride-2/s2d needs even H,W");
-  const int c_blk = x->c, cin = s2d ? 4 * x->c : x->c, cout = dy->c;
-  UAVDET_CHECK_ARG(c_blk % 32 == 0 && cout % 32 == 0, "conv_wgrad: channels must be multiples of 32");
+  const int c_blk0 = x->c, cin = s2d ? 4 * x->c : x->c, cout = dy->c;
+  UAVDET_CHECK_ARG(c_blk0 % 32 == 0 && cout % 32 == 0, "conv_wgrad: channels must be multiples of 32");
   const int hin = s2d ? x->h / 2 : x->h, win = s2d ? x->w / 2 : x->w;
   UAVDET_CHECK_ARG((hin + 2 * pad - k) / stride + 1 == dy->h && (win + 2 * pad - k) / stride + 1 == dy->w,
                    "conv_wgrad: spatial sizes inconsistent");
@@ -325,6 +325,12 @@ extern "C" int uavdet_conv_wgrad(const uavdet_act* x, const uavdet_act* dy, int 
   P.n_img = x->n; P.ho = dy->h; P.wo = dy->w;
   P.cout = cout;
   P.a_width = (cout % 64 == 0) ? 64 : 32;
+  // 32-channel inputs read through the parity view: both pixels of a pair as ONE 64-channel block (see the forward
+  // kernel, igemm.cu) — half the MMAs, 128-byte rows.  Stride 2: the (kh, 0) tap reads channels 32..95 of the pair row;
+  // the zero-filled half adds zeros to the gradient columns of (kh, 1).
+  static const bool no_pair = getenv("UAVDET_IGEMM_NOPAIR") != nullptr;
+  const bool pair = !no_pair && parity && x->c == 32 && x->ld == 32 && (s2d || (k == 3 && pad == 1));
+  const int c_blk = pair ? 64 : c_blk0;
   P.b_width = (c_blk % 64 == 0) ? 64 : 32;
 
   // ---- filter taps, grouped into columns (same channel block / horizontal offset / row parity) ----
@@ -333,11 +339,21 @@ extern "C" int uavdet_conv_wgrad(const uavdet_act* x, const uavdet_act* dy, int 
   int nt = 0;
   for (int kh = 0; kh < k; ++kh)
     for (int kw = 0; kw < k; ++kw) {
-      if (s2d) {
+      if (pair && s2d) {
+        for (int i = 0; i < 2; ++i) {
+          UAVDET_CHECK_ARG(nt < kMaxTaps, "conv_wgrad: too many taps");
+          taps[nt++] = Tap{0, kw - pad, i, kh - pad, ((kh * k + kw) * 4 + i * 2) * c_blk0};
+        }
+      } else if (pair) {
+        if (kw == 2) continue;
+        const int th = kh - pad;
+        const int ph = ((th % 2) + 2) % 2;
+        taps[nt++] = Tap{kw == 0 ? 32 : 0, kw == 0 ? -1 : 0, ph, (th - ph) / 2, (kh * k + kw) * cin};
+      } else if (s2d) {
         for (int i = 0; i < 2; ++i)
           for (int j = 0; j < 2; ++j) {
             UAVDET_CHECK_ARG(nt < kMaxTaps, "conv_wgrad: too many taps");
-            taps[nt++] = Tap{j * x->ld, kw - pad, i, kh - pad, ((kh * k + kw) * 4 + (i * 2 + j)) * c_blk};
+            taps[nt++] = Tap{j * x->ld, kw - pad, i, kh - pad, ((kh * k + kw) * 4 + (i * 2 + j)) * c_blk0};
           }
       } else if (stride == 1) {
         UAVDET_CHECK_ARG(nt < kMaxTaps, "conv_wgrad: too many taps");

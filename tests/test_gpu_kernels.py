@@ -225,6 +225,74 @@ def test_conv_fwd_plain(lib, case):
     assert_close_bf16(to_nchw(y), ref, f"conv_fwd{case}")
 
 
+HALO_CASES = [
+    # n, cin, cout, k, stride, h, w — multi-tap layers with <= 64 input channels and an output width that is a multiple
+    # of 8 run in halo mode (one TMA box per tile, shifted UMMA descriptors per tap)
+    (2, 32, 64, 3, 1, 24, 40),      # rows past the image in the last tile row (24 = 16 + 8), resident weights
+    (3, 64, 32, 3, 1, 96, 64),      # more tiles than SMs x buffers: A-buffer ring wraps, SWIZZLE_128B rows
+    (2, 64, 128, 3, 1, 48, 48),     # weights streamed through the stage ring beside the halo buffers
+    (2, 32, 64, 3, 2, 64, 48),      # stride 2: parity box (both pixels of a pair in one 128-byte row, two row parities)
+    (2, 64, 128, 3, 2, 64, 64),     # stride 2, 64 channels: one box per pixel parity
+    (1, 32, 32, 5, 1, 32, 32),      # 25 taps
+    (1, 64, 64, 5, 2, 64, 64),
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_halo_mode_fwd_dgrad(lib, case):
+    """Forward (plain, statistics epilogue, affine + activation + residual) and data gradient (+ skip gradient) of the
+    thin multi-tap layers against F.conv2d / conv2d_input."""
+    ops = _ops(lib)
+    from multimodal_uav_det_b200._lib import EPI_STATS
+    n, cin, cout, k, stride, h, w = case
+    pad = k // 2
+    x, wt = _conv_case(*case, seed=77)
+    ref = F.conv2d(x, wt, None, stride, pad)
+    wp = ops.pack_weight(wt.to(DEV))
+    s1 = torch.zeros(cout, device=DEV)
+    s2 = torch.zeros(cout, device=DEV)
+    y = ops.conv_fwd(nhwc(x), wp, cout, k, stride, pad, epi=EPI_STATS, sum_=s1, sumsq=s2)
+    ops.check_device()
+    assert_close_bf16(to_nchw(y), ref, f"halo fwd{case}")
+    yr = to_nchw(y)
+    torch.testing.assert_close(s1.cpu(), yr.sum(dim=(0, 2, 3)), rtol=2e-3, atol=5e-2)
+    torch.testing.assert_close(s2.cpu(), (yr * yr).sum(dim=(0, 2, 3)), rtol=2e-3, atol=5e-2)
+    g = torch.Generator().manual_seed(78)
+    res = bf16_round(torch.randn(ref.shape, generator=g))
+    scale = torch.rand(cout, generator=g) + 0.5
+    shift = torch.rand(cout, generator=g) - 0.5
+    y2 = ops.conv_fwd(nhwc(x), wp, cout, k, stride, pad, act="leaky", scale=scale.to(DEV), shift=shift.to(DEV),
+                      res=nhwc(res))
+    ref2 = F.leaky_relu(ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1), 0.1) + res
+    assert_close_bf16(to_nchw(y2), ref2, f"halo fwd affine{case}")
+    # data gradient of the same layer: A = dy (cout channels), taps flipped, stride 2 as four parity planes
+    if cout <= 64:
+        dy = bf16_round(torch.randn(ref.shape, generator=g))
+        skip = bf16_round(torch.randn(x.shape, generator=g))
+        refd = torch.nn.grad.conv2d_input(x.shape, wt, dy, stride, pad) + skip
+        dx = ops.conv_dgrad(nhwc(dy), ops.pack_weight(wt.to(DEV), transposed=True), cin, k, stride, pad, (h, w),
+                            res=nhwc(skip))
+        ops.check_device()
+        assert_close_bf16(to_nchw(dx), refd, f"halo dgrad{case}")
+
+
+def test_conv_halo_mode_space_to_depth_per_sample(lib):
+    """DynamicSOEM at a shape with many tiles: the space-to-depth gather (36 taps over a two-parity box) with one
+    kernel per sample, and its data gradient."""
+    from oracle import oracle as O
+    ops = _ops(lib)
+    n, c, h, w, cout = 3, 32, 96, 64, 64
+    g = torch.Generator().manual_seed(113)
+    x = bf16_round(torch.randn(n, c, h, w, generator=g))
+    wts = bf16_round(torch.randn(n, cout, 4 * c, 3, 3, generator=g) / math.sqrt(36 * c))
+    xs = O.space_to_depth2(x)
+    ref = torch.cat([F.conv2d(xs[i:i + 1], wts[i], None, 1, 1) for i in range(n)])
+    wp = torch.stack([ops.pack_weight(wts[i].to(DEV)) for i in range(n)]).contiguous()
+    y = ops.conv_fwd(nhwc(x), wp, cout, 3, 1, 1, s2d=True, w_batch=n)
+    ops.check_device()
+    assert_close_bf16(to_nchw(y), ref, "halo s2d per-sample")
+
+
 def test_pack_weight_layouts(lib):
     ops = _ops(lib)
     wt = torch.randn(8, 6, 3, 3)
@@ -669,7 +737,7 @@ def _s2d(x):
 
 
 @pytest.mark.parametrize("per_sample", [False, True])
-@pytest.mark.parametrize("c,cout,hw", [(32, 64, 32), (64, 128, 16), (32, 32, 24)])
+@pytest.mark.parametrize("c,cout,hw", [(32, 64, 32), (64, 128, 16), (32, 32, 24), (32, 64, 96), (128, 256, 16), (64, 64, 40)])
 def test_conv_dgrad_s2d_matches_autograd(lib, per_sample, c, cout, hw):
     """Data gradient through the fused space-to-depth conv (DySOEM_SimFPN.py:71-91) incl. the skip-path
     residual and the per-sample pooled-attention shift, against autograd of the materialised formulation."""
