@@ -992,8 +992,8 @@ static int two_cta_mode() {
   return v;
 }
 
-// UAVDET_IGEMM_HALO: 0 = never, 1 (default) = where it measured faster (below), 2 = the same rule without the
-// cout >= cin condition, 3 = wherever it is legal.
+// UAVDET_IGEMM_HALO: 0 = never, 1 (default) = where it measured faster (below), 2 = the same rule for any multiple of
+// 64 input channels, 3 = wherever it is legal.
 // Measured on B200 (tools/trace_halo.py, batch 32 / 16 at 320x320): with the halo box the A operand is in shared memory
 // ~80 cycles after the tile starts, yet a tile still takes ~2,600 cycles of MMA time on the thin layers — the tensor
 // core needs ~72 cycles for every M128 x N x K16 instruction whose N is <= 128 (it re-reads the 4 KB A slice per
@@ -1002,7 +1002,7 @@ static int two_cta_mode() {
 // the slower side: 64 input channels, >= 64 output channels, stride 1, one weight matrix (64 -> 64 at 320x320: 228 ->
 // 197 us; 64 -> 128 at 160x160 inside the training step: 141 -> 104 us; stride-2 and per-sample-weight layers lost
 // 7-35 %: two boxes per tile, and weight tiles that travel alone in 4 KB stages; 128 -> 64 data gradients at 160x160
-// lost 20 %, 128 -> 128 / 256 -> 256 layers gained — hence cout >= cin).
+// lost 20 %, 128 -> 128 at 160x160 lost 9 %, 256 -> 256 at 80x80 gained 3 % — hence 64 input channels only).
 static int halo_mode() {
   static int v = -1;
   if (v < 0) {
@@ -1021,7 +1021,7 @@ static bool plan_halo(IgemmParams& P, const uavdet_act* a_src, int parity, int w
   if (mode == 0 || P.epi == UAVDET_EPI_HEAD || P.num_taps < 4) return false;
   if (P.wo % 8 != 0 || P.ho < 8) return false;
   const int C = a_src->c;
-  if (mode == 1 && P.cout < C) return false;
+  if (mode == 1 && C != 64) return false;
   if (mode <= 2 && (C % 64 != 0 || parity || w_batch != 1 || P.block_n < 64)) return false;
   if (parity && a_src->ld != C) return false;           // the two pixels of a parity pair must be contiguous
   const int span = parity ? 2 * C : C;

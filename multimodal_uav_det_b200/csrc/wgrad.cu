@@ -57,6 +57,7 @@ struct WgradParams {
   int koff[kMaxTaps];               // K offset of every tap inside the packed weight row, column-major order
   int tap_off[kMaxTaps];            // smem byte offset (inside a stage) of the first row each tap reads
   int tap_lbo[kMaxTaps];            // bytes between the channel blocks of that tap's box
+  int merge_taps;                   // 1: one MMA per column and K step (taps as N blocks), where a tap is one channel block
 };
 
 struct WgIssue {
@@ -88,6 +89,33 @@ __device__ __forceinline__ void wgrad_issue(const WgIssue& is, const uint64_t (&
       }
     }
     if (kTwo) tc_commit_2sm(is.empty_bar + 8u * (uint32_t)stage, 3); else tc_commit(is.empty_bar + 8u * (uint32_t)stage);
+    soff += is.stage_step;
+    if (++stage == is.stages) { stage = 0; phase ^= 1u; soff = 0; }
+  }
+}
+
+// The same loop with the taps of a column merged into ONE instruction per K step: the taps of a column read one box at
+// starts tile_w rows apart, which is exactly the layout of an MN-major operand whose N blocks (one per tap, cin_blk
+// channels = one swizzle row each) lie LBO = tile_w rows apart.  The tensor core takes as long for an N = 32 instruction
+// as for an N = 96 one (it is bound by re-reading the dY slice), so a 3x3 layer with <= 64 input channels issues a
+// third of the instructions.  NG = number of columns (instructions per K step).
+constexpr int kMaxGroups = 8;
+template <int NG>
+__device__ __forceinline__ void wgrad_issue_merged(const WgIssue& is, const uint64_t (&gd)[kMaxGroups],
+                                                   const uint32_t (&gcol)[kMaxGroups], const uint32_t (&gidesc)[kMaxGroups]) {
+  int stage = 0;
+  uint32_t phase = 0, soff = 0;
+  for (int kb = 0; kb < is.num_kb; ++kb) {
+    mbar_wait(is.full_bar + 8u * (uint32_t)stage, phase, is.dead, is.watchdog, 0x20u);
+    tc_fence_after();
+    for (int ks = 0; ks < is.ksteps; ++ks) {
+      const uint64_t ad = is.a0 + (uint64_t)(soff + ks * is.a_step);
+      const uint64_t boff = (uint64_t)(soff + ks * is.b_step);
+      const uint32_t accum = (kb | ks) != 0 ? 1u : 0u;
+#pragma unroll
+      for (int i = 0; i < NG; ++i) tc_mma_bf16(is.tmem_base + gcol[i], ad, gd[i] + boff, gidesc[i], accum);
+    }
+    tc_commit(is.empty_bar + 8u * (uint32_t)stage);
     soff += is.stage_step;
     if (++stage == is.stages) { stage = 0; phase ^= 1u; soff = 0; }
   }
@@ -231,6 +259,29 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ 
       is.a0 = a0; is.a_step = a_step; is.b_step = b_step; is.stage_step = stage_step;
       is.tmem_base = tmem_base; is.cin_blk = (uint32_t)P.cin_blk; is.idesc = idesc;
       is.dead = dead; is.watchdog = P.watchdog;
+      // one instruction per column where every tap is a single channel block (see wgrad_issue_merged)
+      bool merged = !kTwo && P.merge_taps && b_blocks == 1 && ncol <= kMaxGroups;
+      for (int c = 0; c < ncol && merged; ++c) merged = P.cols[col0 + c].nv * P.cin_blk <= 256;
+      if (merged) {
+        uint64_t gd[kMaxGroups];
+        uint32_t gcol[kMaxGroups], gidesc[kMaxGroups];
+#pragma unroll
+        for (int c = 0; c < kMaxGroups; ++c) {
+          gd[c] = 0ull; gcol[c] = 0u; gidesc[c] = 0u;
+          if (c < ncol) {
+            const WgCol col = P.cols[col0 + c];
+            gd[c] = make_smem_desc(sa0 + (uint32_t)P.tap_off[col.tap0], (uint32_t)(P.tile_w * b_row), 8 * b_row, b_layout);
+            gcol[c] = (uint32_t)((col.tap0 - t0) * P.cin_blk);
+            gidesc[c] = make_idesc_bf16(col.nv * P.cin_blk, 1, 1, 128);
+          }
+        }
+        switch (ncol) {
+          case 1: wgrad_issue_merged<1>(is, gd, gcol, gidesc); break;  case 2: wgrad_issue_merged<2>(is, gd, gcol, gidesc); break;
+          case 3: wgrad_issue_merged<3>(is, gd, gcol, gidesc); break;  case 4: wgrad_issue_merged<4>(is, gd, gcol, gidesc); break;
+          case 5: wgrad_issue_merged<5>(is, gd, gcol, gidesc); break;  case 6: wgrad_issue_merged<6>(is, gd, gcol, gidesc); break;
+          case 7: wgrad_issue_merged<7>(is, gd, gcol, gidesc); break;  default: wgrad_issue_merged<8>(is, gd, gcol, gidesc); break;
+        }
+      } else
       switch (nslots) {     // one specialisation per tap count: only live MMAs in the instruction stream
         case 1: wgrad_issue<1, kTwo>(is, bd); break;    case 2: wgrad_issue<2, kTwo>(is, bd); break;
         case 3: wgrad_issue<3, kTwo>(is, bd); break;    case 4: wgrad_issue<4, kTwo>(is, bd); break;
@@ -496,6 +547,8 @@ extern "C" int uavdet_conv_wgrad(const uavdet_act* x, const uavdet_act* dy, int 
   P.sample_stride = (long long)cout * P.k_total;
   P.dw = dw_packed;
   P.watchdog = watchdog_word();
+  static const bool no_merge = getenv("UAVDET_WGRAD_NOMERGE") != nullptr;    // A/B switch
+  P.merge_taps = (!no_merge && share) ? 1 : 0;      // shared boxes: the taps of a column are tile_w rows apart
 
   CUtensorMap mapDY, mapX[3];
   int rc = make_act_map(&mapDY, dy, 0, P.a_width, P.tile_w, P.tile_h);
