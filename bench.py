@@ -424,6 +424,10 @@ class ConvTimer:
             return 2.0 * n * ho * wo * cout * 4 * c * k * k
 
         ops.conv_dgrad_s2d = timed(self._orig[3], "igemm", dgrad_s2d_flops)
+        # plane-fused stride-2 data gradient: the ALGORITHMIC flops of the 3x3 layer (9 taps), not the 16 blocks it computes
+        self._orig_s2f = ops.conv_dgrad_s2_fused
+        ops.conv_dgrad_s2_fused = timed(self._orig_s2f, "igemm",
+                                        lambda a, kw: 2.0 * a[0].shape[0] * a[0].shape[1] * a[0].shape[2] * a[0].shape[3] * a[2] * 9)
         # the tensor-core stem (stem_mma.cu) is HBM-bound: recorded with its algorithmic bytes (fp32 NCHW input read +
         # NHWC bf16 tensor written / read), under kinds of its own so it stays out of the igemm / wgrad aggregates
         self._orig_stem = (ops.stem_mma_fwd, ops.stem_mma_wgrad)
@@ -444,6 +448,7 @@ class ConvTimer:
     def __exit__(self, *exc):
         self.ops.conv_fwd, self.ops.conv_dgrad, self.ops.conv_wgrad, self.ops.conv_dgrad_s2d = self._orig
         self.ops.stem_mma_fwd, self.ops.stem_mma_wgrad = self._orig_stem
+        self.ops.conv_dgrad_s2_fused = self._orig_s2f
         if self._orig_bn is not None:
             self.ops.bn_act_fwd, self.ops.bn_act_bwd = self._orig_bn
 

@@ -170,6 +170,16 @@ int uavdet_conv_dgrad(const uavdet_act* dy, const void* w_packed_t, int w_batch,
                       int stride, int pad, const uavdet_act* dx, const uavdet_epilogue* epi,
                       void* stream);
 
+/* Data gradient of a 3x3 stride-2 pad-1 convolution with cin in {32, 64} as ONE implicit GEMM over the four output
+ * parity planes (autograd of the down-sampling layers, BaselineModel.py:63-75 `[C, 3, 2]` entries): N = 4*cin columns
+ * [(row parity, column parity, ci)], K = four dy shifts x cout, weights re-laid out (with zero blocks where a parity
+ * plane has no filter tap for a shift) by uavdet_pack_dgrad_s2_fused from the transposed pack [cin][3][3][cout].
+ * dx: dense (n, 2*ho, 2*wo, cin); epi: NULL or AFFINE with `res` only.  The per-plane route (uavdet_conv_dgrad) issues
+ * nine taps x four planes of N = cin instructions; the tensor core needs as long for N = 32 as for N = 128.            */
+int uavdet_pack_dgrad_s2_fused(const void* w_packed_t, int cin, int cout, void* w_fused, void* stream);
+int uavdet_conv_dgrad_s2_fused(const uavdet_act* dy, const void* w_fused, int cin, const uavdet_act* dx,
+                               const uavdet_epilogue* epi, void* stream);
+
 /* Data gradient through the fused space-to-depth(2) gather of uavdet_conv_fwd(s2d=1)
  * (autograd of DySOEM_SimFPN.py:71-91): dy (n, h/2, w/2, cout) -> dx (n, h, w, c) where the conv's
  * logical input had 4*c channels, block q = 2*(row parity) + (column parity).  w_packed_t: bf16

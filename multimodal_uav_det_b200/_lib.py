@@ -55,6 +55,8 @@ SIGNATURES = {
     "uavdet_conv_fwd": (_i, [_AP, _P, _i, _i, _i, _i, _i, _i, _AP, _EP, _P]),
     "uavdet_conv_dgrad": (_i, [_AP, _P, _i, _i, _i, _i, _i, _AP, _EP, _P]),
     "uavdet_conv_dgrad_s2d": (_i, [_AP, _P, _i, _i, _i, _i, _AP, _EP, _P]),
+    "uavdet_pack_dgrad_s2_fused": (_i, [_P, _i, _i, _P, _P]),
+    "uavdet_conv_dgrad_s2_fused": (_i, [_AP, _P, _i, _AP, _EP, _P]),
     "uavdet_conv_wgrad": (_i, [_AP, _AP, _i, _i, _i, _i, _P, _i, _P]),
     "uavdet_pack_weight": (_i, [_P, _i, _i, _i, _i, _P, _P]),
     "uavdet_pack_weights_batched": (_i, [_P, _i, C.c_longlong, _P]),

@@ -752,13 +752,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         const uint32_t tempty = kTwo ? mapa_shared(smem_u32(&tempty_bar[acc]), 0) : smem_u32(&tempty_bar[acc]);
         for (int sl = 0; sl < n_slabs; ++sl, ++slab_counter) {
           const int cs = tc.n0 + sl * P.slab_w;
+          // fused parity planes: column cs + i of the GEMM is channel (cs + i) % cspan of plane cs / cspan — shift the
+          // residual base so that `res + column` lands there
+          const __nv_bfloat16* res_sl =
+              (res_px && P.out_cspan) ? res_px + (long long)(cs / P.out_cspan) * (P.res_sp - P.out_cspan) : res_px;
           uint8_t* sbuf = staging + (slab_counter & 1u) * slab_bytes;
           if (e_tid == 0) tma_store_wait_read<1>();           // the store that read this buffer two slabs ago
           asm volatile("bar.sync 2, 256;" ::: "memory");
           const bool last = sl == n_slabs - 1;
           if (half < chunks_per_slab) {
             const int c0 = sl * P.slab_w + half * 32;
-            stage_chunk<(kKind == 3 ? 1 : kKind), kTwo>(ccfg, P.scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, sbuf + row * row_bytes, half,
+            stage_chunk<(kKind == 3 ? 1 : kKind), kTwo>(ccfg, P.scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_sl, sbuf + row * row_bytes, half,
                         sw_mask, last, tempty, lane);
             fence_proxy_async();
           } else if (last) {
@@ -1140,7 +1144,6 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
       P.res_tma = 1;
     }
   } else {
-    UAVDET_CHECK_ARG(!(P.out_cspan && P.res), "igemm: fused parity planes with a residual need a warp-private tile");
     rc = make_out_map(&mapOut, P.out, P.n_img, P.ho, P.wo, P.out_cspan ? P.out_cspan : P.cout, P.out_sn, P.out_sh, P.out_sw,
                       P.slab_w, P.tile_w, P.tile_h, P.out_cspan ? P.cout / P.out_cspan : 1, P.out_sp);
     if (rc) return rc;
@@ -1444,6 +1447,76 @@ extern "C" int uavdet_conv_dgrad(const uavdet_act* dy, const void* w_packed_t, i
   return UAVDET_OK;
 }
 
+// Weights of the plane-fused stride-2 data gradient: from the transposed pack wt [cin][3][3][cout] to
+// wf [(ph, pw, ci)][(sh, sw, co)] = wt[ci][ph + 1 - 2 sh][pw + 1 - 2 sw][co], zero where the filter index leaves 0..2.
+__global__ void __launch_bounds__(256)
+pack_dgrad_s2_fused_kernel(const __nv_bfloat16* __restrict__ wt, int cin, int cout, __nv_bfloat16* __restrict__ wf) {
+  const int c8 = cout >> 3;
+  const long long total = 16ll * cin * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % c8) * 8;
+    long long r = i / c8;
+    const int s = (int)(r % 4); r /= 4;          // (sh, sw)
+    const int ci = (int)(r % cin);
+    const int q = (int)(r / cin);                // (ph, pw)
+    const int kh = (q >> 1) + 1 - 2 * (s >> 1), kw = (q & 1) + 1 - 2 * (s & 1);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (kh >= 0 && kh <= 2 && kw >= 0 && kw <= 2)
+      v = *reinterpret_cast<const uint4*>(wt + ((long long)(ci * 3 + kh) * 3 + kw) * cout + co);
+    *reinterpret_cast<uint4*>(wf + ((long long)(q * cin + ci) * 4 + s) * cout + co) = v;
+  }
+}
+
+extern "C" int uavdet_pack_dgrad_s2_fused(const void* w_packed_t, int cin, int cout, void* w_fused, void* stream) {
+  UAVDET_CHECK_ARG(w_packed_t && w_fused && cin % 32 == 0 && cout % 32 == 0, "pack_dgrad_s2_fused: bad arguments");
+  UAVDET_CHECK_ARG((((uintptr_t)w_packed_t | (uintptr_t)w_fused) & 15) == 0, "pack_dgrad_s2_fused: 16-byte alignment");
+  const long long total = 16ll * cin * (cout / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  pack_dgrad_s2_fused_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)w_packed_t, cin, cout,
+                                                                        (__nv_bfloat16*)w_fused);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_conv_dgrad_s2_fused(const uavdet_act* dy, const void* w_fused, int cin, const uavdet_act* dx,
+                                          const uavdet_epilogue* epi, void* stream) {
+  UAVDET_CHECK_ARG(dy && dy->ptr && w_fused && dx && dx->ptr, "conv_dgrad_s2_fused: null input");
+  UAVDET_CHECK_ARG(dy->ld % 8 == 0 && ((uintptr_t)dy->ptr & 15) == 0, "conv_dgrad_s2_fused: dy must be 16-byte aligned");
+  const int cout = dy->c;
+  UAVDET_CHECK_ARG(cout % 32 == 0 && cin % 32 == 0 && 4 * cin <= 256, "conv_dgrad_s2_fused: needs cin in {32, 64}, cout %% 32 == 0");
+  UAVDET_CHECK_ARG(dx->n == dy->n && dx->c == cin && dx->ld == cin && dx->h == 2 * dy->h && dx->w == 2 * dy->w,
+                   "conv_dgrad_s2_fused: dx must be the dense (n, 2*ho, 2*wo, cin) tensor of a 3x3 stride-2 pad-1 conv");
+  UAVDET_CHECK_ARG(!epi || !epi->res || epi->res_ld == cin, "conv_dgrad_s2_fused: the residual must be dense");
+  IgemmParams P{};
+  P.n_img = dy->n;
+  P.ho = dy->h;
+  P.wo = dy->w;
+  P.cout = 4 * cin;
+  P.block_k = (cout % 64 == 0) ? 64 : 32;
+  P.block_n = pick_block_n(4 * cin);
+  P.kc_per_tap = cout / P.block_k;
+  int nt = 0;
+  for (int sh = 0; sh < 2; ++sh)
+    for (int sw = 0; sw < 2; ++sw) P.taps[nt++] = ConvTap{0, sw, 0, sh, (sh * 2 + sw) * cout};
+  P.num_taps = nt;
+  uavdet_act dxv = *dx;
+  dxv.h = P.ho; dxv.w = P.wo;
+  int rc = fill_epilogue(P, epi, &dxv, 4 * cin);
+  if (rc) return rc;
+  UAVDET_CHECK_ARG(P.epi == UAVDET_EPI_AFFINE && !P.scale && !P.shift, "conv_dgrad_s2_fused: plain AFFINE epilogue (residual only)");
+  const long long ld = dx->ld;
+  P.out = (__nv_bfloat16*)dx->ptr;
+  P.out_sw = 2 * ld; P.out_sh = 2ll * dx->w * ld; P.out_sn = (long long)dx->h * dx->w * ld;
+  P.out_cspan = 2 * cin; P.out_sp = (long long)dx->w * ld;
+  if (P.res) {
+    P.res_sw = 2 * ld; P.res_sh = 2ll * dx->w * ld; P.res_sn = (long long)dx->h * dx->w * ld;
+    P.res_sp = (long long)dx->w * ld;
+  }
+  choose_tile(P.ho, P.wo, false, &P.tile_w, &P.tile_h, &P.epi_mode);
+  return launch_igemm(dy, 0, w_fused, 4 * cin, 4 * cout, 1, P, (cudaStream_t)stream);
+}
+
 extern "C" int uavdet_conv_dgrad_s2d(const uavdet_act* dy, const void* w_packed_t, int w_batch, int c, int k, int pad,
                                      const uavdet_act* dx, const uavdet_epilogue* epi, void* stream) {
   UAVDET_CHECK_ARG(dy && dy->ptr && w_packed_t && dx && dx->ptr, "conv_dgrad_s2d: null input");
@@ -1497,7 +1570,7 @@ extern "C" int uavdet_conv_dgrad_s2d(const uavdet_act* dy, const void* w_packed_
     // a store slab (64 | 32 columns) must not straddle two row-parity planes; a shared (not per-sample) shift is [c]
     const bool slab_ok = (2 * c) % ((P.block_n % 64 == 0) ? 64 : 32) == 0;
     const bool shift_ok = !P.shift || epi->shift_per_sample;
-    if (!(P.res && P.epi_mode == 0) && slab_ok && shift_ok)
+    if (slab_ok && shift_ok)
       return launch_igemm(dy, 0, w_packed_t, 4 * c, (int)k_total, w_batch, P, st, 4 * c);
   }
   for (int q = 0; q < 4; ++q) {

@@ -21,6 +21,7 @@ from torch import nn
 from . import ops
 from ._lib import EPI_AFFINE, EPI_STATS
 
+_NO_FUSE_S2 = bool(os.environ.get("UAVDET_NO_FUSE_S2"))      # A/B switch: stride-2 data gradients plane by plane
 _STEM_IM2COL = bool(os.environ.get("UAVDET_STEM_IM2COL"))    # A/B switch: keep the im2col patch tensor of the 3x3 stems
 
 
@@ -211,6 +212,7 @@ class Executor:
         self._bn_counters: List[torch.Tensor] = []
         self._const: Dict[Tuple[str, int, str], torch.Tensor] = {}
         self._bn_fold: Dict[int, Tuple[tuple, torch.Tensor, torch.Tensor]] = {}
+        self._s2f: Dict[tuple, torch.Tensor] = {}    # plane-fused stride-2 data-gradient weights (rebuilt from the pack every step)
         self.grad_ready_hook: Optional[Callable[[torch.Tensor], None]] = None
 
     def producer_streams(self) -> list:
@@ -407,7 +409,21 @@ class Executor:
             if u.s2d:
                 raise NotImplementedError("dgrad through the fused space-to-depth gather")
             wt = self.packs.get(w, transposed=True)
-            dx = ops.conv_dgrad(d_raw, wt, w.shape[1], u.k, u.stride, u.pad, rec.in_hw, res=res, out=out)
+            cin = w.shape[1]
+            h_in, w_in = rec.in_hw
+            fused = (not _NO_FUSE_S2 and u.stride == 2 and u.k == 3 and u.pad == 1 and cin in (32, 64)
+                     and h_in % 2 == 0 and w_in % 2 == 0 and (out is None or out.stride(2) == cin)
+                     and (res is None or res.stride(2) == cin))
+            if fused:
+                # all four output-parity planes as one N = 4*cin GEMM over a re-laid-out (zero-padded) weight matrix
+                key = (id(w), "s2f")
+                buf = self._s2f.get(key)
+                if buf is None or buf.device != wt.device:
+                    buf = torch.empty((4 * cin, 4 * w.shape[0]), dtype=torch.bfloat16, device=wt.device)
+                    self._s2f[key] = buf
+                dx = ops.conv_dgrad_s2_fused(d_raw, ops.pack_dgrad_s2_fused(wt, cin, w.shape[0], out=buf), cin, res=res, out=out)
+            else:
+                dx = ops.conv_dgrad(d_raw, wt, cin, u.k, u.stride, u.pad, rec.in_hw, res=res, out=out)
         # ... then the weight gradient: nothing downstream in backward depends on it, so it goes to a side stream
         # where its tensor-core work overlaps the HBM-bound BatchNorm backward of the next layer (the kernel
         # leaves shared memory for those blocks to share the SM)

@@ -364,6 +364,31 @@ def conv_dgrad(dy: torch.Tensor, w_packed_t: torch.Tensor, cin: int, k: int, str
     return out
 
 
+def pack_dgrad_s2_fused(w_packed_t: torch.Tensor, cin: int, cout: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Transposed pack [cin][3*3*cout] of a 3x3 conv -> [4*cin][4*cout] weights of conv_dgrad_s2_fused."""
+    _require_cuda(w_packed_t)
+    if tuple(w_packed_t.shape) != (cin, 9 * cout) or w_packed_t.dtype != torch.bfloat16 or not w_packed_t.is_contiguous():
+        raise UavdetError("pack_dgrad_s2_fused expects the contiguous bf16 transposed pack (cin, 9*cout)")
+    if out is None:
+        out = torch.empty((4 * cin, 4 * cout), dtype=torch.bfloat16, device=w_packed_t.device)
+    check(_lib.load().uavdet_pack_dgrad_s2_fused(_ptr(w_packed_t), cin, cout, _ptr(out), _stream()), "pack_dgrad_s2_fused")
+    return out
+
+
+def conv_dgrad_s2_fused(dy: torch.Tensor, w_fused: torch.Tensor, cin: int, *, out: Optional[torch.Tensor] = None,
+                        res: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Data gradient of a 3x3 stride-2 pad-1 conv (cin 32 | 64), all four parity planes in one GEMM."""
+    _require_cuda(dy, w_fused)
+    n, ho, wo, _ = dy.shape
+    if out is None:
+        out = empty_act(n, 2 * ho, 2 * wo, cin, dy.device)
+    dv, xv = act_view(dy), act_view(out)
+    e = _epilogue(EPI_AFFINE, None, None, None, res)
+    check(_lib.load().uavdet_conv_dgrad_s2_fused(C.byref(dv), _ptr(w_fused), cin, C.byref(xv), C.byref(e), _stream()),
+          "conv_dgrad_s2_fused")
+    return out
+
+
 def conv_dgrad_s2d(dy: torch.Tensor, w_packed_t: torch.Tensor, c: int, k: int, pad: int, *, w_batch: int = 1,
                    out: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
                    shift: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -481,6 +481,36 @@ def test_conv_dgrad(lib, case):
     assert_close_bf16(to_nchw(dx), ref, f"dgrad{case}")
 
 
+@pytest.mark.parametrize("n,cin,cout,h,w,with_res", [(2, 32, 64, 32, 32, False), (2, 64, 128, 64, 48, True), (3, 32, 64, 80, 96, True),
+                                                     (1, 64, 96, 40, 40, False), (2, 32, 32, 16, 24, True)])
+def test_conv_dgrad_stride2_plane_fused(lib, n, cin, cout, h, w, with_res):
+    """3x3 stride-2 data gradient with the four output-parity planes as one N = 4*cin GEMM over the re-laid-out weight
+    matrix (zero blocks where a plane has no tap for a dy shift), against conv2d_input and against the plane-by-plane
+    kernel."""
+    ops = _ops(lib)
+    x, wt = _conv_case(n, cin, cout, 3, 2, h, w, seed=31)
+    g = torch.Generator().manual_seed(32)
+    dy = bf16_round(torch.randn(n, cout, h // 2, w // 2, generator=g))
+    skip = bf16_round(torch.randn(n, cin, h, w, generator=g)) if with_res else None
+    ref = torch.nn.grad.conv2d_input(x.shape, wt, dy, 2, 1) + (skip if with_res else 0)
+    wtp = ops.pack_weight(wt.to(DEV), transposed=True)
+    wf = ops.pack_dgrad_s2_fused(wtp, cin, cout)
+    # the re-layout itself: row (ph, pw, ci), column (sh, sw, co)
+    wfr = wf.float().cpu().view(2, 2, cin, 2, 2, cout)
+    for ph in range(2):
+        for pw in range(2):
+            for sh in range(2):
+                for sw in range(2):
+                    kh, kw = ph + 1 - 2 * sh, pw + 1 - 2 * sw
+                    want = wt[:, :, kh, kw].t() if 0 <= kh <= 2 and 0 <= kw <= 2 else torch.zeros(cin, cout)
+                    assert torch.equal(wfr[ph, pw, :, sh, sw, :], want)
+    dx = ops.conv_dgrad_s2_fused(nhwc(dy), wf, cin, res=nhwc(skip) if with_res else None)
+    ops.check_device()
+    assert_close_bf16(to_nchw(dx), ref, "plane-fused stride-2 dgrad")
+    dx_planes = ops.conv_dgrad(nhwc(dy), wtp, cin, 3, 2, 1, (h, w), res=nhwc(skip) if with_res else None)
+    assert rel_l2(dx.float().cpu(), dx_planes.float().cpu()) < 3e-3
+
+
 WGRAD_CASES = [(2, 64, 64, 1, 1, 16, 16), (2, 64, 128, 3, 1, 16, 16), (2, 32, 64, 3, 2, 32, 32),
                (1, 128, 256, 3, 2, 20, 20), (2, 256, 128, 1, 1, 20, 20), (1, 64, 32, 1, 1, 32, 32),
                (4, 512, 1024, 3, 1, 20, 20), (2, 64, 128, 1, 2, 16, 16),
