@@ -456,13 +456,15 @@ class ConvTimer:
         self.torch.cuda.synchronize()
         t = self.stamps.cpu().tolist()
         agg = {}
+        t_first = min((t[slot] for _, _, slot in self.records), default=0)
         for i, (kind, fl, slot) in enumerate(self.records):
             sec = (t[slot + 1] - t[slot]) * 1e-9
             if os.environ.get("UAVDET_BENCH_DEBUG"):
+                at = f" @{(t[slot] - t_first) * 1e-3:.0f}" if os.environ.get("UAVDET_BENCH_TIMELINE") else ""
                 if kind.startswith(("bn_", "stem_")):
-                    print(f"[convtimer] {i} {kind} {sec * 1e6:.0f} us {fl / 1e6:.0f} MB {fl / sec / 1e12:.2f} TB/s", file=sys.stderr)
+                    print(f"[convtimer] {i} {kind} {sec * 1e6:.0f} us {fl / 1e6:.0f} MB {fl / sec / 1e12:.2f} TB/s{at}", file=sys.stderr)
                 else:
-                    print(f"[convtimer] {i} {kind} {sec * 1e6:.0f} us {fl / 1e9:.1f} GFLOP", file=sys.stderr)
+                    print(f"[convtimer] {i} {kind} {sec * 1e6:.0f} us {fl / 1e9:.1f} GFLOP{at}", file=sys.stderr)
             a = agg.setdefault(kind, [0.0, 0.0, 0])
             a[0] += fl
             a[1] += sec
@@ -601,7 +603,8 @@ def run_ours(args, rank, world, local_rank):
         else:
             # kernels are timed one at a time: the weight gradients stay in line for this capture (in the timed
             # graph they run on a side stream under the BatchNorm backward, which would smear the stamps)
-            model._exec.overlap_wgrad = False
+            # (UAVDET_BENCH_TIMELINE=1 keeps them on the side stream and prints every launch's start offset instead)
+            model._exec.overlap_wgrad = bool(os.environ.get("UAVDET_BENCH_TIMELINE"))
             instrumented = GraphedTrainStep(model, trainer, x_dev, tg_dev, warmup=0, forward_kwargs=fkw)
             model._exec.overlap_wgrad = True
             instrumented()

@@ -95,12 +95,32 @@ __device__ __forceinline__ float fast_sigmoid(float z) {
   return fmaf(0.5f, t, 0.5f);
 }
 
+// Standard normal CDF for the exact (erf) GELU of nn.GELU() (RTMUAVDet.py:155 channel MLP): Abramowitz & Stegun 26.2.17,
+//   Q(|z|) = phi(|z|) (b1 t + ... + b5 t^5),  t = 1 / (1 + 0.2316419 |z|),  |error| < 7.5e-8,
+// with 1 / sqrt(2 pi) folded into the coefficients and the hardware reciprocal / exp2 (two special-function
+// instructions, 12 others).  Measured against erf in fp32 emulation over [-8, 8]: |gelu error| <= 6.2e-7, three orders
+// below the bf16 rounding of the result.  erff() is ~40 instructions with a branch; in the implicit-GEMM epilogue of the
+// 192 -> 192 and 384 -> 384 channel MLPs (629 M / 315 M elements at batch 128) it made those two launches 1.6 / 0.8 ms
+// against 0.39 / 0.19 ms of HBM time.
+__device__ __forceinline__ float gelu_cdf(float z) {
+  const float a = fabsf(z);
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.2316419f, a, 1.f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-0.72134752f * a * a));
+  float p = fmaf(t, 0.530702714f, -0.726576013f);
+  p = fmaf(p, t, 0.710706871f);
+  p = fmaf(p, t, -0.142248368f);
+  p = fmaf(p, t, 0.127414796f);
+  const float q = p * t * e;
+  return z >= 0.f ? 1.f - q : q;
+}
+
 template <int ACT>
 __device__ __forceinline__ float act_fwd(float z) {
   if (ACT == UAVDET_ACT_LEAKY) return z > 0.f ? z : 0.1f * z;
   if (ACT == UAVDET_ACT_SILU) return z * fast_sigmoid(z);
   if (ACT == UAVDET_ACT_RELU) return z > 0.f ? z : 0.f;
-  if (ACT == UAVDET_ACT_GELU) return 0.5f * z * (1.f + erff(z * 0.70710678118654752f));
+  if (ACT == UAVDET_ACT_GELU) return z * gelu_cdf(z);
   return z;
 }
 __device__ __forceinline__ float act_fwd_rt(int act, float z) {
@@ -122,7 +142,7 @@ __device__ __forceinline__ float act_grad_rt(int act, float z) {
     }
     case UAVDET_ACT_RELU: return z > 0.f ? 1.f : 0.f;
     case UAVDET_ACT_GELU: {
-      float cdf = 0.5f * (1.f + erff(z * 0.70710678118654752f));
+      float cdf = gelu_cdf(z);
       float pdf = 0.3989422804014327f * __expf(-0.5f * z * z);
       return cdf + z * pdf;
     }

@@ -161,9 +161,10 @@ bn_act_fwd_kernel(View raw, const float* __restrict__ scale, const float* __rest
 }
 
 // ---- train-mode BN in one pass over the activations: finalize folded in --------------------------------
-// Every thread derives scale/shift of its 8 channels from the batch sums (a few flops); the threads of the first
-// pixel lane of block column 0 also publish mean / invstd / scale / shift (backward needs them) and update the
-// running statistics (momentum, unbiased variance — nn.BatchNorm2d, BaselineModel.py:14).
+// The first (channels of the block) threads each derive scale/shift of ONE channel from the batch sums and pass them
+// through shared memory (the fp64 part — E[x^2] - E[x]^2 cancels in fp32 — is three operations per block and channel,
+// not 24 per thread); block column 0 also publishes mean / invstd / scale / shift (backward needs them) and updates
+// the running statistics (momentum, unbiased variance — nn.BatchNorm2d, BaselineModel.py:14).
 template <bool HAS_RES>
 __global__ void __launch_bounds__(256)
 bn_train_fwd_kernel(View raw, const float* __restrict__ sum, const float* __restrict__ sumsq, double count, float eps,
@@ -171,35 +172,27 @@ bn_train_fwd_kernel(View raw, const float* __restrict__ sum, const float* __rest
                     float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ mean_out,
                     float* __restrict__ invstd_out, float* __restrict__ scale_out, float* __restrict__ shift_out, int act,
                     const __nv_bfloat16* __restrict__ res, int res_ld, View y) {
+  __shared__ float sh_s[256], sh_t[256];
   const PixLane L = pix_lane(raw.c);
-  if (!L.active) return;
-  float s[8], t[8];
   {
-    float su[8], sq[8], g[8], b[8];
-    load8f(sum + L.c, su);
-    load8f(sumsq + L.c, sq);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { g[j] = 1.f; b[j] = 0.f; }
-    if (gamma) load8f(gamma + L.c, g);
-    if (beta) load8f(beta + L.c, b);
-    const bool publish = blockIdx.x == 0 && threadIdx.x < (raw.c >> 3 < 32 ? raw.c >> 3 : 32);
-    const double inv_count = 1.0 / count;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      // E[x^2] - E[x]^2 cancels in fp32, so those three operations stay in double; the reciprocal square root is
-      // a single fp32 instruction (every thread of the grid runs this preamble: no fp64 divide / sqrt here)
-      const double m = (double)su[j] * inv_count;
-      double var = fma(-m, m, (double)sq[j] * inv_count);
+    const int G = raw.c >> 3;
+    const int Gb = G < 32 ? G : 32;
+    const int c = blockIdx.y * Gb * 8 + threadIdx.x;
+    if ((int)threadIdx.x < Gb * 8 && c < raw.c) {
+      const double inv_count = 1.0 / count;
+      const double m = (double)__ldg(sum + c) * inv_count;
+      double var = fma(-m, m, (double)__ldg(sumsq + c) * inv_count);
       if (var < 0.0) var = 0.0;
       const float is = rsqrtf((float)var + eps);
-      s[j] = g[j] * is;
-      t[j] = b[j] - (float)m * g[j] * is;
-      if (publish) {
-        const int c = L.c + j;
+      const float g = gamma ? __ldg(gamma + c) : 1.f, b = beta ? __ldg(beta + c) : 0.f;
+      const float sc = g * is, sf = b - (float)m * g * is;
+      sh_s[threadIdx.x] = sc;
+      sh_t[threadIdx.x] = sf;
+      if (blockIdx.x == 0) {
         if (mean_out) mean_out[c] = (float)m;
         if (invstd_out) invstd_out[c] = is;
-        scale_out[c] = s[j];
-        shift_out[c] = t[j];
+        scale_out[c] = sc;
+        shift_out[c] = sf;
         if (running_mean) {
           const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
           running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
@@ -207,6 +200,16 @@ bn_train_fwd_kernel(View raw, const float* __restrict__ sum, const float* __rest
         }
       }
     }
+  }
+  __syncthreads();
+  if (!L.active) return;
+  float s[8], t[8];
+  {
+    const int G = raw.c >> 3;
+    const int Gb = G < 32 ? G : 32;
+    const int o = L.c - blockIdx.y * Gb * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = sh_s[o + j]; t[j] = sh_t[o + j]; }
   }
   auto body = [&](const uint4& in, const uint4& rin, long long px) {
     float v[8];
@@ -226,7 +229,7 @@ bn_train_fwd_kernel(View raw, const float* __restrict__ sum, const float* __rest
     uint4 a[4], r[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      a[u] = __ldg(reinterpret_cast<const uint4*>(raw.p + (px + u * L.step) * raw.ld + L.c));
+      a[u] = __ldcs(reinterpret_cast<const uint4*>(raw.p + (px + u * L.step) * raw.ld + L.c));
       if (HAS_RES) r[u] = __ldg(reinterpret_cast<const uint4*>(res + (px + u * L.step) * res_ld + L.c));
       else r[u] = make_uint4(0, 0, 0, 0);
     }
@@ -234,7 +237,7 @@ bn_train_fwd_kernel(View raw, const float* __restrict__ sum, const float* __rest
     for (int u = 0; u < 4; ++u) body(a[u], r[u], px + u * L.step);
   }
   for (; px < raw.npix; px += L.step) {
-    uint4 a = __ldg(reinterpret_cast<const uint4*>(raw.p + px * raw.ld + L.c));
+    uint4 a = __ldcs(reinterpret_cast<const uint4*>(raw.p + px * raw.ld + L.c));
     uint4 r = make_uint4(0, 0, 0, 0);
     if (HAS_RES) r = __ldg(reinterpret_cast<const uint4*>(res + px * res_ld + L.c));
     body(a, r, px);
@@ -1224,7 +1227,8 @@ extern "C" int uavdet_bn_train_fwd(const uavdet_act* raw, const float* sum, cons
       (rc = same_shape(raw, y, "bn_train_fwd")))
     return rc;
   UAVDET_CHECK_ARG(sum && sumsq && scale && shift && count > 0, "bn_train_fwd: sums / outputs missing");
-  dim3 grid = stream_grid(raw, 4);
+  if ((long long)raw->n * raw->h * raw->w == 0) return UAVDET_OK;
+  dim3 grid = stream_grid(raw, 8);
   if (res) {
     if ((rc = check_view(res, "bn_train_fwd res")) || (rc = same_shape(raw, res, "bn_train_fwd res"))) return rc;
     bn_train_fwd_kernel<true><<<grid, 256, 0, ST>>>(mkview(raw), sum, sumsq, count, eps, momentum, gamma, beta,

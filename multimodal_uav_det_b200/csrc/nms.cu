@@ -438,17 +438,73 @@ nms_image_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
     if (rank == 0) *nan_flag = 0u;
   }
   __syncthreads();
-  int local_valid = 0;
-  for (int i = tid; i < n; i += kNmsThreads) {
-    float s = scores[i];
-    if (rank == 0) {
-      keyA[i] = score_key(s);
-      valA[i] = (uint32_t)i;
+  // With a score floor only the candidates above it (or NaN: they sort first) are ever looked at again, and a detector's
+  // floor leaves a few hundred of 96,000 (RTMUAVDet, batch 128: the full-length sort was 2.1 ms of a 19 ms forward).
+  // CTA 0 therefore compacts them first — in index order, so the stable sort below still breaks score ties by index —
+  // and sorts n_valid entries instead of n.  Two sweeps over the scores, each warp owning one contiguous segment:
+  // count, exclusive prefix over the 16 warps, then ballot-ranked writes.
+  const bool compact = score_floor > -INFINITY;
+  int n_sort = n;
+  if (compact && rank == 0) {
+    const int seg = (((n + kNmsWarps - 1) / kNmsWarps) + 31) & ~31;
+    const int i0 = warp * seg, i1 = min(n, i0 + seg);
+    int cnt = 0;
+    for (int base = i0; base < i1; base += 128) {
+      float sv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + 32 * u + lane;
+        sv[u] = i < i1 ? scores[i] : score_floor;     // the floor itself is neither NaN nor above the floor
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) cnt += (sv[u] != sv[u] || sv[u] > score_floor) ? 1 : 0;
     }
-    local_valid += (s != s || s > score_floor) ? 1 : 0;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0) S.bin[warp] = (uint32_t)cnt;
+    __syncthreads();
+    uint32_t off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kNmsWarps; ++w) {
+      const uint32_t c = S.bin[w];
+      if (w < warp) off += c;
+      total += c;
+    }
+    if (tid == 0) S.n_valid = (int)total;
+    n_sort = (int)total;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int base = i0; base < i1; base += 128) {
+      float sv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + 32 * u + lane;
+        sv[u] = i < i1 ? scores[i] : score_floor;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool v = sv[u] != sv[u] || sv[u] > score_floor;
+        const uint32_t m = __ballot_sync(0xffffffffu, v);
+        if (v) {
+          const uint32_t pos = off + __popc(m & lt);
+          keyA[pos] = score_key(sv[u]);
+          valA[pos] = (uint32_t)(base + 32 * u + lane);
+        }
+        off += __popc(m);
+      }
+    }
+    __syncthreads();   // the sort reads keys other threads wrote, and reuses S.bin
+  } else {
+    int local_valid = 0;
+    for (int i = tid; i < n; i += kNmsThreads) {
+      float s = scores[i];
+      if (rank == 0) {
+        keyA[i] = score_key(s);
+        valA[i] = (uint32_t)i;
+      }
+      local_valid += (s != s || s > score_floor) ? 1 : 0;
+    }
+    local_valid = __reduce_add_sync(0xffffffffu, local_valid);
+    if (lane == 0 && local_valid) atomicAdd(&S.n_valid, local_valid);
   }
-  local_valid = __reduce_add_sync(0xffffffffu, local_valid);
-  if (lane == 0 && local_valid) atomicAdd(&S.n_valid, local_valid);
 
   // ---- 2. stable LSD radix sort (CTA 0) ---------------------------------------------------
   uint32_t* kin = keyA; uint32_t* kout = keyB;
@@ -457,9 +513,9 @@ nms_image_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
     const int shift = pass * 8;
     if (tid < 256) S.bin[tid] = 0;
     __syncthreads();  // also orders the previous pass' global writes within the CTA
-    for (int base = 0; base < n; base += kNmsThreads) {  // warp-aggregated histogram
+    for (int base = 0; base < n_sort; base += kNmsThreads) {  // warp-aggregated histogram
       const int i = base + tid;
-      const uint32_t digit = (i < n) ? ((kin[i] >> shift) & 255u) : 256u;
+      const uint32_t digit = (i < n_sort) ? ((kin[i] >> shift) & 255u) : 256u;
       const uint32_t peers = __match_any_sync(0xffffffffu, digit);
       if (digit < 256u && (peers & ((1u << lane) - 1u)) == 0u) atomicAdd(&S.bin[digit], __popc(peers));
     }
@@ -481,9 +537,9 @@ nms_image_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
     }
     __syncthreads();
     // stable scatter, one tile of 1024 consecutive items at a time
-    for (int base = 0; base < n; base += kNmsThreads) {
+    for (int base = 0; base < n_sort; base += kNmsThreads) {
       const int i = base + tid;
-      const bool valid = i < n;
+      const bool valid = i < n_sort;
       uint32_t key = 0, val = 0, digit = 256;  // digit 256 = "no item"
       if (valid) { key = kin[i]; val = vin[i]; digit = (key >> shift) & 255u; }
       // rank among same-digit lanes of this warp (lower lanes first)

@@ -208,56 +208,86 @@ __global__ void __launch_bounds__(kSwThreads) stem_wgrad_kernel(const float* __r
 // grid-stride loop and keeps its statistics / gradient partial sums in registers until the end.  (The generic kernels
 // above — a pixel and all 32 channels per thread, a full warp-wide butterfly of the statistics per pixel; a 32x8 tile
 // with 16 tap slots of which a 1x1 kernel fills 3 — ran this layer at 25 % / 10 % of the HBM rate.)
-template <int CIN>
-__global__ void __launch_bounds__(256) stem1x1_fwd_kernel(StemParams P) {
+template <int CIN, bool STATS>
+__global__ void __launch_bounds__(256, 3) stem1x1_fwd_kernel(StemParams P) {
   __shared__ float red[2][8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cg = (lane & 3) << 3;                    // first of this thread's 8 output channels
-  float wr[8][CIN], sc[8], sh[8];
+  // one instance per epilogue: the statistics sums and the affine coefficients never live in registers together
+  // (one kernel for both sat at 125 registers, two blocks per SM)
+  float wr[8][CIN], sc[STATS ? 1 : 8], sh[STATS ? 1 : 8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci) wr[j][ci] = __ldg(P.wgt + (cg + j) * CIN + ci);
-    sc[j] = P.scale ? __ldg(P.scale + cg + j) : 1.f;
-    sh[j] = P.shift ? __ldg(P.shift + cg + j) : 0.f;
+    if constexpr (!STATS) {
+      sc[j] = P.scale ? __ldg(P.scale + cg + j) : 1.f;
+      sh[j] = P.shift ? __ldg(P.shift + cg + j) : 0.f;
+    }
   }
-  float s1[8], s2[8];
+  float s1[STATS ? 8 : 1], s2[STATS ? 8 : 1];
+  if constexpr (STATS) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+    for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  }
   const long long hw = (long long)P.h * P.w, total = hw * P.n;
-  const bool stats = P.epi == UAVDET_EPI_STATS;
-  // (image, pixel) advance incrementally: a 64-bit divide per pixel cost more than the rest of the loop body
-  const long long step = ((long long)gridDim.x * 256) >> 2;
-  long long p = ((long long)blockIdx.x * 256 + threadIdx.x) >> 2;
-  long long img = p / hw, px = p - img * hw;
+  // A warp takes 32 consecutive pixels per iteration: lane l loads the CIN inputs of pixel l (one coalesced 128-byte
+  // request per channel plane), shuffles hand pixel 8u + (lane >> 2) to its four lanes, and the warp issues four
+  // 512-byte stores.  The inputs of the NEXT chunk are requested before the current one is computed: with one pixel
+  // per thread and iteration (the first version) the ~80-register kernel had 768 threads x 16 bytes in flight per SM
+  // and ran at 1.9 TB/s.  (image, pixel) of the chunk base advance incrementally: no 64-bit divide in the loop.
+  const long long step = (long long)gridDim.x * 256;                 // pixels per grid sweep (8 warps x 32 per block)
+  long long p0 = ((long long)blockIdx.x * 8 + warp) * 32;            // first pixel of this warp's chunk
+  long long img = p0 / hw, px = p0 - img * hw;
   const long long step_img = step / hw, step_px = step - step_img * hw;
-  for (; p < total; p += step, img += step_img, px += step_px) {
-    if (px >= hw) { px -= hw; ++img; }
-    const float* xin = P.x + img * CIN * hw + px;
-    float xv[CIN];
+  auto load_chunk = [&](long long base, long long bimg, long long bpx, float (&xv)[CIN]) {
+    long long li = bimg, lp = bpx + lane;
+    while (lp >= hw) { lp -= hw; ++li; }
+    const bool ok = base + lane < total;
+    const float* xin = P.x + li * CIN * hw + lp;
 #pragma unroll
-    for (int ci = 0; ci < CIN; ++ci) xv[ci] = __ldcs(xin + ci * hw);
-    float v[8];
+    for (int ci = 0; ci < CIN; ++ci) xv[ci] = ok ? __ldcs(xin + ci * hw) : 0.f;
+  };
+  float xcur[CIN], xnext[CIN];
+  if (p0 < total) load_chunk(p0, img, px, xcur);
+  for (; p0 < total; p0 += step) {
+    long long nimg = img + step_img, npx = px + step_px;
+    if (npx >= hw) { npx -= hw; ++nimg; }
+    if (p0 + step < total) load_chunk(p0 + step, nimg, npx, xnext);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float a = 0.f;
+    for (int u = 0; u < 4; ++u) {
+      const int src = 8 * u + (lane >> 2);
+      float xv[CIN];
 #pragma unroll
-      for (int ci = 0; ci < CIN; ++ci) a = fmaf(xv[ci], wr[j][ci], a);
-      v[j] = a;
+      for (int ci = 0; ci < CIN; ++ci) xv[ci] = __shfl_sync(0xffffffffu, xcur[ci], src);
+      const long long p = p0 + src;
+      if (p < total) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float a = 0.f;
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci) a = fmaf(xv[ci], wr[j][ci], a);
+          v[j] = a;
+        }
+        if constexpr (STATS) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s1[j] += v[j]; s2[j] = fmaf(v[j], v[j], s2[j]); }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = act_fwd_rt(P.act, fmaf(v[j], sc[j], sh[j]));
+        }
+        uint4 o;
+        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+        o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(P.y + p * P.y_ld + cg) = o;
+      }
     }
-    if (stats) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s1[j] += v[j]; s2[j] = fmaf(v[j], v[j], s2[j]); }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = act_fwd_rt(P.act, fmaf(v[j], sc[j], sh[j]));
-    }
-    uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(P.y + p * P.y_ld + cg) = o;
+    for (int ci = 0; ci < CIN; ++ci) xcur[ci] = xnext[ci];
+    img = nimg; px = npx;
   }
-  if (stats) {
+  if constexpr (STATS) {
     // lanes with equal (lane & 3) hold the same channels: fold the 8 pixel lanes, then the 8 warps
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -514,11 +544,14 @@ extern "C" int uavdet_stem_fwd(const float* x_nchw, int n, int cin, int h, int w
   cudaStream_t st = (cudaStream_t)stream;
   if (k == 1 && stride == 1 && pad == 0 && P.w_batch == 1 && !padded && (cin == 1 || cin == 3)) {
     // streaming 1x1 stem: 4 lanes per pixel, grid-stride
-    long long blocks = ceil_div64((long long)n * h * w * 4, 256 * 8);
+    long long blocks = ceil_div64((long long)n * h * w, 256 * 4);
     if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
     if (blocks < 1) blocks = 1;
-    if (cin == 1) stem1x1_fwd_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(P);
-    else stem1x1_fwd_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(P);
+    const bool stats = P.epi == UAVDET_EPI_STATS;
+    if (cin == 1 && stats) stem1x1_fwd_kernel<1, true><<<(unsigned)blocks, 256, 0, st>>>(P);
+    else if (cin == 1) stem1x1_fwd_kernel<1, false><<<(unsigned)blocks, 256, 0, st>>>(P);
+    else if (stats) stem1x1_fwd_kernel<3, true><<<(unsigned)blocks, 256, 0, st>>>(P);
+    else stem1x1_fwd_kernel<3, false><<<(unsigned)blocks, 256, 0, st>>>(P);
     UAVDET_LAUNCH_CHECK();
     return UAVDET_OK;
   }

@@ -18,7 +18,7 @@ from ._lib import ACT, EPI_AFFINE, EPI_HEAD, EPI_STATS, Act, Epilogue, UavdetErr
 
 
 import os as _os
-_NO_BN_FUSE = not bool(_os.environ.get("UAVDET_BN_FUSE_FWD"))      # A/B switches for tuning
+_NO_BN_FUSE = bool(_os.environ.get("UAVDET_NO_BN_FUSE_FWD"))      # A/B switches for tuning
 _NO_BN_FUSE_BWD = bool(_os.environ.get("UAVDET_NO_BN_FUSE_BWD"))
 
 

@@ -153,6 +153,40 @@ def test_nms_batched_and_score_floor(lib):
         assert np.array_equal(keep[b, : int(count[b])].cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("n", [1, 7, 33, 511, 513, 4100, 96000])
+def test_nms_score_floor_compaction_edges(lib, n):
+    """The floor path compacts the surviving candidates (index order) before the sort: sizes around the warp-segment
+    and tile boundaries, heavy score ties (tie order = index order must survive the compaction), NaN scores (kept, they
+    sort first), floors that keep nothing / everything, single image and batch — against the oracle on the filtered
+    subset, and (floor below every score) against the full-length path."""
+    from oracle import oracle as O
+    ops = _ops(lib)
+    g = torch.Generator().manual_seed(900 + n)
+    bs = 3
+    boxes = torch.empty(bs, n, 4)
+    scores = torch.empty(bs, n)
+    for b in range(bs):
+        boxes[b], scores[b] = _random_boxes(n, g, quant=8)
+    scores = (scores * 16).round() / 16                     # ~100 distinct values: ties everywhere
+    if n >= 33:
+        scores[1, torch.randperm(n, generator=g)[: max(1, n // 50)]] = float("nan")
+    for floor in (0.5, 0.9375, 2.0, -1.0, 100.0):
+        keep, count = ops.nms_batched(boxes.to(DEV), scores.to(DEV), 0.5, score_floor=floor)
+        for b in range(bs):
+            sel = torch.nonzero(torch.isnan(scores[b]) | (scores[b] > floor)).flatten()
+            want = sel.numpy()[O.nms(boxes[b][sel].numpy(), scores[b][sel].numpy(), 0.5)] if sel.numel() else np.zeros(0, np.int64)
+            assert np.array_equal(keep[b, : int(count[b])].cpu().numpy(), want), (n, floor, b)
+    full, full_count = ops.nms_batched(boxes.to(DEV), scores.to(DEV), 0.5)
+    if n >= 33:
+        scores[1] = torch.nan_to_num(scores[1], nan=0.25)      # (the full-length path is compared without NaN scores)
+        full, full_count = ops.nms_batched(boxes.to(DEV), scores.to(DEV), 0.5)
+    keep, count = ops.nms_batched(boxes.to(DEV), scores.to(DEV), 0.5, score_floor=-1e30)
+    assert torch.equal(count, full_count)
+    for b in range(bs):
+        assert torch.equal(keep[b, : int(count[b])], full[b, : int(count[b])])
+    ops.check_device()
+
+
 # ------------------------------------------------------------------------------------------------
 # decode
 # ------------------------------------------------------------------------------------------------
@@ -305,7 +339,7 @@ def test_pack_weight_layouts(lib):
     assert torch.equal(back, g.view(8, 3, 3, 6).permute(0, 3, 1, 2))
 
 
-@pytest.mark.parametrize("act", ["leaky", "silu", "relu", "none"])
+@pytest.mark.parametrize("act", ["leaky", "silu", "relu", "gelu", "none"])
 def test_conv_fwd_affine_epilogue(lib, act):
     ops = _ops(lib)
     n, cin, cout, k, stride, h, w = 2, 64, 128, 3, 1, 16, 16
@@ -315,12 +349,19 @@ def test_conv_fwd_affine_epilogue(lib, act):
     shift = torch.randn(cout, generator=g) * 0.1
     res = bf16_round(torch.randn(n, cout, h, w, generator=g))
     z = F.conv2d(x, wt, None, stride, 1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
-    a = {"leaky": lambda t: F.leaky_relu(t, 0.1), "silu": F.silu, "relu": F.relu, "none": lambda t: t}[act](z)
+    a = {"leaky": lambda t: F.leaky_relu(t, 0.1), "silu": F.silu, "relu": F.relu, "gelu": F.gelu, "none": lambda t: t}[act](z)
     ref = a + res
     y = ops.conv_fwd(nhwc(x), ops.pack_weight(wt.to(DEV)), cout, k, stride, 1, act=act, scale=scale.to(DEV),
                      shift=shift.to(DEV), res=nhwc(res))
     ops.check_device()
     assert_close_bf16(to_nchw(y), ref, f"affine[{act}]")
+    if act == "gelu":
+        # the exact (erf) GELU of nn.GELU() through the A&S 26.2.17 normal CDF: over a wide range of pre-activations
+        # the streaming kernel's fp32 math must sit within bf16 rounding (2^-9 relative, 1e-6 absolute) of erf
+        zz = torch.linspace(-9, 9, 2 * 8 * 64 * 9).view(2, 8, 9, 64).contiguous()
+        got = ops.bn_act_fwd(zz.to(DEV).to(torch.bfloat16), None, None, "gelu").float().cpu()
+        want = F.gelu(zz.to(torch.bfloat16).float())
+        assert ((got - want).abs() <= want.abs() * 2.0 ** -8 + 1e-6).all()
 
 
 def _check_bn_sums(s1, s2, raw_nhwc, ref_nchw):
@@ -586,7 +627,7 @@ def test_stem_fwd_and_wgrad(lib, cin, k, stride, pad):
 
 @pytest.mark.parametrize("act", ["leaky", "silu", "relu"])
 @pytest.mark.parametrize("c", [32, 64, 192, 1024])
-def test_bn_act_train_fwd_bwd(lib, act, c):
+def test_bn_act_train_fwd_bwd(lib, act, c, monkeypatch):
     """Two-phase train-mode BN + activation (+residual) against autograd on the CPU."""
     ops = _ops(lib)
     n, h, w = 2, 10, 12
@@ -612,12 +653,18 @@ def test_bn_act_train_fwd_bwd(lib, act, c):
     y = ops.bn_act_fwd(raw_d, scale, shift, act, res=nhwc(res))
     assert_close_bf16(to_nchw(y), out_ref.detach(), "bn_act_fwd")
     # fused single-pass variant (finalize folded into the streaming kernel): same outputs, same running stats
-    rm_f, rv_f = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
-    y_f, mean_f, invstd_f, scale_f, shift_f = ops.bn_train_fwd(raw_d, s1, s2, n * h * w, 1e-5, 0.1, gamma.detach().to(DEV),
-                                                               beta.detach().to(DEV), rm_f, rv_f, act, res=nhwc(res))
-    assert_close_bf16(to_nchw(y_f), to_nchw(y), "fused bn fwd vs two-kernel", rel=1e-3)
-    for a_, b_ in ((mean_f, mean), (invstd_f, invstd), (scale_f, scale), (shift_f, shift), (rm_f, rm_d), (rv_f, rv_d)):
-        torch.testing.assert_close(a_, b_, rtol=1e-5, atol=1e-6)
+    # (both settings of the A/B switch: the one-launch kernel and the finalize + apply pair behind the same call)
+    for no_fuse in (False, True):
+        monkeypatch.setattr(ops, "_NO_BN_FUSE", no_fuse)
+        rm_f, rv_f = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+        y_f, mean_f, invstd_f, scale_f, shift_f = ops.bn_train_fwd(raw_d, s1, s2, n * h * w, 1e-5, 0.1, gamma.detach().to(DEV),
+                                                                   beta.detach().to(DEV), rm_f, rv_f, act, res=nhwc(res))
+        assert_close_bf16(to_nchw(y_f), to_nchw(y), "fused bn fwd vs two-kernel", rel=1e-3)
+        for a_, b_ in ((mean_f, mean), (invstd_f, invstd), (scale_f, scale), (shift_f, shift), (rm_f, rm_d), (rv_f, rv_d)):
+            torch.testing.assert_close(a_, b_, rtol=1e-5, atol=1e-6)
+        y_n, *_ = ops.bn_train_fwd(raw_d, s1, s2, n * h * w, 1e-5, 0.1, gamma.detach().to(DEV), beta.detach().to(DEV),
+                                   torch.zeros(c, device=DEV), torch.ones(c, device=DEV), act)
+        assert_close_bf16(to_nchw(y_n), (out_ref - res).detach(), "fused bn fwd without residual")
     d_raw, dgamma, dbeta = ops.bn_act_bwd(nhwc(dy), raw_d, scale, shift, mean, invstd, gamma.detach().to(DEV), act)
     assert_close_bf16(to_nchw(d_raw), raw.grad, "bn d_raw", rel=1e-2, frac=2.0 ** -5)
     torch.testing.assert_close(dgamma.cpu(), gamma.grad, rtol=5e-3, atol=5e-2)
