@@ -1,6 +1,7 @@
 // Library-level plumbing of the C-ABI: error string, launch counter, device watchdog word.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace uavdet {
 
@@ -22,6 +23,13 @@ unsigned int* watchdog_word() {
   unsigned int* p = nullptr;
   cudaGetSymbolAddress((void**)&p, g_watchdog);
   return p;
+}
+
+int pdl_mask() {
+  // off by default: measured on the BaselineModel step (B200, same box, 20 steps each): no attribute 26.63 / 26.69 ms,
+  // implicit GEMM only 26.61, BatchNorm forward only 26.82, BatchNorm backward (reduce + apply) 27.43, all four 27.85
+  static const int mask = getenv("UAVDET_PDL_MASK") ? atoi(getenv("UAVDET_PDL_MASK")) : 0;
+  return mask;
 }
 
 static std::atomic<int> g_sm_margin{0};

@@ -73,10 +73,50 @@ struct PerDeviceOnce {
   }
 };
 
+// ---- programmatic dependent launch (PDL): an experiment that stayed a switch ----------------------------------------
+// A training step is ~560 dependent launches of 10-700 us.  With cudaLaunchAttributeProgrammaticStreamSerialization a
+// kernel that calls pdl_launch_dependents() lets its successor be launched as soon as every CTA of the grid has started
+// (the successor's CTAs take the SMs this grid's CTAs leave and run their prologue), and the successor's pdl_wait()
+// returns once the predecessor grid has COMPLETED and its writes are visible, so the data flow is unchanged.  Both
+// instructions are no-ops for a kernel launched without the attribute.  Measured (UAVDET_PDL_MASK, see pdl_mask()):
+// neutral for the implicit GEMM launches and 0.2-1.2 ms SLOWER per step for the BatchNorm kernels — their early-resident
+// blocks (parked in pdl_wait) hold the registers the weight-gradient kernel of the side stream needs to get onto the SM,
+// i.e. they trade the overlap that matters (tensor-core work under the HBM-bound passes) for launch latency that the
+// CUDA graph had already made small.  Default: off.
+// which launches carry the attribute (UAVDET_PDL_MASK, A/B): 1 implicit GEMM, 2 BatchNorm forward, 4 BatchNorm backward
+// reduce, 8 BatchNorm backward apply
+enum { kPdlIgemm = 1, kPdlBnFwd = 2, kPdlBnReduce = 4, kPdlBnApply = 8 };
+int pdl_mask();
+inline bool pdl_enabled(int who) { return (pdl_mask() & who) != 0; }
+// fills attrs[*n] with the PDL attribute when enabled
+inline void pdl_attr(cudaLaunchAttribute* attrs, unsigned* n, int who) {
+  if (!pdl_enabled(who)) return;
+  attrs[*n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[*n].val.programmaticStreamSerializationAllowed = 1;
+  ++*n;
+}
+// <<<grid, block, smem, stream>>> with the PDL attribute
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int who, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  unsigned n = 0;
+  pdl_attr(attr, &n, who);
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- device helpers -------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -115,6 +115,8 @@ template <bool HAS_RES>
 __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(View raw, const float* __restrict__ scale, const float* __restrict__ shift, int act,
                   const __nv_bfloat16* __restrict__ res, int res_ld, int reverse, View y) {
+  pdl_launch_dependents();
+  pdl_wait();
   const PixLane L = pix_lane(raw.c);
   if (!L.active) return;
   float s[8], t[8];
@@ -173,6 +175,8 @@ bn_train_fwd_kernel(View raw, const float* __restrict__ sum, const float* __rest
                     float* __restrict__ invstd_out, float* __restrict__ scale_out, float* __restrict__ shift_out, int act,
                     const __nv_bfloat16* __restrict__ res, int res_ld, View y) {
   __shared__ float sh_s[256], sh_t[256];
+  pdl_launch_dependents();
+  pdl_wait();
   const PixLane L = pix_lane(raw.c);
   {
     const int G = raw.c >> 3;
@@ -245,10 +249,17 @@ bn_train_fwd_kernel(View raw, const float* __restrict__ sum, const float* __rest
 }
 
 // ---- BN backward, phase 1: per-channel sums of dz and dz*raw ---------------------------------
-__global__ void __launch_bounds__(256)
+// At most 85 registers: the kernel runs beside the weight-gradient kernel of the previous layer (192 threads x 96
+// registers and 176 KB of shared memory per SM), and its two blocks per SM only fit next to it below 92 registers — at
+// 98 the second block of every SM waited for the first, i.e. the pass ran in two waves whenever a weight gradient was
+// in flight.
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 bn_bwd_reduce_kernel(View dy, View raw, const float* __restrict__ scale, const float* __restrict__ shift, int act,
                      float* __restrict__ sum_dz, float* __restrict__ sum_dzr) {
   __shared__ float red[256 * 16];
+  pdl_launch_dependents();
+  pdl_wait();
   const PixLane L = pix_lane(dy.c);
   float a_dz[8], a_dzr[8];
 #pragma unroll
@@ -361,6 +372,8 @@ bn_bwd_apply_fused_kernel(View dy, View raw, const float* __restrict__ scale, co
                           const float* __restrict__ sum_dz, const float* __restrict__ sum_dzr,
                           const float* __restrict__ mean, const float* __restrict__ invstd, float inv_count, int act,
                           float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate, int reverse, View dr) {
+  pdl_launch_dependents();
+  pdl_wait();
   const PixLane L = pix_lane(dy.c);
   if (!L.active) return;
   float s[8], t[8], a1[8], a0[8];
@@ -1150,9 +1163,9 @@ extern "C" int uavdet_bn_act_fwd(const uavdet_act* raw, const float* scale, cons
   dim3 grid = stream_grid(raw, 8);
   static const int reverse = getenv("UAVDET_BN_FWD_REVERSE") ? atoi(getenv("UAVDET_BN_FWD_REVERSE")) : 0;
   if (res)
-    bn_act_fwd_kernel<true><<<grid, 256, 0, ST>>>(r, scale, shift, act, (const __nv_bfloat16*)res->ptr, res->ld, reverse, o);
+    launch_pdl(kPdlBnFwd, bn_act_fwd_kernel<true>, grid, dim3(256), 0, ST, r, scale, shift, act, (const __nv_bfloat16*)res->ptr, res->ld, reverse, o);
   else
-    bn_act_fwd_kernel<false><<<grid, 256, 0, ST>>>(r, scale, shift, act, nullptr, 0, reverse, o);
+    launch_pdl(kPdlBnFwd, bn_act_fwd_kernel<false>, grid, dim3(256), 0, ST, r, scale, shift, act, (const __nv_bfloat16*)nullptr, 0, reverse, o);
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }
@@ -1164,7 +1177,8 @@ extern "C" int uavdet_bn_act_fwd(const uavdet_act* raw, const float* scale, cons
 static void prefer_max_smem_carveout_once() {
   static PerDeviceOnce once;
   once.run([] {
-    cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(bn_bwd_reduce_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(bn_bwd_reduce_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(bn_bwd_apply_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(bn_bwd_apply_fused_kernel<4, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(bn_bwd_apply_fused_kernel<4, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1186,8 +1200,13 @@ extern "C" int uavdet_bn_act_bwd_reduce(const uavdet_act* dy, const uavdet_act* 
   // few long-lived blocks: every block ends with one atomic per channel sum, and thousands of blocks hammering
   // the same 2*c addresses serialise in L2 (the kernel ran at 1.5 TB/s with 1,600 blocks)
   static const int bps = getenv("UAVDET_BN_REDUCE_BPS") ? atoi(getenv("UAVDET_BN_REDUCE_BPS")) : 2;
-  bn_bwd_reduce_kernel<<<stream_grid(dy, 16, bps), 256, 0, ST>>>(mkview(dy), mkview(raw), scale, shift, act, sum_dz,
-                                                            sum_dzr);
+  static const int minb = getenv("UAVDET_BN_REDUCE_MINB") ? atoi(getenv("UAVDET_BN_REDUCE_MINB")) : 3;   // A/B switch
+  if (minb >= 3)
+    launch_pdl(kPdlBnReduce, bn_bwd_reduce_kernel<3>, stream_grid(dy, 16, bps), dim3(256), 0, ST, mkview(dy), mkview(raw), scale, shift, act,
+               sum_dz, sum_dzr);
+  else
+    launch_pdl(kPdlBnReduce, bn_bwd_reduce_kernel<1>, stream_grid(dy, 16, bps), dim3(256), 0, ST, mkview(dy), mkview(raw), scale, shift, act,
+               sum_dz, sum_dzr);
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }
@@ -1231,13 +1250,12 @@ extern "C" int uavdet_bn_train_fwd(const uavdet_act* raw, const float* sum, cons
   dim3 grid = stream_grid(raw, 8);
   if (res) {
     if ((rc = check_view(res, "bn_train_fwd res")) || (rc = same_shape(raw, res, "bn_train_fwd res"))) return rc;
-    bn_train_fwd_kernel<true><<<grid, 256, 0, ST>>>(mkview(raw), sum, sumsq, count, eps, momentum, gamma, beta,
-                                                   running_mean, running_var, mean, invstd, scale, shift, act,
-                                                   (const __nv_bfloat16*)res->ptr, res->ld, mkview(y));
+    launch_pdl(kPdlBnFwd, bn_train_fwd_kernel<true>, grid, dim3(256), 0, ST, mkview(raw), sum, sumsq, count, eps, momentum, gamma, beta,
+               running_mean, running_var, mean, invstd, scale, shift, act, (const __nv_bfloat16*)res->ptr, res->ld,
+               mkview(y));
   } else {
-    bn_train_fwd_kernel<false><<<grid, 256, 0, ST>>>(mkview(raw), sum, sumsq, count, eps, momentum, gamma, beta,
-                                                    running_mean, running_var, mean, invstd, scale, shift, act, nullptr,
-                                                    0, mkview(y));
+    launch_pdl(kPdlBnFwd, bn_train_fwd_kernel<false>, grid, dim3(256), 0, ST, mkview(raw), sum, sumsq, count, eps, momentum, gamma, beta,
+               running_mean, running_var, mean, invstd, scale, shift, act, (const __nv_bfloat16*)nullptr, 0, mkview(y));
   }
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
@@ -1263,9 +1281,9 @@ extern "C" int uavdet_bn_act_bwd_apply_fused(const uavdet_act* dy, const uavdet_
   static const int reverse = getenv("UAVDET_BN_APPLY_REVERSE") ? atoi(getenv("UAVDET_BN_APPLY_REVERSE")) : 0;
   prefer_max_smem_carveout_once();
 #define UAVDET_BN_APPLY(U, MINB, BPS)                                                                                       \
-  bn_bwd_apply_fused_kernel<U, MINB><<<stream_grid(dy, ppt, BPS), 256, 0, ST>>>(                                            \
-      mkview(dy), mkview(raw), scale, shift, sum_dz, sum_dzr, mean, invstd, (float)(1.0 / count), act, dgamma, dbeta,      \
-      accumulate, reverse, mkview(d_raw))
+  launch_pdl(kPdlBnApply, bn_bwd_apply_fused_kernel<U, MINB>, stream_grid(dy, ppt, BPS), dim3(256), 0, ST,                                 \
+             mkview(dy), mkview(raw), scale, shift, sum_dz, sum_dzr, mean, invstd, (float)(1.0 / count), act, dgamma, dbeta, \
+             accumulate, reverse, mkview(d_raw))
   switch (variant) {
     case 1: UAVDET_BN_APPLY(4, 3, 24); break;
     case 2: UAVDET_BN_APPLY(2, 4, 32); break;

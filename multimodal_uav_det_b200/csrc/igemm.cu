@@ -322,6 +322,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();     // the next kernel of the stream may be launched; its CTAs take the SMs this grid leaves
 
   const uint32_t rank = kTwo ? cluster_ctarank() : 0u;
   const bool halo = !kTwo && P.halo != 0;
@@ -383,6 +384,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   if (kTwo) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // barriers, TMEM and descriptors are ready; nothing of the predecessor kernel's output has been touched yet
+  pdl_wait();
 
   const int num_kb = P.num_taps * P.kc_per_tap;
 
@@ -1242,11 +1245,16 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
   cfg.blockDim = dim3(kIgemmThreads);
   cfg.dynamicSmemBytes = (size_t)smem_bytes;
   cfg.stream = st;
-  cudaLaunchAttribute cattr[1];
+  cudaLaunchAttribute cattr[2];
   cattr[0].id = cudaLaunchAttributeClusterDimension;
   cattr[0].val.clusterDim.x = 2; cattr[0].val.clusterDim.y = 1; cattr[0].val.clusterDim.z = 1;
-  cfg.attrs = cattr;
+  cfg.attrs = two ? cattr : cattr + 1;
   cfg.numAttrs = two ? 1 : 0;
+  {
+    unsigned n_pdl = 0;
+    pdl_attr(cattr + 1, &n_pdl, kPdlIgemm);
+    cfg.numAttrs += n_pdl;
+  }
 #define UAVDET_LAUNCH_IGEMM(K, T)                                                                                      \
   do {                                                                                                                 \
     UAVDET_CUDA(attr_once[K][T].run([] {                                                                               \
