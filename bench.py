@@ -389,9 +389,11 @@ class ConvTimer:
             def wrapper(*a, **k):
                 slot = 2 * len(rec)
                 ops.timestamp(stamps, slot)
+                l0 = ops.launch_count()
                 out = fn(*a, **k)
+                n_launch = ops.launch_count() - l0      # kernels of the call (a plane-by-plane stride-2 data gradient is four)
                 ops.timestamp(stamps, slot + 1)
-                rec.append((kind, flops_of(a, k), slot))
+                rec.append((kind, flops_of(a, k), slot, n_launch))
                 return out
             return wrapper
 
@@ -435,29 +437,35 @@ class ConvTimer:
             ops.conv_out_hw(a[0].shape[2], a[0].shape[3], a[2], a[3], a[4])[0] * ops.conv_out_hw(a[0].shape[2], a[0].shape[3], a[2], a[3], a[4])[1])
         ops.stem_mma_fwd = timed(self._orig_stem[0], "stem_fwd", stem_bytes)
         ops.stem_mma_wgrad = timed(self._orig_stem[1], "stem_wgrad", stem_bytes)
+        # the fused objectness + bbox head convolutions are igemm_kernel launches too (N = 16 epilogue of their own)
+        self._orig_head = ops.conv_head
+        ops.conv_head = timed(self._orig_head, "igemm",
+                              lambda a, kw: 2.0 * a[0].shape[0] * a[0].shape[1] * a[0].shape[2] * a[0].shape[3] * 5 * a[3])
         self._orig_bn = None
         if os.environ.get("UAVDET_BENCH_DEBUG"):
             # debug table only: the BatchNorm passes too, with their algorithmic bytes in place of flops
             # (forward: read raw [+ residual] + write y; backward: reduce reads dy, raw; apply reads both, writes d_raw)
-            self._orig_bn = (ops.bn_act_fwd, ops.bn_act_bwd)
-            ops.bn_act_fwd = timed(self._orig_bn[0], "bn_fwd",
-                                   lambda a, kw: (3.0 if kw.get("res") is not None else 2.0) * a[0].numel() * 2)
+            self._orig_bn = (ops.bn_act_fwd, ops.bn_act_bwd, ops.bn_train_fwd)
+            fwd_bytes = lambda a, kw: (3.0 if kw.get("res") is not None else 2.0) * a[0].numel() * 2
+            ops.bn_act_fwd = timed(self._orig_bn[0], "bn_fwd", fwd_bytes)
             ops.bn_act_bwd = timed(self._orig_bn[1], "bn_bwd", lambda a, kw: 5.0 * a[0].numel() * 2)
+            ops.bn_train_fwd = timed(self._orig_bn[2], "bn_fwd", fwd_bytes)
         return self
 
     def __exit__(self, *exc):
         self.ops.conv_fwd, self.ops.conv_dgrad, self.ops.conv_wgrad, self.ops.conv_dgrad_s2d = self._orig
         self.ops.stem_mma_fwd, self.ops.stem_mma_wgrad = self._orig_stem
         self.ops.conv_dgrad_s2_fused = self._orig_s2f
+        self.ops.conv_head = self._orig_head
         if self._orig_bn is not None:
-            self.ops.bn_act_fwd, self.ops.bn_act_bwd = self._orig_bn
+            self.ops.bn_act_fwd, self.ops.bn_act_bwd, self.ops.bn_train_fwd = self._orig_bn
 
     def summary(self):
         self.torch.cuda.synchronize()
         t = self.stamps.cpu().tolist()
         agg = {}
-        t_first = min((t[slot] for _, _, slot in self.records), default=0)
-        for i, (kind, fl, slot) in enumerate(self.records):
+        t_first = min((t[r[2]] for r in self.records), default=0)
+        for i, (kind, fl, slot, n_launch) in enumerate(self.records):
             sec = (t[slot + 1] - t[slot]) * 1e-9
             if os.environ.get("UAVDET_BENCH_DEBUG"):
                 at = f" @{(t[slot] - t_first) * 1e-3:.0f}" if os.environ.get("UAVDET_BENCH_TIMELINE") else ""
@@ -468,7 +476,7 @@ class ConvTimer:
             a = agg.setdefault(kind, [0.0, 0.0, 0])
             a[0] += fl
             a[1] += sec
-            a[2] += 1
+            a[2] += n_launch
         return {k: {"flops": v[0], "seconds": v[1], "launches": v[2]} for k, v in agg.items()}
 
 

@@ -15,7 +15,7 @@ def main(path):
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "nsecond": 1e-9, "us": 1e-6, "usecond": 1e-6,
              "ms": 1e-3, "msecond": 1e-3, "s": 1.0, "second": 1.0}
     for r in csv.DictReader(lines):
-        name = re.sub(r"^void ", "", re.sub(r"[<(].*", "", r["Kernel Name"]))
+        name = re.sub(r"^void ", "", re.sub(r"[<(].*", "", r["Kernel Name"])).split("::")[-1]
         if name not in ("igemm_kernel", "wgrad_kernel"):
             continue
         v = float(r["Metric Value"].replace(",", "")) * scale[r["Metric Unit"]]

@@ -27,3 +27,8 @@ python bench.py --steps 20 --warmup 5 > gpurun_out/r02_ev_bench_full.json 2> gpu
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_ev_bench_reference.json 2> gpurun_out/r02_ev_bench_reference.err
 python bench.py --impl torch-gpu --steps 10 --warmup 3 > gpurun_out/r02_ev_bench_torch_gpu.json 2> gpurun_out/r02_ev_bench_torch_gpu.err
 du -sh gpurun_out
+for m in dyyolo dysoem rtm-infer; do
+  python bench.py --model $m --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02_ev_bench_$m.json 2> gpurun_out/r02_ev_bench_$m.err
+done
+python tools/bench_infer.py > gpurun_out/r02_ev_inference_configs.jsonl 2> gpurun_out/r02_ev_inference.err
+ls -la gpurun_out | tail -30
