@@ -432,6 +432,83 @@ bn_bwd_apply_fused_kernel(View dy, View raw, const float* __restrict__ scale, co
   }
 }
 
+// ---- BN backward, phase 2, coefficients in shared memory -----------------------------------------------------------
+// Same math as bn_bwd_apply_fused_kernel.  The four per-channel coefficient vectors (scale, shift, k1, k0: 32 registers
+// per thread there) live in shared memory instead — derived once per block by its first threads, one channel each —
+// and are read back with 16-byte loads at the point of use, which frees the registers for U pixel rows x two operands
+// of loads in flight per thread at <= 85 registers.  That pass shares the SM with the weight-gradient kernel of the
+// previous layer (18 K registers, 176 KB of shared memory): two 256-thread blocks fit beside it either way, and with
+// U = 4 they keep 64 KB of loads in flight instead of 32 KB; beside that kernel HBM ran at 4.1 TB/s, i.e. the pass was
+// latency-bound, not bandwidth-bound.
+template <int U, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+bn_bwd_apply_smem_kernel(View dy, View raw, const float* __restrict__ scale, const float* __restrict__ shift,
+                         const float* __restrict__ sum_dz, const float* __restrict__ sum_dzr,
+                         const float* __restrict__ mean, const float* __restrict__ invstd, float inv_count, int act,
+                         float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate, View dr) {
+  __shared__ __align__(16) float cs[4][256];            // scale, shift, k1, k0 of the block's (<= 256) channels
+  pdl_launch_dependents();
+  pdl_wait();
+  const PixLane L = pix_lane(dy.c);
+  const int G = dy.c >> 3;
+  const int Gb = G < 32 ? G : 32;
+  const int cbase = blockIdx.y * Gb * 8;
+  {
+    const int c = cbase + threadIdx.x;
+    if ((int)threadIdx.x < Gb * 8 && c < dy.c) {
+      const float sc = __ldg(scale + c), is = __ldg(invstd + c), sd = __ldg(sum_dz + c), mu = __ldg(mean + c);
+      const float dg = is * (__ldg(sum_dzr + c) - mu * sd);
+      const float a1 = -sc * is * dg * inv_count;
+      cs[0][threadIdx.x] = sc;
+      cs[1][threadIdx.x] = __ldg(shift + c);
+      cs[2][threadIdx.x] = a1;
+      cs[3][threadIdx.x] = -sc * sd * inv_count - a1 * mu;
+      if (blockIdx.x == 0) {
+        dgamma[c] = accumulate ? dgamma[c] + dg : dg;
+        dbeta[c] = accumulate ? dbeta[c] + sd : sd;
+      }
+    }
+  }
+  __syncthreads();
+  if (!L.active) return;
+  const int o = L.c - cbase;
+  const float4* c4 = reinterpret_cast<const float4*>(&cs[0][0]);
+  auto body = [&](const uint4& din, const uint4& rin, long long px) {
+    float d[8], r[8];
+    unpack8(din, d);
+    unpack8(rin, r);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 s4 = c4[(0 * 256 + o) / 4 + h], t4 = c4[(1 * 256 + o) / 4 + h];
+      const float4 a4 = c4[(2 * 256 + o) / 4 + h], b4 = c4[(3 * 256 + o) / 4 + h];
+      const float sv[4] = {s4.x, s4.y, s4.z, s4.w}, tv[4] = {t4.x, t4.y, t4.z, t4.w};
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = 4 * h + j;
+        const float dz = d[q] * act_grad_rt(act, fmaf(r[q], sv[j], tv[j]));
+        d[q] = fmaf(sv[j], dz, fmaf(av[j], r[q], bv[j]));
+      }
+    }
+    *reinterpret_cast<uint4*>(dr.p + px * dr.ld + L.c) = pack8(d);
+  };
+  long long px = L.px0;
+  for (; px + (U - 1) * L.step < dy.npix; px += U * L.step) {
+    uint4 a[U], b[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long q = px + u * L.step;
+      a[u] = __ldcs(reinterpret_cast<const uint4*>(dy.p + q * dy.ld + L.c));
+      b[u] = __ldcs(reinterpret_cast<const uint4*>(raw.p + q * raw.ld + L.c));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) body(a[u], b[u], px + u * L.step);
+  }
+  for (; px < dy.npix; px += L.step)
+    body(__ldcs(reinterpret_cast<const uint4*>(dy.p + px * dy.ld + L.c)),
+         __ldcs(reinterpret_cast<const uint4*>(raw.p + px * raw.ld + L.c)), px);
+}
+
 __global__ void act_bwd_kernel(View dy, View raw, const float* __restrict__ scale,
                                const float* __restrict__ shift, int act, View dx) {
   const int c8 = dy.c >> 3;
@@ -1183,6 +1260,8 @@ static void prefer_max_smem_carveout_once() {
     cudaFuncSetAttribute(bn_bwd_apply_fused_kernel<4, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(bn_bwd_apply_fused_kernel<4, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(bn_bwd_apply_fused_kernel<2, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(bn_bwd_apply_smem_kernel<4, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(bn_bwd_apply_smem_kernel<8, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     return cudaFuncSetAttribute(bn_bwd_apply_fused_kernel<2, 3>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                 cudaSharedmemCarveoutMaxShared);
   });
@@ -1284,6 +1363,18 @@ extern "C" int uavdet_bn_act_bwd_apply_fused(const uavdet_act* dy, const uavdet_
   launch_pdl(kPdlBnApply, bn_bwd_apply_fused_kernel<U, MINB>, stream_grid(dy, ppt, BPS), dim3(256), 0, ST,                                 \
              mkview(dy), mkview(raw), scale, shift, sum_dz, sum_dzr, mean, invstd, (float)(1.0 / count), act, dgamma, dbeta, \
              accumulate, reverse, mkview(d_raw))
+  if (variant == 5 || variant == 6) {
+    // coefficients in shared memory (see bn_bwd_apply_smem_kernel)
+    const dim3 grid = stream_grid(dy, ppt * 2, 24);
+    if (variant == 5)
+      launch_pdl(kPdlBnApply, bn_bwd_apply_smem_kernel<4, 3>, grid, dim3(256), 0, ST, mkview(dy), mkview(raw), scale, shift, sum_dz,
+                 sum_dzr, mean, invstd, (float)(1.0 / count), act, dgamma, dbeta, accumulate, mkview(d_raw));
+    else
+      launch_pdl(kPdlBnApply, bn_bwd_apply_smem_kernel<8, 2>, grid, dim3(256), 0, ST, mkview(dy), mkview(raw), scale, shift, sum_dz,
+                 sum_dzr, mean, invstd, (float)(1.0 / count), act, dgamma, dbeta, accumulate, mkview(d_raw));
+    UAVDET_LAUNCH_CHECK();
+    return UAVDET_OK;
+  }
   switch (variant) {
     case 1: UAVDET_BN_APPLY(4, 3, 24); break;
     case 2: UAVDET_BN_APPLY(2, 4, 32); break;
