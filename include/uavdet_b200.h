@@ -351,6 +351,12 @@ int uavdet_attn_mlp_bwd(const float* attn, const float* d_attn, const float* hid
 int uavdet_dyn_bwd_contract(const float* dwb, int n, int K, const float* attn, const float* bank, int O, int I,
                             int k, int packed, float* d_bank, float* d_attn, void* stream);
 
+/* Backward of the per-sample bias bias[b] = attn[b] @ bias_bank of a dynamic conv (DynamicSOEM, DySOEM_SimFPN.py:56-60;
+ * autograd of that matmul): with g = scale * pooled_grad (n, O) — the per-sample channel sums of the output gradient —
+ *   d_bias_bank[kk][o] = sum_b attn[b][kk] * g[b][o]   (written),   d_attn[b][kk] += sum_o g[b][o] * bias_bank[kk][o]. */
+int uavdet_dyn_bias_bwd(const float* pooled_grad, float scale, int n, int K, int O, const float* attn,
+                        const float* bias_bank, float* d_bias_bank, float* d_attn, void* stream);
+
 /* ---- K3 / K6 / K7: RTMUAVDet memory-bound ops -------------------------------------------- */
 /* Per-sample depthwise dynamic conv + residual (MDyConv.forward, RTMUAVDet.py:80-98):
  * y[b,p,c] = x[b,p,c] + channel_w[b,c] * sum_t kernel_w[b,t] * x[b,p+t,c]; k odd, pad = k/2.      */

@@ -89,6 +89,7 @@ SIGNATURES = {
     "uavdet_attn_mlp_bwd": (_i, [_P, _P, _P, _P, _i, _i, _P, _i, _P, _i, _f, _f, _P, _P, _P, _P, _P, _P, _P]),
     "uavdet_dyn_aggregate": (_i, [_P, _i, _i, _P, _i, _i, _i, _i, _P, _P, _P, _P]),
     "uavdet_dyn_bwd_contract": (_i, [_P, _i, _i, _P, _P, _i, _i, _i, _i, _P, _P, _P]),
+    "uavdet_dyn_bias_bwd": (_i, [_P, _f, _i, _i, _i, _P, _P, _P, _P, _P]),
     "uavdet_dwdynconv_fwd": (_i, [_AP, _P, _P, _i, _i, _AP, _P]),
     "uavdet_linear": (_i, [_P, _i, _i, _P, _P, _i, _i, _P, _P]),
     "uavdet_groupnorm1": (_i, [_AP, _AP, _P, _P, _f, _P, _AP, _P]),

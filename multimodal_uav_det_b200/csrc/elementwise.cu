@@ -1212,6 +1212,29 @@ __global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restri
   }
 }
 
+// ---- bias bank of a dynamic conv (DynamicSOEM, DySOEM_SimFPN.py:56-60): bias[b] = attn[b] @ bias_bank ---------------
+// d_bias_bank[kk][o] = sum_b attn[b][kk] * g[b][o];  d_attn[b][kk] += sum_o g[b][o] * bias_bank[kk][o], where
+// g = scale * pooled_grad is the per-sample channel sum of the output gradient (pool kernel x pixel count).  n <= 128,
+// K <= 8, O <= 1024: a few hundred thousand MACs, one thread per output value (the two torch matmuls this replaces were
+// the last cuBLAS launches of the DySOEM_SimFPN step).
+__global__ void dyn_bias_bwd_kernel(const float* __restrict__ g, float scale, int n, int K, int O,
+                                    const float* __restrict__ attn, const float* __restrict__ bias_bank,
+                                    float* __restrict__ d_bias_bank, float* __restrict__ d_attn) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < K * O) {
+    const int kk = i / O, o = i - kk * O;
+    float acc = 0.f;
+    for (int b = 0; b < n; ++b) acc = fmaf(attn[b * K + kk], g[(size_t)b * O + o], acc);
+    d_bias_bank[i] = acc * scale;
+  } else if (i < K * O + n * K) {
+    const int j = i - K * O;
+    const int b = j / K, kk = j - b * K;
+    float acc = 0.f;
+    for (int o = 0; o < O; ++o) acc = fmaf(g[(size_t)b * O + o], bias_bank[(size_t)kk * O + o], acc);
+    d_attn[j] += acc * scale;
+  }
+}
+
 }  // namespace uavdet
 
 using namespace uavdet;
@@ -1530,6 +1553,16 @@ extern "C" int uavdet_dyn_bwd_contract(const float* dwb, int n, int K, const flo
   const long long blocks = (per + (long long)kDbcThreads * kDbcE - 1) / ((long long)kDbcThreads * kDbcE);
   dyn_bwd_contract_kernel<<<(unsigned)blocks, kDbcThreads, sh, ST>>>(dwb, n, K, attn, bank, O, I, k * k, packed, d_bank,
                                                                     d_attn);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_dyn_bias_bwd(const float* pooled_grad, float scale, int n, int K, int O, const float* attn,
+                                   const float* bias_bank, float* d_bias_bank, float* d_attn, void* stream) {
+  UAVDET_CHECK_ARG(pooled_grad && attn && bias_bank && d_bias_bank && d_attn && n > 0 && K > 0 && O > 0,
+                   "dyn_bias_bwd: bad arguments");
+  const int work = K * O + n * K;
+  dyn_bias_bwd_kernel<<<ceil_div(work, 128), 128, 0, ST>>>(pooled_grad, scale, n, K, O, attn, bias_bank, d_bias_bank, d_attn);
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }

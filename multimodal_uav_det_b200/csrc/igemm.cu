@@ -77,21 +77,35 @@ __device__ __forceinline__ int num_iters(const IgemmParams& P) {
   return total > first ? (total - first + step - 1) / step : 0;
 }
 
+// 16 bytes of a per-channel epilogue vector: from the CTA's staged copy in shared memory (an asm load the compiler may
+// schedule freely — the copy is read-only once the epilogue warps have passed their barrier; as a generic load it had to
+// stay ordered with the staging-row stores and the ALU-bound GELU layers lost 15 %) or from global memory (read-only path).
+__device__ __forceinline__ float4 load_epc4(const float* p, bool staged) {
+  float4 r;
+  if (staged) {
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+        : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  } else {
+    r = __ldg(reinterpret_cast<const float4*>(p));
+  }
+  return r;
+}
+
 // 32 accumulator columns of this lane's row -> (scale, shift, act, residual), in place.
 template <int ACT>
 __device__ __forceinline__ void affine_act(float (&v)[32], const float* scale, int cg, const float* shift,
-                                           const uint4 (&res)[4], bool have_res) {
+                                           const uint4 (&res)[4], bool have_res, bool staged) {
   if (scale) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      float4 s = __ldg(reinterpret_cast<const float4*>(scale + cg + i));
+      const float4 s = load_epc4(scale + cg + i, staged);
       v[i] *= s.x; v[i + 1] *= s.y; v[i + 2] *= s.z; v[i + 3] *= s.w;
     }
   }
   if (shift) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      float4 s = __ldg(reinterpret_cast<const float4*>(shift + cg + i));
+      const float4 s = load_epc4(shift + cg + i, staged);
       v[i] += s.x; v[i + 1] += s.y; v[i + 2] += s.z; v[i + 3] += s.w;
     }
   }
@@ -115,9 +129,11 @@ __device__ __forceinline__ void affine_act(float (&v)[32], const float* scale, i
 // grew to 37,000 instructions (595 KB) and the epilogue warps thrashed the instruction cache.
 // Everything it needs from the kernel parameters arrives in registers (`cfg`, `scale`): read through a reference,
 // the fields became a chain of control-dependent generic loads from the parameter bank (~1,000 cycles per call).
-//   cfg bit 0: statistics epilogue; bits 1-3: activation; bit 4: residual operand; bit 5: it is in the staging row
+//   cfg bit 0: statistics epilogue; bits 1-3: activation; bit 4: residual operand; bit 5: it is in the staging row;
+//   bit 6: scale / shift point into the CTA's staged copy in shared memory
 __device__ __forceinline__ uint32_t chunk_cfg(const IgemmParams& P) {
-  return (P.epi == UAVDET_EPI_STATS ? 1u : 0u) | ((uint32_t)P.act << 1) | (P.res ? 16u : 0u) | (P.res_tma ? 32u : 0u);
+  return (P.epi == UAVDET_EPI_STATS ? 1u : 0u) | ((uint32_t)P.act << 1) | (P.res ? 16u : 0u) | (P.res_tma ? 32u : 0u) |
+         ((P.epi != UAVDET_EPI_STATS && P.epi != UAVDET_EPI_HEAD && P.epc_floats > 0) ? 64u : 0u);
 }
 // epilogue math of one 32-column chunk (accumulator values in r) + bf16 pack + swizzled staging store
 // kKind: the kernel instance (see igemm_kernel): 0 statistics epilogue, 1 affine without activation, 2 affine with
@@ -155,15 +171,16 @@ __device__ __forceinline__ void finish_chunk(uint32_t cfg, const float* scale, c
 #pragma unroll
       for (int j = 0; j < 4; ++j) rr[j] = make_uint4(0u, 0u, 0u, 0u);
     }
+    const bool staged = (cfg & 64u) != 0u;
     if (kKind == 1) {
-      affine_act<UAVDET_ACT_NONE>(v, scale, cg, shift, rr, have_res);
+      affine_act<UAVDET_ACT_NONE>(v, scale, cg, shift, rr, have_res, staged);
     } else {
       switch ((cfg >> 1) & 7u) {
-        case UAVDET_ACT_LEAKY: affine_act<UAVDET_ACT_LEAKY>(v, scale, cg, shift, rr, have_res); break;
-        case UAVDET_ACT_SILU: affine_act<UAVDET_ACT_SILU>(v, scale, cg, shift, rr, have_res); break;
-        case UAVDET_ACT_RELU: affine_act<UAVDET_ACT_RELU>(v, scale, cg, shift, rr, have_res); break;
-        case UAVDET_ACT_GELU: affine_act<UAVDET_ACT_GELU>(v, scale, cg, shift, rr, have_res); break;
-        default: affine_act<UAVDET_ACT_NONE>(v, scale, cg, shift, rr, have_res); break;
+        case UAVDET_ACT_LEAKY: affine_act<UAVDET_ACT_LEAKY>(v, scale, cg, shift, rr, have_res, staged); break;
+        case UAVDET_ACT_SILU: affine_act<UAVDET_ACT_SILU>(v, scale, cg, shift, rr, have_res, staged); break;
+        case UAVDET_ACT_RELU: affine_act<UAVDET_ACT_RELU>(v, scale, cg, shift, rr, have_res, staged); break;
+        case UAVDET_ACT_GELU: affine_act<UAVDET_ACT_GELU>(v, scale, cg, shift, rr, have_res, staged); break;
+        default: affine_act<UAVDET_ACT_NONE>(v, scale, cg, shift, rr, have_res, staged); break;
       }
     }
   }
@@ -311,6 +328,10 @@ __device__ __forceinline__ void mma_issue_loop_halo(const IgemmParams& P, uint32
 // pair, every CTA stages its own 128 pixel rows of A and HALF of the weight tile, so the shared-memory traffic per MMA
 // (what bounds the one-CTA kernel on the K >= 1152 layers: operand reads + TMA fill = 96 KB per 512-cycle k-block
 // against 128 B/clk) drops by a third.  The epilogue is unchanged: every CTA drains its own 128 accumulator rows.
+// barriers + TMEM pointer + flags behind the staging buffers (kernel and launch_igemm agree on this size); the staged
+// epilogue constants (IgemmParams::epc_floats) follow it
+constexpr int kCtrlBytes = (8 * (2 * kMaxStages + 5) + 64 + 8 * 2 * kEpiWarps + 8 * 2 * kMaxHaloBufs + 15) & ~15;
+
 template <int kKind, bool kTwo>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -386,6 +407,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   const uint32_t tmem_base = *tmem_ptr;
   // barriers, TMEM and descriptors are ready; nothing of the predecessor kernel's output has been touched yet
   pdl_wait();
+  float* epc = reinterpret_cast<float*>(ctrl + kCtrlBytes);
+  if (kKind != 0 && kKind != 3 && P.epc_floats > 0 && warp >= kEpiWarp0) {
+    // epilogue constants -> shared memory (scale defaults to 1, shift to 0), visible to the 8 epilogue warps only
+    for (int i = (warp - kEpiWarp0) * 32 + lane; i < P.epc_floats; i += 32 * kEpiWarps) {
+      epc[i] = (P.scale && i < P.cout) ? __ldg(P.scale + i) : 1.f;
+      epc[P.epc_floats + i] = (P.shift && i < P.cout) ? __ldg(P.shift + i) : 0.f;
+    }
+    asm volatile("bar.sync 4, 256;" ::: "memory");
+  }
+  const bool use_epc = kKind != 0 && kKind != 3 && P.epc_floats > 0;
+  const float* ep_scale = (use_epc && P.scale) ? epc : P.scale;       // an absent vector stays absent (no multiply by 1)
 
   const int num_kb = P.num_taps * P.kc_per_tap;
 
@@ -627,7 +659,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         }
         const __nv_bfloat16* res_px =
             P.res ? P.res + (size_t)tc.img * P.res_sn + (size_t)oh * P.res_sh + (size_t)ow * P.res_sw : nullptr;
-        const float* shift = P.shift ? P.shift + (size_t)tc.img * P.shift_sn : nullptr;
+        const float* shift = !P.shift ? nullptr : use_epc ? epc + P.epc_floats : P.shift + (size_t)tc.img * P.shift_sn;
         if (tr) P.trace[tl * 16 + 5] = clock64();
         // this warp's first slab of the tile: buffer + residual load before the accumulator is awaited
         // (fused parity planes: the residual always arrives by TMA — launch_igemm guarantees it — so res_px is unused)
@@ -660,14 +692,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
               uint8_t* srow = wbuf + lane * row_bytes;
               const int c0 = sl * P.slab_w;                          // accumulator column of the slab
               if (P.slab_w == 64) {
-                stage_chunk<(kKind == 3 ? 1 : kKind), kTwo>(ccfg, P.scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, srow, 0, sw_mask, false,
+                stage_chunk<(kKind == 3 ? 1 : kKind), kTwo>(ccfg, ep_scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, srow, 0, sw_mask, false,
                             tempty, lane);
                 // the residual tile of this warp's next slab of the tile starts travelling now (other buffer)
                 if (P.res_tma && P.epi_bufs == 2 && !last) wbuf_next = acquire(tc, cs + 2 * P.slab_w, true);
-                stage_chunk<(kKind == 3 ? 1 : kKind), kTwo>(ccfg, P.scale, tbase + (uint32_t)(c0 + 32), tc.n0 + c0 + 32, valid, shift, res_px, srow, 1, sw_mask,
+                stage_chunk<(kKind == 3 ? 1 : kKind), kTwo>(ccfg, ep_scale, tbase + (uint32_t)(c0 + 32), tc.n0 + c0 + 32, valid, shift, res_px, srow, 1, sw_mask,
                             last, tempty, lane);
               } else {
-                stage_chunk<(kKind == 3 ? 1 : kKind), kTwo>(ccfg, P.scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, srow, 0, sw_mask, last, tempty,
+                stage_chunk<(kKind == 3 ? 1 : kKind), kTwo>(ccfg, ep_scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, srow, 0, sw_mask, last, tempty,
                             lane);
               }
               if (tr) P.trace[tl * 16 + 10] = clock64();
@@ -746,7 +778,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         const bool tr = P.trace && blockIdx.x == 0 && tl < P.trace_tiles && ew == 0 && lane == 0;
         const __nv_bfloat16* res_px =
             P.res ? P.res + (size_t)tc.img * P.res_sn + (size_t)oh * P.res_sh + (size_t)ow * P.res_sw : nullptr;
-        const float* shift = P.shift ? P.shift + (size_t)tc.img * P.shift_sn : nullptr;
+        const float* shift = !P.shift ? nullptr : use_epc ? epc + P.epc_floats : P.shift + (size_t)tc.img * P.shift_sn;
         if (tr) P.trace[tl * 16 + 5] = clock64();
         mbar_wait<64>(smem_u32(&tfull_bar[acc]), acc_phase, dead, P.watchdog, 0x8u);
         if (tr) P.trace[tl * 16 + 6] = clock64();
@@ -765,7 +797,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           const bool last = sl == n_slabs - 1;
           if (half < chunks_per_slab) {
             const int c0 = sl * P.slab_w + half * 32;
-            stage_chunk<(kKind == 3 ? 1 : kKind), kTwo>(ccfg, P.scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_sl, sbuf + row * row_bytes, half,
+            stage_chunk<(kKind == 3 ? 1 : kKind), kTwo>(ccfg, ep_scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_sl, sbuf + row * row_bytes, half,
                         sw_mask, last, tempty, lane);
             fence_proxy_async();
           } else if (last) {
@@ -1180,7 +1212,14 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
   const int a_stage = 128 * P.block_k * 2, b_tile = (two ? P.block_n / 2 : P.block_n) * P.block_k * 2;
   const long long b_total = (long long)P.num_taps * P.kc_per_tap * b_tile;
   P.bres_bytes = 0;
-  const int ctrl_bytes = 8 * (2 * kMaxStages + 5) + 64 + 8 * 2 * kEpiWarps + 8 * 2 * kMaxHaloBufs;   // + residual-load / halo barriers
+  // Per-channel scale / shift of an AFFINE epilogue (folded eval-mode BatchNorm, biases): every epilogue thread needs
+  // the 32 values of its chunk, and fetching them from global memory (16 dependent-latency 16-byte loads per chunk in a
+  // thread that has no registers to keep them in flight) cost ~800 of the ~1,650 cycles a chunk took in RTMUAVDet's 1x1
+  // layers (tools/trace_igemm.py rtm2).  One copy per CTA in shared memory instead; per-sample shifts stay global.
+  static const bool no_epc = getenv("UAVDET_IGEMM_NO_EPC") != nullptr;      // A/B switch
+  P.epc_floats = (!no_epc && P.epi == UAVDET_EPI_AFFINE && (P.scale || P.shift) && P.shift_sn == 0 && P.cout <= 2048)
+                     ? ((P.cout + 31) / 32) * 32 : 0;
+  const int ctrl_bytes = kCtrlBytes + 2 * 4 * P.epc_floats;   // barriers (+ residual-load / halo barriers) + epilogue constants
   const int max_smem = 227 * 1024;
   const int staging1 = 2 * 128 * P.slab_w * 2;      // CTA-wide: 2 slabs; warp-private: 8 warps x 1 buffer
   if (P.halo) {

@@ -46,6 +46,8 @@ struct IgemmParams {
   int epi_mode;         // 0 = CTA-wide slab, 1 = per-warp rectangle (5-D map), 2 = per-warp pixel run (flat 3-D map)
   int epi_bufs;         // staging buffers per epilogue warp (modes 1/2)
   int staging_bytes;    // shared memory reserved for output staging
+  int epc_floats;       // > 0: the AFFINE epilogue's scale / shift vectors (padded cout floats each) are staged in shared
+                        // memory behind the barriers (one weight-independent copy per CTA) and read from there
   int prod_warps;       // active TMA producer warps (1 | 2 | 4), divides `stages`
   int bres_bytes;       // > 0: the whole weight matrix stays resident in shared memory (bytes); stages hold A only
   // Halo mode (tile 8 wide x 16 tall): ONE TMA box per tile and channel sub-block brings every input pixel any filter

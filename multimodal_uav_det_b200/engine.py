@@ -642,9 +642,9 @@ class Executor:
         ops.dyn_bwd_contract(dwb.view(n, -1), rec.attn, rec.bank, d_bank, d_attn, packed=not sp.stem)
         d_bias_bank = None
         if rec.bias_bank is not None:
-            dsum = ops.gap(d_raw) * float(d_raw.shape[1] * d_raw.shape[2])         # (n, O) per-sample channel sums
-            d_bias_bank = rec.attn.t() @ dsum
-            d_attn = d_attn + dsum @ rec.bias_bank.t()
+            # per-sample channel sums of d_raw = pool x pixel count; both contractions in one small kernel
+            d_bias_bank = ops.dyn_bias_bwd(ops.gap(d_raw), float(d_raw.shape[1] * d_raw.shape[2]), rec.attn,
+                                           rec.bias_bank.contiguous(), d_attn)
         # Gradient-ready hooks are fired at the END of this function: a data-parallel trainer may step a bucket right
         # behind its all-reduce, and the expert bank / attention weights are still read below (fp32 masters, no pack)
         ready = []

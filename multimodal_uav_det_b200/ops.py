@@ -784,6 +784,23 @@ def dyn_bwd_contract(dwb, attn, bank, d_bank, d_attn, packed: bool):
           "dyn_bwd_contract")
 
 
+def dyn_bias_bwd(pooled_grad, scale: float, attn, bias_bank, d_attn):
+    """Backward of bias[b] = attn[b] @ bias_bank: returns d_bias_bank (K, O) and adds into d_attn (n, K) in place;
+    `pooled_grad` (n, O) x `scale` = per-sample channel sums of the output gradient."""
+    _require_cuda(pooled_grad, attn, bias_bank, d_attn)
+    n, K = attn.shape
+    O = bias_bank.shape[1]
+    if pooled_grad.shape != (n, O) or bias_bank.shape[0] != K or d_attn.shape != (n, K):
+        raise UavdetError("dyn_bias_bwd: shape mismatch")
+    for t in (pooled_grad, attn, bias_bank, d_attn):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise UavdetError("dyn_bias_bwd expects contiguous fp32 tensors")
+    out = torch.empty((K, O), dtype=torch.float32, device=attn.device)
+    check(_lib.load().uavdet_dyn_bias_bwd(_ptr(pooled_grad), float(scale), n, K, O, _ptr(attn), _ptr(bias_bank), _ptr(out),
+                                          _ptr(d_attn), _stream()), "dyn_bias_bwd")
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # RTMUAVDet ops
 # --------------------------------------------------------------------------------------------

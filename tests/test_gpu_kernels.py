@@ -695,6 +695,25 @@ def test_upsample_add_layout_gap(lib):
     torch.testing.assert_close(ops.gap_nchw(img.to(DEV)).cpu(), img.mean(dim=(2, 3)), rtol=1e-5, atol=1e-6)
 
 
+def test_dyn_bias_bwd_matches_matmul_autograd(lib):
+    """bias[b] = attn[b] @ bias_bank (DynamicSOEM's per-sample bias, DySOEM_SimFPN.py:56-60): its backward in one kernel
+    against autograd of the matmul, including the accumulate-into-d_attn contract and the pooled-sum scale."""
+    ops = _ops(lib)
+    g = torch.Generator().manual_seed(77)
+    for n, K, O in [(5, 3, 64), (64, 4, 256), (2, 8, 1000), (1, 1, 8)]:
+        attn = torch.softmax(torch.randn(n, K, generator=g), 1).requires_grad_(True)
+        bank = torch.randn(K, O, generator=g).requires_grad_(True)
+        gsum = torch.randn(n, O, generator=g)                 # per-sample channel sums of the output gradient
+        (attn @ bank).backward(gsum)
+        d_attn0 = torch.randn(n, K, generator=g)
+        d_attn = d_attn0.clone().to(DEV)
+        scale = 400.0
+        d_bank = ops.dyn_bias_bwd((gsum / scale).to(DEV), scale, attn.detach().to(DEV), bank.detach().to(DEV), d_attn)
+        torch.testing.assert_close(d_bank.cpu(), bank.grad, rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(d_attn.cpu(), d_attn0 + attn.grad, rtol=1e-4, atol=1e-4)
+    ops.check_device()
+
+
 def test_attention_mlp_softmax(lib):
     ops = _ops(lib)
     g = torch.Generator().manual_seed(61)

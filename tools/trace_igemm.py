@@ -15,11 +15,16 @@ CASES = [(8, 32, 32, 1, 1, 640, True), (32, 64, 32, 1, 1, 320, True), (32, 32, 6
 if len(sys.argv) > 1 and sys.argv[1] == "rtm":      # the channel MLPs of RTMUAVDet's MDyEncoder (1x1, GELU / none)
     CASES = [(32, 192, 192, 1, 1, 160, "gelu"), (32, 192, 192, 1, 1, 160, "none"), (32, 192, 128, 1, 1, 160, "none"),
              (32, 384, 384, 1, 1, 80, "gelu"), (32, 256, 256, 1, 1, 160, "gelu"), (32, 128, 128, 1, 1, 160, "gelu")]
+if len(sys.argv) > 1 and sys.argv[1] == "rtm2":     # MDyConv's 32 -> 128 1x1 (ReLU) and its neighbours
+    CASES = [(32, 32, 128, 1, 1, 160, "relu"), (32, 32, 128, 1, 1, 160, "none"), (32, 32, 128, 1, 1, 160, "silu"),
+             (32, 64, 32, 1, 1, 160, "silu"), (32, 128, 32, 1, 1, 160, "silu"), (32, 64, 128, 1, 1, 160, "relu")]
 for (n, cin, cout, k, s, hw, stats) in CASES:
     x = torch.randn(n, hw, hw, cin, device="cuda").bfloat16()
     w = ops.pack_weight(torch.randn(cout, cin, k, k, device="cuda") * 0.05)
     s1 = torch.zeros(cout, device="cuda"); s2 = torch.zeros(cout, device="cuda")
     kw = dict(epi=EPI_STATS, sum_=s1, sumsq=s2) if stats is True else dict(act=stats if isinstance(stats, str) else "leaky")
+    if stats is not True:      # eval-mode BatchNorm folded into the epilogue, as the inference models launch it
+        kw.update(scale=torch.rand(cout, device="cuda") + 0.5, shift=torch.randn(cout, device="cuda") * 0.1)
     for _ in range(2):
         ops.conv_fwd(x, w, cout, k, s, k // 2, **kw)
     torch.cuda.synchronize()
