@@ -174,12 +174,14 @@ __device__ __forceinline__ void finish_chunk(uint32_t cfg, const float* scale, c
     const bool staged = (cfg & 64u) != 0u;
     if (kKind == 1) {
       affine_act<UAVDET_ACT_NONE>(v, scale, cg, shift, rr, have_res, staged);
+    } else if (kKind == 4) {
+      affine_act<UAVDET_ACT_GELU>(v, scale, cg, shift, rr, have_res, staged);
+    } else if (kKind == 5) {
+      affine_act<UAVDET_ACT_SILU>(v, scale, cg, shift, rr, have_res, staged);
     } else {
       switch ((cfg >> 1) & 7u) {
         case UAVDET_ACT_LEAKY: affine_act<UAVDET_ACT_LEAKY>(v, scale, cg, shift, rr, have_res, staged); break;
-        case UAVDET_ACT_SILU: affine_act<UAVDET_ACT_SILU>(v, scale, cg, shift, rr, have_res, staged); break;
         case UAVDET_ACT_RELU: affine_act<UAVDET_ACT_RELU>(v, scale, cg, shift, rr, have_res, staged); break;
-        case UAVDET_ACT_GELU: affine_act<UAVDET_ACT_GELU>(v, scale, cg, shift, rr, have_res, staged); break;
         default: affine_act<UAVDET_ACT_NONE>(v, scale, cg, shift, rr, have_res, staged); break;
       }
     }
@@ -324,6 +326,8 @@ __device__ __forceinline__ void mma_issue_loop_halo(const IgemmParams& P, uint32
 // kKind selects the epilogue the instance is compiled with: 0 = batch statistics (training forward), 1 = affine
 // without activation (data gradients), 2 = affine with any activation (fused inference epilogues), 3 = detection
 // head.  One kernel holding all of them was 160 KB of code, and the step time follows the kernel's code size.
+// 4 / 5 = affine with GELU / SiLU only (the inference models' activations get instances of their own: the epilogue math of
+// an instance is inlined per activation, and the ALU-bound GELU epilogue lost 8 % to unrelated code in its kernel).
 // kTwo: the CTA-pair variant (cluster of two CTAs on one TPC, tcgen05.mma.cta_group::2): a 256-pixel x block_n tile per
 // pair, every CTA stages its own 128 pixel rows of A and HALF of the weight tile, so the shared-memory traffic per MMA
 // (what bounds the one-CTA kernel on the K >= 1152 layers: operand reads + TMA fill = 96 KB per 512-cycle k-block
@@ -1277,8 +1281,9 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
   // (UAVDET_IGEMM_RES_PREFETCH=0 switches that off: A/B)
   static const bool res_prefetch = !(getenv("UAVDET_IGEMM_RES_PREFETCH") && getenv("UAVDET_IGEMM_RES_PREFETCH")[0] == '0');
   if (P.res_tma && res_prefetch) P.res_tma = 2;
-  const int kind = (P.epi == UAVDET_EPI_HEAD) ? 3 : (P.epi == UAVDET_EPI_STATS) ? 0 : (P.act == UAVDET_ACT_NONE ? 1 : 2);
-  static PerDeviceOnce attr_once[4][2];   // the dynamic-shared-memory opt-in is per device
+  const int kind = (P.epi == UAVDET_EPI_HEAD) ? 3 : (P.epi == UAVDET_EPI_STATS) ? 0 : P.act == UAVDET_ACT_NONE ? 1
+                   : P.act == UAVDET_ACT_GELU ? 4 : P.act == UAVDET_ACT_SILU ? 5 : 2;
+  static PerDeviceOnce attr_once[6][2];   // the dynamic-shared-memory opt-in is per device
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kIgemmThreads);
@@ -1306,6 +1311,8 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
     switch (kind) {
       case 0: UAVDET_LAUNCH_IGEMM(0, 1); break;
       case 1: UAVDET_LAUNCH_IGEMM(1, 1); break;
+      case 4: UAVDET_LAUNCH_IGEMM(4, 1); break;
+      case 5: UAVDET_LAUNCH_IGEMM(5, 1); break;
       default: UAVDET_LAUNCH_IGEMM(2, 1); break;
     }
   } else {
@@ -1313,6 +1320,8 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
       case 0: UAVDET_LAUNCH_IGEMM(0, 0); break;
       case 1: UAVDET_LAUNCH_IGEMM(1, 0); break;
       case 2: UAVDET_LAUNCH_IGEMM(2, 0); break;
+      case 4: UAVDET_LAUNCH_IGEMM(4, 0); break;
+      case 5: UAVDET_LAUNCH_IGEMM(5, 0); break;
       default: UAVDET_LAUNCH_IGEMM(3, 0); break;
     }
   }
