@@ -149,6 +149,11 @@ typedef struct {
   int head_anchors;   /* A; cout must be 5*A packed [A obj | 4A bbox]                    */
   int shift_per_sample; /* != 0: shift is [n][cout] (aggregated expert bias, DySOEM_SimFPN.py:83-91);
                            in STATS mode a given shift is added before the statistics        */
+  const float* sample_affine; /* AFFINE + ReLU|GELU only, or NULL.  [n][2] = (rstd_n, mean_n*rstd_n) from
+                           uavdet_groupnorm1_fold: y = act(acc*rstd_n + shift[c] - mean_n*rstd_n*scale[c]) — a
+                           GroupNorm(1 group) in front of a 1x1 convolution folded into its epilogue: the GEMM
+                           reads the un-normalised tensor with weights W' = W*diag(gamma), scale[c] = sum_i W'[c][i],
+                           shift[c] = (W beta)[c] + bias[c]  (RTMUAVDet.py:165-177)                              */
 } uavdet_epilogue;
 
 /* Forward convolution  y = conv(x, w), square kernel k in {1,3,5}, stride 1|2, zero pad.
@@ -362,6 +367,11 @@ int uavdet_dyn_bias_bwd(const float* pooled_grad, float scale, int n, int K, int
  * y[b,p,c] = x[b,p,c] + channel_w[b,c] * sum_t kernel_w[b,t] * x[b,p+t,c]; k odd, pad = k/2.      */
 int uavdet_dwdynconv_fwd(const uavdet_act* x, const float* channel_w, const float* kernel_w, int k, int pad,
                          const uavdet_act* y, void* stream);
+/* The same at the MDyEncoder site (RTMUAVDet.py:163-174) with the encoder's residual folded in:
+ * y = dwdynconv(x) + res, and stats[2b] += sum(y), stats[2b+1] += sum(y^2) over the bf16-rounded y of image b
+ * (caller-zeroed, shared by the three MDyConv branches) — the statistics of GroupNorm(cat + residual).          */
+int uavdet_dwdynconv_res_stats_fwd(const uavdet_act* x, const float* channel_w, const float* kernel_w, int k, int pad,
+                                   const uavdet_act* res, float* stats, const uavdet_act* y, void* stream);
 /* out[r][o] = act(in[r][:] . w[o][:] + bias[o])  — the 1x1 convs on pooled vectors (RTMUAVDet.py:54-62). */
 int uavdet_linear(const float* in, int rows, int c, const float* w, const float* bias, int out_dim, int act,
                   float* out, void* stream);
@@ -369,6 +379,12 @@ int uavdet_linear(const float* in, int rows, int c, const float* w, const float*
  * stats_ws: 2*n floats of scratch.                                                              */
 int uavdet_groupnorm1(const uavdet_act* a, const uavdet_act* b, const float* gamma, const float* beta,
                       float eps, float* stats_ws, const uavdet_act* y, void* stream);
+/* GroupNorm(num_groups=1) folded into the 1x1 convolution that consumes it (RTMUAVDet.py:165-169 -> MDyConv.base_conv,
+ * :174-177 -> channel_mlp[0]): uavdet_groupnorm1_stats gives stats[n][2] = per-sample sum / sum of squares of (a [+ b]);
+ * uavdet_groupnorm1_fold turns stats (from it or from uavdet_dwdynconv_res_stats_fwd) into sample_affine[n][2] =
+ * (rstd_n, mean_n*rstd_n), count = h*w*c, for uavdet_epilogue::sample_affine.                                      */
+int uavdet_groupnorm1_stats(const uavdet_act* a, const uavdet_act* b, float* stats, void* stream);
+int uavdet_groupnorm1_fold(const float* stats, int n, double count, float eps, float* sample_affine, void* stream);
 /* nn.Upsample(scale_factor=2, mode='bilinear'), align_corners=False (RTMUAVDet.py:193).           */
 int uavdet_bilinear2x_fwd(const uavdet_act* x, const uavdet_act* y, void* stream);
 /* RTMHead post: sigmoid on obj / bbox logits (RTMUAVDet.py:234,253) + decode (:285-289).           */

@@ -24,7 +24,7 @@ class Epilogue(C.Structure):
     _fields_ = [("epi", C.c_int), ("act", C.c_int), ("scale", C.c_void_p), ("shift", C.c_void_p),
                 ("res", C.c_void_p), ("res_ld", C.c_int), ("sum", C.c_void_p), ("sumsq", C.c_void_p),
                 ("head_obj", C.c_void_p), ("head_bbox", C.c_void_p), ("head_anchors", C.c_int),
-                ("shift_per_sample", C.c_int)]
+                ("shift_per_sample", C.c_int), ("sample_affine", C.c_void_p)]
 
 
 class UavdetError(RuntimeError):
@@ -91,8 +91,11 @@ SIGNATURES = {
     "uavdet_dyn_bwd_contract": (_i, [_P, _i, _i, _P, _P, _i, _i, _i, _i, _P, _P, _P]),
     "uavdet_dyn_bias_bwd": (_i, [_P, _f, _i, _i, _i, _P, _P, _P, _P, _P]),
     "uavdet_dwdynconv_fwd": (_i, [_AP, _P, _P, _i, _i, _AP, _P]),
+    "uavdet_dwdynconv_res_stats_fwd": (_i, [_AP, _P, _P, _i, _i, _AP, _P, _AP, _P]),
     "uavdet_linear": (_i, [_P, _i, _i, _P, _P, _i, _i, _P, _P]),
     "uavdet_groupnorm1": (_i, [_AP, _AP, _P, _P, _f, _P, _AP, _P]),
+    "uavdet_groupnorm1_stats": (_i, [_AP, _AP, _P, _P]),
+    "uavdet_groupnorm1_fold": (_i, [_P, _i, _d, _f, _P, _P]),
     "uavdet_bilinear2x_fwd": (_i, [_AP, _AP, _P]),
     "uavdet_rtm_head_post": (_i, [_P, _P, _i, _i, _i, _i, C.POINTER(_f), _P, _P, _P]),
     "uavdet_sgd_momentum": (_i, [_P, _P, _P, _i64, _f, _f, _f, _i, _P]),

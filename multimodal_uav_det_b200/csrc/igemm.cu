@@ -92,17 +92,26 @@ __device__ __forceinline__ float4 load_epc4(const float* p, bool staged) {
 }
 
 // 32 accumulator columns of this lane's row -> (scale, shift, act, residual), in place.
-template <int ACT>
+// kFold: the GroupNorm-fold form  v * rs + u[c]  — rs = rstd of the tile's image, u = the warp's per-image additive vector
+// (passed as `shift`, always in shared memory): uavdet_epilogue::sample_affine.
+template <int ACT, bool kFold = false>
 __device__ __forceinline__ void affine_act(float (&v)[32], const float* scale, int cg, const float* shift,
-                                           const uint4 (&res)[4], bool have_res, bool staged) {
-  if (scale) {
+                                           const uint4 (&res)[4], bool have_res, bool staged, float rs = 1.f) {
+  if (kFold) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 t = load_epc4(shift + cg + i, true);
+      v[i] = fmaf(v[i], rs, t.x); v[i + 1] = fmaf(v[i + 1], rs, t.y);
+      v[i + 2] = fmaf(v[i + 2], rs, t.z); v[i + 3] = fmaf(v[i + 3], rs, t.w);
+    }
+  } else if (scale) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 s = load_epc4(scale + cg + i, staged);
       v[i] *= s.x; v[i + 1] *= s.y; v[i + 2] *= s.z; v[i + 3] *= s.w;
     }
   }
-  if (shift) {
+  if (!kFold && shift) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 s = load_epc4(shift + cg + i, staged);
@@ -130,10 +139,11 @@ __device__ __forceinline__ void affine_act(float (&v)[32], const float* scale, i
 // Everything it needs from the kernel parameters arrives in registers (`cfg`, `scale`): read through a reference,
 // the fields became a chain of control-dependent generic loads from the parameter bank (~1,000 cycles per call).
 //   cfg bit 0: statistics epilogue; bits 1-3: activation; bit 4: residual operand; bit 5: it is in the staging row;
-//   bit 6: scale / shift point into the CTA's staged copy in shared memory
+//   bit 6: scale / shift point into the CTA's staged copy in shared memory; bit 7: GroupNorm-fold form of the affine map
 __device__ __forceinline__ uint32_t chunk_cfg(const IgemmParams& P) {
   return (P.epi == UAVDET_EPI_STATS ? 1u : 0u) | ((uint32_t)P.act << 1) | (P.res ? 16u : 0u) | (P.res_tma ? 32u : 0u) |
-         ((P.epi != UAVDET_EPI_STATS && P.epi != UAVDET_EPI_HEAD && P.epc_floats > 0) ? 64u : 0u);
+         ((P.epi != UAVDET_EPI_STATS && P.epi != UAVDET_EPI_HEAD && P.epc_floats > 0) ? 64u : 0u) |
+         (P.sample_affine ? 128u : 0u);
 }
 // epilogue math of one 32-column chunk (accumulator values in r) + bf16 pack + swizzled staging store
 // kKind: the kernel instance (see igemm_kernel): 0 statistics epilogue, 1 affine without activation, 2 affine with
@@ -141,7 +151,7 @@ __device__ __forceinline__ uint32_t chunk_cfg(const IgemmParams& P) {
 template <int kKind>
 __device__ __forceinline__ void finish_chunk(uint32_t cfg, const float* scale, const uint32_t (&r)[32], int cg, bool valid,
                                              const float* shift, const __nv_bfloat16* res_px, uint8_t* srow,
-                                             int chunk_in_slab, int sw_mask) {
+                                             int chunk_in_slab, int sw_mask, float sa_rs) {
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
@@ -176,12 +186,17 @@ __device__ __forceinline__ void finish_chunk(uint32_t cfg, const float* scale, c
       affine_act<UAVDET_ACT_NONE>(v, scale, cg, shift, rr, have_res, staged);
     } else if (kKind == 4) {
       affine_act<UAVDET_ACT_GELU>(v, scale, cg, shift, rr, have_res, staged);
+    } else if (kKind == 6) {
+      affine_act<UAVDET_ACT_GELU, true>(v, scale, cg, shift, rr, have_res, staged, sa_rs);
     } else if (kKind == 5) {
       affine_act<UAVDET_ACT_SILU>(v, scale, cg, shift, rr, have_res, staged);
     } else {
       switch ((cfg >> 1) & 7u) {
         case UAVDET_ACT_LEAKY: affine_act<UAVDET_ACT_LEAKY>(v, scale, cg, shift, rr, have_res, staged); break;
-        case UAVDET_ACT_RELU: affine_act<UAVDET_ACT_RELU>(v, scale, cg, shift, rr, have_res, staged); break;
+        case UAVDET_ACT_RELU:
+          if (cfg & 128u) affine_act<UAVDET_ACT_RELU, true>(v, scale, cg, shift, rr, have_res, staged, sa_rs);
+          else affine_act<UAVDET_ACT_RELU>(v, scale, cg, shift, rr, have_res, staged);
+          break;
         default: affine_act<UAVDET_ACT_NONE>(v, scale, cg, shift, rr, have_res, staged); break;
       }
     }
@@ -204,7 +219,8 @@ __device__ __forceinline__ void finish_chunk(uint32_t cfg, const float* scale, c
 template <int kKind, bool kTwo>
 __device__ __noinline__ void stage_chunk(uint32_t cfg, const float* scale, uint32_t taddr, int cg, bool valid,
                                             const float* shift, const __nv_bfloat16* res_px, uint8_t* srow,
-                                            int chunk_in_slab, int sw_mask, bool release, uint32_t tempty, int lane) {
+                                            int chunk_in_slab, int sw_mask, bool release, uint32_t tempty, int lane,
+                                            float sa_rs = 1.f) {
   uint32_t r[32];
   tmem_ld_32x32(taddr, r);
   tmem_ld_wait();
@@ -215,7 +231,7 @@ __device__ __noinline__ void stage_chunk(uint32_t cfg, const float* scale, uint3
     __syncwarp();
     if (lane == 0) { if (kTwo) mbar_arrive_cluster(tempty); else mbar_arrive(tempty); }
   }
-  finish_chunk<kKind>(cfg, scale, r, cg, valid, shift, res_px, srow, chunk_in_slab, sw_mask);
+  finish_chunk<kKind>(cfg, scale, r, cg, valid, shift, res_px, srow, chunk_in_slab, sw_mask, sa_rs);
 }
 
 // MMA issue loop of one CTA (single elected thread), KSTEPS = block_k / 16.
@@ -327,7 +343,8 @@ __device__ __forceinline__ void mma_issue_loop_halo(const IgemmParams& P, uint32
 // without activation (data gradients), 2 = affine with any activation (fused inference epilogues), 3 = detection
 // head.  One kernel holding all of them was 160 KB of code, and the step time follows the kernel's code size.
 // 4 / 5 = affine with GELU / SiLU only (the inference models' activations get instances of their own: the epilogue math of
-// an instance is inlined per activation, and the ALU-bound GELU epilogue lost 8 % to unrelated code in its kernel).
+// an instance is inlined per activation, and the ALU-bound GELU epilogue lost 8 % to unrelated code in its kernel);
+// 6 = GELU behind the GroupNorm-fold form of the affine map (as a runtime branch inside instance 4 it cost that layer 20 %).
 // kTwo: the CTA-pair variant (cluster of two CTAs on one TPC, tcgen05.mma.cta_group::2): a 256-pixel x block_n tile per
 // pair, every CTA stages its own 128 pixel rows of A and HALF of the weight tile, so the shared-memory traffic per MMA
 // (what bounds the one-CTA kernel on the K >= 1152 layers: operand reads + TMA fill = 96 KB per 512-cycle k-block
@@ -418,6 +435,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       epc[i] = (P.scale && i < P.cout) ? __ldg(P.scale + i) : 1.f;
       epc[P.epc_floats + i] = (P.shift && i < P.cout) ? __ldg(P.shift + i) : 0.f;
     }
+    // GroupNorm fold: the per-image (rstd, mean * rstd) pairs behind the warps' additive vectors (a global load per tile
+    // sat on the critical path of the epilogue-bound layers this epilogue serves)
+    if ((kKind == 2 || kKind == 6) && P.sa_staged)
+      for (int i = (warp - kEpiWarp0) * 32 + lane; i < 2 * P.n_img; i += 32 * kEpiWarps)
+        epc[(2 + kEpiWarps) * P.epc_floats + i] = __ldg(P.sample_affine + i);
     asm volatile("bar.sync 4, 256;" ::: "memory");
   }
   const bool use_epc = kKind != 0 && kKind != 3 && P.epc_floats > 0;
@@ -664,6 +686,22 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         const __nv_bfloat16* res_px =
             P.res ? P.res + (size_t)tc.img * P.res_sn + (size_t)oh * P.res_sh + (size_t)ow * P.res_sw : nullptr;
         const float* shift = !P.shift ? nullptr : use_epc ? epc + P.epc_floats : P.shift + (size_t)tc.img * P.shift_sn;
+        // GroupNorm-fold epilogue: with the per-image pair (rstd, mean * rstd) of this tile's image the warp rebuilds its
+        // own additive vector u[c] = shift[c] - mean * rstd * scale[c] in shared memory; the chunk math is then one load
+        // and one FMA per element (acc * rstd + u[c]) like a plain bias.  (With scale, shift and both scalars live in
+        // the chunk function the register allocator serialised the GELU chains of a chunk: +26 % on that layer.)
+        float sa_rs = 1.f;
+        if ((kKind == 2 || kKind == 6) && P.sample_affine) {
+          const int simg = min(tc.img, P.n_img - 1);
+          const float2 sa = P.sa_staged ? *reinterpret_cast<const float2*>(epc + (2 + kEpiWarps) * P.epc_floats + 2 * simg)
+                                        : __ldg(reinterpret_cast<const float2*>(P.sample_affine) + simg);
+          sa_rs = sa.x;
+          float* uw = epc + (2 + ew) * P.epc_floats;
+          __syncwarp();
+          for (int j = lane; j < P.epc_floats; j += 32) uw[j] = fmaf(-sa.y, epc[j], epc[P.epc_floats + j]);
+          __syncwarp();
+          shift = uw;
+        }
         if (tr) P.trace[tl * 16 + 5] = clock64();
         // this warp's first slab of the tile: buffer + residual load before the accumulator is awaited
         // (fused parity planes: the residual always arrives by TMA — launch_igemm guarantees it — so res_px is unused)
@@ -697,14 +735,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
               const int c0 = sl * P.slab_w;                          // accumulator column of the slab
               if (P.slab_w == 64) {
                 stage_chunk<(kKind == 3 ? 1 : kKind), kTwo>(ccfg, ep_scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, srow, 0, sw_mask, false,
-                            tempty, lane);
+                            tempty, lane, sa_rs);
                 // the residual tile of this warp's next slab of the tile starts travelling now (other buffer)
                 if (P.res_tma && P.epi_bufs == 2 && !last) wbuf_next = acquire(tc, cs + 2 * P.slab_w, true);
                 stage_chunk<(kKind == 3 ? 1 : kKind), kTwo>(ccfg, ep_scale, tbase + (uint32_t)(c0 + 32), tc.n0 + c0 + 32, valid, shift, res_px, srow, 1, sw_mask,
-                            last, tempty, lane);
+                            last, tempty, lane, sa_rs);
               } else {
                 stage_chunk<(kKind == 3 ? 1 : kKind), kTwo>(ccfg, ep_scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_px, srow, 0, sw_mask, last, tempty,
-                            lane);
+                            lane, sa_rs);
               }
               if (tr) P.trace[tl * 16 + 10] = clock64();
               fence_proxy_async();
@@ -783,6 +821,22 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         const __nv_bfloat16* res_px =
             P.res ? P.res + (size_t)tc.img * P.res_sn + (size_t)oh * P.res_sh + (size_t)ow * P.res_sw : nullptr;
         const float* shift = !P.shift ? nullptr : use_epc ? epc + P.epc_floats : P.shift + (size_t)tc.img * P.shift_sn;
+        // GroupNorm-fold epilogue: with the per-image pair (rstd, mean * rstd) of this tile's image the warp rebuilds its
+        // own additive vector u[c] = shift[c] - mean * rstd * scale[c] in shared memory; the chunk math is then one load
+        // and one FMA per element (acc * rstd + u[c]) like a plain bias.  (With scale, shift and both scalars live in
+        // the chunk function the register allocator serialised the GELU chains of a chunk: +26 % on that layer.)
+        float sa_rs = 1.f;
+        if ((kKind == 2 || kKind == 6) && P.sample_affine) {
+          const int simg = min(tc.img, P.n_img - 1);
+          const float2 sa = P.sa_staged ? *reinterpret_cast<const float2*>(epc + (2 + kEpiWarps) * P.epc_floats + 2 * simg)
+                                        : __ldg(reinterpret_cast<const float2*>(P.sample_affine) + simg);
+          sa_rs = sa.x;
+          float* uw = epc + (2 + ew) * P.epc_floats;
+          __syncwarp();
+          for (int j = lane; j < P.epc_floats; j += 32) uw[j] = fmaf(-sa.y, epc[j], epc[P.epc_floats + j]);
+          __syncwarp();
+          shift = uw;
+        }
         if (tr) P.trace[tl * 16 + 5] = clock64();
         mbar_wait<64>(smem_u32(&tfull_bar[acc]), acc_phase, dead, P.watchdog, 0x8u);
         if (tr) P.trace[tl * 16 + 6] = clock64();
@@ -802,7 +856,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           if (half < chunks_per_slab) {
             const int c0 = sl * P.slab_w + half * 32;
             stage_chunk<(kKind == 3 ? 1 : kKind), kTwo>(ccfg, ep_scale, tbase + (uint32_t)c0, tc.n0 + c0, valid, shift, res_sl, sbuf + row * row_bytes, half,
-                        sw_mask, last, tempty, lane);
+                        sw_mask, last, tempty, lane, sa_rs);
             fence_proxy_async();
           } else if (last) {
             tc_fence_before();
@@ -1223,7 +1277,11 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
   static const bool no_epc = getenv("UAVDET_IGEMM_NO_EPC") != nullptr;      // A/B switch
   P.epc_floats = (!no_epc && P.epi == UAVDET_EPI_AFFINE && (P.scale || P.shift) && P.shift_sn == 0 && P.cout <= 2048)
                      ? ((P.cout + 31) / 32) * 32 : 0;
-  const int ctrl_bytes = kCtrlBytes + 2 * 4 * P.epc_floats;   // barriers (+ residual-load / halo barriers) + epilogue constants
+  if (P.sample_affine) UAVDET_CHECK_ARG(P.epc_floats > 0, "conv: sample_affine needs the staged epilogue constants (cout <= 2048)");
+  // barriers (+ residual-load / halo barriers) + epilogue constants (+ one additive vector per epilogue warp: GroupNorm fold)
+  P.sa_staged = (P.sample_affine && P.n_img <= 2048) ? 1 : 0;
+  const int ctrl_bytes = kCtrlBytes + (2 + (P.sample_affine ? kEpiWarps : 0)) * 4 * P.epc_floats +
+                         (P.sa_staged ? ((8 * P.n_img + 15) & ~15) : 0);
   const int max_smem = 227 * 1024;
   const int staging1 = 2 * 128 * P.slab_w * 2;      // CTA-wide: 2 slabs; warp-private: 8 warps x 1 buffer
   if (P.halo) {
@@ -1282,8 +1340,8 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
   static const bool res_prefetch = !(getenv("UAVDET_IGEMM_RES_PREFETCH") && getenv("UAVDET_IGEMM_RES_PREFETCH")[0] == '0');
   if (P.res_tma && res_prefetch) P.res_tma = 2;
   const int kind = (P.epi == UAVDET_EPI_HEAD) ? 3 : (P.epi == UAVDET_EPI_STATS) ? 0 : P.act == UAVDET_ACT_NONE ? 1
-                   : P.act == UAVDET_ACT_GELU ? 4 : P.act == UAVDET_ACT_SILU ? 5 : 2;
-  static PerDeviceOnce attr_once[6][2];   // the dynamic-shared-memory opt-in is per device
+                   : P.act == UAVDET_ACT_GELU ? (P.sample_affine ? 6 : 4) : P.act == UAVDET_ACT_SILU ? 5 : 2;
+  static PerDeviceOnce attr_once[7][2];   // the dynamic-shared-memory opt-in is per device
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kIgemmThreads);
@@ -1313,6 +1371,7 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
       case 1: UAVDET_LAUNCH_IGEMM(1, 1); break;
       case 4: UAVDET_LAUNCH_IGEMM(4, 1); break;
       case 5: UAVDET_LAUNCH_IGEMM(5, 1); break;
+      case 6: UAVDET_LAUNCH_IGEMM(6, 1); break;
       default: UAVDET_LAUNCH_IGEMM(2, 1); break;
     }
   } else {
@@ -1322,6 +1381,7 @@ int launch_igemm(const uavdet_act* a_src, int parity, const void* w_packed, int 
       case 2: UAVDET_LAUNCH_IGEMM(2, 0); break;
       case 4: UAVDET_LAUNCH_IGEMM(4, 0); break;
       case 5: UAVDET_LAUNCH_IGEMM(5, 0); break;
+      case 6: UAVDET_LAUNCH_IGEMM(6, 0); break;
       default: UAVDET_LAUNCH_IGEMM(3, 0); break;
     }
   }
@@ -1335,7 +1395,8 @@ static int fill_epilogue(IgemmParams& P, const uavdet_epilogue* epi, const uavde
   P.act = epi ? epi->act : UAVDET_ACT_NONE;
   P.scale = epi ? epi->scale : nullptr;
   P.shift = epi ? epi->shift : nullptr;
-  P.shift_sn = (epi && epi->shift_per_sample) ? cout : 0;
+  P.shift_sn = (epi && (epi->shift_per_sample & 1)) ? cout : 0;
+  P.sample_affine = epi ? epi->sample_affine : nullptr;
   P.res = epi ? (const __nv_bfloat16*)epi->res : nullptr;
   P.sum = epi ? epi->sum : nullptr;
   P.sumsq = epi ? epi->sumsq : nullptr;
@@ -1353,6 +1414,10 @@ static int fill_epilogue(IgemmParams& P, const uavdet_epilogue* epi, const uavde
     UAVDET_CHECK_ARG(y->ld % 8 == 0 && ((uintptr_t)y->ptr & 15) == 0, "conv: output must be 16-byte aligned");
     if (P.epi == UAVDET_EPI_STATS) UAVDET_CHECK_ARG(P.sum && P.sumsq, "conv: STATS epilogue needs sum/sumsq");
     if (P.res) UAVDET_CHECK_ARG(epi->res_ld % 8 == 0 && ((uintptr_t)P.res & 15) == 0, "conv: residual alignment");
+    if (P.sample_affine)
+      UAVDET_CHECK_ARG(P.epi == UAVDET_EPI_AFFINE && P.scale && P.shift && P.shift_sn == 0 &&
+                           (P.act == UAVDET_ACT_RELU || P.act == UAVDET_ACT_GELU) && ((uintptr_t)P.sample_affine & 7) == 0,
+                       "conv: sample_affine needs an AFFINE epilogue with shared scale and shift vectors and ReLU / GELU");
   }
   return UAVDET_OK;
 }
@@ -1621,11 +1686,11 @@ extern "C" int uavdet_conv_dgrad_s2d(const uavdet_act* dy, const void* w_packed_
       P.res_sw = 2 * rl; P.res_sh = 2ll * dx->w * rl; P.res_sn = (long long)dx->h * dx->w * rl;
       P.res_sp = (long long)dx->w * rl;
     }
-    if (P.shift && epi->shift_per_sample) P.shift_sn = 4 * c;
+    if (P.shift && (epi->shift_per_sample & 1)) P.shift_sn = 4 * c;
     choose_tile(P.ho, P.wo, false, &P.tile_w, &P.tile_h, &P.epi_mode);
     // a store slab (64 | 32 columns) must not straddle two row-parity planes; a shared (not per-sample) shift is [c]
     const bool slab_ok = (2 * c) % ((P.block_n % 64 == 0) ? 64 : 32) == 0;
-    const bool shift_ok = !P.shift || epi->shift_per_sample;
+    const bool shift_ok = !P.shift || (epi->shift_per_sample & 1);
     if (slab_ok && shift_ok)
       return launch_igemm(dy, 0, w_packed_t, 4 * c, (int)k_total, w_batch, P, st, 4 * c);
   }
@@ -1659,7 +1724,7 @@ extern "C" int uavdet_conv_dgrad_s2d(const uavdet_act* dy, const void* w_packed_
       P.res = P.res + ((long long)pi * dx->w + pj) * rl;
       P.res_sw = 2 * rl; P.res_sh = 2ll * dx->w * rl; P.res_sn = (long long)dx->h * dx->w * rl;
     }
-    if (P.shift && epi->shift_per_sample) { P.shift = P.shift + q * c; P.shift_sn = 4 * c; }
+    if (P.shift && (epi->shift_per_sample & 1)) { P.shift = P.shift + q * c; P.shift_sn = 4 * c; }
     choose_tile(P.ho, P.wo, false, &P.tile_w, &P.tile_h, &P.epi_mode);
     const __nv_bfloat16* wq = (const __nv_bfloat16*)w_packed_t + (long long)q * c * k_total;
     rc = launch_igemm(dy, 0, wq, c, (int)k_total, w_batch, P, st, 4 * c);

@@ -70,6 +70,8 @@ struct IgemmParams {
   const float* scale;
   const float* shift;
   long long shift_sn;   // per-image stride of `shift` (0 = shared)
+  const float* sample_affine;   // GroupNorm-fold epilogue: [n][2] = (rstd, mean * rstd) per image, or NULL
+  int sa_staged;                // the pairs are copied to shared memory behind the epilogue constants
   int res_tma;          // 1: the warp-private epilogues TMA-load the residual tile into their staging buffer
   const __nv_bfloat16* res;
   long long res_sn, res_sh, res_sw;

@@ -45,11 +45,15 @@ __device__ __forceinline__ Lanes lanes_of(int c) {
 // indices are compile-time constants because the row loop is unrolled by KS.  (The first version gathered a KS x KS
 // window per output row: KS x more bf16 -> fp32 conversions and a register shuffle of the window per row made it
 // instruction-bound — 18 % of the HBM rate for k = 5, 50 % for k = 3.)
-template <int KS>
-__global__ void __launch_bounds__(256)
-dwdynconv_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int h, int w, int c,
+// kFold (the MDyEncoder site, RTMUAVDet.py:171-174): the encoder's residual `res` (a channel slice of its input) is
+// added to the result, and the per-sample sum / sum of squares of the bf16-ROUNDED outputs — the values the 1x1
+// convolution behind GroupNorm(1 group) is going to read — are accumulated into s1 / s2: GroupNorm(cat + residual) then
+// needs neither a statistics pass nor a normalise pass (its affine map is folded into that convolution).
+template <int KS, bool kFold>
+__device__ __forceinline__ void dwdynconv_body(const __nv_bfloat16* __restrict__ x, int x_ld, int h, int w, int c,
                  const float* __restrict__ channel_w, const float* __restrict__ kernel_w, int xblocks, int rows,
-                 __nv_bfloat16* __restrict__ y, int y_ld) {
+                 __nv_bfloat16* __restrict__ y, int y_ld, const __nv_bfloat16* __restrict__ res, int r_ld,
+                 float& s1, float& s2) {
   const Lanes L = lanes_of(c);
   if (!L.active) return;
   const int b = blockIdx.z;
@@ -67,16 +71,20 @@ dwdynconv_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int h, int w, in
   for (int j = 0; j < 8; ++j) cw[j] = __ldg(channel_w + (long long)b * c + cc + j);
   const __nv_bfloat16* xb_ = x + (long long)b * h * w * x_ld + cc;
   __nv_bfloat16* yb_ = y + (long long)b * h * w * y_ld + cc;
+  const __nv_bfloat16* rb_ = kFold ? res + (long long)b * h * w * r_ld + cc : nullptr;
   if (KS == 1) {
     // 1x1: y = x * (1 + channel_w * kernel_w) — a pure stream, four loads in flight
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = fmaf(cw[j], kw[0], 1.f);
     for (int r0 = 0; r0 < nrows; r0 += 4) {
-      uint4 raw[4];
+      uint4 raw[4], rr[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        if (r0 + u < nrows) raw[u] = __ldcs(reinterpret_cast<const uint4*>(xb_ + ((long long)(y0 + r0 + u) * w + ox) * x_ld));
+        if (r0 + u < nrows) {
+          raw[u] = __ldcs(reinterpret_cast<const uint4*>(xb_ + ((long long)(y0 + r0 + u) * w + ox) * x_ld));
+          if (kFold) rr[u] = __ldcs(reinterpret_cast<const uint4*>(rb_ + ((long long)(y0 + r0 + u) * w + ox) * r_ld));
+        }
 #pragma unroll
       for (int u = 0; u < 4; ++u)
         if (r0 + u < nrows) {
@@ -84,7 +92,20 @@ dwdynconv_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int h, int w, in
           unpack8r(raw[u], v);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = fmaf(fmaf(kw[0], v[j], 0.f), cw[j], v[j]);
-          *reinterpret_cast<uint4*>(yb_ + ((long long)(y0 + r0 + u) * w + ox) * y_ld) = pack8r(o);
+          if (kFold) {
+            // same association as the unfused pair of kernels would have in fp32: (x + cw * dw) + res
+            float r[8];
+            unpack8r(rr[u], r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += r[j];
+            const uint4 out = pack8r(o);
+            unpack8r(out, o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s1 += o[j]; s2 = fmaf(o[j], o[j], s2); }
+            *reinterpret_cast<uint4*>(yb_ + ((long long)(y0 + r0 + u) * w + ox) * y_ld) = out;
+          } else {
+            *reinterpret_cast<uint4*>(yb_ + ((long long)(y0 + r0 + u) * w + ox) * y_ld) = pack8r(o);
+          }
         }
     }
     (void)f;
@@ -138,7 +159,19 @@ dwdynconv_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int h, int w, in
           unpack8r(__ldg(reinterpret_cast<const uint4*>(xb_ + ((long long)oy * w + ox) * x_ld)), centre);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = fmaf(cw[j], acc[dslot][j], centre[j]);
-          *reinterpret_cast<uint4*>(yb_ + ((long long)oy * w + ox) * y_ld) = pack8r(o);
+          if (kFold) {
+            float r[8];
+            unpack8r(__ldcs(reinterpret_cast<const uint4*>(rb_ + ((long long)oy * w + ox) * r_ld)), r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += r[j];
+            const uint4 out = pack8r(o);
+            unpack8r(out, o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s1 += o[j]; s2 = fmaf(o[j], o[j], s2); }
+            *reinterpret_cast<uint4*>(yb_ + ((long long)oy * w + ox) * y_ld) = out;
+          } else {
+            *reinterpret_cast<uint4*>(yb_ + ((long long)oy * w + ox) * y_ld) = pack8r(o);
+          }
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[dslot][j] = 0.f;          // the slot now belongs to output row done + KS
@@ -147,6 +180,56 @@ dwdynconv_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int h, int w, in
       }
     }
   }
+}
+
+// block-wide sum of (s1, s2) -> two atomics per block
+__device__ __forceinline__ void block_sum2_atomic(float s1, float s2, float* dst) {
+  __shared__ float red[2][8];
+  for (int off = 16; off; off >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, off); s2 += __shfl_xor_sync(0xffffffffu, s2, off); }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s1 = threadIdx.x < 8 ? red[0][threadIdx.x] : 0.f;
+    s2 = threadIdx.x < 8 ? red[1][threadIdx.x] : 0.f;
+    for (int off = 4; off; off >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, off); s2 += __shfl_xor_sync(0xffffffffu, s2, off); }
+    if (threadIdx.x == 0) { atomicAdd(dst, s1); atomicAdd(dst + 1, s2); }
+  }
+}
+
+template <int KS>
+__global__ void __launch_bounds__(256)
+dwdynconv_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int h, int w, int c,
+                 const float* __restrict__ channel_w, const float* __restrict__ kernel_w, int xblocks, int rows,
+                 __nv_bfloat16* __restrict__ y, int y_ld) {
+  float s1 = 0.f, s2 = 0.f;
+  dwdynconv_body<KS, false>(x, x_ld, h, w, c, channel_w, kernel_w, xblocks, rows, y, y_ld, nullptr, 0, s1, s2);
+}
+
+// + residual + per-sample statistics of the result (stats[2 * b], stats[2 * b + 1], caller-zeroed)
+template <int KS>
+__global__ void __launch_bounds__(256)
+dwdynconv_res_stats_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int h, int w, int c,
+                           const float* __restrict__ channel_w, const float* __restrict__ kernel_w, int xblocks, int rows,
+                           __nv_bfloat16* __restrict__ y, int y_ld, const __nv_bfloat16* __restrict__ res, int r_ld,
+                           float* __restrict__ stats) {
+  float s1 = 0.f, s2 = 0.f;
+  dwdynconv_body<KS, true>(x, x_ld, h, w, c, channel_w, kernel_w, xblocks, rows, y, y_ld, res, r_ld, s1, s2);
+  block_sum2_atomic(s1, s2, stats + 2 * blockIdx.z);
+}
+
+// GroupNorm(1 group) folded into the 1x1 convolution behind it.  With z = (v - mean_n) * rstd_n * gamma + beta and
+// W' = W * diag(gamma):  conv(z)[o] = rstd_n * (W' v)[o] + (W beta)[o] - mean_n * rstd_n * sum_c W'[o][c], so the GEMM runs on
+// the un-normalised v and its epilogue needs two numbers per image: (rstd_n, mean_n * rstd_n).
+__global__ void gn_fold_kernel(const float* __restrict__ stats, int n, double inv_count, float eps, float* __restrict__ out) {
+  const int img = blockIdx.x * blockDim.x + threadIdx.x;
+  if (img >= n) return;
+  // E[x^2] - E[x]^2 in double (cancellation), one fp32 rsqrt — as gn_apply_kernel
+  const double m = (double)stats[2 * img] * inv_count;
+  double var = fma(-m, m, (double)stats[2 * img + 1] * inv_count);
+  if (var < 0) var = 0;
+  const float rstd = rsqrtf((float)var + eps);
+  out[2 * img] = rstd;
+  out[2 * img + 1] = (float)m * rstd;
 }
 
 // out[r][o] = act(sum_c in[r][c] * W[o][c] + b[o]); one warp per output element
@@ -385,6 +468,33 @@ extern "C" int uavdet_dwdynconv_fwd(const uavdet_act* x, const float* channel_w,
   return UAVDET_OK;
 }
 
+extern "C" int uavdet_dwdynconv_res_stats_fwd(const uavdet_act* x, const float* channel_w, const float* kernel_w, int k, int pad,
+                                              const uavdet_act* res, float* stats, const uavdet_act* y, void* stream) {
+  int rc;
+  if ((rc = chk(x, "dwdynconv x")) || (rc = chk(y, "dwdynconv y")) || (rc = chk(res, "dwdynconv res"))) return rc;
+  UAVDET_CHECK_ARG(channel_w && kernel_w && stats && k >= 1 && k <= 7 && 2 * pad == k - 1, "dwdynconv: bad arguments (k=%d pad=%d)", k, pad);
+  UAVDET_CHECK_ARG(x->n == y->n && x->h == y->h && x->w == y->w && x->c == y->c, "dwdynconv: shape mismatch");
+  UAVDET_CHECK_ARG(x->n == res->n && x->h == res->h && x->w == res->w && x->c == res->c, "dwdynconv: residual shape mismatch");
+  const int G = x->c / 8, Gb = G < 32 ? G : 32, PL = 256 / Gb;
+  const int xblocks = ceil_div(x->w, PL);
+  int rows = 32;
+  while (rows > 4 && (long long)xblocks * ceil_div(x->h, rows) * ceil_div(G, Gb) * x->n < 8 * kNumSMs) rows >>= 1;
+  dim3 grid((unsigned)(xblocks * ceil_div(x->h, rows)), (unsigned)ceil_div(G, Gb), (unsigned)x->n);
+  const __nv_bfloat16* xp = (const __nv_bfloat16*)x->ptr;
+  __nv_bfloat16* yp = (__nv_bfloat16*)y->ptr;
+#define UAVDET_DW(KS) dwdynconv_res_stats_kernel<KS><<<grid, 256, 0, ST>>>(xp, x->ld, x->h, x->w, x->c, channel_w, kernel_w, xblocks, \
+                                                                          rows, yp, y->ld, (const __nv_bfloat16*)res->ptr, res->ld, stats)
+  switch (k) {
+    case 1: UAVDET_DW(1); break;
+    case 3: UAVDET_DW(3); break;
+    case 5: UAVDET_DW(5); break;
+    default: UAVDET_DW(7); break;
+  }
+#undef UAVDET_DW
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
 extern "C" int uavdet_linear(const float* in, int rows, int c, const float* w, const float* bias, int out_dim, int act,
                              float* out, void* stream) {
   UAVDET_CHECK_ARG(in && w && out && rows > 0 && c > 0 && out_dim > 0, "linear: bad arguments");
@@ -394,15 +504,7 @@ extern "C" int uavdet_linear(const float* in, int rows, int c, const float* w, c
   return UAVDET_OK;
 }
 
-extern "C" int uavdet_groupnorm1(const uavdet_act* a, const uavdet_act* b, const float* gamma, const float* beta,
-                                 float eps, float* stats_ws, const uavdet_act* y, void* stream) {
-  int rc;
-  if ((rc = chk(a, "groupnorm a")) || (rc = chk(y, "groupnorm y"))) return rc;
-  if (b && (rc = chk(b, "groupnorm b"))) return rc;
-  UAVDET_CHECK_ARG(gamma && beta && stats_ws, "groupnorm: null pointer");
-  UAVDET_CHECK_ARG(a->n == y->n && a->h == y->h && a->w == y->w && a->c == y->c, "groupnorm: shape mismatch");
-  if (b) UAVDET_CHECK_ARG(a->n == b->n && a->h == b->h && a->w == b->w && a->c == b->c, "groupnorm: residual shape mismatch");
-  UAVDET_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * a->n, ST));
+static int gn_grid(const uavdet_act* a, dim3* grid, int* hw_out) {
   const long long hw64 = (long long)a->h * a->w;
   UAVDET_CHECK_ARG(hw64 < (1ll << 30), "groupnorm: map too large");
   const int hw = (int)hw64;
@@ -411,12 +513,46 @@ extern "C" int uavdet_groupnorm1(const uavdet_act* a, const uavdet_act* b, const
   long long cap = ((long long)kNumSMs * 16) / ((long long)a->n * gy) + 1;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
-  dim3 grid((unsigned)bx, (unsigned)gy, (unsigned)a->n);
-  const __nv_bfloat16* bp = b ? (const __nv_bfloat16*)b->ptr : nullptr;
-  gn_stats_kernel<<<grid, 256, 0, ST>>>((const __nv_bfloat16*)a->ptr, a->ld, bp, b ? b->ld : 0, hw, a->c, stats_ws);
+  *grid = dim3((unsigned)bx, (unsigned)gy, (unsigned)a->n);
+  *hw_out = hw;
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_groupnorm1_stats(const uavdet_act* a, const uavdet_act* b, float* stats, void* stream) {
+  int rc;
+  if ((rc = chk(a, "groupnorm a"))) return rc;
+  if (b && (rc = chk(b, "groupnorm b"))) return rc;
+  UAVDET_CHECK_ARG(stats, "groupnorm: null pointer");
+  if (b) UAVDET_CHECK_ARG(a->n == b->n && a->h == b->h && a->w == b->w && a->c == b->c, "groupnorm: residual shape mismatch");
+  UAVDET_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * a->n, ST));
+  dim3 grid;
+  int hw;
+  if ((rc = gn_grid(a, &grid, &hw))) return rc;
+  gn_stats_kernel<<<grid, 256, 0, ST>>>((const __nv_bfloat16*)a->ptr, a->ld, b ? (const __nv_bfloat16*)b->ptr : nullptr,
+                                        b ? b->ld : 0, hw, a->c, stats);
   UAVDET_LAUNCH_CHECK();
-  gn_apply_kernel<<<grid, 256, 0, ST>>>((const __nv_bfloat16*)a->ptr, a->ld, bp, b ? b->ld : 0, hw, a->c, stats_ws, eps,
-                                        gamma, beta, (__nv_bfloat16*)y->ptr, y->ld);
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_groupnorm1_fold(const float* stats, int n, double count, float eps, float* sample_affine, void* stream) {
+  UAVDET_CHECK_ARG(stats && sample_affine && n > 0 && count > 0, "groupnorm fold: bad arguments");
+  gn_fold_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ST>>>(stats, n, 1.0 / count, eps, sample_affine);
+  UAVDET_LAUNCH_CHECK();
+  return UAVDET_OK;
+}
+
+extern "C" int uavdet_groupnorm1(const uavdet_act* a, const uavdet_act* b, const float* gamma, const float* beta,
+                                 float eps, float* stats_ws, const uavdet_act* y, void* stream) {
+  int rc;
+  if ((rc = chk(a, "groupnorm a")) || (rc = chk(y, "groupnorm y"))) return rc;
+  UAVDET_CHECK_ARG(gamma && beta && stats_ws, "groupnorm: null pointer");
+  UAVDET_CHECK_ARG(a->n == y->n && a->h == y->h && a->w == y->w && a->c == y->c, "groupnorm: shape mismatch");
+  if ((rc = uavdet_groupnorm1_stats(a, b, stats_ws, stream))) return rc;
+  dim3 grid;
+  int hw;
+  if ((rc = gn_grid(a, &grid, &hw))) return rc;
+  gn_apply_kernel<<<grid, 256, 0, ST>>>((const __nv_bfloat16*)a->ptr, a->ld, b ? (const __nv_bfloat16*)b->ptr : nullptr,
+                                        b ? b->ld : 0, hw, a->c, stats_ws, eps, gamma, beta, (__nv_bfloat16*)y->ptr, y->ld);
   UAVDET_LAUNCH_CHECK();
   return UAVDET_OK;
 }

@@ -14,6 +14,7 @@ attribute names are swapped (obj head owns `conv_bbox`, :223,243); anchors are n
 """
 from __future__ import annotations
 
+import os
 from typing import List
 
 import torch
@@ -24,6 +25,9 @@ from ..engine import ConvUnit, Executor
 from ..utils.datatype import DetectionResults
 from . import _base
 from ._base import LightningModule, to_nchw, to_nhwc
+
+
+_NO_GN_FOLD = bool(os.environ.get("UAVDET_RTM_NO_GN_FOLD"))     # A/B switch: GroupNorm as two streaming passes
 
 
 class ConvModule(_base.ConvModule):
@@ -58,12 +62,18 @@ class MDyConv(LightningModule):
         self.kernel_fc = nn.Conv2d(attention_out_c, int(self.dy_kernel_size ** 2), kernel_size=(1, 1))
 
     def forward_nhwc(self, x, ex: Executor, out=None):
-        y = ex.conv_forward(self.base_conv.unit(), x, False, None)
+        return self.dynamic_nhwc(ex.conv_forward(self.base_conv.unit(), x, False, None), out=out)
+
+    def dynamic_nhwc(self, y, res=None, stats=None, out=None):
+        """Everything behind base_conv: attention on the pooled map -> per-sample depthwise kernel -> conv + y
+        (+ `res` and the per-sample statistics of the result, for the GroupNorm the MDyEncoder applies next)."""
         pooled = ops.gap(y)
         att = self.attention[1]
         a = ops.linear(pooled, att.weight.detach().flatten(1), att.bias.detach(), "relu")
         ch_w = ops.linear(a, self.channel_fc.weight.detach().flatten(1), self.channel_fc.bias.detach())
         k_w = ops.linear(a, self.kernel_fc.weight.detach().flatten(1), self.kernel_fc.bias.detach())
+        if res is not None:
+            return ops.dwdynconv_res_stats_fwd(y, ch_w, k_w, self.dy_kernel_size, self.dy_padding, res, stats, out=out)
         return ops.dwdynconv_fwd(y, ch_w, k_w, self.dy_kernel_size, self.dy_padding, out=out)
 
     def forward(self, x):
@@ -114,8 +124,66 @@ class MDyEncoder(LightningModule):
         self.channel_mlp = nn.Sequential(nn.Conv2d(in_channels, in_channels, kernel_size=(1, 1)), nn.GELU(), nn.Dropout(0.2),
                                          nn.Conv2d(in_channels, out_channels, kernel_size=(1, 1)))
         self.third = in_channels // 3
+        self._fold = None
+
+    def _folded(self, ex: Executor):
+        """Constants of the GroupNorm folds, rebuilt when a parameter / running statistic they depend on changes.
+
+        GroupNorm(1 group) is one affine map per sample, z = (v - mean_n) * rstd_n * gamma + beta, and both of its consumers
+        are 1x1 convolutions (the three MDyConv.base_conv of :165-169 read GN_in(x); channel_mlp[0] of :174-177 reads
+        GN_out(cat + x)), so the map moves into their epilogues: W' = diag(a) * W * diag(gamma) in bf16 (a = the folded
+        eval-mode BatchNorm scale behind the convolution, or 1) and y = act(acc * rstd_n + b - mean_n * rstd_n *
+        rowsum(W')) with b = a * (W beta) + BatchNorm shift / bias (`sample_affine` epilogue).  The three base
+        convolutions also become ONE 192 -> 192 (384 -> 384) GEMM: their input is read once instead of three times, and
+        the normalised tensor is never written."""
+        from ..engine import param_epoch
+        gi, go = self.group_norm_in, self.group_norm_out
+        mdys = (self.mdy_conv_1x1, self.mdy_conv_3x3, self.mdy_conv_5x5)
+        bns = [m.base_conv.conv[1] for m in mdys]
+        deps = [gi.weight, gi.bias, go.weight, go.bias, self.channel_mlp[0].weight, self.channel_mlp[0].bias]
+        for m, bn in zip(mdys, bns):
+            deps += [m.base_conv.conv[0].weight, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        ver = (param_epoch(),) + tuple((t._version, t.data_ptr()) for t in deps)
+        if self._fold is not None and self._fold[0] == ver:
+            return self._fold[1]
+        with torch.no_grad():
+            w_in = torch.cat([m.base_conv.conv[0].weight.detach().flatten(1) for m in mdys])            # (3t, C)
+            folds = [ex.bn_fold(bn, m.base_conv.conv[0].bias) for m, bn in zip(mdys, bns)]
+            a_in = torch.cat([f[0] for f in folds])
+            wp_in = (a_in[:, None] * w_in * gi.weight.detach()[None, :]).to(torch.bfloat16).contiguous()
+            b_in = (a_in * (w_in @ gi.bias.detach()) + torch.cat([f[1] for f in folds])).contiguous()
+            w_out = self.channel_mlp[0].weight.detach().flatten(1)                                        # (C, C)
+            wp_out = (w_out * go.weight.detach()[None, :]).to(torch.bfloat16).contiguous()
+            b_out = (w_out @ go.bias.detach() + self.channel_mlp[0].bias.detach()).contiguous()
+            # row sums of the ROUNDED weights: the mean term then cancels what the tensor core accumulated
+            consts = dict(wp_in=wp_in, wg_in=wp_in.float().sum(1).contiguous(), b_in=b_in,
+                          wp_out=wp_out, wg_out=wp_out.float().sum(1).contiguous(), b_out=b_out)
+        self._fold = (ver, consts)
+        return consts
 
     def forward_nhwc(self, x, ex: Executor, out=None):
+        if _NO_GN_FOLD:
+            return self._forward_nhwc_unfused(x, ex, out)
+        gi, go = self.group_norm_in, self.group_norm_out
+        k = self._folded(ex)
+        n, h, w, c = x.shape
+        t = self.third
+        # GN_in + the three base convolutions: one GEMM on the raw input with a per-sample epilogue
+        sa = ops.groupnorm1_fold(ops.groupnorm1_stats(x), h * w * c, gi.eps)
+        base = ops.conv_fwd(x, k["wp_in"], 3 * t, 1, 1, 0, act="relu", scale=k["wg_in"], shift=k["b_in"], sample_affine=sa)
+        # the dynamic depthwise convolutions write cat + x and its per-sample statistics
+        cat = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+        stats = torch.zeros((n, 2), dtype=torch.float32, device=x.device)
+        for i, m in enumerate((self.mdy_conv_1x1, self.mdy_conv_3x3, self.mdy_conv_5x5)):
+            sl = slice(i * t, (i + 1) * t)
+            m.dynamic_nhwc(base[..., sl], res=x[..., sl], stats=stats, out=cat[..., sl])
+        # GN_out + channel_mlp[0] + GELU
+        sa = ops.groupnorm1_fold(stats, h * w * c, go.eps)
+        z = ops.conv_fwd(cat, k["wp_out"], c, 1, 1, 0, act="gelu", scale=k["wg_out"], shift=k["b_out"], sample_affine=sa)
+        return ex.conv_forward(ConvUnit(self.channel_mlp[3], None, "none"), z, False, None, out=out)
+
+    def _forward_nhwc_unfused(self, x, ex: Executor, out=None):
+        """The operator-by-operator form (UAVDET_RTM_NO_GN_FOLD=1): GroupNorm as a statistics and a normalise pass."""
         gi, go = self.group_norm_in, self.group_norm_out
         y = ops.groupnorm1(x, gi.weight.detach(), gi.bias.detach(), gi.eps)
         cat = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)

@@ -289,7 +289,7 @@ def unpack_wgrad(dw_packed: torch.Tensor, o: int, i: int, k: int, grad: Optional
 # --------------------------------------------------------------------------------------------
 def _epilogue(epi: int = EPI_AFFINE, act=None, scale=None, shift=None, res: Optional[torch.Tensor] = None,
               sum_=None, sumsq=None, head_obj=None, head_bbox=None, head_anchors: int = 0,
-              shift_per_sample: bool = False) -> Epilogue:
+              shift_per_sample: bool = False, sample_affine=None) -> Epilogue:
     e = Epilogue()
     e.epi = epi
     e.act = ACT[act] if not isinstance(act, int) else act
@@ -306,6 +306,7 @@ def _epilogue(epi: int = EPI_AFFINE, act=None, scale=None, shift=None, res: Opti
     e.head_bbox = head_bbox.data_ptr() if head_bbox is not None else None
     e.head_anchors = head_anchors
     e.shift_per_sample = 1 if shift_per_sample else 0
+    e.sample_affine = sample_affine.data_ptr() if sample_affine is not None else None
     return e
 
 
@@ -316,9 +317,10 @@ def conv_out_hw(h: int, w: int, k: int, stride: int, pad: int) -> Tuple[int, int
 def conv_fwd(x: torch.Tensor, w_packed: torch.Tensor, cout: int, k: int, stride: int, pad: int, *,
              s2d: bool = False, w_batch: int = 1, out: Optional[torch.Tensor] = None, epi: int = EPI_AFFINE,
              act=None, scale=None, shift=None, res=None, sum_=None, sumsq=None,
-             shift_per_sample: bool = False) -> torch.Tensor:
+             shift_per_sample: bool = False, sample_affine=None) -> torch.Tensor:
     """Implicit-GEMM conv.  x NHWC bf16; w_packed from pack_weight / dyn_aggregate.
-    shift_per_sample: `shift` is (n, cout) — one bias row per image."""
+    shift_per_sample: `shift` is (n, cout) — one bias row per image.
+    sample_affine: (n, 2) fp32 from groupnorm1_fold — the GroupNorm-fold epilogue (see the header)."""
     _require_cuda(x, w_packed)
     n, h, w, _ = x.shape
     hin, win = (h // 2, w // 2) if s2d else (h, w)
@@ -326,7 +328,11 @@ def conv_fwd(x: torch.Tensor, w_packed: torch.Tensor, cout: int, k: int, stride:
     if out is None:
         out = empty_act(n, ho, wo, cout, x.device)
     xv, yv = act_view(x), act_view(out)
-    e = _epilogue(epi, act, _f32(scale), _f32(shift), res, _f32(sum_), _f32(sumsq), shift_per_sample=shift_per_sample)
+    if sample_affine is not None and (tuple(sample_affine.shape) != (n, 2) or sample_affine.dtype != torch.float32
+                                      or not sample_affine.is_contiguous()):
+        raise UavdetError(f"sample_affine must be a contiguous ({n}, 2) fp32 tensor")
+    e = _epilogue(epi, act, _f32(scale), _f32(shift), res, _f32(sum_), _f32(sumsq), shift_per_sample=shift_per_sample,
+                  sample_affine=sample_affine)
     check(_lib.load().uavdet_conv_fwd(C.byref(xv), _ptr(w_packed), w_batch, cout, k, stride, pad, 1 if s2d else 0,
                                       C.byref(yv), C.byref(e), _stream()), "conv_fwd")
     return out
@@ -813,6 +819,19 @@ def dwdynconv_fwd(x, channel_w, kernel_w, k, pad, out=None):
     return out
 
 
+def dwdynconv_res_stats_fwd(x, channel_w, kernel_w, k, pad, res, stats, out=None):
+    """out = dwdynconv(x) + res; stats (n, 2) fp32 += per-sample [sum, sum of squares] of the bf16-rounded result."""
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    if stats.dtype != torch.float32 or tuple(stats.shape) != (x.shape[0], 2) or not stats.is_contiguous():
+        raise UavdetError("dwdynconv_res_stats_fwd: stats must be a contiguous (n, 2) fp32 tensor")
+    xv, rv, yv = act_view(x), act_view(res), act_view(out)
+    check(_lib.load().uavdet_dwdynconv_res_stats_fwd(C.byref(xv), _ptr(_f32(channel_w)), _ptr(_f32(kernel_w)), k, pad,
+                                                     C.byref(rv), _ptr(stats), C.byref(yv), _stream()),
+          "dwdynconv_res_stats_fwd")
+    return out
+
+
 def linear(inp, w, bias=None, act=None):
     rows, c = inp.shape
     o = w.shape[0]
@@ -830,6 +849,26 @@ def groupnorm1(a, gamma, beta, eps, b=None, out=None):
     bv = act_view(b) if b is not None else None
     check(_lib.load().uavdet_groupnorm1(C.byref(av), C.byref(bv) if bv is not None else None, _ptr(_f32(gamma)),
                                         _ptr(_f32(beta)), float(eps), _ptr(ws), C.byref(yv), _stream()), "groupnorm1")
+    return out
+
+
+def groupnorm1_stats(a, b=None):
+    """(n, 2) fp32: per-sample sum and sum of squares of (a [+ b]) over h*w*c."""
+    stats = torch.empty((a.shape[0], 2), dtype=torch.float32, device=a.device)
+    av = act_view(a)
+    bv = act_view(b) if b is not None else None
+    check(_lib.load().uavdet_groupnorm1_stats(C.byref(av), C.byref(bv) if bv is not None else None, _ptr(stats), _stream()),
+          "groupnorm1_stats")
+    return stats
+
+
+def groupnorm1_fold(stats, count, eps):
+    """(n, 2) per-sample [sum, sum of squares] over `count` elements -> (n, 2) [rstd, mean * rstd]: the `sample_affine`
+    of the 1x1 conv that absorbs GroupNorm(1 group) (see uavdet_epilogue in the header for the algebra)."""
+    n = stats.shape[0]
+    out = torch.empty((n, 2), dtype=torch.float32, device=stats.device)
+    check(_lib.load().uavdet_groupnorm1_fold(_ptr(_f32(stats)), n, float(count), float(eps), _ptr(out), _stream()),
+          "groupnorm1_fold")
     return out
 
 

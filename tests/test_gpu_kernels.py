@@ -808,6 +808,65 @@ def test_linear_groupnorm_bilinear_rtm_head(lib):
     torch.testing.assert_close(obj.cpu(), torch.sigmoid(ol), rtol=2e-6, atol=1e-6)
 
 
+@pytest.mark.parametrize("k", [1, 3, 5])
+def test_dwdynconv_res_stats_adds_residual_and_sums(lib, k):
+    """The MDyEncoder form of the depthwise dynamic conv (RTMUAVDet.py:163-174): + the encoder's residual, and the per-sample
+    sum / sum of squares of the bf16-rounded result (the statistics of the GroupNorm that follows)."""
+    ops = _ops(lib)
+    g = torch.Generator().manual_seed(157 + k)
+    n, c, h, w = 3, 64, 37, 21
+    x = bf16_round(torch.randn(n, c, h, w, generator=g))
+    r = bf16_round(torch.randn(n, c, h, w, generator=g) * 2 + 0.3)
+    ch_w, k_w = torch.randn(n, c, generator=g), torch.randn(n, k * k, generator=g)
+    filt = (k_w.view(n, 1, k, k) * ch_w.view(n, c, 1, 1)).reshape(n * c, 1, k, k)
+    ref = F.conv2d(x.reshape(1, n * c, h, w), filt, None, 1, k // 2, groups=n * c).view(n, c, h, w) + x + r
+    buf = torch.zeros(n, h, w, 192, dtype=torch.bfloat16, device=DEV)
+    rbuf = torch.zeros(n, h, w, 128, dtype=torch.bfloat16, device=DEV)
+    rbuf[..., 64:] = nhwc(r)
+    stats = torch.zeros(n, 2, dtype=torch.float32, device=DEV)
+    stats[:, 0] = 5.0                                                  # the kernel accumulates
+    ops.dwdynconv_res_stats_fwd(nhwc(x), ch_w.to(DEV), k_w.to(DEV), k, k // 2, rbuf[..., 64:], stats, out=buf[..., 64:128])
+    got = to_nchw(buf[..., 64:128])
+    assert_close_bf16(got, ref, f"dwdynconv+res k={k}")
+    assert torch.all(buf[..., :64] == 0) and torch.all(buf[..., 128:] == 0)
+    want = torch.stack([got.double().sum(dim=(1, 2, 3)) + 5.0, (got.double() ** 2).sum(dim=(1, 2, 3))], 1)
+    torch.testing.assert_close(stats.cpu().double(), want, rtol=2e-5, atol=1e-2)
+
+
+def test_groupnorm_folded_into_the_1x1_conv_behind_it(lib):
+    """GroupNorm(1 group) -> 1x1 conv (-> eval BatchNorm) -> activation as ONE GEMM on the un-normalised tensor with a
+    per-image (rstd, mean * rstd) epilogue (uavdet_groupnorm1_stats / _fold, uavdet_epilogue::sample_affine), against F.group_norm +
+    F.conv2d in fp32 (RTMUAVDet.py:165-177)."""
+    ops = _ops(lib)
+    g = torch.Generator().manual_seed(258)
+    n, c, h, w, cout = 3, 96, 18, 22, 64
+    x = bf16_round(torch.randn(n, c, h, w, generator=g) * torch.tensor([0.5, 2.0, 1.0]).view(n, 1, 1, 1)
+                   + torch.tensor([0.7, -1.5, 0.0]).view(n, 1, 1, 1))
+    r = bf16_round(torch.randn(n, c, h, w, generator=g))
+    gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.3
+    wt, bias = torch.randn(cout, c, 1, 1, generator=g) / c ** 0.5, torch.randn(cout, generator=g) * 0.2
+    a = torch.rand(cout, generator=g) + 0.5                          # a folded BatchNorm scale behind the conv
+    for res, act, a_vec in ((None, "relu", a), (r, "gelu", None)):
+        v = x if res is None else x + r
+        z = F.conv2d(F.group_norm(v, 1, gamma, beta, 1e-5), wt, None)
+        ref = (F.relu if act == "relu" else F.gelu)((z * a_vec.view(1, -1, 1, 1) if a_vec is not None else z) + bias.view(1, -1, 1, 1))
+        rows = a_vec[:, None] if a_vec is not None else 1.0
+        wp = (rows * wt.flatten(1) * gamma[None, :]).to(torch.bfloat16).to(DEV)
+        wg = wp.float().sum(1)
+        wb = wt.flatten(1) @ beta
+        b_vec = ((a_vec * wb if a_vec is not None else wb) + bias).to(DEV)
+        stats = ops.groupnorm1_stats(nhwc(x), None if res is None else nhwc(r))
+        vd = (nhwc(x).float() + (0 if res is None else nhwc(r).float())).to(torch.bfloat16)
+        want_stats = torch.stack([v.double().sum(dim=(1, 2, 3)), (v.double() ** 2).sum(dim=(1, 2, 3))], 1)
+        torch.testing.assert_close(stats.cpu().double(), want_stats, rtol=2e-5, atol=1e-2)
+        sa = ops.groupnorm1_fold(stats, h * w * c, 1e-5)
+        mean, var = v.double().mean(dim=(1, 2, 3)), v.double().var(dim=(1, 2, 3), unbiased=False)
+        rstd = (var + 1e-5).rsqrt()
+        torch.testing.assert_close(sa.cpu().double(), torch.stack([rstd, mean * rstd], 1), rtol=1e-5, atol=1e-5)
+        y = ops.conv_fwd(vd, wp, cout, 1, 1, 0, act=act, scale=wg, shift=b_vec, sample_affine=sa)
+        assert_close_bf16(to_nchw(y), ref, f"groupnorm fold ({act})", rel=8e-3)
+
+
 def test_stem_zero_padded_odd_output(lib):
     """RTM stem 5x5 s2 p1: 39 -> 18.. odd outputs are stored with a zero last row/column."""
     ops = _ops(lib)

@@ -299,6 +299,39 @@ def test_rtmuavdet_forward_matches_oracle(lib):
         assert rb < 0.01 and ro < 0.01      # ~2 x 0.40 % reference self-drift
 
 
+def test_mdy_encoder_folded_groupnorms_match_oracle(lib):
+    """MDyEncoder (RTMUAVDet.py:144-184) with both GroupNorms folded into the 1x1 convolutions behind them and the three
+    base convolutions as one GEMM, against the oracle's operator-by-operator fp32 form; samples with different means /
+    spreads exercise the per-sample epilogue."""
+    from oracle import oracle as O
+    from multimodal_uav_det_b200.engine import Executor
+    from multimodal_uav_det_b200.model.RTMUAVDet import MDyEncoder
+    torch.manual_seed(3)
+    enc = MDyEncoder(192, 128)
+    randomize_bn(enc)
+    with torch.no_grad():
+        for gn in (enc.group_norm_in, enc.group_norm_out):
+            gn.weight.uniform_(0.5, 1.5)
+            gn.bias.normal_(0, 0.2)
+    enc.eval()
+    sd = copy.deepcopy(enc.state_dict())
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(3, 192, 40, 24, generator=g) * torch.tensor([0.5, 1.0, 3.0]).view(3, 1, 1, 1) \
+        + torch.tensor([0.0, 1.0, -2.0]).view(3, 1, 1, 1)
+    x = x.bfloat16().float()
+    with torch.no_grad():
+        want = O.mdy_encoder(x, {"e." + k: v for k, v in sd.items()}, "e")
+        enc = enc.to(DEV)
+        got = enc.forward_nhwc(x.to(DEV).permute(0, 2, 3, 1).contiguous().bfloat16(), Executor())
+        unf = enc._forward_nhwc_unfused(x.to(DEV).permute(0, 2, 3, 1).contiguous().bfloat16(), Executor())
+    from multimodal_uav_det_b200 import ops
+    ops.check_device()
+    r_f = rel_l2(got.float().permute(0, 3, 1, 2).cpu(), want)
+    r_u = rel_l2(unf.float().permute(0, 3, 1, 2).cpu(), want)
+    print(f"mdy_encoder rel_l2: folded {r_f:.4f}, unfused {r_u:.4f}")
+    assert r_f < 0.01 and r_f < 1.5 * r_u + 1e-3
+
+
 def test_detect_decode_nms_bit_exact_on_model_outputs(lib):
     """C1: BaselineModel forward + decode + NMS.  Kept indices must be bit-identical to the oracle's
     NMS on the SAME fp32 boxes/scores (the decode itself is checked to fp32 tolerance)."""

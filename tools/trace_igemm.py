@@ -18,6 +18,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "rtm":      # the channel MLPs of RTMUAV
 if len(sys.argv) > 1 and sys.argv[1] == "rtm2":     # MDyConv's 32 -> 128 1x1 (ReLU) and its neighbours
     CASES = [(32, 32, 128, 1, 1, 160, "relu"), (32, 32, 128, 1, 1, 160, "none"), (32, 32, 128, 1, 1, 160, "silu"),
              (32, 64, 32, 1, 1, 160, "silu"), (32, 128, 32, 1, 1, 160, "silu"), (32, 64, 128, 1, 1, 160, "relu")]
+FOLD = len(sys.argv) > 1 and sys.argv[1] == "rtmfold"   # channel-MLP GELU conv: plain / GroupNorm-fold epilogue (sample_affine)
+if FOLD:
+    CASES = [(32, 192, 192, 1, 1, 160, "gelu"), (32, 192, 192, 1, 1, 160, "gelu+fold"), (32, 192, 192, 1, 1, 160, "relu"),
+             (32, 192, 192, 1, 1, 160, "relu+fold")]
 for (n, cin, cout, k, s, hw, stats) in CASES:
     x = torch.randn(n, hw, hw, cin, device="cuda").bfloat16()
     w = ops.pack_weight(torch.randn(cout, cin, k, k, device="cuda") * 0.05)
@@ -25,6 +29,9 @@ for (n, cin, cout, k, s, hw, stats) in CASES:
     kw = dict(epi=EPI_STATS, sum_=s1, sumsq=s2) if stats is True else dict(act=stats if isinstance(stats, str) else "leaky")
     if stats is not True:      # eval-mode BatchNorm folded into the epilogue, as the inference models launch it
         kw.update(scale=torch.rand(cout, device="cuda") + 0.5, shift=torch.randn(cout, device="cuda") * 0.1)
+    if isinstance(stats, str) and stats.endswith("+fold"):
+        kw["act"] = stats[:-5]
+        kw["sample_affine"] = torch.stack([torch.rand(n, device="cuda") + 0.5, torch.randn(n, device="cuda")], 1).contiguous()
     for _ in range(2):
         ops.conv_fwd(x, w, cout, k, s, k // 2, **kw)
     torch.cuda.synchronize()
