@@ -430,6 +430,10 @@ class ConvTimer:
         self._orig_s2f = ops.conv_dgrad_s2_fused
         ops.conv_dgrad_s2_fused = timed(self._orig_s2f, "igemm",
                                         lambda a, kw: 2.0 * a[0].shape[0] * a[0].shape[1] * a[0].shape[2] * a[0].shape[3] * a[2] * 9)
+        # pixel-pair 3x3 convolution (RTMUAVDet's 256 -> 64 neck layer): the algorithmic flops of the 3x3 layer, not the 12 column shifts
+        self._orig_pair = ops.conv3x3_pair_fwd
+        ops.conv3x3_pair_fwd = timed(self._orig_pair, "igemm",
+                                     lambda a, kw: 2.0 * a[0].shape[0] * a[0].shape[1] * a[0].shape[2] * a[0].shape[3] * a[2] * 9)
         # the tensor-core stem (stem_mma.cu) is HBM-bound: recorded with its algorithmic bytes (fp32 NCHW input read +
         # NHWC bf16 tensor written / read), under kinds of its own so it stays out of the igemm / wgrad aggregates
         self._orig_stem = (ops.stem_mma_fwd, ops.stem_mma_wgrad)
@@ -457,6 +461,7 @@ class ConvTimer:
         self.ops.stem_mma_fwd, self.ops.stem_mma_wgrad = self._orig_stem
         self.ops.conv_dgrad_s2_fused = self._orig_s2f
         self.ops.conv_head = self._orig_head
+        self.ops.conv3x3_pair_fwd = self._orig_pair
         if self._orig_bn is not None:
             self.ops.bn_act_fwd, self.ops.bn_act_bwd, self.ops.bn_train_fwd = self._orig_bn
 

@@ -185,6 +185,14 @@ int uavdet_pack_dgrad_s2_fused(const void* w_packed_t, int cin, int cout, void* 
 int uavdet_conv_dgrad_s2_fused(const uavdet_act* dy, const void* w_fused, int cin, const uavdet_act* dx,
                                const uavdet_epilogue* epi, void* stream);
 
+/* 3x3 stride-1 pad-1 convolution with cout in {64, 128}, two adjacent output pixels per GEMM row (nn.Conv2d at
+ * RTMUAVDet.py:194, 256 -> 64 at 160x160: an N = 64 GEMM runs the tensor core at half rate).  w_pair: bf16
+ * [2*cout][3*4*cin], row px*cout + co, column ((ky*4 + s)*cin + ci) = w[co][ci][ky][s - px] (zero where s - px is not
+ * in 0..2), s = input column shift + 1 relative to the even pixel.  epi: AFFINE, scale / shift of length 2*cout (the
+ * layer's vectors twice), no residual.  x: (n, h, w, cin) with w even, cin % 64 == 0; y: (n, h, w, cout) view.       */
+int uavdet_conv3x3_pair_fwd(const uavdet_act* x, const void* w_pair, int cout, const uavdet_act* y,
+                            const uavdet_epilogue* epi, void* stream);
+
 /* Data gradient through the fused space-to-depth(2) gather of uavdet_conv_fwd(s2d=1)
  * (autograd of DySOEM_SimFPN.py:71-91): dy (n, h/2, w/2, cout) -> dx (n, h, w, c) where the conv's
  * logical input had 4*c channels, block q = 2*(row parity) + (column parity).  w_packed_t: bf16

@@ -54,6 +54,7 @@ SIGNATURES = {
     "uavdet_yolo_head_loss": (_i, [_P, _P, _P, _i, _i, _i, _i, C.POINTER(_f), _i, _f, _f, _f, _f, _P, _P, _P, _P, _P, _P]),
     "uavdet_conv_fwd": (_i, [_AP, _P, _i, _i, _i, _i, _i, _i, _AP, _EP, _P]),
     "uavdet_conv_dgrad": (_i, [_AP, _P, _i, _i, _i, _i, _i, _AP, _EP, _P]),
+    "uavdet_conv3x3_pair_fwd": (_i, [_AP, _P, _i, _AP, _EP, _P]),
     "uavdet_conv_dgrad_s2d": (_i, [_AP, _P, _i, _i, _i, _i, _AP, _EP, _P]),
     "uavdet_pack_dgrad_s2_fused": (_i, [_P, _i, _i, _P, _P]),
     "uavdet_conv_dgrad_s2_fused": (_i, [_AP, _P, _i, _AP, _EP, _P]),

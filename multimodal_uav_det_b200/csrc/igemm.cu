@@ -1638,6 +1638,52 @@ extern "C" int uavdet_conv_dgrad_s2_fused(const uavdet_act* dy, const void* w_fu
   return launch_igemm(dy, 0, w_fused, 4 * cin, 4 * cout, 1, P, (cudaStream_t)stream);
 }
 
+// 3x3 stride-1 pad-1 convolution with few output channels, two adjacent output pixels per GEMM row: N = 2 * cout columns
+// [column parity][cout] over K = 3 x 4 input-column shifts x cin (the tensor core needs as long for an N = 64 instruction
+// as for N = 128, so a 64-channel layer runs at half rate the plain way; here it issues 12 taps per pixel PAIR instead of
+// 2 x 9).  The input is read as pixel pairs ([2 pixels][ld] rows of a 5-D map, like the stride-2 parity view but in the
+// column direction only): shift dx in {-1, 0, 1, 2} of pair j is pixel 2j + dx = pair j + floor(dx / 2), channel
+// offset (dx & 1) * ld; TMA zero-fills the pairs outside the image (the padding).  The output map puts the column
+// parity into its plane dimension (stride ld), so channel slices of a concat buffer work.
+extern "C" int uavdet_conv3x3_pair_fwd(const uavdet_act* x, const void* w_pair, int cout, const uavdet_act* y,
+                                       const uavdet_epilogue* epi, void* stream) {
+  UAVDET_CHECK_ARG(x && x->ptr && w_pair && y && y->ptr, "conv3x3_pair_fwd: null input");
+  UAVDET_CHECK_ARG(x->ld % 8 == 0 && ((uintptr_t)x->ptr & 15) == 0, "conv3x3_pair_fwd: input must be 16-byte aligned");
+  UAVDET_CHECK_ARG(x->c % 64 == 0 && cout % 64 == 0 && 2 * cout <= 256 && x->w % 2 == 0,
+                   "conv3x3_pair_fwd: needs cin %% 64 == 0, cout in {64, 128}, even width (cin=%d cout=%d w=%d)", x->c, cout, x->w);
+  UAVDET_CHECK_ARG(y->n == x->n && y->h == x->h && y->w == x->w && y->c == cout, "conv3x3_pair_fwd: output view mismatch");
+  const int C = x->c;
+  IgemmParams P{};
+  P.n_img = x->n;
+  P.ho = x->h;
+  P.wo = x->w / 2;
+  P.cout = 2 * cout;
+  P.block_k = 64;
+  P.block_n = pick_block_n(2 * cout);
+  P.kc_per_tap = C / 64;
+  int nt = 0;
+  for (int dy = -1; dy <= 1; ++dy)
+    for (int dx = -1; dx <= 2; ++dx)
+      P.taps[nt++] = ConvTap{(dx & 1) ? x->ld : 0, dx < 0 ? -1 : dx / 2, 0, dy, ((dy + 1) * 4 + (dx + 1)) * C};
+  P.num_taps = nt;
+  uavdet_act yv = *y;
+  yv.w = P.wo;
+  int rc = fill_epilogue(P, epi, &yv, 2 * cout);
+  if (rc) return rc;
+  UAVDET_CHECK_ARG(P.epi == UAVDET_EPI_AFFINE && !P.res && P.shift_sn == 0 && !P.sample_affine,
+                   "conv3x3_pair_fwd: AFFINE epilogue with shared [2*cout] scale / shift vectors, no residual");
+  const long long ld = y->ld;
+  P.out = (__nv_bfloat16*)y->ptr;
+  P.out_sw = 2 * ld; P.out_sh = (long long)y->w * ld; P.out_sn = (long long)y->h * y->w * ld;
+  P.out_cspan = cout; P.out_sp = ld;
+  choose_tile(P.ho, P.wo, false, &P.tile_w, &P.tile_h, &P.epi_mode);
+  uavdet_act xp = *x;                 // the pair view: rows of [2 pixels][ld], the second pixel's channels at offset ld
+  xp.w = x->w / 2;
+  xp.c = x->ld + C;
+  xp.ld = 2 * x->ld;
+  return launch_igemm(&xp, 0, w_pair, 2 * cout, 12 * C, 1, P, (cudaStream_t)stream);
+}
+
 extern "C" int uavdet_conv_dgrad_s2d(const uavdet_act* dy, const void* w_packed_t, int w_batch, int c, int k, int pad,
                                      const uavdet_act* dx, const uavdet_epilogue* epi, void* stream) {
   UAVDET_CHECK_ARG(dy && dy->ptr && w_packed_t && dx && dx->ptr, "conv_dgrad_s2d: null input");

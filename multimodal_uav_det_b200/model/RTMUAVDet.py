@@ -28,6 +28,7 @@ from ._base import LightningModule, to_nchw, to_nhwc
 
 
 _NO_GN_FOLD = bool(os.environ.get("UAVDET_RTM_NO_GN_FOLD"))     # A/B switch: GroupNorm as two streaming passes
+_NO_PAIR_CONV = bool(os.environ.get("UAVDET_RTM_NO_PAIR_CONV"))  # A/B switch: the 256 -> 64 neck conv as a plain N = 64 GEMM
 
 
 class ConvModule(_base.ConvModule):
@@ -275,6 +276,7 @@ class RTMUAVDet(LightningModule):
         self._exec = Executor()
         self.stem_on_tensor_cores = True      # False: the direct CUDA-core 5x5 kernel (fp32 input, no bf16 rounding of x)
         self._stem_w3 = None
+        self._up_pair = None
 
     def _stem_s2d_weight(self, w: torch.Tensor) -> torch.Tensor:
         from ..engine import param_epoch
@@ -318,7 +320,17 @@ class RTMUAVDet(LightningModule):
         cat2 = ops.empty_act(n, s1 // 2, s1 // 2, 384, x.device)
         x2 = csp2.forward_nhwc(x1, ex, out=cat2[..., :256])
         up = ops.bilinear2x_fwd(x2)
-        ex.conv_forward(ConvUnit(neck.upsample[1], None, "none"), up, False, None, out=cat1[..., 128:])
+        upc = neck.upsample[1]
+        if _NO_PAIR_CONV or upc.out_channels % 64 or upc.out_channels > 128 or up.shape[2] % 2 or upc.in_channels % 64:
+            ex.conv_forward(ConvUnit(upc, None, "none"), up, False, None, out=cat1[..., 128:])
+        else:
+            # 256 -> 64 at 160x160: two output pixels per GEMM row (N = 128; an N = 64 GEMM runs the tensor core at half rate)
+            from ..engine import param_epoch
+            ver = (upc.weight._version, upc.weight.data_ptr(), param_epoch())
+            if self._up_pair is None or self._up_pair[0] != ver:
+                self._up_pair = (ver, ops.pack_weight_pair(upc.weight))
+            ops.conv3x3_pair_fwd(up, self._up_pair[1], upc.out_channels, shift=None if upc.bias is None else upc.bias.detach(),
+                                 out=cat1[..., 128:])
         e1 = neck.encoder_x1.forward_nhwc(cat1, ex)
         ex.conv_forward(ConvUnit(neck.downsample, None, "none"), e1, False, None, out=cat2[..., 256:])
         e2 = neck.encoder_x2.forward_nhwc(cat2, ex)

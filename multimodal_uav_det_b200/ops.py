@@ -338,6 +338,35 @@ def conv_fwd(x: torch.Tensor, w_packed: torch.Tensor, cout: int, k: int, stride:
     return out
 
 
+def pack_weight_pair(w: torch.Tensor) -> torch.Tensor:
+    """(cout, cin, 3, 3) fp32 -> bf16 [2*cout][3*4*cin] of conv3x3_pair_fwd: row px*cout + co holds the filter shifted by
+    px input columns (zero blocks where the shifted filter has no tap)."""
+    cout, cin, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    wn = w.detach().permute(0, 2, 3, 1)                                   # (cout, ky, kx, cin)
+    wp = torch.zeros((2, cout, 3, 4, cin), dtype=torch.float32, device=w.device)
+    wp[0, :, :, 0:3] = wn
+    wp[1, :, :, 1:4] = wn
+    return wp.reshape(2 * cout, 12 * cin).to(torch.bfloat16).contiguous()
+
+
+def conv3x3_pair_fwd(x: torch.Tensor, w_pair: torch.Tensor, cout: int, *, act=None, scale=None, shift=None,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """3x3 stride-1 pad-1 conv with cout in {64, 128}: two output pixels per GEMM row (see the header).  scale / shift are
+    the layer's [cout] vectors (repeated for the two pixels here)."""
+    _require_cuda(x, w_pair)
+    n, h, w, cin = x.shape
+    if out is None:
+        out = empty_act(n, h, w, cout, x.device)
+    xv, yv = act_view(x), act_view(out)
+    scale2 = None if scale is None else _f32(scale).repeat(2).contiguous()      # alive until the launch below
+    shift2 = None if shift is None else _f32(shift).repeat(2).contiguous()
+    e = _epilogue(EPI_AFFINE, act, scale2, shift2, None)
+    check(_lib.load().uavdet_conv3x3_pair_fwd(C.byref(xv), _ptr(w_pair), cout, C.byref(yv), C.byref(e), _stream()),
+          "conv3x3_pair_fwd")
+    return out
+
+
 def conv_head(x: torch.Tensor, w_packed16: torch.Tensor, bias15: torch.Tensor, anchors: int
               ) -> Tuple[torch.Tensor, torch.Tensor]:
     """Fused objectness+bbox 1x1 head conv (model/_base.py:80-120): one N=16 GEMM writes both

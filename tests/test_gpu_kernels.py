@@ -867,6 +867,25 @@ def test_groupnorm_folded_into_the_1x1_conv_behind_it(lib):
         assert_close_bf16(to_nchw(y), ref, f"groupnorm fold ({act})", rel=8e-3)
 
 
+@pytest.mark.parametrize("cin,cout,h,w", [(64, 64, 10, 12), (256, 64, 40, 48), (128, 128, 9, 34)])
+def test_conv3x3_pair_matches_conv2d(lib, cin, cout, h, w):
+    """3x3 stride-1 pad-1 conv computed two output pixels per GEMM row (N = 2*cout), bias, channel-slice output
+    (RTMUAVDet.py:194)."""
+    ops = _ops(lib)
+    g = torch.Generator().manual_seed(321 + cin + h)
+    n = 3
+    x = bf16_round(torch.randn(n, cin, h, w, generator=g))
+    wt = bf16_round(torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5))
+    bias = torch.randn(cout, generator=g) * 0.3
+    ref = F.conv2d(x, wt, bias, 1, 1)
+    buf = torch.zeros(n, h, w, cout + 64, dtype=torch.bfloat16, device=DEV)
+    ops.conv3x3_pair_fwd(nhwc(x), ops.pack_weight_pair(wt.to(DEV)), cout, shift=bias.to(DEV), out=buf[..., 64:])
+    assert_close_bf16(to_nchw(buf[..., 64:]), ref, f"conv3x3 pair {cin}->{cout}")
+    assert torch.all(buf[..., :64] == 0)
+    plain = ops.conv_fwd(nhwc(x), ops.pack_weight(wt.to(DEV)), cout, 3, 1, 1, shift=bias.to(DEV))
+    assert_close_bf16(to_nchw(buf[..., 64:]), to_nchw(plain).float(), "pair vs plain igemm", rel=2e-3)
+
+
 def test_stem_zero_padded_odd_output(lib):
     """RTM stem 5x5 s2 p1: 39 -> 18.. odd outputs are stored with a zero last row/column."""
     ops = _ops(lib)
