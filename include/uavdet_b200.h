@@ -186,10 +186,13 @@ int uavdet_conv_dgrad_s2_fused(const uavdet_act* dy, const void* w_fused, int ci
                                const uavdet_epilogue* epi, void* stream);
 
 /* 3x3 stride-1 pad-1 convolution with cout in {64, 128}, two adjacent output pixels per GEMM row (nn.Conv2d at
- * RTMUAVDet.py:194, 256 -> 64 at 160x160: an N = 64 GEMM runs the tensor core at half rate).  w_pair: bf16
- * [2*cout][3*4*cin], row px*cout + co, column ((ky*4 + s)*cin + ci) = w[co][ci][ky][s - px] (zero where s - px is not
- * in 0..2), s = input column shift + 1 relative to the even pixel.  epi: AFFINE, scale / shift of length 2*cout (the
- * layer's vectors twice), no residual.  x: (n, h, w, cin) with w even, cin % 64 == 0; y: (n, h, w, cout) view.       */
+ * RTMUAVDet.py:194, 256 -> 64 at 160x160, and the 32 -> 64 layer of the first residual block, BaselineModel.py:63-75:
+ * an N = 64 GEMM runs the tensor core at half rate, 64-byte K rows at a quarter).  w_pair: bf16 [2*cout][3*S*cin], row
+ * px*cout + co, column ((ky*S + s)*cin + ci) = w[co][ci][ky][s + first + 1 - px] (zero where that is not in 0..2) for
+ * input-column shift s + first relative to the even pixel: S = 4, first = -1 for cin % 64 == 0; S = 6, first = -2 for a
+ * dense 32-channel input (k-blocks are whole pixel pairs).  epi: AFFINE with scale / shift of length 2*cout (the layer's
+ * vectors twice), or STATS (sum / sumsq of length cout: both pixels of a pair add to the same channel); no residual.
+ * x: (n, h, w, cin) with w even; y: (n, h, w, cout) view.                                                             */
 int uavdet_conv3x3_pair_fwd(const uavdet_act* x, const void* w_pair, int cout, const uavdet_act* y,
                             const uavdet_epilogue* epi, void* stream);
 

@@ -663,8 +663,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             }
             const int col = n0 + sl * P.slab_w + 2 * pair;
             if (owner && col < P.cout) {
-              atomicAdd(P.sum + col, s0); atomicAdd(P.sum + col + 1, s1);
-              atomicAdd(P.sumsq + col, q0); atomicAdd(P.sumsq + col + 1, q1);
+              // pixel-pair GEMMs: the columns of both pixels of a pair belong to the same channels
+              const int ch = P.stat_mod ? col % P.stat_mod : col;
+              atomicAdd(P.sum + ch, s0); atomicAdd(P.sum + ch + 1, s1);
+              atomicAdd(P.sumsq + ch, q0); atomicAdd(P.sumsq + ch + 1, q1);
             }
           }
           st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f;
@@ -893,8 +895,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             }
             const int col = cs + 2 * pr;
             if (lane < ppw && col < P.cout) {
-              atomicAdd(P.sum + col, s0); atomicAdd(P.sum + col + 1, s1);
-              atomicAdd(P.sumsq + col, q0); atomicAdd(P.sumsq + col + 1, q1);
+              const int ch = P.stat_mod ? col % P.stat_mod : col;
+              atomicAdd(P.sum + ch, s0); atomicAdd(P.sum + ch + 1, s1);
+              atomicAdd(P.sumsq + ch, q0); atomicAdd(P.sumsq + ch + 1, q1);
             }
           }
         }
@@ -1649,8 +1652,11 @@ extern "C" int uavdet_conv3x3_pair_fwd(const uavdet_act* x, const void* w_pair, 
                                        const uavdet_epilogue* epi, void* stream) {
   UAVDET_CHECK_ARG(x && x->ptr && w_pair && y && y->ptr, "conv3x3_pair_fwd: null input");
   UAVDET_CHECK_ARG(x->ld % 8 == 0 && ((uintptr_t)x->ptr & 15) == 0, "conv3x3_pair_fwd: input must be 16-byte aligned");
-  UAVDET_CHECK_ARG(x->c % 64 == 0 && cout % 64 == 0 && 2 * cout <= 256 && x->w % 2 == 0,
-                   "conv3x3_pair_fwd: needs cin %% 64 == 0, cout in {64, 128}, even width (cin=%d cout=%d w=%d)", x->c, cout, x->w);
+  const bool dense_out = y->ld == cout;       // the two pixels of an output pair are one contiguous row of 2 * cout channels
+  UAVDET_CHECK_ARG((x->c % 64 == 0 || (x->c == 32 && x->ld == 32)) && (cout % 64 == 0 || (cout == 32 && dense_out)) &&
+                       2 * cout <= 256 && x->w % 2 == 0,
+                   "conv3x3_pair_fwd: needs cin %% 64 == 0 (or a dense 32-channel input), cout in {64, 128} (or 32 into a "
+                   "dense tensor), even width (cin=%d ld=%d cout=%d w=%d)", x->c, x->ld, cout, x->w);
   UAVDET_CHECK_ARG(y->n == x->n && y->h == x->h && y->w == x->w && y->c == cout, "conv3x3_pair_fwd: output view mismatch");
   const int C = x->c;
   IgemmParams P{};
@@ -1660,28 +1666,38 @@ extern "C" int uavdet_conv3x3_pair_fwd(const uavdet_act* x, const void* w_pair, 
   P.cout = 2 * cout;
   P.block_k = 64;
   P.block_n = pick_block_n(2 * cout);
-  P.kc_per_tap = C / 64;
   int nt = 0;
-  for (int dy = -1; dy <= 1; ++dy)
-    for (int dx = -1; dx <= 2; ++dx)
-      P.taps[nt++] = ConvTap{(dx & 1) ? x->ld : 0, dx < 0 ? -1 : dx / 2, 0, dy, ((dy + 1) * 4 + (dx + 1)) * C};
+  if (C == 32) {
+    // a dense 32-channel input: a pixel pair is ONE 128-byte row, so a k-block is a whole pair (K = 64, SWIZZLE_128B; 64-byte
+    // rows cost the tensor core twice the cycles): pairs j - 1, j, j + 1 = column shifts -2 .. 3, the outer two with zero weights
+    P.kc_per_tap = 1;
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int b = -1; b <= 1; ++b) P.taps[nt++] = ConvTap{0, b, 0, dy, ((dy + 1) * 3 + (b + 1)) * 64};
+  } else {
+    P.kc_per_tap = C / 64;
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 2; ++dx)
+        P.taps[nt++] = ConvTap{(dx & 1) ? x->ld : 0, dx < 0 ? -1 : dx / 2, 0, dy, ((dy + 1) * 4 + (dx + 1)) * C};
+  }
   P.num_taps = nt;
   uavdet_act yv = *y;
   yv.w = P.wo;
   int rc = fill_epilogue(P, epi, &yv, 2 * cout);
   if (rc) return rc;
-  UAVDET_CHECK_ARG(P.epi == UAVDET_EPI_AFFINE && !P.res && P.shift_sn == 0 && !P.sample_affine,
-                   "conv3x3_pair_fwd: AFFINE epilogue with shared [2*cout] scale / shift vectors, no residual");
+  UAVDET_CHECK_ARG((P.epi == UAVDET_EPI_AFFINE || (P.epi == UAVDET_EPI_STATS && !P.shift)) && !P.res && P.shift_sn == 0 &&
+                       !P.sample_affine,
+                   "conv3x3_pair_fwd: AFFINE epilogue with shared [2*cout] scale / shift vectors, or STATS; no residual");
   const long long ld = y->ld;
   P.out = (__nv_bfloat16*)y->ptr;
   P.out_sw = 2 * ld; P.out_sh = (long long)y->w * ld; P.out_sn = (long long)y->h * y->w * ld;
-  P.out_cspan = cout; P.out_sp = ld;
-  choose_tile(P.ho, P.wo, false, &P.tile_w, &P.tile_h, &P.epi_mode);
+  if (!dense_out) { P.out_cspan = cout; P.out_sp = ld; }      // a channel slice: the column parity is a plane of the output map
+  P.stat_mod = cout;                                          // STATS: both pixels of a pair add to the same channel
+  choose_tile(P.ho, P.wo, dense_out, &P.tile_w, &P.tile_h, &P.epi_mode);
   uavdet_act xp = *x;                 // the pair view: rows of [2 pixels][ld], the second pixel's channels at offset ld
   xp.w = x->w / 2;
   xp.c = x->ld + C;
   xp.ld = 2 * x->ld;
-  return launch_igemm(&xp, 0, w_pair, 2 * cout, 12 * C, 1, P, (cudaStream_t)stream);
+  return launch_igemm(&xp, 0, w_pair, 2 * cout, C == 32 ? 9 * 64 : 12 * C, 1, P, (cudaStream_t)stream);
 }
 
 extern "C" int uavdet_conv_dgrad_s2d(const uavdet_act* dy, const void* w_packed_t, int w_batch, int c, int k, int pad,

@@ -82,6 +82,7 @@ struct IgemmParams {
   // n % out_cspan of the pixel-pair row).  0 = ordinary output.
   int out_cspan;
   long long out_sp, res_sp;     // element stride between the row-parity planes
+  int stat_mod;                 // > 0: STATS column n adds to channel n % stat_mod (pixel-pair GEMMs: N = [pixel][channel])
   float* sum;
   float* sumsq;
   float* head_obj;

@@ -22,6 +22,7 @@ from . import ops
 from ._lib import EPI_AFFINE, EPI_STATS
 
 _NO_FUSE_S2 = bool(os.environ.get("UAVDET_NO_FUSE_S2"))      # A/B switch: stride-2 data gradients plane by plane
+_NO_PAIR = bool(os.environ.get("UAVDET_NO_PAIR_CONV"))        # A/B switch: thin 3x3 layers as plain N = 64 GEMMs
 _STEM_IM2COL = bool(os.environ.get("UAVDET_STEM_IM2COL"))    # A/B switch: keep the im2col patch tensor of the 3x3 stems
 
 
@@ -213,6 +214,7 @@ class Executor:
         self._const: Dict[Tuple[str, int, str], torch.Tensor] = {}
         self._bn_fold: Dict[int, Tuple[tuple, torch.Tensor, torch.Tensor]] = {}
         self._s2f: Dict[tuple, torch.Tensor] = {}    # plane-fused stride-2 data-gradient weights (rebuilt from the pack every step)
+        self._pair: Dict[tuple, tuple] = {}          # pixel-pair weight matrices of thin 3x3 layers: (id(w), transposed) -> (version, buffer)
         self.grad_ready_hook: Optional[Callable[[torch.Tensor], None]] = None
 
     def producer_streams(self) -> list:
@@ -301,6 +303,9 @@ class Executor:
                 raw = ops.stem_fwd(x, w.detach(), k, stride, pad, epi=EPI_STATS, sum_=sums[0], sumsq=sums[1])
             elif stem_mma:
                 raw = ops.stem_mma_fwd(x, wp, k, stride, pad, epi=EPI_STATS, sum_=sums[0], sumsq=sums[1])
+            elif self._pair_ok(u, x, s2d):
+                # thin 3x3 layer (32 -> 64 at 320x320): two output pixels per GEMM row, whole pixel pairs as K = 64 k-blocks
+                raw = ops.conv3x3_pair_fwd(x, self._pair_weight(w, wp), c, epi=EPI_STATS, sum_=sums[0], sumsq=sums[1])
             else:
                 raw = ops.conv_fwd(x, wp, c, k, stride, pad, s2d=s2d, epi=EPI_STATS, sum_=sums[0], sumsq=sums[1])
             n, ho, wo, _ = raw.shape
@@ -346,6 +351,26 @@ class Executor:
         if tape is not None:
             tape.append(ConvRecord(u, x, None, scale, None, None, None, res is not None, in_hw))
         return y
+
+    @staticmethod
+    def _pair_ok(u: ConvUnit, x: torch.Tensor, s2d: bool) -> bool:
+        """3x3 stride-1 pad-1 layers with 64 output channels run as pixel-pair GEMMs (ops.conv3x3_pair_fwd)."""
+        if _NO_PAIR or u.stem or s2d or u.k != 3 or u.stride != 1 or u.pad != 1 or u.cout != 64 or x.dim() != 4:
+            return False
+        cin = x.shape[3]
+        return x.shape[2] % 2 == 0 and (cin % 64 == 0 or (cin == 32 and x.stride(2) == 32))
+
+    def _pair_weight(self, w: torch.Tensor, packed: torch.Tensor, transposed: bool = False) -> torch.Tensor:
+        """Pair weight matrix of `w` (of its data gradient: transposed), rebuilt from its current bf16 pack when the
+        weight changed (two strided copies into a persistent buffer whose zero blocks never change)."""
+        ver = self.packs._ver(w)
+        hit = self._pair.get((id(w), transposed))
+        if hit is not None and hit[0] == ver and hit[1].device == w.device:
+            return hit[1]
+        buf = ops.pack_weight_pair(packed, out=hit[1] if hit is not None and hit[1].device == w.device else None,
+                                   flip=transposed)
+        self._pair[(id(w), transposed)] = (ver, buf)
+        return buf
 
     def bn_fold(self, bn: nn.BatchNorm2d, conv_bias: Optional[torch.Tensor] = None):
         """Eval-mode BatchNorm folded to (scale, shift) = (gamma*rsqrt(var+eps), beta - mean*scale [+ bias*scale]),
@@ -414,7 +439,13 @@ class Executor:
             fused = (not _NO_FUSE_S2 and u.stride == 2 and u.k == 3 and u.pad == 1 and cin in (32, 64)
                      and h_in % 2 == 0 and w_in % 2 == 0 and (out is None or out.stride(2) == cin)
                      and (res is None or res.stride(2) == cin))
-            if fused:
+            pair_dgrad = (not _NO_PAIR and not fused and u.k == 3 and u.stride == 1 and u.pad == 1 and cin in (32, 64)
+                          and res is None and out is None and w_in % 2 == 0
+                          and (u.cout % 64 == 0 or (u.cout == 32 and d_raw.stride(2) == 32)))
+            if pair_dgrad:
+                # thin data gradient (N = cin <= 64): two pixels per GEMM row, the mirrored transposed filter as a pair matrix
+                dx = ops.conv3x3_pair_fwd(d_raw, self._pair_weight(w, wt, transposed=True), cin)
+            elif fused:
                 # all four output-parity planes as one N = 4*cin GEMM over a re-laid-out (zero-padded) weight matrix
                 key = (id(w), "s2f")
                 buf = self._s2f.get(key)

@@ -338,22 +338,40 @@ def conv_fwd(x: torch.Tensor, w_packed: torch.Tensor, cout: int, k: int, stride:
     return out
 
 
-def pack_weight_pair(w: torch.Tensor) -> torch.Tensor:
-    """(cout, cin, 3, 3) fp32 -> bf16 [2*cout][3*4*cin] of conv3x3_pair_fwd: row px*cout + co holds the filter shifted by
-    px input columns (zero blocks where the shifted filter has no tap)."""
-    cout, cin, kh, kw = w.shape
-    assert kh == 3 and kw == 3
-    wn = w.detach().permute(0, 2, 3, 1)                                   # (cout, ky, kx, cin)
-    wp = torch.zeros((2, cout, 3, 4, cin), dtype=torch.float32, device=w.device)
-    wp[0, :, :, 0:3] = wn
-    wp[1, :, :, 1:4] = wn
-    return wp.reshape(2 * cout, 12 * cin).to(torch.bfloat16).contiguous()
+def pair_weight_shifts(cin: int) -> Tuple[int, int]:
+    """(S, first): a row of the pair weight matrix covers the S input-column shifts first .. first + S - 1."""
+    return (6, -2) if cin == 32 else (4, -1)
+
+
+def pack_weight_pair(w: torch.Tensor, out: Optional[torch.Tensor] = None, flip: bool = False) -> torch.Tensor:
+    """3x3 conv weight -> bf16 [2*cout][3*S*cin] of conv3x3_pair_fwd: row px*cout + co holds the filter shifted by px input
+    columns, zero blocks where the shifted filter has no tap.  `w`: (cout, cin, 3, 3) fp32, or the bf16 pack
+    [cout][3*3*cin] of pack_weight.  S = 4 column shifts (-1..2) for cin % 64 == 0, 6 (-2..3: whole pixel pairs) for a
+    32-channel input.  `out`: a buffer from an earlier call (its zero blocks are kept, only the filter blocks rewritten).
+    flip=True mirrors the filter: with the TRANSPOSED pack [cin][3*3*cout] of pack_weight this gives the weights of the data
+    gradient, which is the same convolution of dy with the mirrored, transposed filter."""
+    if w.dim() == 4:
+        cout, cin = w.shape[0], w.shape[1]
+        wn = w.detach().permute(0, 2, 3, 1)                               # (cout, ky, kx, cin)
+    else:
+        cout, cin = w.shape[0], w.shape[1] // 9
+        wn = w.view(cout, 3, 3, cin)
+    if flip:
+        wn = wn.flip(1, 2)
+    shifts, first = pair_weight_shifts(cin)
+    if out is None:
+        out = torch.zeros((2 * cout, 3 * shifts * cin), dtype=torch.bfloat16, device=w.device)
+    wp = out.view(2, cout, 3, shifts, cin)
+    a = -1 - first                                                        # index of column shift -1
+    wp[0, :, :, a:a + 3].copy_(wn)
+    wp[1, :, :, a + 1:a + 4].copy_(wn)
+    return out
 
 
 def conv3x3_pair_fwd(x: torch.Tensor, w_pair: torch.Tensor, cout: int, *, act=None, scale=None, shift=None,
-                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     out: Optional[torch.Tensor] = None, epi: int = EPI_AFFINE, sum_=None, sumsq=None) -> torch.Tensor:
     """3x3 stride-1 pad-1 conv with cout in {64, 128}: two output pixels per GEMM row (see the header).  scale / shift are
-    the layer's [cout] vectors (repeated for the two pixels here)."""
+    the layer's [cout] vectors (repeated for the two pixels here); epi=EPI_STATS adds the per-channel sum / sum of squares."""
     _require_cuda(x, w_pair)
     n, h, w, cin = x.shape
     if out is None:
@@ -361,7 +379,7 @@ def conv3x3_pair_fwd(x: torch.Tensor, w_pair: torch.Tensor, cout: int, *, act=No
     xv, yv = act_view(x), act_view(out)
     scale2 = None if scale is None else _f32(scale).repeat(2).contiguous()      # alive until the launch below
     shift2 = None if shift is None else _f32(shift).repeat(2).contiguous()
-    e = _epilogue(EPI_AFFINE, act, scale2, shift2, None)
+    e = _epilogue(epi, act, scale2, shift2, None, _f32(sum_), _f32(sumsq))
     check(_lib.load().uavdet_conv3x3_pair_fwd(C.byref(xv), _ptr(w_pair), cout, C.byref(yv), C.byref(e), _stream()),
           "conv3x3_pair_fwd")
     return out

@@ -886,6 +886,49 @@ def test_conv3x3_pair_matches_conv2d(lib, cin, cout, h, w):
     assert_close_bf16(to_nchw(buf[..., 64:]), to_nchw(plain).float(), "pair vs plain igemm", rel=2e-3)
 
 
+@pytest.mark.parametrize("cin,h,w", [(32, 20, 24), (64, 11, 16)])
+def test_conv3x3_pair_stats_epilogue(lib, cin, h, w):
+    """The training forward of the thin 32 -> 64 layer (BaselineModel.py:63-75, first residual block) as a pixel-pair GEMM:
+    raw output and the per-channel batch statistics (both pixels of a pair add to the same channel)."""
+    from multimodal_uav_det_b200._lib import EPI_STATS
+    ops = _ops(lib)
+    g = torch.Generator().manual_seed(77 + cin)
+    n, cout = 3, 64
+    x = bf16_round(torch.randn(n, cin, h, w, generator=g))
+    wt = bf16_round(torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5))
+    ref = F.conv2d(x, wt, None, 1, 1)
+    s1 = torch.zeros(cout, device=DEV)
+    s2 = torch.zeros(cout, device=DEV)
+    packed = ops.pack_weight(wt.to(DEV))
+    wp = ops.pack_weight_pair(packed)
+    assert torch.equal(wp, ops.pack_weight_pair(wt.to(DEV)))            # from the bf16 pack == from the fp32 weight
+    assert torch.equal(ops.pack_weight_pair(packed, out=wp.clone()), wp)
+    raw = ops.conv3x3_pair_fwd(nhwc(x), wp, cout, epi=EPI_STATS, sum_=s1, sumsq=s2)
+    got = to_nchw(raw)
+    assert_close_bf16(got, ref, f"pair stats conv cin={cin}")
+    torch.testing.assert_close(s1.cpu(), got.sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-2)
+    torch.testing.assert_close(s2.cpu(), (got * got).sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("cin,cout,h,w", [(32, 64, 12, 20), (64, 128, 9, 16), (32, 32, 8, 8)])
+def test_conv3x3_pair_data_gradient_matches_autograd(lib, cin, cout, h, w):
+    """Data gradient of a thin 3x3 stride-1 layer as the pixel-pair convolution of dy with the mirrored, transposed filter
+    (autograd of BaselineModel.py:63-75 residual blocks), against torch autograd and the plain igemm data gradient."""
+    ops = _ops(lib)
+    g = torch.Generator().manual_seed(99 + cin + cout)
+    n = 2
+    wt = bf16_round(torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5))
+    dy = bf16_round(torch.randn(n, cout, h, w, generator=g))
+    x = torch.zeros(n, cin, h, w, requires_grad=True)
+    F.conv2d(x, wt, None, 1, 1).backward(dy)
+    w_t = ops.pack_weight(wt.to(DEV), transposed=True)
+    got = ops.conv3x3_pair_fwd(nhwc(dy), ops.pack_weight_pair(w_t, flip=True), cin)
+    assert got.shape == (n, h, w, cin)
+    assert_close_bf16(to_nchw(got), x.grad, f"pair dgrad {cout}->{cin}")
+    plain = ops.conv_dgrad(nhwc(dy), w_t, cin, 3, 1, 1, (h, w))
+    assert_close_bf16(to_nchw(got), to_nchw(plain).float(), "pair vs plain dgrad", rel=2e-3)
+
+
 def test_stem_zero_padded_odd_output(lib):
     """RTM stem 5x5 s2 p1: 39 -> 18.. odd outputs are stored with a zero last row/column."""
     ops = _ops(lib)
