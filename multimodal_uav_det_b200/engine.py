@@ -443,7 +443,8 @@ class Executor:
                      and (res is None or res.stride(2) == cin))
             pair_dgrad = (not _NO_PAIR and not fused and u.k == 3 and u.stride == 1 and u.pad == 1 and cin in (32, 64)
                           and res is None and out is None and w_in % 2 == 0
-                          and ((u.cout % 64 == 0 and u.cout != 64) or (u.cout == 32 and d_raw.stride(2) == 32)))
+                          and (u.cout % 64 == 0 or (u.cout == 32 and d_raw.stride(2) == 32))
+                          and not (cin == 64 and u.cout == 64))        # 64 -> 64: the halo-tile mode of the plain kernel
             if pair_dgrad:
                 # thin data gradient (N = cin <= 64): two pixels per GEMM row, the mirrored transposed filter as a pair matrix
                 dx = ops.conv3x3_pair_fwd(d_raw, self._pair_weight(w, wt, transposed=True), cin)
