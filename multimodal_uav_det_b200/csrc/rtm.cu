@@ -146,9 +146,14 @@ __device__ __forceinline__ void dwdynconv_body(const __nv_bfloat16* __restrict__
           const int slot = ((u - r) % KS + KS) % KS;            // compile-time after unrolling
 #pragma unroll
           for (int kx = 0; kx < KS; ++kx) {
-            const float wt = kw[r * KS + kx];
+            // two channels per instruction (fma.rn.f32x2: each half rounds like fmaf): the kernel is bound by instruction
+            // issue — KS * KS * 8 FMAs per pixel and input row against five 16-byte loads
+            const float2 w2 = make_float2(kw[r * KS + kx], kw[r * KS + kx]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[slot][j] = fmaf(wt, v[kx][j], acc[slot][j]);
+            for (int j = 0; j < 8; j += 2) {
+              const float2 a2 = __ffma2_rn(w2, make_float2(v[kx][j], v[kx][j + 1]), make_float2(acc[slot][j], acc[slot][j + 1]));
+              acc[slot][j] = a2.x; acc[slot][j + 1] = a2.y;
+            }
           }
         }
         const int done = li - (KS - 1);                           // local output row finished by this input row
@@ -207,7 +212,7 @@ dwdynconv_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int h, int w, in
 
 // + residual + per-sample statistics of the result (stats[2 * b], stats[2 * b + 1], caller-zeroed)
 template <int KS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, KS <= 5 ? 2 : 1)
 dwdynconv_res_stats_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int h, int w, int c,
                            const float* __restrict__ channel_w, const float* __restrict__ kernel_w, int xblocks, int rows,
                            __nv_bfloat16* __restrict__ y, int y_ld, const __nv_bfloat16* __restrict__ res, int r_ld,
