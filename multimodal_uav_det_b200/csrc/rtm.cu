@@ -120,34 +120,50 @@ __device__ __forceinline__ void dwdynconv_body(const __nv_bfloat16* __restrict__
   // (li - r) mod KS; output row y0 + li - (KS - 1) is complete after input row li.  The raw row li + 1 is requested
   // before row li is consumed, so its latency hides behind the KS*KS*8 FMAs of the current row.
   const int n_in = nrows + KS - 1;
-  auto fetch = [&](int li, uint4 (&raw)[KS]) {
-    const int iy = y0 - PAD + li;
-    const bool row_ok = li < n_in && iy >= 0 && iy < h;
+  // Addresses are running pointers (one 64-bit add per row and pointer; computing ((long long)iy * w + ix) * ld for every
+  // access was a third of the kernel's instructions, and the kernel is bound by instruction issue): `fp` walks the input
+  // rows at the centre column, `cp` / `yp` / `rp` the completed output rows.  Pointers outside the image are never
+  // dereferenced.
+  const long long in_stride = (long long)w * x_ld;
+  const __nv_bfloat16* fp = xb_ + ((long long)(y0 - PAD) * w + ox) * x_ld;
+  const __nv_bfloat16* cp = xb_ + ((long long)y0 * w + ox) * x_ld;
+  __nv_bfloat16* yp = yb_ + ((long long)y0 * w + ox) * y_ld;
+  const __nv_bfloat16* rp = kFold ? rb_ + ((long long)y0 * w + ox) * r_ld : nullptr;
+  bool col_ok[KS];
+  int col_off[KS];
 #pragma unroll
-    for (int kx = 0; kx < KS; ++kx) {
-      const int ix = ox + kx - PAD;
-      raw[kx] = (row_ok && ix >= 0 && ix < w) ? __ldg(reinterpret_cast<const uint4*>(xb_ + ((long long)iy * w + ix) * x_ld))
-                                             : make_uint4(0u, 0u, 0u, 0u);
-    }
+  for (int kx = 0; kx < KS; ++kx) {
+    const int ix = ox + kx - PAD;
+    col_ok[kx] = ix >= 0 && ix < w;
+    col_off[kx] = (kx - PAD) * x_ld;
+  }
+  int fy = y0 - PAD;                                     // image row `fp` points at
+  auto fetch = [&](uint4 (&raw)[KS]) {
+    const bool row_ok = fy >= 0 && fy < h && fy < y0 - PAD + n_in;
+#pragma unroll
+    for (int kx = 0; kx < KS; ++kx)
+      raw[kx] = (row_ok && col_ok[kx]) ? __ldg(reinterpret_cast<const uint4*>(fp + col_off[kx])) : make_uint4(0u, 0u, 0u, 0u);
+    fp += in_stride;
+    ++fy;
   };
-  uint4 cur[KS], nxt[KS];
-  fetch(0, cur);
-  for (int base = 0; base < n_in; base += KS) {
+  uint4 buf[2][KS];                                       // ping-pong: the loop is unrolled 2 * KS rows, no copies
+  fetch(buf[0]);
+  for (int base = 0; base < n_in; base += 2 * KS) {
 #pragma unroll
-    for (int u = 0; u < KS; ++u) {
-      const int li = base + u;
+    for (int u2 = 0; u2 < 2 * KS; ++u2) {
+      const int li = base + u2;
+      const int u = u2 % KS;
       if (li < n_in) {
-        fetch(li + 1, nxt);
+        fetch(buf[(u2 + 1) & 1]);
         float v[KS][8];
 #pragma unroll
-        for (int kx = 0; kx < KS; ++kx) unpack8r(cur[kx], v[kx]);
+        for (int kx = 0; kx < KS; ++kx) unpack8r(buf[u2 & 1][kx], v[kx]);
 #pragma unroll
         for (int r = 0; r < KS; ++r) {
           const int slot = ((u - r) % KS + KS) % KS;            // compile-time after unrolling
 #pragma unroll
           for (int kx = 0; kx < KS; ++kx) {
-            // two channels per instruction (fma.rn.f32x2: each half rounds like fmaf): the kernel is bound by instruction
-            // issue — KS * KS * 8 FMAs per pixel and input row against five 16-byte loads
+            // two channels per instruction (fma.rn.f32x2: each half rounds like fmaf)
             const float2 w2 = make_float2(kw[r * KS + kx], kw[r * KS + kx]);
 #pragma unroll
             for (int j = 0; j < 8; j += 2) {
@@ -156,32 +172,31 @@ __device__ __forceinline__ void dwdynconv_body(const __nv_bfloat16* __restrict__
             }
           }
         }
-        const int done = li - (KS - 1);                           // local output row finished by this input row
         const int dslot = (u + 1) % KS;
-        if (done >= 0) {
-          const int oy = y0 + done;
+        if (li >= KS - 1) {                                        // local output row li - (KS - 1) is complete
           float centre[8], o[8];
-          unpack8r(__ldg(reinterpret_cast<const uint4*>(xb_ + ((long long)oy * w + ox) * x_ld)), centre);
+          unpack8r(__ldg(reinterpret_cast<const uint4*>(cp)), centre);
+          cp += in_stride;
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = fmaf(cw[j], acc[dslot][j], centre[j]);
           if (kFold) {
             float r[8];
-            unpack8r(__ldcs(reinterpret_cast<const uint4*>(rb_ + ((long long)oy * w + ox) * r_ld)), r);
+            unpack8r(__ldcs(reinterpret_cast<const uint4*>(rp)), r);
+            rp += (long long)w * r_ld;
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] += r[j];
             const uint4 out = pack8r(o);
             unpack8r(out, o);
 #pragma unroll
             for (int j = 0; j < 8; ++j) { s1 += o[j]; s2 = fmaf(o[j], o[j], s2); }
-            *reinterpret_cast<uint4*>(yb_ + ((long long)oy * w + ox) * y_ld) = out;
+            *reinterpret_cast<uint4*>(yp) = out;
           } else {
-            *reinterpret_cast<uint4*>(yb_ + ((long long)oy * w + ox) * y_ld) = pack8r(o);
+            *reinterpret_cast<uint4*>(yp) = pack8r(o);
           }
+          yp += (long long)w * y_ld;
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[dslot][j] = 0.f;          // the slot now belongs to output row done + KS
-#pragma unroll
-        for (int kx = 0; kx < KS; ++kx) cur[kx] = nxt[kx];
       }
     }
   }
@@ -202,7 +217,7 @@ __device__ __forceinline__ void block_sum2_atomic(float s1, float s2, float* dst
 }
 
 template <int KS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, KS <= 3 ? 3 : (KS <= 5 ? 2 : 1))
 dwdynconv_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int h, int w, int c,
                  const float* __restrict__ channel_w, const float* __restrict__ kernel_w, int xblocks, int rows,
                  __nv_bfloat16* __restrict__ y, int y_ld) {
@@ -212,7 +227,7 @@ dwdynconv_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int h, int w, in
 
 // + residual + per-sample statistics of the result (stats[2 * b], stats[2 * b + 1], caller-zeroed)
 template <int KS>
-__global__ void __launch_bounds__(256, KS <= 5 ? 2 : 1)
+__global__ void __launch_bounds__(256, KS <= 3 ? 3 : (KS <= 5 ? 2 : 1))
 dwdynconv_res_stats_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int h, int w, int c,
                            const float* __restrict__ channel_w, const float* __restrict__ kernel_w, int xblocks, int rows,
                            __nv_bfloat16* __restrict__ y, int y_ld, const __nv_bfloat16* __restrict__ res, int r_ld,
