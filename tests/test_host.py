@@ -377,3 +377,92 @@ def test_reference_named_state_dict_loads_strict_into_a_trainer_wrapped_model():
     off = (w.data_ptr() - b.param.data_ptr()) // 4
     torch.testing.assert_close(b.param[off:off + w.numel()].view(w.shape[0], 3, 3, w.shape[1]).permute(0, 3, 1, 2),
                                ckpt["layers.1.conv.weight"])
+
+
+# ---- host-side algebra of the pixel-pair GEMM and the GroupNorm fold (pure torch, no GPU) -----------------------------
+@pytest.mark.parametrize("cin,cout,flip", [(32, 64, False), (64, 64, False), (128, 64, False), (64, 32, True)])
+def test_pair_weight_matrix_reproduces_the_3x3_convolution(cin, cout, flip):
+    """ops.pack_weight_pair builds the [2*cout][3*S*cin] matrix uavdet_conv3x3_pair_fwd multiplies with the shifted pixel
+    columns (include/uavdet_b200.h): emulate that GEMM on the CPU and compare with F.conv2d (flip=True: with the data
+    gradient of the transposed filter, RTMUAVDet.py:194 / BaselineModel.py:63-75)."""
+    import torch.nn.functional as F
+    from multimodal_uav_det_b200 import ops
+    g = torch.Generator().manual_seed(5 + cin + cout)
+    n, h, w = 2, 5, 8
+    if not flip:
+        wt = torch.randn(cout, cin, 3, 3, generator=g).bfloat16().float()
+        x = torch.randn(n, cin, h, w, generator=g)
+        want = F.conv2d(x, wt, None, 1, 1)
+        wp = ops.pack_weight_pair(wt).float()
+        k_in, n_out = cin, cout
+    else:
+        # forward layer cout_f -> cin_f = (cin -> cout here read as dy channels -> dx channels)
+        wf = torch.randn(cin, cout, 3, 3, generator=g).bfloat16().float()          # forward weight [dy channels][dx channels]
+        x = torch.randn(n, cin, h, w, generator=g)                                  # dy
+        xin = torch.zeros(n, cout, h, w, requires_grad=True)
+        F.conv2d(xin, wf, None, 1, 1).backward(x)
+        want = xin.grad
+        w_t = wf.permute(1, 2, 3, 0).reshape(cout, 9 * cin).bfloat16()              # the transposed pack [dx ch][ky][kx][dy ch]
+        wp = ops.pack_weight_pair(w_t, flip=True).float()
+        k_in, n_out = cin, cout
+    shifts, first = ops.pair_weight_shifts(k_in)
+    assert wp.shape == (2 * n_out, 3 * shifts * k_in)
+    xp = F.pad(x, (8, 8, 1, 1))                                                      # zero padding = TMA's out-of-image fill
+    cols = []
+    for ky in range(3):
+        for s in range(shifts):
+            dx = first + s
+            cols.append(xp[:, :, ky:ky + h, 8 + dx:8 + dx + w:2])                    # pixel 2j + dx of row r + ky - 1
+    a = torch.stack(cols, 1).reshape(n, 3 * shifts * k_in, h, w // 2)               # K index = (ky*S + s)*cin + ci
+    out = torch.einsum("ok,nkhw->nohw", wp, a).reshape(n, 2, n_out, h, w // 2)       # N index = px*cout + co
+    got = torch.stack([out[:, 0], out[:, 1]], -1).reshape(n, n_out, h, w)            # interleave the two pixels of a pair
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)
+    buf = ops.pack_weight_pair(wt if not flip else w_t, flip=flip)
+    assert torch.equal(ops.pack_weight_pair(wt if not flip else w_t, out=buf.clone(), flip=flip), buf)
+
+
+def test_mdy_encoder_groupnorm_fold_constants_reproduce_the_oracle():
+    """MDyEncoder._folded (W' = diag(a) W diag(gamma), row sums, b) with the per-image (rstd, mean*rstd) epilogue
+    y = act(acc*rstd + b - mean*rstd*rowsum(W')) is algebraically GroupNorm -> 1x1 conv (-> BatchNorm) -> activation
+    (RTMUAVDet.py:163-177): evaluate the folded form in fp32 torch and compare with the oracle's operator form."""
+    import torch.nn.functional as F
+    from oracle import oracle as O
+    from multimodal_uav_det_b200.engine import Executor
+    from multimodal_uav_det_b200.model.RTMUAVDet import MDyEncoder
+    torch.manual_seed(11)
+    enc = MDyEncoder(96, 64).eval()
+    g = torch.Generator().manual_seed(12)
+    with torch.no_grad():
+        for m in enc.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1, generator=g); m.running_var.uniform_(0.7, 1.3, generator=g)
+                m.weight.uniform_(0.7, 1.3, generator=g); m.bias.normal_(0, 0.1, generator=g)
+            if isinstance(m, torch.nn.GroupNorm):
+                m.weight.uniform_(0.5, 1.5, generator=g); m.bias.normal_(0, 0.2, generator=g)
+    sd = {"e." + k: v for k, v in enc.state_dict().items()}
+    x = torch.randn(2, 96, 6, 7, generator=g) * torch.tensor([0.5, 2.0]).view(2, 1, 1, 1) + torch.tensor([1.0, -0.5]).view(2, 1, 1, 1)
+    k = enc._folded(Executor())
+    t = enc.third
+
+    def fold(v, wp, wg, b, eps, act):
+        mu = v.mean(dim=(1, 2, 3), keepdim=True)
+        rstd = (v.var(dim=(1, 2, 3), unbiased=False, keepdim=True) + eps).rsqrt()
+        acc = F.conv2d(v, wp.float()[:, :, None, None])
+        return act(acc * rstd + b.view(1, -1, 1, 1) - mu * rstd * wg.view(1, -1, 1, 1))
+
+    with torch.no_grad():
+        base = fold(x, k["wp_in"], k["wg_in"], k["b_in"], enc.group_norm_in.eps, F.relu)
+        y = F.group_norm(x, 1, sd["e.group_norm_in.weight"], sd["e.group_norm_in.bias"], 1e-5)
+        want_base = torch.cat([O.rtm_conv_module(y, sd, f"e.mdy_conv_{n}.base_conv", 1, 0, "relu", False, 1e-5, 0.1)
+                               for n in ("1x1", "3x3", "5x5")], 1)
+        assert base.shape == (2, 3 * t, 6, 7)
+        torch.testing.assert_close(base, want_base, rtol=2e-2, atol=2e-2)            # W' is rounded to bf16
+        v = torch.randn(2, 96, 6, 7, generator=g) + 0.3
+        z = fold(v, k["wp_out"], k["wg_out"], k["b_out"], enc.group_norm_out.eps, F.gelu)
+        want_z = F.gelu(F.conv2d(F.group_norm(v, 1, sd["e.group_norm_out.weight"], sd["e.group_norm_out.bias"], 1e-5),
+                                 sd["e.channel_mlp.0.weight"], sd["e.channel_mlp.0.bias"]))
+        torch.testing.assert_close(z, want_z, rtol=2e-2, atol=2e-2)
+    assert enc._folded(Executor()) is k                                              # cached until a parameter changes
+    with torch.no_grad():
+        enc.group_norm_out.weight.mul_(1.5)
+    assert enc._folded(Executor()) is not k
