@@ -118,8 +118,13 @@ __device__ __forceinline__ void affine_act(float (&v)[32], const float* scale, i
       v[i] += s.x; v[i + 1] += s.y; v[i + 2] += s.z; v[i + 3] += s.w;
     }
   }
+  if (ACT == UAVDET_ACT_GELU) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = act_fwd<ACT>(v[i]);
+    for (int i = 0; i < 32; i += 2) gelu_pair(v[i], v[i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = act_fwd<ACT>(v[i]);
+  }
   if (have_res) {
 #pragma unroll
     for (int i = 0; i < 32; i += 8) {
