@@ -277,6 +277,7 @@ class RTMUAVDet(LightningModule):
         self.stem_on_tensor_cores = True      # False: the direct CUDA-core 5x5 kernel (fp32 input, no bf16 rounding of x)
         self._stem_w3 = None
         self._up_pair = None
+        self._stem_w3_pair = None
 
     def _stem_s2d_weight(self, w: torch.Tensor) -> torch.Tensor:
         from ..engine import param_epoch
@@ -284,6 +285,11 @@ class RTMUAVDet(LightningModule):
         if self._stem_w3 is None or self._stem_w3[0] != ver:
             self._stem_w3 = (ver, ops.pack_weight(ops.s2d_stem_weight(w.detach())))
         return self._stem_w3[1]
+
+    def _stem_pair_weight(self, w3: torch.Tensor) -> torch.Tensor:
+        if self._stem_w3_pair is None or self._stem_w3_pair[0] is not w3:
+            self._stem_w3_pair = (w3, ops.pack_weight_pair(w3))
+        return self._stem_w3_pair[1]
 
     @torch.no_grad()
     def forward(self, x) -> List[DetectionResults]:
@@ -304,7 +310,12 @@ class RTMUAVDet(LightningModule):
             # batch 128.  The GEMM computes a 320th row / column the 5x5 stem does not have; they are zeroed, which is
             # what the zero-padded (even-sized) stem output holds there.
             w3 = self._stem_s2d_weight(stem.conv[0].weight)
-            h = ops.conv_fwd(ops.stem_s2d_pack(x), w3, 32, 3, 1, 1, act="silu", scale=scale, shift=shift)
+            if _NO_PAIR_CONV:
+                h = ops.conv_fwd(ops.stem_s2d_pack(x), w3, 32, 3, 1, 1, act="silu", scale=scale, shift=shift)
+            else:
+                # 32 -> 32 channels: as a pixel-pair GEMM (N = 64, whole pixel pairs as K = 64 k-blocks) the tensor core
+                # issues half the instructions at twice the rate of the 64-byte-row form
+                h = ops.conv3x3_pair_fwd(ops.stem_s2d_pack(x), self._stem_pair_weight(w3), 32, act="silu", scale=scale, shift=shift)
             ho = (x.shape[2] + 2 - 5) // 2 + 1
             wo = (x.shape[3] + 2 - 5) // 2 + 1
             if ho < h.shape[1]:
