@@ -97,12 +97,26 @@ __device__ __forceinline__ float4 load_epc4(const float* p, bool staged) {
 template <int ACT, bool kFold = false>
 __device__ __forceinline__ void affine_act(float (&v)[32], const float* scale, int cg, const float* shift,
                                            const uint4 (&res)[4], bool have_res, bool staged, float rs = 1.f) {
+  // The element-wise math runs on packed fp32x2 instructions (fma.rn.f32x2 & co., two columns per instruction, each half
+  // rounded like the scalar form): these epilogues are bound by instruction issue on their 8 warps.
+  auto fma2 = [](float& a, float& b, float2 m, float2 c) {
+    const float2 r = __ffma2_rn(make_float2(a, b), m, c);
+    a = r.x; b = r.y;
+  };
   if (kFold) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 t = load_epc4(shift + cg + i, true);
-      v[i] = fmaf(v[i], rs, t.x); v[i + 1] = fmaf(v[i + 1], rs, t.y);
-      v[i + 2] = fmaf(v[i + 2], rs, t.z); v[i + 3] = fmaf(v[i + 3], rs, t.w);
+      fma2(v[i], v[i + 1], make_float2(rs, rs), make_float2(t.x, t.y));
+      fma2(v[i + 2], v[i + 3], make_float2(rs, rs), make_float2(t.z, t.w));
+    }
+  } else if (scale && shift) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 s = load_epc4(scale + cg + i, staged);
+      const float4 t = load_epc4(shift + cg + i, staged);
+      fma2(v[i], v[i + 1], make_float2(s.x, s.y), make_float2(t.x, t.y));
+      fma2(v[i + 2], v[i + 3], make_float2(s.z, s.w), make_float2(t.z, t.w));
     }
   } else if (scale) {
 #pragma unroll
@@ -110,17 +124,21 @@ __device__ __forceinline__ void affine_act(float (&v)[32], const float* scale, i
       const float4 s = load_epc4(scale + cg + i, staged);
       v[i] *= s.x; v[i + 1] *= s.y; v[i + 2] *= s.z; v[i + 3] *= s.w;
     }
-  }
-  if (!kFold && shift) {
+  } else if (shift) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 s = load_epc4(shift + cg + i, staged);
-      v[i] += s.x; v[i + 1] += s.y; v[i + 2] += s.z; v[i + 3] += s.w;
+      const float4 t = load_epc4(shift + cg + i, staged);
+      const float2 a = __fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(t.x, t.y));
+      const float2 b = __fadd2_rn(make_float2(v[i + 2], v[i + 3]), make_float2(t.z, t.w));
+      v[i] = a.x; v[i + 1] = a.y; v[i + 2] = b.x; v[i + 3] = b.y;
     }
   }
   if (ACT == UAVDET_ACT_GELU) {
 #pragma unroll
     for (int i = 0; i < 32; i += 2) gelu_pair(v[i], v[i + 1]);
+  } else if (ACT == UAVDET_ACT_SILU) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) silu_pair(v[i], v[i + 1]);
   } else {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = act_fwd<ACT>(v[i]);
@@ -129,10 +147,12 @@ __device__ __forceinline__ void affine_act(float (&v)[32], const float* scale, i
 #pragma unroll
     for (int i = 0; i < 32; i += 8) {
       const uint4 rr = res[i >> 3];
-      v[i] += bf16_lo(rr.x); v[i + 1] += bf16_hi(rr.x);
-      v[i + 2] += bf16_lo(rr.y); v[i + 3] += bf16_hi(rr.y);
-      v[i + 4] += bf16_lo(rr.z); v[i + 5] += bf16_hi(rr.z);
-      v[i + 6] += bf16_lo(rr.w); v[i + 7] += bf16_hi(rr.w);
+      const uint32_t w4[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = __fadd2_rn(make_float2(v[i + 2 * j], v[i + 2 * j + 1]), make_float2(bf16_lo(w4[j]), bf16_hi(w4[j])));
+        v[i + 2 * j] = a.x; v[i + 2 * j + 1] = a.y;
+      }
     }
   }
 }
