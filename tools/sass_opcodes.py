@@ -7,7 +7,7 @@ import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "multimodal_uav_det_b200", "build")
 KEY = ("UTCHMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "UTMAPF", "SYNCS", "UCGABAR", "UTCATOMSWS", "HMMA", "REDG", "ATOMG",
-       "LDG", "STG", "LDS", "STS", "FFMA", "BAR")
+       "LDG", "STG", "LDS", "STS", "FFMA", "FFMA2", "FMUL2", "FADD2", "BAR")
 
 
 def main():
