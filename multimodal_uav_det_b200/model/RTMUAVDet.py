@@ -310,7 +310,7 @@ class RTMUAVDet(LightningModule):
             # batch 128.  The GEMM computes a 320th row / column the 5x5 stem does not have; they are zeroed, which is
             # what the zero-padded (even-sized) stem output holds there.
             w3 = self._stem_s2d_weight(stem.conv[0].weight)
-            if _NO_PAIR_CONV:
+            if _NO_PAIR_CONV or (x.shape[3] // 2) % 2:        # the pair GEMM needs an even width of the space-to-depth map
                 h = ops.conv_fwd(ops.stem_s2d_pack(x), w3, 32, 3, 1, 1, act="silu", scale=scale, shift=shift)
             else:
                 # 32 -> 32 channels: as a pixel-pair GEMM (N = 64, whole pixel pairs as K = 64 k-blocks) the tensor core
